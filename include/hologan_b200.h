@@ -1,0 +1,106 @@
+/* hologan_b200.h -- C ABI of the B200-native HoloGAN generator hot path.
+ *
+ * The reference (ebartrum/lightning_gan_zoo @ 33c7f1b) is 100 % Python on stock torch ops and has no
+ * FFI of its own; each entry point below names the reference lines it replaces
+ * (paths relative to the reference root).  INTEGRATION.md shows the ctypes binding a maintainer of
+ * the reference would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the parameter name ends in `_host`;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - functions only enqueue work: no allocation, no synchronisation, no global mutable state,
+ *     safe to call from several host threads and inside CUDA-graph capture;
+ *   - return 0 on success, a negative hg_status_t otherwise; hg_last_error() returns a
+ *     thread-local message for the last failure on the calling thread.
+ */
+#ifndef HOLOGAN_B200_H
+#define HOLOGAN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HG_ABI_VERSION 1
+
+typedef enum {
+    HG_OK = 0,
+    HG_ERR_INVALID_ARG = -1,   /* null pointer, non-positive dim, unknown enum value     */
+    HG_ERR_UNSUPPORTED = -2,   /* shape / dtype / layout combination has no kernel        */
+    HG_ERR_LAUNCH = -3,        /* CUDA reported an error at launch                        */
+    HG_ERR_NO_DEVICE = -4      /* no sm_100 device / driver entry point unavailable       */
+} hg_status_t;
+
+typedef enum { HG_F32 = 0, HG_BF16 = 1 } hg_dtype_t;
+
+/* Feature-volume layouts.  NCDHW is the reference's (torch) layout. */
+typedef enum {
+    HG_NCDHW = 0,   /* (B, C, S, S, S)                                                     */
+    HG_NDHWC = 1,   /* (B, S, S, S, C)   channels-last                                     */
+    HG_PROJ = 2     /* (B, S, S, C*S): [b, z, x, c*S + (S-1-y)] -- the depth-into-channels  *
+                     * fold of hologan_generator.py:130-133, stored channels-last (NHWC)    */
+} hg_layout_t;
+
+/* How samples whose source coordinate leaves [0, S-1) are produced. */
+typedef enum {
+    HG_BORDER_REFERENCE = 0,  /* reference arithmetic: clamped corners, weights from the clamped *
+                               * corner vs the unclamped coordinate (hologan_generator.py:256-318) *
+                               * -> bit-identical to the reference CPU path in fp32                */
+    HG_BORDER_ZERO = 1        /* write exact 0 where the reference's terms cancel to ~1e-7         */
+} hg_border_t;
+
+int hg_abi_version(void);
+const char *hg_last_error(void);
+
+/* ---- a6 + a7 (+ a8): rigid-body rotate + trilinear resample ------------------------------------
+ * Replaces Generator.apply_transformation / interpolation / meshgrid
+ * (core/models/hologan_generator.py:198-331) and, with out_layout == HG_PROJ, the projection
+ * reshape of :130-133.
+ *   vol      (B,C,S,S,S) in `in_layout`, element type `dtype`
+ *   a_inv    (B,4,4) fp32 row-major: inverse(Tn @ M @ Tc) of :219-221 (rows 0..2 are used)
+ *   out      same element type, `out_layout`, S' == S
+ *   coords_dbg (optional, may be NULL) (3,B,S^3) fp32: x,y,z source coordinates  ("grid coordinates")
+ *   idx_dbg    (optional, may be NULL) (8,B,S^3) int32: flat corner indices a..h incl. the batch
+ *              base b*S^3, i.e. idx_a..idx_h of :278-287                        ("sampling indices")
+ */
+int hg_rotate_fwd(const void *vol, const float *a_inv, void *out, float *coords_dbg, int32_t *idx_dbg,
+                  int batch, int channels, int size, int in_layout, int out_layout, int dtype,
+                  int border, void *stream);
+
+/* Adjoint of hg_rotate_fwd w.r.t. `vol` (what autograd derives from :292-320).  grad_out is in the
+ * forward's out_layout, grad_vol in the forward's in_layout; grad_vol is fully overwritten.
+ * Deterministic, no global atomics. */
+int hg_rotate_bwd(const void *grad_out, const float *a_inv, void *grad_vol, int batch, int channels,
+                  int size, int in_layout, int out_layout, int dtype, int border, void *stream);
+
+/* ---- a1 + a3 (+ activation): adaptive instance norm ---------------------------------------------
+ * Replaces AdaIn (core/models/hologan_generator.py:333-345) fused with the ReLU that follows every
+ * call site (:41, :124):  y = act(scale * (x - mean) * rsqrt(var_unbiased + eps) + bias),
+ * act(v) = v > 0 ? v : neg_slope * v   (neg_slope = 0 -> ReLU, 1 -> identity / plain AdaIn).
+ *   x        (B, C, N) contiguous in N (torch NC* layout); x_batch_stride is the element stride
+ *            between samples: C*N normally, 0 for the learned constant of :49-51,121 (never
+ *            materialised B times)
+ *   scale, bias (B, C) fp32 with row stride `sb_stride` elements (lets both halves of the
+ *            ZMapping output, :18, be used in place)
+ *   y        (B, C, N) same dtype as x
+ *   save_mean, save_rstd (B, C) fp32, written for the backward
+ */
+int hg_adain_act_fwd(const void *x, const float *scale, const float *bias, void *y, float *save_mean,
+                     float *save_rstd, int batch, int channels, int n, long long x_batch_stride,
+                     int sb_stride, float eps, float neg_slope, int dtype, void *stream);
+
+/* Backward of the above.  dy is the gradient w.r.t. the activated output.
+ *   dx       (B, C, N), or (C, N) when x_batch_stride == 0 (summed over the batch)
+ *   dscale, dbias (B, C) fp32 with row stride `dsb_stride`
+ */
+int hg_adain_act_bwd(const void *x, const void *dy, const float *scale, const float *bias,
+                     const float *save_mean, const float *save_rstd, void *dx, float *dscale, float *dbias,
+                     int batch, int channels, int n, long long x_batch_stride, int sb_stride, int dsb_stride,
+                     float neg_slope, int dtype, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HOLOGAN_B200_H */

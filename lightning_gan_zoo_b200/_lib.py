@@ -1,0 +1,72 @@
+"""ctypes binding of libhologan_b200.so (the C ABI declared in include/hologan_b200.h).
+
+There is NO fallback: if the library is missing or a call fails, an exception is raised.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+
+_PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG_DIR, "libhologan_b200.so")
+
+HG_F32, HG_BF16 = 0, 1
+HG_NCDHW, HG_NDHWC, HG_PROJ = 0, 1, 2
+HG_BORDER_REFERENCE, HG_BORDER_ZERO = 0, 1
+
+_c_int, _c_void_p, _c_float, _c_ll = ctypes.c_int, ctypes.c_void_p, ctypes.c_float, ctypes.c_longlong
+
+# name -> argtypes; every function returns int (hg_status_t) unless listed in _RESTYPES
+SIGNATURES = {
+    "hg_abi_version": [],
+    "hg_last_error": [],
+    "hg_rotate_fwd": [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int,
+                      _c_int, _c_int, _c_void_p],
+    "hg_rotate_bwd": [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
+                      _c_void_p],
+    "hg_adain_act_fwd": [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int,
+                         _c_ll, _c_int, _c_float, _c_float, _c_int, _c_void_p],
+    "hg_adain_act_bwd": [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
+                         _c_void_p, _c_int, _c_int, _c_int, _c_ll, _c_int, _c_int, _c_float, _c_int, _c_void_p],
+}
+_RESTYPES = {"hg_last_error": ctypes.c_char_p}
+
+_lib = None
+_lock = threading.Lock()
+
+
+class HologanB200Error(RuntimeError):
+    pass
+
+
+def load() -> ctypes.CDLL:
+    """Load the shared library (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise HologanB200Error(
+                f"{LIB_PATH} not found: build it with `python -m lightning_gan_zoo_b200.build` "
+                "(there is no CPU / PyTorch fallback for the HoloGAN hot path)")
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, argtypes in SIGNATURES.items():
+            fn = getattr(lib, name)       # AttributeError if the .so is stale
+            fn.argtypes = argtypes
+            fn.restype = _RESTYPES.get(name, _c_int)
+        if lib.hg_abi_version() != 1:
+            raise HologanB200Error("libhologan_b200.so ABI version mismatch; rebuild")
+        _lib = lib
+    return _lib
+
+
+def call(name: str, *args) -> None:
+    """Invoke an ABI function and raise HologanB200Error with hg_last_error() on failure."""
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        msg = lib.hg_last_error()
+        raise HologanB200Error(f"{name} failed ({rc}): {msg.decode() if msg else ''}")

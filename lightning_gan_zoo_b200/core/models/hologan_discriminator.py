@@ -1,0 +1,66 @@
+"""HoloGAN discriminator -- interface mirror of the reference's
+`core.models.hologan_discriminator` (core/models/hologan_discriminator.py:7-78).
+
+The discriminator is in the training-step metric but NOT in the custom-kernel list of the hot
+path: it runs on stock PyTorch modules (cuDNN) for now and keeps the
+reference's `state_dict` keys, including the `conv2d_spec_norm` alias of each spectrally
+normalised convolution.  `img_size=128` uses the patched head sizes.
+"""
+from __future__ import annotations
+
+import torch
+from torch import nn
+import torch.nn.functional as F
+
+
+def truncated_normal_initializer(weight, mean=0, std=0.02):
+    """Truncated N(mean, std) at +-2 sigma by picking the first in-range of 4 draws (:72-78)."""
+    with torch.no_grad():
+        draws = torch.randn(tuple(weight.shape) + (4,), dtype=weight.dtype, device=weight.device)
+        in_range = (draws > -2) & (draws < 2)
+        first = in_range.max(dim=-1, keepdim=True)[1]
+        weight.copy_(draws.gather(-1, first).squeeze(-1) * std + mean)
+
+
+class BasicBlock(nn.Module):
+    """spectral-norm Conv5x5 s2 -> InstanceNorm2d -> LeakyReLU(0.2).  Reference :7-23."""
+
+    def __init__(self, in_planes, out_planes):
+        super().__init__()
+        self.conv2d = nn.Conv2d(in_planes, out_planes, kernel_size=5, stride=2, padding=2)
+        truncated_normal_initializer(self.conv2d.weight)
+        nn.init.zeros_(self.conv2d.bias)
+        # same module registered twice, like the reference (keys conv2d.* and conv2d_spec_norm.*)
+        self.conv2d_spec_norm = nn.utils.spectral_norm(self.conv2d)
+        self.instance_norm = nn.InstanceNorm2d(out_planes)
+
+    def forward(self, x):
+        return F.leaky_relu(self.instance_norm(self.conv2d_spec_norm(x)), 0.2)
+
+
+class Discriminator(nn.Module):
+    def __init__(self, in_planes, out_planes, z_planes, img_size=64):
+        super().__init__()
+        self.conv2d = nn.Conv2d(in_planes, out_planes, kernel_size=5, stride=2, padding=2)
+        truncated_normal_initializer(self.conv2d.weight)
+        nn.init.zeros_(self.conv2d.bias)
+        self.blocks = nn.Sequential(BasicBlock(out_planes, out_planes * 2),
+                                    BasicBlock(out_planes * 2, out_planes * 4),
+                                    BasicBlock(out_planes * 4, out_planes * 8))
+        features = out_planes * 8 * (img_size // 16) ** 2       # 8192 at 64x64 (reference :41)
+        self.linear1 = nn.Linear(features, 1)
+        truncated_normal_initializer(self.linear1.weight)
+        nn.init.zeros_(self.linear1.bias)
+        # linear2 / linear3 keep torch's default weight init, as in the reference (:45-50 re-initialise
+        # linear1 by mistake); only their biases are zeroed
+        self.linear2 = nn.Linear(features, 128)
+        nn.init.zeros_(self.linear2.bias)
+        self.linear3 = nn.Linear(128, z_planes)
+        nn.init.zeros_(self.linear3.bias)
+
+    def forward(self, x):
+        h = F.leaky_relu(self.conv2d(x), 0.2)
+        h = self.blocks(h).flatten(1)
+        logits = self.linear1(h)
+        z_prediction = torch.tanh(self.linear3(F.leaky_relu(self.linear2(h), 0.2)))
+        return logits, z_prediction

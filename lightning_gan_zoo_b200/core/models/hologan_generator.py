@@ -1,0 +1,146 @@
+"""HoloGAN generator on the B200 path -- drop-in for the reference's
+`core.models.hologan_generator` (ebartrum/lightning_gan_zoo @ 33c7f1b).
+
+Same public names, constructor / forward signatures and `state_dict` keys as the reference
+(core/models/hologan_generator.py:7-345), so Hydra's
+`_target_: core.models.hologan_generator.Generator` (conf/expt/hologan.yaml:29-49) and reference
+checkpoints keep working (see `lightning_gan_zoo_b200.compat.install`).  The arithmetic of the hot
+path -- AdaIN(+ReLU), the learned-constant broadcast, the rigid-body rotate/resample and its
+backward -- runs in `libhologan_b200.so` through `lightning_gan_zoo_b200.ops`.
+
+Deviations from the reference, all deliberate:
+  * `sample_view` uses np.float64 (the reference's `np.float` crashes on numpy >= 1.24, R7);
+  * `img_size == 128` builds the patched, working head (`ConvTranspose2d(k4, s2, p1)`, R4);
+  * no gradient is propagated into the view parameters (nobody consumes it).
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+from torch import nn
+import torch.nn.functional as F
+
+from ... import ops
+
+
+class ZMapping(nn.Module):
+    """z -> (scale, bias) style vectors.  Reference :7-18."""
+
+    def __init__(self, z_dimension, output_channel):
+        super().__init__()
+        self.output_channel = output_channel
+        self.linear1 = nn.Linear(z_dimension, 2 * output_channel)
+        nn.init.normal_(self.linear1.weight, std=0.02)
+        nn.init.zeros_(self.linear1.bias)
+
+    def forward(self, x):
+        style = F.relu(self.linear1(x))
+        c = self.output_channel
+        return style[:, :c], style[:, c:]
+
+
+def AdaIn(features, scale, bias):
+    """Plain adaptive instance norm (unbiased variance, eps 1e-8).  Reference :333-345."""
+    return ops.adain_act(features, scale.float(), bias.float(), neg_slope=1.0)
+
+
+class BasicBlock(nn.Module):
+    """Transposed conv (x2 upsampling) -> AdaIN -> ReLU.  Reference :20-42."""
+
+    def __init__(self, z_planes, in_planes, out_planes, transpose_dim):
+        super().__init__()
+        if transpose_dim == 2:
+            self.convTranspose = nn.ConvTranspose2d(in_planes, out_planes, kernel_size=4, stride=2, padding=1)
+        elif transpose_dim == 3:
+            self.convTranspose = nn.ConvTranspose3d(in_planes, out_planes, kernel_size=3, stride=2, padding=1,
+                                                    output_padding=1)
+        else:
+            raise ValueError("transpose_dim must be 2 or 3")
+        nn.init.normal_(self.convTranspose.weight, std=0.02)
+        nn.init.zeros_(self.convTranspose.bias)
+        self.zMapping = ZMapping(z_planes, out_planes)
+
+    def forward(self, h, z):
+        h = self.convTranspose(h)
+        scale, bias = self.zMapping(z)
+        return ops.adain_act(h, scale, bias, neg_slope=0.0)      # AdaIN + ReLU in one pass
+
+
+class Generator(nn.Module):
+    def __init__(self, in_planes, out_planes, z_planes, view_args, img_size, view_planes=6, gpu=True):
+        super().__init__()
+        if img_size not in (64, 128):
+            raise ValueError("img_size must be 64 or 128")
+        self.device = torch.device("cuda" if gpu else "cpu")
+        self.view_args = view_args
+        self.img_size = img_size
+        # border handling of the resampler: reference arithmetic (bit-exact) by default
+        self.rotate_border = ops.HG_BORDER_REFERENCE
+
+        self.x = nn.Parameter(((torch.randn(1, in_planes * 8, 4, 4, 4) - 0.5) / 0.5).to(self.device))
+        self.zMapping = ZMapping(z_planes, in_planes * 8)
+        self.block1 = BasicBlock(z_planes, in_planes * 8, in_planes * 2, transpose_dim=3)
+        self.block2 = BasicBlock(z_planes, in_planes * 2, in_planes, transpose_dim=3)
+
+        self.convTranspose2d1 = nn.ConvTranspose2d(in_planes * 16, in_planes * 16, kernel_size=1)
+        nn.init.normal_(self.convTranspose2d1.weight, std=0.02)
+        nn.init.zeros_(self.convTranspose2d1.bias)
+
+        self.block3 = BasicBlock(z_planes, in_planes * 16, in_planes * 4, transpose_dim=2)
+        self.block4 = BasicBlock(z_planes, in_planes * 4, in_planes, transpose_dim=2)
+
+        if img_size == 64:
+            self.final_layer = nn.Conv2d(in_planes, out_planes, kernel_size=3, padding=1)
+        else:   # patched 128 head: the reference's lacks stride=2 and yields 65x65
+            self.final_layer = nn.ConvTranspose2d(in_planes, out_planes, kernel_size=4, stride=2, padding=1)
+        nn.init.normal_(self.final_layer.weight, std=0.02)
+        nn.init.zeros_(self.final_layer.bias)
+
+    # ---- views ------------------------------------------------------------------------------
+    def sample_view(self, batch_size):
+        """Random (azimuth, elevation, scale, tx, ty, tz) rows; same numpy RNG call order as the
+        reference (:80-114): azimuth ints, elevation ints, one scale, then the three shifts."""
+        a = self.view_args
+        view = np.zeros((batch_size, 6), dtype=np.float64)
+        view[:, 0] = np.random.randint(a.azimuth_low, a.azimuth_high, batch_size).astype(np.float64) * math.pi / 180.0
+        if a.elevation_low < a.elevation_high:
+            view[:, 1] = np.random.randint(a.elevation_low, a.elevation_high, batch_size).astype(np.float64) \
+                * math.pi / 180.0
+        view[:, 2] = float(np.random.uniform(a.scale_low, a.scale_high))
+        for col, (lo, hi) in enumerate(((a.transX_low, a.transX_high), (a.transY_low, a.transY_high),
+                                        (a.transZ_low, a.transZ_high)), start=3):
+            view[:, col] = lo + np.random.random(batch_size) * (hi - lo)
+        return view
+
+    def _affine(self, view_params, size, new_size, device):
+        if size != new_size:
+            raise NotImplementedError("resampling onto a grid of a different size is not on the hot path")
+        return ops.view_to_affine(view_params, size, new_size).to(device, non_blocking=True)
+
+    def transformation3d(self, voxel_array, view_params, size=16, new_size=16):
+        """Rigid-body transform + trilinear resample of (B,C,S,S,S).  Reference :145-243."""
+        a_inv = self._affine(view_params, size, new_size, voxel_array.device)
+        return ops.rotate_resample(voxel_array.contiguous(), a_inv, self.rotate_border)
+
+    # ---- forward ----------------------------------------------------------------------------
+    def forward(self, z, view_in=None):
+        batch_size = z.shape[0]
+        if view_in is None:
+            view_in = self.sample_view(batch_size)
+
+        s0, b0 = self.zMapping(z)
+        h0 = ops.adain_act(self.x, s0, b0, neg_slope=0.0)            # constant never repeated B times
+        h1 = self.block1(h0, z)
+        h2 = self.block2(h1, z)
+
+        rot = self.transformation3d(h2, view_in, h2.shape[2], h2.shape[2])
+        # fold depth into channels: out[b, c*S + j, r, col] = rot[b, c, r, S-1-j, col]  (:130-133)
+        s = rot.shape[2]
+        h2_2d = rot.permute(0, 1, 3, 2, 4).flip(2).reshape(batch_size, -1, s, s)
+
+        h3 = F.relu(self.convTranspose2d1(h2_2d))
+        h4 = self.block3(h3, z)
+        h5 = self.block4(h4, z)
+        return torch.tanh(self.final_layer(h5))

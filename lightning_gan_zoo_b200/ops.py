@@ -1,0 +1,223 @@
+"""Torch-facing operators of the HoloGAN hot path.
+
+Each operator is a thin `torch.autograd.Function` over the C ABI of `include/hologan_b200.h`
+(raw device pointers + the current CUDA stream, through ctypes).  PyTorch only provides device
+memory, streams and autograd bookkeeping here; all arithmetic on the path runs in
+`libhologan_b200.so`.  There is no CPU implementation: CPU tensors raise.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import HG_BF16, HG_BORDER_REFERENCE, HG_BORDER_ZERO, HG_F32, HG_NCDHW, HG_NDHWC, HG_PROJ  # noqa: F401
+
+Tensor = torch.Tensor
+
+
+def _dtype_code(t: Tensor) -> int:
+    if t.dtype == torch.float32:
+        return HG_F32
+    if t.dtype == torch.bfloat16:
+        return HG_BF16
+    raise TypeError(f"hologan_b200 ops support float32 and bfloat16 tensors, got {t.dtype}")
+
+
+def _require_cuda(*tensors: Tensor) -> None:
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("hologan_b200 ops run on CUDA tensors only (no CPU fallback)")
+
+
+def _ptr(t: Optional[Tensor]):
+    return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _stream() -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+# ------------------------------------------------------------------------------------------------
+# a5 + a6 (host part): view parameters -> inverse sampling transform
+# ------------------------------------------------------------------------------------------------
+
+def _homogeneous(batch: int) -> Tensor:
+    return torch.eye(4, dtype=torch.float32).unsqueeze(0).repeat(batch, 1, 1)
+
+
+def view_to_affine(view, size: int = 16, new_size: int = 16) -> Tensor:
+    """(B,6) view = (azimuth, elevation, scale, tx, ty, tz) -> (B,4,4) fp32 CPU tensor
+    A = inverse(Tn @ (T @ S @ (Rz @ Ry)) @ Tc).
+
+    Mirrors `Generator.transformation3d` / `apply_transformation`
+    (reference core/models/hologan_generator.py:148-221).  Deliberately computed on the HOST with
+    torch's own fp32 CPU ops in the reference's association order: the sampling coordinates must be
+    bit-identical to the reference CPU path, and its cos/sin (SLEEF) and inverse (LAPACK) are not
+    reproducible by an independent implementation.  It is 64 bytes per sample.
+    """
+    if isinstance(view, torch.Tensor):
+        v = view.detach().to("cpu")
+    else:
+        v = torch.as_tensor(np.asarray(view))
+    if v.dim() != 2 or v.shape[1] != 6:
+        raise ValueError(f"view must have shape (B, 6), got {tuple(v.shape)}")
+    v = v.float()
+    n = v.shape[0]
+    az, el, sc = v[:, 0], v[:, 1], v[:, 2]
+
+    r_az = _homogeneous(n)
+    r_az[:, 0, 0], r_az[:, 0, 1] = az.cos(), az.sin()
+    r_az[:, 1, 0], r_az[:, 1, 1] = -az.sin(), az.cos()
+    r_el = _homogeneous(n)
+    r_el[:, 0, 0], r_el[:, 0, 2] = el.cos(), el.sin()
+    r_el[:, 2, 0], r_el[:, 2, 2] = -el.sin(), el.cos()
+    rot = torch.matmul(r_az, r_el)
+
+    s_mat = _homogeneous(n)
+    s_mat[:, 0, 0] = s_mat[:, 1, 1] = s_mat[:, 2, 2] = sc
+    t_mat = _homogeneous(n)
+    t_mat[:, 0:3, 3] = v[:, 3:6]
+    m = torch.matmul(torch.matmul(t_mat, s_mat), rot)
+
+    to_origin = _homogeneous(n)
+    to_origin[:, 0:3, 3] = -size * 0.5
+    to_new = _homogeneous(n)
+    to_new[:, 0:3, 3] = new_size * 0.5
+    return torch.linalg.inv(torch.matmul(torch.matmul(to_new, m), to_origin)).contiguous()
+
+
+# ------------------------------------------------------------------------------------------------
+# a6 + a7: rotate + resample
+# ------------------------------------------------------------------------------------------------
+
+def rotate_fwd_raw(vol: Tensor, a_inv: Tensor, border: int = HG_BORDER_REFERENCE, in_layout: int = HG_NCDHW,
+                   out_layout: int = HG_NCDHW, debug: bool = False):
+    """Direct call of hg_rotate_fwd.  vol (B,C,S,S,S) [NCDHW] ; a_inv (B,4,4) fp32 on the same device."""
+    _require_cuda(vol, a_inv)
+    if not vol.is_contiguous():
+        raise ValueError("vol must be contiguous")
+    if a_inv.dtype != torch.float32 or tuple(a_inv.shape) != (vol.shape[0], 4, 4) or not a_inv.is_contiguous():
+        raise ValueError("a_inv must be a contiguous fp32 (B,4,4) tensor")
+    if in_layout == HG_NCDHW:
+        b, c, s = vol.shape[0], vol.shape[1], vol.shape[2]
+        cubic = vol.shape[2] == vol.shape[3] == vol.shape[4]
+    else:
+        b, s, c = vol.shape[0], vol.shape[1], vol.shape[4]
+        cubic = vol.shape[1] == vol.shape[2] == vol.shape[3]
+    if vol.dim() != 5 or not cubic:
+        raise ValueError(f"vol must be a cubic 5-D volume, got {tuple(vol.shape)}")
+    if out_layout == HG_NCDHW:
+        out = torch.empty((b, c, s, s, s), dtype=vol.dtype, device=vol.device)
+    elif out_layout == HG_NDHWC:
+        out = torch.empty((b, s, s, s, c), dtype=vol.dtype, device=vol.device)
+    else:
+        out = torch.empty((b, s, s, c * s), dtype=vol.dtype, device=vol.device)
+    coords = idx = None
+    if debug:
+        coords = torch.empty((3, b, s ** 3), dtype=torch.float32, device=vol.device)
+        idx = torch.empty((8, b, s ** 3), dtype=torch.int32, device=vol.device)
+    _lib.call("hg_rotate_fwd", _ptr(vol), _ptr(a_inv), _ptr(out), _ptr(coords), _ptr(idx), b, c, s, in_layout,
+              out_layout, _dtype_code(vol), border, _stream())
+    return (out, coords, idx) if debug else out
+
+
+def rotate_bwd_raw(grad_out: Tensor, a_inv: Tensor, channels: int, size: int, border: int = HG_BORDER_REFERENCE,
+                   in_layout: int = HG_NCDHW, out_layout: int = HG_NCDHW) -> Tensor:
+    _require_cuda(grad_out, a_inv)
+    grad_out = grad_out.contiguous()
+    b, c, s = grad_out.shape[0], channels, size
+    shape = (b, c, s, s, s) if in_layout == HG_NCDHW else (b, s, s, s, c)
+    grad_vol = torch.empty(shape, dtype=grad_out.dtype, device=grad_out.device)
+    _lib.call("hg_rotate_bwd", _ptr(grad_out), _ptr(a_inv), _ptr(grad_vol), b, c, s, in_layout, out_layout,
+              _dtype_code(grad_out), border, _stream())
+    return grad_vol
+
+
+class _RotateResample(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, vol, a_inv, border, in_layout, out_layout):
+        ctx.save_for_backward(a_inv)
+        ctx.meta = (border, in_layout, out_layout,
+                    vol.shape[1] if in_layout == HG_NCDHW else vol.shape[4], vol.shape[2])
+        return rotate_fwd_raw(vol, a_inv, border, in_layout, out_layout)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (a_inv,) = ctx.saved_tensors
+        border, in_layout, out_layout, c, s = ctx.meta
+        return rotate_bwd_raw(grad_out, a_inv, c, s, border, in_layout, out_layout), None, None, None, None
+
+
+def rotate_resample(vol: Tensor, a_inv: Tensor, border: int = HG_BORDER_REFERENCE, in_layout: int = HG_NCDHW,
+                    out_layout: int = HG_NCDHW) -> Tensor:
+    """Differentiable (w.r.t. `vol`) rigid-body rotate + trilinear resample."""
+    return _RotateResample.apply(vol, a_inv, border, in_layout, out_layout)
+
+
+# ------------------------------------------------------------------------------------------------
+# a1 + a3: AdaIN (+ activation)
+# ------------------------------------------------------------------------------------------------
+
+def _adain_dims(x: Tensor, scale: Tensor) -> Tuple[int, int, int, int]:
+    batch = scale.shape[0]
+    c = x.shape[1]
+    n = 1
+    for d in x.shape[2:]:
+        n *= d
+    if x.shape[0] == batch:
+        xbs = c * n
+    elif x.shape[0] == 1:
+        xbs = 0                                   # batch-shared constant (reference :121 `repeat`)
+    else:
+        raise ValueError("x batch must equal the style batch or be 1")
+    return batch, c, n, xbs
+
+
+def _style_stride(scale: Tensor, bias: Tensor) -> int:
+    """scale/bias may be the two halves of one (B, 2C) ZMapping output; both must share a row stride."""
+    if scale.dtype != torch.float32 or bias.dtype != torch.float32:
+        raise TypeError("scale / bias must be float32")
+    if scale.dim() != 2 or scale.shape != bias.shape or scale.stride(1) != 1 or bias.stride(1) != 1 \
+            or scale.stride(0) != bias.stride(0):
+        raise ValueError("scale / bias must be (B, C) row-major views with equal row stride")
+    return scale.stride(0)
+
+
+class _AdaInAct(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, scale, bias, neg_slope, eps):
+        _require_cuda(x, scale, bias)
+        if not x.is_contiguous():
+            x = x.contiguous()
+        b, c, n, xbs = _adain_dims(x, scale)
+        sbs = _style_stride(scale, bias)
+        y = torch.empty((b,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+        mean = torch.empty((b, c), dtype=torch.float32, device=x.device)
+        rstd = torch.empty((b, c), dtype=torch.float32, device=x.device)
+        _lib.call("hg_adain_act_fwd", _ptr(x), _ptr(scale), _ptr(bias), _ptr(y), _ptr(mean), _ptr(rstd), b, c, n, xbs,
+                  sbs, float(eps), float(neg_slope), _dtype_code(x), _stream())
+        ctx.save_for_backward(x, scale, bias, mean, rstd)
+        ctx.meta = (b, c, n, xbs, sbs, float(neg_slope))
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, scale, bias, mean, rstd = ctx.saved_tensors
+        b, c, n, xbs, sbs, neg_slope = ctx.meta
+        dy = dy.contiguous()
+        dx = torch.empty_like(x)
+        dsb = torch.empty((2, b, c), dtype=torch.float32, device=x.device)
+        _lib.call("hg_adain_act_bwd", _ptr(x), _ptr(dy), _ptr(scale), _ptr(bias), _ptr(mean), _ptr(rstd), _ptr(dx),
+                  _ptr(dsb[0]), _ptr(dsb[1]), b, c, n, xbs, sbs, c, neg_slope, _dtype_code(x), _stream())
+        return dx, dsb[0], dsb[1], None, None
+
+
+def adain_act(x: Tensor, scale: Tensor, bias: Tensor, neg_slope: float = 0.0, eps: float = 1e-8) -> Tensor:
+    """act(AdaIn(x, scale, bias)); `neg_slope=1.0` gives the plain AdaIn of the reference
+    (core/models/hologan_generator.py:333-345), `0.0` fuses the ReLU of :41 / :124.
+    x may have batch 1 (the learned constant): it is broadcast without being materialised."""
+    return _AdaInAct.apply(x, scale, bias, neg_slope, eps)

@@ -1,0 +1,139 @@
+"""Rotate-resample kernels vs the reference's golden outputs and the oracle (through the C ABI)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, np_ptr, rel_err
+from lightning_gan_zoo_b200 import ops
+from oracle import hologan_oracle as orc
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+@pytest.mark.parametrize("tag", ["s16", "s8"])
+def test_fwd_fp32_bit_exact_vs_reference(tag):
+    g = load_golden(f"rotate_{tag}.npz")
+    vol = torch.from_numpy(g["vol"]).to(DEV)
+    a = torch.from_numpy(g["a_inv"]).to(DEV)
+    out, coords, idx = ops.rotate_fwd_raw(vol, a, ops.HG_BORDER_REFERENCE, debug=True)
+    b, c, s = vol.shape[:3]
+    # "grid coordinates" and "sampling indices": bit-exact
+    assert np.array_equal(coords.cpu().numpy(), g["coords"])
+    cx, cy, cz = (torch.from_numpy(g["coords"][i]).reshape(-1) for i in range(3))
+    f = lambda t, d: (torch.floor(t).long() + d).clamp(0, s - 1)
+    base = (torch.arange(b) * s ** 3).repeat_interleave(s ** 3)
+    ref_idx = []
+    for dz, dy, dx in ((0, 0, 0), (0, 1, 0), (0, 0, 1), (0, 1, 1), (1, 0, 0), (1, 1, 0), (1, 0, 1), (1, 1, 1)):
+        ref_idx.append(base + f(cz, dz) * s * s + f(cy, dy) * s + f(cx, dx))      # reference :268-287
+    ref_idx = torch.stack(ref_idx).reshape(8, b, -1).to(torch.int32)
+    assert torch.equal(idx.cpu(), ref_idx)
+    # fp32 forward with the reference border arithmetic: bit-exact
+    assert np.array_equal(out.cpu().numpy(), g["out"])
+
+
+@pytest.mark.parametrize("tag", ["s16", "s8"])
+def test_fwd_zero_border_and_bf16(tag):
+    g = load_golden(f"rotate_{tag}.npz")
+    vol = torch.from_numpy(g["vol"]).to(DEV)
+    a = torch.from_numpy(g["a_inv"]).to(DEV)
+    out = ops.rotate_fwd_raw(vol, a, ops.HG_BORDER_ZERO)
+    assert rel_err(out, g["out"]) < 1e-5          # fp32 tolerance of north_star
+    inside = np.all((g["coords"] >= 0) & (g["coords"] < vol.shape[2] - 1), axis=0)       # (B, N)
+    mask = torch.from_numpy(inside).reshape(vol.shape[0], 1, *vol.shape[2:]).expand_as(out)
+    assert torch.equal(out.cpu()[~mask], torch.zeros_like(out.cpu()[~mask]))
+    assert np.array_equal(out.cpu()[mask].numpy(), torch.from_numpy(g["out"])[mask].numpy())
+    ob = ops.rotate_fwd_raw(vol.bfloat16(), a, ops.HG_BORDER_REFERENCE)
+    assert ob.dtype == torch.bfloat16
+    ref_b = orc.rotate_resample(vol.bfloat16().float().cpu(), a_inv=a.cpu())
+    assert rel_err(ob.float(), ref_b) < 2 ** -8   # one bf16 rounding of the output
+    assert rel_err(ob.float(), g["out"]) < 2e-2   # bf16 tolerance of north_star vs the fp32 reference
+
+
+@pytest.mark.parametrize("tag", ["s16", "s8"])
+@pytest.mark.parametrize("border", [ops.HG_BORDER_REFERENCE, ops.HG_BORDER_ZERO])
+def test_bwd_vs_reference(tag, border):
+    g = load_golden(f"rotate_{tag}.npz")
+    a = torch.from_numpy(g["a_inv"]).to(DEV)
+    vol = torch.from_numpy(g["vol"]).to(DEV).requires_grad_(True)
+    out = ops.rotate_resample(vol, a, border)
+    (out * torch.from_numpy(g["grad_out"]).to(DEV)).sum().backward()
+    assert rel_err(vol.grad, g["grad_vol"]) < 1e-5
+    gb = ops.rotate_bwd_raw(torch.from_numpy(g["grad_out"]).to(DEV).bfloat16(), a, vol.shape[1], vol.shape[2], border)
+    assert rel_err(gb.float(), g["grad_vol"]) < 2e-2
+
+
+def test_sweep_coords_hash():
+    g = load_golden("rotate_sweep100.npz")
+    a = torch.from_numpy(g["a_inv"]).to(DEV)
+    vol = torch.zeros(100, 1, 16, 16, 16, device=DEV)
+    _, coords, _ = ops.rotate_fwd_raw(vol, a, debug=True)
+    from conftest import sha16
+    assert sha16(coords.cpu()) == str(g["coords_sha"])
+    assert sha16(torch.floor(coords.cpu()).to(torch.int32)) == str(g["floor_sha"])
+
+
+def test_identity_view_zeroes_last_planes():
+    """identity view returns vol on [:15]^3 and exact 0 on index 15 of every axis."""
+    vol = torch.randn(2, 3, 16, 16, 16, device=DEV)
+    view = np.zeros((2, 6)); view[:, 2] = 1.0
+    a = ops.view_to_affine(view).to(DEV)
+    out = ops.rotate_fwd_raw(vol, a)
+    assert torch.equal(out[:, :, :15, :15, :15], vol[:, :, :15, :15, :15])
+    assert out[:, :, 15].abs().max() == 0 and out[:, :, :, 15].abs().max() == 0 and out[..., 15].abs().max() == 0
+
+
+@pytest.mark.parametrize("shape", [(64, 64, 16), (8, 64, 32), (3, 7, 16), (2, 1, 8)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_full_size_vs_c_oracle_and_adjoint(shape, dtype, c_oracle):
+    """BASELINE cfg 3 sizes (and ragged channel counts): forward against the C oracle, and the
+    size-independent adjoint identity <R v, g> == <v, R^T g> linking forward and backward."""
+    b, c, s = shape
+    gen = torch.Generator().manual_seed(b * 1000 + c)
+    vol = torch.randn(b, c, s, s, s, generator=gen).to(dtype)
+    gout = torch.randn(b, c, s, s, s, generator=gen).to(dtype)
+    view = orc.sample_view(b, np.random.RandomState(c))
+    a_cpu = ops.view_to_affine(view, s, s)
+    a = a_cpu.to(DEV)
+    out = ops.rotate_fwd_raw(vol.to(DEV), a, ops.HG_BORDER_REFERENCE)
+    ref = np.empty((b, c, s, s, s), np.float32)
+    vf = np.ascontiguousarray(vol.float().numpy())
+    c_oracle.orc_rotate_fwd(np_ptr(vf), np_ptr(a_cpu.numpy()), np_ptr(ref), b, c, s)
+    if dtype == torch.float32:
+        assert np.array_equal(out.cpu().numpy(), ref)                  # bit-exact at full size
+    else:
+        assert rel_err(out.float(), ref) < 2 ** -8
+    gv = ops.rotate_bwd_raw(gout.to(DEV), a, c, s, ops.HG_BORDER_REFERENCE)
+    lhs = (out.double() * gout.to(DEV).double()).sum().item()
+    rhs = (vol.to(DEV).double() * gv.double()).sum().item()
+    tol = 1e-5 if dtype == torch.float32 else 2e-2
+    scale = (out.double().abs() * gout.to(DEV).double().abs()).sum().item()
+    assert abs(lhs - rhs) <= tol * scale / 10
+    if dtype == torch.float32:
+        refg = np.empty_like(ref)
+        gf = np.ascontiguousarray(gout.float().numpy())
+        c_oracle.orc_rotate_bwd(np_ptr(gf), np_ptr(a_cpu.numpy()), np_ptr(refg), b, c, s)
+        assert rel_err(gv, refg) < 1e-5
+
+
+def test_linearity():
+    vol1 = torch.randn(4, 8, 16, 16, 16, device=DEV)
+    vol2 = torch.randn(4, 8, 16, 16, 16, device=DEV)
+    a = ops.view_to_affine(orc.sample_view(4, np.random.RandomState(3))).to(DEV)
+    lhs = ops.rotate_fwd_raw(vol1 + 2 * vol2, a, ops.HG_BORDER_ZERO)
+    rhs = ops.rotate_fwd_raw(vol1, a, ops.HG_BORDER_ZERO) + 2 * ops.rotate_fwd_raw(vol2, a, ops.HG_BORDER_ZERO)
+    assert rel_err(lhs, rhs) < 1e-5
+
+
+def test_errors():
+    vol = torch.randn(1, 2, 16, 16, 16, device=DEV)
+    a = torch.eye(4, device=DEV).unsqueeze(0)
+    with pytest.raises(Exception):
+        ops.rotate_fwd_raw(vol.double(), a)
+    with pytest.raises(ValueError):
+        ops.rotate_fwd_raw(vol, a[:, :3])
+    with pytest.raises(RuntimeError):
+        ops.rotate_fwd_raw(vol.cpu(), a.cpu())
+    from lightning_gan_zoo_b200._lib import HologanB200Error
+    with pytest.raises(HologanB200Error, match="size must be"):
+        ops.rotate_fwd_raw(torch.randn(1, 1, 12, 12, 12, device=DEV), a)

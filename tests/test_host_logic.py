@@ -1,0 +1,99 @@
+"""Host-side mirror of the reference interface (no GPU needed)."""
+import json
+import os
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, load_golden
+from lightning_gan_zoo_b200 import compat, ops
+from lightning_gan_zoo_b200.core.models import hologan_discriminator as D
+from lightning_gan_zoo_b200.core.models import hologan_generator as G
+from oracle import hologan_oracle as orc
+
+VIEW_ARGS = SimpleNamespace(azimuth_low=220, azimuth_high=320, elevation_low=70, elevation_high=110, scale_low=1,
+                            scale_high=1, transX_low=0, transX_high=0, transY_low=0, transY_high=0, transZ_low=0,
+                            transZ_high=0, batch_size=32)
+
+
+@pytest.mark.parametrize("tag,size", [("s16", 16), ("s8", 8)])
+def test_view_to_affine_is_bit_exact(tag, size):
+    g = load_golden(f"rotate_{tag}.npz")
+    a = ops.view_to_affine(g["view"], size, size)
+    assert a.dtype == torch.float32 and tuple(a.shape) == (g["view"].shape[0], 4, 4)
+    assert np.array_equal(a.numpy(), g["a_inv"])
+    # torch fp32 views (figure callbacks pass tensors: core/figures/types.py:235,312)
+    a2 = ops.view_to_affine(torch.from_numpy(g["view"]).float(), size, size)
+    assert np.array_equal(a2.numpy(), g["a_inv"])
+    assert np.array_equal(a.numpy()[:, 3], np.tile(np.array([0, 0, 0, 1], np.float32), (a.shape[0], 1)))
+
+
+def test_view_to_affine_sweep():
+    g = load_golden("rotate_sweep100.npz")
+    assert np.array_equal(ops.view_to_affine(g["view"]).numpy(), g["a_inv"])
+    with pytest.raises(ValueError):
+        ops.view_to_affine(np.zeros((4, 5)))
+
+
+def test_state_dict_keys_match_reference():
+    spec = json.load(open(os.path.join(GOLDEN, "state_dict_spec.json")))
+    g = G.Generator(64, 3, 128, VIEW_ARGS, 64, gpu=False)
+    got = [[k, list(v.shape)] for k, v in g.state_dict().items()]
+    assert got == spec["generator_64"]
+    d = D.Discriminator(3, 64, 128)
+    got = [[k, list(v.shape)] for k, v in d.state_dict().items()]
+    assert got == spec["discriminator_64"]
+    assert sum(p.numel() for p in g.parameters()) == 7795907
+    assert sum(p.numel() for p in d.parameters()) == 5379969
+
+
+def test_patched_128_heads():
+    g = G.Generator(16, 3, 128, VIEW_ARGS, 128, gpu=False)
+    assert tuple(g.final_layer.weight.shape) == (16, 3, 4, 4) and g.final_layer.stride == (2, 2)
+    d = D.Discriminator(3, 8, 128, img_size=128)
+    assert d.linear1.in_features == 8 * 8 * 8 * 8
+    with pytest.raises(ValueError):
+        G.Generator(16, 3, 128, VIEW_ARGS, 96, gpu=False)
+
+
+def test_sample_view_rng_parity():
+    g = G.Generator(8, 3, 128, VIEW_ARGS, 64, gpu=False)
+    np.random.seed(7)
+    mine = g.sample_view(16)
+    theirs = orc.sample_view(16, np.random.RandomState(7))
+    assert mine.dtype == np.float64 and np.array_equal(mine, theirs)
+    deg = np.rad2deg(mine[:, 0])
+    assert (deg > 219.999).all() and (deg < 319.001).all() and np.allclose(deg, np.round(deg))
+
+
+def test_cpu_tensors_fail_loudly():
+    g = G.Generator(8, 3, 128, VIEW_ARGS, 64, gpu=False)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        g(torch.zeros(2, 128), view_in=np.zeros((2, 6)))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        G.AdaIn(torch.zeros(1, 4, 8), torch.ones(1, 4), torch.zeros(1, 4))
+
+
+def test_compat_aliases():
+    compat.install()
+    import importlib
+    m = importlib.import_module("core.models.hologan_generator")
+    assert m.Generator is G.Generator
+    assert importlib.import_module("core.models.hologan_discriminator").Discriminator is D.Discriminator
+
+
+def test_discriminator_matches_oracle_on_cpu():
+    """The stock-torch discriminator mirror against the functional oracle (training-mode power iteration)."""
+    gen = torch.Generator().manual_seed(5)
+    dp = orc.init_discriminator_params(3, 8, 128, 64, generator=gen)
+    d = D.Discriminator(3, 8, 128)
+    sd = {k: v.clone() for k, v in dp.items()}
+    sd.update({k.replace(".conv2d.", ".conv2d_spec_norm."): v for k, v in sd.items() if k.startswith("blocks.")})
+    d.load_state_dict(sd)
+    x = torch.rand(2, 3, 64, 64, generator=gen) * 2 - 1
+    d.train()
+    l1, z1 = d(x)
+    l2, z2 = orc.discriminator_forward({k: v.clone() for k, v in dp.items()}, x, training=True)
+    assert torch.allclose(l1, l2, atol=1e-6) and torch.allclose(z1, z2, atol=1e-6)
