@@ -1,0 +1,339 @@
+#!/usr/bin/env python
+"""bench.py -- HoloGAN training-step throughput (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py --gpus 1 --steps 60 --warmup 9
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...      # the reference algorithm (oracle port) on the host cores
+
+One "step" = one `training_step` + optimizer update on one batch, following the reference's
+[D, G, G] optimizer schedule (conf/expt/hologan.yaml:16-17).  Workload (BASELINE.json configs[1]):
+HoloGAN 64x64, batch 64 per GPU, bf16 compute, synthetic data, random-init weights.
+
+Prints ONE JSON line (rank 0).  `value` times K steps with inputs resident in HBM; `e2e` times the
+same K steps through the public API with pinned-host inputs copied H2D and the loss read back D2H
+every step.  `roofline` is measured live for the dominant hand-written kernel; `cpu_baseline` times
+the oracle port on the host (bounded sample).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+METRIC = "hologan_train_images_per_s"
+UNIT = "images/s"
+WORKLOAD = "HoloGAN 64x64 full training step ([D,G,G] schedule), batch 64 per GPU, bf16"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=60)
+    ap.add_argument("--warmup", type=int, default=9)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=64, help="per-GPU batch")
+    ap.add_argument("--img-size", type=int, default=64)
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--cpu-batch", type=int, default=8, help="batch of the CPU baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-roofline", action="store_true")
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------------------------------
+# measured peaks / clocks
+# --------------------------------------------------------------------------------------------------
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"],
+                "bf16_tflops_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.proc = None
+        self.gpu = gpu_index
+        self.path = f"/tmp/hg_clocks_{os.getpid()}.csv"
+
+    def start(self):
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        self.f.close()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            parts = [s.strip() for s in line.split(",")]
+            if len(parts) < 8:
+                continue
+            try:
+                sm.append(float(parts[1])); mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        try:
+            os.remove(self.path)
+        except OSError:
+            pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------------
+# reference arm / CPU baseline: the oracle port on the host cores
+# --------------------------------------------------------------------------------------------------
+
+def cpu_training_steps(batch: int, img_size: int, steps: int, warmup: int):
+    """[D,G,G] training steps of the reference algorithm (oracle/hologan_oracle.py restates
+    core/lightning_module.py:209-237 + the two networks) on the host; returns (images/s, ms/step, threads)."""
+    from oracle import hologan_oracle as orc
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    gen = torch.Generator().manual_seed(1)
+    gp = {k: v.requires_grad_(True) for k, v in orc.init_generator_params(64, 3, 128, img_size, generator=gen).items()}
+    dp = orc.init_discriminator_params(3, 64, 128, img_size, generator=gen)
+    dp = {k: (v.requires_grad_(True) if not k.endswith(("_u", "_v")) else v) for k, v in dp.items()}
+    opt_d = torch.optim.Adam([v for v in dp.values() if v.requires_grad], lr=1e-4, betas=(0.9, 0.999))
+    opt_g = torch.optim.Adam(list(gp.values()), lr=1e-4, betas=(0.9, 0.999))
+    rs = np.random.RandomState(1)
+
+    def one(i):
+        idx = 0 if i % 3 == 0 else 1
+        real = torch.rand(batch, 3, img_size, img_size, generator=gen) * 2 - 1
+        z = torch.rand(batch, 128, generator=gen) * 2 - 1
+        view = orc.sample_view(batch, rs)
+        fake = orc.generator_forward(gp, z, view, img_size)
+        if idx == 0:
+            opt_d.zero_grad(set_to_none=True)
+            loss, _ = orc.hologan_losses(0, dp, real, fake, z)
+            loss.backward()
+            opt_d.step()
+        else:
+            opt_g.zero_grad(set_to_none=True)
+            # Lightning's toggle_optimizer freezes D during the G step: no D weight gradients
+            frozen = {k: v.detach() for k, v in dp.items()}
+            loss, _ = orc.hologan_losses(1, frozen, None, fake, z)
+            loss.backward()
+            opt_g.step()
+            for k in frozen:
+                if k.endswith(("_u", "_v")):
+                    dp[k] = frozen[k]
+        return float(loss)
+
+    for i in range(warmup):
+        one(i)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        one(i)
+    dt = time.perf_counter() - t0
+    return batch * steps / dt, dt / steps * 1e3, threads
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warmup = args.steps, args.warmup
+    ips, ms, threads = cpu_training_steps(args.cpu_batch, args.img_size, steps, warmup)
+    sample = f"batch {args.cpu_batch} per step (bounded sample of the batch-{args.batch} workload), fp32, torch CPU"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": ips, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "img_size": args.img_size, "per_gpu_batch": args.batch},
+        "cpu_baseline": {"value": ips, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": ips, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+# roofline of the dominant hand-written kernel, measured live with CUDA events
+# --------------------------------------------------------------------------------------------------
+
+def rotate_roofline(peaks, device):
+    """cfg 3 microbench: (64, 64, 16^3) fp32 rotate-resample forward.  Algorithmic bytes per launch =
+    read the volume + write the volume = 2*B*C*S^3*4.  Eight buffer pairs (1 GiB) are
+    rotated so every launch reads from HBM, not from the 126 MB L2."""
+    from lightning_gan_zoo_b200 import ops
+    b, c, s = 64, 64, 16
+    nbuf = 8
+    vols = [torch.randn(b, c, s, s, s, device=device) for _ in range(nbuf)]
+    rs = np.random.RandomState(0)
+    view = np.zeros((b, 6)); view[:, 0] = np.deg2rad(rs.randint(220, 320, b)); view[:, 1] = np.deg2rad(rs.randint(70, 110, b)); view[:, 2] = 1
+    a = ops.view_to_affine(view).to(device)
+    for v in vols[:3]:
+        ops.rotate_fwd_raw(v, a, ops.HG_BORDER_REFERENCE)
+    torch.cuda.synchronize()
+    iters = 40
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    ev[0].record()
+    for i in range(iters):
+        ops.rotate_fwd_raw(vols[i % nbuf], a, ops.HG_BORDER_REFERENCE)
+    ev[1].record()
+    torch.cuda.synchronize()
+    ms = ev[0].elapsed_time(ev[1]) / iters
+    bytes_alg = 2 * b * c * s ** 3 * 4
+    achieved = bytes_alg / (ms * 1e-3) / 1e9
+    return {"bound": "hbm", "kernel": "rotate_fwd_ncdhw_kernel<float,4> (64,64,16^3) fp32", "achieved": achieved,
+            "peak": peaks["hbm_gbs"], "peak_source": peaks["source"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
+            "traffic": None, "us_per_launch": ms * 1e3, "algorithmic_bytes": bytes_alg,
+            "l2_policy": "8 rotating 64 MiB inputs (512 MiB) > 126 MB L2"}
+
+
+# --------------------------------------------------------------------------------------------------
+# main arm
+# --------------------------------------------------------------------------------------------------
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    import torch.distributed as dist
+    from lightning_gan_zoo_b200 import _lib, ops
+    from lightning_gan_zoo_b200.training import HologanConfig, HologanTrainer
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the B200 path has no CPU fallback); use --impl reference")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    _lib.load()
+
+    cfg = HologanConfig(batch_size=args.batch, img_size=args.img_size)
+    dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
+    trainer = HologanTrainer(cfg, device=device, compute_dtype=dtype, rank=rank, world_size=world)
+    B, S = args.batch, args.img_size
+    K, W = args.steps, args.warmup
+
+    # ---- synthetic inputs -------------------------------------------------------------------------
+    pool = 6
+    gen = torch.Generator().manual_seed(100 + rank)
+    real_host = [torch.rand(B, 3, S, S, generator=gen).mul_(2).sub_(1).pin_memory() for _ in range(pool)]
+    real_dev = [r.to(device) for r in real_host]
+    z_dev = [trainer.sample_noise(B).to(device) for _ in range(pool)]
+    a_dev = [ops.view_to_affine(trainer.sample_view(B)).to(device) for _ in range(pool)]
+    z_pin = torch.empty(B, cfg.noise_dim).pin_memory()
+    a_pin = torch.empty(B, 4, 4).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def resident_step(i):
+        trainer.step(real_dev[i % pool], i, z=z_dev[i % pool], view=a_dev[i % pool])
+
+    def e2e_step(i):
+        real = real_host[i % pool].to(device, non_blocking=True)
+        z_pin.copy_(trainer.sample_noise(B))
+        a_pin.copy_(ops.view_to_affine(trainer.sample_view(B)))
+        z = z_pin.to(device, non_blocking=True)
+        a = a_pin.to(device, non_blocking=True)
+        loss = trainer.step(real, i, z=z, view=a)
+        return float(loss)            # D2H read of the step's result
+
+    def timed(fn, k):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(k):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=device)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    for i in range(max(W, 3)):
+        resident_step(i)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = _lib.launch_count
+    ms_total = timed(resident_step, K)
+    launches = _lib.launch_count - l0
+    clocks = sampler.stop() if rank == 0 else None
+    for i in range(3):
+        e2e_step(i)
+    ms_e2e = timed(e2e_step, K)
+
+    value = world * B * K / (ms_total * 1e-3)
+    e2e_value = world * B * K / (ms_e2e * 1e-3)
+    h2d = B * 3 * S * S * 4 + B * cfg.noise_dim * 4 + B * 16 * 4
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(W, 3),
+        "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": args.dtype, "data": "synthetic",
+        "config": {"workload": WORKLOAD if (B, S, args.dtype) == (64, 64, "bf16") else
+                   f"HoloGAN {S}x{S} training step, batch {B} per GPU, {args.dtype}",
+                   "img_size": S, "per_gpu_batch": B, "global_batch": B * world, "parallelism": f"dp{world}",
+                   "schedule": "[D,G,G]", "weights": "random init",
+                   "l2": "no flush: one step touches >126 MB of distinct activations/gradients/weights+Adam state"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                "ms_per_step": ms_e2e / K},
+        "gpu_launches": launches,
+        "clocks": clocks,
+    }
+    if rank == 0:
+        peaks = measured_peaks()
+        if not args.no_roofline:
+            line["roofline"] = rotate_roofline(peaks, device)
+        if world == 1 and not args.no_cpu_baseline:
+            ips, ms, threads = cpu_training_steps(args.cpu_batch, S, steps=6, warmup=3)
+            line["cpu_baseline"] = {"value": ips, "unit": UNIT, "cores": threads, "kind": "port",
+                                    "sample": f"6 [D,G,G] steps at batch {args.cpu_batch} (fp32, torch CPU oracle port), "
+                                              f"{ms:.0f} ms/step"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

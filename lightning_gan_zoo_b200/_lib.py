@@ -34,6 +34,7 @@ _RESTYPES = {"hg_last_error": ctypes.c_char_p}
 
 _lib = None
 _lock = threading.Lock()
+launch_count = 0      # number of ABI calls that enqueued kernels (bench.py reports it as gpu_launches)
 
 
 class HologanB200Error(RuntimeError):
@@ -65,8 +66,10 @@ def load() -> ctypes.CDLL:
 
 def call(name: str, *args) -> None:
     """Invoke an ABI function and raise HologanB200Error with hg_last_error() on failure."""
+    global launch_count
     lib = load()
     rc = getattr(lib, name)(*args)
+    launch_count += 1
     if rc != 0:
         msg = lib.hg_last_error()
         raise HologanB200Error(f"{name} failed ({rc}): {msg.decode() if msg else ''}")

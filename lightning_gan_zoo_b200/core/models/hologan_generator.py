@@ -11,7 +11,9 @@ backward -- runs in `libhologan_b200.so` through `lightning_gan_zoo_b200.ops`.
 Deviations from the reference, all deliberate:
   * `sample_view` uses np.float64 (the reference's `np.float` crashes on numpy >= 1.24, R7);
   * `img_size == 128` builds the patched, working head (`ConvTranspose2d(k4, s2, p1)`, R4);
-  * no gradient is propagated into the view parameters (nobody consumes it).
+  * no gradient is propagated into the view parameters (nobody consumes it, SURVEY 3.4);
+  * `view_in` may also be a (B,4,4) fp32 tensor of precomputed inverse transforms
+    (`ops.view_to_affine`), so a caller can keep them resident on the device.
 """
 from __future__ import annotations
 
@@ -36,7 +38,7 @@ class ZMapping(nn.Module):
         nn.init.zeros_(self.linear1.bias)
 
     def forward(self, x):
-        style = F.relu(self.linear1(x))
+        style = F.relu(self.linear1(x)).float()      # AdaIN statistics / modulation stay fp32 under autocast
         c = self.output_channel
         return style[:, :c], style[:, c:]
 
@@ -115,6 +117,8 @@ class Generator(nn.Module):
         return view
 
     def _affine(self, view_params, size, new_size, device):
+        if isinstance(view_params, torch.Tensor) and view_params.dim() == 3 and tuple(view_params.shape[1:]) == (4, 4):
+            return view_params.to(device=device, dtype=torch.float32).contiguous()   # precomputed inverse transforms
         if size != new_size:
             raise NotImplementedError("resampling onto a grid of a different size is not on the hot path")
         return ops.view_to_affine(view_params, size, new_size).to(device, non_blocking=True)

@@ -32,10 +32,22 @@ __device__ __forceinline__ float row_dot(const float *__restrict__ r, float x, f
 
 __device__ __forceinline__ int clampi(int v, int hi) { return min(max(v, 0), hi); }
 
+// Shared-memory placement of voxel (z,y,x): rows keep their order but x is XOR-swizzled with a per-row
+// key so that neighbours along y and z (and not only along x) fall into different banks.  The views
+// of the hot path are near axis-aligned (azimuth ~270 deg, elevation ~90 deg): without the swizzle a
+// warp walking along output x reads source voxels S or S^2 elements apart = one bank, a 16-32-way
+// conflict.  ysh = log2(rows per 128-byte bank line).
+__device__ __forceinline__ int swz(int z, int y, int x, int S, int logS, int ysh)
+{
+    return (((z << logS) + y) << logS) + (x ^ ((z ^ (y >> ysh)) & (S - 1)));
+}
+
 // Corner indices (floor, +1, clamp: :249-261) and weights from the CLAMPED corner as float against
 // the UNCLAMPED coordinate, product order (wx*wy)*wz (:301-318).  Explicit _rn intrinsics keep nvcc
 // from contracting / re-associating, so fp32 results carry the reference's bits.
-__device__ __forceinline__ void make_corners(float x, float y, float z, int S, Corners &c)
+// kSwz: idx[] addresses the swizzled shared-memory tile instead of the linear volume.
+template <bool kSwz>
+__device__ __forceinline__ void make_corners(float x, float y, float z, int S, int logS, int ysh, Corners &c)
 {
     const int fx = __float2int_rd(x), fy = __float2int_rd(y), fz = __float2int_rd(z);
     const int x0 = clampi(fx, S - 1), x1 = clampi(fx + 1, S - 1);
@@ -44,9 +56,19 @@ __device__ __forceinline__ void make_corners(float x, float y, float z, int S, C
     const float ux = __fsub_rn((float)x1, x), lx = __fsub_rn(x, (float)x0);
     const float uy = __fsub_rn((float)y1, y), ly = __fsub_rn(y, (float)y0);
     const float uz = __fsub_rn((float)z1, z), lz = __fsub_rn(z, (float)z0);
-    const int r00 = (z0 * S + y0) * S, r01 = (z0 * S + y1) * S, r10 = (z1 * S + y0) * S, r11 = (z1 * S + y1) * S;
-    c.idx[0] = r00 + x0; c.idx[1] = r01 + x0; c.idx[2] = r00 + x1; c.idx[3] = r01 + x1;
-    c.idx[4] = r10 + x0; c.idx[5] = r11 + x0; c.idx[6] = r10 + x1; c.idx[7] = r11 + x1;
+    if (kSwz) {
+        const int m = S - 1;
+        const int k00 = (z0 ^ (y0 >> ysh)) & m, k01 = (z0 ^ (y1 >> ysh)) & m;
+        const int k10 = (z1 ^ (y0 >> ysh)) & m, k11 = (z1 ^ (y1 >> ysh)) & m;
+        const int r00 = ((z0 << logS) + y0) << logS, r01 = ((z0 << logS) + y1) << logS;
+        const int r10 = ((z1 << logS) + y0) << logS, r11 = ((z1 << logS) + y1) << logS;
+        c.idx[0] = r00 + (x0 ^ k00); c.idx[1] = r01 + (x0 ^ k01); c.idx[2] = r00 + (x1 ^ k00); c.idx[3] = r01 + (x1 ^ k01);
+        c.idx[4] = r10 + (x0 ^ k10); c.idx[5] = r11 + (x0 ^ k11); c.idx[6] = r10 + (x1 ^ k10); c.idx[7] = r11 + (x1 ^ k11);
+    } else {
+        const int r00 = (z0 * S + y0) * S, r01 = (z0 * S + y1) * S, r10 = (z1 * S + y0) * S, r11 = (z1 * S + y1) * S;
+        c.idx[0] = r00 + x0; c.idx[1] = r01 + x0; c.idx[2] = r00 + x1; c.idx[3] = r01 + x1;
+        c.idx[4] = r10 + x0; c.idx[5] = r11 + x0; c.idx[6] = r10 + x1; c.idx[7] = r11 + x1;
+    }
     const float uxuy = __fmul_rn(ux, uy), uxly = __fmul_rn(ux, ly), lxuy = __fmul_rn(lx, uy), lxly = __fmul_rn(lx, ly);
     c.w[0] = __fmul_rn(uxuy, uz); c.w[1] = __fmul_rn(uxly, uz); c.w[2] = __fmul_rn(lxuy, uz); c.w[3] = __fmul_rn(lxly, uz);
     c.w[4] = __fmul_rn(uxuy, lz); c.w[5] = __fmul_rn(uxly, lz); c.w[6] = __fmul_rn(lxuy, lz); c.w[7] = __fmul_rn(lxly, lz);
@@ -93,7 +115,7 @@ __global__ void rotate_debug_kernel(const float *__restrict__ a_inv, float *__re
     }
     if (idx) {
         Corners c;
-        make_corners(x, y, z, S, c);
+        make_corners<false>(x, y, z, S, logS, 0, c);
 #pragma unroll
         for (int k = 0; k < 8; ++k) idx[((size_t)k * B + b) * n + o] = b * n + c.idx[k];
     }
@@ -121,16 +143,26 @@ __global__ void __launch_bounds__(256) rotate_fwd_ncdhw_kernel(const T *__restri
     if (threadIdx.x < 12) m[threadIdx.x] = a_inv[b * 16 + threadIdx.x];
     // n is a multiple of 512 (S >= 8), so every channel slab is 16-byte aligned and sized.
     constexpr int kVec = 16 / sizeof(T);
+    const int ysh = max(0, (sizeof(T) == 4 ? 5 : 6) - logS);
     const int nvec = ct * n / kVec;
-    for (int i = threadIdx.x; i < nvec; i += blockDim.x)
-        reinterpret_cast<uint4 *>(tile)[i] = ld_stream_16(reinterpret_cast<const uint4 *>(src) + i);
+    for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
+        const uint4 u = ld_stream_16(reinterpret_cast<const uint4 *>(src) + i);
+        const T *e = reinterpret_cast<const T *>(&u);
+        const int lin = i * kVec;                       // element index within the CT-channel slab
+        const int ci = lin >> (3 * logS), v = lin & (n - 1);
+        const int vx = v & (S - 1), vy = (v >> logS) & (S - 1), vz = v >> (2 * logS);
+        T *row = tile + ci * n + (((vz << logS) + vy) << logS);
+        const int key = (vz ^ (vy >> ysh)) & (S - 1);
+#pragma unroll
+        for (int j = 0; j < kVec; ++j) row[(vx + j) ^ key] = e[j];
+    }
     __syncthreads();
 
     for (int o = threadIdx.x; o < n; o += blockDim.x) {
         float x, y, z;
         lattice_coords(m, o, S, logS, x, y, z);
         Corners c;
-        make_corners(x, y, z, S, c);
+        make_corners<true>(x, y, z, S, logS, ysh, c);
         if (kZeroBorder && !c.inside) {
 #pragma unroll
             for (int ci = 0; ci < CT; ++ci)
@@ -173,12 +205,13 @@ __global__ void __launch_bounds__(256) rotate_bwd_ncdhw_kernel(const T *__restri
     if (threadIdx.x < 12) m[threadIdx.x] = a_inv[b * 16 + threadIdx.x];
     for (int i = threadIdx.x; i < CT * n; i += blockDim.x) acc[i] = 0.f;
     __syncthreads();
+    const int ysh = max(0, 5 - logS);                    // accumulators are fp32
 
     for (int o = threadIdx.x; o < n; o += blockDim.x) {
         float x, y, z;
         lattice_coords(m, o, S, logS, x, y, z);
         Corners c;
-        make_corners(x, y, z, S, c);
+        make_corners<true>(x, y, z, S, logS, ysh, c);
         if (kZeroBorder && !c.inside) continue;
 #pragma unroll
         for (int ci = 0; ci < CT; ++ci) {
@@ -191,7 +224,11 @@ __global__ void __launch_bounds__(256) rotate_bwd_ncdhw_kernel(const T *__restri
         }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < ct * n; i += blockDim.x) dst[i] = from_f32<T>(acc[i]);
+    for (int i = threadIdx.x; i < ct * n; i += blockDim.x) {
+        const int ci = i >> (3 * logS), v = i & (n - 1);
+        const int vx = v & (S - 1), vy = (v >> logS) & (S - 1), vz = v >> (2 * logS);
+        dst[i] = from_f32<T>(acc[ci * n + swz(vz, vy, vx, S, logS, ysh)]);
+    }
 }
 
 // -------------------------------------------------------------------------------------------------

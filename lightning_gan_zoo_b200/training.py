@@ -1,0 +1,183 @@
+"""Lightning-free HoloGAN training harness (data-parallel, one process per GPU).
+
+Mirrors what the reference gets from `core.lightning_module.HOLOGAN` + `pl.Trainer(accelerator="ddp")`
+(reference core/lightning_module.py:35-102, 209-237; run_network.py:66-72; conf/expt/hologan.yaml):
+
+  * `training_step(batch, batch_idx, optimizer_idx)` -- the two losses of :217-237;
+  * two Adam optimizers (lr 1e-4, betas (0.9, 0.999)) alternating with frequencies
+    disc_freq = 1 / gen_freq = 2, i.e. the batch schedule [D, G, G, D, G, G, ...] (:75-87);
+  * the LambdaLR schedule of core/utils/hologan.py:3-9;
+  * DDP semantics: gradients are averaged over ranks once per optimizer step.  Here each network owns
+    ONE flat gradient buffer (parameters' .grad are views into it), so the exchange is a single NCCL
+    all-reduce per step (payload 21.5 MB for D, 31.2 MB for G in fp32) instead of DDP's buckets.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from types import SimpleNamespace
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.nn.functional as F
+
+from . import ops
+from .core.models.hologan_discriminator import Discriminator
+from .core.models.hologan_generator import Generator
+
+
+@dataclass
+class HologanConfig:
+    """Effective values of `+expt=hologan` (conf/expt/hologan.yaml:1-58, conf/config.yaml)."""
+    noise_dim: int = 128
+    batch_size: int = 32
+    img_size: int = 64
+    channels_img: int = 3
+    num_epochs: int = 25
+    lr: float = 1e-4
+    beta1: float = 0.9
+    beta2: float = 0.999
+    disc_freq: int = 1
+    gen_freq: int = 2
+    gen_in_planes: int = 64
+    disc_out_planes: int = 64
+    view_args: SimpleNamespace = field(default_factory=lambda: SimpleNamespace(
+        elevation_low=70, elevation_high=110, azimuth_low=220, azimuth_high=320, scale_low=1, scale_high=1,
+        transX_low=0, transX_high=0, transY_low=0, transY_high=0, transZ_low=0, transZ_high=0, batch_size=32))
+
+
+def hologan_lr_lambda(total_epochs: int):
+    """x1 until the middle epoch, then linear decay to 0 (core/utils/hologan.py:3-9)."""
+    half = total_epochs / 2
+
+    def factor(epoch: int) -> float:
+        return 1.0 if epoch <= half else 1.0 - (epoch - half) / half
+    return factor
+
+
+def optimizer_index(batch_idx: int, disc_freq: int = 1, gen_freq: int = 2) -> int:
+    """Lightning's `frequency` alternation: disc_freq batches on optimizer 0, then gen_freq on 1."""
+    return 0 if (batch_idx % (disc_freq + gen_freq)) < disc_freq else 1
+
+
+class _FlatGrads:
+    """One contiguous gradient buffer per network; parameter .grad tensors are views into it."""
+
+    def __init__(self, params):
+        self.params = [p for p in params]
+        n = sum(p.numel() for p in self.params)
+        dev, dt = self.params[0].device, self.params[0].dtype
+        self.flat = torch.zeros(n, device=dev, dtype=dt)
+        o = 0
+        for p in self.params:
+            p.grad = self.flat[o:o + p.numel()].view_as(p)
+            o += p.numel()
+
+    def zero(self):
+        self.flat.zero_()
+
+    def all_reduce_mean(self, world: int):
+        if world > 1:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
+            self.flat.div_(world)
+
+
+class HologanTrainer:
+    def __init__(self, cfg: Optional[HologanConfig] = None, device="cuda", compute_dtype=torch.bfloat16,
+                 rank: int = 0, world_size: int = 1, seed: int = 42):
+        self.cfg = cfg = cfg or HologanConfig()
+        self.device = torch.device(device)
+        self.rank, self.world = rank, world_size
+        self.compute_dtype = compute_dtype
+        torch.manual_seed(seed)          # same init on every rank (reference: seed_everything(42), run_network.py:27)
+        self.generator = Generator(cfg.gen_in_planes, cfg.channels_img, cfg.noise_dim, cfg.view_args, cfg.img_size,
+                                   gpu=self.device.type == "cuda").to(self.device)
+        self.discriminator = Discriminator(cfg.channels_img, cfg.disc_out_planes, cfg.noise_dim,
+                                           img_size=cfg.img_size).to(self.device)
+        if self.world > 1:               # identical replicas even if a rank's RNG had diverged
+            for t in list(self.generator.state_dict().values()) + list(self.discriminator.state_dict().values()):
+                dist.broadcast(t, src=0)
+        self.d_grads = _FlatGrads(self.discriminator.parameters())
+        self.g_grads = _FlatGrads(self.generator.parameters())
+        fused = self.device.type == "cuda"
+        self.opt_d = torch.optim.Adam(self.discriminator.parameters(), lr=cfg.lr, betas=(cfg.beta1, cfg.beta2), fused=fused)
+        self.opt_g = torch.optim.Adam(self.generator.parameters(), lr=cfg.lr, betas=(cfg.beta1, cfg.beta2), fused=fused)
+        lam = hologan_lr_lambda(cfg.num_epochs)
+        self.sched_d = torch.optim.lr_scheduler.LambdaLR(self.opt_d, lam)
+        self.sched_g = torch.optim.lr_scheduler.LambdaLR(self.opt_g, lam)
+        # decorrelated latent / view streams per rank (the reference's identical seed-42-per-rank is a quirk)
+        self.noise_rng = torch.Generator().manual_seed(seed + 1000 * (rank + 1))
+        self.view_rng = np.random.RandomState(seed + 1000 * (rank + 1))
+        self.logs: Dict[str, torch.Tensor] = {}
+
+    # ---- sampling (host side, like the reference) -----------------------------------------------
+    def sample_noise(self, n: int) -> torch.Tensor:
+        """U(-1,1) latent (conf/noise_distn/uniform.yaml), drawn on the host (lightning_module.py:212)."""
+        return torch.rand(n, self.cfg.noise_dim, generator=self.noise_rng) * 2 - 1
+
+    def sample_view(self, n: int) -> np.ndarray:
+        a = self.cfg.view_args
+        rs = self.view_rng
+        view = np.zeros((n, 6))
+        view[:, 0] = rs.randint(a.azimuth_low, a.azimuth_high, n).astype(np.float64) * math.pi / 180.0
+        if a.elevation_low < a.elevation_high:
+            view[:, 1] = rs.randint(a.elevation_low, a.elevation_high, n).astype(np.float64) * math.pi / 180.0
+        view[:, 2] = float(rs.uniform(a.scale_low, a.scale_high))
+        for col, (lo, hi) in enumerate(((a.transX_low, a.transX_high), (a.transY_low, a.transY_high),
+                                        (a.transZ_low, a.transZ_high)), start=3):
+            view[:, col] = lo + rs.random_sample(n) * (hi - lo)
+        return view
+
+    # ---- the step the metric counts -------------------------------------------------------------
+    def _autocast(self):
+        enabled = self.compute_dtype != torch.float32 and self.device.type == "cuda"
+        return torch.autocast("cuda", dtype=self.compute_dtype, enabled=enabled)
+
+    def training_step(self, real: torch.Tensor, z: torch.Tensor, view, optimizer_idx: int) -> torch.Tensor:
+        """Losses of HOLOGAN.training_step (lightning_module.py:209-237).  `z` and `view` are explicit
+        (the reference samples them inside); `real` is (B,3,H,W) in [-1,1] on the device."""
+        bce = F.binary_cross_entropy_with_logits
+        if optimizer_idx == 0:
+            with torch.no_grad(), self._autocast():     # the D step detaches fake (:221): no G graph is needed
+                fake = self.generator(z, view_in=view)
+            with self._autocast():
+                d_real, _ = self.discriminator(real)
+                d_fake, z_pred = self.discriminator(fake)
+            d_real, d_fake, z_pred = d_real.float(), d_fake.float(), z_pred.float()
+            loss_d = (bce(d_real, torch.ones_like(d_real)) + bce(d_fake, torch.zeros_like(d_fake))) / 2
+            q = torch.mean((z_pred - z) ** 2)
+            self.logs["train/d_loss"], self.logs["train/q_loss"] = loss_d.detach(), q.detach()
+            return loss_d + q
+        with self._autocast():
+            fake = self.generator(z, view_in=view)
+            out, z_pred = self.discriminator(fake)
+        out, z_pred = out.float(), z_pred.float()
+        loss_g = bce(out, torch.ones_like(out))
+        q = torch.mean((z_pred - z) ** 2)
+        self.logs["train/g_loss"], self.logs["train/q_loss"] = loss_g.detach(), q.detach()
+        return loss_g + q
+
+    def step(self, real: torch.Tensor, batch_idx: int, z: Optional[torch.Tensor] = None, view=None) -> torch.Tensor:
+        """One optimizer step of the [D, G, G] schedule on one batch; returns the (detached) loss."""
+        idx = optimizer_index(batch_idx, self.cfg.disc_freq, self.cfg.gen_freq)
+        n = real.shape[0]
+        if z is None:
+            z = self.sample_noise(n).to(self.device, non_blocking=True)
+        if view is None:
+            view = self.sample_view(n)
+        grads, opt = (self.d_grads, self.opt_d) if idx == 0 else (self.g_grads, self.opt_g)
+        # Lightning's toggle_optimizer: only the stepped network's parameters require grad
+        for p in self.discriminator.parameters():
+            p.requires_grad_(idx == 0)
+        grads.zero()
+        loss = self.training_step(real, z, view, idx)
+        loss.backward()
+        grads.all_reduce_mean(self.world)
+        opt.step()
+        return loss.detach()
+
+    def end_epoch(self):
+        self.sched_d.step()
+        self.sched_g.step()

@@ -183,7 +183,7 @@ def grads_summary(named_grads):
 
 def case_generator(in_planes, bsz, tag, seed, img_size=64, keep_grads=()):
     gen = torch.Generator().manual_seed(seed)
-    p = orc.init_generator_params(in_planes, 3, 128, img_size, generator=gen)
+    p = orc.init_generator_params(in_planes, 3, 128, img_size, generator=gen, bias_std=0.05)
     z = torch.rand(bsz, 128, generator=gen) * 2 - 1
     rs = np.random.RandomState(seed)
     view = orc.sample_view(bsz, rs)
@@ -233,7 +233,7 @@ def case_discriminator_and_step():
     seed = 404
     gen = torch.Generator().manual_seed(seed)
     dp = orc.init_discriminator_params(3, 8, 128, 64, generator=gen)
-    gp = orc.init_generator_params(8, 3, 128, 64, generator=gen)
+    gp = orc.init_generator_params(8, 3, 128, 64, generator=gen, bias_std=0.05)
     bsz = 4
     real = torch.rand(bsz, 3, 64, 64, generator=gen) * 2 - 1
     z = torch.rand(bsz, 128, generator=gen) * 2 - 1

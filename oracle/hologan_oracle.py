@@ -251,12 +251,17 @@ def generator_forward(p: Dict[str, Tensor], z: Tensor, view, img_size: int = 64,
 
 
 def init_generator_params(in_planes: int = 64, out_planes: int = 3, z_planes: int = 128,
-                          img_size: int = 64, generator: Optional[torch.Generator] = None
-                          ) -> Dict[str, Tensor]:
+                          img_size: int = 64, generator: Optional[torch.Generator] = None,
+                          bias_std: float = 0.0) -> Dict[str, Tensor]:
     """Random parameters with the reference's shapes and init distributions
     (hologan_generator.py:11-13,32-33,49,60-62,70-75).  RNG consumption order is the
-    oracle's own -- fixtures store parameters, they are not regenerated from the
-    reference's seed."""
+    oracle's own (fixtures pin a sha256 of the result).
+
+    `bias_std > 0` replaces the reference's all-zero bias init by N(0, bias_std), i.e. a
+    "trained-like" state.  Parity fixtures use it because with exactly-zero biases the ReLU
+    after the 1x1 projection sits on pre-activations that are pure rounding noise wherever the
+    rotated volume is out of range (~1e-9), which makes the REFERENCE's own gradient there a
+    coin flip (observed: 0.9 % change of sum|d bias| between two fp32 evaluation orders)."""
     g = generator
 
     def nrm(*shape, std=0.02):
@@ -289,6 +294,10 @@ def init_generator_params(in_planes: int = 64, out_planes: int = 3, z_planes: in
     else:
         p["final_layer.weight"] = nrm(in_planes, out_planes, 4, 4)
     p["final_layer.bias"] = torch.zeros(out_planes)
+    if bias_std > 0:
+        for k in sorted(p):
+            if k.endswith(".bias"):
+                p[k] = torch.randn(p[k].shape, generator=g) * bias_std
     return p
 
 

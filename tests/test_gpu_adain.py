@@ -40,7 +40,7 @@ def test_hot_path_shapes_vs_oracle(shape, dtype, slope):
     s = torch.rand(bsz, c, generator=gen) + 0.1
     b = torch.randn(bsz, c, generator=gen)
     dy = torch.randn(bsz, c, n, generator=gen).to(dtype)
-    xr = x.float().requires_grad_(True); sr = s.clone().requires_grad_(True); br = b.clone().requires_grad_(True)
+    xr = x.float().clone().requires_grad_(True); sr = s.clone().requires_grad_(True); br = b.clone().requires_grad_(True)
     yr = torch.nn.functional.leaky_relu(orc.adain(xr, sr, br), slope)
     (yr * dy.float()).sum().backward()
     xg = x.to(DEV).requires_grad_(True); sg = s.to(DEV).requires_grad_(True); bg = b.to(DEV).requires_grad_(True)

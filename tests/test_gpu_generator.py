@@ -26,7 +26,7 @@ def _strict_fp32():
 def test_generator_fp32_vs_reference_golden(tag):
     g = load_golden(f"generator_{tag}.npz")
     gen = torch.Generator().manual_seed(int(g["seed"]))
-    p = orc.init_generator_params(int(g["in_planes"]), 3, 128, 64, generator=gen)
+    p = orc.init_generator_params(int(g["in_planes"]), 3, 128, 64, generator=gen, bias_std=0.05)
     if params_sha(p) != str(g["params_sha"]):
         pytest.skip("torch CPU RNG stream differs from the fixture's")
     bsz = g["z"].shape[0]
@@ -60,7 +60,7 @@ def test_generator_accepts_tensor_views_and_samples_views():
     view = orc.sample_view(4, np.random.RandomState(1))
     a = net(z, view_in=view)
     b = net(z, view_in=torch.from_numpy(view).float().to(DEV))
-    assert torch.equal(a, b)
+    assert rel_err(a, b) < 1e-6      # cuDNN's conv kernels are not bitwise run-to-run deterministic
     c = net(z)
     assert tuple(c.shape) == (4, 3, 64, 64) and c.abs().max() <= 1
     net128 = Generator(8, 3, 128, va, 128).to(DEV)
