@@ -100,6 +100,37 @@ int hg_adain_act_bwd(const void *x, const void *dy, const float *scale, const fl
                      int batch, int channels, int n, long long x_batch_stride, int sb_stride, int dsb_stride,
                      float neg_slope, int dtype, void *stream);
 
+
+/* ---- a4 / a9 / a10: transposed convolutions and the 1x1 projection as tcgen05 implicit GEMMs -------
+ * Replace nn.ConvTranspose3d(k3,s2,p1,op1) / nn.ConvTranspose2d(k4,s2,p1) / nn.ConvTranspose2d(k1)
+ * forward and backward (core/models/hologan_generator.py:25-30, 38, 60, 135).  bf16 operands, fp32
+ * accumulation in TMEM.  Layouts (all channels-last, bf16):
+ *   x      (B, [S,] S, S, Cin)                       `ndim` spatial dims of extent `size`
+ *   y_s2d  (B, [S,] S, S, P, Cout)   P = 2^ndim parity classes (P = 1 for kernel 1):
+ *          y_s2d[b, i.., (pz,py,px), co] == y[b, co, 2*iz+pz, 2*iy+py, 2*ix+px] of the torch op
+ *   packed weights (hg_convt_pack_weight) from the torch parameter (Cin, Cout, k..) fp32:
+ *          w_fwd [t][Cout][Cin], w_dgrad [t][Cin][Cout], t = flat kernel index (kz*k + ky)*k + kx
+ * Supported: Cin % 64 == 0, Cout % 16 == 0 (fwd); Cout % 64 == 0 (dgrad); Cin % 128 == 0 and
+ * Cout % 64 == 0 (wgrad); size in {4, 8, 16, 32, ...} tiling into 128-row boxes.
+ */
+int hg_convt_pack_weight(const float *w, void *w_fwd, void *w_dgrad, int cin, int cout, int taps, void *stream);
+/* y_s2d = act(convT(x) + bias); bias (Cout) fp32 or NULL; act: v > 0 ? v : neg_slope * v (1 = none) */
+int hg_convt_fwd(const void *x, const void *w_fwd, const float *bias, void *y_s2d, int batch, int cin, int cout,
+                 int ndim, int size, int kernel, float neg_slope, void *stream);
+/* dx (B, .., Cin) = adjoint of the forward w.r.t. x */
+int hg_convt_dgrad(const void *dy_s2d, const void *w_dgrad, void *dx, int batch, int cin, int cout, int ndim, int size,
+                   int kernel, void *stream);
+/* dw_packed [t][Cin][Cout] fp32 = adjoint w.r.t. the weight (overwritten; split-K partial sums are
+ * combined with fp32 red.global.add); hg_convt_unpack_wgrad converts to the torch layout. */
+int hg_convt_wgrad(const void *x, const void *dy_s2d, float *dw_packed, int batch, int cin, int cout, int ndim, int size,
+                   int kernel, void *stream);
+int hg_convt_unpack_wgrad(const float *dw_packed, float *dw, int cin, int cout, int taps, void *stream);
+
+/* Plain GEMM on the same pipeline: D[M,N] = act(A[M,K] @ B[N,K]^T + bias[N]); bf16 row-major A, B, D
+ * (row stride of D = ldd elements).  Used for the batched ZMapping (a2). */
+int hg_gemm_bf16_nt(const void *a, const void *b, const float *bias, void *d, int m, int n, int k, long long ldd,
+                    float neg_slope, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

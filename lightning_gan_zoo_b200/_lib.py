@@ -29,6 +29,13 @@ SIGNATURES = {
                          _c_ll, _c_int, _c_float, _c_float, _c_int, _c_void_p],
     "hg_adain_act_bwd": [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
                          _c_void_p, _c_int, _c_int, _c_int, _c_ll, _c_int, _c_int, _c_float, _c_int, _c_void_p],
+    "hg_convt_pack_weight": [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p],
+    "hg_convt_fwd": [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_float,
+                     _c_void_p],
+    "hg_convt_dgrad": [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_void_p],
+    "hg_convt_wgrad": [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_void_p],
+    "hg_convt_unpack_wgrad": [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p],
+    "hg_gemm_bf16_nt": [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_ll, _c_float, _c_void_p],
 }
 _RESTYPES = {"hg_last_error": ctypes.c_char_p}
 

@@ -1,0 +1,657 @@
+// tcgen05 implicit-GEMM kernels for the dense contractions of the HoloGAN generator:
+// ConvTranspose3d(k3,s2,p1,op1), ConvTranspose2d(k4,s2,p1) and the 1x1 projection -- forward, dgrad and
+// wgrad (reference core/models/hologan_generator.py:25-30,60,135,38).
+//
+// Formulation.  A stride-2 transposed convolution is split by output parity class: inside one class
+// every output position (b, i) is a plain sum over a few "taps", each tap being the input window
+// shifted by (sz,sy,sx) in {-1,0,+1}^d times one [Cout x Cin] slice of the weight.  Activations are
+// channels-last bf16, so the A operand of a tap is a TMA box of the (C, X, Y, Z, B) tensor at shifted
+// coordinates -- out-of-range rows are zero-filled by the TMA unit (the padding), nothing is ever
+// materialised (no im2col, no zero-insertion).  Conv outputs and their gradients live in a
+// "space-to-depth" layout (B, [Z,] Y, X, P*Cout), P = 2^d parity classes, which makes
+//   forward : Ys2d[pos, cls*Cout + co] = sum_taps X[pos + s][ci] * W[ci, co, tap]        (K-major A, B)
+//   dgrad   : dX[pos, ci] = sum_(cls,tap) dYs2d[pos - s, cls*Cout + co] * W[ci, co, tap]  (K-major A, B)
+//   wgrad   : dW[tap][ci, co] = sum_pos X[pos + s][ci] * dYs2d[pos, cls*Cout + co]        (MN-major A, B)
+// three instances of one warp-specialised pipeline:  TMA producer warp -> 128B-swizzled smem ring ->
+// single-thread tcgen05.mma issue (fp32 accumulators in TMEM) -> 4 epilogue warps (tcgen05.ld).
+#include <cuda.h>
+
+#include "hg_common.cuh"
+#include "sm100_ptx.cuh"
+
+namespace hg {
+
+constexpr int kBM = 128;              // rows of the accumulator tile = TMEM lanes
+constexpr int kBK = 64;               // bf16 elements per 128-byte swizzle row
+constexpr int kThreads = 192;         // warp 0: TMA, warp 1: TMEM alloc + MMA, warps 2-5: epilogue
+constexpr int kMaxStages = 8;
+constexpr int kMaxTaps = 32;
+constexpr int kMaxGroups = 8;
+constexpr int kSmemBudget = 200 * 1024;
+
+struct Tap {
+    int16_t sx, sy, sz, pad;
+    int32_t a_c_off;      // channel offset added to the A box (selects the parity class in s2d tensors)
+    int32_t b_row_off;    // first row of this tap's slice in the packed weight matrix
+};
+struct Group {
+    int32_t tap_begin, tap_count;
+    int32_t out_col_off;  // column offset of this group's output (parity class) in the output row
+    int32_t pad;
+};
+
+enum EpilogueMode { kEpiBf16 = 0, kEpiF32Atomic = 1 };
+
+struct TapGemmParams {
+    CUtensorMap tmA;      // K-major kernel: activations (C, X, Y, Z, B), box (64, bx, by, bz, bb), prod = 128
+    CUtensorMap tmB;      // K-major kernel: packed weights (Kcols, rows), box (64, BN)
+    int X, Y, Z, Bn;      // spatial extents / batch of the A tensor (for the tile -> coordinate decode)
+    int BN;               // accumulator columns
+    int k_chunks;         // 64-wide K chunks per tap
+    int stages;
+    int m_total;          // valid rows
+    long long ld_out;     // elements per output row
+    void *out;
+    const float *bias;    // per output column (without group offset) or null
+    float slope;          // act(v) = v > 0 ? v : slope * v   (1 = identity)
+    int num_groups;
+    Group groups[kMaxGroups];
+    Tap taps[kMaxTaps];
+};
+
+struct WgradParams {
+    CUtensorMap tmX;      // activations (Cin, X, Y, Z, B), box (64, px, py, pz, pb), prod = 64 positions
+    CUtensorMap tmDY;     // output gradients, s2d (P*Cout, X, Y, Z, B), same box
+    int X, Y, Z, Bn;
+    int BN;               // Cout tile
+    int stages;
+    int pos_tiles;        // number of 64-position tiles
+    int splits;           // split-K factor (grid.z = pairs * splits)
+    int cin, cout;
+    float *dw;            // packed fp32 [tap][Cin][Cout], accumulated with red.global.add
+    int num_pairs;
+    struct Pair {
+        int16_t sx, sy, sz, pad;
+        int32_t dy_c_off;     // cls * Cout
+        int32_t tap_flat;     // slice index in dw
+    } pairs[kMaxTaps];
+};
+
+struct SharedCtl {
+    uint64_t full[kMaxStages];
+    uint64_t empty[kMaxStages];
+    uint64_t acc_ready;
+    uint32_t tmem_base;
+};
+
+__device__ __forceinline__ uint32_t tmem_cols_for(int bn) { return bn <= 32 ? 32u : bn <= 64 ? 64u : bn <= 128 ? 128u : 256u; }
+
+__device__ __forceinline__ uint8_t *align_1024(uint8_t *p)
+{
+    return reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(p) + 1023) & ~uintptr_t(1023));
+}
+
+// -------------------------------------------------------------------------------------------------
+// K-major kernel: forward and dgrad (and plain GEMMs).  grid = (m_tiles, n_tiles, groups)
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads, 1) tap_gemm_kernel(const __grid_constant__ TapGemmParams p)
+{
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ SharedCtl ctl;
+    uint8_t *tiles = align_1024(smem_raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int BN = p.BN;
+    const uint32_t a_bytes = kBM * 128, b_bytes = (uint32_t)BN * 128, stage_bytes = a_bytes + b_bytes;
+    const Group grp = p.groups[blockIdx.z];
+    const int n0 = blockIdx.y * BN;
+    const int total_iters = grp.tap_count * p.k_chunks;
+
+    if (warp == 0 && ptx::elect_one()) {
+        ptx::prefetch_tensormap(&p.tmA);
+        ptx::prefetch_tensormap(&p.tmB);
+        for (int s = 0; s < p.stages; ++s) {
+            ptx::mbar_init(&ctl.full[s], 1);
+            ptx::mbar_init(&ctl.empty[s], 1);
+        }
+        ptx::mbar_init(&ctl.acc_ready, 1);
+        ptx::fence_barrier_init();
+    }
+    if (warp == 1) {
+        ptx::tmem_alloc(&ctl.tmem_base, tmem_cols_for(BN));
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = ctl.tmem_base;
+
+    if (warp == 0) {
+        if (ptx::elect_one()) {
+            // ===== TMA producer =====
+            long long pos = (long long)blockIdx.x * kBM;
+            const int x0 = (int)(pos % p.X); pos /= p.X;
+            const int y0 = (int)(pos % p.Y); pos /= p.Y;
+            const int z0 = (int)(pos % p.Z);
+            const int b0 = (int)(pos / p.Z);
+            int it = 0;
+            for (int t = 0; t < grp.tap_count; ++t) {
+                const Tap tap = p.taps[grp.tap_begin + t];
+                for (int kc = 0; kc < p.k_chunks; ++kc, ++it) {
+                    const int s = it % p.stages;
+                    const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+                    ptx::mbar_wait(&ctl.empty[s], ph ^ 1u);
+                    uint8_t *a_dst = tiles + (size_t)s * stage_bytes;
+                    ptx::mbar_arrive_expect_tx(&ctl.full[s], stage_bytes);
+                    ptx::tma_load_5d(a_dst, &p.tmA, &ctl.full[s], tap.a_c_off + kc * kBK, x0 + tap.sx, y0 + tap.sy,
+                                     z0 + tap.sz, b0);
+                    ptx::tma_load_2d(a_dst + a_bytes, &p.tmB, &ctl.full[s], kc * kBK, tap.b_row_off + n0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (ptx::elect_one()) {
+            // ===== MMA issuer =====
+            const uint32_t idesc = ptx::idesc_bf16(kBM, BN, false, false);
+            for (int it = 0; it < total_iters; ++it) {
+                const int s = it % p.stages;
+                const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+                ptx::mbar_wait(&ctl.full[s], ph);
+                ptx::tc_fence_after();
+                const uint32_t a_addr = ptx::smem_u32(tiles + (size_t)s * stage_bytes);
+                const uint64_t a_desc = ptx::smem_desc_sw128(a_addr, 16, 1024);
+                const uint64_t b_desc = ptx::smem_desc_sw128(a_addr + a_bytes, 16, 1024);
+#pragma unroll
+                for (int k = 0; k < kBK / 16; ++k)      // +32 bytes (>>4 = 2) per 16-element K step inside the swizzle row
+                    ptx::umma_bf16(tmem_base, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (it | k) != 0);
+                ptx::umma_commit(&ctl.empty[s]);        // frees the smem slot when these MMAs retire
+            }
+            ptx::umma_commit(&ctl.acc_ready);
+        }
+    } else {
+        // ===== epilogue: TMEM -> registers -> bias / activation -> bf16 -> global =====
+        ptx::mbar_wait(&ctl.acc_ready, 0);
+        ptx::tc_fence_after();
+        const int quad = warp & 3;                      // a warp may only touch TMEM lanes 32*(warp%4) .. +31
+        const int row = quad * 32 + lane;
+        const long long m = (long long)blockIdx.x * kBM + row;
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
+        __nv_bfloat16 *orow = static_cast<__nv_bfloat16 *>(p.out) + m * p.ld_out + grp.out_col_off + n0;
+        for (int c0 = 0; c0 < BN; c0 += 16) {
+            float v[16];
+            ptx::tmem_ld_16(taddr + (uint32_t)c0, v);
+            if (m < p.m_total) {
+                uint32_t packed[8];
+#pragma unroll
+                for (int j = 0; j < 16; j += 2) {
+                    float a = v[j], b = v[j + 1];
+                    if (p.bias) {
+                        a += __ldg(p.bias + n0 + c0 + j);
+                        b += __ldg(p.bias + n0 + c0 + j + 1);
+                    }
+                    a = a > 0.f ? a : a * p.slope;
+                    b = b > 0.f ? b : b * p.slope;
+                    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+                    packed[j >> 1] = *reinterpret_cast<uint32_t *>(&h);
+                }
+                uint4 *dst = reinterpret_cast<uint4 *>(orow + c0);
+                dst[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+                dst[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+            }
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) ptx::tmem_dealloc(tmem_base, tmem_cols_for(BN));
+}
+
+// -------------------------------------------------------------------------------------------------
+// MN-major kernel: wgrad.  grid = (Cin/128, Cout/BN, pairs * splits).  K runs over positions.
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads, 1) wgrad_gemm_kernel(const __grid_constant__ WgradParams p)
+{
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ SharedCtl ctl;
+    uint8_t *tiles = align_1024(smem_raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int BN = p.BN;
+    constexpr int kPos = 64;                                   // positions (K) per stage
+    const uint32_t box_bytes = kPos * 128;                     // one (64 channels x 64 positions) box
+    const uint32_t a_bytes = 2 * box_bytes, b_bytes = (uint32_t)(BN / 64) * box_bytes, stage_bytes = a_bytes + b_bytes;
+    const int pair_idx = blockIdx.z / p.splits, split = blockIdx.z % p.splits;
+    const WgradParams::Pair pr = p.pairs[pair_idx];
+    const int ci0 = blockIdx.x * kBM, co0 = blockIdx.y * BN;
+    const int per = (p.pos_tiles + p.splits - 1) / p.splits;
+    const int t_begin = split * per, t_end = min(p.pos_tiles, t_begin + per);
+    const int total_iters = max(0, t_end - t_begin);
+
+    if (warp == 0 && ptx::elect_one()) {
+        ptx::prefetch_tensormap(&p.tmX);
+        ptx::prefetch_tensormap(&p.tmDY);
+        for (int s = 0; s < p.stages; ++s) {
+            ptx::mbar_init(&ctl.full[s], 1);
+            ptx::mbar_init(&ctl.empty[s], 1);
+        }
+        ptx::mbar_init(&ctl.acc_ready, 1);
+        ptx::fence_barrier_init();
+    }
+    if (warp == 1) {
+        ptx::tmem_alloc(&ctl.tmem_base, tmem_cols_for(BN));
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = ctl.tmem_base;
+
+    if (total_iters > 0) {
+        if (warp == 0) {
+            if (ptx::elect_one()) {
+                for (int it = 0; it < total_iters; ++it) {
+                    long long pos = (long long)(t_begin + it) * kPos;
+                    const int x0 = (int)(pos % p.X); pos /= p.X;
+                    const int y0 = (int)(pos % p.Y); pos /= p.Y;
+                    const int z0 = (int)(pos % p.Z);
+                    const int b0 = (int)(pos / p.Z);
+                    const int s = it % p.stages;
+                    const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+                    ptx::mbar_wait(&ctl.empty[s], ph ^ 1u);
+                    uint8_t *dst = tiles + (size_t)s * stage_bytes;
+                    ptx::mbar_arrive_expect_tx(&ctl.full[s], stage_bytes);
+                    for (int j = 0; j < 2; ++j)
+                        ptx::tma_load_5d(dst + j * box_bytes, &p.tmX, &ctl.full[s], ci0 + j * 64, x0 + pr.sx, y0 + pr.sy,
+                                         z0 + pr.sz, b0);
+                    for (int j = 0; j < BN / 64; ++j)
+                        ptx::tma_load_5d(dst + a_bytes + j * box_bytes, &p.tmDY, &ctl.full[s], pr.dy_c_off + co0 + j * 64, x0,
+                                         y0, z0, b0);
+                }
+            }
+        } else if (warp == 1) {
+            if (ptx::elect_one()) {
+                const uint32_t idesc = ptx::idesc_bf16(kBM, BN, true, true);
+                for (int it = 0; it < total_iters; ++it) {
+                    const int s = it % p.stages;
+                    const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+                    ptx::mbar_wait(&ctl.full[s], ph);
+                    ptx::tc_fence_after();
+                    const uint32_t a_addr = ptx::smem_u32(tiles + (size_t)s * stage_bytes);
+                    // MN-major: LBO = distance between 64-channel groups (one box), SBO = 8 positions
+                    const uint64_t a_desc = ptx::smem_desc_sw128(a_addr, box_bytes, 1024);
+                    const uint64_t b_desc = ptx::smem_desc_sw128(a_addr + a_bytes, box_bytes, 1024);
+#pragma unroll
+                    for (int k = 0; k < kPos / 16; ++k)   // 16 positions = 16 rows x 128 B = 2048 B (>>4 = 128)
+                        ptx::umma_bf16(tmem_base, a_desc + (uint64_t)(k * 128), b_desc + (uint64_t)(k * 128), idesc,
+                                       (it | k) != 0);
+                    ptx::umma_commit(&ctl.empty[s]);
+                }
+                ptx::umma_commit(&ctl.acc_ready);
+            }
+        } else {
+            ptx::mbar_wait(&ctl.acc_ready, 0);
+            ptx::tc_fence_after();
+            const int quad = warp & 3;
+            const int row = quad * 32 + lane;
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
+            float *orow = p.dw + ((size_t)pr.tap_flat * p.cin + ci0 + row) * p.cout + co0;
+            for (int c0 = 0; c0 < BN; c0 += 16) {
+                float v[16];
+                ptx::tmem_ld_16(taddr + (uint32_t)c0, v);
+                if (ci0 + row < p.cin) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) atomicAdd(orow + c0 + j, v[j]);
+                }
+            }
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) ptx::tmem_dealloc(tmem_base, tmem_cols_for(BN));
+}
+
+// -------------------------------------------------------------------------------------------------
+// Weight packing: torch ConvTranspose layout (Cin, Cout, k^d) fp32  <->  GEMM operand layouts
+// -------------------------------------------------------------------------------------------------
+// w_fwd[t][co][ci] (B operand of forward: rows = Cout, K = Cin), w_dgrad[t][ci][co] (rows = Cin, K = Cout)
+__global__ void pack_weight_kernel(const float *__restrict__ w, __nv_bfloat16 *__restrict__ w_fwd,
+                                   __nv_bfloat16 *__restrict__ w_dgrad, int cin, int cout, int taps)
+{
+    const size_t n = (size_t)cin * cout * taps;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        // i enumerates the dgrad layout (t, ci, co): coalesced writes there
+        const int co = (int)(i % cout);
+        const int ci = (int)((i / cout) % cin);
+        const int t = (int)(i / ((size_t)cout * cin));
+        const float v = w[((size_t)ci * cout + co) * taps + t];
+        const __nv_bfloat16 h = __float2bfloat16_rn(v);
+        if (w_dgrad) w_dgrad[i] = h;
+        if (w_fwd) w_fwd[((size_t)t * cout + co) * cin + ci] = h;
+    }
+}
+
+// dw_packed[t][ci][co] fp32 -> torch layout (Cin, Cout, k^d) fp32 (overwrites)
+__global__ void unpack_wgrad_kernel(const float *__restrict__ dwp, float *__restrict__ dw, int cin, int cout, int taps)
+{
+    const size_t n = (size_t)cin * cout * taps;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int t = (int)(i % taps);
+        const int co = (int)((i / taps) % cout);
+        const int ci = (int)(i / ((size_t)taps * cout));
+        dw[i] = dwp[((size_t)t * cin + ci) * cout + co];
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// Host side
+// -------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *sym = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(sym);
+    }
+    return fn;
+}
+
+// bf16 channels-last tensor (C, X, Y, Z, B) with box (64, bx, by, bz, bb), 128B swizzle, zero OOB fill
+static int make_map_5d(CUtensorMap *m, const void *base, long long C, int X, int Y, int Z, int B, int bx, int by, int bz,
+                       int bb)
+{
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return fail(HG_ERR_NO_DEVICE, "cuTensorMapEncodeTiled driver entry point unavailable");
+    cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)X, (cuuint64_t)Y, (cuuint64_t)Z, (cuuint64_t)B};
+    cuuint64_t strides[4] = {(cuuint64_t)C * 2, (cuuint64_t)C * 2 * X, (cuuint64_t)C * 2 * X * Y, (cuuint64_t)C * 2 * X * Y * Z};
+    cuuint32_t box[5] = {(cuuint32_t)kBK, (cuuint32_t)bx, (cuuint32_t)by, (cuuint32_t)bz, (cuuint32_t)bb};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void *>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(HG_ERR_INVALID_ARG, "cuTensorMapEncodeTiled(5d) failed with %d", (int)r);
+    return HG_OK;
+}
+
+static int make_map_2d(CUtensorMap *m, const void *base, long long cols, long long rows, int box_rows)
+{
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return fail(HG_ERR_NO_DEVICE, "cuTensorMapEncodeTiled driver entry point unavailable");
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+    cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(HG_ERR_INVALID_ARG, "cuTensorMapEncodeTiled(2d) failed with %d", (int)r);
+    return HG_OK;
+}
+
+// split `count` positions into a box over (X, Y, Z, B): fill x, then y, then z, then batch
+static bool box_for(int count, int X, int Y, int Z, int &bx, int &by, int &bz, int &bb)
+{
+    bx = by = bz = bb = 1;
+    int rem = count;
+    bx = rem < X ? rem : X; if (X % bx) return false; rem /= bx; if (bx < X) return rem == 1;
+    by = rem < Y ? rem : Y; if (Y % by) return false; rem /= by; if (by < Y) return rem == 1;
+    bz = rem < Z ? rem : Z; if (Z % bz) return false; rem /= bz; if (bz < Z) return rem == 1;
+    bb = rem;
+    return bb <= 256;
+}
+
+static int pick_bn(int n)
+{
+    if (n % 256 == 0) return 256;
+    if (n % 128 == 0) return 128;
+    if (n % 64 == 0) return 64;
+    if (n % 32 == 0) return 32;
+    if (n % 16 == 0) return 16;
+    return 0;
+}
+
+static int pick_stages(int stage_bytes, int iters)
+{
+    int s = (kSmemBudget - 1024) / stage_bytes;
+    if (s > kMaxStages) s = kMaxStages;
+    if (s > iters) s = iters < 1 ? 1 : iters;
+    return s;
+}
+
+// per-dimension tap table of a stride-2 transposed convolution: for output parity p, the kernel
+// indices k and input shifts s with  out[2*i + p] += in[i + s] * w[k]
+struct DimTaps { int n[2]; int k[2][2]; int s[2][2]; int classes; };
+static DimTaps dim_taps(int kernel)
+{
+    DimTaps d{};
+    if (kernel == 4) {          // k4 s2 p1: o = 2i - 1 + k
+        d.classes = 2;
+        d.n[0] = 2; d.k[0][0] = 1; d.s[0][0] = 0; d.k[0][1] = 3; d.s[0][1] = -1;
+        d.n[1] = 2; d.k[1][0] = 0; d.s[1][0] = 1; d.k[1][1] = 2; d.s[1][1] = 0;
+    } else if (kernel == 3) {   // k3 s2 p1 op1: o = 2i - 1 + k
+        d.classes = 2;
+        d.n[0] = 1; d.k[0][0] = 1; d.s[0][0] = 0;
+        d.n[1] = 2; d.k[1][0] = 0; d.s[1][0] = 1; d.k[1][1] = 2; d.s[1][1] = 0;
+    } else {                    // k1 s1: plain per-pixel GEMM
+        d.classes = 1;
+        d.n[0] = 1; d.k[0][0] = 0; d.s[0][0] = 0;
+    }
+    return d;
+}
+
+struct ConvShape {
+    int batch, cin, cout, ndim, size, kernel;
+    int X, Y, Z, P, taps;
+};
+static int conv_shape(ConvShape &c, const char *who)
+{
+    HG_REQUIRE(c.batch > 0 && c.cin > 0 && c.cout > 0 && c.size > 0, HG_ERR_INVALID_ARG, "%s: dims must be positive", who);
+    HG_REQUIRE((c.ndim == 2 && (c.kernel == 4 || c.kernel == 1)) || (c.ndim == 3 && c.kernel == 3), HG_ERR_UNSUPPORTED,
+               "%s: supported: ndim 2 with kernel 4 (s2,p1) or 1, ndim 3 with kernel 3 (s2,p1,op1)", who);
+    c.X = c.size; c.Y = c.size; c.Z = c.ndim == 3 ? c.size : 1;
+    c.P = c.kernel == 1 ? 1 : (c.ndim == 3 ? 8 : 4);
+    c.taps = c.kernel == 1 ? 1 : (c.ndim == 3 ? 27 : 16);
+    return HG_OK;
+}
+
+template <typename Fn>
+static void for_each_class_tap(const ConvShape &c, Fn fn)
+{
+    const DimTaps d = dim_taps(c.kernel);
+    const int nz = c.ndim == 3 ? d.classes : 1;
+    for (int pz = 0; pz < nz; ++pz)
+        for (int py = 0; py < d.classes; ++py)
+            for (int px = 0; px < d.classes; ++px) {
+                const int cls = (pz * d.classes + py) * d.classes + px;
+                const int tz_n = c.ndim == 3 ? d.n[pz] : 1;
+                for (int tz = 0; tz < tz_n; ++tz)
+                    for (int ty = 0; ty < d.n[py]; ++ty)
+                        for (int tx = 0; tx < d.n[px]; ++tx) {
+                            const int kz = c.ndim == 3 ? d.k[pz][tz] : 0, ky = d.k[py][ty], kx = d.k[px][tx];
+                            const int sz = c.ndim == 3 ? d.s[pz][tz] : 0, sy = d.s[py][ty], sx = d.s[px][tx];
+                            const int flat = c.ndim == 3 ? (kz * c.kernel + ky) * c.kernel + kx : ky * c.kernel + kx;
+                            fn(cls, flat, sx, sy, sz);
+                        }
+            }
+}
+
+static int launch_tap_gemm(TapGemmParams &p, int m_tiles, int n_tiles, cudaStream_t st, const char *who)
+{
+    const int stage_bytes = kBM * 128 + p.BN * 128;
+    int max_iters = 0;
+    for (int g = 0; g < p.num_groups; ++g) max_iters = p.groups[g].tap_count * p.k_chunks > max_iters ? p.groups[g].tap_count * p.k_chunks : max_iters;
+    p.stages = pick_stages(stage_bytes, max_iters);
+    const size_t smem = (size_t)p.stages * stage_bytes + 1024;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(tap_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+        attr_set = true;
+    }
+    dim3 grid(m_tiles, n_tiles, p.num_groups);
+    tap_gemm_kernel<<<grid, kThreads, smem, st>>>(p);
+    return check_launch(who);
+}
+
+}  // namespace hg
+
+using namespace hg;
+
+// D[M,N] = act(A[M,K] @ B[N,K]^T + bias), bf16 in / bf16 out, fp32 accumulate.
+extern "C" int hg_gemm_bf16_nt(const void *a, const void *b, const float *bias, void *d, int m, int n, int k, long long ldd,
+                               float neg_slope, void *stream)
+{
+    HG_REQUIRE(a && b && d, HG_ERR_INVALID_ARG, "hg_gemm_bf16_nt: null pointer");
+    HG_REQUIRE(m > 0 && n > 0 && k > 0, HG_ERR_INVALID_ARG, "hg_gemm_bf16_nt: dims must be positive");
+    const int bn = pick_bn(n);
+    HG_REQUIRE(k % kBK == 0 && bn >= 16 && ldd % 8 == 0, HG_ERR_UNSUPPORTED,
+               "hg_gemm_bf16_nt: need K %% 64 == 0, N %% 16 == 0, ldd %% 8 == 0 (got M=%d N=%d K=%d)", m, n, k);
+    TapGemmParams p{};
+    int rc = make_map_5d(&p.tmA, a, k, m, 1, 1, 1, kBM, 1, 1, 1);
+    if (rc) return rc;
+    rc = make_map_2d(&p.tmB, b, k, n, bn);
+    if (rc) return rc;
+    p.X = m; p.Y = 1; p.Z = 1; p.Bn = 1;
+    p.BN = bn; p.k_chunks = k / kBK; p.m_total = m; p.ld_out = ldd; p.out = d; p.bias = bias; p.slope = neg_slope;
+    p.num_groups = 1;
+    p.groups[0] = Group{0, 1, 0, 0};
+    p.taps[0] = Tap{0, 0, 0, 0, 0, 0};
+    return launch_tap_gemm(p, (m + kBM - 1) / kBM, n / bn, static_cast<cudaStream_t>(stream), "hg_gemm_bf16_nt");
+}
+
+extern "C" int hg_convt_pack_weight(const float *w, void *w_fwd, void *w_dgrad, int cin, int cout, int taps, void *stream)
+{
+    HG_REQUIRE(w && (w_fwd || w_dgrad), HG_ERR_INVALID_ARG, "hg_convt_pack_weight: null pointer");
+    HG_REQUIRE(cin > 0 && cout > 0 && taps > 0, HG_ERR_INVALID_ARG, "hg_convt_pack_weight: dims must be positive");
+    const size_t n = (size_t)cin * cout * taps;
+    const int grid = (int)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);
+    pack_weight_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(w, static_cast<__nv_bfloat16 *>(w_fwd),
+                                                                           static_cast<__nv_bfloat16 *>(w_dgrad), cin, cout, taps);
+    return check_launch("hg_convt_pack_weight");
+}
+
+extern "C" int hg_convt_unpack_wgrad(const float *dw_packed, float *dw, int cin, int cout, int taps, void *stream)
+{
+    HG_REQUIRE(dw_packed && dw, HG_ERR_INVALID_ARG, "hg_convt_unpack_wgrad: null pointer");
+    HG_REQUIRE(cin > 0 && cout > 0 && taps > 0, HG_ERR_INVALID_ARG, "hg_convt_unpack_wgrad: dims must be positive");
+    const size_t n = (size_t)cin * cout * taps;
+    const int grid = (int)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);
+    unpack_wgrad_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(dw_packed, dw, cin, cout, taps);
+    return check_launch("hg_convt_unpack_wgrad");
+}
+
+extern "C" int hg_convt_fwd(const void *x, const void *w_fwd, const float *bias, void *y_s2d, int batch, int cin, int cout,
+                            int ndim, int size, int kernel, float neg_slope, void *stream)
+{
+    HG_REQUIRE(x && w_fwd && y_s2d, HG_ERR_INVALID_ARG, "hg_convt_fwd: null pointer");
+    ConvShape c{batch, cin, cout, ndim, size, kernel};
+    int rc = conv_shape(c, "hg_convt_fwd");
+    if (rc) return rc;
+    const int bn = pick_bn(cout);
+    HG_REQUIRE(cin % kBK == 0 && bn >= 16, HG_ERR_UNSUPPORTED, "hg_convt_fwd: need Cin %% 64 == 0 and Cout %% 16 == 0 (got %d, %d)", cin, cout);
+    TapGemmParams p{};
+    int bx, by, bz, bb;
+    HG_REQUIRE(box_for(kBM, c.X, c.Y, c.Z, bx, by, bz, bb), HG_ERR_UNSUPPORTED, "hg_convt_fwd: spatial size %d does not tile into 128-row boxes", size);
+    rc = make_map_5d(&p.tmA, x, cin, c.X, c.Y, c.Z, batch, bx, by, bz, bb);
+    if (rc) return rc;
+    rc = make_map_2d(&p.tmB, w_fwd, cin, (long long)c.taps * cout, bn);
+    if (rc) return rc;
+    p.X = c.X; p.Y = c.Y; p.Z = c.Z; p.Bn = batch;
+    p.BN = bn; p.k_chunks = cin / kBK;
+    const long long m_total = (long long)batch * c.X * c.Y * c.Z;
+    p.m_total = (int)m_total; p.ld_out = (long long)c.P * cout; p.out = y_s2d; p.bias = bias; p.slope = neg_slope;
+    p.num_groups = c.P;
+    int ntap = 0, cur = -1;
+    for_each_class_tap(c, [&](int cls, int flat, int sx, int sy, int sz) {
+        if (cls != cur) {
+            cur = cls;
+            p.groups[cls] = Group{ntap, 0, cls * cout, 0};
+        }
+        p.taps[ntap] = Tap{(int16_t)sx, (int16_t)sy, (int16_t)sz, 0, 0, flat * cout};
+        p.groups[cls].tap_count++;
+        ntap++;
+    });
+    const int m_tiles = (int)((m_total + kBM - 1) / kBM);
+    return launch_tap_gemm(p, m_tiles, cout / bn, static_cast<cudaStream_t>(stream), "hg_convt_fwd");
+}
+
+extern "C" int hg_convt_dgrad(const void *dy_s2d, const void *w_dgrad, void *dx, int batch, int cin, int cout, int ndim,
+                              int size, int kernel, void *stream)
+{
+    HG_REQUIRE(dy_s2d && w_dgrad && dx, HG_ERR_INVALID_ARG, "hg_convt_dgrad: null pointer");
+    ConvShape c{batch, cin, cout, ndim, size, kernel};
+    int rc = conv_shape(c, "hg_convt_dgrad");
+    if (rc) return rc;
+    const int bn = pick_bn(cin);
+    HG_REQUIRE(cout % kBK == 0 && bn >= 16, HG_ERR_UNSUPPORTED, "hg_convt_dgrad: need Cout %% 64 == 0 and Cin %% 16 == 0 (got %d, %d)", cout, cin);
+    TapGemmParams p{};
+    int bx, by, bz, bb;
+    HG_REQUIRE(box_for(kBM, c.X, c.Y, c.Z, bx, by, bz, bb), HG_ERR_UNSUPPORTED, "hg_convt_dgrad: spatial size %d does not tile into 128-row boxes", size);
+    rc = make_map_5d(&p.tmA, dy_s2d, (long long)c.P * cout, c.X, c.Y, c.Z, batch, bx, by, bz, bb);
+    if (rc) return rc;
+    rc = make_map_2d(&p.tmB, w_dgrad, cout, (long long)c.taps * cin, bn);
+    if (rc) return rc;
+    p.X = c.X; p.Y = c.Y; p.Z = c.Z; p.Bn = batch;
+    p.BN = bn; p.k_chunks = cout / kBK;
+    const long long m_total = (long long)batch * c.X * c.Y * c.Z;
+    p.m_total = (int)m_total; p.ld_out = cin; p.out = dx; p.bias = nullptr; p.slope = 1.0f;
+    p.num_groups = 1;
+    int ntap = 0;
+    for_each_class_tap(c, [&](int cls, int flat, int sx, int sy, int sz) {
+        // forward: Y[2i+p] += X[i+s] W[k]   =>   dX[i'] += dY_s2d[i'-s, class p] W[k]
+        p.taps[ntap++] = Tap{(int16_t)-sx, (int16_t)-sy, (int16_t)-sz, 0, cls * cout, flat * cin};
+    });
+    p.groups[0] = Group{0, ntap, 0, 0};
+    const int m_tiles = (int)((m_total + kBM - 1) / kBM);
+    return launch_tap_gemm(p, m_tiles, cin / bn, static_cast<cudaStream_t>(stream), "hg_convt_dgrad");
+}
+
+extern "C" int hg_convt_wgrad(const void *x, const void *dy_s2d, float *dw_packed, int batch, int cin, int cout, int ndim,
+                              int size, int kernel, void *stream)
+{
+    HG_REQUIRE(x && dy_s2d && dw_packed, HG_ERR_INVALID_ARG, "hg_convt_wgrad: null pointer");
+    ConvShape c{batch, cin, cout, ndim, size, kernel};
+    int rc = conv_shape(c, "hg_convt_wgrad");
+    if (rc) return rc;
+    int bn = cout % 256 == 0 ? 256 : cout % 128 == 0 ? 128 : cout % 64 == 0 ? 64 : 0;
+    HG_REQUIRE(cin % kBM == 0 && bn > 0, HG_ERR_UNSUPPORTED, "hg_convt_wgrad: need Cin %% 128 == 0 and Cout %% 64 == 0 (got %d, %d)", cin, cout);
+    WgradParams p{};
+    int bx, by, bz, bb;
+    HG_REQUIRE(box_for(64, c.X, c.Y, c.Z, bx, by, bz, bb), HG_ERR_UNSUPPORTED, "hg_convt_wgrad: spatial size %d does not tile into 64-position boxes", size);
+    rc = make_map_5d(&p.tmX, x, cin, c.X, c.Y, c.Z, batch, bx, by, bz, bb);
+    if (rc) return rc;
+    rc = make_map_5d(&p.tmDY, dy_s2d, (long long)c.P * cout, c.X, c.Y, c.Z, batch, bx, by, bz, bb);
+    if (rc) return rc;
+    p.X = c.X; p.Y = c.Y; p.Z = c.Z; p.Bn = batch;
+    p.BN = bn; p.cin = cin; p.cout = cout; p.dw = dw_packed;
+    const long long positions = (long long)batch * c.X * c.Y * c.Z;
+    p.pos_tiles = (int)((positions + 63) / 64);
+    int np = 0;
+    for_each_class_tap(c, [&](int cls, int flat, int sx, int sy, int sz) {
+        p.pairs[np++] = WgradParams::Pair{(int16_t)sx, (int16_t)sy, (int16_t)sz, 0, cls * cout, flat};
+    });
+    p.num_pairs = np;
+    const int out_tiles = (cin / kBM) * (cout / bn) * np;
+    int splits = (2 * sm_count() + out_tiles - 1) / out_tiles;           // aim at >= 2 waves of CTAs
+    if (splits > p.pos_tiles / 8) splits = p.pos_tiles / 8;              // keep >= 8 K-iterations per CTA
+    if (splits < 1) splits = 1;
+    p.splits = splits;
+    const int stage_bytes = 2 * 64 * 128 + (bn / 64) * 64 * 128;
+    p.stages = pick_stages(stage_bytes, (p.pos_tiles + splits - 1) / splits);
+    const size_t smem = (size_t)p.stages * stage_bytes + 1024;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cudaError_t e = cudaMemsetAsync(dw_packed, 0, sizeof(float) * (size_t)c.taps * cin * cout, st);
+    if (e != cudaSuccess) return fail(HG_ERR_LAUNCH, "hg_convt_wgrad: memset failed: %s", cudaGetErrorString(e));
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(wgrad_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+        attr_set = true;
+    }
+    dim3 grid(cin / kBM, cout / bn, np * splits);
+    wgrad_gemm_kernel<<<grid, kThreads, smem, st>>>(p);
+    return check_launch("hg_convt_wgrad");
+}
