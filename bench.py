@@ -49,6 +49,7 @@ def parse_args():
     ap.add_argument("--cpu-batch", type=int, default=8, help="batch of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--no-graphs", action="store_true", help="eager launches instead of CUDA-graph replay")
     return ap.parse_args()
 
 
@@ -268,12 +269,15 @@ def main():
         trainer.step(real_dev[i % pool], i, z=z_dev[i % pool], view=a_dev[i % pool])
 
     def e2e_step(i):
-        real = real_host[i % pool].to(device, non_blocking=True)
+        # public API with HOST buffers: pinned real images, latents and views sampled on the host (like the
+        # reference, lightning_module.py:212), copied H2D inside the timed region; loss read back D2H
         z_pin.copy_(trainer.sample_noise(B))
         a_pin.copy_(ops.view_to_affine(trainer.sample_view(B)))
-        z = z_pin.to(device, non_blocking=True)
-        a = a_pin.to(device, non_blocking=True)
-        loss = trainer.step(real, i, z=z, view=a)
+        if args.no_graphs:
+            loss = trainer.step(real_host[i % pool].to(device, non_blocking=True), i,
+                                z=z_pin.to(device, non_blocking=True), view=a_pin.to(device, non_blocking=True))
+        else:
+            loss = trainer.step(real_host[i % pool], i, z=z_pin, view=a_pin)
         return float(loss)            # D2H read of the step's result
 
     def timed(fn, k):
@@ -289,6 +293,8 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return ms.item()
 
+    if not args.no_graphs:
+        trainer.enable_cuda_graphs(B)
     for i in range(max(W, 3)):
         resident_step(i)
     sampler = ClockSampler(local_rank)
@@ -313,7 +319,7 @@ def main():
         "config": {"workload": WORKLOAD if (B, S, args.dtype) == (64, 64, "bf16") else
                    f"HoloGAN {S}x{S} training step, batch {B} per GPU, {args.dtype}",
                    "img_size": S, "per_gpu_batch": B, "global_batch": B * world, "parallelism": f"dp{world}",
-                   "schedule": "[D,G,G]", "weights": "random init",
+                   "schedule": "[D,G,G]", "weights": "random init", "cuda_graphs": not args.no_graphs,
                    "l2": "no flush: one step touches >126 MB of distinct activations/gradients/weights+Adam state"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / K},

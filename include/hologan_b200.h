@@ -86,10 +86,13 @@ int hg_rotate_bwd(const void *grad_out, const float *a_inv, void *grad_vol, int 
  *            ZMapping output, :18, be used in place)
  *   y        (B, C, N) same dtype as x
  *   save_mean, save_rstd (B, C) fp32, written for the backward
+ *   biased_var: 0 = unbiased variance (N-1, the generator's AdaIn), 1 = biased (N): with scale = 1,
+ *            bias = 0, eps = 1e-5, neg_slope = 0.2 this is the discriminator's
+ *            InstanceNorm2d + LeakyReLU (core/models/hologan_discriminator.py:16-17,21-22)
  */
 int hg_adain_act_fwd(const void *x, const float *scale, const float *bias, void *y, float *save_mean,
                      float *save_rstd, int batch, int channels, int n, long long x_batch_stride,
-                     int sb_stride, float eps, float neg_slope, int dtype, void *stream);
+                     int sb_stride, float eps, float neg_slope, int biased_var, int dtype, void *stream);
 
 /* Backward of the above.  dy is the gradient w.r.t. the activated output.
  *   dx       (B, C, N), or (C, N) when x_batch_stride == 0 (summed over the batch)
@@ -98,7 +101,7 @@ int hg_adain_act_fwd(const void *x, const float *scale, const float *bias, void 
 int hg_adain_act_bwd(const void *x, const void *dy, const float *scale, const float *bias,
                      const float *save_mean, const float *save_rstd, void *dx, float *dscale, float *dbias,
                      int batch, int channels, int n, long long x_batch_stride, int sb_stride, int dsb_stride,
-                     float neg_slope, int dtype, void *stream);
+                     float neg_slope, int biased_var, int dtype, void *stream);
 
 
 /* ---- a4 / a9 / a10: transposed convolutions and the 1x1 projection as tcgen05 implicit GEMMs -------

@@ -26,9 +26,9 @@ SIGNATURES = {
     "hg_rotate_bwd": [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
                       _c_void_p],
     "hg_adain_act_fwd": [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int,
-                         _c_ll, _c_int, _c_float, _c_float, _c_int, _c_void_p],
+                         _c_ll, _c_int, _c_float, _c_float, _c_int, _c_int, _c_void_p],
     "hg_adain_act_bwd": [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
-                         _c_void_p, _c_int, _c_int, _c_int, _c_ll, _c_int, _c_int, _c_float, _c_int, _c_void_p],
+                         _c_void_p, _c_int, _c_int, _c_int, _c_ll, _c_int, _c_int, _c_float, _c_int, _c_int, _c_void_p],
     "hg_convt_pack_weight": [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p],
     "hg_convt_fwd": [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_float,
                      _c_void_p],

@@ -74,7 +74,7 @@ template <typename T, int GROUP, int ITEMS>
 __global__ void __launch_bounds__(256) adain_fwd_kernel(const T *__restrict__ x, const float *__restrict__ scale,
                                                         const float *__restrict__ bias, T *__restrict__ y,
                                                         float *__restrict__ save_mean, float *__restrict__ save_rstd,
-                                                        int BC, int C, int N, long long xbs, int sbs, float eps, float slope)
+                                                        int BC, int C, int N, long long xbs, int sbs, float eps, float slope, int biased)
 {
     constexpr int V = Vec16<T>::N;
     __shared__ float scratch[16];
@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(256) adain_fwd_kernel(const T *__restrict__ x,
         }
     }
     m2 = group_sum<GROUP>(m2, scratch + 8);
-    const float var = m2 / (float)(N - 1);               // unbiased, torch.var default (:338)
+    const float var = m2 / (float)(biased ? N : N - 1);  // unbiased = torch.var default (:338); biased = InstanceNorm2d
     const float rstd = __frsqrt_rn(var + eps);           // :339
     const float s = scale[(size_t)b * sbs + c], bb = bias[(size_t)b * sbs + c];
     if (t == 0) {
@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(256) adain_bwd_kernel(const T *__restrict__ x,
                                                         const float *__restrict__ save_mean,
                                                         const float *__restrict__ save_rstd, T *__restrict__ dx,
                                                         float *__restrict__ dscale, float *__restrict__ dbias, int B, int C,
-                                                        int N, long long xbs, int sbs, int dsbs, float slope)
+                                                        int N, long long xbs, int sbs, int dsbs, float slope, int biased)
 {
     constexpr int V = Vec16<T>::N;
     __shared__ float scratch[16];
@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(256) adain_bwd_kernel(const T *__restrict__ x,
     const int c = kConstX ? inst : inst % C;
     const int b_begin = kConstX ? 0 : inst / C;
     const int b_end = kConstX ? B : b_begin + 1;
-    const float inv_nm1 = 1.f / (float)(N - 1), inv_n = 1.f / (float)N;
+    const float inv_nm1 = 1.f / (float)(biased ? N : N - 1), inv_n = 1.f / (float)N;
 
     float xv[ITEMS][V];
     float acc[ITEMS][V];
@@ -228,16 +228,16 @@ __global__ void __launch_bounds__(256) adain_bwd_kernel(const T *__restrict__ x,
 
 template <typename T>
 static int adain_fwd_dispatch(const void *x, const float *scale, const float *bias, void *y, float *mean, float *rstd, int B,
-                              int C, int N, long long xbs, int sbs, float eps, float slope, cudaStream_t st)
+                              int C, int N, long long xbs, int sbs, float eps, float slope, int biased, cudaStream_t st)
 {
     constexpr int V = Vec16<T>::N;
     const int BC = B * C;
     const T *xp = static_cast<const T *>(x);
     T *yp = static_cast<T *>(y);
     if (N <= 32 * 4 * V) {
-        adain_fwd_kernel<T, 32, 4><<<(BC + 7) / 8, 256, 0, st>>>(xp, scale, bias, yp, mean, rstd, BC, C, N, xbs, sbs, eps, slope);
+        adain_fwd_kernel<T, 32, 4><<<(BC + 7) / 8, 256, 0, st>>>(xp, scale, bias, yp, mean, rstd, BC, C, N, xbs, sbs, eps, slope, biased);
     } else if (N <= 256 * 4 * V) {
-        adain_fwd_kernel<T, 256, 4><<<BC, 256, 0, st>>>(xp, scale, bias, yp, mean, rstd, BC, C, N, xbs, sbs, eps, slope);
+        adain_fwd_kernel<T, 256, 4><<<BC, 256, 0, st>>>(xp, scale, bias, yp, mean, rstd, BC, C, N, xbs, sbs, eps, slope, biased);
     } else {
         return fail(HG_ERR_UNSUPPORTED, "hg_adain_act_fwd: N=%d exceeds the single-pass limit %d", N, 256 * 4 * V);
     }
@@ -247,7 +247,7 @@ static int adain_fwd_dispatch(const void *x, const float *scale, const float *bi
 template <typename T>
 static int adain_bwd_dispatch(const void *x, const void *dy, const float *scale, const float *bias, const float *mean,
                               const float *rstd, void *dx, float *dscale, float *dbias, int B, int C, int N, long long xbs,
-                              int sbs, int dsbs, float slope, cudaStream_t st)
+                              int sbs, int dsbs, float slope, int biased, cudaStream_t st)
 {
     constexpr int V = Vec16<T>::N;
     const T *xp = static_cast<const T *>(x), *gp = static_cast<const T *>(dy);
@@ -257,14 +257,14 @@ static int adain_bwd_dispatch(const void *x, const void *dy, const float *scale,
     if (N <= 32 * 4 * V) {
         const int grid = (n_inst + 7) / 8;
         if (cx)
-            adain_bwd_kernel<T, 32, 4, true><<<grid, 256, 0, st>>>(xp, gp, scale, bias, mean, rstd, dp, dscale, dbias, B, C, N, xbs, sbs, dsbs, slope);
+            adain_bwd_kernel<T, 32, 4, true><<<grid, 256, 0, st>>>(xp, gp, scale, bias, mean, rstd, dp, dscale, dbias, B, C, N, xbs, sbs, dsbs, slope, biased);
         else
-            adain_bwd_kernel<T, 32, 4, false><<<grid, 256, 0, st>>>(xp, gp, scale, bias, mean, rstd, dp, dscale, dbias, B, C, N, xbs, sbs, dsbs, slope);
+            adain_bwd_kernel<T, 32, 4, false><<<grid, 256, 0, st>>>(xp, gp, scale, bias, mean, rstd, dp, dscale, dbias, B, C, N, xbs, sbs, dsbs, slope, biased);
     } else if (N <= 256 * 4 * V) {
         if (cx)
-            adain_bwd_kernel<T, 256, 4, true><<<n_inst, 256, 0, st>>>(xp, gp, scale, bias, mean, rstd, dp, dscale, dbias, B, C, N, xbs, sbs, dsbs, slope);
+            adain_bwd_kernel<T, 256, 4, true><<<n_inst, 256, 0, st>>>(xp, gp, scale, bias, mean, rstd, dp, dscale, dbias, B, C, N, xbs, sbs, dsbs, slope, biased);
         else
-            adain_bwd_kernel<T, 256, 4, false><<<n_inst, 256, 0, st>>>(xp, gp, scale, bias, mean, rstd, dp, dscale, dbias, B, C, N, xbs, sbs, dsbs, slope);
+            adain_bwd_kernel<T, 256, 4, false><<<n_inst, 256, 0, st>>>(xp, gp, scale, bias, mean, rstd, dp, dscale, dbias, B, C, N, xbs, sbs, dsbs, slope, biased);
     } else {
         return fail(HG_ERR_UNSUPPORTED, "hg_adain_act_bwd: N=%d exceeds the single-pass limit %d", N, 256 * 4 * V);
     }
@@ -277,7 +277,7 @@ using namespace hg;
 
 extern "C" int hg_adain_act_fwd(const void *x, const float *scale, const float *bias, void *y, float *save_mean,
                                 float *save_rstd, int batch, int channels, int n, long long x_batch_stride, int sb_stride,
-                                float eps, float neg_slope, int dtype, void *stream)
+                                float eps, float neg_slope, int biased_var, int dtype, void *stream)
 {
     HG_REQUIRE(x && scale && bias && y && save_mean && save_rstd, HG_ERR_INVALID_ARG, "hg_adain_act_fwd: null pointer");
     HG_REQUIRE(batch > 0 && channels > 0 && n > 0, HG_ERR_INVALID_ARG, "hg_adain_act_fwd: dims must be positive");
@@ -290,14 +290,14 @@ extern "C" int hg_adain_act_fwd(const void *x, const float *scale, const float *
     HG_REQUIRE(sb_stride >= channels, HG_ERR_INVALID_ARG, "hg_adain_act_fwd: sb_stride < channels");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (dtype == HG_F32)
-        return adain_fwd_dispatch<float>(x, scale, bias, y, save_mean, save_rstd, batch, channels, n, x_batch_stride, sb_stride, eps, neg_slope, st);
-    return adain_fwd_dispatch<__nv_bfloat16>(x, scale, bias, y, save_mean, save_rstd, batch, channels, n, x_batch_stride, sb_stride, eps, neg_slope, st);
+        return adain_fwd_dispatch<float>(x, scale, bias, y, save_mean, save_rstd, batch, channels, n, x_batch_stride, sb_stride, eps, neg_slope, biased_var, st);
+    return adain_fwd_dispatch<__nv_bfloat16>(x, scale, bias, y, save_mean, save_rstd, batch, channels, n, x_batch_stride, sb_stride, eps, neg_slope, biased_var, st);
 }
 
 extern "C" int hg_adain_act_bwd(const void *x, const void *dy, const float *scale, const float *bias, const float *save_mean,
                                 const float *save_rstd, void *dx, float *dscale, float *dbias, int batch, int channels, int n,
-                                long long x_batch_stride, int sb_stride, int dsb_stride, float neg_slope, int dtype,
-                                void *stream)
+                                long long x_batch_stride, int sb_stride, int dsb_stride, float neg_slope, int biased_var,
+                                int dtype, void *stream)
 {
     HG_REQUIRE(x && dy && scale && bias && save_mean && save_rstd && dx && dscale && dbias, HG_ERR_INVALID_ARG,
                "hg_adain_act_bwd: null pointer");
@@ -309,6 +309,6 @@ extern "C" int hg_adain_act_bwd(const void *x, const void *dy, const float *scal
     HG_REQUIRE(sb_stride >= channels && dsb_stride >= channels, HG_ERR_INVALID_ARG, "hg_adain_act_bwd: stride < channels");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (dtype == HG_F32)
-        return adain_bwd_dispatch<float>(x, dy, scale, bias, save_mean, save_rstd, dx, dscale, dbias, batch, channels, n, x_batch_stride, sb_stride, dsb_stride, neg_slope, st);
-    return adain_bwd_dispatch<__nv_bfloat16>(x, dy, scale, bias, save_mean, save_rstd, dx, dscale, dbias, batch, channels, n, x_batch_stride, sb_stride, dsb_stride, neg_slope, st);
+        return adain_bwd_dispatch<float>(x, dy, scale, bias, save_mean, save_rstd, dx, dscale, dbias, batch, channels, n, x_batch_stride, sb_stride, dsb_stride, neg_slope, biased_var, st);
+    return adain_bwd_dispatch<__nv_bfloat16>(x, dy, scale, bias, save_mean, save_rstd, dx, dscale, dbias, batch, channels, n, x_batch_stride, sb_stride, dsb_stride, neg_slope, biased_var, st);
 }

@@ -246,7 +246,11 @@ static int launch_fwd_ncdhw(const void *vol, const float *a, void *out, int B, i
 {
     const size_t smem = (size_t)CT * S * S * S * sizeof(T);
     auto k = rotate_fwd_ncdhw_kernel<T, CT, Z>;
-    if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    static bool attr_done = false;      // per template instantiation; not a stream operation (graph-capture safe)
+    if (!attr_done && smem > 48 * 1024) {
+        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr_done = true;
+    }
     dim3 grid((C + CT - 1) / CT, B);
     k<<<grid, 256, smem, st>>>(static_cast<const T *>(vol), a, static_cast<T *>(out), C, S, logS);
     return check_launch("rotate_fwd_ncdhw");
@@ -257,7 +261,11 @@ static int launch_bwd_ncdhw(const void *g, const float *a, void *gv, int B, int 
 {
     const size_t smem = (size_t)CT * S * S * S * sizeof(float);
     auto k = rotate_bwd_ncdhw_kernel<T, CT, Z>;
-    if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    static bool attr_done = false;      // per template instantiation; not a stream operation (graph-capture safe)
+    if (!attr_done && smem > 48 * 1024) {
+        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr_done = true;
+    }
     dim3 grid((C + CT - 1) / CT, B);
     k<<<grid, 256, smem, st>>>(static_cast<const T *>(g), a, static_cast<T *>(gv), C, S, logS);
     return check_launch("rotate_bwd_ncdhw");

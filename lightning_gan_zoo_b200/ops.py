@@ -189,7 +189,7 @@ def _style_stride(scale: Tensor, bias: Tensor) -> int:
 
 class _AdaInAct(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, scale, bias, neg_slope, eps):
+    def forward(ctx, x, scale, bias, neg_slope, eps, biased):
         _require_cuda(x, scale, bias)
         if not x.is_contiguous():
             x = x.contiguous()
@@ -199,25 +199,123 @@ class _AdaInAct(torch.autograd.Function):
         mean = torch.empty((b, c), dtype=torch.float32, device=x.device)
         rstd = torch.empty((b, c), dtype=torch.float32, device=x.device)
         _lib.call("hg_adain_act_fwd", _ptr(x), _ptr(scale), _ptr(bias), _ptr(y), _ptr(mean), _ptr(rstd), b, c, n, xbs,
-                  sbs, float(eps), float(neg_slope), _dtype_code(x), _stream())
+                  sbs, float(eps), float(neg_slope), int(biased), _dtype_code(x), _stream())
         ctx.save_for_backward(x, scale, bias, mean, rstd)
-        ctx.meta = (b, c, n, xbs, sbs, float(neg_slope))
+        ctx.meta = (b, c, n, xbs, sbs, float(neg_slope), int(biased))
         return y
 
     @staticmethod
     def backward(ctx, dy):
         x, scale, bias, mean, rstd = ctx.saved_tensors
-        b, c, n, xbs, sbs, neg_slope = ctx.meta
+        b, c, n, xbs, sbs, neg_slope, biased = ctx.meta
         dy = dy.contiguous()
         dx = torch.empty_like(x)
         dsb = torch.empty((2, b, c), dtype=torch.float32, device=x.device)
         _lib.call("hg_adain_act_bwd", _ptr(x), _ptr(dy), _ptr(scale), _ptr(bias), _ptr(mean), _ptr(rstd), _ptr(dx),
-                  _ptr(dsb[0]), _ptr(dsb[1]), b, c, n, xbs, sbs, c, neg_slope, _dtype_code(x), _stream())
-        return dx, dsb[0], dsb[1], None, None
+                  _ptr(dsb[0]), _ptr(dsb[1]), b, c, n, xbs, sbs, c, neg_slope, biased, _dtype_code(x), _stream())
+        return dx, dsb[0], dsb[1], None, None, None
 
 
-def adain_act(x: Tensor, scale: Tensor, bias: Tensor, neg_slope: float = 0.0, eps: float = 1e-8) -> Tensor:
+def adain_act(x: Tensor, scale: Tensor, bias: Tensor, neg_slope: float = 0.0, eps: float = 1e-8,
+              biased_var: bool = False) -> Tensor:
     """act(AdaIn(x, scale, bias)); `neg_slope=1.0` gives the plain AdaIn of the reference
     (core/models/hologan_generator.py:333-345), `0.0` fuses the ReLU of :41 / :124.
     x may have batch 1 (the learned constant): it is broadcast without being materialised."""
-    return _AdaInAct.apply(x, scale, bias, neg_slope, eps)
+    return _AdaInAct.apply(x, scale, bias, neg_slope, eps, biased_var)
+
+
+def instance_norm_act(x: Tensor, neg_slope: float = 0.2, eps: float = 1e-5) -> Tensor:
+    """InstanceNorm2d (no affine, biased variance) fused with LeakyReLU -- the discriminator's
+    norm + activation (reference core/models/hologan_discriminator.py:16-17,21-22) on the AdaIN kernel."""
+    b, c = x.shape[0], x.shape[1]
+    ones = torch.ones((b, c), dtype=torch.float32, device=x.device)
+    zeros = torch.zeros((b, c), dtype=torch.float32, device=x.device)
+    return _AdaInAct.apply(x, ones, zeros, neg_slope, eps, True)
+
+
+# ------------------------------------------------------------------------------------------------
+# a4 / a9 / a10: transposed convolutions on the tcgen05 implicit-GEMM kernels
+# ------------------------------------------------------------------------------------------------
+
+def convt_supported(cin: int, cout: int) -> bool:
+    """Shapes the tcgen05 path covers (fwd + dgrad + wgrad): Cin % 128 == 0 and Cout % 64 == 0."""
+    return cin % 128 == 0 and cout % 64 == 0
+
+
+def pack_convt_weight(weight: Tensor) -> Tuple[Tensor, Tensor]:
+    """torch ConvTranspose weight (Cin, Cout, k..) fp32 -> (w_fwd [t][Cout][Cin], w_dgrad [t][Cin][Cout]) bf16."""
+    _require_cuda(weight)
+    w = weight.detach().float().contiguous()
+    cin, cout = w.shape[0], w.shape[1]
+    taps = w[0, 0].numel()
+    wf = torch.empty((taps, cout, cin), dtype=torch.bfloat16, device=w.device)
+    wd = torch.empty((taps, cin, cout), dtype=torch.bfloat16, device=w.device)
+    _lib.call("hg_convt_pack_weight", _ptr(w), _ptr(wf), _ptr(wd), cin, cout, taps, _stream())
+    return wf, wd
+
+
+def _conv_dims(x_cl: Tensor, ndim: int):
+    if x_cl.dtype != torch.bfloat16 or not x_cl.is_contiguous() or x_cl.dim() != ndim + 2:
+        raise ValueError("activations must be contiguous channels-last bf16 tensors (B, [S,] S, S, C)")
+    return x_cl.shape[0], x_cl.shape[1], x_cl.shape[-1]
+
+
+class _ConvT(torch.autograd.Function):
+    """y_s2d = act(convT(x) + bias) with x (B,[S,]S,S,Cin) bf16 and y_s2d (B,[S,]S,S,P,Cout) bf16."""
+
+    @staticmethod
+    def forward(ctx, x_cl, weight, bias, ndim, kernel, neg_slope):
+        _require_cuda(x_cl, weight)
+        b, size, cin = _conv_dims(x_cl, ndim)
+        cout = weight.shape[1]
+        if weight.shape[0] != cin:
+            raise ValueError("weight / activation channel mismatch")
+        wf, wd = pack_convt_weight(weight)
+        nclass = 1 if kernel == 1 else 2 ** ndim
+        y = torch.empty((b,) + (size,) * ndim + (nclass, cout), dtype=torch.bfloat16, device=x_cl.device)
+        bias_f = None if bias is None else bias.detach().float().contiguous()
+        _lib.call("hg_convt_fwd", _ptr(x_cl), _ptr(wf), _ptr(bias_f), _ptr(y), b, cin, cout, ndim, size, kernel,
+                  ctypes.c_float(neg_slope), _stream())
+        ctx.save_for_backward(x_cl, wd, y if neg_slope != 1.0 else None)
+        ctx.meta = (b, cin, cout, ndim, size, kernel, neg_slope, tuple(weight.shape), bias is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x_cl, wd, y = ctx.saved_tensors
+        b, cin, cout, ndim, size, kernel, neg_slope, wshape, has_bias = ctx.meta
+        dy = dy.contiguous()
+        if y is not None:                      # activation fused in the forward epilogue
+            dy = torch.where(y > 0, dy, dy * neg_slope)
+        taps = kernel ** ndim
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x_cl)
+            _lib.call("hg_convt_dgrad", _ptr(dy), _ptr(wd), _ptr(dx), b, cin, cout, ndim, size, kernel, _stream())
+        if ctx.needs_input_grad[1]:
+            dwp = torch.empty((taps, cin, cout), dtype=torch.float32, device=dy.device)
+            _lib.call("hg_convt_wgrad", _ptr(x_cl), _ptr(dy), _ptr(dwp), b, cin, cout, ndim, size, kernel, _stream())
+            dw = torch.empty(wshape, dtype=torch.float32, device=dy.device)
+            _lib.call("hg_convt_unpack_wgrad", _ptr(dwp), _ptr(dw), cin, cout, taps, _stream())
+        if has_bias and ctx.needs_input_grad[2]:
+            db = dy.reshape(-1, dy.shape[-2], cout).float().sum(dim=(0, 1))
+        return dx, dw, db, None, None, None
+
+
+def convt(x_cl: Tensor, weight: Tensor, bias: Optional[Tensor], ndim: int, kernel: int, neg_slope: float = 1.0) -> Tensor:
+    return _ConvT.apply(x_cl, weight, bias, ndim, kernel, neg_slope)
+
+
+# ---- layout glue (pure data movement) -------------------------------------------------------------
+
+def s2d_to_nc(y_s2d: Tensor, ndim: int) -> Tensor:
+    """(B,[S,]S,S,P,C) space-to-depth conv output -> torch layout (B,C,2S,[2S,]2S)."""
+    b, s, c = y_s2d.shape[0], y_s2d.shape[1], y_s2d.shape[-1]
+    if ndim == 2:
+        return y_s2d.reshape(b, s, s, 2, 2, c).permute(0, 5, 1, 3, 2, 4).reshape(b, c, 2 * s, 2 * s)
+    return y_s2d.reshape(b, s, s, s, 2, 2, 2, c).permute(0, 7, 1, 4, 2, 5, 3, 6).reshape(b, c, 2 * s, 2 * s, 2 * s)
+
+
+def nc_to_channels_last(x: Tensor) -> Tensor:
+    """(B,C,*sp) -> contiguous (B,*sp,C)."""
+    return x.permute(0, *range(2, x.dim()), 1).contiguous()

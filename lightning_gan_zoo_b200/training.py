@@ -23,7 +23,7 @@ import torch
 import torch.distributed as dist
 import torch.nn.functional as F
 
-from . import ops
+from . import _lib, ops
 from .core.models.hologan_discriminator import Discriminator
 from .core.models.hologan_generator import Generator
 
@@ -101,9 +101,14 @@ class HologanTrainer:
                 dist.broadcast(t, src=0)
         self.d_grads = _FlatGrads(self.discriminator.parameters())
         self.g_grads = _FlatGrads(self.generator.parameters())
-        fused = self.device.type == "cuda"
-        self.opt_d = torch.optim.Adam(self.discriminator.parameters(), lr=cfg.lr, betas=(cfg.beta1, cfg.beta2), fused=fused)
-        self.opt_g = torch.optim.Adam(self.generator.parameters(), lr=cfg.lr, betas=(cfg.beta1, cfg.beta2), fused=fused)
+        cuda = self.device.type == "cuda"
+        # fused multi-tensor Adam; capturable (device-side step counter, tensor lr) so that a whole
+        # optimizer step can live inside a CUDA graph
+        lr = torch.tensor(cfg.lr, device=self.device) if cuda else cfg.lr
+        kw = dict(betas=(cfg.beta1, cfg.beta2), fused=cuda, capturable=cuda)
+        self.opt_d = torch.optim.Adam(self.discriminator.parameters(), lr=lr, **kw)
+        self.opt_g = torch.optim.Adam(self.generator.parameters(), lr=lr.clone() if cuda else lr, **kw)
+        self._graphs = None
         lam = hologan_lr_lambda(cfg.num_epochs)
         self.sched_d = torch.optim.lr_scheduler.LambdaLR(self.opt_d, lam)
         self.sched_g = torch.optim.lr_scheduler.LambdaLR(self.opt_g, lam)
@@ -160,13 +165,19 @@ class HologanTrainer:
         return loss_g + q
 
     def step(self, real: torch.Tensor, batch_idx: int, z: Optional[torch.Tensor] = None, view=None) -> torch.Tensor:
-        """One optimizer step of the [D, G, G] schedule on one batch; returns the (detached) loss."""
+        """One optimizer step of the [D, G, G] schedule on one batch; returns the (detached) loss.
+        `view` may be a (B,6) host array or a (B,4,4) tensor of precomputed inverse transforms."""
         idx = optimizer_index(batch_idx, self.cfg.disc_freq, self.cfg.gen_freq)
         n = real.shape[0]
         if z is None:
             z = self.sample_noise(n).to(self.device, non_blocking=True)
         if view is None:
             view = self.sample_view(n)
+        if self._graphs is not None and n == self._static["real"].shape[0]:
+            return self._replay(real, z, view, idx)
+        return self._eager_step(real, z, view, idx)
+
+    def _eager_step(self, real, z, view, idx):
         grads, opt = (self.d_grads, self.opt_d) if idx == 0 else (self.g_grads, self.opt_g)
         # Lightning's toggle_optimizer: only the stepped network's parameters require grad
         for p in self.discriminator.parameters():
@@ -177,6 +188,61 @@ class HologanTrainer:
         grads.all_reduce_mean(self.world)
         opt.step()
         return loss.detach()
+
+    # ---- CUDA graphs: the whole step (forward, backward, gradient all-reduce, Adam) replayed as one launch ----
+    def enable_cuda_graphs(self, batch_size: Optional[int] = None) -> None:
+        """Capture one graph per optimizer index on static input buffers.  The eager steps that stream
+        capture needs as warm-up are rolled back, so enabling graphs does not change the training state."""
+        if self.device.type != "cuda":
+            raise RuntimeError("CUDA graphs need a CUDA device")
+        b = batch_size or self.cfg.batch_size
+        s = self.cfg.img_size
+        self._static = {"real": torch.zeros(b, self.cfg.channels_img, s, s, device=self.device),
+                        "z": torch.zeros(b, self.cfg.noise_dim, device=self.device),
+                        "a": torch.eye(4, device=self.device).repeat(b, 1, 1)}
+        st = self._static
+        opts = (self.opt_d, self.opt_g)
+        model_t = list(self.generator.state_dict().values()) + list(self.discriminator.state_dict().values())
+        model_saved = [t.clone() for t in model_t]
+        fresh = [len(o.state) == 0 for o in opts]       # torch creates Adam state lazily at the first step
+        opt_saved = [None if f else {id(p): {k: v.clone() for k, v in stt.items() if isinstance(v, torch.Tensor)}
+                                     for p, stt in o.state.items()} for o, f in zip(opts, fresh)]
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            for idx in (0, 1, 1):
+                self._eager_step(st["real"], st["z"], st["a"], idx)
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        graphs = {}
+        for idx in (0, 1):
+            g = torch.cuda.CUDAGraph()
+            n0 = _lib.launch_count
+            with torch.cuda.graph(g):
+                loss = self._eager_step(st["real"], st["z"], st["a"], idx)
+            graphs[idx] = (g, loss, _lib.launch_count - n0)
+        with torch.no_grad():
+            for t, v in zip(model_t, model_saved):
+                t.copy_(v)
+            for o, f, saved in zip(opts, fresh, opt_saved):
+                for p, stt in o.state.items():
+                    for k, v in stt.items():
+                        if isinstance(v, torch.Tensor):
+                            v.zero_() if f else v.copy_(saved[id(p)][k])
+        self._graphs = graphs
+
+    def _replay(self, real, z, view, idx):
+        st = self._static
+        st["real"].copy_(real, non_blocking=True)
+        st["z"].copy_(z, non_blocking=True)
+        if isinstance(view, torch.Tensor) and view.dim() == 3:
+            st["a"].copy_(view, non_blocking=True)
+        else:
+            size = 16
+            st["a"].copy_(ops.view_to_affine(view, size, size), non_blocking=True)
+        g, loss, launches = self._graphs[idx]
+        g.replay()
+        _lib.launch_count += launches          # kernels of libhologan_b200.so inside the replayed graph
+        return loss
 
     def end_epoch(self):
         self.sched_d.step()

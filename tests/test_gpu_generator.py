@@ -65,3 +65,60 @@ def test_generator_accepts_tensor_views_and_samples_views():
     assert tuple(c.shape) == (4, 3, 64, 64) and c.abs().max() <= 1
     net128 = Generator(8, 3, 128, va, 128).to(DEV)
     assert tuple(net128(z).shape) == (4, 3, 128, 128)
+
+
+def _bf16_errors(net, p, z, view, dout):
+    zg = z.to(DEV).requires_grad_(True)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        out = net(zg, view_in=view)
+    (out.float() * dout.to(DEV)).sum().backward()
+    return out, zg.grad, dict(net.named_parameters())
+
+
+def test_generator_bf16_tensor_core_path_vs_oracle():
+    """Full-width generator (in_planes 64) under bf16 autocast: tcgen05 convs + AdaIN + rotate, forward
+    and backward, against the fp32 oracle.
+
+    Tolerances (max|a-b| / max|b|):
+      * activations (output image): north_star's 2e-2;
+      * gradients: bf16 rounding of the stored activations / gradients is amplified by every AdaIN backward
+        (it projects out the mean and x_hat components of the incoming gradient, which carry most of its
+        energy), so even stock PyTorch bf16 autocast (cuDNN convs) sits at 5-14 % for the deep layers on this
+        network (tools/bf16_error_report.py).  The bar here: 2e-2 where the stock bf16 path reaches it,
+        otherwise per tensor no worse than 2x, and on average over all tensors no worse than 1.15x, the
+        stock bf16 path's error on the same inputs (single-sample errors scatter by ~1.5x).
+    """
+    gen = torch.Generator().manual_seed(77)
+    p = orc.init_generator_params(64, 3, 128, 64, generator=gen, bias_std=0.05)
+    bsz = 4
+    z = torch.rand(bsz, 128, generator=gen) * 2 - 1
+    view = orc.sample_view(bsz, np.random.RandomState(77))
+    dout = torch.randn(bsz, 3, 64, 64, generator=gen)
+    pr = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    zr = z.clone().requires_grad_(True)
+    ref = orc.generator_forward(pr, zr, view)
+    (ref * dout).sum().backward()
+
+    net = Generator(64, 3, 128, SimpleNamespace(), 64).to(DEV)
+    net.load_state_dict(p)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        assert net._use_tensor_core_path(z.to(DEV))
+    out, dz, named = _bf16_errors(net, p, z, view, dout)
+    stock = Generator(64, 3, 128, SimpleNamespace(), 64).to(DEV)
+    stock.load_state_dict(p)
+    stock._use_tensor_core_path = lambda _z: False          # same module on torch/cuDNN bf16 convs
+    out_s, dz_s, named_s = _bf16_errors(stock, p, z, view, dout)
+
+    assert rel_err(out.float(), ref) < 2e-2
+    ours, theirs = {"dz": rel_err(dz, zr.grad)}, {"dz": rel_err(dz_s, zr.grad)}
+    for k, v in pr.items():
+        if k.endswith("convTranspose.bias"):
+            assert named[k].grad is None or named[k].grad.abs().max() == 0      # analytically zero
+            continue
+        ours[k], theirs[k] = rel_err(named[k].grad, v.grad), rel_err(named_s[k].grad, v.grad)
+    bad = {k: (ours[k], theirs[k]) for k in ours if ours[k] > max(2e-2, 2.0 * theirs[k])}
+    assert not bad, bad
+    mean_ours, mean_theirs = sum(ours.values()) / len(ours), sum(theirs.values()) / len(theirs)
+    assert mean_ours <= 1.15 * mean_theirs, (mean_ours, mean_theirs)
+    assert rel_err(named["final_layer.weight"].grad, pr["final_layer.weight"].grad) < 2e-2
+    assert rel_err(named["block4.zMapping.linear1.weight"].grad, pr["block4.zMapping.linear1.weight"].grad) < 3e-2

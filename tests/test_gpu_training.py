@@ -1,0 +1,100 @@
+"""Discriminator mirror + training-step harness on the GPU against the reference's golden step."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, params_sha, rel_err, sha16
+from lightning_gan_zoo_b200 import ops
+from lightning_gan_zoo_b200.core.models.hologan_discriminator import Discriminator
+from lightning_gan_zoo_b200.training import HologanConfig, HologanTrainer, optimizer_index
+from oracle import hologan_oracle as orc
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+@pytest.fixture(autouse=True)
+def _strict_fp32():
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def _load_d(dp, out_planes):
+    d = Discriminator(3, out_planes, 128).to(DEV)
+    sd = {k: v.clone() for k, v in dp.items()}
+    sd.update({k.replace(".conv2d.", ".conv2d_spec_norm."): v for k, v in sd.items() if k.startswith("blocks.")})
+    d.load_state_dict(sd)
+    return d
+
+
+def test_training_step_fp32_vs_reference_golden():
+    """HOLOGAN.training_step for both optimizer indices (tiny widths) against the reference's losses,
+    gradients and spectral-norm buffers; D's InstanceNorm+LeakyReLU runs on the fused kernel."""
+    g = load_golden("train_step_tiny.npz")
+    gen = torch.Generator().manual_seed(int(g["seed"]))
+    dp = orc.init_discriminator_params(3, 8, 128, 64, generator=gen)
+    gp = orc.init_generator_params(8, 3, 128, 64, generator=gen, bias_std=0.05)
+    if params_sha(dp) != str(g["d_params_sha"]) or params_sha(gp) != str(g["g_params_sha"]):
+        pytest.skip("torch CPU RNG stream differs from the fixture's")
+    real = torch.rand(4, 3, 64, 64, generator=gen) * 2 - 1
+    assert sha16(real) == str(g["real_sha"])
+    cfg = HologanConfig(batch_size=4, gen_in_planes=8, disc_out_planes=8)
+    tr = HologanTrainer(cfg, device=DEV, compute_dtype=torch.float32)
+    tr.generator.load_state_dict(gp)
+    tr.discriminator = _load_d(dp, 8)
+    z = torch.from_numpy(g["z"]).to(DEV)
+    for p in tr.discriminator.parameters():
+        p.requires_grad_(True)
+    loss_d = tr.training_step(real.to(DEV), z, g["view"], 0)
+    assert abs(loss_d.item() - float(g["loss_d"])) < 2e-6
+    loss_d.backward()
+    named = dict(tr.discriminator.named_parameters())
+    for k, (s, a) in zip([str(k) for k in g["d_grad_keys"]], g["d_grad_summary"]):
+        if k.startswith("blocks.") and k.endswith("conv2d.bias"):
+            continue
+        got = named[k].grad.double().abs().sum().item()
+        assert abs(got - a) <= 1e-4 * a, (k, got, a)
+    for i in range(3):
+        assert np.allclose(tr.discriminator.blocks[i].conv2d.weight_u.cpu().numpy(), g[f"u_after_dstep_{i}"], atol=1e-6)
+    for p in tr.discriminator.parameters():
+        p.requires_grad_(False)
+    loss_g = tr.training_step(None, z, g["view"], 1)
+    assert abs(loss_g.item() - float(g["loss_g"])) < 2e-6
+    loss_g.backward()
+    named = dict(tr.generator.named_parameters())
+    for k, (s, a) in zip([str(k) for k in g["g_grad_keys"]], g["g_grad_summary"]):
+        if k.endswith("convTranspose.bias"):
+            continue
+        got = named[k].grad.double().abs().sum().item()
+        assert abs(got - a) <= 2e-4 * a, (k, got, a)
+
+
+def test_schedule_and_lr():
+    assert [optimizer_index(i) for i in range(7)] == [0, 1, 1, 0, 1, 1, 0]
+    from lightning_gan_zoo_b200.training import hologan_lr_lambda
+    f = hologan_lr_lambda(25)
+    assert f(0) == 1.0 and f(12) == 1.0 and abs(f(13) - (1 - 0.5 / 12.5)) < 1e-12 and abs(f(25)) < 1e-12
+
+
+def test_cuda_graph_step_matches_eager():
+    """Graph replay of the whole step == eager launches (same kernels, same order), and enabling graphs
+    leaves the training state untouched."""
+    cfg = HologanConfig(batch_size=8)
+    a = HologanTrainer(cfg, device=DEV, seed=3)
+    b = HologanTrainer(cfg, device=DEV, seed=3)
+    b.enable_cuda_graphs(8)
+    for pa, pb in zip(a.generator.parameters(), b.generator.parameters()):
+        assert torch.equal(pa, pb)
+    gen = torch.Generator().manual_seed(0)
+    for i in range(6):
+        real = (torch.rand(8, 3, 64, 64, generator=gen) * 2 - 1).to(DEV)
+        z = (torch.rand(8, 128, generator=gen) * 2 - 1).to(DEV)
+        view = orc.sample_view(8, np.random.RandomState(i))
+        la = a.step(real, i, z=z, view=view)
+        lb = b.step(real, i, z=z, view=view)
+        assert abs(la.item() - lb.item()) < 5e-3 * max(1.0, abs(la.item())), (i, la.item(), lb.item())
+    worst = max(rel_err(pb, pa) for pa, pb in zip(a.generator.parameters(), b.generator.parameters()) if pa.numel() > 1)
+    assert worst < 5e-2

@@ -69,10 +69,10 @@ def adain():
             code = ops._dtype_code(xs[0])
 
             def f(x):
-                _lib.call("hg_adain_act_fwd", P(x), P(s), P(bb), P(y), P(mean), P(rstd), b, c, n, c * n, c, 1e-8, 0.0, code, ops._stream())
+                _lib.call("hg_adain_act_fwd", P(x), P(s), P(bb), P(y), P(mean), P(rstd), b, c, n, c * n, c, 1e-8, 0.0, 0, code, ops._stream())
 
             def g(x):
-                _lib.call("hg_adain_act_bwd", P(x), P(y), P(s), P(bb), P(mean), P(rstd), P(dx), P(ds), P(db), b, c, n, c * n, c, c, 0.0, code, ops._stream())
+                _lib.call("hg_adain_act_bwd", P(x), P(y), P(s), P(bb), P(mean), P(rstd), P(dx), P(ds), P(db), b, c, n, c * n, c, c, 0.0, 0, code, ops._stream())
             tf = time_rot(f, xs); tb = time_rot(g, xs)
             fb, bbt = 2 * b * c * n * es, 3 * b * c * n * es
             print(f"adain ({b},{c},{n}) {str(dt)[6:]:8s} fwd {tf*1e6:7.1f} us {fb/tf/1e9:6.0f} GB/s ({fb/tf/1e9/PEAK*100:4.1f}%)"
