@@ -39,8 +39,10 @@ typedef enum { HG_F32 = 0, HG_BF16 = 1 } hg_dtype_t;
 typedef enum {
     HG_NCDHW = 0,   /* (B, C, S, S, S)                                                     */
     HG_NDHWC = 1,   /* (B, S, S, S, C)   channels-last                                     */
-    HG_PROJ = 2     /* (B, S, S, C*S): [b, z, x, c*S + (S-1-y)] -- the depth-into-channels  *
-                     * fold of hologan_generator.py:130-133, stored channels-last (NHWC)    */
+    HG_PROJ = 2     /* (B, S, S, S, C) ordered [b, z, x, y, c]: the depth-into-channels fold of  *
+                     * hologan_generator.py:130-133 as the A operand of the 1x1 projection  *
+                     * GEMM -- row (b, z, x), K index y*C + c, which pairs with the          *
+                     * reference's folded channel c*S + j at y = S-1-j                       */
 } hg_layout_t;
 
 /* How samples whose source coordinate leaves [0, S-1) are produced. */
@@ -60,7 +62,8 @@ const char *hg_last_error(void);
  * reshape of :130-133.
  *   vol      (B,C,S,S,S) in `in_layout`, element type `dtype`
  *   a_inv    (B,4,4) fp32 row-major: inverse(Tn @ M @ Tc) of :219-221 (rows 0..2 are used)
- *   out      same element type, `out_layout`, S' == S
+ *   out      same element type, `out_layout`, S' == S.  Supported layout pairs: NCDHW -> NCDHW
+ *            (fp32 / bf16, S in {8,16,32}) and NDHWC -> NDHWC | PROJ (bf16, channels = 8 * 2^k <= 256)
  *   coords_dbg (optional, may be NULL) (3,B,S^3) fp32: x,y,z source coordinates  ("grid coordinates")
  *   idx_dbg    (optional, may be NULL) (8,B,S^3) int32: flat corner indices a..h incl. the batch
  *              base b*S^3, i.e. idx_a..idx_h of :278-287                        ("sampling indices")
@@ -70,10 +73,15 @@ int hg_rotate_fwd(const void *vol, const float *a_inv, void *out, float *coords_
                   int border, void *stream);
 
 /* Adjoint of hg_rotate_fwd w.r.t. `vol` (what autograd derives from :292-320).  grad_out is in the
- * forward's out_layout, grad_vol in the forward's in_layout; grad_vol is fully overwritten.
- * Deterministic, no global atomics. */
-int hg_rotate_bwd(const void *grad_out, const float *a_inv, void *grad_vol, int batch, int channels,
-                  int size, int in_layout, int out_layout, int dtype, int border, void *stream);
+ * forward's out_layout, grad_vol in the forward's in_layout; grad_vol is fully overwritten.  No global
+ * atomics.  The channels-last path (in_layout == HG_NDHWC) is a deterministic gather and needs a
+ * scratch buffer of hg_rotate_bwd_workspace_bytes() bytes (per-sample cell tables); the NCDHW path
+ * needs none (workspace may be NULL).  Out-of-range samples contribute exactly 0 in both border
+ * modes (the reference's pairwise-cancelling terms, |residue| ~1e-7). */
+long long hg_rotate_bwd_workspace_bytes(int batch, int size, int in_layout);
+int hg_rotate_bwd(const void *grad_out, const float *a_inv, void *grad_vol, void *workspace,
+                  long long workspace_bytes, int batch, int channels, int size, int in_layout, int out_layout,
+                  int dtype, int border, void *stream);
 
 /* ---- a1 + a3 (+ activation): adaptive instance norm ---------------------------------------------
  * Replaces AdaIn (core/models/hologan_generator.py:333-345) fused with the ReLU that follows every
@@ -103,6 +111,18 @@ int hg_adain_act_bwd(const void *x, const void *dy, const float *scale, const fl
                      int batch, int channels, int n, long long x_batch_stride, int sb_stride, int dsb_stride,
                      float neg_slope, int biased_var, int dtype, void *stream);
 
+
+/* Channels-last AdaIN(+activation) for the bf16 pipeline (same arithmetic as hg_adain_act_*).
+ *   x  (B, S^ndim, classes, C) bf16: the space-to-depth output of hg_convt_fwd (classes = 2^ndim), or a
+ *      plain channels-last tensor (classes = 1)
+ *   y  (B, (2S)^ndim, C) bf16 plain channels-last (the depth-to-space shuffle happens in the store);
+ *      dy has y's layout, dx has x's layout.  C % 16 == 0, S^ndim * classes <= 4096. */
+int hg_adain_cl_fwd(const void *x, const float *scale, const float *bias, void *y, float *save_mean, float *save_rstd,
+                    int batch, int channels, int ndim, int size, int classes, int sb_stride, float eps, float neg_slope,
+                    void *stream);
+int hg_adain_cl_bwd(const void *x, const void *dy, const float *scale, const float *bias, const float *save_mean,
+                    const float *save_rstd, void *dx, float *dscale, float *dbias, int batch, int channels, int ndim,
+                    int size, int classes, int sb_stride, int dsb_stride, float neg_slope, void *stream);
 
 /* ---- a4 / a9 / a10: transposed convolutions and the 1x1 projection as tcgen05 implicit GEMMs -------
  * Replace nn.ConvTranspose3d(k3,s2,p1,op1) / nn.ConvTranspose2d(k4,s2,p1) / nn.ConvTranspose2d(k1)

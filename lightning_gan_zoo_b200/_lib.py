@@ -23,8 +23,13 @@ SIGNATURES = {
     "hg_last_error": [],
     "hg_rotate_fwd": [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int,
                       _c_int, _c_int, _c_void_p],
-    "hg_rotate_bwd": [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
-                      _c_void_p],
+    "hg_rotate_bwd_workspace_bytes": [_c_int, _c_int, _c_int],
+    "hg_rotate_bwd": [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_ll, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
+                      _c_int, _c_void_p],
+    "hg_adain_cl_fwd": [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int,
+                        _c_int, _c_int, _c_float, _c_float, _c_void_p],
+    "hg_adain_cl_bwd": [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
+                        _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_float, _c_void_p],
     "hg_adain_act_fwd": [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int,
                          _c_ll, _c_int, _c_float, _c_float, _c_int, _c_int, _c_void_p],
     "hg_adain_act_bwd": [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
@@ -37,7 +42,7 @@ SIGNATURES = {
     "hg_convt_unpack_wgrad": [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p],
     "hg_gemm_bf16_nt": [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_ll, _c_float, _c_void_p],
 }
-_RESTYPES = {"hg_last_error": ctypes.c_char_p}
+_RESTYPES = {"hg_last_error": ctypes.c_char_p, "hg_rotate_bwd_workspace_bytes": ctypes.c_longlong}
 
 _lib = None
 _lock = threading.Lock()

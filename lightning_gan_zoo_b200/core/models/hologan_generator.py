@@ -148,28 +148,28 @@ class Generator(nn.Module):
         n = z.shape[0]
         s0, b0 = self.zMapping(z)
         h0 = ops.adain_act(self.x, s0, b0, neg_slope=0.0)                        # (B,8P,4,4,4) fp32, NC*
-        h = ops.nc_to_channels_last(h0.to(bf16))
+        h = ops.nc_to_channels_last(h0.to(bf16))                                 # (B,4,4,4,8P)
         for block in (self.block1, self.block2):
             y = ops.convt(h, block.convTranspose.weight, None, 3, 3)             # (B,S,S,S,8,Cout) s2d
             sc, bi = block.zMapping(z)
-            hn = ops.adain_act(ops.s2d_to_nc(y, 3).contiguous(), sc, bi, neg_slope=0.0)   # NCDHW bf16
-            h = ops.nc_to_channels_last(hn) if block is self.block1 else hn
-        size = h.shape[2]
+            h = ops.adain_act_channels_last(y, sc, bi, ndim=3, classes=8)        # (B,2S,2S,2S,Cout) NDHWC
+        size = h.shape[1]
         a_inv = self._affine(view_in, size, size, z.device)
-        rot = ops.rotate_resample(h, a_inv, ops.HG_BORDER_ZERO)                  # NCDHW bf16
-        # projection operand [b, z, x, (y, c)]; the reference's fold index c*S + j pairs with y = S-1-j
-        a_proj = rot.permute(0, 2, 4, 3, 1).reshape(n, size, size, -1).contiguous()
-        c = rot.shape[1]
+        # rotate + fold depth into channels in one kernel: out[b, z, x, (y, c)] is the projection's A operand
+        rot = ops.rotate_resample(h, a_inv, ops.HG_BORDER_ZERO, ops.HG_NDHWC, ops.HG_PROJ)
+        c = rot.shape[-1]
+        a_proj = rot.reshape(n, size, size, size * c)
         w = self.convTranspose2d1.weight
+        # K index of the operand is y*C + c; the reference's folded channel c*S + j pairs with y = S-1-j
         w_perm = w.reshape(c, size, w.shape[1]).flip(1).permute(1, 0, 2).reshape(c * size, w.shape[1], 1, 1)
         h = ops.convt(a_proj, w_perm, self.convTranspose2d1.bias, 2, 1, neg_slope=0.0)   # 1x1 conv + bias + ReLU
         h = h.reshape(n, size, size, -1)
         for block in (self.block3, self.block4):
             y = ops.convt(h, block.convTranspose.weight, None, 2, 4)             # (B,S,S,4,Cout) s2d
             sc, bi = block.zMapping(z)
-            hn = ops.adain_act(ops.s2d_to_nc(y, 2).contiguous(), sc, bi, neg_slope=0.0)   # NCHW bf16
-            h = ops.nc_to_channels_last(hn) if block is self.block3 else hn
-        return torch.tanh(self.final_layer(h))
+            h = ops.adain_act_channels_last(y, sc, bi, ndim=2, classes=4)        # (B,2S,2S,Cout) NHWC
+        # final conv + tanh: cuDNN consumes the NHWC buffer as a channels_last-strided NCHW view (no copy)
+        return torch.tanh(self.final_layer(h.permute(0, 3, 1, 2)))
 
     def forward(self, z, view_in=None):
         batch_size = z.shape[0]

@@ -115,7 +115,7 @@ def rotate_fwd_raw(vol: Tensor, a_inv: Tensor, border: int = HG_BORDER_REFERENCE
     elif out_layout == HG_NDHWC:
         out = torch.empty((b, s, s, s, c), dtype=vol.dtype, device=vol.device)
     else:
-        out = torch.empty((b, s, s, c * s), dtype=vol.dtype, device=vol.device)
+        out = torch.empty((b, s, s, s, c), dtype=vol.dtype, device=vol.device)       # [b, z, x, y, c]
     coords = idx = None
     if debug:
         coords = torch.empty((3, b, s ** 3), dtype=torch.float32, device=vol.device)
@@ -132,8 +132,10 @@ def rotate_bwd_raw(grad_out: Tensor, a_inv: Tensor, channels: int, size: int, bo
     b, c, s = grad_out.shape[0], channels, size
     shape = (b, c, s, s, s) if in_layout == HG_NCDHW else (b, s, s, s, c)
     grad_vol = torch.empty(shape, dtype=grad_out.dtype, device=grad_out.device)
-    _lib.call("hg_rotate_bwd", _ptr(grad_out), _ptr(a_inv), _ptr(grad_vol), b, c, s, in_layout, out_layout,
-              _dtype_code(grad_out), border, _stream())
+    ws_bytes = _lib.load().hg_rotate_bwd_workspace_bytes(b, s, in_layout)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=grad_out.device) if ws_bytes else None
+    _lib.call("hg_rotate_bwd", _ptr(grad_out), _ptr(a_inv), _ptr(grad_vol), _ptr(ws), ws_bytes, b, c, s, in_layout,
+              out_layout, _dtype_code(grad_out), border, _stream())
     return grad_vol
 
 
@@ -143,6 +145,7 @@ class _RotateResample(torch.autograd.Function):
         ctx.save_for_backward(a_inv)
         ctx.meta = (border, in_layout, out_layout,
                     vol.shape[1] if in_layout == HG_NCDHW else vol.shape[4], vol.shape[2])
+        ctx.set_materialize_grads(True)
         return rotate_fwd_raw(vol, a_inv, border, in_layout, out_layout)
 
     @staticmethod
@@ -319,3 +322,45 @@ def s2d_to_nc(y_s2d: Tensor, ndim: int) -> Tensor:
 def nc_to_channels_last(x: Tensor) -> Tensor:
     """(B,C,*sp) -> contiguous (B,*sp,C)."""
     return x.permute(0, *range(2, x.dim()), 1).contiguous()
+
+
+# ------------------------------------------------------------------------------------------------
+# channels-last AdaIN (+activation) on conv outputs in space-to-depth layout
+# ------------------------------------------------------------------------------------------------
+
+class _AdaInChannelsLast(torch.autograd.Function):
+    """x (B,[S,]S,S,P,C) bf16 (s2d conv output, P = 2^ndim) or (B,[S,]S,S,C) (P = 1)  ->
+    y (B,[2S,]2S,2S,C) bf16 channels-last."""
+
+    @staticmethod
+    def forward(ctx, x, scale, bias, ndim, classes, neg_slope, eps):
+        _require_cuda(x, scale, bias)
+        if x.dtype != torch.bfloat16 or not x.is_contiguous():
+            raise ValueError("x must be a contiguous bf16 tensor")
+        b, size, c = x.shape[0], x.shape[1], x.shape[-1]
+        sbs = _style_stride(scale, bias)
+        up = 2 if classes > 1 else 1
+        y = torch.empty((b,) + (up * size,) * ndim + (c,), dtype=torch.bfloat16, device=x.device)
+        mean = torch.empty((b, c), dtype=torch.float32, device=x.device)
+        rstd = torch.empty((b, c), dtype=torch.float32, device=x.device)
+        _lib.call("hg_adain_cl_fwd", _ptr(x), _ptr(scale), _ptr(bias), _ptr(y), _ptr(mean), _ptr(rstd), b, c, ndim, size,
+                  classes, sbs, ctypes.c_float(eps), ctypes.c_float(neg_slope), _stream())
+        ctx.save_for_backward(x, scale, bias, mean, rstd)
+        ctx.meta = (b, c, ndim, size, classes, sbs, float(neg_slope))
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, scale, bias, mean, rstd = ctx.saved_tensors
+        b, c, ndim, size, classes, sbs, neg_slope = ctx.meta
+        dy = dy.contiguous()
+        dx = torch.empty_like(x)
+        dsb = torch.empty((2, b, c), dtype=torch.float32, device=x.device)
+        _lib.call("hg_adain_cl_bwd", _ptr(x), _ptr(dy), _ptr(scale), _ptr(bias), _ptr(mean), _ptr(rstd), _ptr(dx),
+                  _ptr(dsb[0]), _ptr(dsb[1]), b, c, ndim, size, classes, sbs, c, ctypes.c_float(neg_slope), _stream())
+        return dx, dsb[0], dsb[1], None, None, None, None
+
+
+def adain_act_channels_last(x: Tensor, scale: Tensor, bias: Tensor, ndim: int, classes: int, neg_slope: float = 0.0,
+                            eps: float = 1e-8) -> Tensor:
+    return _AdaInChannelsLast.apply(x, scale, bias, ndim, classes, neg_slope, eps)

@@ -42,10 +42,10 @@ def test_argument_validation_without_gpu():
     p = ctypes.c_void_p(16)
     assert lib.hg_rotate_fwd(p, p, p, n, n, 1, 1, 17, 0, 0, 0, 0, n) == -2      # size not 8/16/32
     assert lib.hg_rotate_fwd(p, p, p, n, n, 1, 1, 16, 0, 0, 7, 0, n) == -1      # bad dtype
-    assert lib.hg_rotate_bwd(p, p, p, 0, 1, 16, 0, 0, 0, 0, n) == -1            # batch 0
+    assert lib.hg_rotate_bwd(p, p, p, n, 0, 0, 1, 16, 0, 0, 0, 0, n) == -1      # batch 0
     assert lib.hg_adain_act_fwd(p, p, p, p, p, p, 1, 1, 6, 6, 1, 1e-8, 0.0, 0, 0, n) == -2   # N % 4 != 0
     with pytest.raises(_lib.HologanB200Error):
-        _lib.call("hg_rotate_bwd", n, n, n, 1, 1, 16, 0, 0, 0, 0, n)
+        _lib.call("hg_rotate_bwd", n, n, n, n, 0, 1, 1, 16, 0, 0, 0, 0, n)
 
 
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):

@@ -1,0 +1,111 @@
+"""Channels-last kernels of the bf16 pipeline (rotate NDHWC->NDHWC|PROJ fwd/bwd, AdaIN on s2d conv
+outputs) against the reference-layout kernels / the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_err
+from lightning_gan_zoo_b200 import ops
+from oracle import hologan_oracle as orc
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+BF = torch.bfloat16
+
+
+def views(b, seed):
+    v = orc.sample_view(b, np.random.RandomState(seed))
+    if b >= 3:
+        v[0, 0], v[0, 1] = np.deg2rad(270), np.deg2rad(90)      # axis aligned
+        v[1, 2] = 0.7
+        v[2, 3:] = (3.0, -2.0, 1.5)
+    return v
+
+
+@pytest.mark.parametrize("b,c,s", [(4, 64, 16), (3, 16, 8), (2, 128, 16), (5, 8, 16)])
+@pytest.mark.parametrize("border", [ops.HG_BORDER_REFERENCE, ops.HG_BORDER_ZERO])
+def test_rotate_channels_last_forward(b, c, s, border):
+    gen = torch.Generator().manual_seed(c + s)
+    vol = torch.randn(b, c, s, s, s, generator=gen).to(BF)
+    a = ops.view_to_affine(views(b, c), s, s).to(DEV)
+    ref_nc = ops.rotate_fwd_raw(vol.to(DEV), a, border)                               # NCDHW kernel (golden-tested)
+    vol_cl = vol.permute(0, 2, 3, 4, 1).contiguous().to(DEV)
+    out = ops.rotate_fwd_raw(vol_cl, a, border, ops.HG_NDHWC, ops.HG_NDHWC)
+    if border == ops.HG_BORDER_REFERENCE:
+        assert torch.equal(out.permute(0, 4, 1, 2, 3), ref_nc)                        # same op order -> same bits
+    else:
+        assert rel_err(out.permute(0, 4, 1, 2, 3).float(), ref_nc.float()) < 2 ** -7
+    proj = ops.rotate_fwd_raw(vol_cl, a, border, ops.HG_NDHWC, ops.HG_PROJ)            # [b, z, x, y, c]
+    assert torch.equal(proj, out.permute(0, 1, 3, 2, 4).contiguous())
+    # against the fp32 oracle on the bf16-rounded volume
+    oref = orc.rotate_resample(vol.float(), a_inv=a.cpu())
+    assert rel_err(out.permute(0, 4, 1, 2, 3).float(), oref) < 2 ** -7
+    # the projection operand vs the reference's fold (hologan_generator.py:130-133)
+    fold = orc.project_depth_to_channels(oref)                                         # (B, C*S, S, S): [b, c*S+j, z, x]
+    mine = proj.float().cpu().reshape(b, s, s, s, c)                                   # [b, z, x, y, c]
+    fold_from_mine = mine.permute(0, 4, 3, 1, 2).flip(2).reshape(b, c * s, s, s)       # j = S-1-y
+    assert rel_err(fold_from_mine, fold) < 2 ** -7
+
+
+@pytest.mark.parametrize("b,c,s", [(4, 64, 16), (3, 16, 8), (2, 128, 16)])
+@pytest.mark.parametrize("out_layout", [ops.HG_NDHWC, ops.HG_PROJ])
+def test_rotate_channels_last_backward(b, c, s, out_layout):
+    gen = torch.Generator().manual_seed(c * 3 + s)
+    g_nc = torch.randn(b, c, s, s, s, generator=gen).to(BF)
+    a = ops.view_to_affine(views(b, c + 1), s, s).to(DEV)
+    g_cl = g_nc.permute(0, 2, 3, 4, 1).contiguous()
+    if out_layout == ops.HG_PROJ:
+        g_cl = g_cl.permute(0, 1, 3, 2, 4).contiguous()
+    gv = ops.rotate_bwd_raw(g_cl.to(DEV), a, c, s, ops.HG_BORDER_ZERO, ops.HG_NDHWC, out_layout)
+    gv2 = ops.rotate_bwd_raw(g_cl.to(DEV), a, c, s, ops.HG_BORDER_ZERO, ops.HG_NDHWC, out_layout)
+    assert torch.equal(gv, gv2)                                                        # deterministic
+    # oracle adjoint via autograd on the fp32 restatement
+    v = torch.zeros(b, c, s, s, s, requires_grad=True)
+    (orc.rotate_resample(v, a_inv=a.cpu()) * g_nc.float()).sum().backward()
+    assert rel_err(gv.permute(0, 4, 1, 2, 3).float(), v.grad) < 2 ** -7
+    # adjoint identity <R v, g> == <v, R^T g> through the channels-last kernels
+    vol = torch.randn(b, s, s, s, c, generator=gen).to(BF).to(DEV)
+    out = ops.rotate_fwd_raw(vol, a, ops.HG_BORDER_ZERO, ops.HG_NDHWC, out_layout)
+    lhs = (out.double() * g_cl.to(DEV).double()).sum().item()
+    rhs = (vol.double() * gv.double()).sum().item()
+    assert abs(lhs - rhs) <= 2e-2 * (out.double().abs() * g_cl.to(DEV).double().abs()).sum().item() / 10
+
+
+CASES = [(3, 3, 4, 128, 8), (3, 3, 8, 64, 8), (2, 2, 16, 256, 4), (2, 2, 32, 64, 4), (2, 2, 16, 32, 1), (2, 3, 8, 16, 1)]
+
+
+@pytest.mark.parametrize("b,ndim,size,c,classes", CASES)
+@pytest.mark.parametrize("slope", [0.0, 0.2])
+def test_adain_channels_last(b, ndim, size, c, classes, slope):
+    gen = torch.Generator().manual_seed(size * c + classes)
+    sp = (size,) * ndim
+    x = (torch.randn(b, *sp, classes, c, generator=gen) * 1.5 + 0.3).to(BF)
+    if classes == 1:
+        x = x.reshape(b, *sp, c)
+    s = torch.rand(b, c, generator=gen) + 0.2
+    bb = torch.randn(b, c, generator=gen)
+    up = 2 if classes > 1 else 1
+    dy = torch.randn(b, *((up * size,) * ndim), c, generator=gen).to(BF)
+    # oracle on the torch-layout view of the same data
+    x_nc = (ops.s2d_to_nc(x, ndim) if classes > 1 else x.permute(0, ndim + 1, *range(1, ndim + 1))).float()
+    xr = x_nc.clone().requires_grad_(True); sr = s.clone().requires_grad_(True); br = bb.clone().requires_grad_(True)
+    yr = torch.nn.functional.leaky_relu(orc.adain(xr, sr, br), slope)
+    dy_nc = dy.permute(0, ndim + 1, *range(1, ndim + 1)).float()
+    (yr * dy_nc).sum().backward()
+    xg = x.to(DEV).requires_grad_(True); sg = s.to(DEV).requires_grad_(True); bg = bb.to(DEV).requires_grad_(True)
+    y = ops.adain_act_channels_last(xg, sg, bg, ndim, classes, slope)
+    (y.float() * dy.to(DEV).float()).sum().backward()
+    assert rel_err(y.permute(0, ndim + 1, *range(1, ndim + 1)).float(), yr) < 2e-2
+    dx_nc = ops.s2d_to_nc(xg.grad, ndim) if classes > 1 else xg.grad.permute(0, ndim + 1, *range(1, ndim + 1))
+    assert rel_err(dx_nc.float(), xr.grad) < 2e-2
+    assert rel_err(sg.grad, sr.grad) < 2e-2 and rel_err(bg.grad, br.grad) < 2e-2
+
+
+def test_unsupported():
+    from lightning_gan_zoo_b200._lib import HologanB200Error
+    x = torch.zeros(1, 16, 16, 4, 24, dtype=BF, device=DEV)
+    with pytest.raises(HologanB200Error, match="multiple of 16"):
+        ops.adain_act_channels_last(x, torch.ones(1, 24, device=DEV), torch.zeros(1, 24, device=DEV), 2, 4)
+    with pytest.raises(HologanB200Error, match="bf16 only"):
+        ops.rotate_fwd_raw(torch.zeros(1, 16, 16, 16, 8, device=DEV), torch.eye(4, device=DEV)[None], 0, ops.HG_NDHWC,
+                           ops.HG_NDHWC)

@@ -96,5 +96,6 @@ def test_cuda_graph_step_matches_eager():
         la = a.step(real, i, z=z, view=view)
         lb = b.step(real, i, z=z, view=view)
         assert abs(la.item() - lb.item()) < 5e-3 * max(1.0, abs(la.item())), (i, la.item(), lb.item())
-    worst = max(rel_err(pb, pa) for pa, pb in zip(a.generator.parameters(), b.generator.parameters()) if pa.numel() > 1)
+    # weight matrices only: biases start at 0 and Adam moves them by +-lr per step whatever the (noisy) gradient
+    worst = max(rel_err(pb, pa) for pa, pb in zip(a.generator.parameters(), b.generator.parameters()) if pa.dim() > 1)
     assert worst < 5e-2
