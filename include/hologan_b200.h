@@ -136,23 +136,47 @@ int hg_adain_cl_bwd(const void *x, const void *dy, const float *scale, const flo
  * Supported: Cin % 64 == 0, Cout % 16 == 0 (fwd); Cout % 64 == 0 (dgrad); Cin % 128 == 0 and
  * Cout % 64 == 0 (wgrad); size in {4, 8, 16, 32, ...} tiling into 128-row boxes.
  */
-int hg_convt_pack_weight(const float *w, void *w_fwd, void *w_dgrad, int cin, int cout, int taps, void *stream);
+/* perm_c / perm_s: optional permutation of the input-channel (GEMM K) index for the projection operand
+ * in HG_PROJ layout: packed channel y*perm_c + c <-> torch channel c*perm_s + (perm_s-1-y)
+ * (reference :130-133); perm_s = 0 means identity. */
+int hg_convt_pack_weight(const float *w, void *w_fwd, void *w_dgrad, int cin, int cout, int taps, int perm_c, int perm_s,
+                         void *stream);
 /* y_s2d = act(convT(x) + bias); bias (Cout) fp32 or NULL; act: v > 0 ? v : neg_slope * v (1 = none) */
 int hg_convt_fwd(const void *x, const void *w_fwd, const float *bias, void *y_s2d, int batch, int cin, int cout,
                  int ndim, int size, int kernel, float neg_slope, void *stream);
 /* dx (B, .., Cin) = adjoint of the forward w.r.t. x */
 int hg_convt_dgrad(const void *dy_s2d, const void *w_dgrad, void *dx, int batch, int cin, int cout, int ndim, int size,
                    int kernel, void *stream);
-/* dw_packed [t][Cin][Cout] fp32 = adjoint w.r.t. the weight (overwritten; split-K partial sums are
- * combined with fp32 red.global.add); hg_convt_unpack_wgrad converts to the torch layout. */
-int hg_convt_wgrad(const void *x, const void *dy_s2d, float *dw_packed, int batch, int cin, int cout, int ndim, int size,
-                   int kernel, void *stream);
-int hg_convt_unpack_wgrad(const float *dw_packed, float *dw, int cin, int cout, int taps, void *stream);
+/* dw (Cin, Cout, k..) fp32 in the torch parameter layout = adjoint w.r.t. the weight (accumulate != 0:
+ * added to dw, else overwritten).  Split-K partial tiles go to `workspace` with plain stores and are
+ * summed in a fixed order by a second kernel: deterministic, no atomics. */
+long long hg_convt_wgrad_workspace_bytes(int batch, int cin, int cout, int ndim, int size, int kernel);
+int hg_convt_wgrad(const void *x, const void *dy_s2d, float *dw, void *workspace, long long workspace_bytes, int batch,
+                   int cin, int cout, int ndim, int size, int kernel, int perm_c, int perm_s, int accumulate, void *stream);
 
 /* Plain GEMM on the same pipeline: D[M,N] = act(A[M,K] @ B[N,K]^T + bias[N]); bf16 row-major A, B, D
  * (row stride of D = ldd elements).  Used for the batched ZMapping (a2). */
 int hg_gemm_bf16_nt(const void *a, const void *b, const float *bias, void *d, int m, int n, int k, long long ldd,
                     float neg_slope, void *stream);
+
+/* ---- a2: ZMapping  relu(Linear(z))  (core/models/hologan_generator.py:7-18), fp32 ------------------
+ *   z (B,K), w (N,K) torch nn.Linear layout, bias (N), out (B,N) = relu(z @ w^T + bias)
+ *   backward: dw (N,K), dbias (N), dz (B,K) (+= when accumulate_dz, may be NULL) from dout (B,N) */
+int hg_linear_relu_fwd(const float *z, const float *w, const float *bias, float *out, int batch, int k, int n, void *stream);
+int hg_linear_relu_bwd(const float *z, const float *w, const float *out, const float *dout, float *dw, float *dbias,
+                       float *dz, int batch, int k, int n, int accumulate_dz, void *stream);
+
+/* ---- a11: final_layer + tanh  (core/models/hologan_generator.py:69-75,141-142, img_size 64) ---------
+ *   out (B,Cout,S,S) fp32 NCHW = tanh(conv2d(x, w, bias, k3, p1)); x (B,S,S,Cin) bf16 NHWC,
+ *   w torch (Cout,Cin,3,3) fp32.  Cout <= 4, Cin = 8 * 2^k <= 256.  Direct convolution (bandwidth-bound).
+ *   backward: dx (B,S,S,Cin) bf16 (may be NULL), dw, dbias from dout (B,Cout,S,S) fp32; deterministic
+ *   two-stage reduction through `workspace`. */
+int hg_final_conv_tanh_fwd(const void *x, const float *w, const float *bias, float *out, int batch, int cin, int cout,
+                           int size, void *stream);
+long long hg_final_conv_tanh_bwd_workspace_bytes(int batch, int cin, int cout, int size);
+int hg_final_conv_tanh_bwd(const void *x, const float *w, const float *out, const float *dout, void *dx, float *dw,
+                           float *dbias, void *workspace, long long workspace_bytes, int batch, int cin, int cout, int size,
+                           void *stream);
 
 #ifdef __cplusplus
 }

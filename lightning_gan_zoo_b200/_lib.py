@@ -34,15 +34,25 @@ SIGNATURES = {
                          _c_ll, _c_int, _c_float, _c_float, _c_int, _c_int, _c_void_p],
     "hg_adain_act_bwd": [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
                          _c_void_p, _c_int, _c_int, _c_int, _c_ll, _c_int, _c_int, _c_float, _c_int, _c_int, _c_void_p],
-    "hg_convt_pack_weight": [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p],
+    "hg_convt_pack_weight": [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_void_p],
     "hg_convt_fwd": [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_float,
                      _c_void_p],
     "hg_convt_dgrad": [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_void_p],
-    "hg_convt_wgrad": [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_void_p],
-    "hg_convt_unpack_wgrad": [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p],
+    "hg_convt_wgrad_workspace_bytes": [_c_int, _c_int, _c_int, _c_int, _c_int, _c_int],
+    "hg_convt_wgrad": [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_ll, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
+                       _c_int, _c_int, _c_int, _c_void_p],
     "hg_gemm_bf16_nt": [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_ll, _c_float, _c_void_p],
+    "hg_linear_relu_fwd": [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p],
+    "hg_linear_relu_bwd": [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int,
+                           _c_int, _c_int, _c_void_p],
+    "hg_final_conv_tanh_fwd": [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_void_p],
+    "hg_final_conv_tanh_bwd_workspace_bytes": [_c_int, _c_int, _c_int, _c_int],
+    "hg_final_conv_tanh_bwd": [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
+                               _c_ll, _c_int, _c_int, _c_int, _c_int, _c_void_p],
 }
-_RESTYPES = {"hg_last_error": ctypes.c_char_p, "hg_rotate_bwd_workspace_bytes": ctypes.c_longlong}
+_RESTYPES = {"hg_last_error": ctypes.c_char_p, "hg_rotate_bwd_workspace_bytes": ctypes.c_longlong,
+             "hg_convt_wgrad_workspace_bytes": ctypes.c_longlong,
+             "hg_final_conv_tanh_bwd_workspace_bytes": ctypes.c_longlong}
 
 _lib = None
 _lock = threading.Lock()

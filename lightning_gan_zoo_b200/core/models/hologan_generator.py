@@ -40,8 +40,11 @@ class ZMapping(nn.Module):
     def forward(self, x):
         # the style path stays fp32 even under autocast: it is 0.01 % of the FLOPs and every activation
         # of the block is scaled by it
-        with torch.autocast(x.device.type, enabled=False):
-            style = F.relu(F.linear(x.float(), self.linear1.weight, self.linear1.bias))
+        if x.is_cuda:
+            style = ops.linear_relu(x, self.linear1.weight, self.linear1.bias)       # fp32 SIMT kernel
+        else:
+            with torch.autocast(x.device.type, enabled=False):
+                style = F.relu(F.linear(x.float(), self.linear1.weight, self.linear1.bias))
         c = self.output_channel
         return style[:, :c], style[:, c:]
 
@@ -159,16 +162,18 @@ class Generator(nn.Module):
         rot = ops.rotate_resample(h, a_inv, ops.HG_BORDER_ZERO, ops.HG_NDHWC, ops.HG_PROJ)
         c = rot.shape[-1]
         a_proj = rot.reshape(n, size, size, size * c)
-        w = self.convTranspose2d1.weight
-        # K index of the operand is y*C + c; the reference's folded channel c*S + j pairs with y = S-1-j
-        w_perm = w.reshape(c, size, w.shape[1]).flip(1).permute(1, 0, 2).reshape(c * size, w.shape[1], 1, 1)
-        h = ops.convt(a_proj, w_perm, self.convTranspose2d1.bias, 2, 1, neg_slope=0.0)   # 1x1 conv + bias + ReLU
+        # K index of the operand is y*C + c; the reference's folded channel c*S + j pairs with y = S-1-j:
+        # the weight pack / wgrad kernels apply that permutation (perm = (C, S)), the parameter keeps its layout
+        h = ops.convt(a_proj, self.convTranspose2d1.weight, self.convTranspose2d1.bias, 2, 1, neg_slope=0.0,
+                      perm=(c, size))                                             # 1x1 conv + bias + ReLU
         h = h.reshape(n, size, size, -1)
         for block in (self.block3, self.block4):
             y = ops.convt(h, block.convTranspose.weight, None, 2, 4)             # (B,S,S,4,Cout) s2d
             sc, bi = block.zMapping(z)
             h = ops.adain_act_channels_last(y, sc, bi, ndim=2, classes=4)        # (B,2S,2S,Cout) NHWC
-        # final conv + tanh: cuDNN consumes the NHWC buffer as a channels_last-strided NCHW view (no copy)
+        if self.img_size == 64 and ops.final_conv_supported(h.shape[-1], self.final_layer.weight.shape[0]):
+            return ops.final_conv_tanh(h, self.final_layer.weight, self.final_layer.bias)   # direct conv + tanh, fp32 out
+        # patched-128 head (ConvTranspose2d k4 s2): cuDNN on the NHWC buffer viewed as channels_last NCHW
         return torch.tanh(self.final_layer(h.permute(0, 3, 1, 2)))
 
     def forward(self, z, view_in=None):

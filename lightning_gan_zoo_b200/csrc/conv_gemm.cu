@@ -30,7 +30,8 @@ constexpr int kMaxGroups = 8;
 constexpr int kSmemBudget = 200 * 1024;
 
 struct Tap {
-    int16_t sx, sy, sz, pad;
+    int16_t sx, sy, sz;
+    int16_t acc;          // which accumulator (TMEM column block of BN columns) this tap adds into
     int32_t a_c_off;      // channel offset added to the A box (selects the parity class in s2d tensors)
     int32_t b_row_off;    // first row of this tap's slice in the packed weight matrix
 };
@@ -46,7 +47,9 @@ struct TapGemmParams {
     CUtensorMap tmA;      // K-major kernel: activations (C, X, Y, Z, B), box (64, bx, by, bz, bb), prod = 128
     CUtensorMap tmB;      // K-major kernel: packed weights (Kcols, rows), box (64, BN)
     int X, Y, Z, Bn;      // spatial extents / batch of the A tensor (for the tile -> coordinate decode)
-    int BN;               // accumulator columns
+    int BN;               // columns of one accumulator = N of one MMA = rows of one weight box
+    int epi_cols;         // columns the epilogue drains = accumulators per CTA * BN (<= 512)
+    int bias_mod;         // bias index = output column % bias_mod
     int k_chunks;         // 64-wide K chunks per tap
     int stages;
     int m_total;          // valid rows
@@ -68,7 +71,8 @@ struct WgradParams {
     int pos_tiles;        // number of 64-position tiles
     int splits;           // split-K factor (grid.z = pairs * splits)
     int cin, cout;
-    float *dw;            // packed fp32 [tap][Cin][Cout], accumulated with red.global.add
+    int num_taps_total;   // k^d slices per split in the partial buffer
+    float *dw;            // split-K partials, fp32 [split][tap][Cin][Cout] (plain stores; reduced by wgrad_reduce_kernel)
     int num_pairs;
     struct Pair {
         int16_t sx, sy, sz, pad;
@@ -84,7 +88,10 @@ struct SharedCtl {
     uint32_t tmem_base;
 };
 
-__device__ __forceinline__ uint32_t tmem_cols_for(int bn) { return bn <= 32 ? 32u : bn <= 64 ? 64u : bn <= 128 ? 128u : 256u; }
+__device__ __forceinline__ uint32_t tmem_cols_for(int bn)
+{
+    return bn <= 32 ? 32u : bn <= 64 ? 64u : bn <= 128 ? 128u : bn <= 256 ? 256u : 512u;
+}
 
 __device__ __forceinline__ uint8_t *align_1024(uint8_t *p)
 {
@@ -117,7 +124,7 @@ __global__ void __launch_bounds__(kThreads, 1) tap_gemm_kernel(const __grid_cons
         ptx::fence_barrier_init();
     }
     if (warp == 1) {
-        ptx::tmem_alloc(&ctl.tmem_base, tmem_cols_for(BN));
+        ptx::tmem_alloc(&ctl.tmem_base, tmem_cols_for(p.epi_cols));
         ptx::tmem_relinquish();
     }
     ptx::tc_fence_before();
@@ -152,18 +159,26 @@ __global__ void __launch_bounds__(kThreads, 1) tap_gemm_kernel(const __grid_cons
         if (ptx::elect_one()) {
             // ===== MMA issuer =====
             const uint32_t idesc = ptx::idesc_bf16(kBM, BN, false, false);
-            for (int it = 0; it < total_iters; ++it) {
-                const int s = it % p.stages;
-                const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
-                ptx::mbar_wait(&ctl.full[s], ph);
-                ptx::tc_fence_after();
-                const uint32_t a_addr = ptx::smem_u32(tiles + (size_t)s * stage_bytes);
-                const uint64_t a_desc = ptx::smem_desc_sw128(a_addr, 16, 1024);
-                const uint64_t b_desc = ptx::smem_desc_sw128(a_addr + a_bytes, 16, 1024);
+            uint32_t started = 0;                       // accumulators that already hold a partial sum
+            int it = 0;
+            for (int t = 0; t < grp.tap_count; ++t) {
+                const int acc = p.taps[grp.tap_begin + t].acc;
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+                for (int kc = 0; kc < p.k_chunks; ++kc, ++it) {
+                    const int s = it % p.stages;
+                    const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+                    ptx::mbar_wait(&ctl.full[s], ph);
+                    ptx::tc_fence_after();
+                    const uint32_t a_addr = ptx::smem_u32(tiles + (size_t)s * stage_bytes);
+                    const uint64_t a_desc = ptx::smem_desc_sw128(a_addr, 16, 1024);
+                    const uint64_t b_desc = ptx::smem_desc_sw128(a_addr + a_bytes, 16, 1024);
 #pragma unroll
-                for (int k = 0; k < kBK / 16; ++k)      // +32 bytes (>>4 = 2) per 16-element K step inside the swizzle row
-                    ptx::umma_bf16(tmem_base, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (it | k) != 0);
-                ptx::umma_commit(&ctl.empty[s]);        // frees the smem slot when these MMAs retire
+                    for (int k = 0; k < kBK / 16; ++k)  // +32 bytes (>>4 = 2) per 16-element K step inside the swizzle row
+                        ptx::umma_bf16(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc,
+                                       ((started >> acc) & 1u) != 0 || k != 0);
+                    started |= 1u << acc;
+                    ptx::umma_commit(&ctl.empty[s]);    // frees the smem slot when these MMAs retire
+                }
             }
             ptx::umma_commit(&ctl.acc_ready);
         }
@@ -176,17 +191,18 @@ __global__ void __launch_bounds__(kThreads, 1) tap_gemm_kernel(const __grid_cons
         const long long m = (long long)blockIdx.x * kBM + row;
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
         __nv_bfloat16 *orow = static_cast<__nv_bfloat16 *>(p.out) + m * p.ld_out + grp.out_col_off + n0;
-        for (int c0 = 0; c0 < BN; c0 += 16) {
+        for (int c0 = 0; c0 < p.epi_cols; c0 += 16) {
             float v[16];
             ptx::tmem_ld_16(taddr + (uint32_t)c0, v);
             if (m < p.m_total) {
                 uint32_t packed[8];
+                const int bcol = (n0 + c0) % p.bias_mod;
 #pragma unroll
                 for (int j = 0; j < 16; j += 2) {
                     float a = v[j], b = v[j + 1];
                     if (p.bias) {
-                        a += __ldg(p.bias + n0 + c0 + j);
-                        b += __ldg(p.bias + n0 + c0 + j + 1);
+                        a += __ldg(p.bias + bcol + j);
+                        b += __ldg(p.bias + bcol + j + 1);
                     }
                     a = a > 0.f ? a : a * p.slope;
                     b = b > 0.f ? b : b * p.slope;
@@ -201,7 +217,7 @@ __global__ void __launch_bounds__(kThreads, 1) tap_gemm_kernel(const __grid_cons
     }
     ptx::tc_fence_before();
     __syncthreads();
-    if (warp == 1) ptx::tmem_dealloc(tmem_base, tmem_cols_for(BN));
+    if (warp == 1) ptx::tmem_dealloc(tmem_base, tmem_cols_for(p.epi_cols));
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -243,6 +259,13 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_gemm_kernel(const __grid_co
     ptx::tc_fence_after();
     const uint32_t tmem_base = ctl.tmem_base;
 
+    if (total_iters == 0 && warp >= 2) {                       // empty K range: this split's partial tile is all zero
+        const int row = (warp & 3) * 32 + lane;
+        if (ci0 + row < p.cin) {
+            float *orow = p.dw + (((size_t)split * p.num_taps_total + pr.tap_flat) * p.cin + ci0 + row) * p.cout + co0;
+            for (int c = 0; c < BN; c += 4) *reinterpret_cast<float4 *>(orow + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
     if (total_iters > 0) {
         if (warp == 0) {
             if (ptx::elect_one()) {
@@ -291,13 +314,14 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_gemm_kernel(const __grid_co
             const int quad = warp & 3;
             const int row = quad * 32 + lane;
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
-            float *orow = p.dw + ((size_t)pr.tap_flat * p.cin + ci0 + row) * p.cout + co0;
+            float *orow = p.dw + (((size_t)split * p.num_taps_total + pr.tap_flat) * p.cin + ci0 + row) * p.cout + co0;
             for (int c0 = 0; c0 < BN; c0 += 16) {
                 float v[16];
                 ptx::tmem_ld_16(taddr + (uint32_t)c0, v);
                 if (ci0 + row < p.cin) {
+                    float4 *dst = reinterpret_cast<float4 *>(orow + c0);
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) atomicAdd(orow + c0 + j, v[j]);
+                    for (int j = 0; j < 4; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                 }
             }
         }
@@ -310,32 +334,74 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_gemm_kernel(const __grid_co
 // -------------------------------------------------------------------------------------------------
 // Weight packing: torch ConvTranspose layout (Cin, Cout, k^d) fp32  <->  GEMM operand layouts
 // -------------------------------------------------------------------------------------------------
-// w_fwd[t][co][ci] (B operand of forward: rows = Cout, K = Cin), w_dgrad[t][ci][co] (rows = Cin, K = Cout)
-__global__ void pack_weight_kernel(const float *__restrict__ w, __nv_bfloat16 *__restrict__ w_fwd,
-                                   __nv_bfloat16 *__restrict__ w_dgrad, int cin, int cout, int taps)
+// Channel permutation of the projection operand (HG_PROJ): GEMM K index k' = y*C + c pairs with the
+// reference's folded input channel c*S + (S-1-y) (hologan_generator.py:130-133).  perm_s == 0: identity.
+__device__ __forceinline__ int torch_cin(int ci, int perm_c, int perm_s)
 {
-    const size_t n = (size_t)cin * cout * taps;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        // i enumerates the dgrad layout (t, ci, co): coalesced writes there
-        const int co = (int)(i % cout);
-        const int ci = (int)((i / cout) % cin);
-        const int t = (int)(i / ((size_t)cout * cin));
-        const float v = w[((size_t)ci * cout + co) * taps + t];
-        const __nv_bfloat16 h = __float2bfloat16_rn(v);
-        if (w_dgrad) w_dgrad[i] = h;
-        if (w_fwd) w_fwd[((size_t)t * cout + co) * cin + ci] = h;
+    if (perm_s == 0) return ci;
+    const int y = ci / perm_c, c = ci - y * perm_c;
+    return c * perm_s + (perm_s - 1 - y);
+}
+
+// torch (Cin, Cout, T) fp32 -> w_fwd[t][co][ci] (B operand of forward: rows = Cout, K = Cin) and
+// w_dgrad[t][ci][co] (rows = Cin, K = Cout), bf16.  One CTA = a 16(ci) x 16(co) x T brick through smem:
+// global reads are 16*T-float runs, writes 32-byte runs.
+__global__ void __launch_bounds__(256) pack_weight_kernel(const float *__restrict__ w, __nv_bfloat16 *__restrict__ w_fwd,
+                                                          __nv_bfloat16 *__restrict__ w_dgrad, int cin, int cout, int taps,
+                                                          int perm_c, int perm_s)
+{
+    extern __shared__ float brick[];                    // [16 ci][16 co][T] (+1 pad per ci row)
+    const int ci0 = blockIdx.x * 16, co0 = blockIdx.y * 16;
+    const int row_len = 16 * taps, pitch = row_len + 1;
+    for (int i = threadIdx.x; i < 16 * row_len; i += blockDim.x) {
+        const int r = i / row_len, c = i - r * row_len;
+        float v = 0.f;
+        if (ci0 + r < cin && co0 + c / taps < cout)
+            v = w[((size_t)torch_cin(ci0 + r, perm_c, perm_s) * cout + co0) * taps + c];
+        brick[r * pitch + c] = v;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 256 * taps; i += blockDim.x) {
+        const int t = i >> 8, rem = i & 255;
+        {   // dgrad layout: [t][ci][co] -> co fastest
+            const int ci = rem >> 4, co = rem & 15;
+            if (w_dgrad && ci0 + ci < cin && co0 + co < cout)
+                w_dgrad[((size_t)t * cin + ci0 + ci) * cout + co0 + co] = __float2bfloat16_rn(brick[ci * pitch + co * taps + t]);
+        }
+        {   // fwd layout: [t][co][ci] -> ci fastest
+            const int co = rem >> 4, ci = rem & 15;
+            if (w_fwd && ci0 + ci < cin && co0 + co < cout)
+                w_fwd[((size_t)t * cout + co0 + co) * cin + ci0 + ci] = __float2bfloat16_rn(brick[ci * pitch + co * taps + t]);
+        }
     }
 }
 
-// dw_packed[t][ci][co] fp32 -> torch layout (Cin, Cout, k^d) fp32 (overwrites)
-__global__ void unpack_wgrad_kernel(const float *__restrict__ dwp, float *__restrict__ dw, int cin, int cout, int taps)
+// Sum the split-K partials [split][t][ci][co] and write the torch layout (Cin, Cout, T) fp32.
+// accumulate != 0: dw += result (lets the caller target a live .grad buffer).
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float *__restrict__ partial, float *__restrict__ dw, int cin,
+                                                           int cout, int taps, int splits, int perm_c, int perm_s,
+                                                           int accumulate)
 {
-    const size_t n = (size_t)cin * cout * taps;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        const int t = (int)(i % taps);
-        const int co = (int)((i / taps) % cout);
-        const int ci = (int)(i / ((size_t)taps * cout));
-        dw[i] = dwp[((size_t)t * cin + ci) * cout + co];
+    extern __shared__ float brick[];                    // [16 ci][16 co][T]
+    const int ci0 = blockIdx.x * 16, co0 = blockIdx.y * 16;
+    const int row_len = 16 * taps, pitch = row_len + 1;
+    const size_t split_stride = (size_t)taps * cin * cout;
+    for (int i = threadIdx.x; i < 256 * taps; i += blockDim.x) {
+        const int t = i >> 8, rem = i & 255, ci = rem >> 4, co = rem & 15;
+        float v = 0.f;
+        if (ci0 + ci < cin && co0 + co < cout) {
+            const float *src = partial + ((size_t)t * cin + ci0 + ci) * cout + co0 + co;
+            for (int sp = 0; sp < splits; ++sp) v += src[sp * split_stride];
+        }
+        brick[ci * pitch + co * taps + t] = v;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 16 * row_len; i += blockDim.x) {
+        const int r = i / row_len, c = i - r * row_len;
+        if (ci0 + r < cin && co0 + c / taps < cout) {
+            float *dst = dw + ((size_t)torch_cin(ci0 + r, perm_c, perm_s) * cout + co0) * taps + c;
+            *dst = accumulate ? *dst + brick[r * pitch + c] : brick[r * pitch + c];
+        }
     }
 }
 
@@ -516,32 +582,33 @@ extern "C" int hg_gemm_bf16_nt(const void *a, const void *b, const float *bias, 
     rc = make_map_2d(&p.tmB, b, k, n, bn);
     if (rc) return rc;
     p.X = m; p.Y = 1; p.Z = 1; p.Bn = 1;
-    p.BN = bn; p.k_chunks = k / kBK; p.m_total = m; p.ld_out = ldd; p.out = d; p.bias = bias; p.slope = neg_slope;
+    p.BN = bn; p.epi_cols = bn; p.bias_mod = n; p.k_chunks = k / kBK; p.m_total = m; p.ld_out = ldd; p.out = d; p.bias = bias;
+    p.slope = neg_slope;
     p.num_groups = 1;
     p.groups[0] = Group{0, 1, 0, 0};
     p.taps[0] = Tap{0, 0, 0, 0, 0, 0};
     return launch_tap_gemm(p, (m + kBM - 1) / kBM, n / bn, static_cast<cudaStream_t>(stream), "hg_gemm_bf16_nt");
 }
 
-extern "C" int hg_convt_pack_weight(const float *w, void *w_fwd, void *w_dgrad, int cin, int cout, int taps, void *stream)
+static int perm_ok(const char *who, int cin, int perm_c, int perm_s)
 {
-    HG_REQUIRE(w && (w_fwd || w_dgrad), HG_ERR_INVALID_ARG, "hg_convt_pack_weight: null pointer");
-    HG_REQUIRE(cin > 0 && cout > 0 && taps > 0, HG_ERR_INVALID_ARG, "hg_convt_pack_weight: dims must be positive");
-    const size_t n = (size_t)cin * cout * taps;
-    const int grid = (int)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);
-    pack_weight_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(w, static_cast<__nv_bfloat16 *>(w_fwd),
-                                                                           static_cast<__nv_bfloat16 *>(w_dgrad), cin, cout, taps);
-    return check_launch("hg_convt_pack_weight");
+    HG_REQUIRE(perm_s == 0 || (perm_c > 0 && perm_s > 0 && perm_c * perm_s == cin), HG_ERR_INVALID_ARG,
+               "%s: channel permutation (%d, %d) does not factor Cin = %d", who, perm_c, perm_s, cin);
+    return HG_OK;
 }
 
-extern "C" int hg_convt_unpack_wgrad(const float *dw_packed, float *dw, int cin, int cout, int taps, void *stream)
+extern "C" int hg_convt_pack_weight(const float *w, void *w_fwd, void *w_dgrad, int cin, int cout, int taps, int perm_c,
+                                    int perm_s, void *stream)
 {
-    HG_REQUIRE(dw_packed && dw, HG_ERR_INVALID_ARG, "hg_convt_unpack_wgrad: null pointer");
-    HG_REQUIRE(cin > 0 && cout > 0 && taps > 0, HG_ERR_INVALID_ARG, "hg_convt_unpack_wgrad: dims must be positive");
-    const size_t n = (size_t)cin * cout * taps;
-    const int grid = (int)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);
-    unpack_wgrad_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(dw_packed, dw, cin, cout, taps);
-    return check_launch("hg_convt_unpack_wgrad");
+    HG_REQUIRE(w && (w_fwd || w_dgrad), HG_ERR_INVALID_ARG, "hg_convt_pack_weight: null pointer");
+    HG_REQUIRE(cin > 0 && cout > 0 && taps > 0 && taps <= 27, HG_ERR_INVALID_ARG, "hg_convt_pack_weight: bad dims");
+    int rc = perm_ok("hg_convt_pack_weight", cin, perm_c, perm_s);
+    if (rc) return rc;
+    dim3 grid((cin + 15) / 16, (cout + 15) / 16);
+    const size_t smem = (size_t)16 * (16 * taps + 1) * sizeof(float);
+    pack_weight_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(
+        w, static_cast<__nv_bfloat16 *>(w_fwd), static_cast<__nv_bfloat16 *>(w_dgrad), cin, cout, taps, perm_c, perm_s);
+    return check_launch("hg_convt_pack_weight");
 }
 
 extern "C" int hg_convt_fwd(const void *x, const void *w_fwd, const float *bias, void *y_s2d, int batch, int cin, int cout,
@@ -561,18 +628,31 @@ extern "C" int hg_convt_fwd(const void *x, const void *w_fwd, const float *bias,
     rc = make_map_2d(&p.tmB, w_fwd, cin, (long long)c.taps * cout, bn);
     if (rc) return rc;
     p.X = c.X; p.Y = c.Y; p.Z = c.Z; p.Bn = batch;
-    p.BN = bn; p.k_chunks = cin / kBK;
+    p.BN = bn; p.k_chunks = cin / kBK; p.bias_mod = cout;
     const long long m_total = (long long)batch * c.X * c.Y * c.Z;
     p.m_total = (int)m_total; p.ld_out = (long long)c.P * cout; p.out = y_s2d; p.bias = bias; p.slope = neg_slope;
-    p.num_groups = c.P;
-    int ntap = 0, cur = -1;
+    // Narrow layers (Cout <= 128 == one N tile): several parity classes share a CTA, one TMEM accumulator
+    // each (<= 512 columns), so a CTA does classes_per_cta x the work per prologue/epilogue and writes one
+    // contiguous run of the s2d output row.
+    int cpc = 1;
+    if (bn == cout && c.P > 1) {
+        cpc = 512 / cout;
+        if (cpc > c.P) cpc = c.P;
+        while (c.P % cpc) --cpc;
+    }
+    p.epi_cols = cpc * bn;
+    p.num_groups = c.P / cpc;
+    int ntap = 0;
+    for (int g = 0; g < p.num_groups; ++g) p.groups[g] = Group{0, 0, g * cpc * cout, 0};
+    int cur = -1;
     for_each_class_tap(c, [&](int cls, int flat, int sx, int sy, int sz) {
+        const int g = cls / cpc;
         if (cls != cur) {
             cur = cls;
-            p.groups[cls] = Group{ntap, 0, cls * cout, 0};
+            if (cls % cpc == 0) p.groups[g].tap_begin = ntap;
         }
-        p.taps[ntap] = Tap{(int16_t)sx, (int16_t)sy, (int16_t)sz, 0, 0, flat * cout};
-        p.groups[cls].tap_count++;
+        p.taps[ntap] = Tap{(int16_t)sx, (int16_t)sy, (int16_t)sz, (int16_t)(cls % cpc), 0, flat * cout};
+        p.groups[g].tap_count++;
         ntap++;
     });
     const int m_tiles = (int)((m_total + kBM - 1) / kBM);
@@ -596,29 +676,63 @@ extern "C" int hg_convt_dgrad(const void *dy_s2d, const void *w_dgrad, void *dx,
     rc = make_map_2d(&p.tmB, w_dgrad, cout, (long long)c.taps * cin, bn);
     if (rc) return rc;
     p.X = c.X; p.Y = c.Y; p.Z = c.Z; p.Bn = batch;
-    p.BN = bn; p.k_chunks = cout / kBK;
+    p.BN = bn; p.epi_cols = bn; p.bias_mod = cin; p.k_chunks = cout / kBK;
     const long long m_total = (long long)batch * c.X * c.Y * c.Z;
     p.m_total = (int)m_total; p.ld_out = cin; p.out = dx; p.bias = nullptr; p.slope = 1.0f;
     p.num_groups = 1;
     int ntap = 0;
     for_each_class_tap(c, [&](int cls, int flat, int sx, int sy, int sz) {
         // forward: Y[2i+p] += X[i+s] W[k]   =>   dX[i'] += dY_s2d[i'-s, class p] W[k]
-        p.taps[ntap++] = Tap{(int16_t)-sx, (int16_t)-sy, (int16_t)-sz, 0, cls * cout, flat * cin};
+        p.taps[ntap++] = Tap{(int16_t)-sx, (int16_t)-sy, (int16_t)-sz, 0, cls * cout, flat * cin};   // one accumulator
     });
     p.groups[0] = Group{0, ntap, 0, 0};
     const int m_tiles = (int)((m_total + kBM - 1) / kBM);
     return launch_tap_gemm(p, m_tiles, cin / bn, static_cast<cudaStream_t>(stream), "hg_convt_dgrad");
 }
 
-extern "C" int hg_convt_wgrad(const void *x, const void *dy_s2d, float *dw_packed, int batch, int cin, int cout, int ndim,
-                              int size, int kernel, void *stream)
+struct WgradPlan { int bn, splits, pairs, pos_tiles; };
+
+static int wgrad_plan(const ConvShape &c, WgradPlan &pl, const char *who)
 {
-    HG_REQUIRE(x && dy_s2d && dw_packed, HG_ERR_INVALID_ARG, "hg_convt_wgrad: null pointer");
+    pl.bn = c.cout % 256 == 0 ? 256 : c.cout % 128 == 0 ? 128 : c.cout % 64 == 0 ? 64 : 0;
+    HG_REQUIRE(c.cin % kBM == 0 && pl.bn > 0, HG_ERR_UNSUPPORTED, "%s: need Cin %% 128 == 0 and Cout %% 64 == 0 (got %d, %d)", who,
+               c.cin, c.cout);
+    const long long positions = (long long)c.batch * c.X * c.Y * c.Z;
+    pl.pos_tiles = (int)((positions + 63) / 64);
+    pl.pairs = c.taps;                                          // every kernel tap belongs to exactly one parity class
+    const int out_tiles = (c.cin / kBM) * (c.cout / pl.bn) * pl.pairs;
+    int splits = (2 * sm_count() + out_tiles - 1) / out_tiles;   // >= 2 waves of CTAs: these kernels are L2-bound
+    if (splits > pl.pos_tiles / 8) splits = pl.pos_tiles / 8;    // keep >= 8 K-iterations per CTA
+    if (splits < 1) splits = 1;
+    pl.splits = splits;
+    return HG_OK;
+}
+
+extern "C" long long hg_convt_wgrad_workspace_bytes(int batch, int cin, int cout, int ndim, int size, int kernel)
+{
+    ConvShape c{batch, cin, cout, ndim, size, kernel};
+    if (conv_shape(c, "hg_convt_wgrad_workspace_bytes")) return -1;
+    WgradPlan pl;
+    if (wgrad_plan(c, pl, "hg_convt_wgrad_workspace_bytes")) return -1;
+    return (long long)pl.splits * c.taps * cin * cout * (long long)sizeof(float);
+}
+
+extern "C" int hg_convt_wgrad(const void *x, const void *dy_s2d, float *dw, void *workspace, long long workspace_bytes,
+                              int batch, int cin, int cout, int ndim, int size, int kernel, int perm_c, int perm_s,
+                              int accumulate, void *stream)
+{
+    HG_REQUIRE(x && dy_s2d && dw && workspace, HG_ERR_INVALID_ARG, "hg_convt_wgrad: null pointer");
     ConvShape c{batch, cin, cout, ndim, size, kernel};
     int rc = conv_shape(c, "hg_convt_wgrad");
     if (rc) return rc;
-    int bn = cout % 256 == 0 ? 256 : cout % 128 == 0 ? 128 : cout % 64 == 0 ? 64 : 0;
-    HG_REQUIRE(cin % kBM == 0 && bn > 0, HG_ERR_UNSUPPORTED, "hg_convt_wgrad: need Cin %% 128 == 0 and Cout %% 64 == 0 (got %d, %d)", cin, cout);
+    WgradPlan pl;
+    rc = wgrad_plan(c, pl, "hg_convt_wgrad");
+    if (rc) return rc;
+    rc = perm_ok("hg_convt_wgrad", cin, perm_c, perm_s);
+    if (rc) return rc;
+    HG_REQUIRE(workspace_bytes >= (long long)pl.splits * c.taps * cin * cout * (long long)sizeof(float), HG_ERR_INVALID_ARG,
+               "hg_convt_wgrad: workspace smaller than hg_convt_wgrad_workspace_bytes()");
+    const int bn = pl.bn;
     WgradParams p{};
     int bx, by, bz, bb;
     HG_REQUIRE(box_for(64, c.X, c.Y, c.Z, bx, by, bz, bb), HG_ERR_UNSUPPORTED, "hg_convt_wgrad: spatial size %d does not tile into 64-position boxes", size);
@@ -627,31 +741,31 @@ extern "C" int hg_convt_wgrad(const void *x, const void *dy_s2d, float *dw_packe
     rc = make_map_5d(&p.tmDY, dy_s2d, (long long)c.P * cout, c.X, c.Y, c.Z, batch, bx, by, bz, bb);
     if (rc) return rc;
     p.X = c.X; p.Y = c.Y; p.Z = c.Z; p.Bn = batch;
-    p.BN = bn; p.cin = cin; p.cout = cout; p.dw = dw_packed;
-    const long long positions = (long long)batch * c.X * c.Y * c.Z;
-    p.pos_tiles = (int)((positions + 63) / 64);
+    p.BN = bn; p.cin = cin; p.cout = cout; p.dw = static_cast<float *>(workspace); p.num_taps_total = c.taps;
+    p.pos_tiles = pl.pos_tiles;
     int np = 0;
     for_each_class_tap(c, [&](int cls, int flat, int sx, int sy, int sz) {
         p.pairs[np++] = WgradParams::Pair{(int16_t)sx, (int16_t)sy, (int16_t)sz, 0, cls * cout, flat};
     });
     p.num_pairs = np;
-    const int out_tiles = (cin / kBM) * (cout / bn) * np;
-    int splits = (2 * sm_count() + out_tiles - 1) / out_tiles;           // aim at >= 2 waves of CTAs
-    if (splits > p.pos_tiles / 8) splits = p.pos_tiles / 8;              // keep >= 8 K-iterations per CTA
-    if (splits < 1) splits = 1;
-    p.splits = splits;
+    p.splits = pl.splits;
     const int stage_bytes = 2 * 64 * 128 + (bn / 64) * 64 * 128;
-    p.stages = pick_stages(stage_bytes, (p.pos_tiles + splits - 1) / splits);
+    p.stages = pick_stages(stage_bytes, (p.pos_tiles + pl.splits - 1) / pl.splits);
     const size_t smem = (size_t)p.stages * stage_bytes + 1024;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    cudaError_t e = cudaMemsetAsync(dw_packed, 0, sizeof(float) * (size_t)c.taps * cin * cout, st);
-    if (e != cudaSuccess) return fail(HG_ERR_LAUNCH, "hg_convt_wgrad: memset failed: %s", cudaGetErrorString(e));
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(wgrad_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+        cudaFuncSetAttribute(wgrad_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
         attr_set = true;
     }
-    dim3 grid(cin / kBM, cout / bn, np * splits);
+    dim3 grid(cin / kBM, cout / bn, np * pl.splits);
     wgrad_gemm_kernel<<<grid, kThreads, smem, st>>>(p);
-    return check_launch("hg_convt_wgrad");
+    rc = check_launch("hg_convt_wgrad");
+    if (rc) return rc;
+    dim3 rgrid((cin + 15) / 16, (cout + 15) / 16);
+    const size_t rsmem = (size_t)16 * (16 * c.taps + 1) * sizeof(float);
+    wgrad_reduce_kernel<<<rgrid, 256, rsmem, st>>>(static_cast<const float *>(workspace), dw, cin, cout, c.taps, pl.splits,
+                                                  perm_c, perm_s, accumulate);
+    return check_launch("hg_convt_wgrad(reduce)");
 }

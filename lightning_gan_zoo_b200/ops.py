@@ -245,16 +245,31 @@ def convt_supported(cin: int, cout: int) -> bool:
     return cin % 128 == 0 and cout % 64 == 0
 
 
-def pack_convt_weight(weight: Tensor) -> Tuple[Tensor, Tensor]:
-    """torch ConvTranspose weight (Cin, Cout, k..) fp32 -> (w_fwd [t][Cout][Cin], w_dgrad [t][Cin][Cout]) bf16."""
+def pack_convt_weight(weight: Tensor, perm: Tuple[int, int] = (0, 0)) -> Tuple[Tensor, Tensor]:
+    """torch ConvTranspose weight (Cin, Cout, k..) fp32 -> (w_fwd [t][Cout][Cin], w_dgrad [t][Cin][Cout]) bf16.
+    perm = (C, S): input channels re-ordered for the HG_PROJ operand (packed y*C + c <-> torch c*S + S-1-y)."""
     _require_cuda(weight)
     w = weight.detach().float().contiguous()
     cin, cout = w.shape[0], w.shape[1]
     taps = w[0, 0].numel()
     wf = torch.empty((taps, cout, cin), dtype=torch.bfloat16, device=w.device)
     wd = torch.empty((taps, cin, cout), dtype=torch.bfloat16, device=w.device)
-    _lib.call("hg_convt_pack_weight", _ptr(w), _ptr(wf), _ptr(wd), cin, cout, taps, _stream())
+    _lib.call("hg_convt_pack_weight", _ptr(w), _ptr(wf), _ptr(wd), cin, cout, taps, perm[0], perm[1], _stream())
     return wf, wd
+
+
+def convt_wgrad(x_cl: Tensor, dy_s2d: Tensor, wshape, ndim: int, kernel: int, perm: Tuple[int, int] = (0, 0)) -> Tensor:
+    """Weight gradient in the torch parameter layout (fp32)."""
+    b, size, cin = x_cl.shape[0], x_cl.shape[1], x_cl.shape[-1]
+    cout = dy_s2d.shape[-1]
+    nbytes = _lib.load().hg_convt_wgrad_workspace_bytes(b, cin, cout, ndim, size, kernel)
+    if nbytes < 0:
+        raise _lib.HologanB200Error(f"hg_convt_wgrad: unsupported shape Cin={cin} Cout={cout} size={size}")
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=x_cl.device)
+    dw = torch.empty(tuple(wshape), dtype=torch.float32, device=x_cl.device)
+    _lib.call("hg_convt_wgrad", _ptr(x_cl), _ptr(dy_s2d), _ptr(dw), _ptr(ws), nbytes, b, cin, cout, ndim, size, kernel,
+              perm[0], perm[1], 0, _stream())
+    return dw
 
 
 def _conv_dims(x_cl: Tensor, ndim: int):
@@ -267,46 +282,43 @@ class _ConvT(torch.autograd.Function):
     """y_s2d = act(convT(x) + bias) with x (B,[S,]S,S,Cin) bf16 and y_s2d (B,[S,]S,S,P,Cout) bf16."""
 
     @staticmethod
-    def forward(ctx, x_cl, weight, bias, ndim, kernel, neg_slope):
+    def forward(ctx, x_cl, weight, bias, ndim, kernel, neg_slope, perm):
         _require_cuda(x_cl, weight)
         b, size, cin = _conv_dims(x_cl, ndim)
         cout = weight.shape[1]
         if weight.shape[0] != cin:
             raise ValueError("weight / activation channel mismatch")
-        wf, wd = pack_convt_weight(weight)
+        wf, wd = pack_convt_weight(weight, perm)
         nclass = 1 if kernel == 1 else 2 ** ndim
         y = torch.empty((b,) + (size,) * ndim + (nclass, cout), dtype=torch.bfloat16, device=x_cl.device)
         bias_f = None if bias is None else bias.detach().float().contiguous()
         _lib.call("hg_convt_fwd", _ptr(x_cl), _ptr(wf), _ptr(bias_f), _ptr(y), b, cin, cout, ndim, size, kernel,
                   ctypes.c_float(neg_slope), _stream())
         ctx.save_for_backward(x_cl, wd, y if neg_slope != 1.0 else None)
-        ctx.meta = (b, cin, cout, ndim, size, kernel, neg_slope, tuple(weight.shape), bias is not None)
+        ctx.meta = (b, cin, cout, ndim, size, kernel, neg_slope, tuple(weight.shape), bias is not None, perm)
         return y
 
     @staticmethod
     def backward(ctx, dy):
         x_cl, wd, y = ctx.saved_tensors
-        b, cin, cout, ndim, size, kernel, neg_slope, wshape, has_bias = ctx.meta
+        b, cin, cout, ndim, size, kernel, neg_slope, wshape, has_bias, perm = ctx.meta
         dy = dy.contiguous()
         if y is not None:                      # activation fused in the forward epilogue
             dy = torch.where(y > 0, dy, dy * neg_slope)
-        taps = kernel ** ndim
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x_cl)
             _lib.call("hg_convt_dgrad", _ptr(dy), _ptr(wd), _ptr(dx), b, cin, cout, ndim, size, kernel, _stream())
         if ctx.needs_input_grad[1]:
-            dwp = torch.empty((taps, cin, cout), dtype=torch.float32, device=dy.device)
-            _lib.call("hg_convt_wgrad", _ptr(x_cl), _ptr(dy), _ptr(dwp), b, cin, cout, ndim, size, kernel, _stream())
-            dw = torch.empty(wshape, dtype=torch.float32, device=dy.device)
-            _lib.call("hg_convt_unpack_wgrad", _ptr(dwp), _ptr(dw), cin, cout, taps, _stream())
+            dw = convt_wgrad(x_cl, dy, wshape, ndim, kernel, perm)
         if has_bias and ctx.needs_input_grad[2]:
             db = dy.reshape(-1, dy.shape[-2], cout).float().sum(dim=(0, 1))
-        return dx, dw, db, None, None, None
+        return dx, dw, db, None, None, None, None
 
 
-def convt(x_cl: Tensor, weight: Tensor, bias: Optional[Tensor], ndim: int, kernel: int, neg_slope: float = 1.0) -> Tensor:
-    return _ConvT.apply(x_cl, weight, bias, ndim, kernel, neg_slope)
+def convt(x_cl: Tensor, weight: Tensor, bias: Optional[Tensor], ndim: int, kernel: int, neg_slope: float = 1.0,
+          perm: Tuple[int, int] = (0, 0)) -> Tensor:
+    return _ConvT.apply(x_cl, weight, bias, ndim, kernel, neg_slope, perm)
 
 
 # ---- layout glue (pure data movement) -------------------------------------------------------------
@@ -364,3 +376,81 @@ class _AdaInChannelsLast(torch.autograd.Function):
 def adain_act_channels_last(x: Tensor, scale: Tensor, bias: Tensor, ndim: int, classes: int, neg_slope: float = 0.0,
                             eps: float = 1e-8) -> Tensor:
     return _AdaInChannelsLast.apply(x, scale, bias, ndim, classes, neg_slope, eps)
+
+
+# ------------------------------------------------------------------------------------------------
+# a2: ZMapping linear + ReLU (fp32), a11: final conv + tanh
+# ------------------------------------------------------------------------------------------------
+
+class _LinearRelu(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, z, weight, bias):
+        _require_cuda(z, weight, bias)
+        z = z.float().contiguous()
+        w = weight.float().contiguous()
+        bb = bias.float().contiguous()
+        b, k = z.shape
+        n = w.shape[0]
+        out = torch.empty((b, n), dtype=torch.float32, device=z.device)
+        _lib.call("hg_linear_relu_fwd", _ptr(z), _ptr(w), _ptr(bb), _ptr(out), b, k, n, _stream())
+        ctx.save_for_backward(z, w, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        z, w, out = ctx.saved_tensors
+        b, k = z.shape
+        n = w.shape[0]
+        dout = dout.float().contiguous()
+        dw = torch.empty_like(w)
+        db = torch.empty(n, dtype=torch.float32, device=z.device)
+        dz = torch.empty_like(z) if ctx.needs_input_grad[0] else None
+        _lib.call("hg_linear_relu_bwd", _ptr(z), _ptr(w), _ptr(out), _ptr(dout), _ptr(dw), _ptr(db), _ptr(dz), b, k, n, 0,
+                  _stream())
+        return dz, dw, db
+
+
+def linear_relu(z: Tensor, weight: Tensor, bias: Tensor) -> Tensor:
+    """relu(z @ weight.T + bias) in fp32 -- the ZMapping of reference hologan_generator.py:16-17."""
+    return _LinearRelu.apply(z, weight, bias)
+
+
+def final_conv_supported(cin: int, cout: int) -> bool:
+    lanes = cin // 8
+    return cin % 8 == 0 and 8 <= cin <= 256 and (lanes & (lanes - 1)) == 0 and 1 <= cout <= 4
+
+
+class _FinalConvTanh(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x_cl, weight, bias):
+        _require_cuda(x_cl, weight, bias)
+        if x_cl.dtype != torch.bfloat16 or not x_cl.is_contiguous() or x_cl.dim() != 4:
+            raise ValueError("x must be a contiguous (B,S,S,C) bf16 tensor")
+        b, s, cin = x_cl.shape[0], x_cl.shape[1], x_cl.shape[3]
+        w = weight.detach().float().contiguous()
+        bb = bias.detach().float().contiguous()
+        cout = w.shape[0]
+        out = torch.empty((b, cout, s, s), dtype=torch.float32, device=x_cl.device)
+        _lib.call("hg_final_conv_tanh_fwd", _ptr(x_cl), _ptr(w), _ptr(bb), _ptr(out), b, cin, cout, s, _stream())
+        ctx.save_for_backward(x_cl, w, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x_cl, w, out = ctx.saved_tensors
+        b, s, cin = x_cl.shape[0], x_cl.shape[1], x_cl.shape[3]
+        cout = w.shape[0]
+        dout = dout.float().contiguous()
+        nbytes = _lib.load().hg_final_conv_tanh_bwd_workspace_bytes(b, cin, cout, s)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=x_cl.device)
+        dx = torch.empty_like(x_cl) if ctx.needs_input_grad[0] else None
+        dw = torch.empty_like(w)
+        db = torch.empty(cout, dtype=torch.float32, device=x_cl.device)
+        _lib.call("hg_final_conv_tanh_bwd", _ptr(x_cl), _ptr(w), _ptr(out), _ptr(dout), _ptr(dx), _ptr(dw), _ptr(db),
+                  _ptr(ws), nbytes, b, cin, cout, s, _stream())
+        return dx, dw, db
+
+
+def final_conv_tanh(x_cl: Tensor, weight: Tensor, bias: Tensor) -> Tensor:
+    """tanh(conv2d(x, weight, bias, kernel 3, padding 1)) with x (B,S,S,C) bf16 NHWC -> (B,Cout,S,S) fp32 NCHW."""
+    return _FinalConvTanh.apply(x_cl, weight, bias)

@@ -47,7 +47,7 @@ def pack(w, taps):
     cin, cout = w.shape[:2]
     wf = torch.empty(taps, cout, cin, dtype=torch.bfloat16, device=DEV)
     wd = torch.empty(taps, cin, cout, dtype=torch.bfloat16, device=DEV)
-    _lib.call("hg_convt_pack_weight", P(w.contiguous()), P(wf), P(wd), cin, cout, taps, ops._stream())
+    _lib.call("hg_convt_pack_weight", P(w.contiguous()), P(wf), P(wd), cin, cout, taps, 0, 0, ops._stream())
     return wf, wd
 
 
@@ -121,10 +121,9 @@ def test_convt_fwd_dgrad_wgrad(ndim, kernel, batch, cin, cout, size):
     dx_nc = dx.permute(*([0, ndim + 1] + list(range(1, ndim + 1))))
     assert rel_err(dx_nc.float(), xr.grad) < 2 ** -7
     if cin % 128 == 0 and cout % 64 == 0:
-        dwp = torch.empty(taps, cin, cout, dtype=torch.float32, device=DEV)
-        _lib.call("hg_convt_wgrad", P(x_cl), P(dy_s2d), P(dwp), batch, cin, cout, ndim, size, kernel, ops._stream())
-        dw = torch.empty_like(wr)
-        _lib.call("hg_convt_unpack_wgrad", P(dwp), P(dw), cin, cout, taps, ops._stream())
+        dw = ops.convt_wgrad(x_cl, dy_s2d, wr.shape, ndim, kernel)
+        dw2 = ops.convt_wgrad(x_cl, dy_s2d, wr.shape, ndim, kernel)
+        assert torch.equal(dw, dw2)               # split-K partials are reduced in a fixed order
         assert rel_err(dw, wr.grad) < 1e-4        # fp32 accumulation of exact bf16 products
 
 
@@ -140,3 +139,20 @@ def test_fwd_relu_epilogue_and_errors():
         _lib.call("hg_convt_fwd", P(x), P(wf), P(None), P(y), 2, 48, 32, 2, 16, 1, ctypes.c_float(0.0), ops._stream())
     with pytest.raises(_lib.HologanB200Error, match="supported"):
         _lib.call("hg_convt_fwd", P(x), P(wf), P(None), P(y), 2, 64, 32, 2, 16, 3, ctypes.c_float(0.0), ops._stream())
+
+
+def test_projection_channel_permutation():
+    """pack / wgrad with perm=(C,S): GEMM K index y*C + c <-> torch channel c*S + (S-1-y) (reference :130-133)."""
+    c, sz, cout, b = 8, 16, 64, 2
+    cin = c * sz
+    g = torch.Generator().manual_seed(5)
+    w = (torch.randn(cin, cout, 1, 1, generator=g) * 0.05).to(DEV)
+    wf, wd = ops.pack_convt_weight(w, (c, sz))
+    ref = w.reshape(c, sz, cout).flip(1).permute(1, 0, 2).reshape(cin, cout)          # [y*C + c][co]
+    assert torch.equal(wd[0], bf(ref)) and torch.equal(wf[0], bf(ref.t()))
+    x = bf(torch.randn(b, 16, 16, cin, generator=g)).to(DEV)
+    dy = bf(torch.randn(b, 16, 16, 1, cout, generator=g)).to(DEV)
+    dw = ops.convt_wgrad(x, dy, w.shape, 2, 1, (c, sz))
+    dref = (x.float().reshape(-1, cin).t() @ dy.float().reshape(-1, cout))            # [k'][co]
+    dref = dref.reshape(sz, c, cout).permute(1, 0, 2).flip(1).reshape(cin, cout, 1, 1)
+    assert rel_err(dw, dref) < 1e-4

@@ -79,9 +79,51 @@ def adain():
                   f"  bwd {tb*1e6:7.1f} us {bbt/tb/1e9:6.0f} GB/s ({bbt/tb/1e9/PEAK*100:4.1f}%)")
 
 
+def conv():
+    """The 15 dense contractions of one generator fwd+bwd at B=64 (bf16, tcgen05), TFLOP/s against the measured
+    bf16 matmul peak.  Algorithmic FLOPs = 2 * B * positions * Cin * Cout * taps_used."""
+    import ctypes
+    from lightning_gan_zoo_b200 import _lib
+    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {"bf16_tflops": 1590.0}
+    peak = peaks["bf16_tflops"]
+    B = 64
+    P = ops._ptr
+    layers = [("block1", 3, 3, 512, 128, 4), ("block2", 3, 3, 128, 64, 8), ("proj1x1", 2, 1, 1024, 1024, 16),
+              ("block3", 2, 4, 1024, 256, 16), ("block4", 2, 4, 256, 64, 32)]
+    print(f"# conv kernels at B={B}; bf16 peak {peak} TFLOP/s (burst, measured)")
+    tot = {"fwd": 0.0, "dgrad": 0.0, "wgrad": 0.0}
+    for name, ndim, k, cin, cout, size in layers:
+        sp = (size,) * ndim
+        taps = k ** ndim
+        ncls = 1 if k == 1 else 2 ** ndim
+        pos = size ** ndim
+        flops = 2.0 * B * pos * cin * cout * taps
+        nb = 3
+        xs = [torch.randn(B, *sp, cin, device=DEV).to(torch.bfloat16) for _ in range(nb)]
+        dys = [torch.randn(B, *sp, ncls, cout, device=DEV).to(torch.bfloat16) for _ in range(nb)]
+        w = torch.randn(cin, cout, *((k,) * ndim), device=DEV) * 0.02
+        wf, wd = ops.pack_convt_weight(w)
+        y = torch.empty_like(dys[0]); dx = torch.empty_like(xs[0]); dw = torch.empty_like(w)
+        nws = _lib.load().hg_convt_wgrad_workspace_bytes(B, cin, cout, ndim, size, k)
+        ws = torch.empty(nws, dtype=torch.uint8, device=DEV)
+        st = ops._stream()
+        f = lambda i: _lib.call("hg_convt_fwd", P(xs[i]), P(wf), P(None), P(y), B, cin, cout, ndim, size, k, ctypes.c_float(1.0), st)
+        g = lambda i: _lib.call("hg_convt_dgrad", P(dys[i]), P(wd), P(dx), B, cin, cout, ndim, size, k, st)
+        h = lambda i: _lib.call("hg_convt_wgrad", P(xs[i]), P(dys[i]), P(dw), P(ws), nws, B, cin, cout, ndim, size, k, 0, 0, 0, st)
+        row = f"{name:8s} {flops/1e9:7.1f} GF"
+        for tag, fn in (("fwd", f), ("dgrad", g), ("wgrad", h)):
+            t = time_rot(fn, list(range(nb)), iters=12)
+            tot[tag] += t
+            row += f" | {tag} {t*1e6:7.1f} us {flops/t/1e12:6.0f} TF/s ({flops/t/1e12/peak*100:4.1f}%)"
+        print(row)
+    print("totals: " + ", ".join(f"{k} {v*1e6:.0f} us" for k, v in tot.items()))
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     if what in ("rotate", "all"):
         rotate()
     if what in ("adain", "all"):
         adain()
+    if what in ("conv", "all"):
+        conv()

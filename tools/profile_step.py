@@ -29,7 +29,16 @@ from torch.autograd import DeviceType
 kern = [e for e in prof.key_averages() if e.device_type == DeviceType.CUDA]
 tot = sum(e.self_device_time_total for e in kern)
 print(f"GPU kernel time per step: {tot / steps / 1e3:.3f} ms over {steps} steps ({len(kern)} distinct kernels)")
-mine = sum(e.self_device_time_total for e in kern if "hg::" in e.key)
-print(f"  of which libhologan_b200 kernels: {mine / steps / 1e3:.3f} ms")
+def cat(k):
+    if "hg::" in k: return "libhologan_b200"
+    if any(t in k for t in ("cudnn", "cutlass", "nvjet", "implicit_convolve", "convolve_common", "gemv", "sgemm", "nhwcAddPadding")): return "cuDNN/cuBLAS (D convs, final conv, linears)"
+    if "Memset" in k or "Memcpy" in k: return "memset/memcpy"
+    if "multi_tensor_apply" in k or "Adam" in k: return "fused Adam"
+    return "torch elementwise/reduce/copy"
+cats = {}
+for e in kern:
+    cats[cat(e.key)] = cats.get(cat(e.key), 0) + e.self_device_time_total
+for k, v in sorted(cats.items(), key=lambda kv: -kv[1]):
+    print(f"  {v / steps / 1e3:7.3f} ms  {k}")
 for e in sorted(kern, key=lambda e: -e.self_device_time_total)[:40]:
     print(f"{e.self_device_time_total / steps:9.1f} us/step  x{e.count / steps:6.1f}  {e.key[:120]}")
