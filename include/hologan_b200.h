@@ -116,13 +116,16 @@ int hg_adain_act_bwd(const void *x, const void *dy, const float *scale, const fl
  *   x  (B, S^ndim, classes, C) bf16: the space-to-depth output of hg_convt_fwd (classes = 2^ndim), or a
  *      plain channels-last tensor (classes = 1)
  *   y  (B, (2S)^ndim, C) bf16 plain channels-last (the depth-to-space shuffle happens in the store);
- *      dy has y's layout, dx has x's layout.  C % 16 == 0, S^ndim * classes <= 4096. */
+ *      dy has y's layout, dx has x's layout.  C % 16 == 0, S^ndim * classes <= 4096.
+ *   scale / bias may both be NULL (= 1 / 0) and dscale / dbias may both be NULL (not computed); with
+ *   biased_var = 1, eps = 1e-5, neg_slope = 0.2 that is the discriminator's InstanceNorm2d + LeakyReLU
+ *   (core/models/hologan_discriminator.py:16-17,21-22) on channels-last activations. */
 int hg_adain_cl_fwd(const void *x, const float *scale, const float *bias, void *y, float *save_mean, float *save_rstd,
                     int batch, int channels, int ndim, int size, int classes, int sb_stride, float eps, float neg_slope,
-                    void *stream);
+                    int biased_var, void *stream);
 int hg_adain_cl_bwd(const void *x, const void *dy, const float *scale, const float *bias, const float *save_mean,
                     const float *save_rstd, void *dx, float *dscale, float *dbias, int batch, int channels, int ndim,
-                    int size, int classes, int sb_stride, int dsb_stride, float neg_slope, void *stream);
+                    int size, int classes, int sb_stride, int dsb_stride, float neg_slope, int biased_var, void *stream);
 
 /* ---- a4 / a9 / a10: transposed convolutions and the 1x1 projection as tcgen05 implicit GEMMs -------
  * Replace nn.ConvTranspose3d(k3,s2,p1,op1) / nn.ConvTranspose2d(k4,s2,p1) / nn.ConvTranspose2d(k1)
@@ -153,6 +156,15 @@ int hg_convt_dgrad(const void *dy_s2d, const void *w_dgrad, void *dx, int batch,
 long long hg_convt_wgrad_workspace_bytes(int batch, int cin, int cout, int ndim, int size, int kernel);
 int hg_convt_wgrad(const void *x, const void *dy_s2d, float *dw, void *workspace, long long workspace_bytes, int batch,
                    int cin, int cout, int ndim, int size, int kernel, int perm_c, int perm_s, int accumulate, void *stream);
+
+/* Backward of the bias + activation fused into hg_convt_fwd's epilogue (the projection's relu(conv1x1(x)),
+ * core/models/hologan_generator.py:135-136), one pass:
+ *   dpre[m,n] = y[m,n] > 0 ? dy[m,n] : neg_slope * dy[m,n]   (rows x cols, bf16, row-major, cols % 8 == 0)
+ *   dbias[n]  = sum_m dpre[m,n]  (fp32; NULL = not needed, then workspace may be NULL)
+ * Deterministic two-stage column sum through `workspace`. */
+long long hg_act_bwd_bias_workspace_bytes(long long rows, int cols);
+int hg_act_bwd_bias(const void *y, const void *dy, void *dpre, float *dbias, void *workspace, long long workspace_bytes,
+                    long long rows, int cols, float neg_slope, void *stream);
 
 /* Plain GEMM on the same pipeline: D[M,N] = act(A[M,K] @ B[N,K]^T + bias[N]); bf16 row-major A, B, D
  * (row stride of D = ldd elements).  Used for the batched ZMapping (a2). */

@@ -28,6 +28,7 @@ constexpr int kMaxStages = 8;
 constexpr int kMaxTaps = 32;
 constexpr int kMaxGroups = 8;
 constexpr int kSmemBudget = 200 * 1024;
+constexpr int kWgradSmemBudget = 100 * 1024;      // two wgrad CTAs per SM
 
 struct Tap {
     int16_t sx, sy, sz;
@@ -343,64 +344,89 @@ __device__ __forceinline__ int torch_cin(int ci, int perm_c, int perm_s)
     return c * perm_s + (perm_s - 1 - y);
 }
 
+// Bricks of kBrickCi x kBrickCo x T weights go through shared memory so that both sides of the transposition
+// are coalesced: the torch layout (Cin, Cout, T) is read / written in runs of kBrickCo*T floats, the GEMM
+// layouts in runs of kBrickCo (or kBrickCi) consecutive elements.  The tap index is padded to an odd pitch
+// (bank-conflict-free for both access directions).
+constexpr int kBrickCi = 16;
+constexpr int kBrickCo = 32;
+__host__ __device__ inline int brick_tpitch(int taps) { return taps | 1; }
+__host__ __device__ inline int brick_row_pitch(int taps) { return kBrickCo * brick_tpitch(taps) + 1; }
+
 // torch (Cin, Cout, T) fp32 -> w_fwd[t][co][ci] (B operand of forward: rows = Cout, K = Cin) and
-// w_dgrad[t][ci][co] (rows = Cin, K = Cout), bf16.  One CTA = a 16(ci) x 16(co) x T brick through smem:
-// global reads are 16*T-float runs, writes 32-byte runs.
+// w_dgrad[t][ci][co] (rows = Cin, K = Cout), bf16, written as bf16x2 pairs.
 __global__ void __launch_bounds__(256) pack_weight_kernel(const float *__restrict__ w, __nv_bfloat16 *__restrict__ w_fwd,
                                                           __nv_bfloat16 *__restrict__ w_dgrad, int cin, int cout, int taps,
                                                           int perm_c, int perm_s)
 {
-    extern __shared__ float brick[];                    // [16 ci][16 co][T] (+1 pad per ci row)
-    const int ci0 = blockIdx.x * 16, co0 = blockIdx.y * 16;
-    const int row_len = 16 * taps, pitch = row_len + 1;
-    for (int i = threadIdx.x; i < 16 * row_len; i += blockDim.x) {
+    extern __shared__ float brick[];                    // [kBrickCi][kBrickCo][tpitch] (+1 pad per ci row)
+    const int ci0 = blockIdx.x * kBrickCi, co0 = blockIdx.y * kBrickCo;
+    const int row_len = kBrickCo * taps, tp = brick_tpitch(taps), pitch = brick_row_pitch(taps);
+    for (int i = threadIdx.x; i < kBrickCi * row_len; i += blockDim.x) {
         const int r = i / row_len, c = i - r * row_len;
+        const int co = c / taps, t = c - co * taps;
         float v = 0.f;
-        if (ci0 + r < cin && co0 + c / taps < cout)
+        if (ci0 + r < cin && co0 + co < cout)
             v = w[((size_t)torch_cin(ci0 + r, perm_c, perm_s) * cout + co0) * taps + c];
-        brick[r * pitch + c] = v;
+        brick[r * pitch + co * tp + t] = v;
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < 256 * taps; i += blockDim.x) {
-        const int t = i >> 8, rem = i & 255;
-        {   // dgrad layout: [t][ci][co] -> co fastest
-            const int ci = rem >> 4, co = rem & 15;
-            if (w_dgrad && ci0 + ci < cin && co0 + co < cout)
-                w_dgrad[((size_t)t * cin + ci0 + ci) * cout + co0 + co] = __float2bfloat16_rn(brick[ci * pitch + co * taps + t]);
+    if (w_dgrad) {      // [t][ci][co]: a half-warp writes one (t, ci) row of 32 co as 16 bf16x2
+        for (int i = threadIdx.x; i < taps * kBrickCi * (kBrickCo / 2); i += blockDim.x) {
+            const int cp = i % (kBrickCo / 2), ci = (i / (kBrickCo / 2)) % kBrickCi, t = i / (kBrickCi * (kBrickCo / 2));
+            if (ci0 + ci < cin && co0 + 2 * cp < cout) {
+                const float *src = brick + ci * pitch + (2 * cp) * tp + t;
+                *reinterpret_cast<__nv_bfloat162 *>(w_dgrad + ((size_t)t * cin + ci0 + ci) * cout + co0 + 2 * cp) =
+                    __floats2bfloat162_rn(src[0], src[tp]);
+            }
         }
-        {   // fwd layout: [t][co][ci] -> ci fastest
-            const int co = rem >> 4, ci = rem & 15;
-            if (w_fwd && ci0 + ci < cin && co0 + co < cout)
-                w_fwd[((size_t)t * cout + co0 + co) * cin + ci0 + ci] = __float2bfloat16_rn(brick[ci * pitch + co * taps + t]);
+    }
+    if (w_fwd) {        // [t][co][ci]: 8 threads write one (t, co) row of 16 ci as bf16x2
+        for (int i = threadIdx.x; i < taps * kBrickCo * (kBrickCi / 2); i += blockDim.x) {
+            const int cp = i % (kBrickCi / 2), co = (i / (kBrickCi / 2)) % kBrickCo, t = i / (kBrickCo * (kBrickCi / 2));
+            if (ci0 + 2 * cp < cin && co0 + co < cout) {
+                const float *src = brick + (2 * cp) * pitch + co * tp + t;
+                *reinterpret_cast<__nv_bfloat162 *>(w_fwd + ((size_t)t * cout + co0 + co) * cin + ci0 + 2 * cp) =
+                    __floats2bfloat162_rn(src[0], src[pitch]);
+            }
         }
     }
 }
 
-// Sum the split-K partials [split][t][ci][co] and write the torch layout (Cin, Cout, T) fp32.
-// accumulate != 0: dw += result (lets the caller target a live .grad buffer).
+// Sum the split-K partials [split][t][ci][co] (one warp reads one 128-byte (t, ci) row of 32 co per split, four
+// splits in flight) and write the torch layout (Cin, Cout, T) fp32.  accumulate != 0: dw += result (lets the
+// caller target a live .grad buffer).
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float *__restrict__ partial, float *__restrict__ dw, int cin,
                                                            int cout, int taps, int splits, int perm_c, int perm_s,
                                                            int accumulate)
 {
-    extern __shared__ float brick[];                    // [16 ci][16 co][T]
-    const int ci0 = blockIdx.x * 16, co0 = blockIdx.y * 16;
-    const int row_len = 16 * taps, pitch = row_len + 1;
+    extern __shared__ float brick[];
+    const int ci0 = blockIdx.x * kBrickCi, co0 = blockIdx.y * kBrickCo;
+    const int row_len = kBrickCo * taps, tp = brick_tpitch(taps), pitch = brick_row_pitch(taps);
     const size_t split_stride = (size_t)taps * cin * cout;
-    for (int i = threadIdx.x; i < 256 * taps; i += blockDim.x) {
-        const int t = i >> 8, rem = i & 255, ci = rem >> 4, co = rem & 15;
+    for (int i = threadIdx.x; i < taps * kBrickCi * kBrickCo; i += blockDim.x) {
+        const int co = i % kBrickCo, ci = (i / kBrickCo) % kBrickCi, t = i / (kBrickCi * kBrickCo);
         float v = 0.f;
         if (ci0 + ci < cin && co0 + co < cout) {
             const float *src = partial + ((size_t)t * cin + ci0 + ci) * cout + co0 + co;
-            for (int sp = 0; sp < splits; ++sp) v += src[sp * split_stride];
+            int sp = 0;
+            for (; sp + 4 <= splits; sp += 4) {
+                const float a0 = src[(size_t)sp * split_stride], a1 = src[(size_t)(sp + 1) * split_stride];
+                const float a2 = src[(size_t)(sp + 2) * split_stride], a3 = src[(size_t)(sp + 3) * split_stride];
+                v += a0; v += a1; v += a2; v += a3;           // fixed order
+            }
+            for (; sp < splits; ++sp) v += src[(size_t)sp * split_stride];
         }
-        brick[ci * pitch + co * taps + t] = v;
+        brick[ci * pitch + co * tp + t] = v;
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < 16 * row_len; i += blockDim.x) {
+    for (int i = threadIdx.x; i < kBrickCi * row_len; i += blockDim.x) {
         const int r = i / row_len, c = i - r * row_len;
-        if (ci0 + r < cin && co0 + c / taps < cout) {
+        const int co = c / taps, t = c - co * taps;
+        if (ci0 + r < cin && co0 + co < cout) {
             float *dst = dw + ((size_t)torch_cin(ci0 + r, perm_c, perm_s) * cout + co0) * taps + c;
-            *dst = accumulate ? *dst + brick[r * pitch + c] : brick[r * pitch + c];
+            const float v = brick[r * pitch + co * tp + t];
+            *dst = accumulate ? *dst + v : v;
         }
     }
 }
@@ -481,9 +507,9 @@ static int pick_bn(int n)
     return 0;
 }
 
-static int pick_stages(int stage_bytes, int iters)
+static int pick_stages(int stage_bytes, int iters, int budget = kSmemBudget)
 {
-    int s = (kSmemBudget - 1024) / stage_bytes;
+    int s = (budget - 1024) / stage_bytes;
     if (s > kMaxStages) s = kMaxStages;
     if (s > iters) s = iters < 1 ? 1 : iters;
     return s;
@@ -604,8 +630,14 @@ extern "C" int hg_convt_pack_weight(const float *w, void *w_fwd, void *w_dgrad, 
     HG_REQUIRE(cin > 0 && cout > 0 && taps > 0 && taps <= 27, HG_ERR_INVALID_ARG, "hg_convt_pack_weight: bad dims");
     int rc = perm_ok("hg_convt_pack_weight", cin, perm_c, perm_s);
     if (rc) return rc;
-    dim3 grid((cin + 15) / 16, (cout + 15) / 16);
-    const size_t smem = (size_t)16 * (16 * taps + 1) * sizeof(float);
+    HG_REQUIRE(cin % 2 == 0 && cout % 2 == 0, HG_ERR_UNSUPPORTED, "hg_convt_pack_weight: Cin and Cout must be even");
+    dim3 grid((cin + kBrickCi - 1) / kBrickCi, (cout + kBrickCo - 1) / kBrickCo);
+    const size_t smem = (size_t)kBrickCi * brick_row_pitch(taps) * sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(pack_weight_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        attr_set = true;
+    }
     pack_weight_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(
         w, static_cast<__nv_bfloat16 *>(w_fwd), static_cast<__nv_bfloat16 *>(w_dgrad), cin, cout, taps, perm_c, perm_s);
     return check_launch("hg_convt_pack_weight");
@@ -701,7 +733,9 @@ static int wgrad_plan(const ConvShape &c, WgradPlan &pl, const char *who)
     pl.pos_tiles = (int)((positions + 63) / 64);
     pl.pairs = c.taps;                                          // every kernel tap belongs to exactly one parity class
     const int out_tiles = (c.cin / kBM) * (c.cout / pl.bn) * pl.pairs;
-    int splits = (2 * sm_count() + out_tiles - 1) / out_tiles;   // >= 2 waves of CTAs: these kernels are L2-bound
+    // Split K so that all CTAs are resident at once (two per SM, kWgradSmemBudget each): no tail wave, and a
+    // CTA's prologue / epilogue overlaps its neighbour's main loop.
+    int splits = (2 * sm_count()) / out_tiles;
     if (splits > pl.pos_tiles / 8) splits = pl.pos_tiles / 8;    // keep >= 8 K-iterations per CTA
     if (splits < 1) splits = 1;
     pl.splits = splits;
@@ -750,12 +784,12 @@ extern "C" int hg_convt_wgrad(const void *x, const void *dy_s2d, float *dw, void
     p.num_pairs = np;
     p.splits = pl.splits;
     const int stage_bytes = 2 * 64 * 128 + (bn / 64) * 64 * 128;
-    p.stages = pick_stages(stage_bytes, (p.pos_tiles + pl.splits - 1) / pl.splits);
+    p.stages = pick_stages(stage_bytes, (p.pos_tiles + pl.splits - 1) / pl.splits, kWgradSmemBudget);
     const size_t smem = (size_t)p.stages * stage_bytes + 1024;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(wgrad_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+        cudaFuncSetAttribute(wgrad_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgradSmemBudget);
         cudaFuncSetAttribute(wgrad_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
         attr_set = true;
     }
@@ -763,8 +797,8 @@ extern "C" int hg_convt_wgrad(const void *x, const void *dy_s2d, float *dw, void
     wgrad_gemm_kernel<<<grid, kThreads, smem, st>>>(p);
     rc = check_launch("hg_convt_wgrad");
     if (rc) return rc;
-    dim3 rgrid((cin + 15) / 16, (cout + 15) / 16);
-    const size_t rsmem = (size_t)16 * (16 * c.taps + 1) * sizeof(float);
+    dim3 rgrid((cin + kBrickCi - 1) / kBrickCi, (cout + kBrickCo - 1) / kBrickCo);
+    const size_t rsmem = (size_t)kBrickCi * brick_row_pitch(c.taps) * sizeof(float);
     wgrad_reduce_kernel<<<rgrid, 256, rsmem, st>>>(static_cast<const float *>(workspace), dw, cin, cout, c.taps, pl.splits,
                                                   perm_c, perm_s, accumulate);
     return check_launch("hg_convt_wgrad(reduce)");

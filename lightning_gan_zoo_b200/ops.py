@@ -258,18 +258,56 @@ def pack_convt_weight(weight: Tensor, perm: Tuple[int, int] = (0, 0)) -> Tuple[T
     return wf, wd
 
 
-def convt_wgrad(x_cl: Tensor, dy_s2d: Tensor, wshape, ndim: int, kernel: int, perm: Tuple[int, int] = (0, 0)) -> Tensor:
-    """Weight gradient in the torch parameter layout (fp32)."""
+def convt_wgrad(x_cl: Tensor, dy_s2d: Tensor, wshape, ndim: int, kernel: int, perm: Tuple[int, int] = (0, 0),
+                accumulate_into: Optional[Tensor] = None) -> Optional[Tensor]:
+    """Weight gradient in the torch parameter layout (fp32).  With `accumulate_into` (a contiguous fp32 tensor of
+    the parameter's shape, e.g. its live .grad) the result is ADDED there and None is returned."""
     b, size, cin = x_cl.shape[0], x_cl.shape[1], x_cl.shape[-1]
     cout = dy_s2d.shape[-1]
     nbytes = _lib.load().hg_convt_wgrad_workspace_bytes(b, cin, cout, ndim, size, kernel)
     if nbytes < 0:
         raise _lib.HologanB200Error(f"hg_convt_wgrad: unsupported shape Cin={cin} Cout={cout} size={size}")
     ws = torch.empty(nbytes, dtype=torch.uint8, device=x_cl.device)
-    dw = torch.empty(tuple(wshape), dtype=torch.float32, device=x_cl.device)
+    if accumulate_into is not None:
+        dw, acc = accumulate_into, 1
+    else:
+        dw, acc = torch.empty(tuple(wshape), dtype=torch.float32, device=x_cl.device), 0
     _lib.call("hg_convt_wgrad", _ptr(x_cl), _ptr(dy_s2d), _ptr(dw), _ptr(ws), nbytes, b, cin, cout, ndim, size, kernel,
-              perm[0], perm[1], 0, _stream())
-    return dw
+              perm[0], perm[1], acc, _stream())
+    return None if acc else dw
+
+
+def act_bwd_bias(y: Tensor, dy: Tensor, neg_slope: float, want_bias: bool) -> Tuple[Tensor, Optional[Tensor]]:
+    """(dpre, dbias): gradient through `y = act(pre + bias)` in one pass over the bf16 tensors (last dim = columns)."""
+    _require_cuda(y, dy)
+    if y.dtype != torch.bfloat16 or dy.dtype != torch.bfloat16 or not y.is_contiguous() or not dy.is_contiguous():
+        raise ValueError("y / dy must be contiguous bf16 tensors")
+    cols = y.shape[-1]
+    rows = y.numel() // cols
+    dpre = torch.empty_like(dy)
+    db = ws = None
+    nbytes = 0
+    if want_bias:
+        nbytes = _lib.load().hg_act_bwd_bias_workspace_bytes(rows, cols)
+        if nbytes < 0:
+            raise _lib.HologanB200Error(f"hg_act_bwd_bias: unsupported shape rows={rows} cols={cols}")
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=y.device)
+        db = torch.empty(cols, dtype=torch.float32, device=y.device)
+    _lib.call("hg_act_bwd_bias", _ptr(y), _ptr(dy), _ptr(dpre), _ptr(db), _ptr(ws), nbytes, rows, cols,
+              ctypes.c_float(neg_slope), _stream())
+    return dpre, db
+
+
+def _direct_grad_target(param, shape) -> Optional[Tensor]:
+    """The parameter's live .grad if the owner opted in (`param._hg_direct_grad = True`, set by HologanTrainer
+    on its flat gradient buffers): the wgrad kernel then accumulates into it and autograd's extra
+    read-modify-write pass over the gradient is skipped."""
+    if param is None or not getattr(param, "_hg_direct_grad", False):
+        return None
+    g = param.grad
+    if g is None or g.dtype != torch.float32 or not g.is_contiguous() or tuple(g.shape) != tuple(shape):
+        return None
+    return g
 
 
 def _conv_dims(x_cl: Tensor, ndim: int):
@@ -296,6 +334,7 @@ class _ConvT(torch.autograd.Function):
                   ctypes.c_float(neg_slope), _stream())
         ctx.save_for_backward(x_cl, wd, y if neg_slope != 1.0 else None)
         ctx.meta = (b, cin, cout, ndim, size, kernel, neg_slope, tuple(weight.shape), bias is not None, perm)
+        ctx.weight_param = weight if isinstance(weight, torch.nn.Parameter) else None
         return y
 
     @staticmethod
@@ -303,16 +342,22 @@ class _ConvT(torch.autograd.Function):
         x_cl, wd, y = ctx.saved_tensors
         b, cin, cout, ndim, size, kernel, neg_slope, wshape, has_bias, perm = ctx.meta
         dy = dy.contiguous()
-        if y is not None:                      # activation fused in the forward epilogue
-            dy = torch.where(y > 0, dy, dy * neg_slope)
         dx = dw = db = None
+        want_db = has_bias and ctx.needs_input_grad[2]
+        nclass = dy.shape[-2]
+        if y is not None:                      # activation (+ bias) fused in the forward epilogue: one pass
+            if nclass == 1 or not want_db:
+                dy, db = act_bwd_bias(y, dy, neg_slope, want_db)
+            else:
+                dy, _ = act_bwd_bias(y, dy, neg_slope, False)
+        if want_db and db is None:
+            db = dy.reshape(-1, nclass, cout).float().sum(dim=(0, 1))
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x_cl)
             _lib.call("hg_convt_dgrad", _ptr(dy), _ptr(wd), _ptr(dx), b, cin, cout, ndim, size, kernel, _stream())
         if ctx.needs_input_grad[1]:
-            dw = convt_wgrad(x_cl, dy, wshape, ndim, kernel, perm)
-        if has_bias and ctx.needs_input_grad[2]:
-            db = dy.reshape(-1, dy.shape[-2], cout).float().sum(dim=(0, 1))
+            dw = convt_wgrad(x_cl, dy, wshape, ndim, kernel, perm,
+                             accumulate_into=_direct_grad_target(ctx.weight_param, wshape))
         return dx, dw, db, None, None, None, None
 
 
@@ -342,40 +387,49 @@ def nc_to_channels_last(x: Tensor) -> Tensor:
 
 class _AdaInChannelsLast(torch.autograd.Function):
     """x (B,[S,]S,S,P,C) bf16 (s2d conv output, P = 2^ndim) or (B,[S,]S,S,C) (P = 1)  ->
-    y (B,[2S,]2S,2S,C) bf16 channels-last."""
+    y (B,[2S,]2S,2S,C) bf16 channels-last.  scale / bias None = 1 / 0 (no style gradients)."""
 
     @staticmethod
-    def forward(ctx, x, scale, bias, ndim, classes, neg_slope, eps):
+    def forward(ctx, x, scale, bias, ndim, classes, neg_slope, eps, biased):
         _require_cuda(x, scale, bias)
         if x.dtype != torch.bfloat16 or not x.is_contiguous():
             raise ValueError("x must be a contiguous bf16 tensor")
         b, size, c = x.shape[0], x.shape[1], x.shape[-1]
-        sbs = _style_stride(scale, bias)
+        sbs = _style_stride(scale, bias) if scale is not None else 0
         up = 2 if classes > 1 else 1
         y = torch.empty((b,) + (up * size,) * ndim + (c,), dtype=torch.bfloat16, device=x.device)
         mean = torch.empty((b, c), dtype=torch.float32, device=x.device)
         rstd = torch.empty((b, c), dtype=torch.float32, device=x.device)
         _lib.call("hg_adain_cl_fwd", _ptr(x), _ptr(scale), _ptr(bias), _ptr(y), _ptr(mean), _ptr(rstd), b, c, ndim, size,
-                  classes, sbs, ctypes.c_float(eps), ctypes.c_float(neg_slope), _stream())
+                  classes, sbs, ctypes.c_float(eps), ctypes.c_float(neg_slope), int(biased), _stream())
         ctx.save_for_backward(x, scale, bias, mean, rstd)
-        ctx.meta = (b, c, ndim, size, classes, sbs, float(neg_slope))
+        ctx.meta = (b, c, ndim, size, classes, sbs, float(neg_slope), int(biased))
         return y
 
     @staticmethod
     def backward(ctx, dy):
         x, scale, bias, mean, rstd = ctx.saved_tensors
-        b, c, ndim, size, classes, sbs, neg_slope = ctx.meta
+        b, c, ndim, size, classes, sbs, neg_slope, biased = ctx.meta
         dy = dy.contiguous()
         dx = torch.empty_like(x)
-        dsb = torch.empty((2, b, c), dtype=torch.float32, device=x.device)
+        dsb = torch.empty((2, b, c), dtype=torch.float32, device=x.device) if scale is not None else None
         _lib.call("hg_adain_cl_bwd", _ptr(x), _ptr(dy), _ptr(scale), _ptr(bias), _ptr(mean), _ptr(rstd), _ptr(dx),
-                  _ptr(dsb[0]), _ptr(dsb[1]), b, c, ndim, size, classes, sbs, c, ctypes.c_float(neg_slope), _stream())
-        return dx, dsb[0], dsb[1], None, None, None, None
+                  _ptr(None if dsb is None else dsb[0]), _ptr(None if dsb is None else dsb[1]), b, c, ndim, size, classes,
+                  sbs, c, ctypes.c_float(neg_slope), biased, _stream())
+        if dsb is None:
+            return dx, None, None, None, None, None, None, None
+        return dx, dsb[0], dsb[1], None, None, None, None, None
 
 
 def adain_act_channels_last(x: Tensor, scale: Tensor, bias: Tensor, ndim: int, classes: int, neg_slope: float = 0.0,
                             eps: float = 1e-8) -> Tensor:
-    return _AdaInChannelsLast.apply(x, scale, bias, ndim, classes, neg_slope, eps)
+    return _AdaInChannelsLast.apply(x, scale, bias, ndim, classes, neg_slope, eps, False)
+
+
+def instance_norm_act_channels_last(x_nhwc: Tensor, neg_slope: float = 0.2, eps: float = 1e-5) -> Tensor:
+    """InstanceNorm2d (no affine, biased variance) + LeakyReLU on a channels-last (B,H,W,C) bf16 tensor, H == W
+    -- the discriminator's norm + activation (reference core/models/hologan_discriminator.py:16-17,21-22)."""
+    return _AdaInChannelsLast.apply(x_nhwc, None, None, 2, 1, neg_slope, eps, True)
 
 
 # ------------------------------------------------------------------------------------------------

@@ -72,7 +72,12 @@ class _FlatGrads:
         self.flat = torch.zeros(n, device=dev, dtype=dt)
         o = 0
         for p in self.params:
-            p.grad = self.flat[o:o + p.numel()].view_as(p)
+            chunk = self.flat[o:o + p.numel()]
+            if p.dim() == 4 and not p.is_contiguous() and p.is_contiguous(memory_format=torch.channels_last):
+                n, c, h, w = p.shape                      # same strides as the parameter (fused Adam needs that)
+                p.grad = chunk.view(n, h, w, c).permute(0, 3, 1, 2)
+            else:
+                p.grad = chunk.view_as(p)
             o += p.numel()
 
     def zero(self):
@@ -99,8 +104,17 @@ class HologanTrainer:
         if self.world > 1:               # identical replicas even if a rank's RNG had diverged
             for t in list(self.generator.state_dict().values()) + list(self.discriminator.state_dict().values()):
                 dist.broadcast(t, src=0)
+        if self.device.type == "cuda" and compute_dtype == torch.bfloat16:
+            # bf16 pipeline: the discriminator's convolutions run NHWC (cuDNN's native tensor-core layout), so
+            # its weights live channels-last too -- no per-call layout conversions
+            self.discriminator.to(memory_format=torch.channels_last)
         self.d_grads = _FlatGrads(self.discriminator.parameters())
         self.g_grads = _FlatGrads(self.generator.parameters())
+        if self.device.type == "cuda":
+            # the .grad views above are permanent and zeroed before every step: let the wgrad kernels
+            # accumulate straight into them (ops._direct_grad_target)
+            for p in self.generator.parameters():
+                p._hg_direct_grad = True
         cuda = self.device.type == "cuda"
         # fused multi-tensor Adam; capturable (device-side step counter, tensor lr) so that a whole
         # optimizer step can live inside a CUDA graph

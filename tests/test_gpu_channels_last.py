@@ -109,3 +109,22 @@ def test_unsupported():
     with pytest.raises(HologanB200Error, match="bf16 only"):
         ops.rotate_fwd_raw(torch.zeros(1, 16, 16, 16, 8, device=DEV), torch.eye(4, device=DEV)[None], 0, ops.HG_NDHWC,
                            ops.HG_NDHWC)
+
+
+@pytest.mark.parametrize("b,c,s", [(4, 128, 16), (3, 256, 8), (2, 512, 4), (2, 16, 32)])
+def test_instance_norm_lrelu_channels_last(b, c, s):
+    """The discriminator's InstanceNorm2d (biased variance, eps 1e-5, no affine) + LeakyReLU(0.2)
+    (reference hologan_discriminator.py:16-17,21-22) on NHWC bf16 activations, forward and backward."""
+    import torch.nn.functional as F
+    gen = torch.Generator().manual_seed(c + s)
+    x = (torch.randn(b, c, s, s, generator=gen) * 1.5 + 0.3).to(BF)
+    dy = torch.randn(b, c, s, s, generator=gen).to(BF)
+    xr = x.float().clone().requires_grad_(True)
+    ref = F.leaky_relu(F.instance_norm(xr, eps=1e-5), 0.2)
+    (ref * dy.float()).sum().backward()
+    x_cl = x.permute(0, 2, 3, 1).contiguous().to(DEV).requires_grad_(True)
+    y = ops.instance_norm_act_channels_last(x_cl, 0.2, 1e-5)
+    assert y.dtype == BF and tuple(y.shape) == (b, s, s, c)
+    (y.float() * dy.permute(0, 2, 3, 1).to(DEV).float()).sum().backward()
+    assert rel_err(y.permute(0, 3, 1, 2).float(), ref) < 2 ** -7
+    assert rel_err(x_cl.grad.permute(0, 3, 1, 2).float(), xr.grad) < 2e-2

@@ -48,3 +48,18 @@ def test_final_conv_tanh(b, c, s, cout):
     assert rel_err(wg.grad, wr.grad) < 2e-5 and rel_err(bg.grad, br.grad) < 2e-5
     out2 = ops.final_conv_tanh(x_cl.detach(), wg, bg)
     assert torch.equal(out, out2)
+
+
+@pytest.mark.parametrize("rows,cols,slope", [(16384, 1024, 0.0), (300, 64, 0.2), (77, 24, 0.0), (5, 4096, 0.0)])
+def test_act_bwd_bias(rows, cols, slope):
+    g = torch.Generator().manual_seed(rows + cols)
+    y = torch.randn(rows, cols, generator=g).to(torch.bfloat16).to(DEV)
+    dy = torch.randn(rows, cols, generator=g).to(torch.bfloat16).to(DEV)
+    dpre, db = ops.act_bwd_bias(y, dy, slope, True)
+    ref = torch.where(y > 0, dy, (dy.float() * slope).to(torch.bfloat16))
+    assert torch.equal(dpre, ref)
+    assert rel_err(db, ref.float().sum(0)) < 1e-5
+    dpre2, db2 = ops.act_bwd_bias(y, dy, slope, True)
+    assert torch.equal(db, db2)                       # deterministic
+    dpre3, none = ops.act_bwd_bias(y, dy, slope, False)
+    assert none is None and torch.equal(dpre3, ref)

@@ -40,5 +40,6 @@ for e in kern:
     cats[cat(e.key)] = cats.get(cat(e.key), 0) + e.self_device_time_total
 for k, v in sorted(cats.items(), key=lambda kv: -kv[1]):
     print(f"  {v / steps / 1e3:7.3f} ms  {k}")
-for e in sorted(kern, key=lambda e: -e.self_device_time_total)[:40]:
+print(f"kernel launches per step: {sum(e.count for e in kern) / steps:.0f}")
+for e in sorted(kern, key=lambda e: -e.self_device_time_total)[:70]:
     print(f"{e.self_device_time_total / steps:9.1f} us/step  x{e.count / steps:6.1f}  {e.key[:120]}")
