@@ -116,16 +116,20 @@ int hg_adain_act_bwd(const void *x, const void *dy, const float *scale, const fl
  *   x  (B, S^ndim, classes, C) bf16: the space-to-depth output of hg_convt_fwd (classes = 2^ndim), or a
  *      plain channels-last tensor (classes = 1)
  *   y  (B, (2S)^ndim, C) bf16 plain channels-last (the depth-to-space shuffle happens in the store);
- *      dy has y's layout, dx has x's layout.  C % 16 == 0, S^ndim * classes <= 4096.
+ *      dy has y's layout, dx has x's layout.  C = 8 * 2^k <= 2048.
  *   scale / bias may both be NULL (= 1 / 0) and dscale / dbias may both be NULL (not computed); with
  *   biased_var = 1, eps = 1e-5, neg_slope = 0.2 that is the discriminator's InstanceNorm2d + LeakyReLU
- *   (core/models/hologan_discriminator.py:16-17,21-22) on channels-last activations. */
+ *   (core/models/hologan_discriminator.py:16-17,21-22) on channels-last activations.
+ *   workspace: hg_adain_cl_workspace_bytes() bytes of scratch for the per-chunk partial sums (0 for small
+ *   instances, then it may be NULL); deterministic (fixed summation order). */
+long long hg_adain_cl_workspace_bytes(int batch, int channels, int ndim, int size, int classes);
 int hg_adain_cl_fwd(const void *x, const float *scale, const float *bias, void *y, float *save_mean, float *save_rstd,
-                    int batch, int channels, int ndim, int size, int classes, int sb_stride, float eps, float neg_slope,
-                    int biased_var, void *stream);
+                    void *workspace, long long workspace_bytes, int batch, int channels, int ndim, int size, int classes,
+                    int sb_stride, float eps, float neg_slope, int biased_var, void *stream);
 int hg_adain_cl_bwd(const void *x, const void *dy, const float *scale, const float *bias, const float *save_mean,
-                    const float *save_rstd, void *dx, float *dscale, float *dbias, int batch, int channels, int ndim,
-                    int size, int classes, int sb_stride, int dsb_stride, float neg_slope, int biased_var, void *stream);
+                    const float *save_rstd, void *dx, float *dscale, float *dbias, void *workspace, long long workspace_bytes,
+                    int batch, int channels, int ndim, int size, int classes, int sb_stride, int dsb_stride, float neg_slope,
+                    int biased_var, void *stream);
 
 /* ---- a4 / a9 / a10: transposed convolutions and the 1x1 projection as tcgen05 implicit GEMMs -------
  * Replace nn.ConvTranspose3d(k3,s2,p1,op1) / nn.ConvTranspose2d(k4,s2,p1) / nn.ConvTranspose2d(k1)
@@ -141,7 +145,7 @@ int hg_adain_cl_bwd(const void *x, const void *dy, const float *scale, const flo
  */
 /* perm_c / perm_s: optional permutation of the input-channel (GEMM K) index for the projection operand
  * in HG_PROJ layout: packed channel y*perm_c + c <-> torch channel c*perm_s + (perm_s-1-y)
- * (reference :130-133); perm_s = 0 means identity. */
+ * (reference :130-133); perm_s = 0 means identity.  Cin even, Cout % 32 == 0, taps in {1, 16, 27}. */
 int hg_convt_pack_weight(const float *w, void *w_fwd, void *w_dgrad, int cin, int cout, int taps, int perm_c, int perm_s,
                          void *stream);
 /* y_s2d = act(convT(x) + bias); bias (Cout) fp32 or NULL; act: v > 0 ? v : neg_slope * v (1 = none) */

@@ -26,10 +26,11 @@ SIGNATURES = {
     "hg_rotate_bwd_workspace_bytes": [_c_int, _c_int, _c_int],
     "hg_rotate_bwd": [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_ll, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
                       _c_int, _c_void_p],
-    "hg_adain_cl_fwd": [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int,
-                        _c_int, _c_int, _c_float, _c_float, _c_int, _c_void_p],
+    "hg_adain_cl_workspace_bytes": [_c_int, _c_int, _c_int, _c_int, _c_int],
+    "hg_adain_cl_fwd": [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_ll, _c_int, _c_int,
+                        _c_int, _c_int, _c_int, _c_int, _c_float, _c_float, _c_int, _c_void_p],
     "hg_adain_cl_bwd": [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
-                        _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_float, _c_int, _c_void_p],
+                        _c_void_p, _c_ll, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_float, _c_int, _c_void_p],
     "hg_adain_act_fwd": [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int,
                          _c_ll, _c_int, _c_float, _c_float, _c_int, _c_int, _c_void_p],
     "hg_adain_act_bwd": [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
@@ -54,6 +55,7 @@ SIGNATURES = {
 }
 _RESTYPES = {"hg_last_error": ctypes.c_char_p, "hg_rotate_bwd_workspace_bytes": ctypes.c_longlong,
              "hg_convt_wgrad_workspace_bytes": ctypes.c_longlong, "hg_act_bwd_bias_workspace_bytes": ctypes.c_longlong,
+             "hg_adain_cl_workspace_bytes": ctypes.c_longlong,
              "hg_final_conv_tanh_bwd_workspace_bytes": ctypes.c_longlong}
 
 _lib = None

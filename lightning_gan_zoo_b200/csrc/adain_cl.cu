@@ -1,21 +1,33 @@
-// Channels-last AdaIN (+ activation) for the bf16 tensor-core pipeline.
+// Channels-last AdaIN / InstanceNorm (+ activation) for the bf16 pipeline.
 //
-// Same arithmetic as adain.cu (reference AdaIn, core/models/hologan_generator.py:333-345, fused with
-// the ReLU of :41) but on the layouts the implicit-GEMM kernels produce and consume:
-//   input  x : (B, Npos, P, C) bf16 -- the space-to-depth output of hg_convt_fwd (P parity classes,
-//              P = 1 for a plain channels-last tensor), rows r = pos * P + cls
-//   output y : (B, (2S)^d, C) bf16 plain channels-last: row (pos, cls) lands on its up-sampled pixel,
-//              i.e. the depth-to-space shuffle is folded into the store addressing (zero extra passes).
-// One CTA = (sample, 16 channels): every row contributes one 32-byte sector, the whole (N x 16) slab
-// (N <= 4096 rows) is held in registers, statistics are reduced with shuffles + one smem exchange, and
-// the tensor is read exactly once.  The backward makes two passes over its inputs (sums, then dx);
-// the second pass hits L2.
+// Same arithmetic as adain.cu (reference AdaIn, core/models/hologan_generator.py:333-345, fused with the ReLU
+// of :41; with biased_var also the discriminator's InstanceNorm2d + LeakyReLU,
+// core/models/hologan_discriminator.py:16-17,21-22) on the layouts the implicit-GEMM kernels produce / consume:
+//   input  x : (B, Npos, P, C) bf16 -- the space-to-depth output of hg_convt_fwd (P parity classes, P = 1 for
+//              a plain channels-last tensor), rows r = pos * P + cls
+//   output y : (B, (2S)^d, C) bf16 plain channels-last: row (pos, cls) lands on its up-sampled pixel, i.e. the
+//              depth-to-space shuffle is folded into the store addressing (zero extra passes).
+//
+// HBM-bound.  Every global access is a FULL ROW (C * 2 bytes contiguous, C/8 lanes x 16 bytes): a sample is
+// cut into row chunks, one CTA per (chunk, sample) streams its rows with four independent 16-byte loads in
+// flight per thread.
+//   forward : stats kernel  -- per-channel sum(x - K), sum((x - K)^2) per chunk (K = the sample's first row, a
+//                              pivot that removes the cancellation of E[x^2] - E[x]^2; partials ADD, so chunks
+//                              merge in a fixed order without Welford bookkeeping)
+//             apply kernel  -- merges the chunk partials, normalises / modulates / activates its rows (second
+//                              read of x comes from L2) and stores to the up-sampled row
+//   backward: sums kernel   -- sum(g), sum(g * xhat) per chunk, g = dy through the activation
+//             apply kernel  -- dx = rstd * (g * s - s * sum(g) / N - xhat * s * sum(g * xhat) / Nvar)
+// Small instances (a sample <= 64 KB: the discriminator's maps) run both phases in ONE kernel, one CTA per
+// sample, the second pass served by L1.  Algorithmic HBM bytes: fwd 2 * B*N*C*2, bwd 3 * B*N*C*2.
 #include "hg_common.cuh"
 
 namespace hg {
 
-constexpr int kClThreads = 512;
-constexpr int kClGroup = 16;        // channels per CTA
+constexpr int kClThreads = 256;
+constexpr int kClUnroll = 8;          // forward: independent 16-byte loads in flight per thread
+constexpr int kClUnrollBwd = 4;       // backward streams two tensors: 2 x 4 loads in flight
+constexpr int kClMaxChunks = 32;
 
 __device__ __forceinline__ void unpack8(const uint4 &u, float *f)
 {
@@ -50,229 +62,381 @@ __device__ __forceinline__ int upsampled_row(int r, int ndim, int logS, int logP
     return ((2 * iz + pz) * S2 + 2 * iy + py) * S2 + 2 * ix + px;
 }
 
-// Sum 8 per-thread partials over all threads of the CTA that own the same channel half (t & 1).
-// red: [kWarps][16 channels] floats; result is valid in every thread.
-template <int kWarps>
-__device__ __forceinline__ void cta_sum8(float (&a)[8], float (*red)[kClGroup], int warp, int lane)
-{
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-#pragma unroll
-        for (int o = 16; o >= 2; o >>= 1) a[j] += __shfl_xor_sync(0xffffffffu, a[j], o);
-    }
-    if (lane < 2) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) red[warp][lane * 8 + j] = a[j];
-    }
-    __syncthreads();
-    const int half = lane & 1;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) a[j] = 0.f;
-#pragma unroll
-    for (int w = 0; w < kWarps; ++w) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) a[j] += red[w][half * 8 + j];
-    }
-}
-
 __device__ __forceinline__ float modulate_cl(float x, float mean, float rstd, float s, float b)
 {
     return __fadd_rn(__fmul_rn(s, __fmul_rn(__fsub_rn(x, mean), rstd)), b);
 }
 
-template <int VPT, int kThreadsT>
-__global__ void __launch_bounds__(kThreadsT) adain_cl_fwd_kernel(const __nv_bfloat16 *__restrict__ x,
-                                                                  const float *__restrict__ scale,
-                                                                  const float *__restrict__ bias,
-                                                                  __nv_bfloat16 *__restrict__ y,
-                                                                  float *__restrict__ save_mean,
-                                                                  float *__restrict__ save_rstd, int C, int N, int Nvar,
-                                                                  int ndim, int logS, int logP, int sbs, float eps,
-                                                                  float slope)
-{
-    __shared__ float red[2][kThreadsT / 32][kClGroup];
-    const int b = blockIdx.y, c0 = blockIdx.x * kClGroup;
-    const int t = threadIdx.x, lane = t & 31, warp = t >> 5, half = t & 1;
-    const int nvec = N * 2;
-    const size_t base = (size_t)b * N * C + c0 + half * 8;
-    const __nv_bfloat16 *xb = x + base;
+struct ClGeom {
+    int C, N, Nvar, ndim, logS, logP;
+    int lanes;          // C / 8 threads per row
+    int rows_per_pass;  // kClThreads / lanes
+    int chunk_rows;     // rows per CTA (multiple of rows_per_pass)
+    int chunks;
+};
 
-    uint4 raw[VPT];
-    float acc[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-#pragma unroll
-    for (int k = 0; k < VPT; ++k) {
-        const int v = t + k * kThreadsT;
-        if (v < nvec) {
-            raw[k] = ld_stream_16(xb + (size_t)(v >> 1) * C);
-            float f[8];
-            unpack8(raw[k], f);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) acc[j] += f[j];
-        }
-    }
-    cta_sum8<kThreadsT / 32>(acc, red[0], warp, lane);
-    float mean[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        mean[j] = acc[j] / (float)N;
-        acc[j] = 0.f;
-    }
-#pragma unroll
-    for (int k = 0; k < VPT; ++k) {
-        if (t + k * kThreadsT < nvec) {
-            float f[8];
-            unpack8(raw[k], f);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float d = f[j] - mean[j];
-                acc[j] += d * d;
-            }
-        }
-    }
-    cta_sum8<kThreadsT / 32>(acc, red[1], warp, lane);
-    float rstd[8], s[8], bb[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        // Nvar = N - 1: unbiased variance (:338), eps inside the rsqrt (:339); Nvar = N: InstanceNorm2d
-        rstd[j] = __frsqrt_rn(acc[j] / (float)Nvar + eps);
-        s[j] = scale ? scale[(size_t)b * sbs + c0 + half * 8 + j] : 1.f;
-        bb[j] = bias ? bias[(size_t)b * sbs + c0 + half * 8 + j] : 0.f;
-    }
-    if (t < 2) {
+// Sum the two 8-float partials of all row slots of the CTA in a fixed order; result valid for every thread.
+// Row slots that share a warp (lanes < 32) are folded with xor-shuffles first, the remaining <= 8 groups go
+// through shared memory laid out [group][value][channel octet] (conflict-free).
+__device__ __forceinline__ void cta_rowslot_sum(float (&a)[8], float (&b)[8], float *red, int lanes, int rows_per_pass,
+                                                int cs, int rs)
+{
+    for (int o = lanes; o < 32; o <<= 1) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            save_mean[(size_t)b * C + c0 + half * 8 + j] = mean[j];
-            save_rstd[(size_t)b * C + c0 + half * 8 + j] = rstd[j];
+            a[j] += __shfl_xor_sync(0xffffffffu, a[j], o);
+            b[j] += __shfl_xor_sync(0xffffffffu, b[j], o);
         }
     }
-    __nv_bfloat16 *yb = y + base;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int groups = lanes < 32 ? kClThreads / 32 : rows_per_pass;
+    const int grp = lanes < 32 ? warp : rs;
+    __syncthreads();
+    if (lanes >= 32 || lane < lanes) {
 #pragma unroll
-    for (int k = 0; k < VPT; ++k) {
-        const int v = t + k * kThreadsT;
-        if (v < nvec) {
-            float f[8];
-            unpack8(raw[k], f);
+        for (int j = 0; j < 8; ++j) {
+            red[(grp * 16 + j) * lanes + cs] = a[j];
+            red[(grp * 16 + 8 + j) * lanes + cs] = b[j];
+        }
+    }
+    __syncthreads();
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float p = modulate_cl(f[j], mean[j], rstd[j], s[j], bb[j]);
-                f[j] = p > 0.f ? p : p * slope;
-            }
-            const int orow = upsampled_row(v >> 1, ndim, logS, logP);
-            st_stream_16(yb + (size_t)orow * C, pack8(f));
+    for (int j = 0; j < 8; ++j) a[j] = b[j] = 0.f;
+    for (int k = 0; k < groups; ++k) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            a[j] += red[(k * 16 + j) * lanes + cs];
+            b[j] += red[(k * 16 + 8 + j) * lanes + cs];
         }
     }
 }
 
-// Backward.  256 threads per (sample, 16 channels); two passes over x / dy (the second one hits L2), each
-// pass issues kBwdUnroll independent 16-byte loads of x and of dy per thread before consuming them, so a
-// CTA keeps ~64 KB in flight.  Nvar as in the forward.  scale / bias may be null (1 / 0), dscale / dbias may
-// be null (not needed: the discriminator's InstanceNorm has no affine parameters).
-constexpr int kBwdThreads = 256;
-constexpr int kBwdUnroll = 4;
-
-__global__ void __launch_bounds__(kBwdThreads) adain_cl_bwd_kernel(const __nv_bfloat16 *__restrict__ x,
-                                                                   const __nv_bfloat16 *__restrict__ dy,
-                                                                   const float *__restrict__ scale,
-                                                                   const float *__restrict__ bias,
-                                                                   const float *__restrict__ save_mean,
-                                                                   const float *__restrict__ save_rstd,
-                                                                   __nv_bfloat16 *__restrict__ dx, float *__restrict__ dscale,
-                                                                   float *__restrict__ dbias, int C, int N, int Nvar, int ndim,
-                                                                   int logS, int logP, int sbs, int dsbs, float slope)
+// ---- forward pieces -----------------------------------------------------------------------------------
+// s1 += sum(x - K), s2 += sum((x - K)^2) over rows [r0, r1) of this thread's row slot
+__device__ __forceinline__ void fwd_accumulate(const __nv_bfloat16 *__restrict__ xb, const ClGeom &g, int r0, int r1, int rs,
+                                               const float (&piv)[8], float (&s1)[8], float (&s2)[8])
 {
-    __shared__ float red[2][kBwdThreads / 32][kClGroup];
-    const int b = blockIdx.y, c0 = blockIdx.x * kClGroup;
-    const int t = threadIdx.x, lane = t & 31, warp = t >> 5, half = t & 1;
-    const int nvec = N * 2;
-    const size_t base = (size_t)b * N * C + c0 + half * 8;
-    const __nv_bfloat16 *xb = x + base, *gb = dy + base;
+    for (int r = r0 + rs; r < r1; r += kClUnroll * g.rows_per_pass) {
+        uint4 raw[kClUnroll];
+#pragma unroll
+        for (int u = 0; u < kClUnroll; ++u) {
+            const int rr = r + u * g.rows_per_pass;
+            if (rr < r1) raw[u] = __ldg(reinterpret_cast<const uint4 *>(xb + (size_t)rr * g.C));
+        }
+#pragma unroll
+        for (int u = 0; u < kClUnroll; ++u) {
+            if (r + u * g.rows_per_pass < r1) {
+                float f[8];
+                unpack8(raw[u], f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float d = f[j] - piv[j];
+                    s1[j] += d;
+                    s2[j] = fmaf(d, d, s2[j]);
+                }
+            }
+        }
+    }
+}
 
+__device__ __forceinline__ void fwd_apply(const __nv_bfloat16 *__restrict__ xb, __nv_bfloat16 *__restrict__ yb, const ClGeom &g,
+                                          int r0, int r1, int rs, const float (&mean)[8], const float (&rstd)[8],
+                                          const float (&s)[8], const float (&bb)[8], float slope)
+{
+    for (int r = r0 + rs; r < r1; r += kClUnroll * g.rows_per_pass) {
+        uint4 raw[kClUnroll];
+#pragma unroll
+        for (int u = 0; u < kClUnroll; ++u) {
+            const int rr = r + u * g.rows_per_pass;
+            if (rr < r1) raw[u] = __ldg(reinterpret_cast<const uint4 *>(xb + (size_t)rr * g.C));
+        }
+#pragma unroll
+        for (int u = 0; u < kClUnroll; ++u) {
+            const int rr = r + u * g.rows_per_pass;
+            if (rr < r1) {
+                float f[8];
+                unpack8(raw[u], f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float p = modulate_cl(f[j], mean[j], rstd[j], s[j], bb[j]);
+                    f[j] = p > 0.f ? p : p * slope;
+                }
+                st_stream_16(yb + (size_t)upsampled_row(rr, g.ndim, g.logS, g.logP) * g.C, pack8(f));
+            }
+        }
+    }
+}
+
+// grid (chunks, B).  part[(b * chunks + chunk) * 2C + {0, C} + c]
+__global__ void __launch_bounds__(kClThreads) adain_cl_stats_kernel(const __nv_bfloat16 *__restrict__ x, float *__restrict__ part,
+                                                                    ClGeom g)
+{
+    __shared__ float red[kClThreads * 16];
+    const int cs = threadIdx.x % g.lanes, rs = threadIdx.x / g.lanes;
+    const int b = blockIdx.y, chunk = blockIdx.x;
+    const __nv_bfloat16 *xb = x + (size_t)b * g.N * g.C + cs * 8;
+    float piv[8], s1[8], s2[8];
+    unpack8(__ldg(reinterpret_cast<const uint4 *>(xb)), piv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
+    const int r0 = chunk * g.chunk_rows, r1 = min(g.N, r0 + g.chunk_rows);
+    fwd_accumulate(xb, g, r0, r1, rs, piv, s1, s2);
+    cta_rowslot_sum(s1, s2, red, g.lanes, g.rows_per_pass, cs, rs);
+    if (rs == 0) {
+        float *dst = part + ((size_t)b * g.chunks + chunk) * 2 * g.C + cs * 8;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            dst[j] = s1[j];
+            dst[g.C + j] = s2[j];
+        }
+    }
+}
+
+// kFused: one CTA per sample computes the statistics itself (chunks == 1); else they come from `part`.
+// Merge the chunk partials of one sample (fixed chunk order), one thread per channel.
+//   forward : part = {sum(x-K), sum((x-K)^2)}  ->  save_mean, save_rstd
+//   backward: part = {sum(g), sum(g*xhat)}     ->  sums[b][2C] (and dbias / dscale when requested)
+__global__ void __launch_bounds__(256) adain_cl_finalize_kernel(const __nv_bfloat16 *__restrict__ x, const float *__restrict__ part,
+                                                                float *__restrict__ out_a, float *__restrict__ out_b,
+                                                                float *__restrict__ out_a2, float *__restrict__ out_b2, ClGeom g,
+                                                                int out_stride, int out2_stride, float eps, int forward)
+{
+    const int b = blockIdx.y, c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= g.C) return;
+    const float *src = part + (size_t)b * g.chunks * 2 * g.C + c;
+    float a = 0.f, q = 0.f;
+    for (int k = 0; k < g.chunks; ++k) {
+        a += src[(size_t)k * 2 * g.C];
+        q += src[(size_t)k * 2 * g.C + g.C];
+    }
+    if (forward) {
+        const float piv = __bfloat162float(x[(size_t)b * g.N * g.C + c]);
+        const float d = a / (float)g.N;
+        const float var = fmaxf(q - a * d, 0.f) / (float)g.Nvar;
+        out_a[(size_t)b * out_stride + c] = piv + d;
+        out_b[(size_t)b * out_stride + c] = __frsqrt_rn(var + eps);
+    } else {
+        out_a[(size_t)b * out_stride + c] = a;
+        out_b[(size_t)b * out_stride + c] = q;
+        if (out_a2) {
+            out_a2[(size_t)b * out2_stride + c] = a;
+            out_b2[(size_t)b * out2_stride + c] = q;
+        }
+    }
+}
+
+template <bool kFused>
+__global__ void __launch_bounds__(kClThreads) adain_cl_apply_kernel(const __nv_bfloat16 *__restrict__ x,
+                                                                    const float *__restrict__ part,
+                                                                    const float *__restrict__ scale,
+                                                                    const float *__restrict__ bias,
+                                                                    __nv_bfloat16 *__restrict__ y, float *__restrict__ save_mean,
+                                                                    float *__restrict__ save_rstd, ClGeom g, int sbs, float eps,
+                                                                    float slope)
+{
+    __shared__ float red[kFused ? kClThreads * 16 : 1];
+    const int cs = threadIdx.x % g.lanes, rs = threadIdx.x / g.lanes;
+    const int b = blockIdx.y, chunk = blockIdx.x;
+    const __nv_bfloat16 *xb = x + (size_t)b * g.N * g.C + cs * 8;
     float mean[8], rstd[8], s[8], bb[8];
+    if (kFused) {
+        float piv[8], s1[8], s2[8];
+        unpack8(__ldg(reinterpret_cast<const uint4 *>(xb)), piv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
+        fwd_accumulate(xb, g, 0, g.N, rs, piv, s1, s2);
+        cta_rowslot_sum(s1, s2, red, g.lanes, g.rows_per_pass, cs, rs);
+        const float inv_n = 1.f / (float)g.N;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float d = s1[j] * inv_n;                      // mean - K
+            mean[j] = piv[j] + d;
+            // Nvar = N - 1: unbiased variance (:338), eps inside the rsqrt (:339); Nvar = N: InstanceNorm2d
+            const float var = fmaxf(s2[j] - s1[j] * d, 0.f) / (float)g.Nvar;
+            rstd[j] = __frsqrt_rn(var + eps);
+        }
+        if (rs == 0) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                save_mean[(size_t)b * g.C + cs * 8 + j] = mean[j];
+                save_rstd[(size_t)b * g.C + cs * 8 + j] = rstd[j];
+            }
+        }
+    } else {                                                    // merged by adain_cl_finalize_kernel
+        const float4 *m4 = reinterpret_cast<const float4 *>(save_mean + (size_t)b * g.C + cs * 8);
+        const float4 *r4 = reinterpret_cast<const float4 *>(save_rstd + (size_t)b * g.C + cs * 8);
+        const float4 m0 = m4[0], m1 = m4[1], q0 = r4[0], q1 = r4[1];
+        mean[0] = m0.x; mean[1] = m0.y; mean[2] = m0.z; mean[3] = m0.w; mean[4] = m1.x; mean[5] = m1.y; mean[6] = m1.z; mean[7] = m1.w;
+        rstd[0] = q0.x; rstd[1] = q0.y; rstd[2] = q0.z; rstd[3] = q0.w; rstd[4] = q1.x; rstd[5] = q1.y; rstd[6] = q1.z; rstd[7] = q1.w;
+    }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        const int c = c0 + half * 8 + j;
-        mean[j] = save_mean[(size_t)b * C + c];
-        rstd[j] = save_rstd[(size_t)b * C + c];
-        s[j] = scale ? scale[(size_t)b * sbs + c] : 1.f;
-        bb[j] = bias ? bias[(size_t)b * sbs + c] : 0.f;
+        s[j] = scale ? scale[(size_t)b * sbs + cs * 8 + j] : 1.f;
+        bb[j] = bias ? bias[(size_t)b * sbs + cs * 8 + j] : 0.f;
     }
-    float sg[8], sgx[8];
+    const int r0 = kFused ? 0 : chunk * g.chunk_rows, r1 = kFused ? g.N : min(g.N, r0 + g.chunk_rows);
+    fwd_apply(xb, y + (size_t)b * g.N * g.C + cs * 8, g, r0, r1, rs, mean, rstd, s, bb, slope);
+}
+
+// ---- backward pieces ----------------------------------------------------------------------------------
+struct ClStyle {
+    float mean[8], rstd[8], s[8], bb[8];
+};
+
+__device__ __forceinline__ void load_style(ClStyle &st, const float *scale, const float *bias, const float *save_mean,
+                                           const float *save_rstd, int b, int C, int sbs, int c0)
+{
 #pragma unroll
-    for (int j = 0; j < 8; ++j) sg[j] = sgx[j] = 0.f;
-    for (int v0 = t; v0 < nvec; v0 += kBwdThreads * kBwdUnroll) {
-        uint4 xr[kBwdUnroll], gr[kBwdUnroll];
+    for (int j = 0; j < 8; ++j) {
+        st.mean[j] = save_mean[(size_t)b * C + c0 + j];
+        st.rstd[j] = save_rstd[(size_t)b * C + c0 + j];
+        st.s[j] = scale ? scale[(size_t)b * sbs + c0 + j] : 1.f;
+        st.bb[j] = bias ? bias[(size_t)b * sbs + c0 + j] : 0.f;
+    }
+}
+
+__device__ __forceinline__ void bwd_accumulate(const __nv_bfloat16 *__restrict__ xb, const __nv_bfloat16 *__restrict__ gb,
+                                               const ClGeom &g, int r0, int r1, int rs, const ClStyle &st, float slope,
+                                               float (&sg)[8], float (&sgx)[8])
+{
+    for (int r = r0 + rs; r < r1; r += kClUnrollBwd * g.rows_per_pass) {
+        uint4 xr[kClUnrollBwd], gr[kClUnrollBwd];
 #pragma unroll
-        for (int u = 0; u < kBwdUnroll; ++u) {
-            const int v = v0 + u * kBwdThreads;
-            if (v < nvec) {
-                const int row = v >> 1;
-                xr[u] = __ldg(reinterpret_cast<const uint4 *>(xb + (size_t)row * C));
-                gr[u] = __ldg(reinterpret_cast<const uint4 *>(gb + (size_t)upsampled_row(row, ndim, logS, logP) * C));
+        for (int u = 0; u < kClUnrollBwd; ++u) {
+            const int rr = r + u * g.rows_per_pass;
+            if (rr < r1) {
+                xr[u] = __ldg(reinterpret_cast<const uint4 *>(xb + (size_t)rr * g.C));
+                gr[u] = __ldg(reinterpret_cast<const uint4 *>(gb + (size_t)upsampled_row(rr, g.ndim, g.logS, g.logP) * g.C));
             }
         }
 #pragma unroll
-        for (int u = 0; u < kBwdUnroll; ++u) {
-            if (v0 + u * kBwdThreads < nvec) {
+        for (int u = 0; u < kClUnrollBwd; ++u) {
+            if (r + u * g.rows_per_pass < r1) {
                 float xf[8], gf[8];
                 unpack8(xr[u], xf);
                 unpack8(gr[u], gf);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    const float pre = modulate_cl(xf[j], mean[j], rstd[j], s[j], bb[j]);     // the forward's bits
-                    const float g = pre > 0.f ? gf[j] : gf[j] * slope;
-                    sg[j] += g;
-                    sgx[j] += g * ((xf[j] - mean[j]) * rstd[j]);
+                    const float pre = modulate_cl(xf[j], st.mean[j], st.rstd[j], st.s[j], st.bb[j]);   // the forward's bits
+                    const float gg = pre > 0.f ? gf[j] : gf[j] * slope;
+                    sg[j] += gg;
+                    sgx[j] = fmaf(gg, (xf[j] - st.mean[j]) * st.rstd[j], sgx[j]);
                 }
             }
         }
     }
-    cta_sum8<kBwdThreads / 32>(sg, red[0], warp, lane);
-    cta_sum8<kBwdThreads / 32>(sgx, red[1], warp, lane);
-    if (t < 2 && dscale && dbias) {
+}
+
+__device__ __forceinline__ void bwd_apply(const __nv_bfloat16 *__restrict__ xb, const __nv_bfloat16 *__restrict__ gb,
+                                          __nv_bfloat16 *__restrict__ db, const ClGeom &g, int r0, int r1, int rs,
+                                          const ClStyle &st, float slope, const float (&k1)[8], const float (&k2)[8])
+{
+    for (int r = r0 + rs; r < r1; r += kClUnrollBwd * g.rows_per_pass) {
+        uint4 xr[kClUnrollBwd], gr[kClUnrollBwd];
+#pragma unroll
+        for (int u = 0; u < kClUnrollBwd; ++u) {
+            const int rr = r + u * g.rows_per_pass;
+            if (rr < r1) {
+                xr[u] = __ldg(reinterpret_cast<const uint4 *>(xb + (size_t)rr * g.C));
+                gr[u] = __ldg(reinterpret_cast<const uint4 *>(gb + (size_t)upsampled_row(rr, g.ndim, g.logS, g.logP) * g.C));
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kClUnrollBwd; ++u) {
+            const int rr = r + u * g.rows_per_pass;
+            if (rr < r1) {
+                float xf[8], gf[8];
+                unpack8(xr[u], xf);
+                unpack8(gr[u], gf);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float xh = (xf[j] - st.mean[j]) * st.rstd[j];
+                    const float pre = modulate_cl(xf[j], st.mean[j], st.rstd[j], st.s[j], st.bb[j]);
+                    const float gg = pre > 0.f ? gf[j] : gf[j] * slope;
+                    xf[j] = st.rstd[j] * (gg * st.s[j] - k1[j] - xh * k2[j]);
+                }
+                st_stream_16(db + (size_t)rr * g.C, pack8(xf));
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kClThreads) adain_cl_bwd_sums_kernel(const __nv_bfloat16 *__restrict__ x,
+                                                                       const __nv_bfloat16 *__restrict__ dy,
+                                                                       const float *__restrict__ scale,
+                                                                       const float *__restrict__ bias,
+                                                                       const float *__restrict__ save_mean,
+                                                                       const float *__restrict__ save_rstd,
+                                                                       float *__restrict__ part, ClGeom g, int sbs, float slope)
+{
+    __shared__ float red[kClThreads * 16];
+    const int cs = threadIdx.x % g.lanes, rs = threadIdx.x / g.lanes;
+    const int b = blockIdx.y, chunk = blockIdx.x;
+    const size_t base = (size_t)b * g.N * g.C + cs * 8;
+    ClStyle st;
+    load_style(st, scale, bias, save_mean, save_rstd, b, g.C, sbs, cs * 8);
+    float sg[8], sgx[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sg[j] = sgx[j] = 0.f;
+    const int r0 = chunk * g.chunk_rows, r1 = min(g.N, r0 + g.chunk_rows);
+    bwd_accumulate(x + base, dy + base, g, r0, r1, rs, st, slope, sg, sgx);
+    cta_rowslot_sum(sg, sgx, red, g.lanes, g.rows_per_pass, cs, rs);
+    if (rs == 0) {
+        float *dst = part + ((size_t)b * g.chunks + chunk) * 2 * g.C + cs * 8;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            dbias[(size_t)b * dsbs + c0 + half * 8 + j] = sg[j];
-            dscale[(size_t)b * dsbs + c0 + half * 8 + j] = sgx[j];
+            dst[j] = sg[j];
+            dst[g.C + j] = sgx[j];
+        }
+    }
+}
+
+template <bool kFused>
+__global__ void __launch_bounds__(kClThreads) adain_cl_bwd_apply_kernel(const __nv_bfloat16 *__restrict__ x,
+                                                                        const __nv_bfloat16 *__restrict__ dy,
+                                                                        const float *__restrict__ part,
+                                                                        const float *__restrict__ scale,
+                                                                        const float *__restrict__ bias,
+                                                                        const float *__restrict__ save_mean,
+                                                                        const float *__restrict__ save_rstd,
+                                                                        __nv_bfloat16 *__restrict__ dx, float *__restrict__ dscale,
+                                                                        float *__restrict__ dbias, ClGeom g, int sbs, int dsbs,
+                                                                        float slope)
+{
+    __shared__ float red[kFused ? kClThreads * 16 : 1];
+    const int cs = threadIdx.x % g.lanes, rs = threadIdx.x / g.lanes;
+    const int b = blockIdx.y, chunk = blockIdx.x;
+    const size_t base = (size_t)b * g.N * g.C + cs * 8;
+    ClStyle st;
+    load_style(st, scale, bias, save_mean, save_rstd, b, g.C, sbs, cs * 8);
+    float sg[8], sgx[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sg[j] = sgx[j] = 0.f;
+    if (kFused) {
+        bwd_accumulate(x + base, dy + base, g, 0, g.N, rs, st, slope, sg, sgx);
+        cta_rowslot_sum(sg, sgx, red, g.lanes, g.rows_per_pass, cs, rs);
+    } else {                                                    // merged by adain_cl_finalize_kernel: part = sums[b][2C]
+        const float4 *a4 = reinterpret_cast<const float4 *>(part + (size_t)b * 2 * g.C + cs * 8);
+        const float4 *q4 = reinterpret_cast<const float4 *>(part + (size_t)b * 2 * g.C + g.C + cs * 8);
+        const float4 a0 = a4[0], a1 = a4[1], q0 = q4[0], q1 = q4[1];
+        sg[0] = a0.x; sg[1] = a0.y; sg[2] = a0.z; sg[3] = a0.w; sg[4] = a1.x; sg[5] = a1.y; sg[6] = a1.z; sg[7] = a1.w;
+        sgx[0] = q0.x; sgx[1] = q0.y; sgx[2] = q0.z; sgx[3] = q0.w; sgx[4] = q1.x; sgx[5] = q1.y; sgx[6] = q1.z; sgx[7] = q1.w;
+    }
+    if (kFused && rs == 0 && dscale && dbias) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            dbias[(size_t)b * dsbs + cs * 8 + j] = sg[j];
+            dscale[(size_t)b * dsbs + cs * 8 + j] = sgx[j];
         }
     }
     float k1[8], k2[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        k1[j] = s[j] * sg[j] / (float)N;
-        k2[j] = s[j] * sgx[j] / (float)Nvar;
+        k1[j] = st.s[j] * sg[j] / (float)g.N;
+        k2[j] = st.s[j] * sgx[j] / (float)g.Nvar;
     }
-    __nv_bfloat16 *db = dx + base;
-    for (int v0 = t; v0 < nvec; v0 += kBwdThreads * kBwdUnroll) {
-        uint4 xr[kBwdUnroll], gr[kBwdUnroll];
-#pragma unroll
-        for (int u = 0; u < kBwdUnroll; ++u) {
-            const int v = v0 + u * kBwdThreads;
-            if (v < nvec) {
-                const int row = v >> 1;
-                xr[u] = __ldg(reinterpret_cast<const uint4 *>(xb + (size_t)row * C));
-                gr[u] = __ldg(reinterpret_cast<const uint4 *>(gb + (size_t)upsampled_row(row, ndim, logS, logP) * C));
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < kBwdUnroll; ++u) {
-            const int v = v0 + u * kBwdThreads;
-            if (v < nvec) {
-                float xf[8], gf[8];
-                unpack8(xr[u], xf);
-                unpack8(gr[u], gf);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float xh = (xf[j] - mean[j]) * rstd[j];
-                    const float pre = modulate_cl(xf[j], mean[j], rstd[j], s[j], bb[j]);
-                    const float g = pre > 0.f ? gf[j] : gf[j] * slope;
-                    xf[j] = rstd[j] * (g * s[j] - k1[j] - xh * k2[j]);
-                }
-                st_stream_16(db + (size_t)(v >> 1) * C, pack8(xf));
-            }
-        }
-    }
+    const int r0 = kFused ? 0 : chunk * g.chunk_rows, r1 = kFused ? g.N : min(g.N, r0 + g.chunk_rows);
+    bwd_apply(x + base, dy + base, dx + base, g, r0, r1, rs, st, slope, k1, k2);
 }
 
 static int ilog2(int v)
@@ -286,72 +450,117 @@ static int ilog2(int v)
 
 using namespace hg;
 
-static int cl_check(const char *who, int batch, int channels, int ndim, int size, int classes, int &n, int &logS, int &logP)
+static int cl_geom(const char *who, int batch, int channels, int ndim, int size, int classes, int biased_var, ClGeom &g)
 {
     HG_REQUIRE(batch > 0 && channels > 0 && size > 0 && classes > 0, HG_ERR_INVALID_ARG, "%s: dims must be positive", who);
     HG_REQUIRE(batch <= 65535, HG_ERR_UNSUPPORTED, "%s: batch > 65535", who);
     HG_REQUIRE(ndim == 2 || ndim == 3, HG_ERR_INVALID_ARG, "%s: ndim must be 2 or 3", who);
-    logS = ilog2(size);
-    logP = ilog2(classes);
-    HG_REQUIRE(logS >= 0 && (classes == 1 || classes == (1 << ndim)), HG_ERR_UNSUPPORTED,
+    g.logS = ilog2(size);
+    g.logP = ilog2(classes);
+    HG_REQUIRE(g.logS >= 0 && (classes == 1 || classes == (1 << ndim)), HG_ERR_UNSUPPORTED,
                "%s: size must be a power of two and classes 1 or 2^ndim", who);
-    HG_REQUIRE(channels % kClGroup == 0, HG_ERR_UNSUPPORTED, "%s: channels must be a multiple of %d", who, kClGroup);
+    const int lanes = channels / 8;
+    HG_REQUIRE(channels % 8 == 0 && lanes <= kClThreads && ilog2(lanes) >= 0, HG_ERR_UNSUPPORTED,
+               "%s: channels must be 8 * 2^k <= %d (got %d)", who, 8 * kClThreads, channels);
     long long rows = classes;
     for (int i = 0; i < ndim; ++i) rows *= size;
-    HG_REQUIRE(rows >= 2 && rows <= 4096, HG_ERR_UNSUPPORTED, "%s: %lld rows per instance exceed the single-pass limit 4096", who, rows);
-    n = (int)rows;
+    HG_REQUIRE(rows >= 2 && rows <= (1 << 24), HG_ERR_UNSUPPORTED, "%s: %lld rows per instance not supported", who, rows);
+    g.C = channels; g.N = (int)rows; g.Nvar = biased_var ? g.N : g.N - 1; g.ndim = ndim;
+    g.lanes = lanes; g.rows_per_pass = kClThreads / lanes;
+    // small instance (<= 64 KB): one CTA per sample does both phases; else ~16 chunks per sample
+    const long long bytes = rows * channels * 2;
+    // else cut every sample into chunks so that ~2 fat CTAs per SM stream >= kClUnroll rows per thread each
+    int chunks = 1;
+    if (bytes > 64 * 1024) {
+        chunks = (2 * sm_count() + batch - 1) / batch;
+        if (chunks < 2) chunks = 2;
+        if (chunks > kClMaxChunks) chunks = kClMaxChunks;
+        while (chunks > 1 && rows / chunks < (long long)g.rows_per_pass * kClUnroll) --chunks;
+    }
+    int cr = (int)((rows + chunks - 1) / chunks);
+    cr = (cr + g.rows_per_pass - 1) / g.rows_per_pass * g.rows_per_pass;
+    g.chunk_rows = cr;
+    g.chunks = (int)((rows + cr - 1) / cr);
     return HG_OK;
 }
 
+extern "C" long long hg_adain_cl_workspace_bytes(int batch, int channels, int ndim, int size, int classes)
+{
+    ClGeom g;
+    if (cl_geom("hg_adain_cl_workspace_bytes", batch, channels, ndim, size, classes, 0, g)) return -1;
+    // per-chunk partials + the merged sums of the backward
+    return g.chunks > 1 ? (long long)batch * (g.chunks + 1) * 2 * channels * (long long)sizeof(float) : 0;
+}
+
 extern "C" int hg_adain_cl_fwd(const void *x, const float *scale, const float *bias, void *y, float *save_mean,
-                               float *save_rstd, int batch, int channels, int ndim, int size, int classes, int sb_stride,
-                               float eps, float neg_slope, int biased_var, void *stream)
+                               float *save_rstd, void *workspace, long long workspace_bytes, int batch, int channels, int ndim,
+                               int size, int classes, int sb_stride, float eps, float neg_slope, int biased_var, void *stream)
 {
     HG_REQUIRE(x && y && save_mean && save_rstd, HG_ERR_INVALID_ARG, "hg_adain_cl_fwd: null pointer");
     HG_REQUIRE((scale == nullptr) == (bias == nullptr), HG_ERR_INVALID_ARG, "hg_adain_cl_fwd: scale and bias must both be given or both be null");
-    int n, logS, logP;
-    int rc = cl_check("hg_adain_cl_fwd", batch, channels, ndim, size, classes, n, logS, logP);
+    ClGeom g;
+    int rc = cl_geom("hg_adain_cl_fwd", batch, channels, ndim, size, classes, biased_var, g);
     if (rc) return rc;
     HG_REQUIRE(!scale || sb_stride >= channels, HG_ERR_INVALID_ARG, "hg_adain_cl_fwd: sb_stride < channels");
-    const int nvar = biased_var ? n : n - 1;
     const __nv_bfloat16 *xp = static_cast<const __nv_bfloat16 *>(x);
     __nv_bfloat16 *yp = static_cast<__nv_bfloat16 *>(y);
-    dim3 grid(channels / kClGroup, batch);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const int vpt = (n * 2 + kClThreads - 1) / kClThreads;
-#define HG_LAUNCH_CL_T(V, T) adain_cl_fwd_kernel<V, T><<<grid, T, 0, st>>>(xp, scale, bias, yp, save_mean, save_rstd, channels, n, nvar, ndim, logS, logP, sb_stride, eps, neg_slope)
-#define HG_LAUNCH_CL(V) HG_LAUNCH_CL_T(V, kClThreads)
-    // small instances (the discriminator's 16x16 ... 4x4 maps): right-size the CTA, one vector per thread
-    if (n * 2 <= 64) HG_LAUNCH_CL_T(1, 64);
-    else if (n * 2 <= 128) HG_LAUNCH_CL_T(1, 128);
-    else if (n * 2 <= 256) HG_LAUNCH_CL_T(1, 256);
-    else if (vpt <= 1) HG_LAUNCH_CL(1);
-    else if (vpt <= 2) HG_LAUNCH_CL(2);
-    else if (vpt <= 4) HG_LAUNCH_CL(4);
-    else if (vpt <= 8) HG_LAUNCH_CL(8);
-    else HG_LAUNCH_CL(16);
-#undef HG_LAUNCH_CL
-#undef HG_LAUNCH_CL_T
-    return check_launch("hg_adain_cl_fwd");
+    dim3 grid(g.chunks, batch);
+    if (g.chunks == 1) {
+        adain_cl_apply_kernel<true><<<grid, kClThreads, 0, st>>>(xp, nullptr, scale, bias, yp, save_mean, save_rstd, g, sb_stride,
+                                                                eps, neg_slope);
+        return check_launch("hg_adain_cl_fwd");
+    }
+    HG_REQUIRE(workspace && workspace_bytes >= (long long)batch * (g.chunks + 1) * 2 * channels * (long long)sizeof(float),
+               HG_ERR_INVALID_ARG, "hg_adain_cl_fwd: workspace smaller than hg_adain_cl_workspace_bytes()");
+    float *part = static_cast<float *>(workspace);
+    adain_cl_stats_kernel<<<grid, kClThreads, 0, st>>>(xp, part, g);
+    rc = check_launch("hg_adain_cl_fwd(stats)");
+    if (rc) return rc;
+    dim3 fgrid((channels + 255) / 256, batch);
+    adain_cl_finalize_kernel<<<fgrid, 256, 0, st>>>(xp, part, save_mean, save_rstd, nullptr, nullptr, g, channels, 0, eps, 1);
+    rc = check_launch("hg_adain_cl_fwd(finalize)");
+    if (rc) return rc;
+    adain_cl_apply_kernel<false><<<grid, kClThreads, 0, st>>>(xp, part, scale, bias, yp, save_mean, save_rstd, g, sb_stride, eps,
+                                                             neg_slope);
+    return check_launch("hg_adain_cl_fwd(apply)");
 }
 
 extern "C" int hg_adain_cl_bwd(const void *x, const void *dy, const float *scale, const float *bias, const float *save_mean,
-                               const float *save_rstd, void *dx, float *dscale, float *dbias, int batch, int channels,
-                               int ndim, int size, int classes, int sb_stride, int dsb_stride, float neg_slope,
-                               int biased_var, void *stream)
+                               const float *save_rstd, void *dx, float *dscale, float *dbias, void *workspace,
+                               long long workspace_bytes, int batch, int channels, int ndim, int size, int classes, int sb_stride,
+                               int dsb_stride, float neg_slope, int biased_var, void *stream)
 {
     HG_REQUIRE(x && dy && save_mean && save_rstd && dx, HG_ERR_INVALID_ARG, "hg_adain_cl_bwd: null pointer");
     HG_REQUIRE((scale == nullptr) == (bias == nullptr) && (dscale == nullptr) == (dbias == nullptr), HG_ERR_INVALID_ARG,
                "hg_adain_cl_bwd: scale/bias and dscale/dbias come in pairs");
-    int n, logS, logP;
-    int rc = cl_check("hg_adain_cl_bwd", batch, channels, ndim, size, classes, n, logS, logP);
+    ClGeom g;
+    int rc = cl_geom("hg_adain_cl_bwd", batch, channels, ndim, size, classes, biased_var, g);
     if (rc) return rc;
     HG_REQUIRE((!scale || sb_stride >= channels) && (!dscale || dsb_stride >= channels), HG_ERR_INVALID_ARG,
                "hg_adain_cl_bwd: stride < channels");
-    dim3 grid(channels / kClGroup, batch);
-    adain_cl_bwd_kernel<<<grid, kBwdThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const __nv_bfloat16 *>(x), static_cast<const __nv_bfloat16 *>(dy), scale, bias, save_mean, save_rstd,
-        static_cast<__nv_bfloat16 *>(dx), dscale, dbias, channels, n, biased_var ? n : n - 1, ndim, logS, logP, sb_stride,
-        dsb_stride, neg_slope);
-    return check_launch("hg_adain_cl_bwd");
+    const __nv_bfloat16 *xp = static_cast<const __nv_bfloat16 *>(x), *gp = static_cast<const __nv_bfloat16 *>(dy);
+    __nv_bfloat16 *dp = static_cast<__nv_bfloat16 *>(dx);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    dim3 grid(g.chunks, batch);
+    if (g.chunks == 1) {
+        adain_cl_bwd_apply_kernel<true><<<grid, kClThreads, 0, st>>>(xp, gp, nullptr, scale, bias, save_mean, save_rstd, dp, dscale,
+                                                                    dbias, g, sb_stride, dsb_stride, neg_slope);
+        return check_launch("hg_adain_cl_bwd");
+    }
+    HG_REQUIRE(workspace && workspace_bytes >= (long long)batch * (g.chunks + 1) * 2 * channels * (long long)sizeof(float),
+               HG_ERR_INVALID_ARG, "hg_adain_cl_bwd: workspace smaller than hg_adain_cl_workspace_bytes()");
+    float *part = static_cast<float *>(workspace);
+    float *sums = part + (size_t)batch * g.chunks * 2 * channels;          // [b][2C]
+    adain_cl_bwd_sums_kernel<<<grid, kClThreads, 0, st>>>(xp, gp, scale, bias, save_mean, save_rstd, part, g, sb_stride, neg_slope);
+    rc = check_launch("hg_adain_cl_bwd(sums)");
+    if (rc) return rc;
+    dim3 fgrid((channels + 255) / 256, batch);
+    adain_cl_finalize_kernel<<<fgrid, 256, 0, st>>>(xp, part, sums, sums + channels, dbias, dscale, g, 2 * channels, dsb_stride,
+                                                   0.f, 0);
+    rc = check_launch("hg_adain_cl_bwd(finalize)");
+    if (rc) return rc;
+    adain_cl_bwd_apply_kernel<false><<<grid, kClThreads, 0, st>>>(xp, gp, sums, scale, bias, save_mean, save_rstd, dp, dscale,
+                                                                 dbias, g, sb_stride, dsb_stride, neg_slope);
+    return check_launch("hg_adain_cl_bwd(apply)");
 }

@@ -354,27 +354,35 @@ __host__ __device__ inline int brick_tpitch(int taps) { return taps | 1; }
 __host__ __device__ inline int brick_row_pitch(int taps) { return kBrickCo * brick_tpitch(taps) + 1; }
 
 // torch (Cin, Cout, T) fp32 -> w_fwd[t][co][ci] (B operand of forward: rows = Cout, K = Cin) and
-// w_dgrad[t][ci][co] (rows = Cin, K = Cout), bf16, written as bf16x2 pairs.
+// w_dgrad[t][ci][co] (rows = Cin, K = Cout), bf16, written as bf16x2 pairs.  T is a template parameter (1, 16,
+// 27 on the hot path) so the index arithmetic has no runtime divisions; global reads are float4 with four
+// independent loads in flight per thread.
+template <int T>
 __global__ void __launch_bounds__(256) pack_weight_kernel(const float *__restrict__ w, __nv_bfloat16 *__restrict__ w_fwd,
-                                                          __nv_bfloat16 *__restrict__ w_dgrad, int cin, int cout, int taps,
-                                                          int perm_c, int perm_s)
+                                                          __nv_bfloat16 *__restrict__ w_dgrad, int cin, int cout, int perm_c,
+                                                          int perm_s)
 {
     extern __shared__ float brick[];                    // [kBrickCi][kBrickCo][tpitch] (+1 pad per ci row)
+    constexpr int row_len = kBrickCo * T, tp = T | 1, pitch = kBrickCo * tp + 1, vec_per_row = row_len / 4;
     const int ci0 = blockIdx.x * kBrickCi, co0 = blockIdx.y * kBrickCo;
-    const int row_len = kBrickCo * taps, tp = brick_tpitch(taps), pitch = brick_row_pitch(taps);
-    for (int i = threadIdx.x; i < kBrickCi * row_len; i += blockDim.x) {
-        const int r = i / row_len, c = i - r * row_len;
-        const int co = c / taps, t = c - co * taps;
-        float v = 0.f;
-        if (ci0 + r < cin && co0 + co < cout)
-            v = w[((size_t)torch_cin(ci0 + r, perm_c, perm_s) * cout + co0) * taps + c];
-        brick[r * pitch + co * tp + t] = v;
+#pragma unroll 4
+    for (int i = threadIdx.x; i < kBrickCi * vec_per_row; i += 256) {
+        const int r = i / vec_per_row, c = (i - r * vec_per_row) * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ci0 + r < cin)      // cout % kBrickCo == 0 (checked on the host): the whole row is in range
+            v = __ldg(reinterpret_cast<const float4 *>(w + ((size_t)torch_cin(ci0 + r, perm_c, perm_s) * cout + co0) * T + c));
+        const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int co = (c + j) / T, t = (c + j) - co * T;
+            brick[r * pitch + co * tp + t] = e[j];
+        }
     }
     __syncthreads();
     if (w_dgrad) {      // [t][ci][co]: a half-warp writes one (t, ci) row of 32 co as 16 bf16x2
-        for (int i = threadIdx.x; i < taps * kBrickCi * (kBrickCo / 2); i += blockDim.x) {
+        for (int i = threadIdx.x; i < T * kBrickCi * (kBrickCo / 2); i += 256) {
             const int cp = i % (kBrickCo / 2), ci = (i / (kBrickCo / 2)) % kBrickCi, t = i / (kBrickCi * (kBrickCo / 2));
-            if (ci0 + ci < cin && co0 + 2 * cp < cout) {
+            if (ci0 + ci < cin) {
                 const float *src = brick + ci * pitch + (2 * cp) * tp + t;
                 *reinterpret_cast<__nv_bfloat162 *>(w_dgrad + ((size_t)t * cin + ci0 + ci) * cout + co0 + 2 * cp) =
                     __floats2bfloat162_rn(src[0], src[tp]);
@@ -382,9 +390,9 @@ __global__ void __launch_bounds__(256) pack_weight_kernel(const float *__restric
         }
     }
     if (w_fwd) {        // [t][co][ci]: 8 threads write one (t, co) row of 16 ci as bf16x2
-        for (int i = threadIdx.x; i < taps * kBrickCo * (kBrickCi / 2); i += blockDim.x) {
+        for (int i = threadIdx.x; i < T * kBrickCo * (kBrickCi / 2); i += 256) {
             const int cp = i % (kBrickCi / 2), co = (i / (kBrickCi / 2)) % kBrickCo, t = i / (kBrickCo * (kBrickCi / 2));
-            if (ci0 + 2 * cp < cin && co0 + co < cout) {
+            if (ci0 + 2 * cp < cin) {
                 const float *src = brick + (2 * cp) * pitch + co * tp + t;
                 *reinterpret_cast<__nv_bfloat162 *>(w_fwd + ((size_t)t * cout + co0 + co) * cin + ci0 + 2 * cp) =
                     __floats2bfloat162_rn(src[0], src[pitch]);
@@ -393,40 +401,60 @@ __global__ void __launch_bounds__(256) pack_weight_kernel(const float *__restric
     }
 }
 
-// Sum the split-K partials [split][t][ci][co] (one warp reads one 128-byte (t, ci) row of 32 co per split, four
-// splits in flight) and write the torch layout (Cin, Cout, T) fp32.  accumulate != 0: dw += result (lets the
-// caller target a live .grad buffer).
+// Sum the split-K partials [split][t][ci][co] and write the torch layout (Cin, Cout, T) fp32.  A thread reads
+// float4 (4 co) of one (t, ci) row for every split, two rows in flight; writes are float4 runs of the torch
+// rows.  accumulate != 0: dw += result (lets the caller target a live .grad buffer).  Fixed summation order.
+template <int T>
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float *__restrict__ partial, float *__restrict__ dw, int cin,
-                                                           int cout, int taps, int splits, int perm_c, int perm_s,
-                                                           int accumulate)
+                                                           int cout, int splits, int perm_c, int perm_s, int accumulate)
 {
     extern __shared__ float brick[];
+    constexpr int row_len = kBrickCo * T, tp = T | 1, pitch = kBrickCo * tp + 1, vec_per_row = row_len / 4;
     const int ci0 = blockIdx.x * kBrickCi, co0 = blockIdx.y * kBrickCo;
-    const int row_len = kBrickCo * taps, tp = brick_tpitch(taps), pitch = brick_row_pitch(taps);
-    const size_t split_stride = (size_t)taps * cin * cout;
-    for (int i = threadIdx.x; i < taps * kBrickCi * kBrickCo; i += blockDim.x) {
-        const int co = i % kBrickCo, ci = (i / kBrickCo) % kBrickCi, t = i / (kBrickCi * kBrickCo);
-        float v = 0.f;
-        if (ci0 + ci < cin && co0 + co < cout) {
-            const float *src = partial + ((size_t)t * cin + ci0 + ci) * cout + co0 + co;
+    const size_t split_stride = (size_t)T * cin * cout;
+#pragma unroll 2
+    for (int i = threadIdx.x; i < T * kBrickCi * (kBrickCo / 4); i += 256) {
+        const int cq = i % (kBrickCo / 4), ci = (i / (kBrickCo / 4)) % kBrickCi, t = i / (kBrickCi * (kBrickCo / 4));
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ci0 + ci < cin) {
+            const float *src = partial + ((size_t)t * cin + ci0 + ci) * cout + co0 + cq * 4;
             int sp = 0;
             for (; sp + 4 <= splits; sp += 4) {
-                const float a0 = src[(size_t)sp * split_stride], a1 = src[(size_t)(sp + 1) * split_stride];
-                const float a2 = src[(size_t)(sp + 2) * split_stride], a3 = src[(size_t)(sp + 3) * split_stride];
-                v += a0; v += a1; v += a2; v += a3;           // fixed order
+                const float4 a0 = __ldg(reinterpret_cast<const float4 *>(src + (size_t)sp * split_stride));
+                const float4 a1 = __ldg(reinterpret_cast<const float4 *>(src + (size_t)(sp + 1) * split_stride));
+                const float4 a2 = __ldg(reinterpret_cast<const float4 *>(src + (size_t)(sp + 2) * split_stride));
+                const float4 a3 = __ldg(reinterpret_cast<const float4 *>(src + (size_t)(sp + 3) * split_stride));
+                v.x += a0.x; v.y += a0.y; v.z += a0.z; v.w += a0.w;
+                v.x += a1.x; v.y += a1.y; v.z += a1.z; v.w += a1.w;
+                v.x += a2.x; v.y += a2.y; v.z += a2.z; v.w += a2.w;
+                v.x += a3.x; v.y += a3.y; v.z += a3.z; v.w += a3.w;
             }
-            for (; sp < splits; ++sp) v += src[(size_t)sp * split_stride];
+            for (; sp < splits; ++sp) {
+                const float4 a = __ldg(reinterpret_cast<const float4 *>(src + (size_t)sp * split_stride));
+                v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+            }
         }
-        brick[ci * pitch + co * tp + t] = v;
+        float *d = brick + ci * pitch + (cq * 4) * tp + t;
+        d[0] = v.x; d[tp] = v.y; d[2 * tp] = v.z; d[3 * tp] = v.w;
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < kBrickCi * row_len; i += blockDim.x) {
-        const int r = i / row_len, c = i - r * row_len;
-        const int co = c / taps, t = c - co * taps;
-        if (ci0 + r < cin && co0 + co < cout) {
-            float *dst = dw + ((size_t)torch_cin(ci0 + r, perm_c, perm_s) * cout + co0) * taps + c;
-            const float v = brick[r * pitch + co * tp + t];
-            *dst = accumulate ? *dst + v : v;
+#pragma unroll 2
+    for (int i = threadIdx.x; i < kBrickCi * vec_per_row; i += 256) {
+        const int r = i / vec_per_row, c = (i - r * vec_per_row) * 4;
+        if (ci0 + r < cin) {
+            float e[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int co = (c + j) / T, t = (c + j) - co * T;
+                e[j] = brick[r * pitch + co * tp + t];
+            }
+            float4 *dst = reinterpret_cast<float4 *>(dw + ((size_t)torch_cin(ci0 + r, perm_c, perm_s) * cout + co0) * T + c);
+            float4 o = make_float4(e[0], e[1], e[2], e[3]);
+            if (accumulate) {
+                const float4 old = *dst;
+                o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+            }
+            *dst = o;
         }
     }
 }
@@ -630,16 +658,22 @@ extern "C" int hg_convt_pack_weight(const float *w, void *w_fwd, void *w_dgrad, 
     HG_REQUIRE(cin > 0 && cout > 0 && taps > 0 && taps <= 27, HG_ERR_INVALID_ARG, "hg_convt_pack_weight: bad dims");
     int rc = perm_ok("hg_convt_pack_weight", cin, perm_c, perm_s);
     if (rc) return rc;
-    HG_REQUIRE(cin % 2 == 0 && cout % 2 == 0, HG_ERR_UNSUPPORTED, "hg_convt_pack_weight: Cin and Cout must be even");
-    dim3 grid((cin + kBrickCi - 1) / kBrickCi, (cout + kBrickCo - 1) / kBrickCo);
+    HG_REQUIRE(cin % 2 == 0 && cout % kBrickCo == 0, HG_ERR_UNSUPPORTED,
+               "hg_convt_pack_weight: Cin must be even and Cout a multiple of %d (got %d, %d)", kBrickCo, cin, cout);
+    HG_REQUIRE(taps == 1 || taps == 16 || taps == 27, HG_ERR_UNSUPPORTED,
+               "hg_convt_pack_weight: taps must be 1 (k1), 16 (2-D k4) or 27 (3-D k3), got %d", taps);
+    dim3 grid((cin + kBrickCi - 1) / kBrickCi, cout / kBrickCo);
     const size_t smem = (size_t)kBrickCi * brick_row_pitch(taps) * sizeof(float);
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(pack_weight_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        cudaFuncSetAttribute(pack_weight_kernel<27>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
         attr_set = true;
     }
-    pack_weight_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(
-        w, static_cast<__nv_bfloat16 *>(w_fwd), static_cast<__nv_bfloat16 *>(w_dgrad), cin, cout, taps, perm_c, perm_s);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    __nv_bfloat16 *wf = static_cast<__nv_bfloat16 *>(w_fwd), *wd = static_cast<__nv_bfloat16 *>(w_dgrad);
+    if (taps == 1) pack_weight_kernel<1><<<grid, 256, smem, st>>>(w, wf, wd, cin, cout, perm_c, perm_s);
+    else if (taps == 16) pack_weight_kernel<16><<<grid, 256, smem, st>>>(w, wf, wd, cin, cout, perm_c, perm_s);
+    else pack_weight_kernel<27><<<grid, 256, smem, st>>>(w, wf, wd, cin, cout, perm_c, perm_s);
     return check_launch("hg_convt_pack_weight");
 }
 
@@ -790,7 +824,7 @@ extern "C" int hg_convt_wgrad(const void *x, const void *dy_s2d, float *dw, void
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(wgrad_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgradSmemBudget);
-        cudaFuncSetAttribute(wgrad_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        cudaFuncSetAttribute(wgrad_reduce_kernel<27>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
         attr_set = true;
     }
     dim3 grid(cin / kBM, cout / bn, np * pl.splits);
@@ -799,7 +833,9 @@ extern "C" int hg_convt_wgrad(const void *x, const void *dy_s2d, float *dw, void
     if (rc) return rc;
     dim3 rgrid((cin + kBrickCi - 1) / kBrickCi, (cout + kBrickCo - 1) / kBrickCo);
     const size_t rsmem = (size_t)kBrickCi * brick_row_pitch(c.taps) * sizeof(float);
-    wgrad_reduce_kernel<<<rgrid, 256, rsmem, st>>>(static_cast<const float *>(workspace), dw, cin, cout, c.taps, pl.splits,
-                                                  perm_c, perm_s, accumulate);
+    const float *part = static_cast<const float *>(workspace);
+    if (c.taps == 1) wgrad_reduce_kernel<1><<<rgrid, 256, rsmem, st>>>(part, dw, cin, cout, pl.splits, perm_c, perm_s, accumulate);
+    else if (c.taps == 16) wgrad_reduce_kernel<16><<<rgrid, 256, rsmem, st>>>(part, dw, cin, cout, pl.splits, perm_c, perm_s, accumulate);
+    else wgrad_reduce_kernel<27><<<rgrid, 256, rsmem, st>>>(part, dw, cin, cout, pl.splits, perm_c, perm_s, accumulate);
     return check_launch("hg_convt_wgrad(reduce)");
 }

@@ -48,41 +48,47 @@ __device__ __forceinline__ void unpack8_f(const uint4 &u, float *f)
     }
 }
 
-// smem weight layout: a lane's 8 channels of (tap, co) are two float4 at [(tap*COUT+co)][half][sub] -> the L
-// lanes of a pixel read L consecutive 16-byte chunks (conflict-free), pixels of a warp read the same chunks
-// (broadcast).
+// smem weight layout: [sub][tap*COUT + co][8 channels] with a padded per-sub stride: a thread keeps ONE base
+// pointer (its channel octet) and every (tap, co) access is a compile-time offset from it -- no per-access index
+// arithmetic.  The stride (72*COUT + 4 floats = an odd number of 16-byte groups) makes the L lanes of a pixel hit
+// distinct bank groups.
+template <int COUT>
+__host__ __device__ constexpr int fc_wstride() { return 9 * COUT * 8 + 4; }
+
 template <int COUT>
 __device__ __forceinline__ void load_weights_smem(float *ws, const float *__restrict__ w, int C)
 {
-    const int L = C >> 3;
     for (int i = threadIdx.x; i < 9 * COUT * C; i += blockDim.x) {
-        const int ci = i % C, co = (i / C) % COUT, t = i / (C * COUT);
-        const int sub = ci >> 3, h = (ci >> 2) & 1, q = ci & 3;
-        ws[((((t * COUT + co) * 2 + h) * L + sub) << 2) + q] = w[((size_t)co * C + ci) * 9 + t];
+        const int t = i % 9, ci = (i / 9) % C, co = i / (9 * C);          // torch order (co, ci, t): coalesced read
+        ws[(ci >> 3) * fc_wstride<COUT>() + (t * COUT + co) * 8 + (ci & 7)] = w[i];
     }
 }
 
-__device__ __forceinline__ void lane_weights(const float *ws, int tc, int L, int sub, float (&wv)[8])
+// wsub = ws + sub * fc_wstride<COUT>();  tc = tap * COUT + co (compile-time at every call site)
+__device__ __forceinline__ void lane_weights(const float *wsub, int tc, float (&wv)[8])
 {
-    const float4 a = *reinterpret_cast<const float4 *>(ws + (((tc * 2 + 0) * L + sub) << 2));
-    const float4 b = *reinterpret_cast<const float4 *>(ws + (((tc * 2 + 1) * L + sub) << 2));
+    const float4 a = *reinterpret_cast<const float4 *>(wsub + tc * 8);
+    const float4 b = *reinterpret_cast<const float4 *>(wsub + tc * 8 + 4);
     wv[0] = a.x; wv[1] = a.y; wv[2] = a.z; wv[3] = a.w; wv[4] = b.x; wv[5] = b.y; wv[6] = b.z; wv[7] = b.w;
 }
 
 // -------------------------------------------------------------------------------------------------
 // forward
 // -------------------------------------------------------------------------------------------------
-template <int COUT>
+// LT > 0: compile-time lane count (C = 8 * LT, tile 256/LT pixels wide, needs S >= 256/LT): the hot path C = 64.
+template <int COUT, int LT>
 __global__ void __launch_bounds__(kFcThreads, 2) final_conv_tanh_fwd_kernel(const __nv_bfloat16 *__restrict__ x,
                                                                             const float *__restrict__ w,
                                                                             const float *__restrict__ bias,
-                                                                            float *__restrict__ out, int C, int S, int tw,
+                                                                            float *__restrict__ out, int C, int S, int tw_arg,
                                                                             int tiles_x)
 {
-    extern __shared__ __align__(16) float ws[];        // [9][COUT][2][L][4]
+    extern __shared__ __align__(16) float ws[];        // [L][9*COUT][8] (+4 pad per L)
     load_weights_smem<COUT>(ws, w, C);
     __syncthreads();
-    const int L = C >> 3, sub = threadIdx.x % L, slot = threadIdx.x / L;
+    const int L = LT > 0 ? LT : (C >> 3), tw = LT > 0 ? kFcThreads / LT : tw_arg;
+    const int sub = threadIdx.x % L, slot = threadIdx.x / L;
+    const float *wsub = ws + sub * fc_wstride<COUT>();
     const int lx = slot % tw, ly = slot / tw, th = (kFcThreads / L) / tw;
     const int b = blockIdx.y, tile_x = blockIdx.x % tiles_x, tile_y = blockIdx.x / tiles_x;
     const int px = tile_x * tw + lx, y0 = tile_y * th * kFcR + ly * kFcR;
@@ -116,7 +122,7 @@ __global__ void __launch_bounds__(kFcThreads, 2) final_conv_tanh_fwd_kernel(cons
 #pragma unroll
                 for (int co = 0; co < COUT; ++co) {
                     float wv[8];
-                    lane_weights(ws, (ty * 3 + tx) * COUT + co, L, sub, wv);
+                    lane_weights(wsub, (ty * 3 + tx) * COUT + co, wv);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) acc[r][co] = fmaf(f[j], wv[j], acc[r][co]);
                 }
@@ -168,17 +174,19 @@ __device__ __forceinline__ float stage_g_tile(float *gs, const float *__restrict
 // -------------------------------------------------------------------------------------------------
 // dx[b,y,x,ci] = sum_(co,ty,tx) g[b,co,y-ty+1,x-tx+1] * w[co,ci,ty,tx]
 // -------------------------------------------------------------------------------------------------
-template <int COUT>
+template <int COUT, int LT>
 __global__ void __launch_bounds__(kFcThreads, 2) final_conv_tanh_bwd_x_kernel(const float *__restrict__ w,
                                                                               const float *__restrict__ out,
                                                                               const float *__restrict__ dout,
                                                                               __nv_bfloat16 *__restrict__ dx, int C, int S,
-                                                                              int tw, int tiles_x)
+                                                                              int tw_arg, int tiles_x)
 {
     extern __shared__ __align__(16) float ws[];        // weights, then the g tile
-    const int L = C >> 3, sub = threadIdx.x % L, slot = threadIdx.x / L;
+    const int L = LT > 0 ? LT : (C >> 3), tw = LT > 0 ? kFcThreads / LT : tw_arg;
+    const int sub = threadIdx.x % L, slot = threadIdx.x / L;
+    const float *wsub = ws + sub * fc_wstride<COUT>();
     const int lx = slot % tw, ly = slot / tw, th = (kFcThreads / L) / tw, TH = th * kFcR;
-    float *gs = ws + 9 * COUT * C;
+    float *gs = ws + L * fc_wstride<COUT>();
     const int b = blockIdx.y, tile_x = blockIdx.x % tiles_x, tile_y = blockIdx.x / tiles_x;
     load_weights_smem<COUT>(ws, w, C);
     stage_g_tile<COUT>(gs, out, dout, b, S, tile_x * tw, tile_y * TH, tw, TH, 0, COUT);
@@ -198,7 +206,7 @@ __global__ void __launch_bounds__(kFcThreads, 2) final_conv_tanh_bwd_x_kernel(co
 #pragma unroll
             for (int co = 0; co < COUT; ++co) {
                 float wv[8];
-                lane_weights(ws, (ty * 3 + tx) * COUT + co, L, sub, wv);
+                lane_weights(wsub, (ty * 3 + tx) * COUT + co, wv);
                 const float *gp = gs + (co * gh + ly * kFcR + 2 - ty) * gw + lx + 2 - tx;
 #pragma unroll
                 for (int r = 0; r < kFcR; ++r) {
@@ -231,16 +239,17 @@ __global__ void __launch_bounds__(kFcThreads, 2) final_conv_tanh_bwd_x_kernel(co
 // grid = (kFcDwCtas, COUT): a CTA owns one co and strides over (sample, tile); partials per CTA:
 // part[(cta * COUT + co) * (9*C + 1) + tap*C + ci], bias sum at index 9*C.
 // -------------------------------------------------------------------------------------------------
-template <int COUT>
+template <int COUT, int LT>
 __global__ void __launch_bounds__(kFcThreads, 2) final_conv_tanh_bwd_w_kernel(const __nv_bfloat16 *__restrict__ x,
                                                                               const float *__restrict__ out,
                                                                               const float *__restrict__ dout,
                                                                               float *__restrict__ part, int C, int S, int B,
-                                                                              int tw, int tiles_x, int tiles_y)
+                                                                              int tw_arg, int tiles_x, int tiles_y)
 {
     extern __shared__ __align__(16) float gs[];        // g tile [(TH+2)][(tw+2)], later the reduction scratch
     __shared__ float bsum[kFcThreads / 32];
-    const int L = C >> 3, sub = threadIdx.x % L, slot = threadIdx.x / L;
+    const int L = LT > 0 ? LT : (C >> 3), tw = LT > 0 ? kFcThreads / LT : tw_arg;
+    const int sub = threadIdx.x % L, slot = threadIdx.x / L;
     const int lx = slot % tw, ly = slot / tw, th = (kFcThreads / L) / tw, TH = th * kFcR;
     const int co = blockIdx.y;
     const int gw = tw + 2;
@@ -350,13 +359,24 @@ static int final_check(const char *who, int batch, int cin, int cout, int size)
     return HG_OK;
 }
 
-#define HG_FC_DISPATCH(COUT_VAR, CALL)      \
-    switch (COUT_VAR) {                     \
-    case 1: { constexpr int CO = 1; CALL; } break; \
-    case 2: { constexpr int CO = 2; CALL; } break; \
-    case 3: { constexpr int CO = 3; CALL; } break; \
-    default: { constexpr int CO = 4; CALL; } break; \
+// CO = Cout, LT = compile-time lanes per pixel (8 for the hot path Cout 3 / Cin 64 / S >= 32, else 0 = runtime)
+#define HG_FC_DISPATCH(COUT_VAR, HOT, CALL)                         \
+    switch (COUT_VAR) {                                             \
+    case 1: { constexpr int CO = 1, LT = 0; CALL; } break;          \
+    case 2: { constexpr int CO = 2, LT = 0; CALL; } break;          \
+    case 3:                                                         \
+        if (HOT) { constexpr int CO = 3, LT = 8; CALL; }            \
+        else { constexpr int CO = 3, LT = 0; CALL; }                \
+        break;                                                      \
+    default: { constexpr int CO = 4, LT = 0; CALL; } break;         \
     }
+
+template <int COUT>
+static size_t fc_weight_smem_floats(int cin) { return (size_t)(cin / 8) * fc_wstride<COUT>(); }
+static size_t fc_weight_smem_bytes(int cin, int cout)
+{
+    return (size_t)(cin / 8) * (9 * cout * 8 + 4) * sizeof(float);
+}
 
 extern "C" int hg_final_conv_tanh_fwd(const void *x, const float *w, const float *bias, float *out, int batch, int cin,
                                       int cout, int size, void *stream)
@@ -366,9 +386,10 @@ extern "C" int hg_final_conv_tanh_fwd(const void *x, const float *w, const float
     if (rc) return rc;
     const FcGeom g = fc_geom(cin, size);
     dim3 grid(g.tiles_x * g.tiles_y, batch);
-    const size_t smem = (size_t)9 * cout * cin * sizeof(float);
+    const size_t smem = fc_weight_smem_bytes(cin, cout);
+    const bool hot = cin == 64 && size >= 32;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    HG_FC_DISPATCH(cout, (final_conv_tanh_fwd_kernel<CO><<<grid, kFcThreads, smem, st>>>(
+    HG_FC_DISPATCH(cout, hot, (final_conv_tanh_fwd_kernel<CO, LT><<<grid, kFcThreads, smem, st>>>(
                              static_cast<const __nv_bfloat16 *>(x), w, bias, out, cin, size, g.tw, g.tiles_x)));
     return check_launch("hg_final_conv_tanh_fwd");
 }
@@ -391,10 +412,11 @@ extern "C" int hg_final_conv_tanh_bwd(const void *x, const float *w, const float
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const FcGeom g = fc_geom(cin, size);
     const size_t tile_floats = (size_t)(g.TH + 2) * (g.tw + 2);
+    const bool hot = cin == 64 && size >= 32;
     if (dx) {
         dim3 grid(g.tiles_x * g.tiles_y, batch);
-        const size_t smem = ((size_t)9 * cout * cin + cout * tile_floats) * sizeof(float);
-        HG_FC_DISPATCH(cout, (final_conv_tanh_bwd_x_kernel<CO><<<grid, kFcThreads, smem, st>>>(
+        const size_t smem = fc_weight_smem_bytes(cin, cout) + cout * tile_floats * sizeof(float);
+        HG_FC_DISPATCH(cout, hot, (final_conv_tanh_bwd_x_kernel<CO, LT><<<grid, kFcThreads, smem, st>>>(
                                  w, out, dout, static_cast<__nv_bfloat16 *>(dx), cin, size, g.tw, g.tiles_x)));
         rc = check_launch("hg_final_conv_tanh_bwd(x)");
         if (rc) return rc;
@@ -403,7 +425,7 @@ extern "C" int hg_final_conv_tanh_bwd(const void *x, const float *w, const float
     size_t wsmem = tile_floats > (size_t)groups * cin ? tile_floats : (size_t)groups * cin;
     wsmem *= sizeof(float);
     dim3 wgrid(kFcDwCtas, cout);
-    HG_FC_DISPATCH(cout, (final_conv_tanh_bwd_w_kernel<CO><<<wgrid, kFcThreads, wsmem, st>>>(
+    HG_FC_DISPATCH(cout, hot, (final_conv_tanh_bwd_w_kernel<CO, LT><<<wgrid, kFcThreads, wsmem, st>>>(
                              static_cast<const __nv_bfloat16 *>(x), out, dout, static_cast<float *>(workspace), cin, size, batch,
                              g.tw, g.tiles_x, g.tiles_y)));
     rc = check_launch("hg_final_conv_tanh_bwd(w)");

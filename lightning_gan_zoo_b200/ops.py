@@ -400,8 +400,12 @@ class _AdaInChannelsLast(torch.autograd.Function):
         y = torch.empty((b,) + (up * size,) * ndim + (c,), dtype=torch.bfloat16, device=x.device)
         mean = torch.empty((b, c), dtype=torch.float32, device=x.device)
         rstd = torch.empty((b, c), dtype=torch.float32, device=x.device)
-        _lib.call("hg_adain_cl_fwd", _ptr(x), _ptr(scale), _ptr(bias), _ptr(y), _ptr(mean), _ptr(rstd), b, c, ndim, size,
-                  classes, sbs, ctypes.c_float(eps), ctypes.c_float(neg_slope), int(biased), _stream())
+        nbytes = _lib.load().hg_adain_cl_workspace_bytes(b, c, ndim, size, classes)
+        if nbytes < 0:
+            raise _lib.HologanB200Error(f"hg_adain_cl_fwd: unsupported shape C={c} size={size} classes={classes}")
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device) if nbytes else None
+        _lib.call("hg_adain_cl_fwd", _ptr(x), _ptr(scale), _ptr(bias), _ptr(y), _ptr(mean), _ptr(rstd), _ptr(ws), nbytes, b, c,
+                  ndim, size, classes, sbs, ctypes.c_float(eps), ctypes.c_float(neg_slope), int(biased), _stream())
         ctx.save_for_backward(x, scale, bias, mean, rstd)
         ctx.meta = (b, c, ndim, size, classes, sbs, float(neg_slope), int(biased))
         return y
@@ -413,9 +417,11 @@ class _AdaInChannelsLast(torch.autograd.Function):
         dy = dy.contiguous()
         dx = torch.empty_like(x)
         dsb = torch.empty((2, b, c), dtype=torch.float32, device=x.device) if scale is not None else None
+        nbytes = _lib.load().hg_adain_cl_workspace_bytes(b, c, ndim, size, classes)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device) if nbytes else None
         _lib.call("hg_adain_cl_bwd", _ptr(x), _ptr(dy), _ptr(scale), _ptr(bias), _ptr(mean), _ptr(rstd), _ptr(dx),
-                  _ptr(None if dsb is None else dsb[0]), _ptr(None if dsb is None else dsb[1]), b, c, ndim, size, classes,
-                  sbs, c, ctypes.c_float(neg_slope), biased, _stream())
+                  _ptr(None if dsb is None else dsb[0]), _ptr(None if dsb is None else dsb[1]), _ptr(ws), nbytes, b, c, ndim,
+                  size, classes, sbs, c, ctypes.c_float(neg_slope), biased, _stream())
         if dsb is None:
             return dx, None, None, None, None, None, None, None
         return dx, dsb[0], dsb[1], None, None, None, None, None

@@ -104,7 +104,7 @@ def test_adain_channels_last(b, ndim, size, c, classes, slope):
 def test_unsupported():
     from lightning_gan_zoo_b200._lib import HologanB200Error
     x = torch.zeros(1, 16, 16, 4, 24, dtype=BF, device=DEV)
-    with pytest.raises(HologanB200Error, match="multiple of 16"):
+    with pytest.raises(HologanB200Error, match="unsupported shape"):
         ops.adain_act_channels_last(x, torch.ones(1, 24, device=DEV), torch.zeros(1, 24, device=DEV), 2, 4)
     with pytest.raises(HologanB200Error, match="bf16 only"):
         ops.rotate_fwd_raw(torch.zeros(1, 16, 16, 16, 8, device=DEV), torch.eye(4, device=DEV)[None], 0, ops.HG_NDHWC,

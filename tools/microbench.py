@@ -18,14 +18,36 @@ if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")):
     PEAK = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
 
 
-def time_rot(fn, bufs, iters=30):
+def time_rot(fn, bufs, iters=30, graph=True):
+    """Seconds per call of fn over rotating buffers.  The calls are captured into ONE CUDA graph and the graph
+    replay is timed with CUDA events, so host-side launch overhead (ctypes, allocator, autograd) does not hide
+    kernels that are shorter than a Python call."""
     for b in bufs[:3]:
         fn(b)
     torch.cuda.synchronize()
+    if not graph:                                   # autograd-driven calls cannot be stream-captured
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(iters):
+            fn(bufs[i % len(bufs)])
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters * 1e-3
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        fn(bufs[0])
+        torch.cuda.synchronize()
+        with torch.cuda.graph(graph, stream=side):
+            for i in range(iters):
+                fn(bufs[i % len(bufs)])
+    torch.cuda.current_stream().wait_stream(side)
+    graph.replay()
+    torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for i in range(iters):
-        fn(bufs[i % len(bufs)])
+    graph.replay()
     e1.record()
     torch.cuda.synchronize()
     return e0.elapsed_time(e1) / iters * 1e-3
@@ -106,10 +128,9 @@ def conv():
         y = torch.empty_like(dys[0]); dx = torch.empty_like(xs[0]); dw = torch.empty_like(w)
         nws = _lib.load().hg_convt_wgrad_workspace_bytes(B, cin, cout, ndim, size, k)
         ws = torch.empty(nws, dtype=torch.uint8, device=DEV)
-        st = ops._stream()
-        f = lambda i: _lib.call("hg_convt_fwd", P(xs[i]), P(wf), P(None), P(y), B, cin, cout, ndim, size, k, ctypes.c_float(1.0), st)
-        g = lambda i: _lib.call("hg_convt_dgrad", P(dys[i]), P(wd), P(dx), B, cin, cout, ndim, size, k, st)
-        h = lambda i: _lib.call("hg_convt_wgrad", P(xs[i]), P(dys[i]), P(dw), P(ws), nws, B, cin, cout, ndim, size, k, 0, 0, 0, st)
+        f = lambda i: _lib.call("hg_convt_fwd", P(xs[i]), P(wf), P(None), P(y), B, cin, cout, ndim, size, k, ctypes.c_float(1.0), ops._stream())
+        g = lambda i: _lib.call("hg_convt_dgrad", P(dys[i]), P(wd), P(dx), B, cin, cout, ndim, size, k, ops._stream())
+        h = lambda i: _lib.call("hg_convt_wgrad", P(xs[i]), P(dys[i]), P(dw), P(ws), nws, B, cin, cout, ndim, size, k, 0, 0, 0, ops._stream())
         row = f"{name:8s} {flops/1e9:7.1f} GF"
         for tag, fn in (("fwd", f), ("dgrad", g), ("wgrad", h)):
             t = time_rot(fn, list(range(nb)), iters=12)
@@ -117,6 +138,81 @@ def conv():
             row += f" | {tag} {t*1e6:7.1f} us {flops/t/1e12:6.0f} TF/s ({flops/t/1e12/peak*100:4.1f}%)"
         print(row)
     print("totals: " + ", ".join(f"{k} {v*1e6:.0f} us" for k, v in tot.items()))
+
+
+def pipeline():
+    """The HBM-bound kernels of the bf16 pipeline at their hot-path shapes (B = 64): channels-last AdaIN on
+    s2d conv outputs, channels-last rotate (-> PROJ), final conv + tanh, weight packing, activation backward."""
+    import ctypes
+    from lightning_gan_zoo_b200 import _lib
+    B = 64
+    P = ops._ptr
+    bf = torch.bfloat16
+    print(f"# bf16 pipeline kernels at B={B}; HBM peak {PEAK} GB/s; bytes = algorithmic (DESIGN.md 4.1)")
+
+    def report(name, t, nbytes):
+        print(f"{name:44s} {t*1e6:8.1f} us {nbytes/t/1e9:7.0f} GB/s ({nbytes/t/1e9/PEAK*100:5.1f}%)")
+
+    # AdaIN channels-last: (ndim, size, classes, C)  -- block1, block2, block3, block4 outputs; D blocks
+    for name, ndim, size, classes, c, biased in [("adain_cl block1 (4^3 x8 -> 8^3, C128)", 3, 4, 8, 128, 0),
+                                                 ("adain_cl block2 (8^3 x8 -> 16^3, C64)", 3, 8, 8, 64, 0),
+                                                 ("adain_cl block3 (16^2 x4 -> 32^2, C256)", 2, 16, 4, 256, 0),
+                                                 ("adain_cl block4 (32^2 x4 -> 64^2, C64)", 2, 32, 4, 64, 0),
+                                                 ("inorm_cl D blk0 (16^2, C128)", 2, 16, 1, 128, 1),
+                                                 ("inorm_cl D blk1 (8^2, C256)", 2, 8, 1, 256, 1),
+                                                 ("inorm_cl D blk2 (4^2, C512)", 2, 4, 1, 512, 1)]:
+        n = size ** ndim * classes
+        nb = min(12, max(3, int(300e6 // (B * n * c * 2)) + 1))
+        xs = [torch.randn(B, n, c, device=DEV).to(bf) for _ in range(nb)]
+        dy = torch.randn(B, n, c, device=DEV).to(bf)
+        sc = torch.rand(B, c, device=DEV); bi = torch.randn(B, c, device=DEV)
+        mean = torch.empty(B, c, device=DEV); rstd = torch.empty(B, c, device=DEV)
+        y = torch.empty_like(xs[0]); dx = torch.empty_like(xs[0]); ds = torch.empty(B, c, device=DEV); db = torch.empty(B, c, device=DEV)
+        nws = _lib.load().hg_adain_cl_workspace_bytes(B, c, ndim, size, classes)
+        wsp = torch.empty(max(nws, 16), dtype=torch.uint8, device=DEV)
+        f = lambda x: _lib.call("hg_adain_cl_fwd", P(x), P(sc), P(bi), P(y), P(mean), P(rstd), P(wsp), nws, B, c, ndim, size,
+                                classes, c, ctypes.c_float(1e-8), ctypes.c_float(0.0), biased, ops._stream())
+        g = lambda x: _lib.call("hg_adain_cl_bwd", P(x), P(dy), P(sc), P(bi), P(mean), P(rstd), P(dx), P(ds), P(db), P(wsp), nws,
+                                B, c, ndim, size, classes, c, c, ctypes.c_float(0.0), biased, ops._stream())
+        tf = time_rot(f, xs); f(xs[0]); tb = time_rot(g, xs)
+        report(name + " fwd", tf, 2 * B * n * c * 2)
+        report(name + " bwd", tb, 3 * B * n * c * 2)
+    # rotate channels-last -> PROJ
+    s, c = 16, 64
+    a = ops.view_to_affine(views(B), s, s).to(DEV)
+    vols = [torch.randn(B, s, s, s, c, device=DEV).to(bf) for _ in range(10)]
+    tf = time_rot(lambda v: ops.rotate_fwd_raw(v, a, ops.HG_BORDER_ZERO, ops.HG_NDHWC, ops.HG_PROJ), vols)
+    tb = time_rot(lambda v: ops.rotate_bwd_raw(v, a, c, s, ops.HG_BORDER_ZERO, ops.HG_NDHWC, ops.HG_PROJ), vols)
+    report("rotate_cl NDHWC->PROJ (64,16^3,64) fwd", tf, 2 * B * s ** 3 * c * 2)
+    report("rotate_cl NDHWC->PROJ (64,16^3,64) bwd", tb, 2 * B * s ** 3 * c * 2)
+    del vols
+    # final conv + tanh
+    xs = [torch.randn(B, 64, 64, 64, device=DEV).to(bf).requires_grad_(True) for _ in range(10)]
+    w = (torch.randn(3, 64, 3, 3, device=DEV) * 0.02).requires_grad_(True); bias = torch.zeros(3, device=DEV, requires_grad=True)
+    dout = torch.randn(B, 3, 64, 64, device=DEV)
+    outs = {}
+    def ff(x):
+        outs["o"] = ops.final_conv_tanh(x, w, bias)
+    tf = time_rot(ff, xs)
+    def fb(x):
+        o = ops.final_conv_tanh(x, w, bias)
+        o.backward(dout)
+    tfb = time_rot(fb, xs, graph=False)
+    nbytes = B * 64 * 64 * 64 * 2 + B * 3 * 64 * 64 * 4
+    report("final_conv_tanh (64,64^2,64->3) fwd", tf, nbytes)
+    report("final_conv_tanh fwd+bwd (dx + dw)", tfb, 3 * nbytes)
+    # weight packing (all five conv layers of G) and activation backward of the projection
+    ws = [torch.randn(512, 128, 3, 3, 3, device=DEV), torch.randn(128, 64, 3, 3, 3, device=DEV), torch.randn(1024, 1024, 1, 1, device=DEV),
+          torch.randn(1024, 256, 4, 4, device=DEV), torch.randn(256, 64, 4, 4, device=DEV)]
+    def pk(_):
+        for wt in ws:
+            ops.pack_convt_weight(wt)
+    t = time_rot(pk, [0, 1, 2])
+    report("pack_weight x5 (7.5 M params: 4 B in, 2x2 B out)", t, sum(wt.numel() for wt in ws) * 8)
+    ys = [torch.randn(B * 256, 1024, device=DEV).to(bf) for _ in range(6)]
+    dyy = torch.randn(B * 256, 1024, device=DEV).to(bf)
+    t = time_rot(lambda yv: ops.act_bwd_bias(yv, dyy, 0.0, True), ys)
+    report("act_bwd_bias (16384 x 1024)", t, 3 * B * 256 * 1024 * 2)
 
 
 if __name__ == "__main__":
@@ -127,3 +223,5 @@ if __name__ == "__main__":
         adain()
     if what in ("conv", "all"):
         conv()
+    if what in ("pipeline", "all"):
+        pipeline()
