@@ -75,77 +75,80 @@ __device__ __forceinline__ void lane_weights(const float *wsub, int tc, float (&
 // -------------------------------------------------------------------------------------------------
 // forward
 // -------------------------------------------------------------------------------------------------
-// LT > 0: compile-time lane count (C = 8 * LT, tile 256/LT pixels wide, needs S >= 256/LT): the hot path C = 64.
-template <int COUT, int LT>
+// -------------------------------------------------------------------------------------------------
+// forward.  CTA = 8 warps on a tile of 32 pixels x kFcR rows.  The input tile (with halo) is staged in shared
+// memory by coalesced 16-byte loads (pixel pitch C*2 + 16 bytes: conflict-free for the reads below); lane =
+// pixel column, WARP = channel octet, so every weight fetch is a warp-uniform LDS.128 (one wavefront) feeding
+// 8 * kFcR FMAs per thread, and the FP32 pipe -- not shared memory -- is the limit.  Partial sums of the
+// octets meet in shared memory; bias + tanh + one coalesced 128-byte store per (co, row).
+// -------------------------------------------------------------------------------------------------
+constexpr int kFcTw = 32;
+
+__host__ __device__ inline int fc_pixel_pitch(int C) { return C * 2 + 16; }      // bytes
+
+template <int COUT>
 __global__ void __launch_bounds__(kFcThreads, 2) final_conv_tanh_fwd_kernel(const __nv_bfloat16 *__restrict__ x,
                                                                             const float *__restrict__ w,
                                                                             const float *__restrict__ bias,
-                                                                            float *__restrict__ out, int C, int S, int tw_arg,
-                                                                            int tiles_x)
+                                                                            float *__restrict__ out, int C, int S, int tiles_x)
 {
-    extern __shared__ __align__(16) float ws[];        // [L][9*COUT][8] (+4 pad per L)
-    load_weights_smem<COUT>(ws, w, C);
-    __syncthreads();
-    const int L = LT > 0 ? LT : (C >> 3), tw = LT > 0 ? kFcThreads / LT : tw_arg;
-    const int sub = threadIdx.x % L, slot = threadIdx.x / L;
-    const float *wsub = ws + sub * fc_wstride<COUT>();
-    const int lx = slot % tw, ly = slot / tw, th = (kFcThreads / L) / tw;
+    extern __shared__ __align__(16) unsigned char smem_fc[];
+    const int L = C >> 3, pitch = fc_pixel_pitch(C);
+    float *ws = reinterpret_cast<float *>(smem_fc);                           // [L][9*COUT*8 + 4]
+    unsigned char *xs = smem_fc + (size_t)L * fc_wstride<COUT>() * sizeof(float);   // [(R+2)][(32+2)] pixels
+    float *red = reinterpret_cast<float *>(xs + (size_t)(kFcR + 2) * (kFcTw + 2) * pitch);   // [8][R*COUT][32]
     const int b = blockIdx.y, tile_x = blockIdx.x % tiles_x, tile_y = blockIdx.x / tiles_x;
-    const int px = tile_x * tw + lx, y0 = tile_y * th * kFcR + ly * kFcR;
-    const __nv_bfloat16 *xb = x + (size_t)b * S * S * C + sub * 8;
-
+    const int x0 = tile_x * kFcTw, y0 = tile_y * kFcR;
+    load_weights_smem<COUT>(ws, w, C);
+    const __nv_bfloat16 *xb = x + (size_t)b * S * S * C;
+    for (int i = threadIdx.x; i < (kFcR + 2) * (kFcTw + 2) * L; i += kFcThreads) {
+        const int v = i % L, pix = i / L, gx = pix % (kFcTw + 2), gy = pix / (kFcTw + 2);
+        const int yy = y0 + gy - 1, xx = x0 + gx - 1;
+        uint4 val = make_uint4(0, 0, 0, 0);
+        if (yy >= 0 && yy < S && xx >= 0 && xx < S) val = __ldg(reinterpret_cast<const uint4 *>(xb + ((size_t)yy * S + xx) * C) + v);
+        *reinterpret_cast<uint4 *>(xs + (size_t)pix * pitch + v * 16) = val;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float acc[kFcR][COUT];
 #pragma unroll
     for (int r = 0; r < kFcR; ++r)
 #pragma unroll
         for (int co = 0; co < COUT; ++co) acc[r][co] = 0.f;
-
+    for (int sub = warp; sub < L; sub += kFcThreads / 32) {
+        const float *wsub = ws + sub * fc_wstride<COUT>();
+        const unsigned char *xl = xs + (size_t)lane * pitch + sub * 16;
 #pragma unroll
-    for (int ri = 0; ri < kFcR + 2; ++ri) {            // input row y0 + ri - 1 feeds output rows ri - ty
-        const int yy = y0 + ri - 1;
-        uint4 raw[3];
+        for (int ty = 0; ty < 3; ++ty) {
 #pragma unroll
-        for (int tx = 0; tx < 3; ++tx) {
-            const int xx = px + tx - 1;
-            raw[tx] = make_uint4(0, 0, 0, 0);
-            if (yy >= 0 && yy < S && xx >= 0 && xx < S)
-                raw[tx] = __ldg(reinterpret_cast<const uint4 *>(xb + ((size_t)yy * S + xx) * C));
-        }
+            for (int tx = 0; tx < 3; ++tx) {
+                float f[kFcR][8];
 #pragma unroll
-        for (int tx = 0; tx < 3; ++tx) {
-            float f[8];
-            unpack8_f(raw[tx], f);
-#pragma unroll
-            for (int ty = 0; ty < 3; ++ty) {
-                const int r = ri - ty;
-                if (r < 0 || r >= kFcR) continue;
+                for (int r = 0; r < kFcR; ++r)
+                    unpack8_f(*reinterpret_cast<const uint4 *>(xl + (size_t)((r + ty) * (kFcTw + 2) + tx) * pitch), f[r]);
 #pragma unroll
                 for (int co = 0; co < COUT; ++co) {
                     float wv[8];
                     lane_weights(wsub, (ty * 3 + tx) * COUT + co, wv);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) acc[r][co] = fmaf(f[j], wv[j], acc[r][co]);
+                    for (int r = 0; r < kFcR; ++r)
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) acc[r][co] = fmaf(f[r][j], wv[j], acc[r][co]);
                 }
             }
         }
     }
-    // sum over the L lanes of the pixel (contiguous lanes of one warp)
-    for (int o = 1; o < L; o <<= 1) {
 #pragma unroll
-        for (int r = 0; r < kFcR; ++r)
+    for (int r = 0; r < kFcR; ++r)
 #pragma unroll
-            for (int co = 0; co < COUT; ++co) acc[r][co] += __shfl_xor_sync(0xffffffffu, acc[r][co], o);
-    }
-    if (sub == 0 && px < S) {
+        for (int co = 0; co < COUT; ++co) red[(warp * kFcR * COUT + r * COUT + co) * 32 + lane] = acc[r][co];
+    __syncthreads();
+    for (int k = warp; k < kFcR * COUT; k += kFcThreads / 32) {      // k = r * COUT + co
+        float sum = 0.f;
 #pragma unroll
-        for (int r = 0; r < kFcR; ++r) {
-            const int y = y0 + r;
-            if (y < S) {
-#pragma unroll
-                for (int co = 0; co < COUT; ++co)
-                    out[(((size_t)b * COUT + co) * S + y) * S + px] = tanhf(acc[r][co] + bias[co]);
-            }
-        }
+        for (int wgt = 0; wgt < kFcThreads / 32; ++wgt) sum += red[(wgt * kFcR * COUT + k) * 32 + lane];
+        const int r = k / COUT, co = k - r * COUT;
+        if (y0 + r < S && x0 + lane < S) out[(((size_t)b * COUT + co) * S + y0 + r) * S + x0 + lane] = tanhf(sum + bias[co]);
     }
 }
 
@@ -172,65 +175,72 @@ __device__ __forceinline__ float stage_g_tile(float *gs, const float *__restrict
 }
 
 // -------------------------------------------------------------------------------------------------
-// dx[b,y,x,ci] = sum_(co,ty,tx) g[b,co,y-ty+1,x-tx+1] * w[co,ci,ty,tx]
+// dx[b,y,x,ci] = sum_(co,ty,tx) g[b,co,y-ty+1,x-tx+1] * w[co,ci,ty,tx].  Same thread map as the forward (lane =
+// pixel column, warp = channel octet: warp-uniform weight fetches, conflict-free g reads); results are staged
+// in shared memory and leave as coalesced 16-byte stores.
 // -------------------------------------------------------------------------------------------------
-template <int COUT, int LT>
+template <int COUT>
 __global__ void __launch_bounds__(kFcThreads, 2) final_conv_tanh_bwd_x_kernel(const float *__restrict__ w,
                                                                               const float *__restrict__ out,
                                                                               const float *__restrict__ dout,
                                                                               __nv_bfloat16 *__restrict__ dx, int C, int S,
-                                                                              int tw_arg, int tiles_x)
+                                                                              int tiles_x)
 {
-    extern __shared__ __align__(16) float ws[];        // weights, then the g tile
-    const int L = LT > 0 ? LT : (C >> 3), tw = LT > 0 ? kFcThreads / LT : tw_arg;
-    const int sub = threadIdx.x % L, slot = threadIdx.x / L;
-    const float *wsub = ws + sub * fc_wstride<COUT>();
-    const int lx = slot % tw, ly = slot / tw, th = (kFcThreads / L) / tw, TH = th * kFcR;
-    float *gs = ws + L * fc_wstride<COUT>();
+    extern __shared__ __align__(16) unsigned char smem_fc[];
+    const int L = C >> 3, pitch = fc_pixel_pitch(C);
+    constexpr int gw = kFcTw + 2, gh = kFcR + 2;
+    float *ws = reinterpret_cast<float *>(smem_fc);
+    float *gs = ws + (size_t)L * fc_wstride<COUT>();                            // [COUT][gh][gw]
+    unsigned char *os = reinterpret_cast<unsigned char *>(gs + COUT * gh * gw + 2);   // [kFcR * 32] pixels, 16-byte aligned below
+    os = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(os) + 15) & ~uintptr_t(15));
     const int b = blockIdx.y, tile_x = blockIdx.x % tiles_x, tile_y = blockIdx.x / tiles_x;
+    const int x0 = tile_x * kFcTw, y0 = tile_y * kFcR;
     load_weights_smem<COUT>(ws, w, C);
-    stage_g_tile<COUT>(gs, out, dout, b, S, tile_x * tw, tile_y * TH, tw, TH, 0, COUT);
+    stage_g_tile<COUT>(gs, out, dout, b, S, x0, y0, kFcTw, kFcR, 0, COUT);
     __syncthreads();
-    const int px = tile_x * tw + lx, y0 = tile_y * TH + ly * kFcR;
-    const int gw = tw + 2, gh = TH + 2;
-
-    float acc[kFcR][8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int sub = warp; sub < L; sub += kFcThreads / 32) {
+        const float *wsub = ws + sub * fc_wstride<COUT>();
+        float acc[kFcR][8];
 #pragma unroll
-    for (int r = 0; r < kFcR; ++r)
+        for (int r = 0; r < kFcR; ++r)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[r][j] = 0.f;
+            for (int j = 0; j < 8; ++j) acc[r][j] = 0.f;
 #pragma unroll
-    for (int ty = 0; ty < 3; ++ty) {
+        for (int ty = 0; ty < 3; ++ty) {
 #pragma unroll
-        for (int tx = 0; tx < 3; ++tx) {
+            for (int tx = 0; tx < 3; ++tx) {
 #pragma unroll
-            for (int co = 0; co < COUT; ++co) {
-                float wv[8];
-                lane_weights(wsub, (ty * 3 + tx) * COUT + co, wv);
-                const float *gp = gs + (co * gh + ly * kFcR + 2 - ty) * gw + lx + 2 - tx;
+                for (int co = 0; co < COUT; ++co) {
+                    float wv[8];
+                    lane_weights(wsub, (ty * 3 + tx) * COUT + co, wv);
+                    const float *gp = gs + (co * gh + 2 - ty) * gw + lane + 2 - tx;
 #pragma unroll
-                for (int r = 0; r < kFcR; ++r) {
-                    const float g = gp[r * gw];
+                    for (int r = 0; r < kFcR; ++r) {
+                        const float g = gp[r * gw];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) acc[r][j] = fmaf(g, wv[j], acc[r][j]);
+                        for (int j = 0; j < 8; ++j) acc[r][j] = fmaf(g, wv[j], acc[r][j]);
+                    }
                 }
             }
         }
-    }
-    if (px < S) {
 #pragma unroll
         for (int r = 0; r < kFcR; ++r) {
-            const int y = y0 + r;
-            if (y < S) {
-                uint32_t pk[4];
+            uint32_t pk[4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    __nv_bfloat162 h = __floats2bfloat162_rn(acc[r][2 * j], acc[r][2 * j + 1]);
-                    pk[j] = *reinterpret_cast<uint32_t *>(&h);
-                }
-                st_stream_16(dx + (((size_t)b * S + y) * S + px) * C + sub * 8, make_uint4(pk[0], pk[1], pk[2], pk[3]));
+            for (int j = 0; j < 4; ++j) {
+                __nv_bfloat162 h = __floats2bfloat162_rn(acc[r][2 * j], acc[r][2 * j + 1]);
+                pk[j] = *reinterpret_cast<uint32_t *>(&h);
             }
+            *reinterpret_cast<uint4 *>(os + (size_t)(r * kFcTw + lane) * pitch + sub * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < kFcR * kFcTw * L; i += kFcThreads) {
+        const int v = i % L, pix = i / L, lx = pix % kFcTw, r = pix / kFcTw;
+        if (y0 + r < S && x0 + lx < S)
+            st_stream_16(dx + (((size_t)b * S + y0 + r) * S + x0 + lx) * C + v * 8,
+                         *reinterpret_cast<const uint4 *>(os + (size_t)pix * pitch + v * 16));
     }
 }
 
@@ -362,13 +372,13 @@ static int final_check(const char *who, int batch, int cin, int cout, int size)
 // CO = Cout, LT = compile-time lanes per pixel (8 for the hot path Cout 3 / Cin 64 / S >= 32, else 0 = runtime)
 #define HG_FC_DISPATCH(COUT_VAR, HOT, CALL)                         \
     switch (COUT_VAR) {                                             \
-    case 1: { constexpr int CO = 1, LT = 0; CALL; } break;          \
-    case 2: { constexpr int CO = 2, LT = 0; CALL; } break;          \
+    case 1: { constexpr int CO = 1, LT = 0; (void)LT; CALL; } break;          \
+    case 2: { constexpr int CO = 2, LT = 0; (void)LT; CALL; } break;          \
     case 3:                                                         \
-        if (HOT) { constexpr int CO = 3, LT = 8; CALL; }            \
-        else { constexpr int CO = 3, LT = 0; CALL; }                \
+        if (HOT) { constexpr int CO = 3, LT = 8; (void)LT; CALL; }            \
+        else { constexpr int CO = 3, LT = 0; (void)LT; CALL; }                \
         break;                                                      \
-    default: { constexpr int CO = 4, LT = 0; CALL; } break;         \
+    default: { constexpr int CO = 4, LT = 0; (void)LT; CALL; } break;         \
     }
 
 template <int COUT>
@@ -384,13 +394,21 @@ extern "C" int hg_final_conv_tanh_fwd(const void *x, const float *w, const float
     HG_REQUIRE(x && w && bias && out, HG_ERR_INVALID_ARG, "hg_final_conv_tanh_fwd: null pointer");
     int rc = final_check("hg_final_conv_tanh_fwd", batch, cin, cout, size);
     if (rc) return rc;
-    const FcGeom g = fc_geom(cin, size);
-    dim3 grid(g.tiles_x * g.tiles_y, batch);
-    const size_t smem = fc_weight_smem_bytes(cin, cout);
-    const bool hot = cin == 64 && size >= 32;
+    const int tiles_x = (size + kFcTw - 1) / kFcTw, tiles_y = (size + kFcR - 1) / kFcR;
+    dim3 grid(tiles_x * tiles_y, batch);
+    const size_t smem = fc_weight_smem_bytes(cin, cout) + (size_t)(kFcR + 2) * (kFcTw + 2) * fc_pixel_pitch(cin) +
+                        (size_t)(kFcThreads / 32) * kFcR * cout * 32 * sizeof(float);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    HG_FC_DISPATCH(cout, hot, (final_conv_tanh_fwd_kernel<CO, LT><<<grid, kFcThreads, smem, st>>>(
-                             static_cast<const __nv_bfloat16 *>(x), w, bias, out, cin, size, g.tw, g.tiles_x)));
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(final_conv_tanh_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(final_conv_tanh_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(final_conv_tanh_fwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(final_conv_tanh_fwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        attr_done = true;
+    }
+    HG_FC_DISPATCH(cout, false, (final_conv_tanh_fwd_kernel<CO><<<grid, kFcThreads, smem, st>>>(
+                                    static_cast<const __nv_bfloat16 *>(x), w, bias, out, cin, size, tiles_x)));
     return check_launch("hg_final_conv_tanh_fwd");
 }
 
@@ -414,10 +432,20 @@ extern "C" int hg_final_conv_tanh_bwd(const void *x, const float *w, const float
     const size_t tile_floats = (size_t)(g.TH + 2) * (g.tw + 2);
     const bool hot = cin == 64 && size >= 32;
     if (dx) {
-        dim3 grid(g.tiles_x * g.tiles_y, batch);
-        const size_t smem = fc_weight_smem_bytes(cin, cout) + cout * tile_floats * sizeof(float);
-        HG_FC_DISPATCH(cout, hot, (final_conv_tanh_bwd_x_kernel<CO, LT><<<grid, kFcThreads, smem, st>>>(
-                                 w, out, dout, static_cast<__nv_bfloat16 *>(dx), cin, size, g.tw, g.tiles_x)));
+        const int tiles_x = (size + kFcTw - 1) / kFcTw, tiles_y = (size + kFcR - 1) / kFcR;
+        dim3 grid(tiles_x * tiles_y, batch);
+        const size_t smem = fc_weight_smem_bytes(cin, cout) + (size_t)(cout * (kFcR + 2) * (kFcTw + 2) + 2) * sizeof(float) + 16 +
+                            (size_t)kFcR * kFcTw * fc_pixel_pitch(cin);
+        static bool attr_done = false;
+        if (!attr_done) {
+            cudaFuncSetAttribute(final_conv_tanh_bwd_x_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            cudaFuncSetAttribute(final_conv_tanh_bwd_x_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            cudaFuncSetAttribute(final_conv_tanh_bwd_x_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            cudaFuncSetAttribute(final_conv_tanh_bwd_x_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            attr_done = true;
+        }
+        HG_FC_DISPATCH(cout, false, (final_conv_tanh_bwd_x_kernel<CO><<<grid, kFcThreads, smem, st>>>(
+                                        w, out, dout, static_cast<__nv_bfloat16 *>(dx), cin, size, tiles_x)));
         rc = check_launch("hg_final_conv_tanh_bwd(x)");
         if (rc) return rc;
     }
