@@ -1,0 +1,47 @@
+#!/bin/bash
+# One gpurun call = one measurement round.  Usage (from the repo root, on the GPU box):
+#   bash tools/gpu_round.sh TAG [tests] [bench] [micro] [launches] [step] [ncu:<targets,comma-separated>]
+# With no stage names every stage runs.  Everything lands under gpurun_out/TAG_* (merged back by gpurun).
+set -u
+TAG=${1:-rXX}; shift || true
+STAGES="$*"
+[ -z "$STAGES" ] && STAGES="tests bench micro launches step ncu:rotate,rotate_cl,adain_cl,final_conv,conv"
+OUT=gpurun_out
+mkdir -p $OUT
+has() { case " $STAGES " in *" $1 "*) return 0;; esac; return 1; }
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $OUT/${TAG}_gpu.txt 2>&1
+
+if has tests; then
+  timeout 1500 python -m pytest tests -m gpu -x -q > $OUT/${TAG}_pytest_gpu.txt 2>&1
+  echo "pytest exit $?" >> $OUT/${TAG}_pytest_gpu.txt
+  tail -5 $OUT/${TAG}_pytest_gpu.txt
+fi
+if has bench; then
+  timeout 900 python bench.py --steps 60 --warmup 9 > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err
+  echo "bench exit $?"; cat $OUT/${TAG}_bench.json
+fi
+if has micro; then
+  timeout 900 python tools/microbench.py all > $OUT/${TAG}_microbench.txt 2>&1
+  echo "microbench exit $?"
+fi
+if has step; then
+  timeout 600 python tools/profile_step.py 6 > $OUT/${TAG}_torch_profiler_step.txt 2>&1
+  echo "profile_step exit $?"
+fi
+if has launches; then
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file $OUT/${TAG}_launches.csv \
+      python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-roofline > $OUT/${TAG}_launches_run.log 2>&1
+  echo "launch list exit $?"
+fi
+for st in $STAGES; do
+  case $st in ncu:*)
+    targets=$(echo ${st#ncu:} | tr ',' ' ')
+    for t in $targets; do
+      HG_NCU_REPS=1 timeout 900 ncu --set full --clock-control none --import-source on -k regex:hg:: -c 40 -f \
+          -o $OUT/${TAG}_full_$t python tools/ncu_targets.py $t > $OUT/${TAG}_full_$t.log 2>&1
+      echo "ncu full $t exit $?"
+      ncu -i $OUT/${TAG}_full_$t.ncu-rep --page raw --csv > $OUT/${TAG}_full_${t}_raw.csv 2>/dev/null
+    done;;
+  esac
+done
+ls -la $OUT | head -50

@@ -31,7 +31,7 @@ def views(b, seed=0):
     return v
 
 
-REPS = 2
+REPS = int(os.environ.get("HG_NCU_REPS", "2"))
 if on("adain_cl"):
     for ndim, size, classes, c in [(2, 16, 4, 256), (2, 32, 4, 64)]:
         n = size ** ndim * classes
