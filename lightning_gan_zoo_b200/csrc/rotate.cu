@@ -220,10 +220,20 @@ int hg_rotate_cl_bwd_impl(const void *grad_out, const float *a_inv, void *grad_v
                           long long workspace_bytes, int batch, int channels, int size, int logS, int out_layout,
                           cudaStream_t st);
 
+// rotate_il.cu
+bool hg_rotate_il_supported(int channels, int size, int dtype);
+size_t hg_rotate_il_ws_bytes(int batch, int size);
+int hg_rotate_il_fwd(const void *vol, const float *a_inv, void *out, int batch, int channels, int size, int logS, int dtype,
+                     int border, cudaStream_t st);
+int hg_rotate_il_bwd(const void *grad_out, const float *a_inv, void *grad_vol, void *workspace, int batch, int channels,
+                     int size, int logS, int dtype, int border, cudaStream_t st);
+
 extern "C" long long hg_rotate_bwd_workspace_bytes(int batch, int size, int in_layout)
 {
-    if (in_layout != HG_NDHWC || batch <= 0 || size <= 0) return 0;
-    return (long long)hg_rotate_cl_ws_bytes(batch, size);
+    if (batch <= 0 || size <= 0) return 0;
+    if (in_layout == HG_NDHWC) return (long long)hg_rotate_cl_ws_bytes(batch, size);
+    // NCDHW: the gather adjoint (sizes 8, 16) needs per-sample cell + adjoint tables; 32^3 scatters in shared memory
+    return size <= 16 ? (long long)hg_rotate_il_ws_bytes(batch, size) : 0;
 }
 
 extern "C" int hg_rotate_fwd(const void *vol, const float *a_inv, void *out, float *coords_dbg, int32_t *idx_dbg,
@@ -247,6 +257,8 @@ extern "C" int hg_rotate_fwd(const void *vol, const float *a_inv, void *out, flo
         if (rc) return rc;
     }
     if (in_layout == HG_NCDHW && out_layout == HG_NCDHW) {
+        if (hg_rotate_il_supported(channels, size, dtype))
+            return hg_rotate_il_fwd(vol, a_inv, out, batch, channels, size, logS, dtype, border, st);
         const bool z = border == HG_BORDER_ZERO;
         if (dtype == HG_F32)
             return z ? fwd_ncdhw_by_size<float, true>(vol, a_inv, out, batch, channels, size, logS, st)
@@ -275,6 +287,9 @@ extern "C" int hg_rotate_bwd(const void *grad_out, const float *a_inv, void *gra
                "hg_rotate_bwd: unknown border mode %d", border);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (in_layout == HG_NCDHW && out_layout == HG_NCDHW) {
+        if (hg_rotate_il_supported(channels, size, dtype) && workspace &&
+            workspace_bytes >= (long long)hg_rotate_il_ws_bytes(batch, size))
+            return hg_rotate_il_bwd(grad_out, a_inv, grad_vol, workspace, batch, channels, size, logS, dtype, border, st);
         const bool z = border == HG_BORDER_ZERO;
         if (dtype == HG_F32)
             return z ? bwd_ncdhw_by_size<float, true>(grad_out, a_inv, grad_vol, batch, channels, size, logS, st)

@@ -103,8 +103,10 @@ __global__ void __launch_bounds__(256) rotate_cl_fwd_kernel(const __nv_bfloat16 
 __host__ __device__ inline size_t cells_ws_elems(int n) { return (size_t)(n + 8) + (size_t)n; }
 
 // One CTA per sample.  Counting sort of the in-range output points by the cell their floor() lands in.
+// include_outside: also list the out-of-range outputs, keyed by their CLAMPED floor corner (reference border mode).
 __global__ void __launch_bounds__(1024) rotate_cells_kernel(const float *__restrict__ a_inv, uint16_t *__restrict__ ws,
-                                                            int S, int logS)
+                                                            size_t sample_stride_elems, int S, int logS,
+                                                            int include_outside)
 {
     extern __shared__ uint32_t sm[];
     const int n = S * S * S;
@@ -121,8 +123,9 @@ __global__ void __launch_bounds__(1024) rotate_cells_kernel(const float *__restr
     for (int o = t; o < n; o += blockDim.x) {
         float x, y, z;
         lattice_coords(m, o, S, logS, x, y, z);
-        if (x >= 0.f && x < lim && y >= 0.f && y < lim && z >= 0.f && z < lim) {
-            const int q = (((__float2int_rd(z) << logS) + __float2int_rd(y)) << logS) + __float2int_rd(x);
+        if (include_outside || (x >= 0.f && x < lim && y >= 0.f && y < lim && z >= 0.f && z < lim)) {
+            const int q = (((clampi(__float2int_rd(z), S - 1) << logS) + clampi(__float2int_rd(y), S - 1)) << logS) +
+                          clampi(__float2int_rd(x), S - 1);
             atomicAdd(&count[q], 1u);
         }
     }
@@ -161,8 +164,9 @@ __global__ void __launch_bounds__(1024) rotate_cells_kernel(const float *__restr
     for (int o = t; o < n; o += blockDim.x) {
         float x, y, z;
         lattice_coords(m, o, S, logS, x, y, z);
-        if (x >= 0.f && x < lim && y >= 0.f && y < lim && z >= 0.f && z < lim) {
-            const int q = (((__float2int_rd(z) << logS) + __float2int_rd(y)) << logS) + __float2int_rd(x);
+        if (include_outside || (x >= 0.f && x < lim && y >= 0.f && y < lim && z >= 0.f && z < lim)) {
+            const int q = (((clampi(__float2int_rd(z), S - 1) << logS) + clampi(__float2int_rd(y), S - 1)) << logS) +
+                          clampi(__float2int_rd(x), S - 1);
             items[atomicAdd(&count[q], 1u)] = (uint32_t)o;
         }
     }
@@ -181,7 +185,7 @@ __global__ void __launch_bounds__(1024) rotate_cells_kernel(const float *__restr
         }
     }
     __syncthreads();
-    uint16_t *wb = ws + (size_t)b * cells_ws_elems(n);
+    uint16_t *wb = ws + (size_t)b * sample_stride_elems;
     for (int i = t; i <= n; i += blockDim.x) wb[i] = (uint16_t)start[i];
     for (int i = t; i < n; i += blockDim.x) wb[n + 8 + i] = (uint16_t)items[i];
 }
@@ -270,6 +274,25 @@ size_t hg_rotate_cl_ws_bytes(int batch, int size)
     return (size_t)batch * cells_ws_elems(n) * sizeof(uint16_t);
 }
 
+// Per-sample cell tables (size 8 or 16): also used by the NCDHW gather adjoint of rotate_il.cu.
+// sample_stride_bytes: distance between two samples' tables (0 = densely packed).
+int hg_rotate_cells_launch(const float *a_inv, void *workspace, size_t sample_stride_bytes, int batch, int size, int logS,
+                           int include_outside, cudaStream_t st)
+{
+    const int n = size * size * size;
+    const int threads = n >= 4096 ? 1024 : 512;
+    const size_t smem = (size_t)(3 * n + 1) * sizeof(uint32_t);
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(rotate_cells_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        attr_done = true;
+    }
+    const size_t stride = sample_stride_bytes ? sample_stride_bytes / sizeof(uint16_t) : cells_ws_elems(n);
+    rotate_cells_kernel<<<batch, threads, smem, st>>>(a_inv, static_cast<uint16_t *>(workspace), stride, size, logS,
+                                                      include_outside);
+    return check_launch("rotate_cells");
+}
+
 int hg_rotate_cl_bwd_impl(const void *grad_out, const float *a_inv, void *grad_vol, void *workspace,
                           long long workspace_bytes, int batch, int channels, int size, int logS, int out_layout,
                           cudaStream_t st)
@@ -281,15 +304,7 @@ int hg_rotate_cl_bwd_impl(const void *grad_out, const float *a_inv, void *grad_v
                "hg_rotate_bwd: channels-last path needs a workspace of hg_rotate_bwd_workspace_bytes() bytes");
     const int n = size * size * size;
     uint16_t *ws = static_cast<uint16_t *>(workspace);
-    const int threads = n >= 4096 ? 1024 : 512;
-    const size_t smem = (size_t)(3 * n + 1) * sizeof(uint32_t);
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaFuncSetAttribute(rotate_cells_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-        attr_done = true;
-    }
-    rotate_cells_kernel<<<batch, threads, smem, st>>>(a_inv, ws, size, logS);
-    int rc = check_launch("rotate_cells");
+    int rc = hg_rotate_cells_launch(a_inv, workspace, 0, batch, size, logS, 0, st);
     if (rc) return rc;
     const int vpc = n >= 4096 ? 512 : n;
     dim3 grid((n + vpc - 1) / vpc, batch);

@@ -106,9 +106,11 @@ template <> struct IlUnit<__nv_bfloat16> {
 // lane -> voxel of the j-th 8x2x2 block: quarter warps (lanes 8q..8q+7) are 2x2x2 sub-blocks
 __device__ __forceinline__ void il_block_voxel(int j, int lane, int S, int logS, int &x, int &y, int &z)
 {
-    const int bxn = S >> 3, byn = S >> 1;
-    const int bx = j % bxn, t = j / bxn;
-    const int by = t % byn, bz = t / byn;
+    // S is a power of two >= 8: S/8 blocks along x, S/2 along y and z
+    const int lbx = logS - 3, lby = logS - 1;
+    const int bx = j & ((1 << lbx) - 1), t = j >> lbx;
+    const int by = t & ((1 << lby) - 1), bz = t >> lby;
+    (void)S;
     x = (bx << 3) + (lane & 1) + ((lane >> 3) << 1);
     y = (by << 1) + ((lane >> 1) & 1);
     z = (bz << 1) + ((lane >> 2) & 1);
@@ -163,44 +165,122 @@ template <> __device__ __forceinline__ void st_stream_elem<__nv_bfloat16>(__nv_b
 }
 
 // -------------------------------------------------------------------------------------------------
+// Persistent tile pipeline.  A "tile" is one (sample, 16-byte channel group): n units of shared memory.
+// One CTA per SM walks tiles t = blockIdx.x, + gridDim.x, ...; while it computes tile t out of one buffer
+// the loads of tile t' = t + gridDim.x are in flight into registers, and are written to the other buffer
+// afterwards -> one __syncthreads per tile, HBM latency hidden behind the gather.
+// -------------------------------------------------------------------------------------------------
+template <typename T, int LOGS, int NT> struct IlPrefetch;
+
+template <int LOGS, int NT> struct IlPrefetch<float, LOGS, NT> {
+    static constexpr int N = 1 << (3 * LOGS);
+    static constexpr int PF = (N + NT - 1) / NT;
+    uint4 r[PF];
+    __device__ __forceinline__ void load(const float *__restrict__ src)
+    {
+#pragma unroll
+        for (int i = 0; i < PF; ++i) {
+            const int v = threadIdx.x + i * NT;
+            if (N % NT == 0 || v < N) {
+                r[i].x = ld_stream_4(src + v);
+                r[i].y = ld_stream_4(src + N + v);
+                r[i].z = ld_stream_4(src + 2 * N + v);
+                r[i].w = ld_stream_4(src + 3 * N + v);
+            }
+        }
+    }
+    __device__ __forceinline__ void store(uint4 *__restrict__ buf) const
+    {
+#pragma unroll
+        for (int i = 0; i < PF; ++i) {
+            const int v = threadIdx.x + i * NT;
+            if (N % NT == 0 || v < N) buf[il_unit(v, LOGS)] = r[i];
+        }
+    }
+};
+
+template <int LOGS, int NT> struct IlPrefetch<__nv_bfloat16, LOGS, NT> {
+    static constexpr int N = 1 << (3 * LOGS);
+    static constexpr int NP = N / 2;                         // voxel pairs (v, v+1), v even
+    static constexpr int PF = (NP + NT - 1) / NT;
+    uint32_t r[PF][8];
+    __device__ __forceinline__ void load(const __nv_bfloat16 *__restrict__ src)
+    {
+#pragma unroll
+        for (int i = 0; i < PF; ++i) {
+            const int v = 2 * (threadIdx.x + i * NT);
+            if (NP % NT == 0 || v < N) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) r[i][c] = ld_stream_4(src + c * N + v);
+            }
+        }
+    }
+    __device__ __forceinline__ void store(uint4 *__restrict__ buf) const
+    {
+#pragma unroll
+        for (int i = 0; i < PF; ++i) {
+            const int v = 2 * (threadIdx.x + i * NT);
+            if (NP % NT == 0 || v < N) {
+                uint4 lo, hi;
+                lo.x = __byte_perm(r[i][0], r[i][1], 0x5410); hi.x = __byte_perm(r[i][0], r[i][1], 0x7632);
+                lo.y = __byte_perm(r[i][2], r[i][3], 0x5410); hi.y = __byte_perm(r[i][2], r[i][3], 0x7632);
+                lo.z = __byte_perm(r[i][4], r[i][5], 0x5410); hi.z = __byte_perm(r[i][4], r[i][5], 0x7632);
+                lo.w = __byte_perm(r[i][6], r[i][7], 0x5410); hi.w = __byte_perm(r[i][6], r[i][7], 0x7632);
+                buf[il_unit(v, LOGS)] = lo;
+                buf[il_unit(v + 1, LOGS)] = hi;
+            }
+        }
+    }
+};
+
+// -------------------------------------------------------------------------------------------------
 // forward
 // -------------------------------------------------------------------------------------------------
-template <typename T, int G, bool kZeroBorder>
-__global__ void __launch_bounds__(256 * G) rotate_fwd_il_kernel(const T *__restrict__ vol, const float *__restrict__ a_inv,
-                                                                T *__restrict__ out, int C, int S, int logS)
+template <typename T, int LOGS, int NT, bool kZeroBorder>
+__global__ void __launch_bounds__(NT) rotate_fwd_il_kernel(const T *__restrict__ vol, const float *__restrict__ a_inv,
+                                                           T *__restrict__ out, int groups, int ntiles)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint4 *tile = reinterpret_cast<uint4 *>(smem_raw);
-    __shared__ float m[12];
-    constexpr int CI = IlUnit<T>::CI, CT = G * CI;
+    constexpr int S = 1 << LOGS, N = S * S * S, CI = IlUnit<T>::CI;
+    uint4 *buf = reinterpret_cast<uint4 *>(smem_raw);       // [2][N]
+    __shared__ float msh[2][12];
 
-    const int n = S * S * S;
-    const int b = blockIdx.y, c0 = blockIdx.x * CT;
-    const T *src = vol + ((size_t)b * C + c0) * n;
-    T *dst = out + ((size_t)b * C + c0) * n;
-    if (threadIdx.x < 12) m[threadIdx.x] = a_inv[b * 16 + threadIdx.x];
-    il_stage<T, G>(src, tile, n, logS);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int t = blockIdx.x;
+    if (t >= ntiles) return;
+    IlPrefetch<T, LOGS, NT> pf;
+    float mreg = 0.f;
+    pf.load(vol + (size_t)t * CI * N);
+    if (threadIdx.x < 12) mreg = a_inv[(t / groups) * 16 + threadIdx.x];
+    pf.store(buf);
+    if (threadIdx.x < 12) msh[0][threadIdx.x] = mreg;
     __syncthreads();
-
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    for (int j = warp; j < (n >> 5); j += nwarps) {
-        int ox, oy, oz;
-        il_block_voxel(j, lane, S, logS, ox, oy, oz);
-        const int o = (((oz << logS) + oy) << logS) + ox;
-        float x, y, z;
-        il_coords(m, ox, oy, oz, x, y, z);
-        IlCorners c;
-        il_corners(x, y, z, S, logS, c);
-        if (kZeroBorder && !c.inside) {
-#pragma unroll
-            for (int ci = 0; ci < CT; ++ci) st_stream_elem<T>(dst + (size_t)ci * n + o, 0.f);
-            continue;
+    int cur = 0;
+    for (; t < ntiles; t += gridDim.x) {
+        const int tn = t + gridDim.x;
+        if (tn < ntiles) {
+            pf.load(vol + (size_t)tn * CI * N);
+            if (threadIdx.x < 12) mreg = a_inv[(tn / groups) * 16 + threadIdx.x];
         }
+        const uint4 *tile = buf + cur * N;
+        const float *m = msh[cur];
+        T *dst = out + (size_t)t * CI * N;
+        for (int j = warp; j < N / 32; j += NT / 32) {
+            int ox, oy, oz;
+            il_block_voxel(j, lane, S, LOGS, ox, oy, oz);
+            const int o = (((oz << LOGS) + oy) << LOGS) + ox;
+            float x, y, z;
+            il_coords(m, ox, oy, oz, x, y, z);
+            IlCorners c;
+            il_corners(x, y, z, S, LOGS, c);
+            if (kZeroBorder && !c.inside) {
 #pragma unroll
-        for (int g = 0; g < G; ++g) {
+                for (int ci = 0; ci < CI; ++ci) st_stream_elem<T>(dst + ci * N + o, 0.f);
+                continue;
+            }
             uint4 raw[8];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) raw[k] = tile[g * n + c.u[k]];
+            for (int k = 0; k < 8; ++k) raw[k] = tile[c.u[k]];
             float acc[CI], f[CI];
             IlUnit<T>::unpack(raw[0], f);
 #pragma unroll
@@ -215,118 +295,266 @@ __global__ void __launch_bounds__(256 * G) rotate_fwd_il_kernel(const T *__restr
                 }
             }
 #pragma unroll
-            for (int i = 0; i < CI; ++i) st_stream_elem<T>(dst + (size_t)(g * CI + i) * n + o, acc[i]);
+            for (int i = 0; i < CI; ++i) st_stream_elem<T>(dst + i * N + o, acc[i]);
         }
+        if (tn < ntiles) {
+            pf.store(buf + (cur ^ 1) * N);
+            if (threadIdx.x < 12) msh[cur ^ 1][threadIdx.x] = mreg;
+        }
+        __syncthreads();
+        cur ^= 1;
     }
 }
 
 // -------------------------------------------------------------------------------------------------
-// backward (gather-formulated adjoint).  ws: per-sample cell tables built by hg_rotate_cells_launch:
-// uint16 start[n + 1] (padded to n + 8), uint16 items[n].  Zero border: the table holds the in-range
-// outputs keyed by floor(); reference border: ALL outputs keyed by the clamped floor corner, and an
-// output whose clamped corners coincide contributes the sum of the coinciding weights.
+// backward: gather-formulated adjoint, driven by a per-sample ADJOINT TABLE in ELL-block form.
+//
+// Source voxels are grouped in the same 8x2x2 blocks as the forward's outputs (block j, lane l).  For every
+// block the table holds K_j rows of 32 packed entries, row k / lane l = the k-th contribution of voxel
+// (j, l):  entry = (w_q << 12) | u,  u = hashed unit index of the output voxel whose 2x2x2 footprint covers
+// the source voxel, w_q = its trilinear weight in 20-bit fixed point (|error| <= 2^-21; the weights are the
+// forward's, in [0, 1]); short rows are padded with zero-weight entries.  A warp reads one row with one
+// coalesced 128-byte load, so an entry costs ~14 instructions for 4 fp32 (8 bf16) channels and there is no
+// divergence.  The table depends on the views only: it is built once per call by two small kernels
+// (rotate_cells_kernel -> "cell -> outputs" counting sort with fixed order, rotate_ell_kernel -> rows) and
+// shared by all channel groups.  Summation order is fixed -> deterministic; no atomics on floating point.
+// Samples whose table would not fit the workspace (KCAP rows per block on average; only views that shrink
+// the lattice by more than ~1.3x per axis) fall back to walking the cell table directly.
+// Out-of-range outputs contribute exactly 0 in both border modes (include/hologan_b200.h): in the reference
+// their clamped corners coincide and the paired weights cancel to ~1e-7 residues.
 // -------------------------------------------------------------------------------------------------
-template <typename T, int G, bool kZeroBorder>
-__global__ void __launch_bounds__(256 * G) rotate_bwd_il_kernel(const T *__restrict__ grad_out, const float *__restrict__ a_inv,
-                                                                const uint16_t *__restrict__ ws, T *__restrict__ grad_vol,
-                                                                int C, int S, int logS)
+constexpr int kEllCap = 20;                                 // average rows per block the workspace holds
+constexpr float kEllScale = 1048575.0f;                     // 2^20 - 1
+
+struct IlWsLayout {
+    size_t cells_off, hdr_off, ell_off, per_sample;         // bytes
+};
+__host__ __device__ inline IlWsLayout il_ws_layout(int n)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint4 *tile = reinterpret_cast<uint4 *>(smem_raw);
+    IlWsLayout l;
+    const size_t nblk = (size_t)n / 32;
+    l.cells_off = 0;                                                        // uint16 start[n + 8], items[n]
+    l.hdr_off = ((size_t)(2 * n + 8) * 2 + 15) / 16 * 16;                   // uint32 blockoff[nblk + 1], flag
+    l.ell_off = l.hdr_off + ((nblk + 2) * 4 + 15) / 16 * 16;                // uint32 rows[nblk * kEllCap][32]
+    l.per_sample = l.ell_off + nblk * kEllCap * 32 * 4;
+    return l;
+}
+
+// One CTA per sample, one warp per block (round robin).  cells: the table of rotate_cells_kernel.
+template <int LOGS>
+__global__ void __launch_bounds__(1024) rotate_ell_kernel(const float *__restrict__ a_inv, unsigned char *__restrict__ ws,
+                                                          size_t ws_stride, size_t cells_stride_elems)
+{
+    constexpr int S = 1 << LOGS, N = S * S * S, NBLK = N / 32;
     __shared__ float m[12];
-    constexpr int CI = IlUnit<T>::CI, CT = G * CI;
-
-    const int n = S * S * S;
-    const int b = blockIdx.y, c0 = blockIdx.x * CT;
-    const T *src = grad_out + ((size_t)b * C + c0) * n;
-    T *dst = grad_vol + ((size_t)b * C + c0) * n;
-    const uint16_t *start = ws + (size_t)b * ((size_t)(n + 8) + n);
-    const uint16_t *items = start + n + 8;
+    __shared__ uint32_t kblk[NBLK + 1];
+    const IlWsLayout lay = il_ws_layout(N);
+    const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    unsigned char *wsb = ws + (size_t)b * ws_stride;
+    const uint16_t *start = reinterpret_cast<const uint16_t *>(wsb + lay.cells_off);
+    const uint16_t *items = start + N + 8;
+    (void)cells_stride_elems;
+    uint32_t *hdr = reinterpret_cast<uint32_t *>(wsb + lay.hdr_off);
+    uint32_t *rows = reinterpret_cast<uint32_t *>(wsb + lay.ell_off);
     if (threadIdx.x < 12) m[threadIdx.x] = a_inv[b * 16 + threadIdx.x];
-    il_stage<T, G>(src, tile, n, logS);
-    __syncthreads();
-
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    const int qmax = kZeroBorder ? S - 2 : S - 1;
-    for (int j = warp; j < (n >> 5); j += nwarps) {
+    // pass 1: entries per voxel -> rows per block
+    for (int j = warp; j < NBLK; j += nwarps) {
         int sx, sy, sz;
-        il_block_voxel(j, lane, S, logS, sx, sy, sz);
-        const int s = (((sz << logS) + sy) << logS) + sx;
-        float acc[CT];
+        il_block_voxel(j, lane, S, LOGS, sx, sy, sz);
+        int cnt = 0;
 #pragma unroll
-        for (int i = 0; i < CT; ++i) acc[i] = 0.f;
+        for (int d = 0; d < 8; ++d) {
+            const int qx = sx - (d & 1), qy = sy - ((d >> 1) & 1), qz = sz - (d >> 2);
+            if (qx < 0 || qy < 0 || qz < 0 || qx > S - 2 || qy > S - 2 || qz > S - 2) continue;
+            const int q = (((qz << LOGS) + qy) << LOGS) + qx;
+            cnt += (int)start[q + 1] - (int)start[q];
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) cnt = max(cnt, __shfl_xor_sync(0xffffffffu, cnt, o));
+        if (lane == 0) kblk[j] = (uint32_t)cnt;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {                                 // NBLK <= 128: a serial scan is a few hundred cycles
+        uint32_t run = 0;
+        for (int j = 0; j < NBLK; ++j) {
+            const uint32_t k = kblk[j];
+            kblk[j] = run;
+            run += k;
+        }
+        kblk[NBLK] = run;
+    }
+    __syncthreads();
+    const bool fits = kblk[NBLK] <= (uint32_t)(NBLK * kEllCap);
+    for (int j = threadIdx.x; j <= NBLK; j += blockDim.x) hdr[j] = kblk[j];
+    if (threadIdx.x == 0) hdr[NBLK + 1] = fits ? 1u : 0u;
+    if (!fits) return;
+    // pass 2: the rows
+    for (int j = warp; j < NBLK; j += nwarps) {
+        int sx, sy, sz;
+        il_block_voxel(j, lane, S, LOGS, sx, sy, sz);
+        const uint32_t r0 = kblk[j], r1 = kblk[j + 1];
+        uint32_t r = r0;
 #pragma unroll 1
         for (int d = 0; d < 8; ++d) {
             const int dx = d & 1, dy = (d >> 1) & 1, dz = d >> 2;
             const int qx = sx - dx, qy = sy - dy, qz = sz - dz;
-            if (qx < 0 || qy < 0 || qz < 0 || qx > qmax || qy > qmax || qz > qmax) continue;
-            const int q = (((qz << logS) + qy) << logS) + qx;
-            const int lo = __ldg(start + q), hi = __ldg(start + q + 1);
+            if (qx < 0 || qy < 0 || qz < 0 || qx > S - 2 || qy > S - 2 || qz > S - 2) continue;
+            const int q = (((qz << LOGS) + qy) << LOGS) + qx;
+            const int lo = start[q], hi = start[q + 1];
             for (int i = lo; i < hi; ++i) {
-                const int o = __ldg(items + i);
-                const int ox = o & (S - 1), oy = (o >> logS) & (S - 1), oz = o >> (2 * logS);
+                const int o = items[i];
+                const int ox = o & (S - 1), oy = (o >> LOGS) & (S - 1), oz = o >> (2 * LOGS);
                 float x, y, z;
                 il_coords(m, ox, oy, oz, x, y, z);                  // same bits as the forward
-                float w;
-                if (kZeroBorder) {
-                    // floor == q by construction
-                    const float wx = dx ? __fsub_rn(x, (float)qx) : __fsub_rn((float)(qx + 1), x);
-                    const float wy = dy ? __fsub_rn(y, (float)qy) : __fsub_rn((float)(qy + 1), y);
-                    const float wz = dz ? __fsub_rn(z, (float)qz) : __fsub_rn((float)(qz + 1), z);
-                    w = __fmul_rn(__fmul_rn(wx, wy), wz);
-                } else {
-                    Corners c;
-                    make_corners<false>(x, y, z, S, logS, 0, c);
-                    w = 0.f;
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) w += (c.idx[k] == s) ? c.w[k] : 0.f;
-                }
-                const int uo = il_unit(o, logS);
-#pragma unroll
-                for (int g = 0; g < G; ++g) {
-                    float f[CI];
-                    IlUnit<T>::unpack(tile[g * n + uo], f);
-#pragma unroll
-                    for (int c = 0; c < CI; ++c) acc[g * CI + c] = fmaf(w, f[c], acc[g * CI + c]);
-                }
+                // forward weights of this output point (floor == q by construction)
+                const float wx = dx ? __fsub_rn(x, (float)qx) : __fsub_rn((float)(qx + 1), x);
+                const float wy = dy ? __fsub_rn(y, (float)qy) : __fsub_rn((float)(qy + 1), y);
+                const float wz = dz ? __fsub_rn(z, (float)qz) : __fsub_rn((float)(qz + 1), z);
+                const float w = __fmul_rn(__fmul_rn(wx, wy), wz);
+                const uint32_t wq = (uint32_t)__float2int_rn(fminf(fmaxf(w, 0.f), 1.f) * kEllScale);
+                rows[(size_t)r * 32 + lane] = (wq << 12) | (uint32_t)il_unit(o, LOGS);
+                ++r;
             }
         }
+        for (; r < r1; ++r) rows[(size_t)r * 32 + lane] = 0u;
+    }
+}
+
+template <typename T, int LOGS, int NT>
+__global__ void __launch_bounds__(NT) rotate_bwd_il_kernel(const T *__restrict__ grad_out, const float *__restrict__ a_inv,
+                                                           const unsigned char *__restrict__ ws, size_t ws_stride,
+                                                           T *__restrict__ grad_vol, int groups, int ntiles)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int S = 1 << LOGS, N = S * S * S, CI = IlUnit<T>::CI, NBLK = N / 32;
+    uint4 *buf = reinterpret_cast<uint4 *>(smem_raw);       // [2][N]
+    __shared__ float msh[2][12];
+    const IlWsLayout lay = il_ws_layout(N);
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int t = blockIdx.x;
+    if (t >= ntiles) return;
+    IlPrefetch<T, LOGS, NT> pf;
+    float mreg = 0.f;
+    pf.load(grad_out + (size_t)t * CI * N);
+    if (threadIdx.x < 12) mreg = a_inv[(t / groups) * 16 + threadIdx.x];
+    pf.store(buf);
+    if (threadIdx.x < 12) msh[0][threadIdx.x] = mreg;
+    __syncthreads();
+    int cur = 0;
+    for (; t < ntiles; t += gridDim.x) {
+        const int tn = t + gridDim.x;
+        if (tn < ntiles) {
+            pf.load(grad_out + (size_t)tn * CI * N);
+            if (threadIdx.x < 12) mreg = a_inv[(tn / groups) * 16 + threadIdx.x];
+        }
+        const uint4 *tile = buf + cur * N;
+        const float *m = msh[cur];
+        T *dst = grad_vol + (size_t)t * CI * N;
+        const unsigned char *wsb = ws + (size_t)(t / groups) * ws_stride;
+        const uint32_t *hdr = reinterpret_cast<const uint32_t *>(wsb + lay.hdr_off);
+        const uint32_t *rows = reinterpret_cast<const uint32_t *>(wsb + lay.ell_off);
+        const bool ell = __ldg(hdr + NBLK + 1) != 0u;
+        for (int j = warp; j < NBLK; j += NT / 32) {
+            int sx, sy, sz;
+            il_block_voxel(j, lane, S, LOGS, sx, sy, sz);
+            const int s = (((sz << LOGS) + sy) << LOGS) + sx;
+            float acc[CI];
 #pragma unroll
-        for (int i = 0; i < CT; ++i) st_stream_elem<T>(dst + (size_t)i * n + s, acc[i]);
+            for (int i = 0; i < CI; ++i) acc[i] = 0.f;
+            if (ell) {
+                const uint32_t r0 = __ldg(hdr + j), r1 = __ldg(hdr + j + 1);
+                const uint32_t *rp = rows + (size_t)r0 * 32 + lane;
+#pragma unroll 4
+                for (uint32_t r = r0; r < r1; ++r, rp += 32) {
+                    const uint32_t e = __ldg(rp);
+                    const float w = (float)(e >> 12) * (1.0f / kEllScale);
+                    float f[CI];
+                    IlUnit<T>::unpack(tile[e & 0xfffu], f);
+#pragma unroll
+                    for (int c = 0; c < CI; ++c) acc[c] = fmaf(w, f[c], acc[c]);
+                }
+            } else {
+                const uint16_t *start = reinterpret_cast<const uint16_t *>(wsb + lay.cells_off);
+                const uint16_t *items = start + N + 8;
+#pragma unroll 1
+                for (int d = 0; d < 8; ++d) {
+                    const int dx = d & 1, dy = (d >> 1) & 1, dz = d >> 2;
+                    const int qx = sx - dx, qy = sy - dy, qz = sz - dz;
+                    if (qx < 0 || qy < 0 || qz < 0 || qx > S - 2 || qy > S - 2 || qz > S - 2) continue;
+                    const int q = (((qz << LOGS) + qy) << LOGS) + qx;
+                    const int lo = __ldg(start + q), hi = __ldg(start + q + 1);
+                    for (int i = lo; i < hi; ++i) {
+                        const int o = __ldg(items + i);
+                        const int ox = o & (S - 1), oy = (o >> LOGS) & (S - 1), oz = o >> (2 * LOGS);
+                        float x, y, z;
+                        il_coords(m, ox, oy, oz, x, y, z);
+                        const float wx = dx ? __fsub_rn(x, (float)qx) : __fsub_rn((float)(qx + 1), x);
+                        const float wy = dy ? __fsub_rn(y, (float)qy) : __fsub_rn((float)(qy + 1), y);
+                        const float wz = dz ? __fsub_rn(z, (float)qz) : __fsub_rn((float)(qz + 1), z);
+                        const float w = __fmul_rn(__fmul_rn(wx, wy), wz);
+                        float f[CI];
+                        IlUnit<T>::unpack(tile[il_unit(o, LOGS)], f);
+#pragma unroll
+                        for (int c = 0; c < CI; ++c) acc[c] = fmaf(w, f[c], acc[c]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < CI; ++i) st_stream_elem<T>(dst + i * N + s, acc[i]);
+        }
+        if (tn < ntiles) {
+            pf.store(buf + (cur ^ 1) * N);
+            if (threadIdx.x < 12) msh[cur ^ 1][threadIdx.x] = mreg;
+        }
+        __syncthreads();
+        cur ^= 1;
     }
 }
 
 // -------------------------------------------------------------------------------------------------
 // host side
 // -------------------------------------------------------------------------------------------------
-template <typename T, int G, bool Z>
-static int launch_fwd_il(const void *vol, const float *a, void *out, int B, int C, int S, int logS, cudaStream_t st)
+static int g_il_threads = 512;      // tuning knob (hg_rotate_il_set_threads): 512 or 1024 threads per CTA
+
+template <typename K>
+static void il_set_smem(K kernel, size_t smem, bool &done)
 {
-    const size_t smem = (size_t)G * S * S * S * 16;
-    auto k = rotate_fwd_il_kernel<T, G, Z>;
-    static bool attr_done = false;      // per template instantiation; not a stream operation (graph-capture safe)
-    if (!attr_done && smem > 48 * 1024) {
-        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr_done = true;
-    }
-    dim3 grid(C / (G * IlUnit<T>::CI), B);
-    k<<<grid, 256 * G, smem, st>>>(static_cast<const T *>(vol), a, static_cast<T *>(out), C, S, logS);
+    if (!done && smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    done = true;        // not a stream operation (graph-capture safe)
+}
+
+static int il_grid(int ntiles, int size, int threads)
+{
+    const int per_sm = size == 16 ? 1 : (threads == 512 ? 4 : 2);       // 128 KB tiles: one CTA per SM
+    return min(ntiles, sm_count() * per_sm);
+}
+
+template <typename T, int LOGS, int NT, bool Z>
+static int launch_fwd_il(const void *vol, const float *a, void *out, int B, int C, cudaStream_t st)
+{
+    constexpr int N = 1 << (3 * LOGS);
+    const size_t smem = (size_t)2 * N * 16;
+    auto k = rotate_fwd_il_kernel<T, LOGS, NT, Z>;
+    static bool attr_done = false;
+    il_set_smem(k, smem, attr_done);
+    const int groups = C / IlUnit<T>::CI, ntiles = B * groups;
+    k<<<il_grid(ntiles, 1 << LOGS, NT), NT, smem, st>>>(static_cast<const T *>(vol), a, static_cast<T *>(out), groups, ntiles);
     return check_launch("rotate_fwd_il");
 }
 
-template <typename T, int G, bool Z>
-static int launch_bwd_il(const void *g, const float *a, const uint16_t *ws, void *gv, int B, int C, int S, int logS,
+template <typename T, int LOGS, int NT>
+static int launch_bwd_il(const void *g, const float *a, const void *ws, size_t ws_stride, void *gv, int B, int C,
                          cudaStream_t st)
 {
-    const size_t smem = (size_t)G * S * S * S * 16;
-    auto k = rotate_bwd_il_kernel<T, G, Z>;
+    constexpr int N = 1 << (3 * LOGS);
+    const size_t smem = (size_t)2 * N * 16;
+    auto k = rotate_bwd_il_kernel<T, LOGS, NT>;
     static bool attr_done = false;
-    if (!attr_done && smem > 48 * 1024) {
-        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr_done = true;
-    }
-    dim3 grid(C / (G * IlUnit<T>::CI), B);
-    k<<<grid, 256 * G, smem, st>>>(static_cast<const T *>(g), a, ws, static_cast<T *>(gv), C, S, logS);
+    il_set_smem(k, smem, attr_done);
+    const int groups = C / IlUnit<T>::CI, ntiles = B * groups;
+    k<<<il_grid(ntiles, 1 << LOGS, NT), NT, smem, st>>>(static_cast<const T *>(g), a, static_cast<const unsigned char *>(ws),
+                                                        ws_stride, static_cast<T *>(gv), groups, ntiles);
     return check_launch("rotate_bwd_il");
 }
 
@@ -335,8 +563,8 @@ static int launch_bwd_il(const void *g, const float *a, const uint16_t *ws, void
 using namespace hg;
 
 // rotate_cl.cu
-int hg_rotate_cells_launch(const float *a_inv, void *workspace, int batch, int size, int logS, int include_outside,
-                           cudaStream_t st);
+int hg_rotate_cells_launch(const float *a_inv, void *workspace, size_t sample_stride_bytes, int batch, int size, int logS,
+                           int include_outside, cudaStream_t st);
 
 // Interleaved-tile kernels cover S in {8, 16} and channel counts that are a multiple of one 16-byte unit
 // (4 fp32 / 8 bf16 channels); everything else stays on rotate.cu's per-channel tiles.
@@ -346,40 +574,47 @@ bool hg_rotate_il_supported(int channels, int size, int dtype)
     return (size == 8 || size == 16) && channels % ci == 0;
 }
 
-static int g_il_groups = 1;     // channel groups per CTA (tuning knob, see hg_rotate_il_set_groups)
-extern "C" void hg_rotate_il_set_groups(int g) { g_il_groups = (g == 2) ? 2 : 1; }
+size_t hg_rotate_il_ws_bytes(int batch, int size) { return (size_t)batch * il_ws_layout(size * size * size).per_sample; }
+
+extern "C" void hg_rotate_il_set_threads(int t) { g_il_threads = (t == 1024) ? 1024 : 512; }
 
 int hg_rotate_il_fwd(const void *vol, const float *a_inv, void *out, int batch, int channels, int size, int logS, int dtype,
                      int border, cudaStream_t st)
 {
+    (void)size;
     const bool z = border == HG_BORDER_ZERO;
-    const int ci = dtype == HG_F32 ? 4 : 8;
-    const bool two = g_il_groups == 2 && size == 16 && channels % (2 * ci) == 0;
-#define HG_IL_FWD(T, G, Z) launch_fwd_il<T, G, Z>(vol, a_inv, out, batch, channels, size, logS, st)
+    const bool big = g_il_threads == 1024;
+#define HG_IL_FWD(T, L, NT) \
+    (z ? launch_fwd_il<T, L, NT, true>(vol, a_inv, out, batch, channels, st) : launch_fwd_il<T, L, NT, false>(vol, a_inv, out, batch, channels, st))
     if (dtype == HG_F32) {
-        if (two) return z ? HG_IL_FWD(float, 2, true) : HG_IL_FWD(float, 2, false);
-        return z ? HG_IL_FWD(float, 1, true) : HG_IL_FWD(float, 1, false);
+        if (logS == 4) return big ? HG_IL_FWD(float, 4, 1024) : HG_IL_FWD(float, 4, 512);
+        return HG_IL_FWD(float, 3, 512);
     }
-    if (two) return z ? HG_IL_FWD(__nv_bfloat16, 2, true) : HG_IL_FWD(__nv_bfloat16, 2, false);
-    return z ? HG_IL_FWD(__nv_bfloat16, 1, true) : HG_IL_FWD(__nv_bfloat16, 1, false);
+    if (logS == 4) return big ? HG_IL_FWD(__nv_bfloat16, 4, 1024) : HG_IL_FWD(__nv_bfloat16, 4, 512);
+    return HG_IL_FWD(__nv_bfloat16, 3, 512);
 #undef HG_IL_FWD
 }
 
 int hg_rotate_il_bwd(const void *grad_out, const float *a_inv, void *grad_vol, void *workspace, int batch, int channels,
                      int size, int logS, int dtype, int border, cudaStream_t st)
 {
-    const bool z = border == HG_BORDER_ZERO;
-    int rc = hg_rotate_cells_launch(a_inv, workspace, batch, size, logS, z ? 0 : 1, st);
+    (void)border;
+    const int n = size * size * size;
+    const IlWsLayout lay = il_ws_layout(n);
+    unsigned char *ws = static_cast<unsigned char *>(workspace);
+    int rc = hg_rotate_cells_launch(a_inv, ws + lay.cells_off, lay.per_sample, batch, size, logS, 0, st);
     if (rc) return rc;
-    const uint16_t *ws = static_cast<const uint16_t *>(workspace);
-    const int ci = dtype == HG_F32 ? 4 : 8;
-    const bool two = g_il_groups == 2 && size == 16 && channels % (2 * ci) == 0;
-#define HG_IL_BWD(T, G, Z) launch_bwd_il<T, G, Z>(grad_out, a_inv, ws, grad_vol, batch, channels, size, logS, st)
+    if (logS == 4) rotate_ell_kernel<4><<<batch, 1024, 0, st>>>(a_inv, ws, lay.per_sample, 0);
+    else rotate_ell_kernel<3><<<batch, 512, 0, st>>>(a_inv, ws, lay.per_sample, 0);
+    rc = check_launch("rotate_ell");
+    if (rc) return rc;
+    const bool big = g_il_threads == 1024;
+#define HG_IL_BWD(T, L, NT) launch_bwd_il<T, L, NT>(grad_out, a_inv, ws, lay.per_sample, grad_vol, batch, channels, st)
     if (dtype == HG_F32) {
-        if (two) return z ? HG_IL_BWD(float, 2, true) : HG_IL_BWD(float, 2, false);
-        return z ? HG_IL_BWD(float, 1, true) : HG_IL_BWD(float, 1, false);
+        if (logS == 4) return big ? HG_IL_BWD(float, 4, 1024) : HG_IL_BWD(float, 4, 512);
+        return HG_IL_BWD(float, 3, 512);
     }
-    if (two) return z ? HG_IL_BWD(__nv_bfloat16, 2, true) : HG_IL_BWD(__nv_bfloat16, 2, false);
-    return z ? HG_IL_BWD(__nv_bfloat16, 1, true) : HG_IL_BWD(__nv_bfloat16, 1, false);
+    if (logS == 4) return big ? HG_IL_BWD(__nv_bfloat16, 4, 1024) : HG_IL_BWD(__nv_bfloat16, 4, 512);
+    return HG_IL_BWD(__nv_bfloat16, 3, 512);
 #undef HG_IL_BWD
 }

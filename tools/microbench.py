@@ -59,9 +59,9 @@ def views(b, seed=0):
     return v
 
 
-def rotate():
+def rotate(shapes=None):
     print(f"# rotate-resample, HBM peak {PEAK} GB/s; algorithmic bytes = 2*B*C*S^3*sizeof")
-    for (b, c, s) in [(64, 64, 16), (64, 128, 16), (64, 256, 16), (64, 64, 32), (64, 128, 32)]:
+    for (b, c, s) in shapes or [(64, 64, 16), (64, 128, 16), (64, 256, 16), (64, 64, 32), (64, 128, 32)]:
         for dt in (torch.float32, torch.bfloat16):
             a = ops.view_to_affine(views(b), s, s).to(DEV)
             nbytes = 2 * b * c * s ** 3 * (4 if dt == torch.float32 else 2)
@@ -219,6 +219,13 @@ if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     if what in ("rotate", "all"):
         rotate()
+    if what == "rotate16":                  # tuning: interleaved-tile kernels with 1 and 2 channel groups per CTA
+        from lightning_gan_zoo_b200 import _lib
+        for g in (512, 1024):
+            _lib.load().hg_rotate_il_set_threads(g)
+            print(f"## threads per CTA = {g}")
+            rotate([(64, 64, 16), (64, 256, 16), (64, 64, 8)])
+        _lib.load().hg_rotate_il_set_threads(512)
     if what in ("adain", "all"):
         adain()
     if what in ("conv", "all"):
