@@ -315,8 +315,8 @@ __global__ void __launch_bounds__(NT) rotate_fwd_il_kernel(const T *__restrict__
 // the source voxel, w_q = its trilinear weight in 20-bit fixed point (|error| <= 2^-21; the weights are the
 // forward's, in [0, 1]); short rows are padded with zero-weight entries.  A warp reads one row with one
 // coalesced 128-byte load, so an entry costs ~14 instructions for 4 fp32 (8 bf16) channels and there is no
-// divergence.  The table depends on the views only: it is built once per call by two small kernels
-// (rotate_cells_kernel -> "cell -> outputs" counting sort with fixed order, rotate_ell_kernel -> rows) and
+// divergence.  The table depends on the views only: it is built once per call by one small kernel
+// (rotate_adjoint_table_kernel: "cell -> outputs" counting sort with fixed order, then the rows) and
 // shared by all channel groups.  Summation order is fixed -> deterministic; no atomics on floating point.
 // Samples whose table would not fit the workspace (KCAP rows per block on average; only views that shrink
 // the lattice by more than ~1.3x per axis) fall back to walking the cell table directly.
@@ -340,83 +340,188 @@ __host__ __device__ inline IlWsLayout il_ws_layout(int n)
     return l;
 }
 
-// One CTA per sample, one warp per block (round robin).  cells: the table of rotate_cells_kernel.
+// block / lane of source voxel (x, y, z): inverse of il_block_voxel
+__device__ __forceinline__ void il_voxel_block(int x, int y, int z, int logS, int &j, int &lane)
+{
+    j = ((((z >> 1) << (logS - 1)) + (y >> 1)) << (logS - 3)) + (x >> 3);
+    lane = (x & 1) | ((y & 1) << 1) | ((z & 1) << 2) | (((x >> 1) & 3) << 3);
+}
+
+// One CTA per sample builds both tables in shared memory:
+//   1. counting sort "cell -> in-range outputs whose floor() lands in it" (fixed order inside a cell);
+//   2. per source voxel s the running offsets P(s, d) = sum over d' < d of |cell(s - d')|  (d = 0..7 numbers the
+//      corner (dx, dy, dz) that s is of cell s - d), hence the voxel's entry count and the block's row count K_j;
+//   3. exclusive scan of K_j over the blocks;
+//   4. OUTPUT-centric fill (no divergence): output o at position i of cell q writes its 8 weights to
+//      row  blockoff[j(s)] + P(s, d) + i,  lane l(s),  for s = q + d;  short rows are zero-padded.
+// The cell table is also written out: samples whose rows overflow the workspace use it directly.
 template <int LOGS>
-__global__ void __launch_bounds__(1024) rotate_ell_kernel(const float *__restrict__ a_inv, unsigned char *__restrict__ ws,
-                                                          size_t ws_stride, size_t cells_stride_elems)
+__global__ void __launch_bounds__(1024) rotate_adjoint_table_kernel(const float *__restrict__ a_inv, unsigned char *__restrict__ ws,
+                                                                     size_t ws_stride)
 {
     constexpr int S = 1 << LOGS, N = S * S * S, NBLK = N / 32;
+    extern __shared__ uint32_t sm[];
+    uint32_t *count = sm;                    // [N]  -> later the running cursor
+    uint32_t *start = sm + N;                // [N + 1]
+    uint32_t *items = sm + 2 * N + 1;        // [N]
+    unsigned char *p8 = reinterpret_cast<unsigned char *>(sm + 3 * N + 2);   // [N][8], 8-byte aligned
     __shared__ float m[12];
+    __shared__ uint32_t warp_tot[32];
     __shared__ uint32_t kblk[NBLK + 1];
     const IlWsLayout lay = il_ws_layout(N);
-    const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5, nwarps = blockDim.x >> 5;
     unsigned char *wsb = ws + (size_t)b * ws_stride;
-    const uint16_t *start = reinterpret_cast<const uint16_t *>(wsb + lay.cells_off);
-    const uint16_t *items = start + N + 8;
-    (void)cells_stride_elems;
+    uint16_t *g_start = reinterpret_cast<uint16_t *>(wsb + lay.cells_off);
+    uint16_t *g_items = g_start + N + 8;
     uint32_t *hdr = reinterpret_cast<uint32_t *>(wsb + lay.hdr_off);
     uint32_t *rows = reinterpret_cast<uint32_t *>(wsb + lay.ell_off);
-    if (threadIdx.x < 12) m[threadIdx.x] = a_inv[b * 16 + threadIdx.x];
-    // pass 1: entries per voxel -> rows per block
+
+    if (t < 12) m[t] = a_inv[b * 16 + t];
+    for (int i = t; i < N; i += blockDim.x) count[i] = 0;
+    __syncthreads();
+    // ---- 1. counting sort --------------------------------------------------------------------------
+    const float lim = (float)(S - 1);
+    for (int o = t; o < N; o += blockDim.x) {
+        float x, y, z;
+        il_coords(m, o & (S - 1), (o >> LOGS) & (S - 1), o >> (2 * LOGS), x, y, z);
+        if (x >= 0.f && x < lim && y >= 0.f && y < lim && z >= 0.f && z < lim) {
+            const int q = (((__float2int_rd(z) << LOGS) + __float2int_rd(y)) << LOGS) + __float2int_rd(x);
+            atomicAdd(&count[q], 1u);
+        }
+    }
+    __syncthreads();
+    const int per = N / blockDim.x;          // N = 512 / 4096 with 512 / 1024 threads -> 1 or 4
+    uint32_t local = 0;
+    for (int i = 0; i < per; ++i) local += count[t * per + i];
+    uint32_t incl = local;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    if (t < 32) {
+        uint32_t w = t < nwarps ? warp_tot[t] : 0, wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, wi, o);
+            if (t >= o) wi += v;
+        }
+        warp_tot[t] = wi - w;
+    }
+    __syncthreads();
+    uint32_t run = warp_tot[warp] + incl - local;
+    for (int i = 0; i < per; ++i) {
+        const uint32_t c = count[t * per + i];
+        start[t * per + i] = run;
+        count[t * per + i] = run;            // cursor
+        run += c;
+    }
+    if (t == (int)blockDim.x - 1) start[N] = run;
+    __syncthreads();
+    for (int o = t; o < N; o += blockDim.x) {
+        float x, y, z;
+        il_coords(m, o & (S - 1), (o >> LOGS) & (S - 1), o >> (2 * LOGS), x, y, z);
+        if (x >= 0.f && x < lim && y >= 0.f && y < lim && z >= 0.f && z < lim) {
+            const int q = (((__float2int_rd(z) << LOGS) + __float2int_rd(y)) << LOGS) + __float2int_rd(x);
+            items[atomicAdd(&count[q], 1u)] = (uint32_t)o;
+        }
+    }
+    __syncthreads();
+    for (int q = t; q < N; q += blockDim.x) {            // fixed order inside every cell
+        const uint32_t lo = start[q], hi = start[q + 1];
+        for (uint32_t i = lo + 1; i < hi; ++i) {
+            const uint32_t v = items[i];
+            uint32_t j = i;
+            while (j > lo && items[j - 1] > v) {
+                items[j] = items[j - 1];
+                --j;
+            }
+            items[j] = v;
+        }
+    }
+    __syncthreads();
+    for (int i = t; i <= N; i += blockDim.x) g_start[i] = (uint16_t)start[i];
+    for (int i = t; i < N; i += blockDim.x) g_items[i] = (uint16_t)items[i];
+    // ---- 2. per-voxel offsets and per-block row counts ---------------------------------------------
     for (int j = warp; j < NBLK; j += nwarps) {
         int sx, sy, sz;
         il_block_voxel(j, lane, S, LOGS, sx, sy, sz);
-        int cnt = 0;
+        const int s = (((sz << LOGS) + sy) << LOGS) + sx;
+        uint32_t runv = 0;
+        uint32_t packed[2] = {0u, 0u};
 #pragma unroll
         for (int d = 0; d < 8; ++d) {
+            packed[d >> 2] |= min(runv, 255u) << (8 * (d & 3));
             const int qx = sx - (d & 1), qy = sy - ((d >> 1) & 1), qz = sz - (d >> 2);
-            if (qx < 0 || qy < 0 || qz < 0 || qx > S - 2 || qy > S - 2 || qz > S - 2) continue;
-            const int q = (((qz << LOGS) + qy) << LOGS) + qx;
-            cnt += (int)start[q + 1] - (int)start[q];
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) cnt = max(cnt, __shfl_xor_sync(0xffffffffu, cnt, o));
-        if (lane == 0) kblk[j] = (uint32_t)cnt;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {                                 // NBLK <= 128: a serial scan is a few hundred cycles
-        uint32_t run = 0;
-        for (int j = 0; j < NBLK; ++j) {
-            const uint32_t k = kblk[j];
-            kblk[j] = run;
-            run += k;
-        }
-        kblk[NBLK] = run;
-    }
-    __syncthreads();
-    const bool fits = kblk[NBLK] <= (uint32_t)(NBLK * kEllCap);
-    for (int j = threadIdx.x; j <= NBLK; j += blockDim.x) hdr[j] = kblk[j];
-    if (threadIdx.x == 0) hdr[NBLK + 1] = fits ? 1u : 0u;
-    if (!fits) return;
-    // pass 2: the rows
-    for (int j = warp; j < NBLK; j += nwarps) {
-        int sx, sy, sz;
-        il_block_voxel(j, lane, S, LOGS, sx, sy, sz);
-        const uint32_t r0 = kblk[j], r1 = kblk[j + 1];
-        uint32_t r = r0;
-#pragma unroll 1
-        for (int d = 0; d < 8; ++d) {
-            const int dx = d & 1, dy = (d >> 1) & 1, dz = d >> 2;
-            const int qx = sx - dx, qy = sy - dy, qz = sz - dz;
-            if (qx < 0 || qy < 0 || qz < 0 || qx > S - 2 || qy > S - 2 || qz > S - 2) continue;
-            const int q = (((qz << LOGS) + qy) << LOGS) + qx;
-            const int lo = start[q], hi = start[q + 1];
-            for (int i = lo; i < hi; ++i) {
-                const int o = items[i];
-                const int ox = o & (S - 1), oy = (o >> LOGS) & (S - 1), oz = o >> (2 * LOGS);
-                float x, y, z;
-                il_coords(m, ox, oy, oz, x, y, z);                  // same bits as the forward
-                // forward weights of this output point (floor == q by construction)
-                const float wx = dx ? __fsub_rn(x, (float)qx) : __fsub_rn((float)(qx + 1), x);
-                const float wy = dy ? __fsub_rn(y, (float)qy) : __fsub_rn((float)(qy + 1), y);
-                const float wz = dz ? __fsub_rn(z, (float)qz) : __fsub_rn((float)(qz + 1), z);
-                const float w = __fmul_rn(__fmul_rn(wx, wy), wz);
-                const uint32_t wq = (uint32_t)__float2int_rn(fminf(fmaxf(w, 0.f), 1.f) * kEllScale);
-                rows[(size_t)r * 32 + lane] = (wq << 12) | (uint32_t)il_unit(o, LOGS);
-                ++r;
+            if (qx >= 0 && qy >= 0 && qz >= 0 && qx <= S - 2 && qy <= S - 2 && qz <= S - 2) {
+                const int q = (((qz << LOGS) + qy) << LOGS) + qx;
+                runv += start[q + 1] - start[q];
             }
         }
-        for (; r < r1; ++r) rows[(size_t)r * 32 + lane] = 0u;
+        reinterpret_cast<uint2 *>(p8)[s] = make_uint2(packed[0], packed[1]);
+        uint32_t kmax = runv;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
+        if (lane == 0) kblk[j] = kmax;
+        count[s] = runv;                      // reuse: entries of voxel s (for the padding)
+    }
+    __syncthreads();
+    // ---- 3. scan over the blocks --------------------------------------------------------------------
+    if (t < 32) {
+        uint32_t carry = 0;
+        for (int base = 0; base < NBLK; base += 32) {
+            const uint32_t k = base + t < NBLK ? kblk[base + t] : 0u;
+            uint32_t inc = k;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
+                if (t >= o) inc += v;
+            }
+            if (base + t < NBLK) kblk[base + t] = carry + inc - k;
+            carry += __shfl_sync(0xffffffffu, inc, 31);
+        }
+        if (t == 0) kblk[NBLK] = carry;
+    }
+    __syncthreads();
+    const uint32_t total_rows = kblk[NBLK];
+    const bool fits = total_rows <= (uint32_t)(NBLK * kEllCap);
+    for (int j = t; j <= NBLK; j += blockDim.x) hdr[j] = kblk[j];
+    if (t == 0) hdr[NBLK + 1] = fits ? 1u : 0u;
+    if (!fits) return;
+    // ---- 4. fill --------------------------------------------------------------------------------------
+    for (int j = warp; j < NBLK; j += nwarps) {          // padding first (disjoint from the real entries)
+        int sx, sy, sz;
+        il_block_voxel(j, lane, S, LOGS, sx, sy, sz);
+        const int s = (((sz << LOGS) + sy) << LOGS) + sx;
+        for (uint32_t r = kblk[j] + count[s]; r < kblk[j + 1]; ++r) rows[(size_t)r * 32 + lane] = 0u;
+    }
+    const int n_items = (int)start[N];
+    for (int idx = t; idx < n_items; idx += blockDim.x) {
+        const int o = (int)items[idx];
+        float x, y, z;
+        il_coords(m, o & (S - 1), (o >> LOGS) & (S - 1), o >> (2 * LOGS), x, y, z);     // same bits as the forward
+        const int qx = __float2int_rd(x), qy = __float2int_rd(y), qz = __float2int_rd(z);
+        const int q = (((qz << LOGS) + qy) << LOGS) + qx;
+        const uint32_t i = (uint32_t)idx - start[q];
+        // the forward's weights (make_corners): u* = corner0 side, l* = corner1 side
+        const float ux = __fsub_rn((float)(qx + 1), x), lx = __fsub_rn(x, (float)qx);
+        const float uy = __fsub_rn((float)(qy + 1), y), ly = __fsub_rn(y, (float)qy);
+        const float uz = __fsub_rn((float)(qz + 1), z), lz = __fsub_rn(z, (float)qz);
+        const uint32_t unit = (uint32_t)il_unit(o, LOGS);
+#pragma unroll
+        for (int d = 0; d < 8; ++d) {
+            const int dx = d & 1, dy = (d >> 1) & 1, dz = d >> 2;
+            const float w = __fmul_rn(__fmul_rn(dx ? lx : ux, dy ? ly : uy), dz ? lz : uz);
+            const int sx = qx + dx, sy = qy + dy, sz = qz + dz;
+            const int s = (((sz << LOGS) + sy) << LOGS) + sx;
+            int j, l;
+            il_voxel_block(sx, sy, sz, LOGS, j, l);
+            const uint32_t r = kblk[j] + p8[s * 8 + d] + i;
+            const uint32_t wq = (uint32_t)__float2int_rn(fminf(fmaxf(w, 0.f), 1.f) * kEllScale);
+            rows[(size_t)r * 32 + l] = (wq << 12) | unit;
+        }
     }
 }
 
@@ -426,9 +531,11 @@ __global__ void __launch_bounds__(NT) rotate_bwd_il_kernel(const T *__restrict__
                                                            T *__restrict__ grad_vol, int groups, int ntiles)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr int S = 1 << LOGS, N = S * S * S, CI = IlUnit<T>::CI, NBLK = N / 32;
+    constexpr int S = 1 << LOGS, N = S * S * S, CI = IlUnit<T>::CI, NBLK = N / 32, NW = NT / 32;
+    constexpr int KU = 16;                                  // rows of a block held in registers at once
     uint4 *buf = reinterpret_cast<uint4 *>(smem_raw);       // [2][N]
     __shared__ float msh[2][12];
+    __shared__ uint32_t hsh[2][NBLK + 2];                   // blockoff[NBLK + 1], fits flag
     const IlWsLayout lay = il_ws_layout(N);
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -436,10 +543,14 @@ __global__ void __launch_bounds__(NT) rotate_bwd_il_kernel(const T *__restrict__
     if (t >= ntiles) return;
     IlPrefetch<T, LOGS, NT> pf;
     float mreg = 0.f;
+    uint32_t hreg = 0u;
     pf.load(grad_out + (size_t)t * CI * N);
     if (threadIdx.x < 12) mreg = a_inv[(t / groups) * 16 + threadIdx.x];
+    if (threadIdx.x < NBLK + 2)
+        hreg = reinterpret_cast<const uint32_t *>(ws + (size_t)(t / groups) * ws_stride + lay.hdr_off)[threadIdx.x];
     pf.store(buf);
     if (threadIdx.x < 12) msh[0][threadIdx.x] = mreg;
+    if (threadIdx.x < NBLK + 2) hsh[0][threadIdx.x] = hreg;
     __syncthreads();
     int cur = 0;
     for (; t < ntiles; t += gridDim.x) {
@@ -447,36 +558,74 @@ __global__ void __launch_bounds__(NT) rotate_bwd_il_kernel(const T *__restrict__
         if (tn < ntiles) {
             pf.load(grad_out + (size_t)tn * CI * N);
             if (threadIdx.x < 12) mreg = a_inv[(tn / groups) * 16 + threadIdx.x];
+            if (threadIdx.x < NBLK + 2)
+                hreg = reinterpret_cast<const uint32_t *>(ws + (size_t)(tn / groups) * ws_stride + lay.hdr_off)[threadIdx.x];
         }
         const uint4 *tile = buf + cur * N;
         const float *m = msh[cur];
+        const uint32_t *hdr = hsh[cur];
         T *dst = grad_vol + (size_t)t * CI * N;
         const unsigned char *wsb = ws + (size_t)(t / groups) * ws_stride;
-        const uint32_t *hdr = reinterpret_cast<const uint32_t *>(wsb + lay.hdr_off);
         const uint32_t *rows = reinterpret_cast<const uint32_t *>(wsb + lay.ell_off);
-        const bool ell = __ldg(hdr + NBLK + 1) != 0u;
-        for (int j = warp; j < NBLK; j += NT / 32) {
-            int sx, sy, sz;
-            il_block_voxel(j, lane, S, LOGS, sx, sy, sz);
-            const int s = (((sz << LOGS) + sy) << LOGS) + sx;
-            float acc[CI];
-#pragma unroll
-            for (int i = 0; i < CI; ++i) acc[i] = 0.f;
-            if (ell) {
-                const uint32_t r0 = __ldg(hdr + j), r1 = __ldg(hdr + j + 1);
+        if (hdr[NBLK + 1] != 0u) {
+            // ---- adjoint-table path: the next block's rows are in flight while this block is summed ----
+            uint32_t e[KU];
+            {
+                const uint32_t r0 = hdr[warp], k = hdr[warp + 1] - r0;
                 const uint32_t *rp = rows + (size_t)r0 * 32 + lane;
-#pragma unroll 4
-                for (uint32_t r = r0; r < r1; ++r, rp += 32) {
-                    const uint32_t e = __ldg(rp);
-                    const float w = (float)(e >> 12) * (1.0f / kEllScale);
+#pragma unroll
+                for (int i = 0; i < KU; ++i) e[i] = (uint32_t)i < k ? __ldg(rp + i * 32) : 0u;
+            }
+            for (int j = warp; j < NBLK; j += NW) {
+                const uint32_t r0 = hdr[j], k = hdr[j + 1] - r0;
+                uint32_t en[KU];
+                const int jn = j + NW;
+                if (jn < NBLK) {
+                    const uint32_t rn0 = hdr[jn], kn = hdr[jn + 1] - rn0;
+                    const uint32_t *rp = rows + (size_t)rn0 * 32 + lane;
+#pragma unroll
+                    for (int i = 0; i < KU; ++i) en[i] = (uint32_t)i < kn ? __ldg(rp + i * 32) : 0u;
+                }
+                int sx, sy, sz;
+                il_block_voxel(j, lane, S, LOGS, sx, sy, sz);
+                const int s = (((sz << LOGS) + sy) << LOGS) + sx;
+                float acc[CI];
+#pragma unroll
+                for (int i = 0; i < CI; ++i) acc[i] = 0.f;
+#pragma unroll
+                for (int i = 0; i < KU; ++i) {
+                    if ((uint32_t)i < k) {                          // uniform over the warp
+                        const float w = (float)(e[i] >> 12) * (1.0f / kEllScale);
+                        float f[CI];
+                        IlUnit<T>::unpack(tile[e[i] & 0xfffu], f);
+#pragma unroll
+                        for (int c = 0; c < CI; ++c) acc[c] = fmaf(w, f[c], acc[c]);
+                    }
+                }
+                for (uint32_t i = KU; i < k; ++i) {                 // rare: more than KU rows in a block
+                    const uint32_t ee = __ldg(rows + (size_t)(r0 + i) * 32 + lane);
+                    const float w = (float)(ee >> 12) * (1.0f / kEllScale);
                     float f[CI];
-                    IlUnit<T>::unpack(tile[e & 0xfffu], f);
+                    IlUnit<T>::unpack(tile[ee & 0xfffu], f);
 #pragma unroll
                     for (int c = 0; c < CI; ++c) acc[c] = fmaf(w, f[c], acc[c]);
                 }
-            } else {
-                const uint16_t *start = reinterpret_cast<const uint16_t *>(wsb + lay.cells_off);
-                const uint16_t *items = start + N + 8;
+#pragma unroll
+                for (int i = 0; i < CI; ++i) st_stream_elem<T>(dst + i * N + s, acc[i]);
+#pragma unroll
+                for (int i = 0; i < KU; ++i) e[i] = en[i];
+            }
+        } else {
+            // ---- fallback: walk the cell table, recompute the weights ----------------------------------
+            const uint16_t *start = reinterpret_cast<const uint16_t *>(wsb + lay.cells_off);
+            const uint16_t *items = start + N + 8;
+            for (int j = warp; j < NBLK; j += NW) {
+                int sx, sy, sz;
+                il_block_voxel(j, lane, S, LOGS, sx, sy, sz);
+                const int s = (((sz << LOGS) + sy) << LOGS) + sx;
+                float acc[CI];
+#pragma unroll
+                for (int i = 0; i < CI; ++i) acc[i] = 0.f;
 #pragma unroll 1
                 for (int d = 0; d < 8; ++d) {
                     const int dx = d & 1, dy = (d >> 1) & 1, dz = d >> 2;
@@ -486,9 +635,8 @@ __global__ void __launch_bounds__(NT) rotate_bwd_il_kernel(const T *__restrict__
                     const int lo = __ldg(start + q), hi = __ldg(start + q + 1);
                     for (int i = lo; i < hi; ++i) {
                         const int o = __ldg(items + i);
-                        const int ox = o & (S - 1), oy = (o >> LOGS) & (S - 1), oz = o >> (2 * LOGS);
                         float x, y, z;
-                        il_coords(m, ox, oy, oz, x, y, z);
+                        il_coords(m, o & (S - 1), (o >> LOGS) & (S - 1), o >> (2 * LOGS), x, y, z);
                         const float wx = dx ? __fsub_rn(x, (float)qx) : __fsub_rn((float)(qx + 1), x);
                         const float wy = dy ? __fsub_rn(y, (float)qy) : __fsub_rn((float)(qy + 1), y);
                         const float wz = dz ? __fsub_rn(z, (float)qz) : __fsub_rn((float)(qz + 1), z);
@@ -499,13 +647,14 @@ __global__ void __launch_bounds__(NT) rotate_bwd_il_kernel(const T *__restrict__
                         for (int c = 0; c < CI; ++c) acc[c] = fmaf(w, f[c], acc[c]);
                     }
                 }
-            }
 #pragma unroll
-            for (int i = 0; i < CI; ++i) st_stream_elem<T>(dst + i * N + s, acc[i]);
+                for (int i = 0; i < CI; ++i) st_stream_elem<T>(dst + i * N + s, acc[i]);
+            }
         }
         if (tn < ntiles) {
             pf.store(buf + (cur ^ 1) * N);
             if (threadIdx.x < 12) msh[cur ^ 1][threadIdx.x] = mreg;
+            if (threadIdx.x < NBLK + 2) hsh[cur ^ 1][threadIdx.x] = hreg;
         }
         __syncthreads();
         cur ^= 1;
@@ -562,10 +711,6 @@ static int launch_bwd_il(const void *g, const float *a, const void *ws, size_t w
 
 using namespace hg;
 
-// rotate_cl.cu
-int hg_rotate_cells_launch(const float *a_inv, void *workspace, size_t sample_stride_bytes, int batch, int size, int logS,
-                           int include_outside, cudaStream_t st);
-
 // Interleaved-tile kernels cover S in {8, 16} and channel counts that are a multiple of one 16-byte unit
 // (4 fp32 / 8 bf16 channels); everything else stays on rotate.cu's per-channel tiles.
 bool hg_rotate_il_supported(int channels, int size, int dtype)
@@ -602,12 +747,18 @@ int hg_rotate_il_bwd(const void *grad_out, const float *a_inv, void *grad_vol, v
     const int n = size * size * size;
     const IlWsLayout lay = il_ws_layout(n);
     unsigned char *ws = static_cast<unsigned char *>(workspace);
-    int rc = hg_rotate_cells_launch(a_inv, ws + lay.cells_off, lay.per_sample, batch, size, logS, 0, st);
-    if (rc) return rc;
-    if (logS == 4) rotate_ell_kernel<4><<<batch, 1024, 0, st>>>(a_inv, ws, lay.per_sample, 0);
-    else rotate_ell_kernel<3><<<batch, 512, 0, st>>>(a_inv, ws, lay.per_sample, 0);
-    rc = check_launch("rotate_ell");
-    if (rc) return rc;
+    {
+        const size_t smem = (size_t)(3 * n + 2) * sizeof(uint32_t) + (size_t)n * 8;
+        static bool attr_done = false;
+        if (!attr_done) {
+            cudaFuncSetAttribute(rotate_adjoint_table_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+            attr_done = true;
+        }
+        if (logS == 4) rotate_adjoint_table_kernel<4><<<batch, 1024, smem, st>>>(a_inv, ws, lay.per_sample);
+        else rotate_adjoint_table_kernel<3><<<batch, 512, smem, st>>>(a_inv, ws, lay.per_sample);
+        int rc = check_launch("rotate_adjoint_table");
+        if (rc) return rc;
+    }
     const bool big = g_il_threads == 1024;
 #define HG_IL_BWD(T, L, NT) launch_bwd_il<T, L, NT>(grad_out, a_inv, ws, lay.per_sample, grad_vol, batch, channels, st)
     if (dtype == HG_F32) {
