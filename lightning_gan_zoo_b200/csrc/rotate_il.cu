@@ -347,7 +347,26 @@ __device__ __forceinline__ void il_voxel_block(int x, int y, int z, int logS, in
     lane = (x & 1) | ((y & 1) << 1) | ((z & 1) << 2) | (((x >> 1) & 3) << 3);
 }
 
-// One CTA per sample builds both tables in shared memory:
+// Two outputs can share a floor() cell only if they are lattice neighbours (differ by at most 1 per axis)
+// when every row of |L^-1| (L = linear part of the output -> source map) sums to less than 2: true for any
+// rotation at scale 1 (row sums <= sqrt 3).  Then the rank of an output inside its cell follows from its 26
+// neighbours and the table needs no sort (rotate_adjoint_table_kernel); otherwise (or when the rows overflow the
+// workspace) it leaves flag 0 in the header and the counting-sort variant below, launched right after it, takes the sample.
+__device__ __forceinline__ bool il_neighbour_rank_ok(const float *__restrict__ m)
+{
+    const float a = m[0], b = m[1], c = m[2], d = m[4], e = m[5], f = m[6], g = m[8], h = m[9], i = m[10];
+    const float A = e * i - f * h, B = c * h - b * i, C = b * f - c * e;
+    const float D = f * g - d * i, E = a * i - c * g, F = c * d - a * f;
+    const float G = d * h - e * g, H = b * g - a * h, I = a * e - b * d;
+    const float det = a * A + b * D + c * G;
+    if (!(fabsf(det) > 1e-12f)) return false;
+    const float r = 1.0f / fabsf(det);
+    const float s0 = (fabsf(A) + fabsf(B) + fabsf(C)) * r, s1 = (fabsf(D) + fabsf(E) + fabsf(F)) * r,
+                s2 = (fabsf(G) + fabsf(H) + fabsf(I)) * r;
+    return fmaxf(s0, fmaxf(s1, s2)) < 1.999f;
+}
+
+// Counting-sort variant.  One CTA per sample builds both tables in shared memory:
 //   1. counting sort "cell -> in-range outputs whose floor() lands in it" (fixed order inside a cell);
 //   2. per source voxel s the running offsets P(s, d) = sum over d' < d of |cell(s - d')|  (d = 0..7 numbers the
 //      corner (dx, dy, dz) that s is of cell s - d), hence the voxel's entry count and the block's row count K_j;
@@ -356,10 +375,14 @@ __device__ __forceinline__ void il_voxel_block(int x, int y, int z, int logS, in
 //      row  blockoff[j(s)] + P(s, d) + i,  lane l(s),  for s = q + d;  short rows are zero-padded.
 // The cell table is also written out: samples whose rows overflow the workspace use it directly.
 template <int LOGS>
-__global__ void __launch_bounds__(1024) rotate_adjoint_table_kernel(const float *__restrict__ a_inv, unsigned char *__restrict__ ws,
-                                                                     size_t ws_stride)
+__global__ void __launch_bounds__(1024) rotate_adjoint_table_sort_kernel(const float *__restrict__ a_inv,
+                                                                          unsigned char *__restrict__ ws, size_t ws_stride)
 {
     constexpr int S = 1 << LOGS, N = S * S * S, NBLK = N / 32;
+    {   // the sort-free kernel ran first on this stream: flag 1 = it built this sample's table
+        const uint32_t *flag = reinterpret_cast<const uint32_t *>(ws + (size_t)blockIdx.x * ws_stride + il_ws_layout(N).hdr_off) + NBLK + 1;
+        if (*flag == 1u) return;
+    }
     extern __shared__ uint32_t sm[];
     uint32_t *count = sm;                    // [N]  -> later the running cursor
     uint32_t *start = sm + N;                // [N + 1]
@@ -525,6 +548,149 @@ __global__ void __launch_bounds__(1024) rotate_adjoint_table_kernel(const float 
     }
 }
 
+// Sort-free variant (the normal case, see il_neighbour_rank_ok):
+//   a. cellof[o] = floor() cell of every in-range output;
+//   b. rank i of o inside its cell (ascending o) and the cell's size from the 26 lattice neighbours -- no atomics;
+//   c./d./e. as steps 2-4 above, the fill running straight from the (cell, rank) held in registers.
+template <int LOGS>
+__global__ void __launch_bounds__(1024) rotate_adjoint_table_kernel(const float *__restrict__ a_inv, unsigned char *__restrict__ ws,
+                                                                     size_t ws_stride)
+{
+    constexpr int S = 1 << LOGS, N = S * S * S, NBLK = N / 32, PER = (N + 1023) / 1024;
+    extern __shared__ uint32_t sm[];
+    uint16_t *cellof = reinterpret_cast<uint16_t *>(sm);                     // [N]   later: entries per voxel
+    uint16_t *cnt = cellof + N;                                               // [N]   outputs per cell
+    unsigned char *p8 = reinterpret_cast<unsigned char *>(cnt + N);          // [N][8]
+    __shared__ float m[12];
+    __shared__ uint32_t kblk[NBLK + 1];
+    const IlWsLayout lay = il_ws_layout(N);
+    const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5, nwarps = blockDim.x >> 5;
+    unsigned char *wsb = ws + (size_t)b * ws_stride;
+    uint32_t *hdr = reinterpret_cast<uint32_t *>(wsb + lay.hdr_off);
+    if (!il_neighbour_rank_ok(a_inv + b * 16)) {         // flag 0: left to the counting-sort kernel
+        if (t == 0) hdr[NBLK + 1] = 0u;
+        return;
+    }
+    uint32_t *rows = reinterpret_cast<uint32_t *>(wsb + lay.ell_off);
+    if (t < 12) m[t] = a_inv[b * 16 + t];
+    __syncthreads();
+    // ---- a. cell of every output ----------------------------------------------------------------------
+    const float lim = (float)(S - 1);
+    float px[PER], py[PER], pz[PER];
+    int cq[PER], rank[PER];
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+        const int o = t + k * 1024;
+        cq[k] = -1;
+        if (o < N) {
+            il_coords(m, o & (S - 1), (o >> LOGS) & (S - 1), o >> (2 * LOGS), px[k], py[k], pz[k]);   // the forward's bits
+            if (px[k] >= 0.f && px[k] < lim && py[k] >= 0.f && py[k] < lim && pz[k] >= 0.f && pz[k] < lim)
+                cq[k] = (((__float2int_rd(pz[k]) << LOGS) + __float2int_rd(py[k])) << LOGS) + __float2int_rd(px[k]);
+            cellof[o] = (uint16_t)(cq[k] < 0 ? 0xffff : cq[k]);
+            cnt[o] = 0;
+        }
+    }
+    __syncthreads();
+    // ---- b. rank inside the cell ------------------------------------------------------------------------
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+        const int o = t + k * 1024;
+        rank[k] = 0;
+        if (o < N && cq[k] >= 0) {
+            const int ox = o & (S - 1), oy = (o >> LOGS) & (S - 1), oz = o >> (2 * LOGS);
+            int before = 0, after = 0;
+#pragma unroll
+            for (int d = 0; d < 27; ++d) {
+                if (d == 13) continue;
+                const int dx = d % 3 - 1, dy = (d / 3) % 3 - 1, dz = d / 9 - 1;
+                const int nx = ox + dx, ny = oy + dy, nz = oz + dz;
+                if ((unsigned)nx < (unsigned)S && (unsigned)ny < (unsigned)S && (unsigned)nz < (unsigned)S) {
+                    const int match = cellof[o + (((dz << LOGS) + dy) << LOGS) + dx] == (uint16_t)cq[k];
+                    if (d < 13) before += match; else after += match;
+                }
+            }
+            rank[k] = before;
+            if (before == 0) cnt[cq[k]] = (uint16_t)(1 + after);
+        }
+    }
+    __syncthreads();
+    // ---- c. per-voxel offsets and per-block row counts -----------------------------------------------
+    for (int j = warp; j < NBLK; j += nwarps) {
+        int sx, sy, sz;
+        il_block_voxel(j, lane, S, LOGS, sx, sy, sz);
+        const int s = (((sz << LOGS) + sy) << LOGS) + sx;
+        uint32_t runv = 0;
+        uint32_t packed[2] = {0u, 0u};
+#pragma unroll
+        for (int d = 0; d < 8; ++d) {
+            packed[d >> 2] |= min(runv, 255u) << (8 * (d & 3));
+            const int qx = sx - (d & 1), qy = sy - ((d >> 1) & 1), qz = sz - (d >> 2);
+            if (qx >= 0 && qy >= 0 && qz >= 0 && qx <= S - 2 && qy <= S - 2 && qz <= S - 2)
+                runv += cnt[(((qz << LOGS) + qy) << LOGS) + qx];
+        }
+        reinterpret_cast<uint2 *>(p8)[s] = make_uint2(packed[0], packed[1]);
+        uint32_t kmax = runv;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
+        if (lane == 0) kblk[j] = kmax;
+        cellof[s] = (uint16_t)runv;              // reuse: entries of voxel s (for the padding)
+    }
+    __syncthreads();
+    // ---- d. scan over the blocks ----------------------------------------------------------------------
+    if (t < 32) {
+        uint32_t carry = 0;
+        for (int base = 0; base < NBLK; base += 32) {
+            const uint32_t k = base + t < NBLK ? kblk[base + t] : 0u;
+            uint32_t inc = k;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
+                if (t >= o) inc += v;
+            }
+            if (base + t < NBLK) kblk[base + t] = carry + inc - k;
+            carry += __shfl_sync(0xffffffffu, inc, 31);
+        }
+        if (t == 0) kblk[NBLK] = carry;
+    }
+    __syncthreads();
+    const bool fits = kblk[NBLK] <= (uint32_t)(NBLK * kEllCap);      // true at scale ~1 (K_j <= ~16)
+    for (int j = t; j <= NBLK; j += blockDim.x) hdr[j] = kblk[j];
+    if (t == 0) hdr[NBLK + 1] = fits ? 1u : 0u;                      // 0: rows overflow -> counting-sort kernel + cell walk
+    if (!fits) return;
+    // ---- e. fill ----------------------------------------------------------------------------------------
+    for (int j = warp; j < NBLK; j += nwarps) {
+        int sx, sy, sz;
+        il_block_voxel(j, lane, S, LOGS, sx, sy, sz);
+        const int s = (((sz << LOGS) + sy) << LOGS) + sx;
+        for (uint32_t r = kblk[j] + cellof[s]; r < kblk[j + 1]; ++r) rows[(size_t)r * 32 + lane] = 0u;
+    }
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+        const int o = t + k * 1024;
+        if (o < N && cq[k] >= 0) {
+            const int q = cq[k];
+            const int qx = q & (S - 1), qy = (q >> LOGS) & (S - 1), qz = q >> (2 * LOGS);
+            const float x = px[k], y = py[k], z = pz[k];
+            const float ux = __fsub_rn((float)(qx + 1), x), lx = __fsub_rn(x, (float)qx);
+            const float uy = __fsub_rn((float)(qy + 1), y), ly = __fsub_rn(y, (float)qy);
+            const float uz = __fsub_rn((float)(qz + 1), z), lz = __fsub_rn(z, (float)qz);
+            const uint32_t unit = (uint32_t)il_unit(o, LOGS);
+#pragma unroll
+            for (int d = 0; d < 8; ++d) {
+                const int dx = d & 1, dy = (d >> 1) & 1, dz = d >> 2;
+                const float w = __fmul_rn(__fmul_rn(dx ? lx : ux, dy ? ly : uy), dz ? lz : uz);
+                const int sx = qx + dx, sy = qy + dy, sz = qz + dz;
+                const int s = (((sz << LOGS) + sy) << LOGS) + sx;
+                int j, l;
+                il_voxel_block(sx, sy, sz, LOGS, j, l);
+                const uint32_t r = kblk[j] + p8[s * 8 + d] + (uint32_t)rank[k];
+                const uint32_t wq = (uint32_t)__float2int_rn(fminf(fmaxf(w, 0.f), 1.f) * kEllScale);
+                rows[(size_t)r * 32 + l] = (wq << 12) | unit;
+            }
+        }
+    }
+}
+
 template <typename T, int LOGS, int NT>
 __global__ void __launch_bounds__(NT) rotate_bwd_il_kernel(const T *__restrict__ grad_out, const float *__restrict__ a_inv,
                                                            const unsigned char *__restrict__ ws, size_t ws_stride,
@@ -568,24 +734,19 @@ __global__ void __launch_bounds__(NT) rotate_bwd_il_kernel(const T *__restrict__
         const unsigned char *wsb = ws + (size_t)(t / groups) * ws_stride;
         const uint32_t *rows = reinterpret_cast<const uint32_t *>(wsb + lay.ell_off);
         if (hdr[NBLK + 1] != 0u) {
-            // ---- adjoint-table path: the next block's rows are in flight while this block is summed ----
-            uint32_t e[KU];
-            {
-                const uint32_t r0 = hdr[warp], k = hdr[warp + 1] - r0;
-                const uint32_t *rp = rows + (size_t)r0 * 32 + lane;
+            // ---- adjoint-table path: the next block's rows are in flight while this block is summed.
+            // Rows are consumed four at a time (zero-weight padding entries are harmless), two register
+            // sets ping-pong between "being summed" and "in flight".
+            auto load_rows = [&](uint32_t (&e)[KU], int j) {
+                if (j < NBLK) {
+                    const uint32_t r0 = hdr[j], k = hdr[j + 1] - r0;
+                    const uint32_t *rp = rows + (size_t)r0 * 32 + lane;
 #pragma unroll
-                for (int i = 0; i < KU; ++i) e[i] = (uint32_t)i < k ? __ldg(rp + i * 32) : 0u;
-            }
-            for (int j = warp; j < NBLK; j += NW) {
-                const uint32_t r0 = hdr[j], k = hdr[j + 1] - r0;
-                uint32_t en[KU];
-                const int jn = j + NW;
-                if (jn < NBLK) {
-                    const uint32_t rn0 = hdr[jn], kn = hdr[jn + 1] - rn0;
-                    const uint32_t *rp = rows + (size_t)rn0 * 32 + lane;
-#pragma unroll
-                    for (int i = 0; i < KU; ++i) en[i] = (uint32_t)i < kn ? __ldg(rp + i * 32) : 0u;
+                    for (int i = 0; i < KU; ++i) e[i] = (uint32_t)i < k ? __ldg(rp + i * 32) : 0u;
                 }
+            };
+            auto sum_block = [&](const uint32_t (&e)[KU], int j) {
+                const uint32_t r0 = hdr[j], k = hdr[j + 1] - r0;
                 int sx, sy, sz;
                 il_block_voxel(j, lane, S, LOGS, sx, sy, sz);
                 const int s = (((sz << LOGS) + sy) << LOGS) + sx;
@@ -593,13 +754,19 @@ __global__ void __launch_bounds__(NT) rotate_bwd_il_kernel(const T *__restrict__
 #pragma unroll
                 for (int i = 0; i < CI; ++i) acc[i] = 0.f;
 #pragma unroll
-                for (int i = 0; i < KU; ++i) {
-                    if ((uint32_t)i < k) {                          // uniform over the warp
-                        const float w = (float)(e[i] >> 12) * (1.0f / kEllScale);
-                        float f[CI];
-                        IlUnit<T>::unpack(tile[e[i] & 0xfffu], f);
+                for (int i0 = 0; i0 < KU; i0 += 4) {
+                    if ((uint32_t)i0 < k) {                         // uniform over the warp
+                        uint4 raw[4];
 #pragma unroll
-                        for (int c = 0; c < CI; ++c) acc[c] = fmaf(w, f[c], acc[c]);
+                        for (int i = 0; i < 4; ++i) raw[i] = tile[e[i0 + i] & 0xfffu];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float w = (float)(e[i0 + i] >> 12) * (1.0f / kEllScale);
+                            float f[CI];
+                            IlUnit<T>::unpack(raw[i], f);
+#pragma unroll
+                            for (int c = 0; c < CI; ++c) acc[c] = fmaf(w, f[c], acc[c]);
+                        }
                     }
                 }
                 for (uint32_t i = KU; i < k; ++i) {                 // rare: more than KU rows in a block
@@ -612,8 +779,14 @@ __global__ void __launch_bounds__(NT) rotate_bwd_il_kernel(const T *__restrict__
                 }
 #pragma unroll
                 for (int i = 0; i < CI; ++i) st_stream_elem<T>(dst + i * N + s, acc[i]);
-#pragma unroll
-                for (int i = 0; i < KU; ++i) e[i] = en[i];
+            };
+            uint32_t ea[KU], eb[KU];
+            load_rows(ea, warp);
+            for (int j = warp; j < NBLK; j += 2 * NW) {
+                load_rows(eb, j + NW);
+                sum_block(ea, j);
+                load_rows(ea, j + 2 * NW);
+                if (j + NW < NBLK) sum_block(eb, j + NW);
             }
         } else {
             // ---- fallback: walk the cell table, recompute the weights ----------------------------------
@@ -748,14 +921,22 @@ int hg_rotate_il_bwd(const void *grad_out, const float *a_inv, void *grad_vol, v
     const IlWsLayout lay = il_ws_layout(n);
     unsigned char *ws = static_cast<unsigned char *>(workspace);
     {
-        const size_t smem = (size_t)(3 * n + 2) * sizeof(uint32_t) + (size_t)n * 8;
+        // sort-free table kernel first; the counting-sort kernel only proceeds for samples it declined
+        const size_t smem_fast = (size_t)n * 2 * 2 + (size_t)n * 8;
+        const size_t smem_sort = (size_t)(3 * n + 2) * sizeof(uint32_t) + (size_t)n * 8;
         static bool attr_done = false;
         if (!attr_done) {
-            cudaFuncSetAttribute(rotate_adjoint_table_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+            cudaFuncSetAttribute(rotate_adjoint_table_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+            cudaFuncSetAttribute(rotate_adjoint_table_sort_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
             attr_done = true;
         }
-        if (logS == 4) rotate_adjoint_table_kernel<4><<<batch, 1024, smem, st>>>(a_inv, ws, lay.per_sample);
-        else rotate_adjoint_table_kernel<3><<<batch, 512, smem, st>>>(a_inv, ws, lay.per_sample);
+        if (logS == 4) {
+            rotate_adjoint_table_kernel<4><<<batch, 1024, smem_fast, st>>>(a_inv, ws, lay.per_sample);
+            rotate_adjoint_table_sort_kernel<4><<<batch, 1024, smem_sort, st>>>(a_inv, ws, lay.per_sample);
+        } else {
+            rotate_adjoint_table_kernel<3><<<batch, 1024, smem_fast, st>>>(a_inv, ws, lay.per_sample);
+            rotate_adjoint_table_sort_kernel<3><<<batch, 512, smem_sort, st>>>(a_inv, ws, lay.per_sample);
+        }
         int rc = check_launch("rotate_adjoint_table");
         if (rc) return rc;
     }
