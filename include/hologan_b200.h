@@ -52,6 +52,9 @@ typedef enum {
                                * -> bit-identical to the reference CPU path in fp32                */
     HG_BORDER_ZERO = 1        /* write exact 0 where the reference's terms cancel to ~1e-7         */
 } hg_border_t;
+/* Launch-shape tuning flag, OR-ed into a `border` argument of hg_rotate_fwd / hg_rotate_bwd (NCDHW,
+ * S = 16): use 1024-thread CTAs instead of 512.  Results are identical; the library keeps no state. */
+#define HG_TUNE_CTA1024 0x100
 
 int hg_abi_version(void);
 const char *hg_last_error(void);

@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_PKG_DIR, "libhologan_b200.so")
 HG_F32, HG_BF16 = 0, 1
 HG_NCDHW, HG_NDHWC, HG_PROJ = 0, 1, 2
 HG_BORDER_REFERENCE, HG_BORDER_ZERO = 0, 1
+HG_TUNE_CTA1024 = 0x100        # OR into `border`: 1024-thread CTAs for the NCDHW 16^3 rotate (same results)
 
 _c_int, _c_void_p, _c_float, _c_ll = ctypes.c_int, ctypes.c_void_p, ctypes.c_float, ctypes.c_longlong
 

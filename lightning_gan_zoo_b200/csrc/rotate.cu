@@ -246,6 +246,8 @@ extern "C" int hg_rotate_fwd(const void *vol, const float *a_inv, void *out, flo
     const int logS = log2_exact(size);
     HG_REQUIRE(logS >= 3 && size <= 32, HG_ERR_UNSUPPORTED, "hg_rotate_fwd: size must be 8, 16 or 32 (got %d)", size);
     HG_REQUIRE(dtype == HG_F32 || dtype == HG_BF16, HG_ERR_INVALID_ARG, "hg_rotate_fwd: unknown dtype %d", dtype);
+    const int tune = border & HG_TUNE_CTA1024;      // launch-shape tuning flag, results unaffected
+    border &= ~HG_TUNE_CTA1024;
     HG_REQUIRE(border == HG_BORDER_REFERENCE || border == HG_BORDER_ZERO, HG_ERR_INVALID_ARG,
                "hg_rotate_fwd: unknown border mode %d", border);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -258,7 +260,7 @@ extern "C" int hg_rotate_fwd(const void *vol, const float *a_inv, void *out, flo
     }
     if (in_layout == HG_NCDHW && out_layout == HG_NCDHW) {
         if (hg_rotate_il_supported(channels, size, dtype))
-            return hg_rotate_il_fwd(vol, a_inv, out, batch, channels, size, logS, dtype, border, st);
+            return hg_rotate_il_fwd(vol, a_inv, out, batch, channels, size, logS, dtype, border | tune, st);
         const bool z = border == HG_BORDER_ZERO;
         if (dtype == HG_F32)
             return z ? fwd_ncdhw_by_size<float, true>(vol, a_inv, out, batch, channels, size, logS, st)
@@ -283,13 +285,15 @@ extern "C" int hg_rotate_bwd(const void *grad_out, const float *a_inv, void *gra
     const int logS = log2_exact(size);
     HG_REQUIRE(logS >= 3 && size <= 32, HG_ERR_UNSUPPORTED, "hg_rotate_bwd: size must be 8, 16 or 32 (got %d)", size);
     HG_REQUIRE(dtype == HG_F32 || dtype == HG_BF16, HG_ERR_INVALID_ARG, "hg_rotate_bwd: unknown dtype %d", dtype);
+    const int tune = border & HG_TUNE_CTA1024;      // launch-shape tuning flag, results unaffected
+    border &= ~HG_TUNE_CTA1024;
     HG_REQUIRE(border == HG_BORDER_REFERENCE || border == HG_BORDER_ZERO, HG_ERR_INVALID_ARG,
                "hg_rotate_bwd: unknown border mode %d", border);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (in_layout == HG_NCDHW && out_layout == HG_NCDHW) {
         if (hg_rotate_il_supported(channels, size, dtype) && workspace &&
             workspace_bytes >= (long long)hg_rotate_il_ws_bytes(batch, size))
-            return hg_rotate_il_bwd(grad_out, a_inv, grad_vol, workspace, batch, channels, size, logS, dtype, border, st);
+            return hg_rotate_il_bwd(grad_out, a_inv, grad_vol, workspace, batch, channels, size, logS, dtype, border | tune, st);
         const bool z = border == HG_BORDER_ZERO;
         if (dtype == HG_F32)
             return z ? bwd_ncdhw_by_size<float, true>(grad_out, a_inv, grad_vol, batch, channels, size, logS, st)

@@ -837,7 +837,6 @@ __global__ void __launch_bounds__(NT) rotate_bwd_il_kernel(const T *__restrict__
 // -------------------------------------------------------------------------------------------------
 // host side
 // -------------------------------------------------------------------------------------------------
-static int g_il_threads = 512;      // tuning knob (hg_rotate_il_set_threads): 512 or 1024 threads per CTA
 
 template <typename K>
 static void il_set_smem(K kernel, size_t smem, bool &done)
@@ -894,14 +893,12 @@ bool hg_rotate_il_supported(int channels, int size, int dtype)
 
 size_t hg_rotate_il_ws_bytes(int batch, int size) { return (size_t)batch * il_ws_layout(size * size * size).per_sample; }
 
-extern "C" void hg_rotate_il_set_threads(int t) { g_il_threads = (t == 1024) ? 1024 : 512; }
-
 int hg_rotate_il_fwd(const void *vol, const float *a_inv, void *out, int batch, int channels, int size, int logS, int dtype,
                      int border, cudaStream_t st)
 {
     (void)size;
-    const bool z = border == HG_BORDER_ZERO;
-    const bool big = g_il_threads == 1024;
+    const bool z = (border & 0xFF) == HG_BORDER_ZERO;
+    const bool big = (border & HG_TUNE_CTA1024) != 0;
 #define HG_IL_FWD(T, L, NT) \
     (z ? launch_fwd_il<T, L, NT, true>(vol, a_inv, out, batch, channels, st) : launch_fwd_il<T, L, NT, false>(vol, a_inv, out, batch, channels, st))
     if (dtype == HG_F32) {
@@ -916,7 +913,6 @@ int hg_rotate_il_fwd(const void *vol, const float *a_inv, void *out, int batch, 
 int hg_rotate_il_bwd(const void *grad_out, const float *a_inv, void *grad_vol, void *workspace, int batch, int channels,
                      int size, int logS, int dtype, int border, cudaStream_t st)
 {
-    (void)border;
     const int n = size * size * size;
     const IlWsLayout lay = il_ws_layout(n);
     unsigned char *ws = static_cast<unsigned char *>(workspace);
@@ -940,7 +936,7 @@ int hg_rotate_il_bwd(const void *grad_out, const float *a_inv, void *grad_vol, v
         int rc = check_launch("rotate_adjoint_table");
         if (rc) return rc;
     }
-    const bool big = g_il_threads == 1024;
+    const bool big = (border & HG_TUNE_CTA1024) != 0;
 #define HG_IL_BWD(T, L, NT) launch_bwd_il<T, L, NT>(grad_out, a_inv, ws, lay.per_sample, grad_vol, batch, channels, st)
     if (dtype == HG_F32) {
         if (logS == 4) return big ? HG_IL_BWD(float, 4, 1024) : HG_IL_BWD(float, 4, 512);

@@ -137,13 +137,10 @@ def test_scaled_shifted_views_fwd_bwd(scale, threads, size, c_oracle):
     view[:, 3:6] = np.random.RandomState(8).uniform(-2, 2, (b, 3))
     a_cpu = ops.view_to_affine(view, s, s)
     a = a_cpu.to(DEV)
-    _lib.load().hg_rotate_il_set_threads(threads)
-    try:
-        out = ops.rotate_fwd_raw(vol.to(DEV), a, ops.HG_BORDER_REFERENCE)
-        gv = ops.rotate_bwd_raw(gout.to(DEV), a, c, s, ops.HG_BORDER_REFERENCE)
-        gvb = ops.rotate_bwd_raw(gout.to(DEV).bfloat16(), a, c, s, ops.HG_BORDER_ZERO)
-    finally:
-        _lib.load().hg_rotate_il_set_threads(512)
+    tune = _lib.HG_TUNE_CTA1024 if threads == 1024 else 0
+    out = ops.rotate_fwd_raw(vol.to(DEV), a, ops.HG_BORDER_REFERENCE | tune)
+    gv = ops.rotate_bwd_raw(gout.to(DEV), a, c, s, ops.HG_BORDER_REFERENCE | tune)
+    gvb = ops.rotate_bwd_raw(gout.to(DEV).bfloat16(), a, c, s, ops.HG_BORDER_ZERO | tune)
     ref = np.empty((b, c, s, s, s), np.float32)
     refg = np.empty_like(ref)
     c_oracle.orc_rotate_fwd(np_ptr(np.ascontiguousarray(vol.numpy())), np_ptr(a_cpu.numpy()), np_ptr(ref), b, c, s)

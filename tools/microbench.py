@@ -59,7 +59,7 @@ def views(b, seed=0):
     return v
 
 
-def rotate(shapes=None):
+def rotate(shapes=None, tune=0):
     print(f"# rotate-resample, HBM peak {PEAK} GB/s; algorithmic bytes = 2*B*C*S^3*sizeof")
     for (b, c, s) in shapes or [(64, 64, 16), (64, 128, 16), (64, 256, 16), (64, 64, 32), (64, 128, 32)]:
         for dt in (torch.float32, torch.bfloat16):
@@ -69,8 +69,8 @@ def rotate(shapes=None):
             nbuf = min(nbuf, 12)
             bufs = [torch.randn(b, c, s, s, s, device=DEV, dtype=dt) for _ in range(nbuf)]
             for border, bn in ((ops.HG_BORDER_REFERENCE, "ref"), (ops.HG_BORDER_ZERO, "zero")):
-                tf = time_rot(lambda v: ops.rotate_fwd_raw(v, a, border), bufs)
-                tb = time_rot(lambda v: ops.rotate_bwd_raw(v, a, c, s, border), bufs)
+                tf = time_rot(lambda v: ops.rotate_fwd_raw(v, a, border | tune), bufs)
+                tb = time_rot(lambda v: ops.rotate_bwd_raw(v, a, c, s, border | tune), bufs)
                 print(f"rotate ({b},{c},{s}^3) {str(dt)[6:]:8s} border={bn:4s} fwd {tf*1e6:8.1f} us {nbytes/tf/1e9:7.0f} GB/s "
                       f"({nbytes/tf/1e9/PEAK*100:4.1f}%)  bwd {tb*1e6:8.1f} us {nbytes/tb/1e9:7.0f} GB/s ({nbytes/tb/1e9/PEAK*100:4.1f}%)")
             del bufs
@@ -222,10 +222,8 @@ if __name__ == "__main__":
     if what == "rotate16":                  # tuning: interleaved-tile kernels with 1 and 2 channel groups per CTA
         from lightning_gan_zoo_b200 import _lib
         for g in (512, 1024):
-            _lib.load().hg_rotate_il_set_threads(g)
             print(f"## threads per CTA = {g}")
-            rotate([(64, 64, 16), (64, 256, 16), (64, 64, 8)])
-        _lib.load().hg_rotate_il_set_threads(512)
+            rotate([(64, 64, 16), (64, 256, 16), (64, 64, 8)], tune=_lib.HG_TUNE_CTA1024 if g == 1024 else 0)
     if what in ("adain", "all"):
         adain()
     if what in ("conv", "all"):
