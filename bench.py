@@ -190,10 +190,60 @@ def run_reference(args):
 # roofline of the dominant hand-written kernel, measured live with CUDA events
 # --------------------------------------------------------------------------------------------------
 
+def _event_time_ms(fn, nbuf, iters):
+    """Average milliseconds per call of fn(i) on torch's current stream (the stream the C ABI launches on)."""
+    for i in range(min(nbuf, 3)):
+        fn(i)
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    ev[0].record()
+    for i in range(iters):
+        fn(i % nbuf)
+    ev[1].record()
+    torch.cuda.synchronize()
+    return ev[0].elapsed_time(ev[1]) / iters
+
+
+def _ncu_traffic(kernel_key):
+    """dram bytes per launch from the committed `ncu --set full` summary (profiles/ncu_traffic.json), or None."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(path):
+        return None
+    try:
+        return json.load(open(path)).get(kernel_key, {}).get("dram_bytes_per_launch")
+    except (ValueError, OSError):
+        return None
+
+
+def conv_roofline(peaks, device):
+    """Dominant kernel of the step: hg::tap_gemm_kernel (18 % of the step's kernel time, profiles/*_launches_summary.txt),
+    timed at its largest instance -- block3 forward, ConvTranspose2d 1024->256 k4 s2 at 16x16, B = 64.
+    Algorithmic FLOPs per launch = 2147.5 MFLOP/sample x 64 = 137.4 GFLOP.  Tensor-pipe roofline
+    against the measured cuBLAS bf16 burst peak (the kernel is timed alone).  Three rotating operand sets."""
+    import ctypes
+    from lightning_gan_zoo_b200 import _lib, ops
+    B, cin, cout, size, k, ndim = 64, 1024, 256, 16, 4, 2
+    nb = 3
+    xs = [torch.randn(B, size, size, cin, device=device).to(torch.bfloat16) for _ in range(nb)]
+    w = torch.randn(cin, cout, k, k, device=device) * 0.02
+    wf, _ = ops.pack_convt_weight(w)
+    y = torch.empty(B, size, size, 4, cout, device=device, dtype=torch.bfloat16)
+    P = ops._ptr
+    fn = lambda i: _lib.call("hg_convt_fwd", P(xs[i]), P(wf), P(None), P(y), B, cin, cout, ndim, size, k,
+                             ctypes.c_float(1.0), ops._stream())
+    ms = _event_time_ms(fn, nb, 40)
+    flops = 2.0 * B * size * size * cin * cout * k * k
+    achieved = flops / (ms * 1e-3) / 1e12
+    return {"bound": "tensor", "kernel": "hg::tap_gemm_kernel, block3 fwd (ConvT2d 1024->256 k4 s2 @16x16, B=64, bf16)",
+            "achieved": achieved, "peak": peaks["bf16_tflops"], "peak_source": peaks["source"] + " (burst)",
+            "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops"], "traffic": _ncu_traffic("tap_gemm_block3_fwd"),
+            "us_per_launch": ms * 1e3, "algorithmic_flops": flops}
+
+
 def rotate_roofline(peaks, device):
-    """cfg 3 microbench: (64, 64, 16^3) fp32 rotate-resample forward.  Algorithmic bytes per launch =
-    read the volume + write the volume = 2*B*C*S^3*4.  Eight buffer pairs (1 GiB) are
-    rotated so every launch reads from HBM, not from the 126 MB L2."""
+    """cfg 3 microbench ("voxel-rotate HBM GB/s" of the metric): (64, 64, 16^3) fp32 rotate-resample, forward and
+    backward.  Algorithmic bytes per launch = read one volume + write one volume = 2*B*C*S^3*4 = 128 MiB
+    (DESIGN.md 4.1).  Eight rotating 64 MiB inputs (512 MiB) so every launch reads from HBM, not the 126 MB L2."""
     from lightning_gan_zoo_b200 import ops
     b, c, s = 64, 64, 16
     nbuf = 8
@@ -201,23 +251,18 @@ def rotate_roofline(peaks, device):
     rs = np.random.RandomState(0)
     view = np.zeros((b, 6)); view[:, 0] = np.deg2rad(rs.randint(220, 320, b)); view[:, 1] = np.deg2rad(rs.randint(70, 110, b)); view[:, 2] = 1
     a = ops.view_to_affine(view).to(device)
-    for v in vols[:3]:
-        ops.rotate_fwd_raw(v, a, ops.HG_BORDER_REFERENCE)
-    torch.cuda.synchronize()
-    iters = 40
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-    ev[0].record()
-    for i in range(iters):
-        ops.rotate_fwd_raw(vols[i % nbuf], a, ops.HG_BORDER_REFERENCE)
-    ev[1].record()
-    torch.cuda.synchronize()
-    ms = ev[0].elapsed_time(ev[1]) / iters
+    ms_f = _event_time_ms(lambda i: ops.rotate_fwd_raw(vols[i], a, ops.HG_BORDER_REFERENCE), nbuf, 40)
+    ms_b = _event_time_ms(lambda i: ops.rotate_bwd_raw(vols[i], a, c, s, ops.HG_BORDER_REFERENCE), nbuf, 40)
     bytes_alg = 2 * b * c * s ** 3 * 4
-    achieved = bytes_alg / (ms * 1e-3) / 1e9
-    return {"bound": "hbm", "kernel": "rotate_fwd_ncdhw_kernel<float,4> (64,64,16^3) fp32", "achieved": achieved,
-            "peak": peaks["hbm_gbs"], "peak_source": peaks["source"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
-            "traffic": None, "us_per_launch": ms * 1e3, "algorithmic_bytes": bytes_alg,
-            "l2_policy": "8 rotating 64 MiB inputs (512 MiB) > 126 MB L2"}
+    out = {}
+    for tag, ms, key, kern in (("fwd", ms_f, "rotate_il_fwd", "hg::rotate_fwd_il_kernel<float,4,512,false>"),
+                               ("bwd", ms_b, "rotate_il_bwd", "hg::rotate_adjoint_table_kernel<4> + hg::rotate_bwd_il_kernel<float,4,512>")):
+        achieved = bytes_alg / (ms * 1e-3) / 1e9
+        out[tag] = {"bound": "hbm", "kernel": kern + " (64,64,16^3) fp32", "achieved": achieved, "peak": peaks["hbm_gbs"],
+                    "peak_source": peaks["source"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
+                    "traffic": _ncu_traffic(key), "us_per_launch": ms * 1e3, "algorithmic_bytes": bytes_alg}
+    out["l2_policy"] = "8 rotating 64 MiB inputs (512 MiB) > 126 MB L2"
+    return out
 
 
 # --------------------------------------------------------------------------------------------------
@@ -329,7 +374,8 @@ def main():
     if rank == 0:
         peaks = measured_peaks()
         if not args.no_roofline:
-            line["roofline"] = rotate_roofline(peaks, device)
+            line["roofline"] = conv_roofline(peaks, device)
+            line["roofline_rotate"] = rotate_roofline(peaks, device)
         if world == 1 and not args.no_cpu_baseline:
             ips, ms, threads = cpu_training_steps(args.cpu_batch, S, steps=6, warmup=3)
             line["cpu_baseline"] = {"value": ips, "unit": UNIT, "cores": threads, "kind": "port",

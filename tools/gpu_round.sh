@@ -24,6 +24,10 @@ if has micro; then
   timeout 900 python tools/microbench.py all > $OUT/${TAG}_microbench.txt 2>&1
   echo "microbench exit $?"
 fi
+if has rot16; then
+  timeout 600 python tools/microbench.py rotate16 > $OUT/${TAG}_rotate16.txt 2>&1
+  echo "rotate16 exit $?"
+fi
 if has step; then
   timeout 600 python tools/profile_step.py 6 > $OUT/${TAG}_torch_profiler_step.txt 2>&1
   echo "profile_step exit $?"
