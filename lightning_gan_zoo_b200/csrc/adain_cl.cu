@@ -192,39 +192,8 @@ __global__ void __launch_bounds__(kClThreads) adain_cl_stats_kernel(const __nv_b
     }
 }
 
-// kFused: one CTA per sample computes the statistics itself (chunks == 1); else they come from `part`.
-// Merge the chunk partials of one sample (fixed chunk order), one thread per channel.
-//   forward : part = {sum(x-K), sum((x-K)^2)}  ->  save_mean, save_rstd
-//   backward: part = {sum(g), sum(g*xhat)}     ->  sums[b][2C] (and dbias / dscale when requested)
-__global__ void __launch_bounds__(256) adain_cl_finalize_kernel(const __nv_bfloat16 *__restrict__ x, const float *__restrict__ part,
-                                                                float *__restrict__ out_a, float *__restrict__ out_b,
-                                                                float *__restrict__ out_a2, float *__restrict__ out_b2, ClGeom g,
-                                                                int out_stride, int out2_stride, float eps, int forward)
-{
-    const int b = blockIdx.y, c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= g.C) return;
-    const float *src = part + (size_t)b * g.chunks * 2 * g.C + c;
-    float a = 0.f, q = 0.f;
-    for (int k = 0; k < g.chunks; ++k) {
-        a += src[(size_t)k * 2 * g.C];
-        q += src[(size_t)k * 2 * g.C + g.C];
-    }
-    if (forward) {
-        const float piv = __bfloat162float(x[(size_t)b * g.N * g.C + c]);
-        const float d = a / (float)g.N;
-        const float var = fmaxf(q - a * d, 0.f) / (float)g.Nvar;
-        out_a[(size_t)b * out_stride + c] = piv + d;
-        out_b[(size_t)b * out_stride + c] = __frsqrt_rn(var + eps);
-    } else {
-        out_a[(size_t)b * out_stride + c] = a;
-        out_b[(size_t)b * out_stride + c] = q;
-        if (out_a2) {
-            out_a2[(size_t)b * out2_stride + c] = a;
-            out_b2[(size_t)b * out2_stride + c] = q;
-        }
-    }
-}
-
+// kFused: one CTA per sample computes the statistics itself (chunks == 1); else every CTA merges the chunk
+// partials in `part` (fixed order).
 template <bool kFused>
 __global__ void __launch_bounds__(kClThreads) adain_cl_apply_kernel(const __nv_bfloat16 *__restrict__ x,
                                                                     const float *__restrict__ part,
@@ -262,12 +231,35 @@ __global__ void __launch_bounds__(kClThreads) adain_cl_apply_kernel(const __nv_b
                 save_rstd[(size_t)b * g.C + cs * 8 + j] = rstd[j];
             }
         }
-    } else {                                                    // merged by adain_cl_finalize_kernel
-        const float4 *m4 = reinterpret_cast<const float4 *>(save_mean + (size_t)b * g.C + cs * 8);
-        const float4 *r4 = reinterpret_cast<const float4 *>(save_rstd + (size_t)b * g.C + cs * 8);
-        const float4 m0 = m4[0], m1 = m4[1], q0 = r4[0], q1 = r4[1];
-        mean[0] = m0.x; mean[1] = m0.y; mean[2] = m0.z; mean[3] = m0.w; mean[4] = m1.x; mean[5] = m1.y; mean[6] = m1.z; mean[7] = m1.w;
-        rstd[0] = q0.x; rstd[1] = q0.y; rstd[2] = q0.z; rstd[3] = q0.w; rstd[4] = q1.x; rstd[5] = q1.y; rstd[6] = q1.z; rstd[7] = q1.w;
+    } else {
+        // merge the chunk partials of adain_cl_stats_kernel (fixed chunk order: every CTA of the sample gets the
+        // same bits); the sample's first chunk also publishes mean / rstd for the backward
+        float piv[8], s1[8], s2[8];
+        unpack8(__ldg(reinterpret_cast<const uint4 *>(xb)), piv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
+        const float *src = part + (size_t)b * g.chunks * 2 * g.C + cs * 8;
+        for (int k = 0; k < g.chunks; ++k) {
+            const float4 *a4 = reinterpret_cast<const float4 *>(src + (size_t)k * 2 * g.C);
+            const float4 *q4 = reinterpret_cast<const float4 *>(src + (size_t)k * 2 * g.C + g.C);
+            const float4 a0 = a4[0], a1 = a4[1], q0 = q4[0], q1 = q4[1];
+            s1[0] += a0.x; s1[1] += a0.y; s1[2] += a0.z; s1[3] += a0.w; s1[4] += a1.x; s1[5] += a1.y; s1[6] += a1.z; s1[7] += a1.w;
+            s2[0] += q0.x; s2[1] += q0.y; s2[2] += q0.z; s2[3] += q0.w; s2[4] += q1.x; s2[5] += q1.y; s2[6] += q1.z; s2[7] += q1.w;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float d = s1[j] / (float)g.N;                 // mean - K
+            mean[j] = piv[j] + d;
+            const float var = fmaxf(s2[j] - s1[j] * d, 0.f) / (float)g.Nvar;
+            rstd[j] = __frsqrt_rn(var + eps);
+        }
+        if (chunk == 0 && rs == 0) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                save_mean[(size_t)b * g.C + cs * 8 + j] = mean[j];
+                save_rstd[(size_t)b * g.C + cs * 8 + j] = rstd[j];
+            }
+        }
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -415,14 +407,17 @@ __global__ void __launch_bounds__(kClThreads) adain_cl_bwd_apply_kernel(const __
     if (kFused) {
         bwd_accumulate(x + base, dy + base, g, 0, g.N, rs, st, slope, sg, sgx);
         cta_rowslot_sum(sg, sgx, red, g.lanes, g.rows_per_pass, cs, rs);
-    } else {                                                    // merged by adain_cl_finalize_kernel: part = sums[b][2C]
-        const float4 *a4 = reinterpret_cast<const float4 *>(part + (size_t)b * 2 * g.C + cs * 8);
-        const float4 *q4 = reinterpret_cast<const float4 *>(part + (size_t)b * 2 * g.C + g.C + cs * 8);
-        const float4 a0 = a4[0], a1 = a4[1], q0 = q4[0], q1 = q4[1];
-        sg[0] = a0.x; sg[1] = a0.y; sg[2] = a0.z; sg[3] = a0.w; sg[4] = a1.x; sg[5] = a1.y; sg[6] = a1.z; sg[7] = a1.w;
-        sgx[0] = q0.x; sgx[1] = q0.y; sgx[2] = q0.z; sgx[3] = q0.w; sgx[4] = q1.x; sgx[5] = q1.y; sgx[6] = q1.z; sgx[7] = q1.w;
+    } else {                                                    // merge the chunk partials of adain_cl_bwd_sums_kernel
+        const float *src = part + (size_t)b * g.chunks * 2 * g.C + cs * 8;
+        for (int k = 0; k < g.chunks; ++k) {
+            const float4 *a4 = reinterpret_cast<const float4 *>(src + (size_t)k * 2 * g.C);
+            const float4 *q4 = reinterpret_cast<const float4 *>(src + (size_t)k * 2 * g.C + g.C);
+            const float4 a0 = a4[0], a1 = a4[1], q0 = q4[0], q1 = q4[1];
+            sg[0] += a0.x; sg[1] += a0.y; sg[2] += a0.z; sg[3] += a0.w; sg[4] += a1.x; sg[5] += a1.y; sg[6] += a1.z; sg[7] += a1.w;
+            sgx[0] += q0.x; sgx[1] += q0.y; sgx[2] += q0.z; sgx[3] += q0.w; sgx[4] += q1.x; sgx[5] += q1.y; sgx[6] += q1.z; sgx[7] += q1.w;
+        }
     }
-    if (kFused && rs == 0 && dscale && dbias) {
+    if ((kFused || chunk == 0) && rs == 0 && dscale && dbias) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             dbias[(size_t)b * dsbs + cs * 8 + j] = sg[j];
@@ -517,10 +512,6 @@ extern "C" int hg_adain_cl_fwd(const void *x, const float *scale, const float *b
     adain_cl_stats_kernel<<<grid, kClThreads, 0, st>>>(xp, part, g);
     rc = check_launch("hg_adain_cl_fwd(stats)");
     if (rc) return rc;
-    dim3 fgrid((channels + 255) / 256, batch);
-    adain_cl_finalize_kernel<<<fgrid, 256, 0, st>>>(xp, part, save_mean, save_rstd, nullptr, nullptr, g, channels, 0, eps, 1);
-    rc = check_launch("hg_adain_cl_fwd(finalize)");
-    if (rc) return rc;
     adain_cl_apply_kernel<false><<<grid, kClThreads, 0, st>>>(xp, part, scale, bias, yp, save_mean, save_rstd, g, sb_stride, eps,
                                                              neg_slope);
     return check_launch("hg_adain_cl_fwd(apply)");
@@ -551,16 +542,10 @@ extern "C" int hg_adain_cl_bwd(const void *x, const void *dy, const float *scale
     HG_REQUIRE(workspace && workspace_bytes >= (long long)batch * (g.chunks + 1) * 2 * channels * (long long)sizeof(float),
                HG_ERR_INVALID_ARG, "hg_adain_cl_bwd: workspace smaller than hg_adain_cl_workspace_bytes()");
     float *part = static_cast<float *>(workspace);
-    float *sums = part + (size_t)batch * g.chunks * 2 * channels;          // [b][2C]
     adain_cl_bwd_sums_kernel<<<grid, kClThreads, 0, st>>>(xp, gp, scale, bias, save_mean, save_rstd, part, g, sb_stride, neg_slope);
     rc = check_launch("hg_adain_cl_bwd(sums)");
     if (rc) return rc;
-    dim3 fgrid((channels + 255) / 256, batch);
-    adain_cl_finalize_kernel<<<fgrid, 256, 0, st>>>(xp, part, sums, sums + channels, dbias, dscale, g, 2 * channels, dsb_stride,
-                                                   0.f, 0);
-    rc = check_launch("hg_adain_cl_bwd(finalize)");
-    if (rc) return rc;
-    adain_cl_bwd_apply_kernel<false><<<grid, kClThreads, 0, st>>>(xp, gp, sums, scale, bias, save_mean, save_rstd, dp, dscale,
+    adain_cl_bwd_apply_kernel<false><<<grid, kClThreads, 0, st>>>(xp, gp, part, scale, bias, save_mean, save_rstd, dp, dscale,
                                                                  dbias, g, sb_stride, dsb_stride, neg_slope);
     return check_launch("hg_adain_cl_bwd(apply)");
 }

@@ -15,6 +15,7 @@
 // three instances of one warp-specialised pipeline:  TMA producer warp -> 128B-swizzled smem ring ->
 // single-thread tcgen05.mma issue (fp32 accumulators in TMEM) -> 4 epilogue warps (tcgen05.ld).
 #include <cuda.h>
+#include <cstdlib>
 
 #include "hg_common.cuh"
 #include "sm100_ptx.cuh"
@@ -28,6 +29,8 @@ constexpr int kMaxStages = 8;
 constexpr int kMaxTaps = 32;
 constexpr int kMaxGroups = 8;
 constexpr int kSmemBudget = 200 * 1024;
+constexpr int kDualSmemBudget = 100 * 1024;       // "dual" launches: two tap-GEMM CTAs per SM (<= 256 TMEM columns each)
+constexpr long long kDualMaxBytes = 2ll << 20;    // ... chosen when a CTA streams at most this many operand bytes
 constexpr int kWgradSmemBudget = 100 * 1024;      // two wgrad CTAs per SM
 
 struct Tap {
@@ -192,18 +195,26 @@ __global__ void __launch_bounds__(kThreads, 1) tap_gemm_kernel(const __grid_cons
         const long long m = (long long)blockIdx.x * kBM + row;
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
         __nv_bfloat16 *orow = static_cast<__nv_bfloat16 *>(p.out) + m * p.ld_out + grp.out_col_off + n0;
-        for (int c0 = 0; c0 < p.epi_cols; c0 += 16) {
-            float v[16];
-            ptx::tmem_ld_16(taddr + (uint32_t)c0, v);
-            if (m < p.m_total) {
-                uint32_t packed[8];
-                const int bcol = (n0 + c0) % p.bias_mod;
+        for (int c0 = 0; c0 < p.epi_cols; c0 += 32) {
+            float v[32];
+            if (c0 + 32 <= p.epi_cols) {
+                ptx::tmem_ld_32(taddr + (uint32_t)c0, v);
+            } else {                                    // 16-column tail (epi_cols is a multiple of 16)
+                float t[16];
+                ptx::tmem_ld_16(taddr + (uint32_t)c0, t);
 #pragma unroll
-                for (int j = 0; j < 16; j += 2) {
+                for (int j = 0; j < 16; ++j) { v[j] = t[j]; v[16 + j] = 0.f; }
+            }
+            if (m < p.m_total) {
+                const int ncol = min(32, p.epi_cols - c0);
+                const int bcol = (n0 + c0) % p.bias_mod;      // bias_mod is a multiple of 16 and of ncol's run
+                uint32_t packed[16];
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) {
                     float a = v[j], b = v[j + 1];
-                    if (p.bias) {
-                        a += __ldg(p.bias + bcol + j);
-                        b += __ldg(p.bias + bcol + j + 1);
+                    if (p.bias && j < ncol) {
+                        a += __ldg(p.bias + (bcol + j) % p.bias_mod);
+                        b += __ldg(p.bias + (bcol + j + 1) % p.bias_mod);
                     }
                     a = a > 0.f ? a : a * p.slope;
                     b = b > 0.f ? b : b * p.slope;
@@ -213,6 +224,10 @@ __global__ void __launch_bounds__(kThreads, 1) tap_gemm_kernel(const __grid_cons
                 uint4 *dst = reinterpret_cast<uint4 *>(orow + c0);
                 dst[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
                 dst[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+                if (ncol > 16) {
+                    dst[2] = make_uint4(packed[8], packed[9], packed[10], packed[11]);
+                    dst[3] = make_uint4(packed[12], packed[13], packed[14], packed[15]);
+                }
             }
         }
     }
@@ -600,12 +615,31 @@ static void for_each_class_tap(const ConvShape &c, Fn fn)
             }
 }
 
+// Launch shape of the K-major kernel.  "single": one CTA per SM with a deep ring (kSmemBudget) and up to 512
+// accumulator columns.  "dual": two co-resident CTAs per SM (kDualSmemBudget each, <= 256 columns each), so that a
+// CTA's prologue (tensor-map fetch, first TMA round trip) and epilogue (TMEM drain + stores) overlap its
+// neighbour's main loop -- the ~11 k cycles of fixed cost per CTA are half the life of a CTA on the narrow layers
+// (profiles/r01c_ncu_full_summary.txt).  HG_TAPGEMM_DUAL=0/1 overrides the choice (tuning only; read per call).
+static int dual_override()
+{
+    const char *e = getenv("HG_TAPGEMM_DUAL");
+    return e ? (e[0] == '1' ? 1 : 0) : -1;
+}
+static bool want_dual(int stage_bytes, int iters_per_cta, int epi_cols)
+{
+    if (epi_cols > 256 || 2 * stage_bytes + 1024 > kDualSmemBudget) return false;
+    const int ov = dual_override();
+    if (ov >= 0) return ov == 1;
+    return (long long)stage_bytes * iters_per_cta <= kDualMaxBytes;
+}
+
 static int launch_tap_gemm(TapGemmParams &p, int m_tiles, int n_tiles, cudaStream_t st, const char *who)
 {
     const int stage_bytes = kBM * 128 + p.BN * 128;
     int max_iters = 0;
     for (int g = 0; g < p.num_groups; ++g) max_iters = p.groups[g].tap_count * p.k_chunks > max_iters ? p.groups[g].tap_count * p.k_chunks : max_iters;
-    p.stages = pick_stages(stage_bytes, max_iters);
+    const bool dual = want_dual(stage_bytes, max_iters, p.epi_cols);
+    p.stages = pick_stages(stage_bytes, max_iters, dual ? kDualSmemBudget : kSmemBudget);
     const size_t smem = (size_t)p.stages * stage_bytes + 1024;
     static bool attr_set = false;
     if (!attr_set) {
@@ -615,6 +649,14 @@ static int launch_tap_gemm(TapGemmParams &p, int m_tiles, int n_tiles, cudaStrea
     dim3 grid(m_tiles, n_tiles, p.num_groups);
     tap_gemm_kernel<<<grid, kThreads, smem, st>>>(p);
     return check_launch(who);
+}
+
+// N tile of a K-major GEMM: the widest MMA that divides n, narrowed while the grid would leave SMs idle.
+static int pick_bn_for_grid(int n, int m_tiles)
+{
+    int bn = pick_bn(n);
+    while (bn > 64 && 4ll * m_tiles * (n / bn) < 3ll * sm_count()) bn /= 2;
+    return bn;
 }
 
 }  // namespace hg
@@ -627,7 +669,7 @@ extern "C" int hg_gemm_bf16_nt(const void *a, const void *b, const float *bias, 
 {
     HG_REQUIRE(a && b && d, HG_ERR_INVALID_ARG, "hg_gemm_bf16_nt: null pointer");
     HG_REQUIRE(m > 0 && n > 0 && k > 0, HG_ERR_INVALID_ARG, "hg_gemm_bf16_nt: dims must be positive");
-    const int bn = pick_bn(n);
+    const int bn = pick_bn_for_grid(n, (m + kBM - 1) / kBM);
     HG_REQUIRE(k % kBK == 0 && bn >= 16 && ldd % 8 == 0, HG_ERR_UNSUPPORTED,
                "hg_gemm_bf16_nt: need K %% 64 == 0, N %% 16 == 0, ldd %% 8 == 0 (got M=%d N=%d K=%d)", m, n, k);
     TapGemmParams p{};
@@ -698,13 +740,38 @@ extern "C" int hg_convt_fwd(const void *x, const void *w_fwd, const float *bias,
     const long long m_total = (long long)batch * c.X * c.Y * c.Z;
     p.m_total = (int)m_total; p.ld_out = (long long)c.P * cout; p.out = y_s2d; p.bias = bias; p.slope = neg_slope;
     // Narrow layers (Cout <= 128 == one N tile): several parity classes share a CTA, one TMEM accumulator
-    // each (<= 512 columns), so a CTA does classes_per_cta x the work per prologue/epilogue and writes one
-    // contiguous run of the s2d output row.
-    int cpc = 1;
-    if (bn == cout && c.P > 1) {
-        cpc = 512 / cout;
-        if (cpc > c.P) cpc = c.P;
-        while (c.P % cpc) --cpc;
+    // each, so a CTA does classes_per_cta x the work per prologue/epilogue and writes one contiguous run of the
+    // s2d output row.  Single launches may fill all 512 TMEM columns; dual launches (see want_dual) stop at 256,
+    // and split further while the longest CTA (classes are unequal: 1..2^d taps) would outlast an even share of
+    // the whole layer over the 2 x SM slots.
+    const int m_tiles = (int)((m_total + kBM - 1) / kBM);
+    auto classes_per_cta = [&](int max_cols) {
+        int v = 1;
+        if (bn == cout && c.P > 1) {
+            v = max_cols / cout;
+            if (v > c.P) v = c.P;
+            if (v < 1) v = 1;
+            while (c.P % v) --v;
+        }
+        return v;
+    };
+    auto longest_taps = [&](int per) {          // taps of the heaviest group when `per` consecutive classes share a CTA
+        int best = 0, cur_g = -1, cur_n = 0;
+        for_each_class_tap(c, [&](int cls, int, int, int, int) {
+            const int g = cls / per;
+            if (g != cur_g) { cur_g = g; cur_n = 0; }
+            ++cur_n;
+            if (cur_n > best) best = cur_n;
+        });
+        return best;
+    };
+    int cpc = classes_per_cta(512);
+    {
+        int cd = classes_per_cta(256);
+        const int stage_bytes = kBM * 128 + bn * 128;
+        const double fair = (double)m_tiles * (cout / bn) * c.taps / (2.0 * sm_count());     // taps per slot, evenly spread
+        while (cd > 1 && longest_taps(cd) > fair && c.P % (cd / 2) == 0) cd /= 2;
+        if (want_dual(stage_bytes, longest_taps(cd) * (cin / kBK), cd * bn)) cpc = cd;
     }
     p.epi_cols = cpc * bn;
     p.num_groups = c.P / cpc;
@@ -721,7 +788,6 @@ extern "C" int hg_convt_fwd(const void *x, const void *w_fwd, const float *bias,
         p.groups[g].tap_count++;
         ntap++;
     });
-    const int m_tiles = (int)((m_total + kBM - 1) / kBM);
     return launch_tap_gemm(p, m_tiles, cout / bn, static_cast<cudaStream_t>(stream), "hg_convt_fwd");
 }
 
@@ -732,7 +798,9 @@ extern "C" int hg_convt_dgrad(const void *dy_s2d, const void *w_dgrad, void *dx,
     ConvShape c{batch, cin, cout, ndim, size, kernel};
     int rc = conv_shape(c, "hg_convt_dgrad");
     if (rc) return rc;
-    const int bn = pick_bn(cin);
+    const long long m_total = (long long)batch * c.X * c.Y * c.Z;
+    const int m_tiles = (int)((m_total + kBM - 1) / kBM);
+    const int bn = pick_bn_for_grid(cin, m_tiles);
     HG_REQUIRE(cout % kBK == 0 && bn >= 16, HG_ERR_UNSUPPORTED, "hg_convt_dgrad: need Cout %% 64 == 0 and Cin %% 16 == 0 (got %d, %d)", cout, cin);
     TapGemmParams p{};
     int bx, by, bz, bb;
@@ -743,7 +811,6 @@ extern "C" int hg_convt_dgrad(const void *dy_s2d, const void *w_dgrad, void *dx,
     if (rc) return rc;
     p.X = c.X; p.Y = c.Y; p.Z = c.Z; p.Bn = batch;
     p.BN = bn; p.epi_cols = bn; p.bias_mod = cin; p.k_chunks = cout / kBK;
-    const long long m_total = (long long)batch * c.X * c.Y * c.Z;
     p.m_total = (int)m_total; p.ld_out = cin; p.out = dx; p.bias = nullptr; p.slope = 1.0f;
     p.num_groups = 1;
     int ntap = 0;
@@ -752,7 +819,6 @@ extern "C" int hg_convt_dgrad(const void *dy_s2d, const void *w_dgrad, void *dx,
         p.taps[ntap++] = Tap{(int16_t)-sx, (int16_t)-sy, (int16_t)-sz, 0, cls * cout, flat * cin};   // one accumulator
     });
     p.groups[0] = Group{0, ntap, 0, 0};
-    const int m_tiles = (int)((m_total + kBM - 1) / kBM);
     return launch_tap_gemm(p, m_tiles, cin / bn, static_cast<cudaStream_t>(stream), "hg_convt_dgrad");
 }
 

@@ -565,6 +565,9 @@ __global__ void __launch_bounds__(1024) rotate_adjoint_table_kernel(const float 
     __shared__ uint32_t kblk[NBLK + 1];
     const IlWsLayout lay = il_ws_layout(N);
     const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5, nwarps = blockDim.x >> 5;
+    // gridDim.y CTAs share a sample: steps a-d are cheap and recomputed by each (identical results, identical
+    // header), the fill (step e, the scattered global stores) is split between them by warp.
+    const int part = blockIdx.y, nparts = gridDim.y;
     unsigned char *wsb = ws + (size_t)b * ws_stride;
     uint32_t *hdr = reinterpret_cast<uint32_t *>(wsb + lay.hdr_off);
     if (!il_neighbour_rank_ok(a_inv + b * 16)) {         // flag 0: left to the counting-sort kernel
@@ -658,7 +661,7 @@ __global__ void __launch_bounds__(1024) rotate_adjoint_table_kernel(const float 
     if (t == 0) hdr[NBLK + 1] = fits ? 1u : 0u;                      // 0: rows overflow -> counting-sort kernel + cell walk
     if (!fits) return;
     // ---- e. fill ----------------------------------------------------------------------------------------
-    for (int j = warp; j < NBLK; j += nwarps) {
+    for (int j = warp * nparts + part; j < NBLK; j += nwarps * nparts) {
         int sx, sy, sz;
         il_block_voxel(j, lane, S, LOGS, sx, sy, sz);
         const int s = (((sz << LOGS) + sy) << LOGS) + sx;
@@ -667,6 +670,7 @@ __global__ void __launch_bounds__(1024) rotate_adjoint_table_kernel(const float 
 #pragma unroll
     for (int k = 0; k < PER; ++k) {
         const int o = t + k * 1024;
+        if ((warp + k) % nparts != part) continue;
         if (o < N && cq[k] >= 0) {
             const int q = cq[k];
             const int qx = q & (S - 1), qy = (q >> LOGS) & (S - 1), qz = q >> (2 * LOGS);
@@ -835,6 +839,112 @@ __global__ void __launch_bounds__(NT) rotate_bwd_il_kernel(const T *__restrict__
 }
 
 // -------------------------------------------------------------------------------------------------
+// Channels-last backward (bf16 pipeline: grad_out NDHWC or PROJ rows of C channels -> grad_vol NDHWC), driven by
+// the same adjoint tables.  C/8 lanes own one source voxel (16 bytes each); a voxel's k-th table entry names
+// the output row to fetch (one coalesced C*2-byte line for the lane group) and its weight, so the dependent
+// chain is entry -> line instead of the cell table's start -> item -> coordinates -> line, the trip count is
+// uniform per 32-voxel block, and four entries / four lines are in flight per thread.
+// -------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int il_out_row(int o, int logS, int out_layout)
+{
+    if (out_layout != HG_PROJ) return o;
+    const int S = 1 << logS;
+    const int x = o & (S - 1), y = (o >> logS) & (S - 1), z = o >> (2 * logS);
+    return (((z << logS) + x) << logS) + y;          // [z][x][y]
+}
+
+template <int LOGS>
+__global__ void __launch_bounds__(256) rotate_cl_bwd_ell_kernel(const __nv_bfloat16 *__restrict__ grad_out,
+                                                                const float *__restrict__ a_inv,
+                                                                const unsigned char *__restrict__ ws, size_t ws_stride,
+                                                                __nv_bfloat16 *__restrict__ grad_vol, int C, int out_layout,
+                                                                int voxels_per_cta)
+{
+    constexpr int S = 1 << LOGS, N = S * S * S, NBLK = N / 32;
+    const IlWsLayout lay = il_ws_layout(N);
+    __shared__ float m[12];
+    const int b = blockIdx.y;
+    if (threadIdx.x < 12) m[threadIdx.x] = a_inv[b * 16 + threadIdx.x];
+    __syncthreads();
+    const int lanes = C >> 3;                           // threads per voxel (power of two <= 32)
+    const int sub = threadIdx.x % lanes;
+    const int vslot = threadIdx.x / lanes, vstep = blockDim.x / lanes;
+    const unsigned char *wsb = ws + (size_t)b * ws_stride;
+    const uint32_t *hdr = reinterpret_cast<const uint32_t *>(wsb + lay.hdr_off);
+    const uint32_t *rows = reinterpret_cast<const uint32_t *>(wsb + lay.ell_off);
+    const __nv_bfloat16 *gb = grad_out + (size_t)b * N * C + sub * 8;
+    __nv_bfloat16 *db = grad_vol + (size_t)b * N * C + sub * 8;
+    const bool table = __ldg(hdr + NBLK + 1) != 0u;
+    const int v_end = min(N, (int)(blockIdx.x + 1) * voxels_per_cta);
+    // voxel slots in block-major order: slot = 32 * j + l  (block j, lane l of the table rows)
+    for (int slot = blockIdx.x * voxels_per_cta + vslot; slot < v_end; slot += vstep) {
+        const int j = slot >> 5, l = slot & 31;
+        int sx, sy, sz;
+        il_block_voxel(j, l, S, LOGS, sx, sy, sz);
+        const int s = (((sz << LOGS) + sy) << LOGS) + sx;
+        float acc[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[c] = 0.f;
+        if (table) {
+            const uint32_t r0 = __ldg(hdr + j), k = __ldg(hdr + j + 1) - r0;
+            const uint32_t *rp = rows + (size_t)r0 * 32 + l;
+            for (uint32_t i0 = 0; i0 < k; i0 += 4) {                 // uniform over the lane group (and the block)
+                uint32_t e[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) e[i] = i0 + i < k ? __ldg(rp + (size_t)(i0 + i) * 32) : 0u;
+                uint4 raw[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int o = il_unit((int)(e[i] & 0xfffu), LOGS);        // the hash is an involution
+                    raw[i] = __ldg(reinterpret_cast<const uint4 *>(gb + (size_t)il_out_row(o, LOGS, out_layout) * C));
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float w = (float)(e[i] >> 12) * (1.0f / kEllScale);
+                    float f[8];
+                    IlUnit<__nv_bfloat16>::unpack(raw[i], f);
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) acc[c] = fmaf(w, f[c], acc[c]);
+                }
+            }
+        } else {
+            // fallback (table overflow: strongly shrinking views): walk the cell table, recompute the weights
+            const uint16_t *start = reinterpret_cast<const uint16_t *>(wsb + lay.cells_off);
+            const uint16_t *items = start + N + 8;
+#pragma unroll 1
+            for (int d = 0; d < 8; ++d) {
+                const int dx = d & 1, dy = (d >> 1) & 1, dz = d >> 2;
+                const int qx = sx - dx, qy = sy - dy, qz = sz - dz;
+                if (qx < 0 || qy < 0 || qz < 0 || qx > S - 2 || qy > S - 2 || qz > S - 2) continue;
+                const int q = (((qz << LOGS) + qy) << LOGS) + qx;
+                const int lo = __ldg(start + q), hi = __ldg(start + q + 1);
+                for (int i = lo; i < hi; ++i) {
+                    const int o = __ldg(items + i);
+                    float x, y, z;
+                    il_coords(m, o & (S - 1), (o >> LOGS) & (S - 1), o >> (2 * LOGS), x, y, z);
+                    const float wx = dx ? __fsub_rn(x, (float)qx) : __fsub_rn((float)(qx + 1), x);
+                    const float wy = dy ? __fsub_rn(y, (float)qy) : __fsub_rn((float)(qy + 1), y);
+                    const float wz = dz ? __fsub_rn(z, (float)qz) : __fsub_rn((float)(qz + 1), z);
+                    const float w = __fmul_rn(__fmul_rn(wx, wy), wz);
+                    float f[8];
+                    IlUnit<__nv_bfloat16>::unpack(
+                        __ldg(reinterpret_cast<const uint4 *>(gb + (size_t)il_out_row(o, LOGS, out_layout) * C)), f);
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) acc[c] = fmaf(w, f[c], acc[c]);
+                }
+            }
+        }
+        uint32_t pk[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            __nv_bfloat162 h = __floats2bfloat162_rn(acc[2 * c], acc[2 * c + 1]);
+            pk[c] = *reinterpret_cast<uint32_t *>(&h);
+        }
+        st_stream_16(db + (size_t)s * C, make_uint4(pk[0], pk[1], pk[2], pk[3]));
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
 // host side
 // -------------------------------------------------------------------------------------------------
 
@@ -910,32 +1020,58 @@ int hg_rotate_il_fwd(const void *vol, const float *a_inv, void *out, int batch, 
 #undef HG_IL_FWD
 }
 
+// Per-sample adjoint tables (views only; shared by every channel group / layout).  The sort-free kernel runs first,
+// two CTAs per sample; the counting-sort kernel only proceeds for samples it declined.
+static int il_build_tables(const float *a_inv, unsigned char *ws, const IlWsLayout &lay, int batch, int logS, cudaStream_t st)
+{
+    const int n = 1 << (3 * logS);
+    const size_t smem_fast = (size_t)n * 2 * 2 + (size_t)n * 8;
+    const size_t smem_sort = (size_t)(3 * n + 2) * sizeof(uint32_t) + (size_t)n * 8;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(rotate_adjoint_table_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        cudaFuncSetAttribute(rotate_adjoint_table_sort_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        attr_done = true;
+    }
+    const int parts = 2 * batch <= 2 * sm_count() ? 2 : 1;
+    if (logS == 4) {
+        rotate_adjoint_table_kernel<4><<<dim3(batch, parts), 1024, smem_fast, st>>>(a_inv, ws, lay.per_sample);
+        rotate_adjoint_table_sort_kernel<4><<<batch, 1024, smem_sort, st>>>(a_inv, ws, lay.per_sample);
+    } else {
+        rotate_adjoint_table_kernel<3><<<dim3(batch, parts), 1024, smem_fast, st>>>(a_inv, ws, lay.per_sample);
+        rotate_adjoint_table_sort_kernel<3><<<batch, 512, smem_sort, st>>>(a_inv, ws, lay.per_sample);
+    }
+    return check_launch("rotate_adjoint_table");
+}
+
+// channels-last (bf16) adjoint: called from rotate_cl.cu's dispatcher
+int hg_rotate_cl_bwd_table_impl(const void *grad_out, const float *a_inv, void *grad_vol, void *workspace, int batch,
+                                int channels, int size, int logS, int out_layout, cudaStream_t st)
+{
+    const int n = size * size * size;
+    const IlWsLayout lay = il_ws_layout(n);
+    unsigned char *ws = static_cast<unsigned char *>(workspace);
+    int rc = il_build_tables(a_inv, ws, lay, batch, logS, st);
+    if (rc) return rc;
+    const int vpc = n >= 4096 ? 512 : n;                  // source voxels per CTA: 16 table blocks = one z-pair slab at 16^3
+    dim3 grid((n + vpc - 1) / vpc, batch);
+    const __nv_bfloat16 *g = static_cast<const __nv_bfloat16 *>(grad_out);
+    __nv_bfloat16 *gv = static_cast<__nv_bfloat16 *>(grad_vol);
+    if (logS == 4)
+        rotate_cl_bwd_ell_kernel<4><<<grid, 256, 0, st>>>(g, a_inv, ws, lay.per_sample, gv, channels, out_layout, vpc);
+    else
+        rotate_cl_bwd_ell_kernel<3><<<grid, 256, 0, st>>>(g, a_inv, ws, lay.per_sample, gv, channels, out_layout, vpc);
+    return check_launch("rotate_cl_bwd_ell");
+}
+
 int hg_rotate_il_bwd(const void *grad_out, const float *a_inv, void *grad_vol, void *workspace, int batch, int channels,
                      int size, int logS, int dtype, int border, cudaStream_t st)
 {
     const int n = size * size * size;
     const IlWsLayout lay = il_ws_layout(n);
     unsigned char *ws = static_cast<unsigned char *>(workspace);
-    {
-        // sort-free table kernel first; the counting-sort kernel only proceeds for samples it declined
-        const size_t smem_fast = (size_t)n * 2 * 2 + (size_t)n * 8;
-        const size_t smem_sort = (size_t)(3 * n + 2) * sizeof(uint32_t) + (size_t)n * 8;
-        static bool attr_done = false;
-        if (!attr_done) {
-            cudaFuncSetAttribute(rotate_adjoint_table_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-            cudaFuncSetAttribute(rotate_adjoint_table_sort_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-            attr_done = true;
-        }
-        if (logS == 4) {
-            rotate_adjoint_table_kernel<4><<<batch, 1024, smem_fast, st>>>(a_inv, ws, lay.per_sample);
-            rotate_adjoint_table_sort_kernel<4><<<batch, 1024, smem_sort, st>>>(a_inv, ws, lay.per_sample);
-        } else {
-            rotate_adjoint_table_kernel<3><<<batch, 1024, smem_fast, st>>>(a_inv, ws, lay.per_sample);
-            rotate_adjoint_table_sort_kernel<3><<<batch, 512, smem_sort, st>>>(a_inv, ws, lay.per_sample);
-        }
-        int rc = check_launch("rotate_adjoint_table");
-        if (rc) return rc;
-    }
+    int rc = il_build_tables(a_inv, ws, lay, batch, logS, st);
+    if (rc) return rc;
     const bool big = (border & HG_TUNE_CTA1024) != 0;
 #define HG_IL_BWD(T, L, NT) launch_bwd_il<T, L, NT>(grad_out, a_inv, ws, lay.per_sample, grad_vol, batch, channels, st)
     if (dtype == HG_F32) {

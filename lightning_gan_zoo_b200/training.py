@@ -89,6 +89,36 @@ class _FlatGrads:
             self.flat.div_(world)
 
 
+class PendingLoss:
+    """Loss of a step launched by `HologanTrainer.step_host`: the value lands in pinned host memory through an
+    asynchronous device-to-host copy; `item()` waits for that copy only."""
+
+    def __init__(self, buf: torch.Tensor, event):
+        self._buf, self._event = buf, event
+
+    def item(self) -> float:
+        self._event.synchronize()
+        return float(self._buf[0])
+
+    __float__ = item
+
+
+class _FeedSlot:
+    """Pinned host staging + device staging buffers of one in-flight step."""
+
+    def __init__(self, batch, channels, size, noise_dim, device):
+        self.real_pin = torch.empty(batch, channels, size, size).pin_memory()
+        self.z_pin = torch.empty(batch, noise_dim).pin_memory()
+        self.a_pin = torch.empty(batch, 4, 4).pin_memory()
+        self.loss_pin = torch.zeros(1).pin_memory()
+        self.real_dev = torch.empty(batch, channels, size, size, device=device)
+        self.z_dev = torch.empty(batch, noise_dim, device=device)
+        self.a_dev = torch.empty(batch, 4, 4, device=device)
+        self.ready = torch.cuda.Event()      # H2D copies of this slot finished (recorded on the copy stream)
+        self.done = torch.cuda.Event()       # the step consumed the device staging buffers and wrote the loss
+        self.done.record()
+
+
 class HologanTrainer:
     def __init__(self, cfg: Optional[HologanConfig] = None, device="cuda", compute_dtype=torch.bfloat16,
                  rank: int = 0, world_size: int = 1, seed: int = 42):
@@ -190,6 +220,44 @@ class HologanTrainer:
         if self._graphs is not None and n == self._static["real"].shape[0]:
             return self._replay(real, z, view, idx)
         return self._eager_step(real, z, view, idx)
+
+    def step_host(self, real: torch.Tensor, batch_idx: int, z: Optional[torch.Tensor] = None, view=None) -> PendingLoss:
+        """`step` for HOST inputs, pipelined: the inputs go through pinned memory and a copy stream into device
+        staging buffers (so the transfer of step i overlaps the kernels of step i-1), the step runs on the current
+        stream, and the loss comes back through an asynchronous D2H copy -- read it with `.item()` whenever it is
+        needed (reading the previous step's loss after launching the next one keeps the GPU busy).  Two slots
+        alternate; a slot is reused only after the step that used it has finished."""
+        if self.device.type != "cuda":
+            raise RuntimeError("step_host needs a CUDA device (the B200 path has no CPU fallback)")
+        n = real.shape[0]
+        if z is None:
+            z = self.sample_noise(n)
+        if view is None:
+            view = self.sample_view(n)
+        a = view if isinstance(view, torch.Tensor) and view.dim() == 3 else ops.view_to_affine(view, 16, 16)
+        feeds = getattr(self, "_feeds", None)
+        if feeds is None or feeds[0].real_pin.shape[0] != n:
+            feeds = self._feeds = [_FeedSlot(n, self.cfg.channels_img, self.cfg.img_size, self.cfg.noise_dim, self.device)
+                                   for _ in range(2)]
+            self._feed_next = 0
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        slot = feeds[self._feed_next]
+        self._feed_next ^= 1
+        slot.done.synchronize()                               # normally long finished: the caller lags one step at most
+        src_real = real if real.is_pinned() else slot.real_pin.copy_(real)
+        slot.z_pin.copy_(z)
+        slot.a_pin.copy_(a)
+        cur = torch.cuda.current_stream(self.device)
+        with torch.cuda.stream(self._copy_stream):
+            slot.real_dev.copy_(src_real, non_blocking=True)
+            slot.z_dev.copy_(slot.z_pin, non_blocking=True)
+            slot.a_dev.copy_(slot.a_pin, non_blocking=True)
+            slot.ready.record(self._copy_stream)
+        cur.wait_event(slot.ready)
+        loss = self.step(slot.real_dev, batch_idx, z=slot.z_dev, view=slot.a_dev)
+        slot.loss_pin.copy_(loss.detach().reshape(1), non_blocking=True)
+        slot.done.record(cur)
+        return PendingLoss(slot.loss_pin, slot.done)
 
     def _eager_step(self, real, z, view, idx):
         grads, opt = (self.d_grads, self.opt_d) if idx == 0 else (self.g_grads, self.opt_g)

@@ -47,7 +47,29 @@ def test_rotate_channels_last_forward(b, c, s, border):
     assert rel_err(fold_from_mine, fold) < 2 ** -7
 
 
-@pytest.mark.parametrize("b,c,s", [(4, 64, 16), (3, 16, 8), (2, 128, 16)])
+@pytest.mark.parametrize("scale", [0.5, 1.6, 2.5])
+@pytest.mark.parametrize("c,s", [(64, 16), (8, 8), (256, 16)])
+def test_rotate_channels_last_backward_scaled_views(scale, c, s):
+    """Scaled / shifted views: long adjoint-table rows, and (scale 2.5) tables that overflow the workspace, which
+    sends the sample down the cell-walk fallback of the channels-last backward."""
+    b = 3
+    gen = torch.Generator().manual_seed(int(scale * 10) + c)
+    g_nc = torch.randn(b, c, s, s, s, generator=gen).to(BF)
+    v = orc.sample_view(b, np.random.RandomState(c))
+    v[:, 2] = scale
+    v[1:, 3:6] = np.random.RandomState(5).uniform(-2, 2, (b - 1, 3))
+    a = ops.view_to_affine(v, s, s).to(DEV)
+    g_cl = g_nc.permute(0, 2, 3, 4, 1).contiguous().to(DEV)
+    gv = ops.rotate_bwd_raw(g_cl, a, c, s, ops.HG_BORDER_ZERO, ops.HG_NDHWC, ops.HG_NDHWC)
+    vz = torch.zeros(b, c, s, s, s, requires_grad=True)
+    (orc.rotate_resample(vz, a_inv=a.cpu()) * g_nc.float()).sum().backward()
+    assert rel_err(gv.permute(0, 4, 1, 2, 3).float(), vz.grad) < 2 ** -7
+    # and the NCDHW bf16 kernel, which consumes the same tables, agrees to rounding
+    gv_nc = ops.rotate_bwd_raw(g_nc.to(DEV), a, c, s, ops.HG_BORDER_ZERO)
+    assert rel_err(gv.permute(0, 4, 1, 2, 3).float(), gv_nc.float()) < 2 ** -7
+
+
+@pytest.mark.parametrize("b,c,s", [(4, 64, 16), (3, 16, 8), (2, 128, 16), (3, 8, 16), (2, 256, 16)])
 @pytest.mark.parametrize("out_layout", [ops.HG_NDHWC, ops.HG_PROJ])
 def test_rotate_channels_last_backward(b, c, s, out_layout):
     gen = torch.Generator().manual_seed(c * 3 + s)

@@ -99,3 +99,34 @@ def test_cuda_graph_step_matches_eager():
     # weight matrices only: biases start at 0 and Adam moves them by +-lr per step whatever the (noisy) gradient
     worst = max(rel_err(pb, pa) for pa, pb in zip(a.generator.parameters(), b.generator.parameters()) if pa.dim() > 1)
     assert worst < 5e-2
+
+
+@pytest.mark.parametrize("graphs", [False, True])
+def test_step_host_matches_step(graphs):
+    """The pipelined host-input entry (pinned staging, copy stream, asynchronous loss read-back) runs the same
+    step as `step` on device-resident inputs: same losses, read one step late, and same weights afterwards."""
+    cfg = HologanConfig(batch_size=8)
+    a = HologanTrainer(cfg, device=DEV, seed=5)
+    b = HologanTrainer(cfg, device=DEV, seed=5)
+    if graphs:
+        a.enable_cuda_graphs(8)
+        b.enable_cuda_graphs(8)
+    gen = torch.Generator().manual_seed(1)
+    ref, got, pend = [], [], None
+    for i in range(7):
+        real = torch.rand(8, 3, 64, 64, generator=gen) * 2 - 1
+        if i % 2:
+            real = real.pin_memory()
+        z = torch.rand(8, 128, generator=gen) * 2 - 1
+        view = orc.sample_view(8, np.random.RandomState(i))
+        ref.append(a.step(real.to(DEV), i, z=z.to(DEV), view=view).item())
+        nxt = b.step_host(real, i, z=z, view=view)
+        if pend is not None:
+            got.append(pend.item())
+        pend = nxt
+    got.append(float(pend))
+    # same kernels on the same inputs (cuDNN's discriminator kernels may reorder their reductions between runs)
+    for r, g in zip(ref, got):
+        assert abs(r - g) < 5e-3 * max(1.0, abs(r)), (ref, got)
+    worst = max(rel_err(pb, pa) for pa, pb in zip(a.generator.parameters(), b.generator.parameters()) if pa.dim() > 1)
+    assert worst < 5e-2
