@@ -197,6 +197,20 @@ int hg_final_conv_tanh_bwd(const void *x, const float *w, const float *out, cons
                            float *dbias, void *workspace, long long workspace_bytes, int batch, int cin, int cout, int size,
                            void *stream);
 
+/* ---- a13: the losses of HOLOGAN.training_step  (core/lightning_module.py:217-237) -------------------
+ *   adv = wa * mean_i BCEWithLogits(a[i], ta) + wb * mean_j BCEWithLogits(b[j], tb)   (b may be NULL, nb = 0)
+ *   q   = mean_k (zp[k] - z[k])^2
+ *   total[0] = adv + q;  parts[0] = adv, parts[1] = q.
+ * D step (:219-229): a = D(real) logits, ta = 1, wa = 0.5, b = D(fake) logits, tb = 0, wb = 0.5.
+ * G step (:231-237): a = D(fake) logits, ta = 1, wa = 1, nb = 0.
+ * a, b, zp have `dtype` (HG_F32 / HG_BF16), z is fp32; arithmetic in fp32, fixed summation order.
+ * backward: da, db, dzp (same dtype / sizes as a, b, zp) = d total / d(.) * gout[0]  (gout: device fp32 scalar,
+ * NULL = 1). */
+int hg_gan_loss_fwd(const void *a, int na, float ta, float wa, const void *b, int nb, float tb, float wb, const void *zp,
+                    const float *z, int nz, int dtype, float *total, float *parts, void *stream);
+int hg_gan_loss_bwd(const float *gout, const void *a, int na, float ta, float wa, const void *b, int nb, float tb, float wb,
+                    const void *zp, const float *z, int nz, int dtype, void *da, void *db, void *dzp, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -37,14 +37,18 @@ class ZMapping(nn.Module):
         nn.init.normal_(self.linear1.weight, std=0.02)
         nn.init.zeros_(self.linear1.bias)
 
-    def forward(self, x):
+    def style(self, x):
+        """The packed (B, 2C) output [scale | bias]: the AdaIN kernels read both halves in place, so the hot path
+        never slices it (two slices cost two zero-fills + two copies + an add in autograd's backward)."""
         # the style path stays fp32 even under autocast: it is 0.01 % of the FLOPs and every activation
         # of the block is scaled by it
         if x.is_cuda:
-            style = ops.linear_relu(x, self.linear1.weight, self.linear1.bias)       # fp32 SIMT kernel
-        else:
-            with torch.autocast(x.device.type, enabled=False):
-                style = F.relu(F.linear(x.float(), self.linear1.weight, self.linear1.bias))
+            return ops.linear_relu(x, self.linear1.weight, self.linear1.bias)        # fp32 SIMT kernel
+        with torch.autocast(x.device.type, enabled=False):
+            return F.relu(F.linear(x.float(), self.linear1.weight, self.linear1.bias))
+
+    def forward(self, x):
+        style = self.style(x)
         c = self.output_channel
         return style[:, :c], style[:, c:]
 
@@ -72,8 +76,7 @@ class BasicBlock(nn.Module):
 
     def forward(self, h, z):
         h = self.convTranspose(h)
-        scale, bias = self.zMapping(z)
-        return ops.adain_act(h, scale, bias, neg_slope=0.0)      # AdaIN + ReLU in one pass
+        return ops.adain_act(h, self.zMapping.style(z), None, neg_slope=0.0)      # AdaIN + ReLU in one pass
 
 
 class Generator(nn.Module):
@@ -149,13 +152,11 @@ class Generator(nn.Module):
         unchanged and their gradient is identically zero (the reference only holds rounding noise there)."""
         bf16 = torch.bfloat16
         n = z.shape[0]
-        s0, b0 = self.zMapping(z)
-        h0 = ops.adain_act(self.x, s0, b0, neg_slope=0.0)                        # (B,8P,4,4,4) fp32, NC*
+        h0 = ops.adain_act(self.x, self.zMapping.style(z), None, neg_slope=0.0)  # (B,8P,4,4,4) fp32, NC*
         h = ops.nc_to_channels_last(h0.to(bf16))                                 # (B,4,4,4,8P)
         for block in (self.block1, self.block2):
             y = ops.convt(h, block.convTranspose.weight, None, 3, 3)             # (B,S,S,S,8,Cout) s2d
-            sc, bi = block.zMapping(z)
-            h = ops.adain_act_channels_last(y, sc, bi, ndim=3, classes=8)        # (B,2S,2S,2S,Cout) NDHWC
+            h = ops.adain_act_channels_last(y, block.zMapping.style(z), None, ndim=3, classes=8)   # (B,2S,2S,2S,Cout) NDHWC
         size = h.shape[1]
         a_inv = self._affine(view_in, size, size, z.device)
         # rotate + fold depth into channels in one kernel: out[b, z, x, (y, c)] is the projection's A operand
@@ -169,8 +170,7 @@ class Generator(nn.Module):
         h = h.reshape(n, size, size, -1)
         for block in (self.block3, self.block4):
             y = ops.convt(h, block.convTranspose.weight, None, 2, 4)             # (B,S,S,4,Cout) s2d
-            sc, bi = block.zMapping(z)
-            h = ops.adain_act_channels_last(y, sc, bi, ndim=2, classes=4)        # (B,2S,2S,Cout) NHWC
+            h = ops.adain_act_channels_last(y, block.zMapping.style(z), None, ndim=2, classes=4)   # (B,2S,2S,Cout) NHWC
         if self.img_size == 64 and ops.final_conv_supported(h.shape[-1], self.final_layer.weight.shape[0]):
             return ops.final_conv_tanh(h, self.final_layer.weight, self.final_layer.bias)   # direct conv + tanh, fp32 out
         # patched-128 head (ConvTranspose2d k4 s2): cuDNN on the NHWC buffer viewed as channels_last NCHW
@@ -183,8 +183,7 @@ class Generator(nn.Module):
         if self._use_tensor_core_path(z):
             return self._forward_tensor_core(z, view_in)
 
-        s0, b0 = self.zMapping(z)
-        h0 = ops.adain_act(self.x, s0, b0, neg_slope=0.0)            # constant never repeated B times
+        h0 = ops.adain_act(self.x, self.zMapping.style(z), None, neg_slope=0.0)      # constant never repeated B times
         h1 = self.block1(h0, z)
         h2 = self.block2(h1, z)
 

@@ -190,6 +190,25 @@ def _style_stride(scale: Tensor, bias: Tensor) -> int:
     return scale.stride(0)
 
 
+def _style_ptrs(scale: Tensor, bias: Optional[Tensor], channels: int):
+    """(scale pointer, bias pointer, row stride).  `bias is None` means `scale` is a packed ZMapping output
+    (B, 2C) = [scale | bias] (reference hologan_generator.py:17-18 slices it): both halves are read in place."""
+    if bias is not None:
+        return _ptr(scale), _ptr(bias), _style_stride(scale, bias)
+    if scale.dtype != torch.float32 or scale.dim() != 2 or scale.shape[1] != 2 * channels or not scale.is_contiguous():
+        raise ValueError("packed style must be a contiguous fp32 (B, 2C) tensor")
+    return _ptr(scale), ctypes.c_void_p(scale.data_ptr() + 4 * channels), 2 * channels
+
+
+def _dstyle_ptrs(packed: bool, b: int, c: int, device):
+    """Gradient buffers for the styles: one (B, 2C) tensor for a packed style, else a (2, B, C) pair."""
+    if packed:
+        d = torch.empty((b, 2 * c), dtype=torch.float32, device=device)
+        return d, _ptr(d), ctypes.c_void_p(d.data_ptr() + 4 * c), 2 * c
+    d = torch.empty((2, b, c), dtype=torch.float32, device=device)
+    return d, _ptr(d[0]), _ptr(d[1]), c
+
+
 class _AdaInAct(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, scale, bias, neg_slope, eps, biased):
@@ -197,33 +216,37 @@ class _AdaInAct(torch.autograd.Function):
         if not x.is_contiguous():
             x = x.contiguous()
         b, c, n, xbs = _adain_dims(x, scale)
-        sbs = _style_stride(scale, bias)
+        sp, bp, sbs = _style_ptrs(scale, bias, c)
         y = torch.empty((b,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
         mean = torch.empty((b, c), dtype=torch.float32, device=x.device)
         rstd = torch.empty((b, c), dtype=torch.float32, device=x.device)
-        _lib.call("hg_adain_act_fwd", _ptr(x), _ptr(scale), _ptr(bias), _ptr(y), _ptr(mean), _ptr(rstd), b, c, n, xbs,
+        _lib.call("hg_adain_act_fwd", _ptr(x), sp, bp, _ptr(y), _ptr(mean), _ptr(rstd), b, c, n, xbs,
                   sbs, float(eps), float(neg_slope), int(biased), _dtype_code(x), _stream())
         ctx.save_for_backward(x, scale, bias, mean, rstd)
-        ctx.meta = (b, c, n, xbs, sbs, float(neg_slope), int(biased))
+        ctx.meta = (b, c, n, xbs, float(neg_slope), int(biased))
         return y
 
     @staticmethod
     def backward(ctx, dy):
         x, scale, bias, mean, rstd = ctx.saved_tensors
-        b, c, n, xbs, sbs, neg_slope, biased = ctx.meta
+        b, c, n, xbs, neg_slope, biased = ctx.meta
+        sp, bp, sbs = _style_ptrs(scale, bias, c)
         dy = dy.contiguous()
         dx = torch.empty_like(x)
-        dsb = torch.empty((2, b, c), dtype=torch.float32, device=x.device)
-        _lib.call("hg_adain_act_bwd", _ptr(x), _ptr(dy), _ptr(scale), _ptr(bias), _ptr(mean), _ptr(rstd), _ptr(dx),
-                  _ptr(dsb[0]), _ptr(dsb[1]), b, c, n, xbs, sbs, c, neg_slope, biased, _dtype_code(x), _stream())
+        dsb, dsp, dbp, dstride = _dstyle_ptrs(bias is None, b, c, x.device)
+        _lib.call("hg_adain_act_bwd", _ptr(x), _ptr(dy), sp, bp, _ptr(mean), _ptr(rstd), _ptr(dx),
+                  dsp, dbp, b, c, n, xbs, sbs, dstride, neg_slope, biased, _dtype_code(x), _stream())
+        if bias is None:
+            return dx, dsb, None, None, None, None
         return dx, dsb[0], dsb[1], None, None, None
 
 
-def adain_act(x: Tensor, scale: Tensor, bias: Tensor, neg_slope: float = 0.0, eps: float = 1e-8,
+def adain_act(x: Tensor, scale: Tensor, bias: Optional[Tensor], neg_slope: float = 0.0, eps: float = 1e-8,
               biased_var: bool = False) -> Tensor:
     """act(AdaIn(x, scale, bias)); `neg_slope=1.0` gives the plain AdaIn of the reference
     (core/models/hologan_generator.py:333-345), `0.0` fuses the ReLU of :41 / :124.
-    x may have batch 1 (the learned constant): it is broadcast without being materialised."""
+    x may have batch 1 (the learned constant): it is broadcast without being materialised.
+    `bias=None`: `scale` is the packed (B, 2C) ZMapping output [scale | bias] -- no slices, one style gradient."""
     return _AdaInAct.apply(x, scale, bias, neg_slope, eps, biased_var)
 
 
@@ -259,9 +282,10 @@ def pack_convt_weight(weight: Tensor, perm: Tuple[int, int] = (0, 0)) -> Tuple[T
 
 
 def convt_wgrad(x_cl: Tensor, dy_s2d: Tensor, wshape, ndim: int, kernel: int, perm: Tuple[int, int] = (0, 0),
-                accumulate_into: Optional[Tensor] = None) -> Optional[Tensor]:
+                accumulate_into: Optional[Tensor] = None, overwrite: bool = False) -> Optional[Tensor]:
     """Weight gradient in the torch parameter layout (fp32).  With `accumulate_into` (a contiguous fp32 tensor of
-    the parameter's shape, e.g. its live .grad) the result is ADDED there and None is returned."""
+    the parameter's shape, e.g. its live .grad) the result is ADDED there (or, with `overwrite`, stored there) and
+    None is returned."""
     b, size, cin = x_cl.shape[0], x_cl.shape[1], x_cl.shape[-1]
     cout = dy_s2d.shape[-1]
     nbytes = _lib.load().hg_convt_wgrad_workspace_bytes(b, cin, cout, ndim, size, kernel)
@@ -269,12 +293,12 @@ def convt_wgrad(x_cl: Tensor, dy_s2d: Tensor, wshape, ndim: int, kernel: int, pe
         raise _lib.HologanB200Error(f"hg_convt_wgrad: unsupported shape Cin={cin} Cout={cout} size={size}")
     ws = torch.empty(nbytes, dtype=torch.uint8, device=x_cl.device)
     if accumulate_into is not None:
-        dw, acc = accumulate_into, 1
+        dw, acc = accumulate_into, (0 if overwrite else 1)
     else:
         dw, acc = torch.empty(tuple(wshape), dtype=torch.float32, device=x_cl.device), 0
     _lib.call("hg_convt_wgrad", _ptr(x_cl), _ptr(dy_s2d), _ptr(dw), _ptr(ws), nbytes, b, cin, cout, ndim, size, kernel,
               perm[0], perm[1], acc, _stream())
-    return None if acc else dw
+    return None if accumulate_into is not None else dw
 
 
 def act_bwd_bias(y: Tensor, dy: Tensor, neg_slope: float, want_bias: bool) -> Tuple[Tensor, Optional[Tensor]]:
@@ -298,16 +322,18 @@ def act_bwd_bias(y: Tensor, dy: Tensor, neg_slope: float, want_bias: bool) -> Tu
     return dpre, db
 
 
-def _direct_grad_target(param, shape) -> Optional[Tensor]:
-    """The parameter's live .grad if the owner opted in (`param._hg_direct_grad = True`, set by HologanTrainer
-    on its flat gradient buffers): the wgrad kernel then accumulates into it and autograd's extra
-    read-modify-write pass over the gradient is skipped."""
-    if param is None or not getattr(param, "_hg_direct_grad", False):
-        return None
-    g = param.grad
+def _direct_grad_target(param, shape) -> Tuple[Optional[Tensor], bool]:
+    """(buffer, overwrite): where the wgrad kernel may put the parameter's gradient itself, if the owner opted in.
+    `param._hg_direct_grad = True`: accumulate into the live .grad (autograd's extra read-modify-write pass over the
+    gradient is skipped).  `param._hg_direct_grad = <tensor>` (HologanTrainer: a view of its flat gradient buffer,
+    one backward per step): STORE the gradient there -- the buffer then needs no zero-fill either."""
+    mode = None if param is None else getattr(param, "_hg_direct_grad", None)
+    if mode is None or mode is False:
+        return None, False
+    g, overwrite = (param.grad, False) if mode is True else (mode, True)
     if g is None or g.dtype != torch.float32 or not g.is_contiguous() or tuple(g.shape) != tuple(shape):
-        return None
-    return g
+        return None, False
+    return g, overwrite
 
 
 def _conv_dims(x_cl: Tensor, ndim: int):
@@ -356,8 +382,8 @@ class _ConvT(torch.autograd.Function):
             dx = torch.empty_like(x_cl)
             _lib.call("hg_convt_dgrad", _ptr(dy), _ptr(wd), _ptr(dx), b, cin, cout, ndim, size, kernel, _stream())
         if ctx.needs_input_grad[1]:
-            dw = convt_wgrad(x_cl, dy, wshape, ndim, kernel, perm,
-                             accumulate_into=_direct_grad_target(ctx.weight_param, wshape))
+            target, overwrite = _direct_grad_target(ctx.weight_param, wshape)
+            dw = convt_wgrad(x_cl, dy, wshape, ndim, kernel, perm, accumulate_into=target, overwrite=overwrite)
         return dx, dw, db, None, None, None, None
 
 
@@ -395,7 +421,7 @@ class _AdaInChannelsLast(torch.autograd.Function):
         if x.dtype != torch.bfloat16 or not x.is_contiguous():
             raise ValueError("x must be a contiguous bf16 tensor")
         b, size, c = x.shape[0], x.shape[1], x.shape[-1]
-        sbs = _style_stride(scale, bias) if scale is not None else 0
+        sp, bp, sbs = _style_ptrs(scale, bias, c) if scale is not None else (_ptr(None), _ptr(None), 0)
         up = 2 if classes > 1 else 1
         y = torch.empty((b,) + (up * size,) * ndim + (c,), dtype=torch.bfloat16, device=x.device)
         mean = torch.empty((b, c), dtype=torch.float32, device=x.device)
@@ -404,31 +430,39 @@ class _AdaInChannelsLast(torch.autograd.Function):
         if nbytes < 0:
             raise _lib.HologanB200Error(f"hg_adain_cl_fwd: unsupported shape C={c} size={size} classes={classes}")
         ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device) if nbytes else None
-        _lib.call("hg_adain_cl_fwd", _ptr(x), _ptr(scale), _ptr(bias), _ptr(y), _ptr(mean), _ptr(rstd), _ptr(ws), nbytes, b, c,
+        _lib.call("hg_adain_cl_fwd", _ptr(x), sp, bp, _ptr(y), _ptr(mean), _ptr(rstd), _ptr(ws), nbytes, b, c,
                   ndim, size, classes, sbs, ctypes.c_float(eps), ctypes.c_float(neg_slope), int(biased), _stream())
         ctx.save_for_backward(x, scale, bias, mean, rstd)
-        ctx.meta = (b, c, ndim, size, classes, sbs, float(neg_slope), int(biased))
+        ctx.meta = (b, c, ndim, size, classes, float(neg_slope), int(biased))
         return y
 
     @staticmethod
     def backward(ctx, dy):
         x, scale, bias, mean, rstd = ctx.saved_tensors
-        b, c, ndim, size, classes, sbs, neg_slope, biased = ctx.meta
+        b, c, ndim, size, classes, neg_slope, biased = ctx.meta
         dy = dy.contiguous()
         dx = torch.empty_like(x)
-        dsb = torch.empty((2, b, c), dtype=torch.float32, device=x.device) if scale is not None else None
+        if scale is not None:
+            sp, bp, sbs = _style_ptrs(scale, bias, c)
+            dsb, dsp, dbp, dstride = _dstyle_ptrs(bias is None, b, c, x.device)
+        else:
+            sp = bp = dsp = dbp = _ptr(None)
+            dsb, sbs, dstride = None, 0, c
         nbytes = _lib.load().hg_adain_cl_workspace_bytes(b, c, ndim, size, classes)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device) if nbytes else None
-        _lib.call("hg_adain_cl_bwd", _ptr(x), _ptr(dy), _ptr(scale), _ptr(bias), _ptr(mean), _ptr(rstd), _ptr(dx),
-                  _ptr(None if dsb is None else dsb[0]), _ptr(None if dsb is None else dsb[1]), _ptr(ws), nbytes, b, c, ndim,
-                  size, classes, sbs, c, ctypes.c_float(neg_slope), biased, _stream())
+        _lib.call("hg_adain_cl_bwd", _ptr(x), _ptr(dy), sp, bp, _ptr(mean), _ptr(rstd), _ptr(dx),
+                  dsp, dbp, _ptr(ws), nbytes, b, c, ndim,
+                  size, classes, sbs, dstride, ctypes.c_float(neg_slope), biased, _stream())
         if dsb is None:
             return dx, None, None, None, None, None, None, None
+        if bias is None:
+            return dx, dsb, None, None, None, None, None, None
         return dx, dsb[0], dsb[1], None, None, None, None, None
 
 
-def adain_act_channels_last(x: Tensor, scale: Tensor, bias: Tensor, ndim: int, classes: int, neg_slope: float = 0.0,
-                            eps: float = 1e-8) -> Tensor:
+def adain_act_channels_last(x: Tensor, scale: Tensor, bias: Optional[Tensor], ndim: int, classes: int,
+                            neg_slope: float = 0.0, eps: float = 1e-8) -> Tensor:
+    """`bias=None`: `scale` is the packed (B, 2C) style [scale | bias] (see adain_act)."""
     return _AdaInChannelsLast.apply(x, scale, bias, ndim, classes, neg_slope, eps, False)
 
 
@@ -514,3 +548,54 @@ class _FinalConvTanh(torch.autograd.Function):
 def final_conv_tanh(x_cl: Tensor, weight: Tensor, bias: Tensor) -> Tensor:
     """tanh(conv2d(x, weight, bias, kernel 3, padding 1)) with x (B,S,S,C) bf16 NHWC -> (B,Cout,S,S) fp32 NCHW."""
     return _FinalConvTanh.apply(x_cl, weight, bias)
+
+
+# ------------------------------------------------------------------------------------------------
+# a13: the losses of HOLOGAN.training_step
+# ------------------------------------------------------------------------------------------------
+
+class _GanLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b, z_pred, z, ta, wa, tb, wb):
+        _require_cuda(a, b, z_pred, z)
+        a, z_pred = a.contiguous(), z_pred.contiguous()
+        b = None if b is None else b.contiguous()
+        z = z.float().contiguous()
+        if z_pred.dtype != a.dtype or (b is not None and b.dtype != a.dtype) or z_pred.numel() != z.numel():
+            raise ValueError("logits / z_pred must share a dtype; z_pred and z must have the same size")
+        total = torch.empty((), dtype=torch.float32, device=a.device)
+        parts = torch.empty(2, dtype=torch.float32, device=a.device)
+        nb = 0 if b is None else b.numel()
+        _lib.call("hg_gan_loss_fwd", _ptr(a), a.numel(), float(ta), float(wa), _ptr(b), nb, float(tb), float(wb),
+                  _ptr(z_pred), _ptr(z), z.numel(), _dtype_code(a), _ptr(total), _ptr(parts), _stream())
+        ctx.save_for_backward(a, b, z_pred, z)
+        ctx.meta = (float(ta), float(wa), float(tb), float(wb))
+        ctx.mark_non_differentiable(parts)
+        ctx.set_materialize_grads(False)
+        return total, parts
+
+    @staticmethod
+    def backward(ctx, gtotal, _gparts):
+        a, b, z_pred, z = ctx.saved_tensors
+        ta, wa, tb, wb = ctx.meta
+        if gtotal is None:
+            return (None,) * 8
+        gtotal = gtotal.float().contiguous()
+        da, dzp = torch.empty_like(a), torch.empty_like(z_pred)
+        db = None if b is None else torch.empty_like(b)
+        nb = 0 if b is None else b.numel()
+        _lib.call("hg_gan_loss_bwd", _ptr(gtotal), _ptr(a), a.numel(), ta, wa, _ptr(b), nb, tb, wb, _ptr(z_pred), _ptr(z),
+                  z.numel(), _dtype_code(a), _ptr(da), _ptr(db), _ptr(dzp), _stream())
+        return da, db, dzp, None, None, None, None, None
+
+
+def hologan_d_loss(d_real: Tensor, d_fake: Tensor, z_pred: Tensor, z: Tensor) -> Tuple[Tensor, Tensor]:
+    """Discriminator-step loss of the reference (core/lightning_module.py:219-229):
+    (BCE(D(real), 1) + BCE(D(fake), 0)) / 2 + mean((z_pred - z)^2).  Returns (total, [d_loss, q_loss])."""
+    return _GanLoss.apply(d_real, d_fake, z_pred, z, 1.0, 0.5, 0.0, 0.5)
+
+
+def hologan_g_loss(d_fake: Tensor, z_pred: Tensor, z: Tensor) -> Tuple[Tensor, Tensor]:
+    """Generator-step loss (core/lightning_module.py:231-237): BCE(D(fake), 1) + mean((z_pred - z)^2).
+    Returns (total, [g_loss, q_loss])."""
+    return _GanLoss.apply(d_fake, None, z_pred, z, 1.0, 1.0, 0.0, 0.0)

@@ -63,25 +63,52 @@ def optimizer_index(batch_idx: int, disc_freq: int = 1, gen_freq: int = 2) -> in
 
 
 class _FlatGrads:
-    """One contiguous gradient buffer per network; parameter .grad tensors are views into it."""
+    """One contiguous gradient buffer per network; parameter .grad tensors are views into it.
 
-    def __init__(self, params):
+    No per-step zero-fill and no per-parameter accumulation kernels: before a backward pass `begin()` detaches the
+    views, so autograd hands every parameter its freshly computed gradient (AccumulateGrad keeps the incoming tensor
+    instead of launching `grad += new`); `finish()` moves them into the flat buffer with ONE multi-tensor copy and
+    re-attaches the views.  The tcgen05 wgrad kernels store straight into their view (`_hg_direct_grad`).  A view
+    that no backward ever writes (a parameter without gradient) keeps its initial zeros."""
+
+    def __init__(self, params, direct: bool = False):
         self.params = [p for p in params]
         n = sum(p.numel() for p in self.params)
         dev, dt = self.params[0].device, self.params[0].dtype
         self.flat = torch.zeros(n, device=dev, dtype=dt)
+        self.views = []
         o = 0
         for p in self.params:
             chunk = self.flat[o:o + p.numel()]
             if p.dim() == 4 and not p.is_contiguous() and p.is_contiguous(memory_format=torch.channels_last):
                 n, c, h, w = p.shape                      # same strides as the parameter (fused Adam needs that)
-                p.grad = chunk.view(n, h, w, c).permute(0, 3, 1, 2)
+                view = chunk.view(n, h, w, c).permute(0, 3, 1, 2)
             else:
-                p.grad = chunk.view_as(p)
+                view = chunk.view_as(p)
+            p.grad = view
+            if direct:
+                p._hg_direct_grad = view                  # ops._direct_grad_target: wgrad kernels store here
+            self.views.append(view)
             o += p.numel()
 
     def zero(self):
         self.flat.zero_()
+
+    def begin(self):
+        for p in self.params:
+            p.grad = None
+
+    def finish(self):
+        src, dst = [], []
+        for p, view in zip(self.params, self.views):
+            g = p.grad
+            if g is not None and g.data_ptr() != view.data_ptr():
+                src.append(g.detach())
+                dst.append(view)
+            p.grad = view
+        if src:
+            with torch.no_grad():
+                torch._foreach_copy_(dst, src)
 
     def all_reduce_mean(self, world: int):
         if world > 1:
@@ -139,12 +166,8 @@ class HologanTrainer:
             # its weights live channels-last too -- no per-call layout conversions
             self.discriminator.to(memory_format=torch.channels_last)
         self.d_grads = _FlatGrads(self.discriminator.parameters())
-        self.g_grads = _FlatGrads(self.generator.parameters())
-        if self.device.type == "cuda":
-            # the .grad views above are permanent and zeroed before every step: let the wgrad kernels
-            # accumulate straight into them (ops._direct_grad_target)
-            for p in self.generator.parameters():
-                p._hg_direct_grad = True
+        # the generator's tcgen05 wgrad kernels store straight into the flat buffer (ops._direct_grad_target)
+        self.g_grads = _FlatGrads(self.generator.parameters(), direct=self.device.type == "cuda")
         cuda = self.device.type == "cuda"
         # fused multi-tensor Adam; capturable (device-side step counter, tensor lr) so that a whole
         # optimizer step can live inside a CUDA graph
@@ -188,12 +211,17 @@ class HologanTrainer:
         """Losses of HOLOGAN.training_step (lightning_module.py:209-237).  `z` and `view` are explicit
         (the reference samples them inside); `real` is (B,3,H,W) in [-1,1] on the device."""
         bce = F.binary_cross_entropy_with_logits
+        cuda = self.device.type == "cuda"
         if optimizer_idx == 0:
             with torch.no_grad(), self._autocast():     # the D step detaches fake (:221): no G graph is needed
                 fake = self.generator(z, view_in=view)
             with self._autocast():
                 d_real, _ = self.discriminator(real)
                 d_fake, z_pred = self.discriminator(fake)
+            if cuda:                                    # both losses + their gradients: one launch each way
+                loss, parts = ops.hologan_d_loss(d_real, d_fake, z_pred, z)
+                self.logs["train/d_loss"], self.logs["train/q_loss"] = parts[0], parts[1]
+                return loss
             d_real, d_fake, z_pred = d_real.float(), d_fake.float(), z_pred.float()
             loss_d = (bce(d_real, torch.ones_like(d_real)) + bce(d_fake, torch.zeros_like(d_fake))) / 2
             q = torch.mean((z_pred - z) ** 2)
@@ -202,6 +230,10 @@ class HologanTrainer:
         with self._autocast():
             fake = self.generator(z, view_in=view)
             out, z_pred = self.discriminator(fake)
+        if cuda:
+            loss, parts = ops.hologan_g_loss(out, z_pred, z)
+            self.logs["train/g_loss"], self.logs["train/q_loss"] = parts[0], parts[1]
+            return loss
         out, z_pred = out.float(), z_pred.float()
         loss_g = bce(out, torch.ones_like(out))
         q = torch.mean((z_pred - z) ** 2)
@@ -264,9 +296,10 @@ class HologanTrainer:
         # Lightning's toggle_optimizer: only the stepped network's parameters require grad
         for p in self.discriminator.parameters():
             p.requires_grad_(idx == 0)
-        grads.zero()
+        grads.begin()
         loss = self.training_step(real, z, view, idx)
         loss.backward()
+        grads.finish()
         grads.all_reduce_mean(self.world)
         opt.step()
         return loss.detach()

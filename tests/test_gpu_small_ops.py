@@ -63,3 +63,66 @@ def test_act_bwd_bias(rows, cols, slope):
     assert torch.equal(db, db2)                       # deterministic
     dpre3, none = ops.act_bwd_bias(y, dy, slope, False)
     assert none is None and torch.equal(dpre3, ref)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.bfloat16, 2e-2)])
+@pytest.mark.parametrize("b", [4, 64, 300])
+def test_gan_losses_vs_torch(dtype, tol, b):
+    """Fused D-step / G-step losses (core/lightning_module.py:217-237) and their gradients against the stock
+    BCEWithLogits + MSE formulation in fp32."""
+    g = torch.Generator().manual_seed(b)
+    d_real = (torch.randn(b, 1, generator=g) * 3).to(dtype)
+    d_fake = (torch.randn(b, 1, generator=g) * 3).to(dtype)
+    d_fake[0, 0] = 40.0          # saturated logits: stable forms only
+    d_real[0, 0] = -40.0
+    z_pred = torch.tanh(torch.randn(b, 128, generator=g)).to(dtype)
+    z = torch.rand(b, 128, generator=g) * 2 - 1
+    bce = F.binary_cross_entropy_with_logits
+    # --- D step
+    rr, rf, rz = (t.float().clone().requires_grad_(True) for t in (d_real, d_fake, z_pred))
+    ref_adv = (bce(rr, torch.ones_like(rr)) + bce(rf, torch.zeros_like(rf))) / 2
+    ref_q = torch.mean((rz - z) ** 2)
+    ((ref_adv + ref_q) * 1.7).backward()
+    gr, gf, gz = (t.to(DEV).requires_grad_(True) for t in (d_real, d_fake, z_pred))
+    total, parts = ops.hologan_d_loss(gr, gf, gz, z.to(DEV))
+    (total * 1.7).backward()
+    assert abs(total.item() - (ref_adv + ref_q).item()) <= 2e-6 * max(1.0, abs((ref_adv + ref_q).item()))
+    assert abs(parts[0].item() - ref_adv.item()) <= 2e-6 * max(1.0, ref_adv.item()) and abs(parts[1].item() - ref_q.item()) <= 2e-6
+    for got, ref in ((gr.grad, rr.grad), (gf.grad, rf.grad), (gz.grad, rz.grad)):
+        assert got.dtype == dtype and rel_err(got.float(), ref) < tol
+    # --- G step
+    rf2, rz2 = (t.float().clone().requires_grad_(True) for t in (d_fake, z_pred))
+    ref = bce(rf2, torch.ones_like(rf2)) + torch.mean((rz2 - z) ** 2)
+    ref.backward()
+    gf2, gz2 = (t.to(DEV).requires_grad_(True) for t in (d_fake, z_pred))
+    total2, parts2 = ops.hologan_g_loss(gf2, gz2, z.to(DEV))
+    total2.backward()
+    assert abs(total2.item() - ref.item()) <= 2e-6 * max(1.0, abs(ref.item()))
+    assert rel_err(gf2.grad.float(), rf2.grad) < tol and rel_err(gz2.grad.float(), rz2.grad) < tol
+
+
+def test_packed_style_matches_split_style():
+    """AdaIN with the packed (B, 2C) ZMapping output == AdaIN with its two slices, forward and backward."""
+    g = torch.Generator().manual_seed(5)
+    b, c = 6, 32
+    x = torch.randn(b, c, 8, 8, 8, generator=g).to(DEV)
+    style = torch.rand(b, 2 * c, generator=g).to(DEV)
+    dy = torch.randn(b, c, 8, 8, 8, generator=g).to(DEV)
+    x1, s1 = x.clone().requires_grad_(True), style.clone().requires_grad_(True)
+    y1 = ops.adain_act(x1, s1, None, neg_slope=0.0)
+    (y1 * dy).sum().backward()
+    x2, s2 = x.clone().requires_grad_(True), style.clone().requires_grad_(True)
+    y2 = ops.adain_act(x2, s2[:, :c], s2[:, c:], neg_slope=0.0)
+    (y2 * dy).sum().backward()
+    assert torch.equal(y1, y2) and torch.equal(x1.grad, x2.grad) and torch.equal(s1.grad, s2.grad)
+    # channels-last variant on an s2d conv output
+    xs = torch.randn(b, 4, 4, 4, 64, generator=g).to(DEV).to(torch.bfloat16)
+    st = torch.rand(b, 128, generator=g).to(DEV)
+    dyc = torch.randn(b, 8, 8, 64, generator=g).to(DEV).to(torch.bfloat16)
+    xa, sa = xs.clone().requires_grad_(True), st.clone().requires_grad_(True)
+    ya = ops.adain_act_channels_last(xa, sa, None, ndim=2, classes=4)
+    (ya.float() * dyc.float()).sum().backward()
+    xb, sb = xs.clone().requires_grad_(True), st.clone().requires_grad_(True)
+    yb = ops.adain_act_channels_last(xb, sb[:, :64], sb[:, 64:], ndim=2, classes=4)
+    (yb.float() * dyc.float()).sum().backward()
+    assert torch.equal(ya, yb) and torch.equal(xa.grad, xb.grad) and torch.equal(sa.grad, sb.grad)
