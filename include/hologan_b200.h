@@ -24,6 +24,7 @@ extern "C" {
 #endif
 
 #define HG_ABI_VERSION 1
+#define HG_SN_MAX_LAYERS 4
 
 typedef enum {
     HG_OK = 0,
@@ -196,6 +197,26 @@ long long hg_final_conv_tanh_bwd_workspace_bytes(int batch, int cin, int cout, i
 int hg_final_conv_tanh_bwd(const void *x, const float *w, const float *out, const float *dout, void *dx, float *dw,
                            float *dbias, void *workspace, long long workspace_bytes, int batch, int cin, int cout, int size,
                            void *stream);
+
+/* ---- a14: spectral normalisation of the discriminator's convolutions, grouped over the layers ----------
+ * Replaces torch.nn.utils.spectral_norm (n_power_iterations = 1, eps = 1e-12, dim = 0) as used at
+ * core/models/hologan_discriminator.py:15 -- per layer i, with W = w[i] viewed as (cout, K = cin * taps):
+ *     t = W^T u;  v = t / max(|t|, eps);  s = W v;  u = s / max(|s|, eps);  sigma = u . s;  w_out = W / sigma
+ * u[i] (cout) and v[i] (K, LOGICAL order (ci, tap), as in the reference's state_dict) are updated in place when
+ * power_iteration != 0 (training-mode forward) and only read otherwise (eval).  W, w_out, dw, dw_orig are in the
+ * parameter's PHYSICAL element order: channels_last != 0 means (cout, tap, cin), else (cout, cin, tap).
+ * state[i]: hg_spectral_norm_state_floats() floats written by the forward ([0] sigma, [1] 1/sigma, the u and v used)
+ * -- the backward reads it, so the buffers may be overwritten by the next forward in between.
+ * backward: dw_orig = dw / sigma - (sum(dw * W) / sigma^2) * u v^T   (+= when accumulate != 0); dw has dw_dtype.
+ * The arrays of pointers / dims are HOST arrays of `layers` (<= HG_SN_MAX_LAYERS) entries.  Deterministic. */
+long long hg_spectral_norm_state_floats(int cout, int cin, int taps);
+long long hg_spectral_norm_workspace_bytes(int layers, const int *cout, const int *cin, const int *taps);
+int hg_spectral_norm_fwd(int layers, const float *const *w, float *const *u, float *const *v, void *const *w_out,
+                         float *const *state, const int *cout, const int *cin, const int *taps, int channels_last,
+                         int power_iteration, float eps, int out_dtype, void *workspace, long long workspace_bytes, void *stream);
+int hg_spectral_norm_bwd(int layers, const void *const *dw, const float *const *w, const float *const *state,
+                         float *const *dw_orig, const int *cout, const int *cin, const int *taps, int accumulate, int dw_dtype,
+                         void *workspace, long long workspace_bytes, void *stream);
 
 /* ---- a13: the losses of HOLOGAN.training_step  (core/lightning_module.py:217-237) -------------------
  *   adv = wa * mean_i BCEWithLogits(a[i], ta) + wb * mean_j BCEWithLogits(b[j], tb)   (b may be NULL, nb = 0)

@@ -57,11 +57,18 @@ SIGNATURES = {
                         _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p],
     "hg_gan_loss_bwd": [_c_void_p, _c_void_p, _c_int, _c_float, _c_float, _c_void_p, _c_int, _c_float, _c_float, _c_void_p,
                         _c_void_p, _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_void_p],
+    "hg_spectral_norm_state_floats": [_c_int, _c_int, _c_int],
+    "hg_spectral_norm_workspace_bytes": [_c_int, _c_void_p, _c_void_p, _c_void_p],
+    "hg_spectral_norm_fwd": [_c_int, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
+                             _c_int, _c_int, _c_float, _c_int, _c_void_p, _c_ll, _c_void_p],
+    "hg_spectral_norm_bwd": [_c_int, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int,
+                             _c_int, _c_void_p, _c_ll, _c_void_p],
 }
 _RESTYPES = {"hg_last_error": ctypes.c_char_p, "hg_rotate_bwd_workspace_bytes": ctypes.c_longlong,
              "hg_convt_wgrad_workspace_bytes": ctypes.c_longlong, "hg_act_bwd_bias_workspace_bytes": ctypes.c_longlong,
              "hg_adain_cl_workspace_bytes": ctypes.c_longlong,
-             "hg_final_conv_tanh_bwd_workspace_bytes": ctypes.c_longlong}
+             "hg_final_conv_tanh_bwd_workspace_bytes": ctypes.c_longlong,
+             "hg_spectral_norm_state_floats": ctypes.c_longlong, "hg_spectral_norm_workspace_bytes": ctypes.c_longlong}
 
 _lib = None
 _lock = threading.Lock()

@@ -71,11 +71,38 @@ class Discriminator(nn.Module):
         self.linear3 = nn.Linear(128, z_planes)
         nn.init.zeros_(self.linear3.bias)
 
+    def _blocks_bf16(self, h):
+        """The three spectral-norm blocks of the bf16 pipeline.  One grouped call normalises all three weights
+        (power iteration on `weight_u` / `weight_v`, sigma, bf16 channels-last conv operand) instead of the hook's
+        ~16 launches per layer; the convolution biases are not applied -- the InstanceNorm that follows removes any
+        per-channel constant, so the output is unchanged and their gradient is identically zero (the reference only
+        holds rounding noise there)."""
+        convs = [blk.conv2d for blk in self.blocks]
+        ws = ops.spectral_norm_weights([c.weight_orig for c in convs], [c.weight_u for c in convs],
+                                       [c.weight_v for c in convs], power_iteration=self.training,
+                                       out_dtype=torch.bfloat16)
+        for blk, w in zip(self.blocks, ws):
+            h = F.conv2d(h, w, None, stride=2, padding=2)
+            h = ops.instance_norm_act_channels_last(h.permute(0, 2, 3, 1), 0.2, blk.instance_norm.eps).permute(0, 3, 1, 2)
+        return h
+
+    def _bf16_pipeline_ok(self, x):
+        if not (x.is_cuda and torch.is_autocast_enabled() and torch.get_autocast_dtype("cuda") == torch.bfloat16):
+            return False
+        w = self.blocks[0].conv2d.weight_orig
+        side = x.shape[-1] // 4                                       # spatial extent after the first block
+        return (x.shape[-1] == x.shape[-2] and w.shape[0] % 16 == 0 and side * side <= 4096 and (side // 4) ** 2 >= 2
+                and all(b.conv2d.weight_orig.is_contiguous(memory_format=torch.channels_last) for b in self.blocks))
+
     def forward(self, x):
-        if x.is_cuda and torch.is_autocast_enabled() and torch.get_autocast_dtype("cuda") == torch.bfloat16:
+        bf16 = x.is_cuda and torch.is_autocast_enabled() and torch.get_autocast_dtype("cuda") == torch.bfloat16
+        if bf16:
             x = x.contiguous(memory_format=torch.channels_last)      # NHWC pipeline (3 MB at B = 64)
         h = F.leaky_relu(self.conv2d(x), 0.2)
-        h = self.blocks(h).flatten(1)                                 # logical (c, h, w) order, as the reference (:60)
+        if bf16 and self._bf16_pipeline_ok(x):
+            h = self._blocks_bf16(h).flatten(1)
+        else:
+            h = self.blocks(h).flatten(1)                             # logical (c, h, w) order, as the reference (:60)
         logits = self.linear1(h)
         z_prediction = torch.tanh(self.linear3(F.leaky_relu(self.linear2(h), 0.2)))
         return logits, z_prediction

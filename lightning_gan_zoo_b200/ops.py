@@ -599,3 +599,89 @@ def hologan_g_loss(d_fake: Tensor, z_pred: Tensor, z: Tensor) -> Tuple[Tensor, T
     """Generator-step loss (core/lightning_module.py:231-237): BCE(D(fake), 1) + mean((z_pred - z)^2).
     Returns (total, [g_loss, q_loss])."""
     return _GanLoss.apply(d_fake, None, z_pred, z, 1.0, 1.0, 0.0, 0.0)
+
+
+# ------------------------------------------------------------------------------------------------
+# a14: spectral normalisation of the discriminator's convolutions (all layers in one call)
+# ------------------------------------------------------------------------------------------------
+
+def _c_array(ctype, values):
+    return (ctype * len(values))(*values)
+
+
+def _sn_geometry(weights):
+    w0 = weights[0]
+    if all(w.is_contiguous() for w in weights):
+        channels_last = 0
+    elif all(w.dim() == 4 and w.is_contiguous(memory_format=torch.channels_last) for w in weights):
+        channels_last = 1
+    else:
+        raise ValueError("spectral_norm_weights: weights must all be contiguous or all channels_last")
+    for w in weights:
+        if w.dtype != torch.float32 or w.dim() < 2 or w.device != w0.device:
+            raise ValueError("spectral_norm_weights: fp32 weights of >= 2 dims on one device")
+    cout = [w.shape[0] for w in weights]
+    cin = [w.shape[1] for w in weights]
+    taps = [w[0, 0].numel() for w in weights]
+    return channels_last, cout, cin, taps
+
+
+class _SpectralNormWeights(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, us, vs, iterate, out_dtype, eps, *weights):
+        _require_cuda(*weights, *us, *vs)
+        n = len(weights)
+        channels_last, cout, cin, taps = _sn_geometry(weights)
+        for w, u, v, co, ci, t in zip(weights, us, vs, cout, cin, taps):
+            if u.dtype != torch.float32 or v.dtype != torch.float32 or u.numel() != co or v.numel() != ci * t \
+                    or not u.is_contiguous() or not v.is_contiguous():
+                raise ValueError("spectral_norm_weights: u (Cout) / v (Cin*taps) must be contiguous fp32 buffers")
+        lib = _lib.load()
+        ci_arr, co_arr, t_arr = _c_array(ctypes.c_int, cin), _c_array(ctypes.c_int, cout), _c_array(ctypes.c_int, taps)
+        nbytes = lib.hg_spectral_norm_workspace_bytes(n, co_arr, ci_arr, t_arr)
+        if nbytes < 0:
+            raise _lib.HologanB200Error(f"hg_spectral_norm_fwd: unsupported layer count {n}")
+        dev = weights[0].device
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        outs = [torch.empty_like(w, dtype=out_dtype) for w in weights]           # same physical layout
+        states = [torch.empty(lib.hg_spectral_norm_state_floats(co, ci, t), dtype=torch.float32, device=dev)
+                  for co, ci, t in zip(cout, cin, taps)]
+        vp = ctypes.c_void_p
+        _lib.call("hg_spectral_norm_fwd", n, _c_array(vp, [w.data_ptr() for w in weights]),
+                  _c_array(vp, [u.data_ptr() for u in us]), _c_array(vp, [v.data_ptr() for v in vs]),
+                  _c_array(vp, [o.data_ptr() for o in outs]), _c_array(vp, [s.data_ptr() for s in states]),
+                  co_arr, ci_arr, t_arr, channels_last, int(bool(iterate)), float(eps),
+                  HG_BF16 if out_dtype == torch.bfloat16 else HG_F32, _ptr(ws), nbytes, _stream())
+        ctx.save_for_backward(*weights, *states)
+        ctx.meta = (n, channels_last, cout, cin, taps, out_dtype)
+        ctx.params = [w if isinstance(w, torch.nn.Parameter) else None for w in weights]
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        n, channels_last, cout, cin, taps, out_dtype = ctx.meta
+        weights, states = ctx.saved_tensors[:n], ctx.saved_tensors[n:]
+        fmt = torch.channels_last if channels_last else torch.contiguous_format
+        grads = [g.to(out_dtype).contiguous(memory_format=fmt) for g in grads]
+        # HologanTrainer's flat gradient buffer: accumulate straight into the parameter's view (the D step runs the
+        # discriminator twice, so two backward calls add into it; the trainer zeroes these views before the step)
+        targets = [_direct_grad_target(p, w.shape)[0] if p is not None else None for p, w in zip(ctx.params, weights)]
+        direct = all(t is not None and t.stride() == w.stride() for t, w in zip(targets, weights))
+        dws = targets if direct else [torch.empty_like(w) for w in weights]
+        lib = _lib.load()
+        ci_arr, co_arr, t_arr = _c_array(ctypes.c_int, cin), _c_array(ctypes.c_int, cout), _c_array(ctypes.c_int, taps)
+        nbytes = lib.hg_spectral_norm_workspace_bytes(n, co_arr, ci_arr, t_arr)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=weights[0].device)
+        vp = ctypes.c_void_p
+        _lib.call("hg_spectral_norm_bwd", n, _c_array(vp, [g.data_ptr() for g in grads]),
+                  _c_array(vp, [w.data_ptr() for w in weights]), _c_array(vp, [s.data_ptr() for s in states]),
+                  _c_array(vp, [d.data_ptr() for d in dws]), co_arr, ci_arr, t_arr, int(direct),
+                  HG_BF16 if out_dtype == torch.bfloat16 else HG_F32, _ptr(ws), nbytes, _stream())
+        return (None, None, None, None, None) + ((None,) * n if direct else tuple(dws))
+
+
+def spectral_norm_weights(weights, us, vs, power_iteration: bool = True, out_dtype=torch.float32, eps: float = 1e-12):
+    """W_i / sigma_i for a group of (<= 4) weights, with one power iteration that updates `us[i]` / `vs[i]` in place
+    when `power_iteration` -- torch.nn.utils.spectral_norm's training-mode forward as the reference uses it
+    (core/models/hologan_discriminator.py:15).  Outputs have `out_dtype` and the weights' memory format."""
+    return _SpectralNormWeights.apply(list(us), list(vs), power_iteration, out_dtype, eps, *weights)

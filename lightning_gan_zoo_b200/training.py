@@ -71,8 +71,13 @@ class _FlatGrads:
     re-attaches the views.  The tcgen05 wgrad kernels store straight into their view (`_hg_direct_grad`).  A view
     that no backward ever writes (a parameter without gradient) keeps its initial zeros."""
 
-    def __init__(self, params, direct: bool = False):
+    def __init__(self, params, direct: bool = False, accumulate_into=()):
+        """direct: every parameter's view is offered to the kernels as a store target (one backward per step).
+        accumulate_into: parameters whose kernels ADD into the view (several backward calls per step, e.g. the
+        discriminator's spectral-norm weights: D runs on real and fake) -- those views are zeroed by `begin()`."""
         self.params = [p for p in params]
+        acc_ids = {id(p) for p in accumulate_into}
+        self.zero_views = []
         n = sum(p.numel() for p in self.params)
         dev, dt = self.params[0].device, self.params[0].dtype
         self.flat = torch.zeros(n, device=dev, dtype=dt)
@@ -86,8 +91,10 @@ class _FlatGrads:
             else:
                 view = chunk.view_as(p)
             p.grad = view
-            if direct:
-                p._hg_direct_grad = view                  # ops._direct_grad_target: wgrad kernels store here
+            if direct or id(p) in acc_ids:
+                p._hg_direct_grad = view                  # ops._direct_grad_target: wgrad kernels store / add here
+            if id(p) in acc_ids:
+                self.zero_views.append(view)
             self.views.append(view)
             o += p.numel()
 
@@ -97,6 +104,9 @@ class _FlatGrads:
     def begin(self):
         for p in self.params:
             p.grad = None
+        if self.zero_views:
+            with torch.no_grad():
+                torch._foreach_zero_(self.zero_views)
 
     def finish(self):
         src, dst = [], []
@@ -165,7 +175,8 @@ class HologanTrainer:
             # bf16 pipeline: the discriminator's convolutions run NHWC (cuDNN's native tensor-core layout), so
             # its weights live channels-last too -- no per-call layout conversions
             self.discriminator.to(memory_format=torch.channels_last)
-        self.d_grads = _FlatGrads(self.discriminator.parameters())
+        sn_weights = [blk.conv2d.weight_orig for blk in self.discriminator.blocks] if self.device.type == "cuda" else ()
+        self.d_grads = _FlatGrads(self.discriminator.parameters(), accumulate_into=sn_weights)
         # the generator's tcgen05 wgrad kernels store straight into the flat buffer (ops._direct_grad_target)
         self.g_grads = _FlatGrads(self.generator.parameters(), direct=self.device.type == "cuda")
         cuda = self.device.type == "cuda"

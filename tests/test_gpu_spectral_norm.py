@@ -1,0 +1,120 @@
+"""Grouped spectral-norm kernels (hg_spectral_norm_fwd/bwd) against torch.nn.utils.spectral_norm -- the module the
+reference wraps its discriminator convolutions in (core/models/hologan_discriminator.py:15) -- and the discriminator's
+bf16 pipeline against its own stock-module path."""
+import copy
+
+import pytest
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from conftest import rel_err
+from lightning_gan_zoo_b200 import ops
+from lightning_gan_zoo_b200.core.models.hologan_discriminator import Discriminator
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _torch_sn_convs(shapes, seed):
+    torch.manual_seed(seed)
+    convs = []
+    for cout, cin in shapes:
+        c = nn.Conv2d(cin, cout, 5, stride=2, padding=2)
+        nn.init.normal_(c.weight, std=0.05)
+        convs.append(nn.utils.spectral_norm(c))
+    return convs
+
+
+@pytest.mark.parametrize("channels_last", [False, True])
+@pytest.mark.parametrize("shapes", [[(16, 8), (32, 16), (64, 32)], [(128, 64)], [(24, 12), (40, 20)]])
+def test_forward_backward_vs_torch_hook(shapes, channels_last):
+    """Two consecutive training-mode forwards (the D step calls D twice) + backward through both, then an eval
+    forward: normalised weights, sigma-dependent gradients and the u / v buffers against the stock hook (CPU fp32)."""
+    ref = _torch_sn_convs(shapes, 3)
+    mine = copy.deepcopy(ref)
+    ws = [c.weight_orig.detach().clone().to(DEV) for c in mine]
+    if channels_last:
+        ws = [w.contiguous(memory_format=torch.channels_last) for w in ws]
+    ws = [w.requires_grad_(True) for w in ws]
+    us = [c.weight_u.detach().clone().to(DEV) for c in mine]
+    vs = [c.weight_v.detach().clone().to(DEV) for c in mine]
+    g = torch.Generator().manual_seed(11)
+    cots = [[torch.randn(c.weight_orig.shape, generator=g) for c in ref] for _ in range(2)]
+    # reference: the hook recomputes `weight` at every training-mode forward
+    ref_loss = 0
+    ref_w = []
+    for call in range(2):
+        for c, cot in zip(ref, cots[call]):
+            c.train()
+            x = torch.zeros(1, c.in_channels, 8, 8)
+            c(x)                                           # runs the pre-forward hook (power iteration)
+            ref_w.append(c.weight.detach().clone())
+            ref_loss = ref_loss + (c.weight * cot).sum()
+    ref_loss.backward()
+    got_w = []
+    loss = 0
+    for call in range(2):
+        outs = ops.spectral_norm_weights(ws, us, vs, power_iteration=True, out_dtype=torch.float32)
+        for o, w, cot in zip(outs, ws, cots[call]):
+            assert o.stride() == w.stride()
+            got_w.append(o.detach().clone())
+            loss = loss + (o * cot.to(DEV)).sum()
+    loss.backward()
+    n = len(shapes)
+    for i in range(2 * n):
+        assert rel_err(got_w[i], ref_w[i]) < 1e-5, i
+    for i, c in enumerate(ref):
+        assert rel_err(us[i], c.weight_u) < 1e-5 and rel_err(vs[i], c.weight_v) < 1e-5
+        assert rel_err(ws[i].grad, c.weight_orig.grad) < 1e-5, i
+    # eval: no power iteration, buffers untouched
+    u_before = [u.clone() for u in us]
+    outs = ops.spectral_norm_weights(ws, us, vs, power_iteration=False, out_dtype=torch.float32)
+    for o, c, u0, u in zip(outs, ref, u_before, us):
+        c.eval()
+        c(torch.zeros(1, c.in_channels, 8, 8))
+        assert rel_err(o, c.weight) < 1e-5 and torch.equal(u0, u)
+
+
+def test_bf16_output_is_rounded_fp32():
+    ref = _torch_sn_convs([(128, 64), (256, 128)], 5)
+    ws = [c.weight_orig.detach().clone().to(DEV).contiguous(memory_format=torch.channels_last) for c in ref]
+    us = [c.weight_u.detach().clone().to(DEV) for c in ref]
+    vs = [c.weight_v.detach().clone().to(DEV) for c in ref]
+    o32 = ops.spectral_norm_weights(ws, [u.clone() for u in us], [v.clone() for v in vs], True, torch.float32)
+    o16 = ops.spectral_norm_weights(ws, us, vs, True, torch.bfloat16)
+    for a, b in zip(o32, o16):
+        assert b.dtype == torch.bfloat16 and b.is_contiguous(memory_format=torch.channels_last)
+        assert torch.equal(a.to(torch.bfloat16), b)
+
+
+def test_discriminator_bf16_pipeline_vs_stock_modules():
+    """D's bf16 pipeline (grouped spectral norm, bias-free block convs, fused InstanceNorm+LeakyReLU) against the same
+    module run through the stock hook path in fp32: outputs, parameter gradients and u buffers."""
+    torch.manual_seed(0)
+    d_ref = Discriminator(3, 64, 128).to(DEV)
+    d = copy.deepcopy(d_ref).to(memory_format=torch.channels_last)
+    x = (torch.rand(8, 3, 64, 64, device=DEV) * 2 - 1)
+    z = torch.rand(8, 128, device=DEV) * 2 - 1
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        lr, zr = d_ref(x)
+        (F.binary_cross_entropy_with_logits(lr, torch.ones_like(lr)) + ((zr - z) ** 2).mean()).backward()
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            lg, zg = d(x)
+        assert lg.dtype == torch.bfloat16
+        loss, _ = ops.hologan_g_loss(lg, zg, z)
+        loss.backward()
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    assert rel_err(lg.float(), lr) < 2e-2 and rel_err(zg.float(), zr) < 2e-2
+    ref_p = dict(d_ref.named_parameters())
+    for k, p in d.named_parameters():
+        if k.startswith("blocks.") and k.endswith("conv2d.bias"):
+            assert p.grad is None                  # not applied: InstanceNorm cancels it (the reference holds rounding noise)
+            continue
+        assert rel_err(p.grad, ref_p[k].grad) < 3e-2, k
+    for a, b in zip(d.blocks, d_ref.blocks):
+        assert rel_err(a.conv2d.weight_u, b.conv2d.weight_u) < 1e-5
+        assert rel_err(a.conv2d.weight_v, b.conv2d.weight_v) < 1e-5
