@@ -25,6 +25,7 @@ extern "C" {
 
 #define HG_ABI_VERSION 1
 #define HG_SN_MAX_LAYERS 4
+#define HG_LINEAR_GROUP_MAX 8
 
 typedef enum {
     HG_OK = 0,
@@ -185,6 +186,15 @@ int hg_gemm_bf16_nt(const void *a, const void *b, const float *bias, void *d, in
 int hg_linear_relu_fwd(const float *z, const float *w, const float *bias, float *out, int batch, int k, int n, void *stream);
 int hg_linear_relu_bwd(const float *z, const float *w, const float *out, const float *dout, float *dw, float *dbias,
                        float *dz, int batch, int k, int n, int accumulate_dz, void *stream);
+
+/* Grouped form: `layers` (<= HG_LINEAR_GROUP_MAX) ZMappings that read the same z (the generator's five, reference
+ * :34,54) in one launch each way.  w / bias / out / dout / dw / dbias and n are HOST arrays of `layers` entries
+ * (device pointers / feature counts); out[l] is (B, n[l]).  The backward gives dw, dbias only (z carries no gradient
+ * in training). */
+int hg_linear_relu_group_fwd(int layers, const float *z, const float *const *w, const float *const *bias, float *const *out,
+                             const int *n, int batch, int k, void *stream);
+int hg_linear_relu_group_bwd(int layers, const float *z, const float *const *out, const float *const *dout, float *const *dw,
+                             float *const *dbias, const int *n, int batch, int k, void *stream);
 
 /* ---- a11: final_layer + tanh  (core/models/hologan_generator.py:69-75,141-142, img_size 64) ---------
  *   out (B,Cout,S,S) fp32 NCHW = tanh(conv2d(x, w, bias, k3, p1)); x (B,S,S,Cin) bf16 NHWC,

@@ -49,6 +49,9 @@ SIGNATURES = {
     "hg_linear_relu_fwd": [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p],
     "hg_linear_relu_bwd": [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int,
                            _c_int, _c_int, _c_void_p],
+    "hg_linear_relu_group_fwd": [_c_int, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_void_p],
+    "hg_linear_relu_group_bwd": [_c_int, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int,
+                                 _c_void_p],
     "hg_final_conv_tanh_fwd": [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_void_p],
     "hg_final_conv_tanh_bwd_workspace_bytes": [_c_int, _c_int, _c_int, _c_int],
     "hg_final_conv_tanh_bwd": [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p,

@@ -152,11 +152,14 @@ class Generator(nn.Module):
         unchanged and their gradient is identically zero (the reference only holds rounding noise there)."""
         bf16 = torch.bfloat16
         n = z.shape[0]
-        h0 = ops.adain_act(self.x, self.zMapping.style(z), None, neg_slope=0.0)  # (B,8P,4,4,4) fp32, NC*
+        # all five ZMappings read the same z: one launch (packed (B, 2C) styles, fp32)
+        maps = [self.zMapping] + [b.zMapping for b in (self.block1, self.block2, self.block3, self.block4)]
+        styles = ops.linear_relu_group(z, [m.linear1.weight for m in maps], [m.linear1.bias for m in maps])
+        h0 = ops.adain_act(self.x, styles[0], None, neg_slope=0.0)               # (B,8P,4,4,4) fp32, NC*
         h = ops.nc_to_channels_last(h0.to(bf16))                                 # (B,4,4,4,8P)
-        for block in (self.block1, self.block2):
+        for block, style in ((self.block1, styles[1]), (self.block2, styles[2])):
             y = ops.convt(h, block.convTranspose.weight, None, 3, 3)             # (B,S,S,S,8,Cout) s2d
-            h = ops.adain_act_channels_last(y, block.zMapping.style(z), None, ndim=3, classes=8)   # (B,2S,2S,2S,Cout) NDHWC
+            h = ops.adain_act_channels_last(y, style, None, ndim=3, classes=8)   # (B,2S,2S,2S,Cout) NDHWC
         size = h.shape[1]
         a_inv = self._affine(view_in, size, size, z.device)
         # rotate + fold depth into channels in one kernel: out[b, z, x, (y, c)] is the projection's A operand
@@ -168,9 +171,9 @@ class Generator(nn.Module):
         h = ops.convt(a_proj, self.convTranspose2d1.weight, self.convTranspose2d1.bias, 2, 1, neg_slope=0.0,
                       perm=(c, size))                                             # 1x1 conv + bias + ReLU
         h = h.reshape(n, size, size, -1)
-        for block in (self.block3, self.block4):
+        for block, style in ((self.block3, styles[3]), (self.block4, styles[4])):
             y = ops.convt(h, block.convTranspose.weight, None, 2, 4)             # (B,S,S,4,Cout) s2d
-            h = ops.adain_act_channels_last(y, block.zMapping.style(z), None, ndim=2, classes=4)   # (B,2S,2S,Cout) NHWC
+            h = ops.adain_act_channels_last(y, style, None, ndim=2, classes=4)   # (B,2S,2S,Cout) NHWC
         if self.img_size == 64 and ops.final_conv_supported(h.shape[-1], self.final_layer.weight.shape[0]):
             return ops.final_conv_tanh(h, self.final_layer.weight, self.final_layer.bias)   # direct conv + tanh, fp32 out
         # patched-128 head (ConvTranspose2d k4 s2): cuDNN on the NHWC buffer viewed as channels_last NCHW

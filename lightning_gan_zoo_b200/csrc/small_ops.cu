@@ -11,13 +11,13 @@ namespace hg {
 // loaded with coalesced rows; the dot products read z as a broadcast and W conflict-free).
 constexpr int kLinTn = 16, kLinTb = 64, kLinTk = 128;
 
-__global__ void __launch_bounds__(256) linear_relu_fwd_kernel(const float *__restrict__ z, const float *__restrict__ w,
-                                                              const float *__restrict__ bias, float *__restrict__ out, int B,
-                                                              int K, int N)
+__device__ __forceinline__ void linear_relu_fwd_body(const float *__restrict__ z, const float *__restrict__ w,
+                                                     const float *__restrict__ bias, float *__restrict__ out, int B, int K,
+                                                     int N, int bx, int by)
 {
     __shared__ float zs[kLinTb][kLinTk];
     __shared__ float ws[kLinTn][kLinTk + 1];
-    const int n0 = blockIdx.x * kLinTn, b0 = blockIdx.y * kLinTb;
+    const int n0 = bx * kLinTn, b0 = by * kLinTb;
     const int nl = threadIdx.x % kLinTn, bg = threadIdx.x / kLinTn;        // 16 sample groups x 4 samples
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
     for (int k0 = 0; k0 < K; k0 += kLinTk) {
@@ -51,15 +51,50 @@ __global__ void __launch_bounds__(256) linear_relu_fwd_kernel(const float *__res
     }
 }
 
+__global__ void __launch_bounds__(256) linear_relu_fwd_kernel(const float *__restrict__ z, const float *__restrict__ w,
+                                                              const float *__restrict__ bias, float *__restrict__ out, int B,
+                                                              int K, int N)
+{
+    linear_relu_fwd_body(z, w, bias, out, B, K, N, blockIdx.x, blockIdx.y);
+}
+
+// Grouped variant: the generator's five ZMappings read the same z (reference hologan_generator.py:34,54) -- one
+// launch walks the feature tiles of all of them (tile_start = prefix sums of ceil(N_l / 16)).
+constexpr int kLinMaxGroup = HG_LINEAR_GROUP_MAX;
+struct LinGroup {
+    const float *w[kLinMaxGroup];
+    const float *bias[kLinMaxGroup];
+    float *out[kLinMaxGroup];           // forward: outputs; backward: the saved outputs
+    const float *dout[kLinMaxGroup];
+    float *dw[kLinMaxGroup];
+    float *dbias[kLinMaxGroup];
+    int n[kLinMaxGroup];
+    int tile_start[kLinMaxGroup + 1];
+    int layers;
+};
+__device__ __forceinline__ int lin_group_layer(const LinGroup &g, int tile)
+{
+    int l = 0;
+    while (l + 1 < g.layers && tile >= g.tile_start[l + 1]) ++l;
+    return l;
+}
+
+__global__ void __launch_bounds__(256) linear_relu_group_fwd_kernel(const __grid_constant__ LinGroup g,
+                                                                    const float *__restrict__ z, int B, int K)
+{
+    const int l = lin_group_layer(g, blockIdx.x);
+    linear_relu_fwd_body(z, g.w[l], g.bias[l], g.out[l], B, K, g.n[l], blockIdx.x - g.tile_start[l], blockIdx.y);
+}
+
 // dW[n,k] = sum_b g[b,n] z[b,k], dbias[n] = sum_b g[b,n], with g = dout * (out > 0).
 // grid = (N/16, K/128); samples in chunks of 64 through shared memory; fixed summation order.
-__global__ void __launch_bounds__(256) linear_relu_bwd_w_kernel(const float *__restrict__ z, const float *__restrict__ out,
-                                                                const float *__restrict__ dout, float *__restrict__ dw,
-                                                                float *__restrict__ dbias, int B, int K, int N)
+__device__ __forceinline__ void linear_relu_bwd_w_body(const float *__restrict__ z, const float *__restrict__ out,
+                                                       const float *__restrict__ dout, float *__restrict__ dw,
+                                                       float *__restrict__ dbias, int B, int K, int N, int bx, int by)
 {
     __shared__ float zs[kLinTb][kLinTk];
     __shared__ float gs[kLinTb][kLinTn];
-    const int n0 = blockIdx.x * kLinTn, k0 = blockIdx.y * kLinTk;
+    const int n0 = bx * kLinTn, k0 = by * kLinTk;
     const int kl = threadIdx.x % kLinTk, nh = threadIdx.x / kLinTk;        // 2 feature groups x 8 features
     float acc[8];
 #pragma unroll
@@ -87,7 +122,7 @@ __global__ void __launch_bounds__(256) linear_relu_bwd_w_kernel(const float *__r
 #pragma unroll
             for (int j = 0; j < 8; ++j) acc[j] = fmaf(gs[b][nh * 8 + j], zv, acc[j]);
         }
-        if (blockIdx.y == 0 && threadIdx.x < kLinTn)
+        if (by == 0 && threadIdx.x < kLinTn)
             for (int b = 0; b < kLinTb; ++b) bsum += gs[b][threadIdx.x];
     }
     if (k0 + kl < K) {
@@ -95,7 +130,22 @@ __global__ void __launch_bounds__(256) linear_relu_bwd_w_kernel(const float *__r
         for (int j = 0; j < 8; ++j)
             if (n0 + nh * 8 + j < N) dw[(size_t)(n0 + nh * 8 + j) * K + k0 + kl] = acc[j];
     }
-    if (blockIdx.y == 0 && threadIdx.x < kLinTn && n0 + threadIdx.x < N) dbias[n0 + threadIdx.x] = bsum;
+    if (by == 0 && threadIdx.x < kLinTn && n0 + threadIdx.x < N) dbias[n0 + threadIdx.x] = bsum;
+}
+
+__global__ void __launch_bounds__(256) linear_relu_bwd_w_kernel(const float *__restrict__ z, const float *__restrict__ out,
+                                                                const float *__restrict__ dout, float *__restrict__ dw,
+                                                                float *__restrict__ dbias, int B, int K, int N)
+{
+    linear_relu_bwd_w_body(z, out, dout, dw, dbias, B, K, N, blockIdx.x, blockIdx.y);
+}
+
+__global__ void __launch_bounds__(256) linear_relu_group_bwd_w_kernel(const __grid_constant__ LinGroup g,
+                                                                      const float *__restrict__ z, int B, int K)
+{
+    const int l = lin_group_layer(g, blockIdx.x);
+    linear_relu_bwd_w_body(z, g.out[l], g.dout[l], g.dw[l], g.dbias[l], B, K, g.n[l], blockIdx.x - g.tile_start[l],
+                           blockIdx.y);
 }
 
 // dz[b,k] (+)= sum_n g[b,n] W[n,k].  One CTA per sample, threads over k.
@@ -144,4 +194,52 @@ extern "C" int hg_linear_relu_bwd(const float *z, const float *w, const float *o
     if (rc || !dz) return rc;
     linear_relu_bwd_z_kernel<<<batch, 128, n * sizeof(float), st>>>(w, out, dout, dz, k, n, accumulate_dz);
     return check_launch("hg_linear_relu_bwd(z)");
+}
+
+static int lin_group_fill(LinGroup &g, int layers, const int *n)
+{
+    g.layers = layers;
+    int tiles = 0;
+    for (int l = 0; l < layers; ++l) {
+        g.n[l] = n[l];
+        g.tile_start[l] = tiles;
+        tiles += (n[l] + kLinTn - 1) / kLinTn;
+    }
+    g.tile_start[layers] = tiles;
+    return tiles;
+}
+
+extern "C" int hg_linear_relu_group_fwd(int layers, const float *z, const float *const *w, const float *const *bias,
+                                        float *const *out, const int *n, int batch, int k, void *stream)
+{
+    HG_REQUIRE(layers >= 1 && layers <= kLinMaxGroup, HG_ERR_INVALID_ARG, "hg_linear_relu_group_fwd: 1..%d layers", kLinMaxGroup);
+    HG_REQUIRE(z && w && bias && out && n, HG_ERR_INVALID_ARG, "hg_linear_relu_group_fwd: null pointer");
+    HG_REQUIRE(batch > 0 && k > 0 && k <= 8192, HG_ERR_INVALID_ARG, "hg_linear_relu_group_fwd: bad dims");
+    LinGroup g{};
+    for (int l = 0; l < layers; ++l) {
+        HG_REQUIRE(w[l] && bias[l] && out[l] && n[l] > 0, HG_ERR_INVALID_ARG, "hg_linear_relu_group_fwd: bad layer %d", l);
+        g.w[l] = w[l]; g.bias[l] = bias[l]; g.out[l] = out[l];
+    }
+    const int tiles = lin_group_fill(g, layers, n);
+    dim3 grid(tiles, (batch + kLinTb - 1) / kLinTb);
+    linear_relu_group_fwd_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(g, z, batch, k);
+    return check_launch("hg_linear_relu_group_fwd");
+}
+
+extern "C" int hg_linear_relu_group_bwd(int layers, const float *z, const float *const *out, const float *const *dout,
+                                        float *const *dw, float *const *dbias, const int *n, int batch, int k, void *stream)
+{
+    HG_REQUIRE(layers >= 1 && layers <= kLinMaxGroup, HG_ERR_INVALID_ARG, "hg_linear_relu_group_bwd: 1..%d layers", kLinMaxGroup);
+    HG_REQUIRE(z && out && dout && dw && dbias && n, HG_ERR_INVALID_ARG, "hg_linear_relu_group_bwd: null pointer");
+    HG_REQUIRE(batch > 0 && k > 0 && batch <= 8192, HG_ERR_INVALID_ARG, "hg_linear_relu_group_bwd: bad dims");
+    LinGroup g{};
+    for (int l = 0; l < layers; ++l) {
+        HG_REQUIRE(out[l] && dout[l] && dw[l] && dbias[l] && n[l] > 0 && n[l] <= 8192, HG_ERR_INVALID_ARG,
+                   "hg_linear_relu_group_bwd: bad layer %d", l);
+        g.out[l] = const_cast<float *>(out[l]); g.dout[l] = dout[l]; g.dw[l] = dw[l]; g.dbias[l] = dbias[l];
+    }
+    const int tiles = lin_group_fill(g, layers, n);
+    dim3 grid(tiles, (k + kLinTk - 1) / kLinTk);
+    linear_relu_group_bwd_w_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(g, z, batch, k);
+    return check_launch("hg_linear_relu_group_bwd");
 }

@@ -509,6 +509,51 @@ def linear_relu(z: Tensor, weight: Tensor, bias: Tensor) -> Tensor:
     return _LinearRelu.apply(z, weight, bias)
 
 
+class _LinearReluGroup(torch.autograd.Function):
+    """styles_l = relu(z @ W_l^T + b_l) for several ZMappings of the same z: one launch forward, one backward."""
+
+    @staticmethod
+    def forward(ctx, z, n_layers, *wb):
+        weights, biases = wb[:n_layers], wb[n_layers:]
+        _require_cuda(z, *weights, *biases)
+        z = z.float().contiguous()
+        ws = [w.float().contiguous() for w in weights]
+        bs = [b.float().contiguous() for b in biases]
+        b, k = z.shape
+        ns = [w.shape[0] for w in ws]
+        if any(w.shape[1] != k for w in ws):
+            raise ValueError("linear_relu_group: every weight must be (N_l, K) with K = z.shape[1]")
+        outs = [torch.empty((b, n), dtype=torch.float32, device=z.device) for n in ns]
+        vp = ctypes.c_void_p
+        _lib.call("hg_linear_relu_group_fwd", n_layers, _ptr(z), _c_array(vp, [w.data_ptr() for w in ws]),
+                  _c_array(vp, [t.data_ptr() for t in bs]), _c_array(vp, [o.data_ptr() for o in outs]),
+                  _c_array(ctypes.c_int, ns), b, k, _stream())
+        ctx.save_for_backward(z, *outs)
+        ctx.meta = (n_layers, ns, k)
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *douts):
+        z, outs = ctx.saved_tensors[0], ctx.saved_tensors[1:]
+        n_layers, ns, k = ctx.meta
+        douts = [d.float().contiguous() for d in douts]
+        dws = [torch.empty((n, k), dtype=torch.float32, device=z.device) for n in ns]
+        dbs = [torch.empty(n, dtype=torch.float32, device=z.device) for n in ns]
+        vp = ctypes.c_void_p
+        _lib.call("hg_linear_relu_group_bwd", n_layers, _ptr(z), _c_array(vp, [o.data_ptr() for o in outs]),
+                  _c_array(vp, [d.data_ptr() for d in douts]), _c_array(vp, [d.data_ptr() for d in dws]),
+                  _c_array(vp, [d.data_ptr() for d in dbs]), _c_array(ctypes.c_int, ns), z.shape[0], k, _stream())
+        return (None, None) + tuple(dws) + tuple(dbs)
+
+
+def linear_relu_group(z: Tensor, weights, biases):
+    """[relu(z @ W^T + b) for W, b in zip(weights, biases)] -- the generator's five ZMappings of one latent batch
+    (reference hologan_generator.py:34,54) in a single launch.  `z` gets no gradient (use `linear_relu` for that)."""
+    if z.requires_grad:
+        return tuple(linear_relu(z, w, b) for w, b in zip(weights, biases))
+    return _LinearReluGroup.apply(z, len(weights), *weights, *biases)
+
+
 def final_conv_supported(cin: int, cout: int) -> bool:
     lanes = cin // 8
     return cin % 8 == 0 and 8 <= cin <= 256 and (lanes & (lanes - 1)) == 0 and 1 <= cout <= 4

@@ -126,3 +126,21 @@ def test_packed_style_matches_split_style():
     yb = ops.adain_act_channels_last(xb, sb[:, :64], sb[:, 64:], ndim=2, classes=4)
     (yb.float() * dyc.float()).sum().backward()
     assert torch.equal(ya, yb) and torch.equal(xa.grad, xb.grad) and torch.equal(sa.grad, sb.grad)
+
+
+def test_linear_relu_group_matches_single_calls():
+    g = torch.Generator().manual_seed(9)
+    b, k = 64, 128
+    ns = [1024, 256, 128, 512, 128, 24]
+    z = (torch.rand(b, k, generator=g) * 2 - 1).to(DEV)
+    ws = [(torch.randn(n, k, generator=g) * 0.05).to(DEV) for n in ns]
+    bs = [(torch.randn(n, generator=g) * 0.1).to(DEV) for n in ns]
+    douts = [torch.randn(b, n, generator=g).to(DEV) for n in ns]
+    w1, b1 = [w.clone().requires_grad_(True) for w in ws], [t.clone().requires_grad_(True) for t in bs]
+    outs = ops.linear_relu_group(z, w1, b1)
+    sum((o * d).sum() for o, d in zip(outs, douts)).backward()
+    for i, n in enumerate(ns):
+        w2, b2 = ws[i].clone().requires_grad_(True), bs[i].clone().requires_grad_(True)
+        ref = ops.linear_relu(z, w2, b2)
+        (ref * douts[i]).sum().backward()
+        assert torch.equal(outs[i], ref) and torch.equal(w1[i].grad, w2.grad) and torch.equal(b1[i].grad, b2.grad), n
