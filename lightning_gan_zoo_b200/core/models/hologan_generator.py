@@ -145,13 +145,12 @@ class Generator(nn.Module):
         c0 = self.x.shape[1]
         return c0 % 512 == 0
 
-    def _forward_tensor_core(self, z, view_in):
-        """bf16 pipeline: channels-last activations, transposed convs / projection on the tcgen05 kernels
-        (`ops.convt`), conv outputs in space-to-depth layout.  The ConvTranspose biases in front of an
-        AdaIN are not applied: instance normalisation removes any per-channel constant, so the output is
-        unchanged and their gradient is identically zero (the reference only holds rounding noise there)."""
+    def _trunk_tensor_core(self, z):
+        """bf16 pipeline, view-independent half: styles, learned constant, the two ConvTranspose3d blocks.
+        Returns (h2 NDHWC bf16, styles).  The ConvTranspose biases in front of an AdaIN are not applied: instance
+        normalisation removes any per-channel constant, so the output is unchanged and their gradient is
+        identically zero (the reference only holds rounding noise there)."""
         bf16 = torch.bfloat16
-        n = z.shape[0]
         # all five ZMappings read the same z: one launch (packed (B, 2C) styles, fp32)
         maps = [self.zMapping] + [b.zMapping for b in (self.block1, self.block2, self.block3, self.block4)]
         styles = ops.linear_relu_group(z, [m.linear1.weight for m in maps], [m.linear1.bias for m in maps])
@@ -160,8 +159,12 @@ class Generator(nn.Module):
         for block, style in ((self.block1, styles[1]), (self.block2, styles[2])):
             y = ops.convt(h, block.convTranspose.weight, None, 3, 3)             # (B,S,S,S,8,Cout) s2d
             h = ops.adain_act_channels_last(y, style, None, ndim=3, classes=8)   # (B,2S,2S,2S,Cout) NDHWC
-        size = h.shape[1]
-        a_inv = self._affine(view_in, size, size, z.device)
+        return h, styles
+
+    def _decode_tensor_core(self, h, a_inv, styles):
+        """bf16 pipeline, view-dependent half: rotate + depth fold, 1x1 projection, the two ConvTranspose2d
+        blocks, final layer + tanh.  h: (B,S,S,S,C) NDHWC bf16, a_inv: (B,4,4) fp32 on the device."""
+        n, size = h.shape[0], h.shape[1]
         # rotate + fold depth into channels in one kernel: out[b, z, x, (y, c)] is the projection's A operand
         rot = ops.rotate_resample(h, a_inv, ops.HG_BORDER_ZERO, ops.HG_NDHWC, ops.HG_PROJ)
         c = rot.shape[-1]
@@ -179,6 +182,68 @@ class Generator(nn.Module):
         # patched-128 head (ConvTranspose2d k4 s2): cuDNN on the NHWC buffer viewed as channels_last NCHW
         return torch.tanh(self.final_layer(h.permute(0, 3, 1, 2)))
 
+    def _forward_tensor_core(self, z, view_in):
+        """bf16 pipeline: channels-last activations, transposed convs / projection on the tcgen05 kernels
+        (`ops.convt`), conv outputs in space-to-depth layout."""
+        h, styles = self._trunk_tensor_core(z)
+        size = h.shape[1]
+        return self._decode_tensor_core(h, self._affine(view_in, size, size, z.device), styles)
+
+    # ---- fp32 parity path, split the same way --------------------------------------------------
+    def _trunk(self, z):
+        h0 = ops.adain_act(self.x, self.zMapping.style(z), None, neg_slope=0.0)      # constant never repeated B times
+        return self.block2(self.block1(h0, z), z)
+
+    def _decode(self, h2, view_in, z):
+        batch_size = z.shape[0]
+        rot = self.transformation3d(h2, view_in, h2.shape[2], h2.shape[2])
+        # fold depth into channels: out[b, c*S + j, r, col] = rot[b, c, r, S-1-j, col]  (:130-133)
+        s = rot.shape[2]
+        h2_2d = rot.permute(0, 1, 3, 2, 4).flip(2).reshape(batch_size, -1, s, s)
+        h3 = F.relu(self.convTranspose2d1(h2_2d))
+        h4 = self.block3(h3, z)
+        h5 = self.block4(h4, z)
+        return torch.tanh(self.final_layer(h5))
+
+    # ---- view sweeps (SURVEY 3.5 / 8-f3) ---------------------------------------------------------
+    @torch.no_grad()
+    def render_views(self, z, views):
+        """Every latent under every view: (B, V, out_planes, H, W).
+
+        The reference's figure callbacks (core/figures/types.py:217-239 ElevationStep, :300-322 ElevationGif) call
+        `generator(z, view_in=view)` once per view with the SAME z, recomputing the view-independent 3D trunk
+        (constant -> AdaIN -> two ConvTranspose3d blocks) every time.  Here the trunk runs once per z and only
+        rotate -> projection -> 2D decoder runs per view; `render_views(z, views)[:, v]` is bit-identical to
+        `forward(z, view_in=views[v])` under the same autocast state.
+
+        views: (V, 6) rows (azimuth, elevation, scale, tx, ty, tz) shared by all latents, or (B, V, 6);
+        numpy float64 or torch, like `view_in`."""
+        n = z.shape[0]
+        views = views.detach().cpu().numpy() if isinstance(views, torch.Tensor) else np.asarray(views)
+        if views.ndim == 2:
+            views = np.broadcast_to(views[None], (n,) + views.shape)
+        if views.ndim != 3 or views.shape[0] != n or views.shape[2] != 6:
+            raise ValueError("views must be (V, 6) or (B, V, 6)")
+        n_views = views.shape[1]
+        tc = self._use_tensor_core_path(z)
+        if tc:
+            h, styles = self._trunk_tensor_core(z)
+            size = h.shape[1]
+        else:
+            h = self._trunk(z)
+            size = h.shape[2]
+        # all B*V inverse transforms in one host pass + one H2D copy
+        a_inv = ops.view_to_affine(np.ascontiguousarray(views.reshape(n * n_views, 6)), size, size)
+        a_inv = a_inv.reshape(n, n_views, 4, 4).to(z.device, non_blocking=True)
+        out = None
+        for v in range(n_views):
+            a_v = a_inv[:, v].contiguous()
+            img = self._decode_tensor_core(h, a_v, styles) if tc else self._decode(h, a_v, z)
+            if out is None:
+                out = torch.empty((n, n_views) + tuple(img.shape[1:]), dtype=img.dtype, device=img.device)
+            out[:, v] = img
+        return out
+
     def forward(self, z, view_in=None):
         batch_size = z.shape[0]
         if view_in is None:
@@ -186,16 +251,4 @@ class Generator(nn.Module):
         if self._use_tensor_core_path(z):
             return self._forward_tensor_core(z, view_in)
 
-        h0 = ops.adain_act(self.x, self.zMapping.style(z), None, neg_slope=0.0)      # constant never repeated B times
-        h1 = self.block1(h0, z)
-        h2 = self.block2(h1, z)
-
-        rot = self.transformation3d(h2, view_in, h2.shape[2], h2.shape[2])
-        # fold depth into channels: out[b, c*S + j, r, col] = rot[b, c, r, S-1-j, col]  (:130-133)
-        s = rot.shape[2]
-        h2_2d = rot.permute(0, 1, 3, 2, 4).flip(2).reshape(batch_size, -1, s, s)
-
-        h3 = F.relu(self.convTranspose2d1(h2_2d))
-        h4 = self.block3(h3, z)
-        h5 = self.block4(h4, z)
-        return torch.tanh(self.final_layer(h5))
+        return self._decode(self._trunk(z), view_in, z)

@@ -67,6 +67,36 @@ def test_generator_accepts_tensor_views_and_samples_views():
     assert tuple(net128(z).shape) == (4, 3, 128, 128)
 
 
+@pytest.mark.parametrize("in_planes,bf16", [(8, False), (64, True)])
+def test_render_views_equals_per_view_forward(in_planes, bf16):
+    """View sweep (BASELINE cfg 5): the 3D trunk runs once per z, rotate + decoder per view; every column
+    must equal the reference-style call `generator(z, view_in=view)` (core/figures/types.py:233-237)."""
+    torch.manual_seed(5)
+    net = Generator(in_planes, 3, 128, SimpleNamespace(), 64).to(DEV).eval()
+    z = torch.rand(3, 128, device=DEV) * 2 - 1
+    views = np.zeros((6, 6))
+    views[:, 0] = np.deg2rad(np.linspace(220, 320, 6))
+    views[:, 1] = np.deg2rad(90.0)
+    views[:, 2] = 1.0
+    with torch.autocast("cuda", dtype=torch.bfloat16, enabled=bf16), torch.no_grad():
+        assert net._use_tensor_core_path(z) == bf16
+        sweep = net.render_views(z, views)
+        assert tuple(sweep.shape) == (3, 6, 3, 64, 64)
+        for v in range(6):
+            one = net(z, view_in=np.repeat(views[v:v + 1], 3, axis=0))
+            if bf16:
+                assert torch.equal(sweep[:, v], one)       # our kernels only: deterministic
+            else:
+                assert rel_err(sweep[:, v], one) < 1e-6    # cuDNN fp32 convs are not bitwise run-to-run deterministic
+        # per-latent views (B, V, 6)
+        pv = np.stack([np.roll(views, i, axis=0) for i in range(3)])
+        sweep2 = net.render_views(z, pv)
+        one = net(z, view_in=pv[:, 2])
+        assert rel_err(sweep2[:, 2], one) < 1e-6
+    with pytest.raises(ValueError):
+        net.render_views(z, np.zeros((4, 5)))
+
+
 def _bf16_errors(net, p, z, view, dout):
     zg = z.to(DEV).requires_grad_(True)
     with torch.autocast("cuda", dtype=torch.bfloat16):

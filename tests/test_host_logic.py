@@ -37,6 +37,21 @@ def test_view_to_affine_sweep():
         ops.view_to_affine(np.zeros((4, 5)))
 
 
+def test_view_to_affine_batched_sweep_equals_per_view():
+    """`Generator.render_views` converts all B*V views in one host pass: each matrix must carry the same bits as the
+    per-view call the reference's figure callbacks make (core/figures/types.py:233-237)."""
+    rs = np.random.RandomState(3)
+    b, v = 5, 36
+    views = np.zeros((b, v, 6))
+    views[..., 0] = np.deg2rad(np.linspace(220, 320, v))[None]
+    views[..., 1] = np.deg2rad(rs.randint(70, 110, (b, 1)))
+    views[..., 2] = 1.0
+    views[..., 3:] = rs.uniform(-1, 1, (b, 1, 3))
+    a = ops.view_to_affine(views.reshape(b * v, 6)).reshape(b, v, 4, 4)
+    for i in range(v):
+        assert torch.equal(a[:, i], ops.view_to_affine(views[:, i]))
+
+
 def test_state_dict_keys_match_reference():
     spec = json.load(open(os.path.join(GOLDEN, "state_dict_spec.json")))
     g = G.Generator(64, 3, 128, VIEW_ARGS, 64, gpu=False)

@@ -20,6 +20,15 @@ if has bench; then
   timeout 900 python bench.py --steps 60 --warmup 9 > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err
   echo "bench exit $?"; cat $OUT/${TAG}_bench.json
 fi
+if has bench128; then
+  timeout 600 python bench.py --steps 30 --warmup 6 --img-size 128 --batch 32 --no-cpu-baseline --no-roofline > $OUT/${TAG}_bench128.json 2> $OUT/${TAG}_bench128.err
+  echo "bench128 exit $?"; cat $OUT/${TAG}_bench128.json
+fi
+if has sweep; then
+  timeout 600 python tools/sweep_bench.py --img-size 64 > $OUT/${TAG}_sweep.txt 2>&1
+  timeout 600 python tools/sweep_bench.py --img-size 128 >> $OUT/${TAG}_sweep.txt 2>&1
+  echo "sweep exit $?"; grep metric $OUT/${TAG}_sweep.txt
+fi
 if has micro; then
   timeout 900 python tools/microbench.py all > $OUT/${TAG}_microbench.txt 2>&1
   echo "microbench exit $?"
