@@ -20,11 +20,26 @@
 //             apply kernel  -- dx = rstd * (g * s - s * sum(g) / N - xhat * s * sum(g * xhat) / Nvar)
 // Small instances (a sample <= 64 KB: the discriminator's maps) run both phases in ONE kernel, one CTA per
 // sample, the second pass served by L1.  Algorithmic HBM bytes: fwd 2 * B*N*C*2, bwd 3 * B*N*C*2.
+//
+// Cluster path (the normal case for the generator's AdaIN sites and the larger discriminator maps): a sample is
+// spread over a thread-block CLUSTER of up to 8 CTAs; every thread parks its rows (<= 16 x 16 bytes) in shared
+// memory with cp.async (private slots: no CTA barrier needed), the per-CTA partial sums are exchanged through
+// distributed shared memory (cluster.map_shared_rank, fixed rank order -> deterministic), and the normalised rows
+// are produced from the staged copy: ONE kernel, x is read from HBM exactly once (forward: 1 read + 1 write, backward: 2 reads + 1 write = the algorithmic traffic).
+#include <cooperative_groups.h>
+#include <stdlib.h>
+
 #include "hg_common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace hg {
 
 constexpr int kClThreads = 256;
+constexpr int kClBwdClusterThreads = 512;   // cluster backward: two tensors in registers -> twice the threads per CTA
+constexpr int kClClusterMaxC = 512;         // channels the cluster path covers (per-CTA partials in static smem)
+constexpr int kClClusterFwdRows = 16;       // rows (16-byte units) a thread stages: 64 KB per forward CTA
+constexpr int kClClusterBwdRows = 8;        // per tensor: 2 x 64 KB per backward CTA
 constexpr int kClUnroll = 8;          // forward: independent 16-byte loads in flight per thread
 constexpr int kClUnrollBwd = 4;       // backward streams two tensors: 2 x 4 loads in flight
 constexpr int kClMaxChunks = 32;
@@ -78,6 +93,7 @@ struct ClGeom {
 // Sum the two 8-float partials of all row slots of the CTA in a fixed order; result valid for every thread.
 // Row slots that share a warp (lanes < 32) are folded with xor-shuffles first, the remaining <= 8 groups go
 // through shared memory laid out [group][value][channel octet] (conflict-free).
+template <int NT = kClThreads>
 __device__ __forceinline__ void cta_rowslot_sum(float (&a)[8], float (&b)[8], float *red, int lanes, int rows_per_pass,
                                                 int cs, int rs)
 {
@@ -89,7 +105,7 @@ __device__ __forceinline__ void cta_rowslot_sum(float (&a)[8], float (&b)[8], fl
         }
     }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int groups = lanes < 32 ? kClThreads / 32 : rows_per_pass;
+    const int groups = lanes < 32 ? NT / 32 : rows_per_pass;
     const int grp = lanes < 32 ? warp : rs;
     __syncthreads();
     if (lanes >= 32 || lane < lanes) {
@@ -434,6 +450,192 @@ __global__ void __launch_bounds__(kClThreads) adain_cl_bwd_apply_kernel(const __
     bwd_apply(x + base, dy + base, dx + base, g, r0, r1, rs, st, slope, k1, k2);
 }
 
+
+// ---- cluster path -------------------------------------------------------------------------------------
+// grid (CS, B), cluster (CS, 1, 1): CTA `blockIdx.x` of the cluster owns rows [blockIdx.x * U * rpp, +U * rpp) of
+// sample blockIdx.y; thread (rs, cs) holds rows r0 + rs + u * rpp, u < U, of channel octet cs in registers.
+
+// Publish this CTA's two 8-float partials per channel octet, sum the cluster's in rank order (every thread ends up
+// with the same bits).  The caller must cluster.sync() once more before the CTA exits (remote reads of cpart).
+__device__ __forceinline__ void cluster_octet_sum(cg::cluster_group &cluster, float (&a)[8], float (&b)[8], float *cpart, int C,
+                                                  int cs, int rs)
+{
+    if (rs == 0) {
+        float4 *pa = reinterpret_cast<float4 *>(cpart + cs * 8), *pb = reinterpret_cast<float4 *>(cpart + C + cs * 8);
+        pa[0] = make_float4(a[0], a[1], a[2], a[3]); pa[1] = make_float4(a[4], a[5], a[6], a[7]);
+        pb[0] = make_float4(b[0], b[1], b[2], b[3]); pb[1] = make_float4(b[4], b[5], b[6], b[7]);
+    }
+    cluster.sync();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] = b[j] = 0.f;
+    const unsigned n = cluster.num_blocks();
+    for (unsigned r = 0; r < n; ++r) {
+        const float *rp = cluster.map_shared_rank(cpart, r);
+        const float4 *pa = reinterpret_cast<const float4 *>(rp + cs * 8), *pb = reinterpret_cast<const float4 *>(rp + C + cs * 8);
+        const float4 a0 = pa[0], a1 = pa[1], b0 = pb[0], b1 = pb[1];
+        a[0] += a0.x; a[1] += a0.y; a[2] += a0.z; a[3] += a0.w; a[4] += a1.x; a[5] += a1.y; a[6] += a1.z; a[7] += a1.w;
+        b[0] += b0.x; b[1] += b0.y; b[2] += b0.z; b[3] += b0.w; b[4] += b1.x; b[5] += b1.y; b[6] += b1.z; b[7] += b1.w;
+    }
+}
+
+// 16-byte asynchronous global -> shared copy (LDGSTS, L2 only): the rows a thread owns wait in shared memory,
+// slot [u][tid], instead of in registers; only the issuing thread reads them back, so cp.async.wait_all is the only
+// synchronisation they need.
+__device__ __forceinline__ void cp_async_16(void *smem_dst, const void *gsrc)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+__global__ void __launch_bounds__(kClThreads, 2) adain_cl_cluster_fwd_kernel(const __nv_bfloat16 *__restrict__ x,
+                                                                             const float *__restrict__ scale,
+                                                                             const float *__restrict__ bias,
+                                                                             __nv_bfloat16 *__restrict__ y,
+                                                                             float *__restrict__ save_mean,
+                                                                             float *__restrict__ save_rstd, ClGeom g, int U,
+                                                                             int sbs, float eps, float slope)
+{
+    extern __shared__ __align__(16) unsigned char cl_dyn[];
+    uint4 *tile = reinterpret_cast<uint4 *>(cl_dyn) + threadIdx.x;      // [U][kClThreads], this thread's column
+    __shared__ float red[kClThreads * 16];
+    __shared__ __align__(16) float cpart[2 * kClClusterMaxC];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int cs = threadIdx.x % g.lanes, rs = threadIdx.x / g.lanes;
+    const int b = blockIdx.y;
+    const __nv_bfloat16 *xb = x + (size_t)b * g.N * g.C + cs * 8;
+    const int r0 = blockIdx.x * (U * g.rows_per_pass) + rs;
+    for (int u = 0; u < U; ++u) cp_async_16(tile + u * kClThreads, xb + (size_t)(r0 + u * g.rows_per_pass) * g.C);
+    float piv[8], s1[8], s2[8];
+    unpack8(__ldg(reinterpret_cast<const uint4 *>(xb)), piv);           // pivot K = the sample's first row
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
+    cp_async_wait_all();
+#pragma unroll 4
+    for (int u = 0; u < U; ++u) {
+        float f[8];
+        unpack8(tile[u * kClThreads], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float d = f[j] - piv[j];
+            s1[j] += d;
+            s2[j] = fmaf(d, d, s2[j]);
+        }
+    }
+    cta_rowslot_sum<kClThreads>(s1, s2, red, g.lanes, g.rows_per_pass, cs, rs);
+    cluster_octet_sum(cluster, s1, s2, cpart, g.C, cs, rs);
+    // y = act(x * a + c),  a = scale * rstd,  c = bias - mean * a; the cluster backward recomputes the same a, c
+    // from the saved statistics (same bits, same activation mask)
+    float a[8], c[8];
+    const float inv_n = 1.f / (float)g.N;
+    const bool publish = blockIdx.x == 0 && rs == 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float d = s1[j] * inv_n;                                  // mean - K
+        const float mean = piv[j] + d;
+        // Nvar = N - 1: unbiased variance (:338), eps inside the rsqrt (:339); Nvar = N: InstanceNorm2d
+        const float var = fmaxf(s2[j] - s1[j] * d, 0.f) / (float)g.Nvar;
+        const float rstd = __frsqrt_rn(var + eps);
+        if (publish) {
+            save_mean[(size_t)b * g.C + cs * 8 + j] = mean;
+            save_rstd[(size_t)b * g.C + cs * 8 + j] = rstd;
+        }
+        a[j] = __fmul_rn(scale ? scale[(size_t)b * sbs + cs * 8 + j] : 1.f, rstd);
+        c[j] = __fsub_rn(bias ? bias[(size_t)b * sbs + cs * 8 + j] : 0.f, __fmul_rn(mean, a[j]));
+    }
+    __nv_bfloat16 *yb = y + (size_t)b * g.N * g.C + cs * 8;
+#pragma unroll 4
+    for (int u = 0; u < U; ++u) {
+        float f[8];
+        unpack8(tile[u * kClThreads], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float p = fmaf(f[j], a[j], c[j]);
+            f[j] = p > 0.f ? p : p * slope;
+        }
+        st_stream_16(yb + (size_t)upsampled_row(r0 + u * g.rows_per_pass, g.ndim, g.logS, g.logP) * g.C, pack8(f));
+    }
+    cluster.sync();                                                     // cpart stays alive until every peer has read it
+}
+
+__global__ void __launch_bounds__(kClBwdClusterThreads, 1) adain_cl_cluster_bwd_kernel(
+    const __nv_bfloat16 *__restrict__ x, const __nv_bfloat16 *__restrict__ dy, const float *__restrict__ scale,
+    const float *__restrict__ bias, const float *__restrict__ save_mean, const float *__restrict__ save_rstd,
+    __nv_bfloat16 *__restrict__ dx, float *__restrict__ dscale, float *__restrict__ dbias, ClGeom g, int U, int sbs, int dsbs,
+    float slope)
+{
+    constexpr int NT = kClBwdClusterThreads;
+    extern __shared__ __align__(16) unsigned char cl_dyn[];
+    uint4 *xt = reinterpret_cast<uint4 *>(cl_dyn) + threadIdx.x;        // [U][NT] rows of x, then [U][NT] rows of dy
+    uint4 *gt = xt + U * NT;
+    __shared__ float red[NT * 16];
+    __shared__ __align__(16) float cpart[2 * kClClusterMaxC];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int cs = threadIdx.x % g.lanes, rs = threadIdx.x / g.lanes;
+    const int b = blockIdx.y;
+    const size_t base = (size_t)b * g.N * g.C + cs * 8;
+    const int r0 = blockIdx.x * (U * g.rows_per_pass) + rs;
+    for (int u = 0; u < U; ++u) {
+        const int rr = r0 + u * g.rows_per_pass;
+        cp_async_16(xt + u * NT, x + base + (size_t)rr * g.C);
+        cp_async_16(gt + u * NT, dy + base + (size_t)upsampled_row(rr, g.ndim, g.logS, g.logP) * g.C);
+    }
+    // phase 1 constants: a, c (the forward's pre-activation x * a + c -> activation mask) and the mean
+    float a[8], c[8], mean[8];
+    const float *pm = save_mean + (size_t)b * g.C + cs * 8, *pr = save_rstd + (size_t)b * g.C + cs * 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        mean[j] = pm[j];
+        a[j] = __fmul_rn(scale ? scale[(size_t)b * sbs + cs * 8 + j] : 1.f, pr[j]);
+        c[j] = __fsub_rn(bias ? bias[(size_t)b * sbs + cs * 8 + j] : 0.f, __fmul_rn(mean[j], a[j]));
+    }
+    float sg[8], sgx[8];                                                // sum(g), sum(g * (x - mean))
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sg[j] = sgx[j] = 0.f;
+    cp_async_wait_all();
+#pragma unroll 2
+    for (int u = 0; u < U; ++u) {
+        float xf[8], gf[8];
+        unpack8(xt[u * NT], xf);
+        unpack8(gt[u * NT], gf);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float gg = fmaf(xf[j], a[j], c[j]) > 0.f ? gf[j] : gf[j] * slope;
+            sg[j] += gg;
+            sgx[j] = fmaf(gg, xf[j] - mean[j], sgx[j]);
+        }
+    }
+    cta_rowslot_sum<NT>(sg, sgx, red, g.lanes, g.rows_per_pass, cs, rs);
+    cluster_octet_sum(cluster, sg, sgx, cpart, g.C, cs, rs);
+    // phase 2 constants: dx = rstd * (g s - s sum(g) / N - xhat s sum(g xhat) / Nvar) = g * a - (x * c2 + c1)
+    const bool publish = blockIdx.x == 0 && rs == 0 && dscale && dbias;
+    float c1[8], c2[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float rstd = pr[j];
+        const float sgxh = sgx[j] * rstd;                               // sum(g * xhat)
+        if (publish) {
+            dbias[(size_t)b * dsbs + cs * 8 + j] = sg[j];
+            dscale[(size_t)b * dsbs + cs * 8 + j] = sgxh;
+        }
+        c2[j] = a[j] * rstd * (sgxh / (float)g.Nvar);                   // s rstd^2 sum(g xhat) / Nvar
+        c1[j] = a[j] * (sg[j] / (float)g.N) - mean[j] * c2[j];
+    }
+#pragma unroll 2
+    for (int u = 0; u < U; ++u) {
+        float xf[8], gf[8];
+        unpack8(xt[u * NT], xf);
+        unpack8(gt[u * NT], gf);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float gg = fmaf(xf[j], a[j], c[j]) > 0.f ? gf[j] : gf[j] * slope;
+            xf[j] = fmaf(gg, a[j], -fmaf(xf[j], c2[j], c1[j]));
+        }
+        st_stream_16(dx + base + (size_t)(r0 + u * g.rows_per_pass) * g.C, pack8(xf));
+    }
+    cluster.sync();
+}
+
 static int ilog2(int v)
 {
     int l = 0;
@@ -479,6 +681,58 @@ static int cl_geom(const char *who, int batch, int channels, int ndim, int size,
     return HG_OK;
 }
 
+
+// Cluster plan for a CTA of `threads`: rows_per_pass = threads / lanes, q = N / rows_per_pass row passes per sample,
+// split over the largest cluster size cs in {8, 4, 2} that leaves u = q / cs <= max_u rows per thread.
+// Returns false when the instance has no such split (or HG_ADAIN_CL_NO_CLUSTER is set: A/B runs and tests of the
+// chunked kernels) -> the chunked two-kernel path takes it.
+static bool cl_cluster_plan(const ClGeom &g, int threads, int max_u, ClGeom &cg_out, int &cs_out, int &u_out)
+{
+    const char *off = getenv("HG_ADAIN_CL_NO_CLUSTER");
+    if (off && off[0] && off[0] != '0') return false;
+    if (g.C > kClClusterMaxC || g.lanes > threads) return false;
+    if ((long long)g.N * g.C * 2 < 32 * 1024) return false;           // tiny instances: one CTA per sample is enough
+    const int rpp = threads / g.lanes;
+    if (g.N % rpp) return false;
+    const int q = g.N / rpp;
+    for (int cs = 8; cs >= 2; cs >>= 1) {
+        if (q % cs) continue;
+        const int u = q / cs;
+        if (u > max_u) continue;
+        cg_out = g;
+        cg_out.rows_per_pass = rpp;
+        cg_out.chunk_rows = u * rpp;
+        cg_out.chunks = cs;
+        cs_out = cs;
+        u_out = u;
+        return true;
+    }
+    return false;
+}
+
+template <typename K, typename... Args>
+static int cl_cluster_launch(const char *what, K kernel, int cs, int batch, int threads, size_t smem, cudaStream_t st, Args... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(cs, batch);
+    cfg.blockDim = dim3(threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cs;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, args...);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(HG_ERR_LAUNCH, "%s: %s", what, cudaGetErrorString(e));
+    }
+    return check_launch(what);
+}
+
 extern "C" long long hg_adain_cl_workspace_bytes(int batch, int channels, int ndim, int size, int classes)
 {
     ClGeom g;
@@ -500,6 +754,21 @@ extern "C" int hg_adain_cl_fwd(const void *x, const float *scale, const float *b
     const __nv_bfloat16 *xp = static_cast<const __nv_bfloat16 *>(x);
     __nv_bfloat16 *yp = static_cast<__nv_bfloat16 *>(y);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    {
+        ClGeom cgm;
+        int cs = 0, u = 0;
+        if (cl_cluster_plan(g, kClThreads, kClClusterFwdRows, cgm, cs, u)) {
+            static bool attr_done = false;      // not a stream operation (graph-capture safe)
+            if (!attr_done) {
+                cudaFuncSetAttribute(adain_cl_cluster_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     kClClusterFwdRows * kClThreads * 16);
+                attr_done = true;
+            }
+            return cl_cluster_launch("hg_adain_cl_fwd(cluster)", adain_cl_cluster_fwd_kernel, cs, batch, kClThreads,
+                                     (size_t)u * kClThreads * 16, st, xp, scale, bias, yp, save_mean, save_rstd, cgm, u, sb_stride,
+                                     eps, neg_slope);
+        }
+    }
     dim3 grid(g.chunks, batch);
     if (g.chunks == 1) {
         adain_cl_apply_kernel<true><<<grid, kClThreads, 0, st>>>(xp, nullptr, scale, bias, yp, save_mean, save_rstd, g, sb_stride,
@@ -533,6 +802,21 @@ extern "C" int hg_adain_cl_bwd(const void *x, const void *dy, const float *scale
     const __nv_bfloat16 *xp = static_cast<const __nv_bfloat16 *>(x), *gp = static_cast<const __nv_bfloat16 *>(dy);
     __nv_bfloat16 *dp = static_cast<__nv_bfloat16 *>(dx);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    {
+        ClGeom cgm;
+        int cs = 0, u = 0;
+        if (cl_cluster_plan(g, kClBwdClusterThreads, kClClusterBwdRows, cgm, cs, u)) {
+            static bool attr_done = false;      // not a stream operation (graph-capture safe)
+            if (!attr_done) {
+                cudaFuncSetAttribute(adain_cl_cluster_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     2 * kClClusterBwdRows * kClBwdClusterThreads * 16);
+                attr_done = true;
+            }
+            return cl_cluster_launch("hg_adain_cl_bwd(cluster)", adain_cl_cluster_bwd_kernel, cs, batch, kClBwdClusterThreads,
+                                     (size_t)2 * u * kClBwdClusterThreads * 16, st, xp, gp, scale, bias, save_mean, save_rstd, dp,
+                                     dscale, dbias, cgm, u, sb_stride, dsb_stride, neg_slope);
+        }
+    }
     dim3 grid(g.chunks, batch);
     if (g.chunks == 1) {
         adain_cl_bwd_apply_kernel<true><<<grid, kClThreads, 0, st>>>(xp, gp, nullptr, scale, bias, save_mean, save_rstd, dp, dscale,

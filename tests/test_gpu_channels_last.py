@@ -123,6 +123,36 @@ def test_adain_channels_last(b, ndim, size, c, classes, slope):
     assert rel_err(sg.grad, sr.grad) < 2e-2 and rel_err(bg.grad, br.grad) < 2e-2
 
 
+@pytest.mark.parametrize("b,ndim,size,c,classes", CASES + [(3, 2, 16, 128, 1), (2, 2, 8, 256, 1)])
+def test_adain_channels_last_cluster_vs_chunked(b, ndim, size, c, classes, monkeypatch):
+    """The single-pass cluster kernels (DSMEM reduction, rows staged in shared memory) against the chunked two-kernel
+    path on the same inputs: statistics to fp32 rounding, outputs / gradients to bf16 rounding."""
+    gen = torch.Generator().manual_seed(size + c)
+    sp = (size,) * ndim
+    shape = (b, *sp, classes, c) if classes > 1 else (b, *sp, c)
+    x = (torch.randn(*shape, generator=gen) * 1.5 + 0.3).to(BF).to(DEV)
+    s = (torch.rand(b, c, generator=gen) + 0.2).to(DEV)
+    bb = torch.randn(b, c, generator=gen).to(DEV)
+    up = 2 if classes > 1 else 1
+    dy = torch.randn(b, *((up * size,) * ndim), c, generator=gen).to(BF).to(DEV)
+
+    def run():
+        xg = x.clone().requires_grad_(True); sg = s.clone().requires_grad_(True); bg = bb.clone().requires_grad_(True)
+        y = ops.adain_act_channels_last(xg, sg, bg, ndim, classes, 0.2)
+        (y.float() * dy.float()).sum().backward()
+        return y.detach().float(), xg.grad.float(), sg.grad, bg.grad
+
+    got = run()
+    monkeypatch.setenv("HG_ADAIN_CL_NO_CLUSTER", "1")
+    ref = run()
+    monkeypatch.delenv("HG_ADAIN_CL_NO_CLUSTER")
+    again = run()
+    assert rel_err(got[0], ref[0]) < 2 ** -7 and rel_err(got[1], ref[1]) < 2 ** -6
+    assert rel_err(got[2], ref[2]) < 1e-4 and rel_err(got[3], ref[3]) < 1e-4
+    for u, v in zip(got, again):
+        assert torch.equal(u, v)                      # deterministic (fixed reduction order through the cluster)
+
+
 def test_unsupported():
     from lightning_gan_zoo_b200._lib import HologanB200Error
     x = torch.zeros(1, 16, 16, 4, 24, dtype=BF, device=DEV)

@@ -12,7 +12,7 @@ has() { case " $STAGES " in *" $1 "*) return 0;; esac; return 1; }
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $OUT/${TAG}_gpu.txt 2>&1
 
 if has tests; then
-  timeout 1500 python -m pytest tests -m gpu ${PYTEST_X--x} -q > $OUT/${TAG}_pytest_gpu.txt 2>&1
+  timeout 600 python -m pytest tests -m gpu ${PYTEST_X--x} -q > $OUT/${TAG}_pytest_gpu.txt 2>&1
   echo "pytest exit $?" >> $OUT/${TAG}_pytest_gpu.txt
   tail -5 $OUT/${TAG}_pytest_gpu.txt
 fi
