@@ -455,10 +455,13 @@ __global__ void __launch_bounds__(kClThreads) adain_cl_bwd_apply_kernel(const __
 // grid (CS, B), cluster (CS, 1, 1): CTA `blockIdx.x` of the cluster owns rows [blockIdx.x * U * rpp, +U * rpp) of
 // sample blockIdx.y; thread (rs, cs) holds rows r0 + rs + u * rpp, u < U, of channel octet cs in registers.
 
-// Publish this CTA's two 8-float partials per channel octet, sum the cluster's in rank order (every thread ends up
-// with the same bits).  The caller must cluster.sync() once more before the CTA exits (remote reads of cpart).
-__device__ __forceinline__ void cluster_octet_sum(cg::cluster_group &cluster, float (&a)[8], float (&b)[8], float *cpart, int C,
-                                                  int cs, int rs)
+// Publish this CTA's two 8-float partials per channel octet in `cpart`, sum the cluster's in rank order (every CTA /
+// thread ends up with the same bits).  Only C / 2 threads touch remote shared memory (one float4 column each, the
+// <= 8 remote loads in flight together); the totals go through the local `ctot` to the rest of the CTA -- a first
+// version in which every thread read every peer moved more bytes over the SM-to-SM network than the kernel reads
+// from HBM.  The caller must cluster.sync() once more before the CTA exits (peers may still be reading cpart).
+__device__ __forceinline__ void cluster_octet_sum(cg::cluster_group &cluster, float (&a)[8], float (&b)[8], float *cpart,
+                                                  float *ctot, int C, int cs, int rs)
 {
     if (rs == 0) {
         float4 *pa = reinterpret_cast<float4 *>(cpart + cs * 8), *pb = reinterpret_cast<float4 *>(cpart + C + cs * 8);
@@ -466,16 +469,23 @@ __device__ __forceinline__ void cluster_octet_sum(cg::cluster_group &cluster, fl
         pb[0] = make_float4(b[0], b[1], b[2], b[3]); pb[1] = make_float4(b[4], b[5], b[6], b[7]);
     }
     cluster.sync();
-#pragma unroll
-    for (int j = 0; j < 8; ++j) a[j] = b[j] = 0.f;
     const unsigned n = cluster.num_blocks();
-    for (unsigned r = 0; r < n; ++r) {
-        const float *rp = cluster.map_shared_rank(cpart, r);
-        const float4 *pa = reinterpret_cast<const float4 *>(rp + cs * 8), *pb = reinterpret_cast<const float4 *>(rp + C + cs * 8);
-        const float4 a0 = pa[0], a1 = pa[1], b0 = pb[0], b1 = pb[1];
-        a[0] += a0.x; a[1] += a0.y; a[2] += a0.z; a[3] += a0.w; a[4] += a1.x; a[5] += a1.y; a[6] += a1.z; a[7] += a1.w;
-        b[0] += b0.x; b[1] += b0.y; b[2] += b0.z; b[3] += b0.w; b[4] += b1.x; b[5] += b1.y; b[6] += b1.z; b[7] += b1.w;
+    for (int i = threadIdx.x; i < C / 2; i += blockDim.x) {             // 2C floats = C / 2 float4 columns
+        float4 v[8];
+#pragma unroll
+        for (unsigned r = 0; r < 8; ++r)
+            if (r < n) v[r] = reinterpret_cast<const float4 *>(cluster.map_shared_rank(cpart, r))[i];
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (unsigned r = 0; r < 8; ++r)
+            if (r < n) { acc.x += v[r].x; acc.y += v[r].y; acc.z += v[r].z; acc.w += v[r].w; }
+        reinterpret_cast<float4 *>(ctot)[i] = acc;
     }
+    __syncthreads();
+    const float4 *pa = reinterpret_cast<const float4 *>(ctot + cs * 8), *pb = reinterpret_cast<const float4 *>(ctot + C + cs * 8);
+    const float4 a0 = pa[0], a1 = pa[1], b0 = pb[0], b1 = pb[1];
+    a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+    b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w; b[4] = b1.x; b[5] = b1.y; b[6] = b1.z; b[7] = b1.w;
 }
 
 // 16-byte asynchronous global -> shared copy (LDGSTS, L2 only): the rows a thread owns wait in shared memory,
@@ -499,7 +509,7 @@ __global__ void __launch_bounds__(kClThreads, 2) adain_cl_cluster_fwd_kernel(con
     extern __shared__ __align__(16) unsigned char cl_dyn[];
     uint4 *tile = reinterpret_cast<uint4 *>(cl_dyn) + threadIdx.x;      // [U][kClThreads], this thread's column
     __shared__ float red[kClThreads * 16];
-    __shared__ __align__(16) float cpart[2 * kClClusterMaxC];
+    __shared__ __align__(16) float cpart[2 * kClClusterMaxC], ctot[2 * kClClusterMaxC];
     cg::cluster_group cluster = cg::this_cluster();
     const int cs = threadIdx.x % g.lanes, rs = threadIdx.x / g.lanes;
     const int b = blockIdx.y;
@@ -523,7 +533,7 @@ __global__ void __launch_bounds__(kClThreads, 2) adain_cl_cluster_fwd_kernel(con
         }
     }
     cta_rowslot_sum<kClThreads>(s1, s2, red, g.lanes, g.rows_per_pass, cs, rs);
-    cluster_octet_sum(cluster, s1, s2, cpart, g.C, cs, rs);
+    cluster_octet_sum(cluster, s1, s2, cpart, ctot, g.C, cs, rs);
     // y = act(x * a + c),  a = scale * rstd,  c = bias - mean * a; the cluster backward recomputes the same a, c
     // from the saved statistics (same bits, same activation mask)
     float a[8], c[8];
@@ -569,7 +579,7 @@ __global__ void __launch_bounds__(kClBwdClusterThreads, 1) adain_cl_cluster_bwd_
     uint4 *xt = reinterpret_cast<uint4 *>(cl_dyn) + threadIdx.x;        // [U][NT] rows of x, then [U][NT] rows of dy
     uint4 *gt = xt + U * NT;
     __shared__ float red[NT * 16];
-    __shared__ __align__(16) float cpart[2 * kClClusterMaxC];
+    __shared__ __align__(16) float cpart[2 * kClClusterMaxC], ctot[2 * kClClusterMaxC];
     cg::cluster_group cluster = cg::this_cluster();
     const int cs = threadIdx.x % g.lanes, rs = threadIdx.x / g.lanes;
     const int b = blockIdx.y;
@@ -606,7 +616,7 @@ __global__ void __launch_bounds__(kClBwdClusterThreads, 1) adain_cl_cluster_bwd_
         }
     }
     cta_rowslot_sum<NT>(sg, sgx, red, g.lanes, g.rows_per_pass, cs, rs);
-    cluster_octet_sum(cluster, sg, sgx, cpart, g.C, cs, rs);
+    cluster_octet_sum(cluster, sg, sgx, cpart, ctot, g.C, cs, rs);
     // phase 2 constants: dx = rstd * (g s - s sum(g) / N - xhat s sum(g xhat) / Nvar) = g * a - (x * c2 + c1)
     const bool publish = blockIdx.x == 0 && rs == 0 && dscale && dbias;
     float c1[8], c2[8];
@@ -684,14 +694,22 @@ static int cl_geom(const char *who, int batch, int channels, int ndim, int size,
 
 // Cluster plan for a CTA of `threads`: rows_per_pass = threads / lanes, q = N / rows_per_pass row passes per sample,
 // split over the largest cluster size cs in {8, 4, 2} that leaves u = q / cs <= max_u rows per thread.
-// Returns false when the instance has no such split (or HG_ADAIN_CL_NO_CLUSTER is set: A/B runs and tests of the
-// chunked kernels) -> the chunked two-kernel path takes it.
-static bool cl_cluster_plan(const ClGeom &g, int threads, int max_u, ClGeom &cg_out, int &cs_out, int &u_out)
+// Returns false when the instance has no such split, is too small to pay for a cluster launch, or
+// HG_ADAIN_CL_NO_CLUSTER is set (A/B runs and tests of the chunked kernels) -> the chunked two-kernel path takes it.
+static bool cl_cluster_plan(const ClGeom &g, int threads, int max_u, bool backward, ClGeom &cg_out, int &cs_out, int &u_out)
 {
     const char *off = getenv("HG_ADAIN_CL_NO_CLUSTER");
     if (off && off[0] && off[0] != '0') return false;
     if (g.C > kClClusterMaxC || g.lanes > threads) return false;
-    if ((long long)g.N * g.C * 2 < 32 * 1024) return false;           // tiny instances: one CTA per sample is enough
+    // Measured on B200 (profiles/r01g_microbench_pipeline.txt): a cluster launch has a ~6 us floor per wave, so the
+    // forward only wins for the generator's 512 KB instances (24 us vs 32 us); the backward (two staged tensors ->
+    // one 164 KB CTA per SM, 3.5 lock-step waves) does not beat the chunked kernels (62 us vs 59 us) and stays
+    // opt-in (HG_ADAIN_CL_CLUSTER_BWD=1: tests, experiments).
+    if ((long long)g.N * g.C * 2 < 256 * 1024) return false;
+    if (backward) {
+        const char *on = getenv("HG_ADAIN_CL_CLUSTER_BWD");
+        if (!(on && on[0] && on[0] != '0')) return false;
+    }
     const int rpp = threads / g.lanes;
     if (g.N % rpp) return false;
     const int q = g.N / rpp;
@@ -757,7 +775,7 @@ extern "C" int hg_adain_cl_fwd(const void *x, const float *scale, const float *b
     {
         ClGeom cgm;
         int cs = 0, u = 0;
-        if (cl_cluster_plan(g, kClThreads, kClClusterFwdRows, cgm, cs, u)) {
+        if (cl_cluster_plan(g, kClThreads, kClClusterFwdRows, false, cgm, cs, u)) {
             static bool attr_done = false;      // not a stream operation (graph-capture safe)
             if (!attr_done) {
                 cudaFuncSetAttribute(adain_cl_cluster_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -805,7 +823,7 @@ extern "C" int hg_adain_cl_bwd(const void *x, const void *dy, const float *scale
     {
         ClGeom cgm;
         int cs = 0, u = 0;
-        if (cl_cluster_plan(g, kClBwdClusterThreads, kClClusterBwdRows, cgm, cs, u)) {
+        if (cl_cluster_plan(g, kClBwdClusterThreads, kClClusterBwdRows, true, cgm, cs, u)) {
             static bool attr_done = false;      // not a stream operation (graph-capture safe)
             if (!attr_done) {
                 cudaFuncSetAttribute(adain_cl_cluster_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -343,7 +343,12 @@ class HologanTrainer:
         for idx in (0, 1):
             g = torch.cuda.CUDAGraph()
             n0 = _lib.launch_count
-            with torch.cuda.graph(g):
+            if self.world > 1:
+                # the warm-up all-reduces must have left the NCCL watchdog's queue before capture starts, and the
+                # watchdog thread's event queries must not invalidate the capture: thread-local error mode
+                torch.cuda.synchronize(self.device)
+                dist.barrier()
+            with torch.cuda.graph(g, capture_error_mode="thread_local" if self.world > 1 else "global"):
                 loss = self._eager_step(st["real"], st["z"], st["a"], idx)
             graphs[idx] = (g, loss, _lib.launch_count - n0)
         with torch.no_grad():

@@ -123,7 +123,8 @@ def test_adain_channels_last(b, ndim, size, c, classes, slope):
     assert rel_err(sg.grad, sr.grad) < 2e-2 and rel_err(bg.grad, br.grad) < 2e-2
 
 
-@pytest.mark.parametrize("b,ndim,size,c,classes", CASES + [(3, 2, 16, 128, 1), (2, 2, 8, 256, 1)])
+@pytest.mark.parametrize("b,ndim,size,c,classes", [(3, 3, 8, 64, 8), (2, 2, 16, 256, 4), (2, 2, 32, 64, 4), (2, 2, 32, 128, 1),
+                                                  (2, 2, 16, 512, 4), (3, 3, 4, 128, 8)])
 def test_adain_channels_last_cluster_vs_chunked(b, ndim, size, c, classes, monkeypatch):
     """The single-pass cluster kernels (DSMEM reduction, rows staged in shared memory) against the chunked two-kernel
     path on the same inputs: statistics to fp32 rounding, outputs / gradients to bf16 rounding."""
@@ -142,6 +143,7 @@ def test_adain_channels_last_cluster_vs_chunked(b, ndim, size, c, classes, monke
         (y.float() * dy.float()).sum().backward()
         return y.detach().float(), xg.grad.float(), sg.grad, bg.grad
 
+    monkeypatch.setenv("HG_ADAIN_CL_CLUSTER_BWD", "1")        # the cluster backward is opt-in (slower than the chunked one)
     got = run()
     monkeypatch.setenv("HG_ADAIN_CL_NO_CLUSTER", "1")
     ref = run()

@@ -29,6 +29,15 @@ if has sweep; then
   timeout 600 python tools/sweep_bench.py --img-size 128 >> $OUT/${TAG}_sweep.txt 2>&1
   echo "sweep exit $?"; grep metric $OUT/${TAG}_sweep.txt
 fi
+if has tests_cl; then
+  timeout 600 python -m pytest tests/test_gpu_channels_last.py tests/test_gpu_generator.py -m gpu -q > $OUT/${TAG}_pytest_cl.txt 2>&1
+  echo "pytest exit $?" >> $OUT/${TAG}_pytest_cl.txt
+  tail -3 $OUT/${TAG}_pytest_cl.txt
+fi
+if has pipe; then
+  timeout 600 python tools/microbench.py pipeline > $OUT/${TAG}_microbench_pipeline.txt 2>&1
+  echo "microbench pipeline exit $?"; grep -E "adain_cl|inorm_cl|rotate_cl|final_conv" $OUT/${TAG}_microbench_pipeline.txt
+fi
 if has micro; then
   timeout 900 python tools/microbench.py all > $OUT/${TAG}_microbench.txt 2>&1
   echo "microbench exit $?"

@@ -174,11 +174,12 @@ def pipeline():
                                 classes, c, ctypes.c_float(1e-8), ctypes.c_float(0.0), biased, ops._stream())
         g = lambda x: _lib.call("hg_adain_cl_bwd", P(x), P(dy), P(sc), P(bi), P(mean), P(rstd), P(dx), P(ds), P(db), P(wsp), nws,
                                 B, c, ndim, size, classes, c, c, ctypes.c_float(0.0), biased, ops._stream())
-        for tag, env in (("", None), (" [chunked]", "1")):          # cluster single-pass kernels vs the chunked two-kernel path
-            if env:
-                os.environ["HG_ADAIN_CL_NO_CLUSTER"] = env
+        # default dispatch / cluster single-pass kernels forced for the backward too / chunked two-kernel path only
+        for tag, env in (("", {}), (" [cluster bwd]", {"HG_ADAIN_CL_CLUSTER_BWD": "1"}), (" [chunked]", {"HG_ADAIN_CL_NO_CLUSTER": "1"})):
+            os.environ.update(env)
             tf = time_rot(f, xs); f(xs[0]); tb = time_rot(g, xs)
-            os.environ.pop("HG_ADAIN_CL_NO_CLUSTER", None)
+            for k in env:
+                os.environ.pop(k, None)
             report(name + " fwd" + tag, tf, 2 * B * n * c * 2)
             report(name + " bwd" + tag, tb, 3 * B * n * c * 2)
     # rotate channels-last -> PROJ
