@@ -388,8 +388,32 @@ def main():
                                               f"{ms:.0f} ms/step"}
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        _exit_without_nccl_teardown(rank)
+
+
+def _exit_without_nccl_teardown(rank: int):
+    """Multi-rank runs end with a hard exit.  Measured on 2 x B200 (profiles/r01h_bench_n2.*): after the JSON line
+    was printed, `dist.barrier(); dist.destroy_process_group()` never returned -- the step's CUDA graphs hold captured
+    NCCL all-reduces, and tearing the communicator down under live graphs blocks.  Nothing after the timed region needs
+    NCCL (the max-over-ranks all-reduce already happened): the other ranks wait on the rendezvous store (TCP, not NCCL)
+    until rank 0 has printed its line, then every rank flushes and leaves with exit code 0."""
+    import sys
+    import time
+    from datetime import timedelta
+    import torch.distributed as dist
+    try:
+        store = dist.distributed_c10d._get_default_store()
+        if rank == 0:
+            store.set("hg_bench_done", "1")
+            time.sleep(0.5)                      # let the store answer the waiters before the server thread dies
+        else:
+            store.wait(["hg_bench_done"], timedelta(seconds=900))
+    except Exception:                            # a missing store / closed connection must not turn into a hang or a failure
+        pass
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)
 
 
 if __name__ == "__main__":

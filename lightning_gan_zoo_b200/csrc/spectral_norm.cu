@@ -16,8 +16,8 @@
 namespace hg {
 
 constexpr int kSnMaxLayers = HG_SN_MAX_LAYERS;
-constexpr int kSnOSplit = 8;        // row splits of the W^T u pass
-constexpr int kSnDotBlocks = 64;    // partial sums of the backward dot product
+constexpr int kSnOSplit = 32;       // row splits of the W^T u pass (<= 16 rows per thread: every load in flight at once)
+constexpr int kSnDotBlocks = 256;   // partial sums of the backward dot product (one per thread of the consumer CTA)
 
 struct SnLayer {
     const float *w;       // (Cout, K) physical order
@@ -51,6 +51,14 @@ __device__ __forceinline__ int sn_logical(int j, int cin, int taps, int channels
     return channels_last ? (j % cin) * taps + j / cin : j;
 }
 
+// 16-byte alignment of every pointer of a vectorised path (parameters and gradient views usually are; a view into a
+// flat buffer behind an odd-sized tensor is not -> scalar path)
+__device__ __forceinline__ bool sn_aligned16(const void *a, const void *b = nullptr, const void *c = nullptr, const void *d = nullptr)
+{
+    return ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(c) |
+             reinterpret_cast<uintptr_t>(d)) & 15) == 0;
+}
+
 template <int NT> __device__ __forceinline__ float sn_block_sum(float v, float *sh)
 {
     v = warp_sum(v);
@@ -73,6 +81,7 @@ __global__ void __launch_bounds__(128) sn_tu_kernel(const __grid_constant__ SnPa
     const int per = (L.cout + kSnOSplit - 1) / kSnOSplit;
     const int o0 = blockIdx.y * per, o1 = min(L.cout, o0 + per);
     float acc = 0.f;
+#pragma unroll 8
     for (int o = o0; o < o1; ++o) acc = fmaf(__ldg(L.w + (size_t)o * L.K + j), __ldg(L.u + o), acc);
     L.t_part[(size_t)blockIdx.y * L.K + j] = acc;
 }
@@ -103,17 +112,27 @@ __global__ void __launch_bounds__(1024) sn_v_kernel(const __grid_constant__ SnPa
     }
 }
 
-// s[o] = W[o] . v  (one warp per row)
+// s[o] = W[o] . v  (one CTA per row: 16-byte loads, all of a thread's loads independent, fixed-order block sum)
 __global__ void __launch_bounds__(256) sn_s_kernel(const __grid_constant__ SnParams p)
 {
+    __shared__ float sh[8];
     const SnLayer &L = p.l[blockIdx.y];
-    const int o = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    const int o = blockIdx.x;
     if (o >= L.cout) return;
     const float *row = L.w + (size_t)o * L.K, *vphys = L.state + 4 + L.cout;
     float acc = 0.f;
-    for (int j = lane; j < L.K; j += 32) acc = fmaf(__ldg(row + j), vphys[j], acc);
-    acc = warp_sum(acc);
-    if (lane == 0) L.s[o] = acc;
+    if (((L.K | L.cout) & 3) == 0 && sn_aligned16(L.w, L.state)) {   // rows and the v vector are 16-byte aligned
+#pragma unroll 4
+        for (int j = threadIdx.x * 4; j < L.K; j += 1024) {
+            const float4 a = __ldg(reinterpret_cast<const float4 *>(row + j));
+            const float4 b = *reinterpret_cast<const float4 *>(vphys + j);
+            acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc); acc = fmaf(a.z, b.z, acc); acc = fmaf(a.w, b.w, acc);
+        }
+    } else {
+        for (int j = threadIdx.x; j < L.K; j += 256) acc = fmaf(__ldg(row + j), vphys[j], acc);
+    }
+    const float tot = sn_block_sum<256>(acc, sh);
+    if (threadIdx.x == 0) L.s[o] = tot;
 }
 
 // sigma (every CTA recomputes it from s, identically), u, and out = W / sigma
@@ -149,6 +168,19 @@ template <typename TO> __global__ void __launch_bounds__(256) sn_scale_kernel(co
     }
     const size_t n = (size_t)L.cout * L.K;
     TO *out = static_cast<TO *>(L.out);
+    if ((L.K & 3) == 0 && sn_aligned16(L.w, out)) {      // four elements per thread and trip: 16-byte loads, 8/16-byte stores
+        for (size_t i = ((size_t)blockIdx.x * 256 + threadIdx.x) * 4; i < n; i += (size_t)gridDim.x * 1024) {
+            const float4 a = __ldg(reinterpret_cast<const float4 *>(L.w + i));
+            const float q0 = __fdiv_rn(a.x, sigma), q1 = __fdiv_rn(a.y, sigma), q2 = __fdiv_rn(a.z, sigma), q3 = __fdiv_rn(a.w, sigma);
+            if constexpr (sizeof(TO) == 4) {
+                *reinterpret_cast<float4 *>(out + i) = make_float4(q0, q1, q2, q3);
+            } else {
+                __nv_bfloat162 lo = __floats2bfloat162_rn(q0, q1), hi = __floats2bfloat162_rn(q2, q3);
+                *reinterpret_cast<uint2 *>(out + i) = make_uint2(*reinterpret_cast<uint32_t *>(&lo), *reinterpret_cast<uint32_t *>(&hi));
+            }
+        }
+        return;
+    }
     for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256)
         out[i] = from_f32<TO>(__fdiv_rn(__ldg(L.w + i), sigma));
 }
@@ -161,23 +193,65 @@ template <typename TG> __global__ void __launch_bounds__(256) sn_bwd_dot_kernel(
     const TG *dw = static_cast<const TG *>(L.dw);
     const size_t n = (size_t)L.cout * L.K;
     float acc = 0.f;
-    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)kSnDotBlocks * 256)
-        acc = fmaf(to_f32<TG>(dw[i]), __ldg(L.w + i), acc);
+    if ((L.K & 3) == 0 && sn_aligned16(L.w, dw)) {
+#pragma unroll 4
+        for (size_t i = ((size_t)blockIdx.x * 256 + threadIdx.x) * 4; i < n; i += (size_t)kSnDotBlocks * 1024) {
+            const float4 a = __ldg(reinterpret_cast<const float4 *>(L.w + i));
+            float g[4];
+            if constexpr (sizeof(TG) == 4) {
+                const float4 q = __ldg(reinterpret_cast<const float4 *>(dw + i));
+                g[0] = q.x; g[1] = q.y; g[2] = q.z; g[3] = q.w;
+            } else {
+                const uint2 q = __ldg(reinterpret_cast<const uint2 *>(dw + i));
+                g[0] = __uint_as_float(q.x << 16); g[1] = __uint_as_float(q.x & 0xffff0000u);
+                g[2] = __uint_as_float(q.y << 16); g[3] = __uint_as_float(q.y & 0xffff0000u);
+            }
+            acc = fmaf(g[0], a.x, acc); acc = fmaf(g[1], a.y, acc); acc = fmaf(g[2], a.z, acc); acc = fmaf(g[3], a.w, acc);
+        }
+    } else {
+        for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)kSnDotBlocks * 256)
+            acc = fmaf(to_f32<TG>(dw[i]), __ldg(L.w + i), acc);
+    }
     const float tot = sn_block_sum<256>(acc, sh);
     if (threadIdx.x == 0) L.partial[blockIdx.x] = tot;
 }
 
 template <typename TG> __global__ void __launch_bounds__(256) sn_bwd_apply_kernel(const __grid_constant__ SnBwdParams p)
 {
+    __shared__ float sh[8];
     const SnBwdLayer &L = p.l[blockIdx.y];
     const TG *dw = static_cast<const TG *>(L.dw);
-    float dot = 0.f;
-#pragma unroll 8
-    for (int i = 0; i < kSnDotBlocks; ++i) dot += L.partial[i];
+    static_assert(kSnDotBlocks == 256, "one partial per thread");
+    const float dot = sn_block_sum<256>(L.partial[threadIdx.x], sh);      // fixed order: same bits in every CTA
     const float inv = L.state[1];
     const float c = dot * inv * inv;
     const float *u = L.state + 4, *vphys = L.state + 4 + L.cout;
     const size_t n = (size_t)L.cout * L.K;
+    if (((L.K | L.cout) & 3) == 0 && n < (1ull << 31) && sn_aligned16(dw, L.state, L.dw_orig)) {   // four elements of one row per thread and trip
+        const unsigned K = (unsigned)L.K;
+        for (unsigned i = (blockIdx.x * 256u + threadIdx.x) * 4u; i < (unsigned)n; i += gridDim.x * 1024u) {
+            const unsigned o = i / K, j = i - o * K;
+            float g[4];
+            if constexpr (sizeof(TG) == 4) {
+                const float4 q = __ldg(reinterpret_cast<const float4 *>(dw + i));
+                g[0] = q.x; g[1] = q.y; g[2] = q.z; g[3] = q.w;
+            } else {
+                const uint2 q = __ldg(reinterpret_cast<const uint2 *>(dw + i));
+                g[0] = __uint_as_float(q.x << 16); g[1] = __uint_as_float(q.x & 0xffff0000u);
+                g[2] = __uint_as_float(q.y << 16); g[3] = __uint_as_float(q.y & 0xffff0000u);
+            }
+            const float cu = c * u[o];
+            const float4 v = *reinterpret_cast<const float4 *>(vphys + j);
+            float4 r = make_float4(g[0] * inv - cu * v.x, g[1] * inv - cu * v.y, g[2] * inv - cu * v.z, g[3] * inv - cu * v.w);
+            float4 *dst = reinterpret_cast<float4 *>(L.dw_orig + i);
+            if (p.accumulate) {
+                const float4 old = *dst;
+                r.x += old.x; r.y += old.y; r.z += old.z; r.w += old.w;
+            }
+            *dst = r;
+        }
+        return;
+    }
     for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) {
         const int o = (int)(i / L.K), j = (int)(i - (size_t)o * L.K);
         const float g = to_f32<TG>(dw[i]) * inv - c * u[o] * vphys[j];
@@ -239,7 +313,7 @@ extern "C" int hg_spectral_norm_fwd(int layers, const float *const *w, float *co
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (p.iterate) sn_tu_kernel<<<dim3((max_k + 127) / 128, kSnOSplit, layers), 128, 0, st>>>(p);
     sn_v_kernel<<<layers, 1024, 0, st>>>(p);
-    sn_s_kernel<<<dim3((max_cout + 7) / 8, layers), 256, 0, st>>>(p);
+    sn_s_kernel<<<dim3(max_cout, layers), 256, 0, st>>>(p);
     const size_t want = (max_n + 256 * 8 - 1) / (256 * 8), cap = (size_t)sm_count() * 2;
     const int gx = (int)(want < cap ? want : cap);
     if (out_dtype == HG_F32) sn_scale_kernel<float><<<dim3(gx, layers), 256, 0, st>>>(p);

@@ -119,3 +119,33 @@ def test_flat_grads_views_and_zero():
     fg.zero()
     assert lin.weight.grad.abs().sum() == 0 and lin.bias.grad.abs().sum() == 0
     fg.all_reduce_mean(1)           # world 1: no process group needed
+
+
+_EXIT_SCRIPT = """
+import sys, time, torch, torch.distributed as dist
+sys.path.insert(0, {root!r})
+import bench
+torch.cuda.synchronize = lambda *a, **k: None      # no GPU here: the handshake itself is what is tested
+dist.init_process_group("gloo")
+rank = dist.get_rank()
+if rank == 0:
+    time.sleep(1.0)                                 # rank 0 still measures its rooflines while the others wait
+    print("LINE", flush=True)
+bench._exit_without_nccl_teardown(rank)
+raise SystemExit(3)                                 # never reached
+"""
+
+
+def test_bench_multi_rank_exit_handshake(tmp_path):
+    """bench.py leaves multi-rank runs through a store handshake + hard exit (no NCCL teardown under live CUDA
+    graphs, which hung on 2 x B200): under torchrun every rank must end with code 0, after rank 0 printed."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "exit_check.py"
+    script.write_text(_EXIT_SCRIPT.format(root=root))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(WORLD),
+                        "--master-addr", "127.0.0.1", "--master-port", str(_free_port()), str(script)],
+                       capture_output=True, text=True, timeout=180)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "LINE" in r.stdout

@@ -36,7 +36,7 @@ if has tests_cl; then
 fi
 if has pipe; then
   timeout 600 python tools/microbench.py pipeline > $OUT/${TAG}_microbench_pipeline.txt 2>&1
-  echo "microbench pipeline exit $?"; grep -E "adain_cl|inorm_cl|rotate_cl|final_conv" $OUT/${TAG}_microbench_pipeline.txt
+  echo "microbench pipeline exit $?"; grep -E "adain_cl block|spectral|rotate_cl|final_conv" $OUT/${TAG}_microbench_pipeline.txt
 fi
 if has micro; then
   timeout 900 python tools/microbench.py all > $OUT/${TAG}_microbench.txt 2>&1

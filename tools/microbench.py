@@ -182,6 +182,21 @@ def pipeline():
                 os.environ.pop(k, None)
             report(name + " fwd" + tag, tf, 2 * B * n * c * 2)
             report(name + " bwd" + tag, tb, 3 * B * n * c * 2)
+    # spectral norm of the discriminator's three 5x5 convolutions (one grouped call each way); bytes: fwd reads W three
+    # times (W^T u, W v, scale) and writes the bf16 operand, bwd reads dW (bf16) + W twice and writes dW_orig
+    ws_ = [torch.randn(co, ci, 5, 5, device=DEV).mul_(0.02).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+           for co, ci in ((128, 64), (256, 128), (512, 256))]
+    us_ = [torch.randn(w.shape[0], device=DEV) for w in ws_]
+    vs_ = [torch.randn(w[0].numel(), device=DEV) for w in ws_]
+    nel = sum(w.numel() for w in ws_)
+    with torch.no_grad():
+        t = time_rot(lambda _: ops.spectral_norm_weights(ws_, us_, vs_, True, bf), [0, 1, 2])
+    report("spectral_norm fwd (3 layers, 4.1 M weights)", t, nel * (3 * 4 + 2))
+    def sn_fb(_):
+        outs = ops.spectral_norm_weights(ws_, us_, vs_, True, bf)
+        torch.autograd.backward(outs, [torch.ones_like(o) for o in outs])
+    t2 = time_rot(sn_fb, [0, 1, 2], graph=False)
+    report("spectral_norm fwd+bwd (eager, incl. autograd)", t2, nel * (3 * 4 + 2 + 2 * 2 + 2 * 4 + 4))
     # rotate channels-last -> PROJ
     s, c = 16, 64
     a = ops.view_to_affine(views(B), s, s).to(DEV)
