@@ -144,15 +144,21 @@ __global__ void __launch_bounds__(256) adain_bwd_kernel(const T *__restrict__ x,
                                                         int N, long long xbs, int sbs, int dsbs, float slope, int biased)
 {
     constexpr int V = Vec16<T>::N;
+    // kSplit (the learned constant at warp-sized instances, the hot-path case C = 512, N = 64): one CTA per channel,
+    // its 8 warps take the samples b = warp, warp + 8, ... and their partial dx sums meet in shared memory in a fixed
+    // order.  A single warp walking all B samples (64 dependent load -> reduce rounds) took 64 us at B = 64.
+    constexpr bool kSplit = kConstX && GROUP == 32;
     __shared__ float scratch[16];
+    __shared__ float part[kSplit ? 8 * ITEMS * V * 32 : 1];
     const int n_inst = kConstX ? C : B * C;
-    const int inst = blockIdx.x * (256 / GROUP) + threadIdx.x / GROUP;
-    if (GROUP == 32 && inst >= n_inst) return;
+    const int inst = kSplit ? (int)blockIdx.x : (int)(blockIdx.x * (256 / GROUP) + threadIdx.x / GROUP);
+    if (!kSplit && GROUP == 32 && inst >= n_inst) return;
     const int t = threadIdx.x % GROUP;
     const int nvec = N / V;
     const int c = kConstX ? inst : inst % C;
-    const int b_begin = kConstX ? 0 : inst / C;
+    const int b_begin = kSplit ? (int)(threadIdx.x / 32) : (kConstX ? 0 : inst / C);
     const int b_end = kConstX ? B : b_begin + 1;
+    const int b_step = kSplit ? 8 : 1;
     const float inv_nm1 = 1.f / (float)(biased ? N : N - 1), inv_n = 1.f / (float)N;
 
     float xv[ITEMS][V];
@@ -166,7 +172,7 @@ __global__ void __launch_bounds__(256) adain_bwd_kernel(const T *__restrict__ x,
             for (int j = 0; j < V; ++j) acc[it][j] = 0.f;
         }
     }
-    for (int b = b_begin; b < b_end; ++b) {
+    for (int b = b_begin; b < b_end; b += b_step) {
         const size_t bc = (size_t)b * C + c;
         const uint4 *gp = reinterpret_cast<const uint4 *>(dy + bc * N);
         const float mean = save_mean[bc], rstd = save_rstd[bc];
@@ -218,6 +224,24 @@ __global__ void __launch_bounds__(256) adain_bwd_kernel(const T *__restrict__ x,
             }
         }
     }
+    if (kSplit) {
+        const int warp = threadIdx.x / 32;
+#pragma unroll
+        for (int it = 0; it < ITEMS; ++it)
+#pragma unroll
+            for (int j = 0; j < V; ++j) part[((warp * ITEMS + it) * V + j) * 32 + t] = acc[it][j];
+        __syncthreads();
+        if (warp != 0) return;
+#pragma unroll
+        for (int it = 0; it < ITEMS; ++it)
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+                float sum = 0.f;
+#pragma unroll
+                for (int w = 0; w < 8; ++w) sum += part[((w * ITEMS + it) * V + j) * 32 + t];     // fixed order
+                acc[it][j] = sum;
+            }
+    }
     if (kConstX) {
         uint4 *dp = reinterpret_cast<uint4 *>(dx + (size_t)c * N);
 #pragma unroll
@@ -256,8 +280,8 @@ static int adain_bwd_dispatch(const void *x, const void *dy, const float *scale,
     const int n_inst = cx ? C : B * C;
     if (N <= 32 * 4 * V) {
         const int grid = (n_inst + 7) / 8;
-        if (cx)
-            adain_bwd_kernel<T, 32, 4, true><<<grid, 256, 0, st>>>(xp, gp, scale, bias, mean, rstd, dp, dscale, dbias, B, C, N, xbs, sbs, dsbs, slope, biased);
+        if (cx)                                   // one CTA per channel, the 8 warps split the batch
+            adain_bwd_kernel<T, 32, 4, true><<<n_inst, 256, 0, st>>>(xp, gp, scale, bias, mean, rstd, dp, dscale, dbias, B, C, N, xbs, sbs, dsbs, slope, biased);
         else
             adain_bwd_kernel<T, 32, 4, false><<<grid, 256, 0, st>>>(xp, gp, scale, bias, mean, rstd, dp, dscale, dbias, B, C, N, xbs, sbs, dsbs, slope, biased);
     } else if (N <= 256 * 4 * V) {

@@ -11,6 +11,8 @@
 //   dx      : g = dout * (1 - out^2) staged once per tile in smem (with halo), 27 (tap, co) x 8 channels
 //   dw      : 72 accumulators (9 taps x 8 channels) per thread for one co; CTAs stride over tiles, fixed-order
 //             reduction (shuffles -> smem -> per-CTA partial -> second kernel): deterministic, no atomics
+#include <stdlib.h>
+
 #include "hg_common.cuh"
 
 namespace hg {
@@ -18,7 +20,7 @@ namespace hg {
 constexpr int kFinalMaxCout = 4;
 constexpr int kFcThreads = 256;
 constexpr int kFcR = 4;              // rows per thread
-constexpr int kFcDwCtas = 96;        // CTAs per output channel in the dw kernel
+constexpr int kFcDwCtas = 148;       // CTAs per output channel in the dw kernel (= CTAs of the MMA dw kernel)
 
 struct FcGeom {
     int L, slots, tw, th, TH, tiles_x, tiles_y;
@@ -360,6 +362,23 @@ __global__ void __launch_bounds__(256) final_conv_reduce_kernel(const float *__r
 
 using namespace hg;
 
+// final_conv_mma.cu: the same three passes on mma.sync (Cin = 64, Cout = 3, S % 32 == 0)
+bool hg_final_conv_mma_supported(int cin, int cout, int size);
+int hg_final_conv_fwd_mma(const void *x, const float *w, const float *bias, float *out, int batch, int size, cudaStream_t st);
+int hg_final_conv_bwd_x_mma(const float *w, const float *out, const float *dout, void *dx, int batch, int size, cudaStream_t st);
+int hg_final_conv_bwd_w_mma(const void *x, const float *out, const float *dout, float *part, int n_cta, int batch, int size,
+                            cudaStream_t st);
+
+// Which passes run on the tensor-core kernels: bit 0 forward, bit 1 dx, bit 2 dw.  HG_FINAL_CONV_MMA overrides the
+// default (A/B measurements, tests of both implementations); read per call, no state kept.
+constexpr int kFcMmaDefault = 0;
+static int fc_mma_mask(int cin, int cout, int size)
+{
+    if (!hg_final_conv_mma_supported(cin, cout, size)) return 0;
+    const char *e = getenv("HG_FINAL_CONV_MMA");
+    return (e && e[0]) ? atoi(e) : kFcMmaDefault;
+}
+
 static int final_check(const char *who, int batch, int cin, int cout, int size)
 {
     HG_REQUIRE(batch > 0 && batch <= 65535 && size > 0, HG_ERR_INVALID_ARG, "%s: bad batch / size", who);
@@ -394,11 +413,12 @@ extern "C" int hg_final_conv_tanh_fwd(const void *x, const float *w, const float
     HG_REQUIRE(x && w && bias && out, HG_ERR_INVALID_ARG, "hg_final_conv_tanh_fwd: null pointer");
     int rc = final_check("hg_final_conv_tanh_fwd", batch, cin, cout, size);
     if (rc) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (fc_mma_mask(cin, cout, size) & 1) return hg_final_conv_fwd_mma(x, w, bias, out, batch, size, st);
     const int tiles_x = (size + kFcTw - 1) / kFcTw, tiles_y = (size + kFcR - 1) / kFcR;
     dim3 grid(tiles_x * tiles_y, batch);
     const size_t smem = fc_weight_smem_bytes(cin, cout) + (size_t)(kFcR + 2) * (kFcTw + 2) * fc_pixel_pitch(cin) +
                         (size_t)(kFcThreads / 32) * kFcR * cout * 32 * sizeof(float);
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
     static bool attr_done = false;
     if (!attr_done) {
         cudaFuncSetAttribute(final_conv_tanh_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -431,7 +451,11 @@ extern "C" int hg_final_conv_tanh_bwd(const void *x, const float *w, const float
     const FcGeom g = fc_geom(cin, size);
     const size_t tile_floats = (size_t)(g.TH + 2) * (g.tw + 2);
     const bool hot = cin == 64 && size >= 32;
-    if (dx) {
+    const int mma = fc_mma_mask(cin, cout, size);
+    if (dx && (mma & 2)) {
+        rc = hg_final_conv_bwd_x_mma(w, out, dout, dx, batch, size, st);
+        if (rc) return rc;
+    } else if (dx) {
         const int tiles_x = (size + kFcTw - 1) / kFcTw, tiles_y = (size + kFcR - 1) / kFcR;
         dim3 grid(tiles_x * tiles_y, batch);
         const size_t smem = fc_weight_smem_bytes(cin, cout) + (size_t)(cout * (kFcR + 2) * (kFcTw + 2) + 2) * sizeof(float) + 16 +
@@ -452,12 +476,17 @@ extern "C" int hg_final_conv_tanh_bwd(const void *x, const float *w, const float
     const int groups = g.L >= 32 ? kFcThreads / g.L : kFcThreads / 32;
     size_t wsmem = tile_floats > (size_t)groups * cin ? tile_floats : (size_t)groups * cin;
     wsmem *= sizeof(float);
-    dim3 wgrid(kFcDwCtas, cout);
-    HG_FC_DISPATCH(cout, hot, (final_conv_tanh_bwd_w_kernel<CO, LT><<<wgrid, kFcThreads, wsmem, st>>>(
-                             static_cast<const __nv_bfloat16 *>(x), out, dout, static_cast<float *>(workspace), cin, size, batch,
-                             g.tw, g.tiles_x, g.tiles_y)));
-    rc = check_launch("hg_final_conv_tanh_bwd(w)");
-    if (rc) return rc;
+    if (mma & 4) {
+        rc = hg_final_conv_bwd_w_mma(x, out, dout, static_cast<float *>(workspace), kFcDwCtas, batch, size, st);
+        if (rc) return rc;
+    } else {
+        dim3 wgrid(kFcDwCtas, cout);
+        HG_FC_DISPATCH(cout, hot, (final_conv_tanh_bwd_w_kernel<CO, LT><<<wgrid, kFcThreads, wsmem, st>>>(
+                                 static_cast<const __nv_bfloat16 *>(x), out, dout, static_cast<float *>(workspace), cin, size, batch,
+                                 g.tw, g.tiles_x, g.tiles_y)));
+        rc = check_launch("hg_final_conv_tanh_bwd(w)");
+        if (rc) return rc;
+    }
     const int entries = cout * (9 * cin + 1);
     final_conv_reduce_kernel<<<(entries * 32 + 255) / 256, 256, 0, st>>>(static_cast<const float *>(workspace), dw, dbias, cin,
                                                                         cout, kFcDwCtas);

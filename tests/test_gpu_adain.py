@@ -54,19 +54,21 @@ def test_hot_path_shapes_vs_oracle(shape, dtype, slope):
     assert rel_err(bg.grad, br.grad) < (3e-5 if dtype == torch.float32 else 2e-2)
 
 
-def test_constant_input_broadcast():
+@pytest.mark.parametrize("n", [16, 5, 67])
+def test_constant_input_broadcast(n):
     """x of batch 1 (the learned 4^3 constant) == the reference's x.repeat(B, ...) (:121), with the
-    gradient summed over the batch."""
+    gradient summed over the batch (8 warps per channel split the samples: fewer samples than warps, and a
+    batch that is not a multiple of 8, are both covered)."""
     gen = torch.Generator().manual_seed(9)
     x = (torch.randn(1, 512, 4, 4, 4, generator=gen) - 0.5) / 0.5
-    s = torch.rand(16, 512, generator=gen); b = torch.randn(16, 512, generator=gen)
-    dy = torch.randn(16, 512, 4, 4, 4, generator=gen)
+    s = torch.rand(n, 512, generator=gen); b = torch.randn(n, 512, generator=gen)
+    dy = torch.randn(n, 512, 4, 4, 4, generator=gen)
     xr = x.clone().requires_grad_(True); sr = s.clone().requires_grad_(True); br = b.clone().requires_grad_(True)
-    yr = torch.relu(orc.adain(xr.repeat(16, 1, 1, 1, 1), sr, br))
+    yr = torch.relu(orc.adain(xr.repeat(n, 1, 1, 1, 1), sr, br))
     (yr * dy).sum().backward()
     xg = x.to(DEV).requires_grad_(True); sg = s.to(DEV).requires_grad_(True); bg = b.to(DEV).requires_grad_(True)
     y = ops.adain_act(xg, sg, bg, 0.0)
-    assert tuple(y.shape) == (16, 512, 4, 4, 4)
+    assert tuple(y.shape) == (n, 512, 4, 4, 4)
     (y * dy.to(DEV)).sum().backward()
     assert rel_err(y, yr) < 1e-5
     assert tuple(xg.grad.shape) == (1, 512, 4, 4, 4)

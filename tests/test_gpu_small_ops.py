@@ -1,4 +1,6 @@
 """ZMapping linear+ReLU and final conv+tanh kernels against torch fp32."""
+import os
+
 import pytest
 import torch
 import torch.nn.functional as F
@@ -48,6 +50,47 @@ def test_final_conv_tanh(b, c, s, cout):
     assert rel_err(wg.grad, wr.grad) < 2e-5 and rel_err(bg.grad, br.grad) < 2e-5
     out2 = ops.final_conv_tanh(x_cl.detach(), wg, bg)
     assert torch.equal(out, out2)
+
+
+@pytest.mark.parametrize("b,s", [(4, 64), (3, 32), (1, 128)])
+@pytest.mark.parametrize("mask", [7, 1, 6])
+def test_final_conv_tanh_mma_kernels(b, s, mask, monkeypatch):
+    """The tensor-core (mma.sync) kernels of the final layer at the hot-path shape Cin = 64, Cout = 3 -- forward (bit 0),
+    dx (bit 1), dw (bit 2) selected through HG_FINAL_CONV_MMA -- against torch fp32 with the SIMT kernels' tolerances
+    (weights and g enter the MMA as hi + lo bf16 pairs), and against the SIMT kernels themselves."""
+    torch.backends.cudnn.allow_tf32 = False
+    g = torch.Generator().manual_seed(b + s)
+    c, cout = 64, 3
+    x = torch.randn(b, c, s, s, generator=g).to(torch.bfloat16)
+    w = torch.randn(cout, c, 3, 3, generator=g) * 0.05
+    bias = torch.randn(cout, generator=g) * 0.1
+    dout = torch.randn(b, cout, s, s, generator=g)
+    xr = x.float().clone().requires_grad_(True); wr = w.clone().requires_grad_(True); br = bias.clone().requires_grad_(True)
+    ref = torch.tanh(F.conv2d(xr, wr, br, padding=1))
+    (ref * dout).sum().backward()
+
+    def run():
+        x_cl = x.permute(0, 2, 3, 1).contiguous().to(DEV).requires_grad_(True)
+        wg = w.to(DEV).requires_grad_(True); bg = bias.to(DEV).requires_grad_(True)
+        out = ops.final_conv_tanh(x_cl, wg, bg)
+        (out * dout.to(DEV)).sum().backward()
+        return out.detach(), x_cl.grad.permute(0, 3, 1, 2).float(), wg.grad, bg.grad
+
+    monkeypatch.setenv("HG_FINAL_CONV_MMA", str(mask))
+    out, dx, dw, db = run()
+    out2 = run()[0]
+    monkeypatch.setenv("HG_FINAL_CONV_MMA", "0")
+    out_s, dx_s, dw_s, db_s = run()
+    errs = {"out": rel_err(out, ref), "dx": rel_err(dx, xr.grad), "dw": rel_err(dw, wr.grad), "db": rel_err(db, br.grad),
+            "simt_out": rel_err(out_s, ref), "simt_dx": rel_err(dx_s, xr.grad), "simt_dw": rel_err(dw_s, wr.grad)}
+    log_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(log_dir):                              # measurement runs keep the achieved errors next to the timings
+        with open(os.path.join(log_dir, "final_conv_mma_errors.txt"), "a") as f:
+            f.write(f"b={b} s={s} mask={mask} " + " ".join(f"{k}={v:.3e}" for k, v in errs.items()) + "\n")
+    assert rel_err(out, ref) < 1e-5 and torch.equal(out, out2), errs
+    assert rel_err(dx, xr.grad) < 2 ** -7, errs
+    assert rel_err(dw, wr.grad) < 2e-5 and rel_err(db, br.grad) < 2e-5, errs
+    assert rel_err(out, out_s) < 1e-5 and rel_err(dx, dx_s) < 2 ** -7 and rel_err(dw, dw_s) < 2e-5 and rel_err(db, db_s) < 2e-5
 
 
 @pytest.mark.parametrize("rows,cols,slope", [(16384, 1024, 0.0), (300, 64, 0.2), (77, 24, 0.0), (5, 4096, 0.0)])

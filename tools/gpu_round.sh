@@ -38,6 +38,13 @@ if has pipe; then
   timeout 600 python tools/microbench.py pipeline > $OUT/${TAG}_microbench_pipeline.txt 2>&1
   echo "microbench pipeline exit $?"; grep -E "adain_cl block|spectral|rotate_cl|final_conv" $OUT/${TAG}_microbench_pipeline.txt
 fi
+if has mma; then
+  # tensor-core final-layer kernels forced on (HG_FINAL_CONV_MMA=7): pipeline microbench + a short bench
+  HG_FINAL_CONV_MMA=7 timeout 300 python tools/microbench.py pipeline > $OUT/${TAG}_microbench_pipeline_mma.txt 2>&1
+  grep -E "final_conv" $OUT/${TAG}_microbench_pipeline_mma.txt
+  HG_FINAL_CONV_MMA=7 timeout 300 python bench.py --steps 30 --warmup 6 --no-cpu-baseline --no-roofline > $OUT/${TAG}_bench_mma.json 2> $OUT/${TAG}_bench_mma.err
+  echo "bench mma exit $?"; cut -c1-220 $OUT/${TAG}_bench_mma.json
+fi
 if has micro; then
   timeout 900 python tools/microbench.py all > $OUT/${TAG}_microbench.txt 2>&1
   echo "microbench exit $?"
