@@ -157,7 +157,7 @@ def cpu_training_steps(batch: int, img_size: int, steps: int, warmup: int):
             for k in frozen:
                 if k.endswith(("_u", "_v")):
                     dp[k] = frozen[k]
-        return float(loss)
+        return float(loss.detach())
 
     for i in range(warmup):
         one(i)

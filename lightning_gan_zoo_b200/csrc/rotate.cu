@@ -220,6 +220,11 @@ int hg_rotate_cl_bwd_impl(const void *grad_out, const float *a_inv, void *grad_v
                           long long workspace_bytes, int batch, int channels, int size, int logS, int out_layout,
                           cudaStream_t st);
 
+// rotate_slab.cu (32^3 forward on source-slab tiles, opt-in)
+bool hg_rotate_slab32_enabled(int channels, int size, int dtype, int batch);
+int hg_rotate_slab32_fwd(const void *vol, const float *a_inv, void *out, int batch, int channels, int dtype, int border,
+                         cudaStream_t st);
+
 // rotate_il.cu
 bool hg_rotate_il_supported(int channels, int size, int dtype);
 size_t hg_rotate_il_ws_bytes(int batch, int size);
@@ -259,6 +264,8 @@ extern "C" int hg_rotate_fwd(const void *vol, const float *a_inv, void *out, flo
         if (rc) return rc;
     }
     if (in_layout == HG_NCDHW && out_layout == HG_NCDHW) {
+        if (hg_rotate_slab32_enabled(channels, size, dtype, batch))
+            return hg_rotate_slab32_fwd(vol, a_inv, out, batch, channels, dtype, border, st);
         if (hg_rotate_il_supported(channels, size, dtype))
             return hg_rotate_il_fwd(vol, a_inv, out, batch, channels, size, logS, dtype, border | tune, st);
         const bool z = border == HG_BORDER_ZERO;
