@@ -375,6 +375,44 @@ class HologanTrainer:
         _lib.launch_count += launches          # kernels of libhologan_b200.so inside the replayed graph
         return loss
 
+    # ---- checkpoint / resume: the Lightning checkpoint layout the reference writes and resumes from ----------
+    # (run_network.py:48-50 ModelCheckpoint, :61-71 resume_from_checkpoint)
+    def checkpoint(self, epoch: int = 0, global_step: int = 0) -> dict:
+        """A dict in Lightning's checkpoint layout: `state_dict` with `generator.*` / `discriminator.*` keys in the
+        reference's names and torch-native (contiguous, fp32) layouts, the two optimizer states in the reference's
+        order ([D, G], lightning_module.py:75-87), the LambdaLR states and the host RNG streams.  `torch.save` it."""
+        sd = {}
+        for prefix, net in (("generator.", self.generator), ("discriminator.", self.discriminator)):
+            for k, v in net.state_dict().items():
+                sd[prefix + k] = v.detach().to("cpu").contiguous().clone()
+        return {
+            "epoch": int(epoch), "global_step": int(global_step), "state_dict": sd,
+            "optimizer_states": [self.opt_d.state_dict(), self.opt_g.state_dict()],
+            "lr_schedulers": [self.sched_d.state_dict(), self.sched_g.state_dict()],
+            "hologan_b200": {"noise_rng": self.noise_rng.get_state(), "view_rng": self.view_rng.get_state()},
+        }
+
+    def load_checkpoint(self, ckpt: dict, strict: bool = True, load_optimizers: bool = True) -> None:
+        """Load a checkpoint written by `checkpoint()` or by the reference (a Lightning `.ckpt`: only `state_dict` is
+        required).  Parameters are copied in place (their memory format and the flat-gradient views stay valid);
+        captured CUDA graphs are dropped because the optimizer state tensors are replaced -- call
+        `enable_cuda_graphs()` again after loading."""
+        sd = ckpt["state_dict"] if "state_dict" in ckpt else ckpt
+        for prefix, net in (("generator.", self.generator), ("discriminator.", self.discriminator)):
+            part = {k[len(prefix):]: v for k, v in sd.items() if k.startswith(prefix)}
+            if part or strict:
+                net.load_state_dict(part, strict=strict)
+        if load_optimizers and "optimizer_states" in ckpt:
+            for opt, st in zip((self.opt_d, self.opt_g), ckpt["optimizer_states"]):
+                opt.load_state_dict(st)
+            for sch, st in zip((self.sched_d, self.sched_g), ckpt.get("lr_schedulers", ())):
+                sch.load_state_dict(st)
+        extra = ckpt.get("hologan_b200")
+        if extra:
+            self.noise_rng.set_state(extra["noise_rng"])
+            self.view_rng.set_state(extra["view_rng"])
+        self._graphs = None
+
     def end_epoch(self):
         self.sched_d.step()
         self.sched_g.step()

@@ -112,3 +112,66 @@ def test_discriminator_matches_oracle_on_cpu():
     l1, z1 = d(x)
     l2, z2 = orc.discriminator_forward({k: v.clone() for k, v in dp.items()}, x, training=True)
     assert torch.allclose(l1, l2, atol=1e-6) and torch.allclose(z1, z2, atol=1e-6)
+
+
+def _cpu_trainer(seed):
+    from lightning_gan_zoo_b200.training import HologanConfig, HologanTrainer
+    cfg = HologanConfig(batch_size=4, gen_in_planes=8, disc_out_planes=8, num_epochs=4)
+    return HologanTrainer(cfg, device="cpu", compute_dtype=torch.float32, seed=seed)
+
+
+def _cpu_d_step(tr, seed):
+    """One discriminator optimizer step on given fakes (the D branch of lightning_module.py:217-228) -- the generator has
+    no CPU path, the discriminator mirror does."""
+    import torch.nn.functional as F
+    gen = torch.Generator().manual_seed(seed)
+    real = torch.rand(4, 3, 64, 64, generator=gen) * 2 - 1
+    fake = torch.rand(4, 3, 64, 64, generator=gen) * 2 - 1
+    z = torch.rand(4, 128, generator=gen) * 2 - 1
+    bce = F.binary_cross_entropy_with_logits
+    tr.d_grads.zero()
+    d_real, _ = tr.discriminator(real)
+    d_fake, z_pred = tr.discriminator(fake)
+    ((bce(d_real, torch.ones_like(d_real)) + bce(d_fake, torch.zeros_like(d_fake))) / 2 + torch.mean((z_pred - z) ** 2)).backward()
+    tr.opt_d.step()
+
+
+def test_checkpoint_round_trip_and_reference_layout(tmp_path):
+    """Checkpoint / resume in the Lightning layout the reference writes (run_network.py:48-50,61-71): keys
+    `generator.*` / `discriminator.*` exactly as in the reference's state_dict, optimizer order [D, G]; a resumed
+    trainer continues bit-identically; a reference-style .ckpt (only `state_dict`) loads too."""
+    a = _cpu_trainer(seed=1)
+    for i in range(2):
+        _cpu_d_step(a, 10 + i)
+    a.end_epoch()
+    a.sample_noise(3); a.sample_view(3)
+    path = tmp_path / "model.ckpt"
+    torch.save(a.checkpoint(epoch=1, global_step=2), path)
+    ckpt = torch.load(path, weights_only=False)
+
+    spec = json.load(open(os.path.join(GOLDEN, "state_dict_spec.json")))
+    want = {"generator." + k for k, _ in spec["generator_64"]} | {"discriminator." + k for k, _ in spec["discriminator_64"]}
+    assert set(ckpt["state_dict"]) == want
+    assert all(v.is_contiguous() and v.device.type == "cpu" for v in ckpt["state_dict"].values())
+    assert ckpt["epoch"] == 1 and ckpt["global_step"] == 2 and len(ckpt["optimizer_states"]) == 2
+
+    b = _cpu_trainer(seed=2)                                   # different init, different RNG streams
+    b.load_checkpoint(ckpt)
+    for (k, va), vb in zip(a.discriminator.state_dict().items(), b.discriminator.state_dict().values()):
+        assert torch.equal(va, vb), k
+    for va, vb in zip(a.generator.state_dict().values(), b.generator.state_dict().values()):
+        assert torch.equal(va, vb)
+    assert b.opt_d.param_groups[0]["lr"] == a.opt_d.param_groups[0]["lr"]
+    assert torch.equal(a.sample_noise(5), b.sample_noise(5)) and np.array_equal(a.sample_view(5), b.sample_view(5))
+    _cpu_d_step(a, 99)
+    _cpu_d_step(b, 99)                                         # Adam moments and step count were restored
+    for pa, pb in zip(a.discriminator.parameters(), b.discriminator.parameters()):
+        assert torch.equal(pa, pb)
+
+    # a reference checkpoint carries no optimizer layout we rely on: weights only
+    c = _cpu_trainer(seed=3)
+    c.load_checkpoint({"state_dict": ckpt["state_dict"]})
+    for (k, v) in c.generator.state_dict().items():
+        assert torch.equal(v, ckpt["state_dict"]["generator." + k]), k
+    with pytest.raises(RuntimeError):
+        c.load_checkpoint({"state_dict": {"generator.x": torch.zeros(1)}})             # strict: missing / mismatching keys
