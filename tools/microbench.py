@@ -73,6 +73,13 @@ def rotate(shapes=None, tune=0):
                 tb = time_rot(lambda v: ops.rotate_bwd_raw(v, a, c, s, border | tune), bufs)
                 print(f"rotate ({b},{c},{s}^3) {str(dt)[6:]:8s} border={bn:4s} fwd {tf*1e6:8.1f} us {nbytes/tf/1e9:7.0f} GB/s "
                       f"({nbytes/tf/1e9/PEAK*100:4.1f}%)  bwd {tb*1e6:8.1f} us {nbytes/tb/1e9:7.0f} GB/s ({nbytes/tb/1e9/PEAK*100:4.1f}%)")
+                if s == 32 and os.environ.get("HG_BENCH_SLAB32", "0") != "0":
+                    # opt-in source-slab forward (rotate_slab.cu): A/B against the default kernel above
+                    os.environ["HG_ROTATE_SLAB32"] = "1"
+                    ts = time_rot(lambda v: ops.rotate_fwd_raw(v, a, border | tune), bufs)
+                    os.environ.pop("HG_ROTATE_SLAB32", None)
+                    print(f"rotate ({b},{c},{s}^3) {str(dt)[6:]:8s} border={bn:4s} fwd [slab32] {ts*1e6:8.1f} us "
+                          f"{nbytes/ts/1e9:7.0f} GB/s ({nbytes/ts/1e9/PEAK*100:4.1f}%)")
             del bufs
 
 
