@@ -138,7 +138,9 @@ int hg_adain_cl_bwd(const void *x, const void *dy, const float *scale, const flo
 
 /* ---- a4 / a9 / a10: transposed convolutions and the 1x1 projection as tcgen05 implicit GEMMs -------
  * Replace nn.ConvTranspose3d(k3,s2,p1,op1) / nn.ConvTranspose2d(k4,s2,p1) / nn.ConvTranspose2d(k1)
- * forward and backward (core/models/hologan_generator.py:25-30, 38, 60, 135).  bf16 operands, fp32
+ * forward and backward (core/models/hologan_generator.py:25-30, 38, 60, 135).  kernel = 5 (2-D: s2, p2, op1) is the
+ * transposed convolution whose dgrad / forward / wgrad are the forward / dgrad / wgrad of the discriminator's
+ * Conv2d(k5, s2, p2) (core/models/hologan_discriminator.py:12) on a space-to-depth input.  bf16 operands, fp32
  * accumulation in TMEM.  Layouts (all channels-last, bf16):
  *   x      (B, [S,] S, S, Cin)                       `ndim` spatial dims of extent `size`
  *   y_s2d  (B, [S,] S, S, P, Cout)   P = 2^ndim parity classes (P = 1 for kernel 1):
@@ -150,7 +152,7 @@ int hg_adain_cl_bwd(const void *x, const void *dy, const float *scale, const flo
  */
 /* perm_c / perm_s: optional permutation of the input-channel (GEMM K) index for the projection operand
  * in HG_PROJ layout: packed channel y*perm_c + c <-> torch channel c*perm_s + (perm_s-1-y)
- * (reference :130-133); perm_s = 0 means identity.  Cin even, Cout % 32 == 0, taps in {1, 16, 27}. */
+ * (reference :130-133); perm_s = 0 means identity.  Cin even, Cout % 32 == 0, taps in {1, 16, 25, 27}. */
 int hg_convt_pack_weight(const float *w, void *w_fwd, void *w_dgrad, int cin, int cout, int taps, int perm_c, int perm_s,
                          void *stream);
 /* y_s2d = act(convT(x) + bias); bias (Cout) fp32 or NULL; act: v > 0 ? v : neg_slope * v (1 = none) */

@@ -560,11 +560,15 @@ static int pick_stages(int stage_bytes, int iters, int budget = kSmemBudget)
 
 // per-dimension tap table of a stride-2 transposed convolution: for output parity p, the kernel
 // indices k and input shifts s with  out[2*i + p] += in[i + s] * w[k]
-struct DimTaps { int n[2]; int k[2][2]; int s[2][2]; int classes; };
+struct DimTaps { int n[2]; int k[2][3]; int s[2][3]; int classes; };
 static DimTaps dim_taps(int kernel)
 {
     DimTaps d{};
-    if (kernel == 4) {          // k4 s2 p1: o = 2i - 1 + k
+    if (kernel == 5) {          // k5 s2 p2 op1: o = 2i - 2 + k.  Its dgrad is Conv2d(k5, s2, p2) -- the discriminator's
+        d.classes = 2;          // convolution (core/models/hologan_discriminator.py:12) -- on a space-to-depth input.
+        d.n[0] = 3; d.k[0][0] = 0; d.s[0][0] = 1; d.k[0][1] = 2; d.s[0][1] = 0; d.k[0][2] = 4; d.s[0][2] = -1;
+        d.n[1] = 2; d.k[1][0] = 1; d.s[1][0] = 1; d.k[1][1] = 3; d.s[1][1] = 0;
+    } else if (kernel == 4) {   // k4 s2 p1: o = 2i - 1 + k
         d.classes = 2;
         d.n[0] = 2; d.k[0][0] = 1; d.s[0][0] = 0; d.k[0][1] = 3; d.s[0][1] = -1;
         d.n[1] = 2; d.k[1][0] = 0; d.s[1][0] = 1; d.k[1][1] = 2; d.s[1][1] = 0;
@@ -586,11 +590,11 @@ struct ConvShape {
 static int conv_shape(ConvShape &c, const char *who)
 {
     HG_REQUIRE(c.batch > 0 && c.cin > 0 && c.cout > 0 && c.size > 0, HG_ERR_INVALID_ARG, "%s: dims must be positive", who);
-    HG_REQUIRE((c.ndim == 2 && (c.kernel == 4 || c.kernel == 1)) || (c.ndim == 3 && c.kernel == 3), HG_ERR_UNSUPPORTED,
-               "%s: supported: ndim 2 with kernel 4 (s2,p1) or 1, ndim 3 with kernel 3 (s2,p1,op1)", who);
+    HG_REQUIRE((c.ndim == 2 && (c.kernel == 4 || c.kernel == 5 || c.kernel == 1)) || (c.ndim == 3 && c.kernel == 3), HG_ERR_UNSUPPORTED,
+               "%s: supported: ndim 2 with kernel 4 (s2,p1), 5 (s2,p2,op1) or 1, ndim 3 with kernel 3 (s2,p1,op1)", who);
     c.X = c.size; c.Y = c.size; c.Z = c.ndim == 3 ? c.size : 1;
     c.P = c.kernel == 1 ? 1 : (c.ndim == 3 ? 8 : 4);
-    c.taps = c.kernel == 1 ? 1 : (c.ndim == 3 ? 27 : 16);
+    c.taps = c.kernel == 1 ? 1 : (c.ndim == 3 ? 27 : c.kernel * c.kernel);
     return HG_OK;
 }
 
@@ -702,19 +706,21 @@ extern "C" int hg_convt_pack_weight(const float *w, void *w_fwd, void *w_dgrad, 
     if (rc) return rc;
     HG_REQUIRE(cin % 2 == 0 && cout % kBrickCo == 0, HG_ERR_UNSUPPORTED,
                "hg_convt_pack_weight: Cin must be even and Cout a multiple of %d (got %d, %d)", kBrickCo, cin, cout);
-    HG_REQUIRE(taps == 1 || taps == 16 || taps == 27, HG_ERR_UNSUPPORTED,
-               "hg_convt_pack_weight: taps must be 1 (k1), 16 (2-D k4) or 27 (3-D k3), got %d", taps);
+    HG_REQUIRE(taps == 1 || taps == 16 || taps == 25 || taps == 27, HG_ERR_UNSUPPORTED,
+               "hg_convt_pack_weight: taps must be 1 (k1), 16 (2-D k4), 25 (2-D k5) or 27 (3-D k3), got %d", taps);
     dim3 grid((cin + kBrickCi - 1) / kBrickCi, cout / kBrickCo);
     const size_t smem = (size_t)kBrickCi * brick_row_pitch(taps) * sizeof(float);
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(pack_weight_kernel<27>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        cudaFuncSetAttribute(pack_weight_kernel<25>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
         attr_set = true;
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     __nv_bfloat16 *wf = static_cast<__nv_bfloat16 *>(w_fwd), *wd = static_cast<__nv_bfloat16 *>(w_dgrad);
     if (taps == 1) pack_weight_kernel<1><<<grid, 256, smem, st>>>(w, wf, wd, cin, cout, perm_c, perm_s);
     else if (taps == 16) pack_weight_kernel<16><<<grid, 256, smem, st>>>(w, wf, wd, cin, cout, perm_c, perm_s);
+    else if (taps == 25) pack_weight_kernel<25><<<grid, 256, smem, st>>>(w, wf, wd, cin, cout, perm_c, perm_s);
     else pack_weight_kernel<27><<<grid, 256, smem, st>>>(w, wf, wd, cin, cout, perm_c, perm_s);
     return check_launch("hg_convt_pack_weight");
 }
@@ -891,6 +897,7 @@ extern "C" int hg_convt_wgrad(const void *x, const void *dy_s2d, float *dw, void
     if (!attr_set) {
         cudaFuncSetAttribute(wgrad_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgradSmemBudget);
         cudaFuncSetAttribute(wgrad_reduce_kernel<27>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        cudaFuncSetAttribute(wgrad_reduce_kernel<25>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
         attr_set = true;
     }
     dim3 grid(cin / kBM, cout / bn, np * pl.splits);
@@ -902,6 +909,7 @@ extern "C" int hg_convt_wgrad(const void *x, const void *dy_s2d, float *dw, void
     const float *part = static_cast<const float *>(workspace);
     if (c.taps == 1) wgrad_reduce_kernel<1><<<rgrid, 256, rsmem, st>>>(part, dw, cin, cout, pl.splits, perm_c, perm_s, accumulate);
     else if (c.taps == 16) wgrad_reduce_kernel<16><<<rgrid, 256, rsmem, st>>>(part, dw, cin, cout, pl.splits, perm_c, perm_s, accumulate);
+    else if (c.taps == 25) wgrad_reduce_kernel<25><<<rgrid, 256, rsmem, st>>>(part, dw, cin, cout, pl.splits, perm_c, perm_s, accumulate);
     else wgrad_reduce_kernel<27><<<rgrid, 256, rsmem, st>>>(part, dw, cin, cout, pl.splits, perm_c, perm_s, accumulate);
     return check_launch("hg_convt_wgrad(reduce)");
 }

@@ -2,6 +2,7 @@
 same bf16-rounded operands.  The reference arithmetic of these ops IS torch's, so
 F.conv_transpose{2,3}d on fp32 copies of the operands is the oracle; tolerance = bf16 output rounding."""
 import ctypes
+import os
 
 import pytest
 import torch
@@ -85,9 +86,34 @@ CASES = [  # (ndim, kernel, batch, cin, cout, size)
 def torch_convt(x, w, bias, ndim, kernel):
     if kernel == 1:
         return F.conv_transpose2d(x, w, bias)
+    if ndim == 2 and kernel == 5:
+        return F.conv_transpose2d(x, w, bias, stride=2, padding=2, output_padding=1)
     if ndim == 2:
         return F.conv_transpose2d(x, w, bias, stride=2, padding=1)
     return F.conv_transpose3d(x, w, bias, stride=2, padding=1, output_padding=1)
+
+
+# k5 (s2, p2, op1): the transposed convolution whose dgrad / forward / wgrad are the discriminator's Conv2d(k5, s2, p2)
+# forward / dgrad / wgrad.  Shapes = the duals of D's three spectral-norm blocks.
+K5_CASES = [(2, 5, 4, 128, 64, 16), (2, 5, 4, 256, 128, 8), (2, 5, 8, 512, 256, 4), (2, 5, 3, 128, 64, 16)]
+
+
+@pytest.mark.skipif(os.environ.get("HG_TEST_K5") != "1", reason="run through test_convt_k5_in_child_process")
+@pytest.mark.parametrize("ndim,kernel,batch,cin,cout,size", K5_CASES)
+def test_convt_k5_cases(ndim, kernel, batch, cin, cout, size):
+    test_convt_fwd_dgrad_wgrad(ndim, kernel, batch, cin, cout, size)
+
+
+@pytest.mark.xfail(strict=False, reason="kernel-5 tap tables were enabled (and checked on CPU against torch, tests/test_host_logic.py) "
+                                        "after the round's GPU budget was spent -- not yet run on a B200")
+def test_convt_k5_in_child_process():
+    """Child process: an unmeasured code path must not be able to poison this process's CUDA context."""
+    import subprocess
+    import sys
+    env = dict(os.environ, HG_TEST_K5="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-k", "test_convt_k5_cases", "-m", "gpu"],
+                       capture_output=True, text=True, timeout=900, env=env, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-1000:]
 
 
 @pytest.mark.parametrize("ndim,kernel,batch,cin,cout,size", CASES)

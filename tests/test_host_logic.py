@@ -175,3 +175,51 @@ def test_checkpoint_round_trip_and_reference_layout(tmp_path):
         assert torch.equal(v, ckpt["state_dict"]["generator." + k]), k
     with pytest.raises(RuntimeError):
         c.load_checkpoint({"state_dict": {"generator.x": torch.zeros(1)}})             # strict: missing / mismatching keys
+
+
+# per-dimension tap tables of lightning_gan_zoo_b200/csrc/conv_gemm.cu::dim_taps -- out[2 i + p] += in[i + s] * w[k]
+_DIM_TAPS = {
+    4: {0: [(1, 0), (3, -1)], 1: [(0, 1), (2, 0)]},                     # k4 s2 p1
+    3: {0: [(1, 0)], 1: [(0, 1), (2, 0)]},                              # k3 s2 p1 op1
+    5: {0: [(0, 1), (2, 0), (4, -1)], 1: [(1, 1), (3, 0)]},             # k5 s2 p2 op1
+}
+
+
+def _convt2d_by_taps(x, w, kernel):
+    """Transposed convolution as the tap GEMMs compute it: per output parity class a sum over (k, shift) taps of the
+    zero-padded, shifted input times one weight slice (x: (B,Cin,S,S), w: (Cin,Cout,k,k)) -> (B,Cout,2S,2S)."""
+    b, cin, s, _ = x.shape
+    cout = w.shape[1]
+    y = torch.zeros(b, cout, 2 * s, 2 * s, dtype=x.dtype)
+    xp = torch.nn.functional.pad(x, (1, 1, 1, 1))
+    for py, ty in _DIM_TAPS[kernel].items():
+        for px, tx in _DIM_TAPS[kernel].items():
+            acc = torch.zeros(b, cout, s, s, dtype=x.dtype)
+            for ky, sy in ty:
+                for kx, sx in tx:
+                    shifted = xp[:, :, 1 + sy:1 + sy + s, 1 + sx:1 + sx + s]              # in[i + s], zero outside
+                    acc += torch.einsum("bchw,cd->bdhw", shifted, w[:, :, ky, kx])
+            y[:, :, py::2, px::2] = acc
+    return y
+
+
+@pytest.mark.parametrize("kernel,pad,opad", [(4, 1, 0), (5, 2, 1)])
+def test_tap_tables_reproduce_transposed_conv_and_the_conv_duality(kernel, pad, opad):
+    """The tap tables the tcgen05 implicit-GEMM kernels are driven by (conv_gemm.cu::dim_taps), restated here, against
+    torch: k4 (the generator's ConvTranspose2d) and k5 (s2, p2, op1).  For k5 the adjoint of that transposed
+    convolution is the discriminator's Conv2d(k5, s2, p2) (core/models/hologan_discriminator.py:12): the same tables
+    run it as a 'dgrad' on a space-to-depth input -- checked through autograd."""
+    import torch.nn.functional as F
+    gen = torch.Generator().manual_seed(kernel)
+    x = torch.randn(2, 6, 8, 8, generator=gen, dtype=torch.float64)
+    w = torch.randn(6, 4, kernel, kernel, generator=gen, dtype=torch.float64)
+    ref = F.conv_transpose2d(x, w, stride=2, padding=pad, output_padding=opad)
+    got = _convt2d_by_taps(x, w, kernel)
+    assert tuple(got.shape) == tuple(ref.shape) and torch.allclose(got, ref, atol=1e-12)
+    if kernel == 5:
+        # Conv2d(k5, s2, p2) with weight (Cout_c = 6, Cin_c = 4, 5, 5) == adjoint of the transposed conv above
+        img = torch.randn(2, 4, 16, 16, generator=gen, dtype=torch.float64)
+        conv = F.conv2d(img, w, stride=2, padding=2)                                      # (2, 6, 8, 8)
+        xg = x.clone().requires_grad_(True)
+        (_convt2d_by_taps(xg, w, 5) * img).sum().backward()                               # <convT(x), img> = <x, conv(img)>
+        assert torch.allclose(xg.grad, conv, atol=1e-12)
