@@ -86,6 +86,33 @@ class Discriminator(nn.Module):
             h = ops.instance_norm_act_channels_last(h.permute(0, 2, 3, 1), 0.2, blk.instance_norm.eps).permute(0, 3, 1, 2)
         return h
 
+    def _blocks_tcgen05(self, h):
+        """The same three blocks with the convolutions on the tcgen05 tap GEMMs (`ops.conv5x5_s2`: Conv2d(k5, s2, p2) as
+        the dgrad of the dual transposed convolution on a space-to-depth input) instead of cuDNN.  Opt-in
+        (HG_D_TCGEN05=1) until it has been measured on a B200; needs contiguous (not channels_last) weights, because the
+        weight pack reads the torch layout."""
+        convs = [blk.conv2d for blk in self.blocks]
+        ws = ops.spectral_norm_weights([c.weight_orig for c in convs], [c.weight_u for c in convs],
+                                       [c.weight_v for c in convs], power_iteration=self.training,
+                                       out_dtype=torch.float32)
+        h = h.permute(0, 2, 3, 1)                                                     # logical NCHW on NHWC memory -> (B, H, W, C)
+        for blk, w in zip(self.blocks, ws):
+            y = ops.conv5x5_s2(ops.nhwc_to_s2d(h.contiguous()), w)                    # (B, H/2, W/2, Cout)
+            h = ops.instance_norm_act_channels_last(y, 0.2, blk.instance_norm.eps)
+        return h.permute(0, 3, 1, 2)
+
+    def _tcgen05_ok(self, x):
+        import os
+        if os.environ.get("HG_D_TCGEN05", "0") in ("", "0"):
+            return False
+        side = x.shape[-1] // 2                                                       # spatial extent entering the first block
+        for blk in self.blocks:
+            w = blk.conv2d.weight_orig
+            side //= 2
+            if not (w.is_contiguous() and ops.conv5x5_s2_supported(w.shape[1], w.shape[0], side, x.shape[0])):
+                return False
+        return True
+
     def _bf16_pipeline_ok(self, x):
         if not (x.is_cuda and torch.is_autocast_enabled() and torch.get_autocast_dtype("cuda") == torch.bfloat16):
             return False
@@ -99,7 +126,9 @@ class Discriminator(nn.Module):
         if bf16:
             x = x.contiguous(memory_format=torch.channels_last)      # NHWC pipeline (3 MB at B = 64)
         h = F.leaky_relu(self.conv2d(x), 0.2)
-        if bf16 and self._bf16_pipeline_ok(x):
+        if bf16 and self._tcgen05_ok(x):
+            h = self._blocks_tcgen05(h).flatten(1)
+        elif bf16 and self._bf16_pipeline_ok(x):
             h = self._blocks_bf16(h).flatten(1)
         else:
             h = self.blocks(h).flatten(1)                             # logical (c, h, w) order, as the reference (:60)

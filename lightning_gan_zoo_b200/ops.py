@@ -392,6 +392,65 @@ def convt(x_cl: Tensor, weight: Tensor, bias: Optional[Tensor], ndim: int, kerne
     return _ConvT.apply(x_cl, weight, bias, ndim, kernel, neg_slope, perm)
 
 
+class _ConvS2K5(torch.autograd.Function):
+    """y = Conv2d(k5, s2, p2)(x) (no bias) on the tcgen05 tap GEMMs through the transposed-conv duality: the
+    discriminator's convolution (reference core/models/hologan_discriminator.py:12) is the dgrad of
+    ConvTranspose2d(k5, s2, p2, op1) with the same weight tensor (Conv2d (Cout, Cin, 5, 5) == ConvTranspose2d
+    (Cin_T = Cout, Cout_T = Cin, 5, 5)), so
+        forward  = hg_convt_dgrad   (x in space-to-depth layout plays dy_s2d),
+        dx       = hg_convt_fwd     (dy plays x; the result is dx in space-to-depth layout),
+        dw       = hg_convt_wgrad   (dy plays x, x_s2d plays dy_s2d; the result has the Conv2d weight layout).
+    x_s2d: (B, S, S, 4, Cin) bf16 with x_s2d[b, i, j, (py, px), c] = x[b, c, 2i + py, 2j + px]; y: (B, S, S, Cout) bf16."""
+
+    @staticmethod
+    def forward(ctx, x_s2d, weight):
+        _require_cuda(x_s2d, weight)
+        if x_s2d.dtype != torch.bfloat16 or not x_s2d.is_contiguous() or x_s2d.dim() != 5 or x_s2d.shape[3] != 4:
+            raise ValueError("x_s2d must be a contiguous bf16 tensor (B, S, S, 4, Cin)")
+        b, size, cin = x_s2d.shape[0], x_s2d.shape[1], x_s2d.shape[4]
+        cout = weight.shape[0]
+        if tuple(weight.shape[1:]) != (cin, 5, 5):
+            raise ValueError("weight must be (Cout, Cin, 5, 5)")
+        wf, wd = pack_convt_weight(weight)                  # as ConvTranspose2d weight: Cin_T = Cout, Cout_T = Cin
+        y = torch.empty((b, size, size, cout), dtype=torch.bfloat16, device=x_s2d.device)
+        _lib.call("hg_convt_dgrad", _ptr(x_s2d), _ptr(wd), _ptr(y), b, cout, cin, 2, size, 5, _stream())
+        ctx.save_for_backward(x_s2d, wf)
+        ctx.meta = (b, size, cin, cout, tuple(weight.shape))
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x_s2d, wf = ctx.saved_tensors
+        b, size, cin, cout, wshape = ctx.meta
+        dy = dy.contiguous()
+        dx = dw = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x_s2d)
+            _lib.call("hg_convt_fwd", _ptr(dy), _ptr(wf), _ptr(None), _ptr(dx), b, cout, cin, 2, size, 5, ctypes.c_float(1.0),
+                      _stream())
+        if ctx.needs_input_grad[1]:
+            dw = convt_wgrad(dy, x_s2d, wshape, 2, 5)
+        return dx, dw
+
+
+def conv5x5_s2(x_s2d: Tensor, weight: Tensor) -> Tensor:
+    """Conv2d(kernel 5, stride 2, padding 2, no bias) of a space-to-depth input on the tcgen05 kernels."""
+    return _ConvS2K5.apply(x_s2d, weight)
+
+
+def conv5x5_s2_supported(cin: int, cout: int, size_out: int, batch: int) -> bool:
+    """Shapes the dual transposed-conv kernels cover: forward needs Cin % 64 == 0 and Cout % 16 == 0, dx the converse
+    with 64 / 16 swapped, dw Cout % 128 == 0 and Cin % 64 == 0; rows tile into 128-position boxes."""
+    rows = size_out * size_out
+    return cin % 64 == 0 and cout % 128 == 0 and (rows % 128 == 0 or (128 % rows == 0 and (batch * rows) % 128 == 0))
+
+
+def nhwc_to_s2d(x: Tensor) -> Tensor:
+    """(B, H, W, C) channels-last -> (B, H/2, W/2, 4, C) space-to-depth (one copy)."""
+    b, h, w, c = x.shape
+    return x.reshape(b, h // 2, 2, w // 2, 2, c).permute(0, 1, 3, 2, 4, 5).reshape(b, h // 2, w // 2, 4, c).contiguous()
+
+
 # ---- layout glue (pure data movement) -------------------------------------------------------------
 
 def s2d_to_nc(y_s2d: Tensor, ndim: int) -> Tensor:

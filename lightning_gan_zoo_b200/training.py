@@ -14,6 +14,7 @@ Mirrors what the reference gets from `core.lightning_module.HOLOGAN` + `pl.Train
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass, field
 from types import SimpleNamespace
 from typing import Dict, Optional
@@ -171,7 +172,7 @@ class HologanTrainer:
         if self.world > 1:               # identical replicas even if a rank's RNG had diverged
             for t in list(self.generator.state_dict().values()) + list(self.discriminator.state_dict().values()):
                 dist.broadcast(t, src=0)
-        if self.device.type == "cuda" and compute_dtype == torch.bfloat16:
+        if self.device.type == "cuda" and compute_dtype == torch.bfloat16 and os.environ.get("HG_D_TCGEN05", "0") in ("", "0"):
             # bf16 pipeline: the discriminator's convolutions run NHWC (cuDNN's native tensor-core layout), so
             # its weights live channels-last too -- no per-call layout conversions
             self.discriminator.to(memory_format=torch.channels_last)
