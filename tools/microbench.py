@@ -251,6 +251,8 @@ if __name__ == "__main__":
         for g in (512, 1024):
             print(f"## threads per CTA = {g}")
             rotate([(64, 64, 16), (64, 256, 16), (64, 64, 8)], tune=_lib.HG_TUNE_CTA1024 if g == 1024 else 0)
+    if what == "rotate32":                  # BASELINE cfg 3 at 32^3 only (with HG_BENCH_SLAB32=1: the slab forward A/B)
+        rotate([(64, 64, 32), (64, 128, 32)])
     if what in ("adain", "all"):
         adain()
     if what in ("conv", "all"):
