@@ -203,6 +203,22 @@ def _convt2d_by_taps(x, w, kernel):
     return y
 
 
+def _convt2d_dgrad_by_taps(dy, w, kernel):
+    """The dgrad GEMM as conv_gemm.cu::hg_convt_dgrad sets it up: dX[i] = sum over (class, tap) of the class plane of
+    dY shifted by -s, times W[k]^T (dy: (B,Cout,2S,2S), w: (Cin,Cout,k,k)) -> (B,Cin,S,S)."""
+    b, cout, s2, _ = dy.shape
+    s = s2 // 2
+    dx = torch.zeros(b, w.shape[0], s, s, dtype=dy.dtype)
+    for py, ty in _DIM_TAPS[kernel].items():
+        for px, tx in _DIM_TAPS[kernel].items():
+            plane = torch.nn.functional.pad(dy[:, :, py::2, px::2], (1, 1, 1, 1))        # dY_s2d[:, class (py, px)]
+            for ky, sy in ty:
+                for kx, sx in tx:
+                    shifted = plane[:, :, 1 - sy:1 - sy + s, 1 - sx:1 - sx + s]          # dY_s2d[i - s]
+                    dx += torch.einsum("bdhw,cd->bchw", shifted, w[:, :, ky, kx])
+    return dx
+
+
 @pytest.mark.parametrize("kernel,pad,opad", [(4, 1, 0), (5, 2, 1)])
 def test_tap_tables_reproduce_transposed_conv_and_the_conv_duality(kernel, pad, opad):
     """The tap tables the tcgen05 implicit-GEMM kernels are driven by (conv_gemm.cu::dim_taps), restated here, against
@@ -223,3 +239,10 @@ def test_tap_tables_reproduce_transposed_conv_and_the_conv_duality(kernel, pad, 
         xg = x.clone().requires_grad_(True)
         (_convt2d_by_taps(xg, w, 5) * img).sum().backward()                               # <convT(x), img> = <x, conv(img)>
         assert torch.allclose(xg.grad, conv, atol=1e-12)
+        # ... and explicitly in the form ops.conv5x5_s2 calls it: hg_convt_dgrad on the space-to-depth image
+        assert torch.allclose(_convt2d_dgrad_by_taps(img, w, 5), conv, atol=1e-12)
+    else:
+        dy = torch.randn(2, 4, 16, 16, generator=gen, dtype=torch.float64)
+        xg = x.clone().requires_grad_(True)
+        (F.conv_transpose2d(xg, w, stride=2, padding=pad) * dy).sum().backward()
+        assert torch.allclose(_convt2d_dgrad_by_taps(dy, w, kernel), xg.grad, atol=1e-12)
