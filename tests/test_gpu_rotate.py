@@ -170,7 +170,7 @@ def test_slab32_forward_vs_c_oracle(c_oracle, tmp_path):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     script = tmp_path / "slab32_check.py"
     script.write_text(_SLAB32_SCRIPT.format(root=root))
-    r = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, timeout=600)
+    r = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, timeout=240)
     assert r.returncode == 0 and "SLAB32 OK" in r.stdout, r.stdout[-1500:] + r.stderr[-3000:]
 
 

@@ -191,5 +191,5 @@ def test_discriminator_tcgen05_convs_in_child_process(tmp_path):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     script = tmp_path / "d_tcgen05_check.py"
     script.write_text(_D_TCGEN05_SCRIPT.format(root=root))
-    r = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, timeout=900)
+    r = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "D TCGEN05 OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
