@@ -225,6 +225,10 @@ bool hg_rotate_slab32_enabled(int channels, int size, int dtype, int batch);
 int hg_rotate_slab32_fwd(const void *vol, const float *a_inv, void *out, int batch, int channels, int dtype, int border,
                          cudaStream_t st);
 
+bool hg_rotate_gather_bwd_enabled(int size, int batch);
+int hg_rotate_gather_bwd(const void *grad_out, const float *a_inv, void *grad_vol, int batch, int channels, int size, int logS,
+                         int dtype, cudaStream_t st);
+
 // rotate_il.cu
 bool hg_rotate_il_supported(int channels, int size, int dtype);
 size_t hg_rotate_il_ws_bytes(int batch, int size);
@@ -298,6 +302,8 @@ extern "C" int hg_rotate_bwd(const void *grad_out, const float *a_inv, void *gra
                "hg_rotate_bwd: unknown border mode %d", border);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (in_layout == HG_NCDHW && out_layout == HG_NCDHW) {
+        if (hg_rotate_gather_bwd_enabled(size, batch))
+            return hg_rotate_gather_bwd(grad_out, a_inv, grad_vol, batch, channels, size, logS, dtype, st);
         if (hg_rotate_il_supported(channels, size, dtype) && workspace &&
             workspace_bytes >= (long long)hg_rotate_il_ws_bytes(batch, size))
             return hg_rotate_il_bwd(grad_out, a_inv, grad_vol, workspace, batch, channels, size, logS, dtype, border | tune, st);

@@ -141,6 +141,153 @@ __global__ void __launch_bounds__(kSlabThreads, 2) rotate_fwd_slab32_kernel(cons
     }
 }
 
+// -------------------------------------------------------------------------------------------------
+// Backward for volumes whose channel group does not fit in shared memory (32^3): per-voxel gather with an analytic
+// candidate search -- no tables, no workspace, no atomics (shared-memory fp32 atomicAdd is a CAS loop on sm_100,
+// ATOMS.CAST.SPIN in the SASS: that is what makes the scatter backward of rotate.cu take 5.5 ms at (64,64,32^3)).
+//   grad_vol[s] = sum over outputs o whose 2x2x2 footprint contains s of w(o, s) * grad_out[o]
+// The outputs that can touch source voxel s satisfy |src(o) - s|_inf < 1, i.e. o lies in the image of the cube
+// (s-1, s+1)^3 under the inverse affine map: |o_a - oc_a| < h_a = sum_j |Linv[a][j]| with oc = Linv (s - t).  Every
+// lane scans that lattice box (same trip counts for the whole sample), decides hits with the forward's exact
+// coordinate chain (same bits -> same floor cell as the forward) and keeps (output index, weight) pairs in a
+// per-thread shared-memory list (phase 1); phase 2 walks the list once per chunk of channels, so the search is paid
+// once per voxel and the gathers of a warp (32 neighbouring source voxels) hit the same few lines of grad_out.
+// Hits beyond the list capacity (strongly shrinking views) are re-enumerated per chunk.  Fixed order: deterministic.
+// Out-of-range outputs contribute exactly 0, as in the other backward kernels (include/hologan_b200.h).
+// Status: opt-in (HG_ROTATE_GATHER_BWD=1), enumeration emulated on CPU against the scatter definition; not yet run on
+// a B200.
+// -------------------------------------------------------------------------------------------------
+constexpr int kGbThreads = 256;
+constexpr int kGbHits = 20;                                // list entries per source voxel (8 cells x ~1-2 outputs at scale 1)
+constexpr int kGbChunk = 8;                                // channels per pass over the list
+constexpr float kGbEps = 0.01f;
+
+struct GbSearch {
+    float m[12];        // rows 0..2 of a_inv: src = L o + t
+    float li[9];        // L^-1
+    float h[3];         // half extents of the candidate box
+    int n[3];           // trip counts per axis
+};
+
+__device__ __forceinline__ bool gb_hit(const float *__restrict__ m, int ox, int oy, int oz, int sx, int sy, int sz, float lim,
+                                       float &w)
+{
+    float x, y, z;
+    il_coords(m, ox, oy, oz, x, y, z);                     // the forward's bits
+    if (!((x >= 0.f) && (x < lim) && (y >= 0.f) && (y < lim) && (z >= 0.f) && (z < lim))) return false;
+    const int qx = __float2int_rd(x), qy = __float2int_rd(y), qz = __float2int_rd(z);
+    const int dx = sx - qx, dy = sy - qy, dz = sz - qz;
+    if ((unsigned)dx > 1u || (unsigned)dy > 1u || (unsigned)dz > 1u) return false;
+    const float wx = dx ? __fsub_rn(x, (float)qx) : __fsub_rn((float)(qx + 1), x);
+    const float wy = dy ? __fsub_rn(y, (float)qy) : __fsub_rn((float)(qy + 1), y);
+    const float wz = dz ? __fsub_rn(z, (float)qz) : __fsub_rn((float)(qz + 1), z);
+    w = __fmul_rn(__fmul_rn(wx, wy), wz);
+    return true;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kGbThreads) rotate_bwd_gather_kernel(const T *__restrict__ grad_out, const float *__restrict__ a_inv,
+                                                                       T *__restrict__ grad_vol, int C, int S, int logS)
+{
+    extern __shared__ uint2 gb_hits[];                      // [kGbHits][kGbThreads]: (output index, weight bits)
+    __shared__ GbSearch q;
+    const int N = S * S * S;
+    const int b = blockIdx.y;
+    if (threadIdx.x == 0) {
+        const float *a = a_inv + b * 16;
+        for (int i = 0; i < 12; ++i) q.m[i] = a[i];
+        const float a0 = a[0], a1 = a[1], a2 = a[2], b0 = a[4], b1 = a[5], b2 = a[6], c0 = a[8], c1 = a[9], c2 = a[10];
+        const float A = b1 * c2 - b2 * c1, B = a2 * c1 - a1 * c2, Cc = a1 * b2 - a2 * b1;
+        const float D = b2 * c0 - b0 * c2, E = a0 * c2 - a2 * c0, F = a2 * b0 - a0 * b2;
+        const float G = b0 * c1 - b1 * c0, H = a1 * c0 - a0 * c1, I = a0 * b1 - a1 * b0;
+        const float det = a0 * A + a1 * D + a2 * G;
+        const bool ok = fabsf(det) > 1e-12f;
+        const float r = ok ? 1.0f / det : 0.f;
+        const float li[9] = {A * r, B * r, Cc * r, D * r, E * r, F * r, G * r, H * r, I * r};
+        for (int i = 0; i < 9; ++i) q.li[i] = li[i];
+        for (int ax = 0; ax < 3; ++ax) {
+            const float h = fabsf(li[3 * ax]) + fabsf(li[3 * ax + 1]) + fabsf(li[3 * ax + 2]) + kGbEps;
+            q.h[ax] = h;
+            const float span = 2.f * h + 2.f;
+            q.n[ax] = (!ok || span > (float)S) ? S : (int)span;       // degenerate / strongly shrinking: scan the axis
+        }
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int j = blockIdx.x * (kGbThreads / 32) + warp;   // 8x2x2 block of source voxels
+    int sx, sy, sz;
+    il_block_voxel(j, lane, S, logS, sx, sy, sz);
+    const int s = (((sz << logS) + sy) << logS) + sx;
+    const float lim = (float)(S - 1);
+    // candidate box: start_a = ceil(oc_a - h_a), n_a points (or the whole axis)
+    const float tx = (float)sx - q.m[3], ty = (float)sy - q.m[7], tz = (float)sz - q.m[11];
+    int st[3];
+#pragma unroll
+    for (int ax = 0; ax < 3; ++ax) {
+        const float oc = q.li[3 * ax] * tx + q.li[3 * ax + 1] * ty + q.li[3 * ax + 2] * tz;
+        st[ax] = q.n[ax] >= S ? 0 : (int)ceilf(oc - q.h[ax]);
+    }
+    const int nx = q.n[0], ny = q.n[1], nz = q.n[2];
+    // ---- phase 1: enumerate, keep the first kGbHits hits ----------------------------------------------------
+    int count = 0;
+    for (int iz = 0; iz < nz; ++iz) {
+        const int oz = st[2] + iz;
+        for (int iy = 0; iy < ny; ++iy) {
+            const int oy = st[1] + iy;
+            for (int ix = 0; ix < nx; ++ix) {
+                const int ox = st[0] + ix;
+                float w;
+                if ((unsigned)ox < (unsigned)S && (unsigned)oy < (unsigned)S && (unsigned)oz < (unsigned)S &&
+                    gb_hit(q.m, ox, oy, oz, sx, sy, sz, lim, w)) {
+                    if (count < kGbHits)
+                        gb_hits[count * kGbThreads + threadIdx.x] = make_uint2((uint32_t)((((oz << logS) + oy) << logS) + ox), __float_as_uint(w));
+                    ++count;
+                }
+            }
+        }
+    }
+    const int listed = min(count, kGbHits);
+    const int nmax = __reduce_max_sync(0xffffffffu, listed);
+    // ---- phase 2: one pass over the list per chunk of channels ------------------------------------------------
+    for (int c0 = 0; c0 < C; c0 += kGbChunk) {
+        const int nc = min(kGbChunk, C - c0);
+        const T *g = grad_out + ((size_t)b * C + c0) * N;
+        float acc[kGbChunk];
+#pragma unroll
+        for (int c = 0; c < kGbChunk; ++c) acc[c] = 0.f;
+        for (int i = 0; i < nmax; ++i) {
+            if (i < listed) {
+                const uint2 e = gb_hits[i * kGbThreads + threadIdx.x];
+                const float w = __uint_as_float(e.y);
+#pragma unroll
+                for (int c = 0; c < kGbChunk; ++c)
+                    if (c < nc) acc[c] = fmaf(w, to_f32<T>(g[(size_t)c * N + e.x]), acc[c]);
+            }
+        }
+        if (count > kGbHits) {                              // rare: re-enumerate the hits that did not fit
+            int seen = 0;
+            for (int iz = 0; iz < nz; ++iz)
+                for (int iy = 0; iy < ny; ++iy)
+                    for (int ix = 0; ix < nx; ++ix) {
+                        const int ox = st[0] + ix, oy = st[1] + iy, oz = st[2] + iz;
+                        float w;
+                        if ((unsigned)ox < (unsigned)S && (unsigned)oy < (unsigned)S && (unsigned)oz < (unsigned)S &&
+                            gb_hit(q.m, ox, oy, oz, sx, sy, sz, lim, w)) {
+                            if (seen >= kGbHits) {
+                                const int o = (((oz << logS) + oy) << logS) + ox;
+                                for (int c = 0; c < nc; ++c) acc[c] = fmaf(w, to_f32<T>(g[(size_t)c * N + o]), acc[c]);
+                            }
+                            ++seen;
+                        }
+                    }
+        }
+        T *dst = grad_vol + ((size_t)b * C + c0) * N + s;
+#pragma unroll
+        for (int c = 0; c < kGbChunk; ++c)
+            if (c < nc) st_stream_elem<T>(dst + (size_t)c * N, acc[c]);
+    }
+}
+
 template <typename T, bool Z>
 static int launch_fwd_slab32(const void *vol, const float *a, void *out, int B, int C, cudaStream_t st)
 {
@@ -178,4 +325,27 @@ int hg_rotate_slab32_fwd(const void *vol, const float *a_inv, void *out, int bat
                  : launch_fwd_slab32<float, false>(vol, a_inv, out, batch, channels, st);
     return z ? launch_fwd_slab32<__nv_bfloat16, true>(vol, a_inv, out, batch, channels, st)
              : launch_fwd_slab32<__nv_bfloat16, false>(vol, a_inv, out, batch, channels, st);
+}
+
+// size 32 (any channel count), opt-in
+bool hg_rotate_gather_bwd_enabled(int size, int batch)
+{
+    if (size != 32 || batch > 65535) return false;
+    const char *e = getenv("HG_ROTATE_GATHER_BWD");
+    return e && e[0] && e[0] != '0';
+}
+
+int hg_rotate_gather_bwd(const void *grad_out, const float *a_inv, void *grad_vol, int batch, int channels, int size, int logS,
+                         int dtype, cudaStream_t st)
+{
+    const int n = size * size * size;
+    const size_t smem = (size_t)kGbHits * kGbThreads * sizeof(uint2);
+    dim3 grid(n / kGbThreads, batch);
+    if (dtype == HG_F32)
+        rotate_bwd_gather_kernel<float><<<grid, kGbThreads, smem, st>>>(static_cast<const float *>(grad_out), a_inv,
+                                                                       static_cast<float *>(grad_vol), channels, size, logS);
+    else
+        rotate_bwd_gather_kernel<__nv_bfloat16><<<grid, kGbThreads, smem, st>>>(static_cast<const __nv_bfloat16 *>(grad_out), a_inv,
+                                                                               static_cast<__nv_bfloat16 *>(grad_vol), channels, size, logS);
+    return check_launch("rotate_bwd_gather");
 }

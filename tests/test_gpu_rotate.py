@@ -154,15 +154,38 @@ for dtype in (torch.float32, torch.bfloat16):
             ref = np.empty((b, c, s, s, s), np.float32)
             lib.orc_rotate_fwd(ptr(np.ascontiguousarray(vol.numpy())), ptr(a_cpu.numpy()), ptr(ref), b, c, s)
             assert np.array_equal(out.cpu().numpy(), ref), scale
+# gather backward (rotate_slab.cu, HG_ROTATE_GATHER_BWD=1) against the C oracle's scatter adjoint; ragged channel count
+os.environ.pop("HG_ROTATE_SLAB32", None)
+for scale in (1.0, 0.7, 1.8):
+    b, c, s = 4, 7, 32
+    gen = torch.Generator().manual_seed(int(scale * 10) + 1)
+    gout = torch.randn(b, c, s, s, s, generator=gen)
+    view = orc.sample_view(b, np.random.RandomState(21))
+    view[:, 2] = scale
+    view[1:, 3:6] = np.random.RandomState(22).uniform(-3, 3, (b - 1, 3))
+    a_cpu = ops.view_to_affine(view, s, s)
+    a = a_cpu.to(DEV)
+    refg = np.empty((b, c, s, s, s), np.float32)
+    lib.orc_rotate_bwd(ptr(np.ascontiguousarray(gout.numpy())), ptr(a_cpu.numpy()), ptr(refg), b, c, s)
+    os.environ["HG_ROTATE_GATHER_BWD"] = "1"
+    gv = ops.rotate_bwd_raw(gout.to(DEV), a, c, s, ops.HG_BORDER_REFERENCE)
+    gv2 = ops.rotate_bwd_raw(gout.to(DEV), a, c, s, ops.HG_BORDER_REFERENCE)
+    gvb = ops.rotate_bwd_raw(gout.to(DEV).bfloat16(), a, c, s, ops.HG_BORDER_ZERO)
+    os.environ.pop("HG_ROTATE_GATHER_BWD", None)
+    torch.cuda.synchronize()
+    assert torch.equal(gv, gv2), scale                               # deterministic
+    assert rel_err(gv, refg) < 1e-5, (scale, rel_err(gv, refg))
+    assert rel_err(gvb.float(), refg) < 2e-2, scale
 print("SLAB32 OK")
 """
 
 
-@pytest.mark.xfail(strict=False, reason="opt-in 32^3 source-slab kernel (HG_ROTATE_SLAB32=1): written and emulated on CPU after "
-                                        "the round's GPU budget was spent -- not yet run on a B200")
+@pytest.mark.xfail(strict=False, reason="opt-in 32^3 kernels (HG_ROTATE_SLAB32=1 forward, HG_ROTATE_GATHER_BWD=1 backward): written and "
+                                        "emulated on CPU after the round's GPU budget was spent -- not yet run on a B200")
 def test_slab32_forward_vs_c_oracle(c_oracle, tmp_path):
     """32^3 forward on source-slab tiles (rotate_slab.cu) against the C oracle (bit-exact in fp32) and against the
-    default per-channel kernel, both border modes.  Runs in a child process: the kernel has not been on a GPU yet,
+    default per-channel kernel, both border modes; and the table-free gather backward against the C oracle's scatter
+    adjoint.  Runs in a child process: the kernel has not been on a GPU yet,
     and a fault in it must not poison this process's CUDA context."""
     import os
     import subprocess

@@ -78,8 +78,12 @@ def rotate(shapes=None, tune=0):
                     os.environ["HG_ROTATE_SLAB32"] = "1"
                     ts = time_rot(lambda v: ops.rotate_fwd_raw(v, a, border | tune), bufs)
                     os.environ.pop("HG_ROTATE_SLAB32", None)
+                    os.environ["HG_ROTATE_GATHER_BWD"] = "1"
+                    tg = time_rot(lambda v: ops.rotate_bwd_raw(v, a, c, s, border | tune), bufs)
+                    os.environ.pop("HG_ROTATE_GATHER_BWD", None)
                     print(f"rotate ({b},{c},{s}^3) {str(dt)[6:]:8s} border={bn:4s} fwd [slab32] {ts*1e6:8.1f} us "
-                          f"{nbytes/ts/1e9:7.0f} GB/s ({nbytes/ts/1e9/PEAK*100:4.1f}%)")
+                          f"{nbytes/ts/1e9:7.0f} GB/s ({nbytes/ts/1e9/PEAK*100:4.1f}%)  bwd [gather] {tg*1e6:8.1f} us "
+                          f"{nbytes/tg/1e9:7.0f} GB/s ({nbytes/tg/1e9/PEAK*100:4.1f}%)")
             del bufs
 
 
