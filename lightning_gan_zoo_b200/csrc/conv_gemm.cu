@@ -85,6 +85,24 @@ struct WgradParams {
     } pairs[kMaxTaps];
 };
 
+// Grouped wgrad (opt-in, HG_WGRAD_GROUP=1): pairs that read the SAME shifted X box are served by one CTA -- the box
+// is loaded once and multiplied against the dY column blocks of all (<= kWgMaxCols) parity classes that use this shift,
+// one BN-wide accumulator block each (N = ncols * BN <= 256 TMEM columns).
+constexpr int kWgMaxCols = 4;
+struct WgradGroupParams {
+    CUtensorMap tmX, tmDY;
+    int X, Y, Z, Bn;
+    int BN;               // Cout tile of one class (== Cout here: one N tile per class)
+    int stages, pos_tiles, splits, cin, cout, num_taps_total;
+    float *dw;            // split-K partials, fp32 [split][tap][Cin][Cout]
+    int num_groups;
+    struct Grp {
+        int16_t sx, sy, sz, ncols;
+        int32_t dy_c_off[kWgMaxCols];     // cls * Cout of every column block
+        int32_t tap_flat[kWgMaxCols];     // slice index in dw of every column block
+    } groups[kMaxTaps];
+};
+
 struct SharedCtl {
     uint64_t full[kMaxStages];
     uint64_t empty[kMaxStages];
@@ -345,6 +363,125 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_gemm_kernel(const __grid_co
     ptx::tc_fence_before();
     __syncthreads();
     if (warp == 1) ptx::tmem_dealloc(tmem_base, tmem_cols_for(BN));
+}
+
+// -------------------------------------------------------------------------------------------------
+// Grouped wgrad kernel: wgrad_gemm_kernel with several dY column blocks per CTA (see WgradGroupParams).  Not yet run on a
+// B200: selected only by HG_WGRAD_GROUP=1, the default path above is untouched.
+// grid = (Cin/128, 1, groups * splits)
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads, 1) wgrad_gemm_grouped_kernel(const __grid_constant__ WgradGroupParams p)
+{
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ SharedCtl ctl;
+    uint8_t *tiles = align_1024(smem_raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int BN = p.BN;
+    constexpr int kPos = 64;
+    const uint32_t box_bytes = kPos * 128;
+    const int grp_idx = blockIdx.z / p.splits, split = blockIdx.z % p.splits;
+    const WgradGroupParams::Grp gr = p.groups[grp_idx];
+    const int ncols = gr.ncols, ntot = ncols * BN;               // accumulator columns of this CTA
+    const uint32_t a_bytes = 2 * box_bytes, b_bytes = (uint32_t)(ntot / 64) * box_bytes, stage_bytes = a_bytes + b_bytes;
+    const int ci0 = blockIdx.x * kBM;
+    const int per = (p.pos_tiles + p.splits - 1) / p.splits;
+    const int t_begin = split * per, t_end = min(p.pos_tiles, t_begin + per);
+    const int total_iters = max(0, t_end - t_begin);
+
+    if (warp == 0 && ptx::elect_one()) {
+        ptx::prefetch_tensormap(&p.tmX);
+        ptx::prefetch_tensormap(&p.tmDY);
+        for (int s = 0; s < p.stages; ++s) {
+            ptx::mbar_init(&ctl.full[s], 1);
+            ptx::mbar_init(&ctl.empty[s], 1);
+        }
+        ptx::mbar_init(&ctl.acc_ready, 1);
+        ptx::fence_barrier_init();
+    }
+    if (warp == 1) {
+        ptx::tmem_alloc(&ctl.tmem_base, tmem_cols_for(ntot));
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = ctl.tmem_base;
+
+    if (total_iters == 0 && warp >= 2) {                       // empty K range: this split's partial tiles are all zero
+        const int row = (warp & 3) * 32 + lane;
+        if (ci0 + row < p.cin) {
+            for (int jc = 0; jc < ncols; ++jc) {
+                float *orow = p.dw + (((size_t)split * p.num_taps_total + gr.tap_flat[jc]) * p.cin + ci0 + row) * p.cout;
+                for (int c = 0; c < BN; c += 4) *reinterpret_cast<float4 *>(orow + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+    }
+    if (total_iters > 0) {
+        if (warp == 0) {
+            if (ptx::elect_one()) {
+                for (int it = 0; it < total_iters; ++it) {
+                    long long pos = (long long)(t_begin + it) * kPos;
+                    const int x0 = (int)(pos % p.X); pos /= p.X;
+                    const int y0 = (int)(pos % p.Y); pos /= p.Y;
+                    const int z0 = (int)(pos % p.Z);
+                    const int b0 = (int)(pos / p.Z);
+                    const int s = it % p.stages;
+                    const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+                    ptx::mbar_wait(&ctl.empty[s], ph ^ 1u);
+                    uint8_t *dst = tiles + (size_t)s * stage_bytes;
+                    ptx::mbar_arrive_expect_tx(&ctl.full[s], stage_bytes);
+                    for (int j = 0; j < 2; ++j)
+                        ptx::tma_load_5d(dst + j * box_bytes, &p.tmX, &ctl.full[s], ci0 + j * 64, x0 + gr.sx, y0 + gr.sy,
+                                         z0 + gr.sz, b0);
+                    int box = 0;
+                    for (int jc = 0; jc < ncols; ++jc)
+                        for (int j = 0; j < BN / 64; ++j, ++box)
+                            ptx::tma_load_5d(dst + a_bytes + box * box_bytes, &p.tmDY, &ctl.full[s], gr.dy_c_off[jc] + j * 64, x0, y0,
+                                             z0, b0);
+                }
+            }
+        } else if (warp == 1) {
+            if (ptx::elect_one()) {
+                const uint32_t idesc = ptx::idesc_bf16(kBM, ntot, true, true);
+                for (int it = 0; it < total_iters; ++it) {
+                    const int s = it % p.stages;
+                    const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+                    ptx::mbar_wait(&ctl.full[s], ph);
+                    ptx::tc_fence_after();
+                    const uint32_t a_addr = ptx::smem_u32(tiles + (size_t)s * stage_bytes);
+                    const uint64_t a_desc = ptx::smem_desc_sw128(a_addr, box_bytes, 1024);
+                    const uint64_t b_desc = ptx::smem_desc_sw128(a_addr + a_bytes, box_bytes, 1024);
+#pragma unroll
+                    for (int k = 0; k < kPos / 16; ++k)
+                        ptx::umma_bf16(tmem_base, a_desc + (uint64_t)(k * 128), b_desc + (uint64_t)(k * 128), idesc,
+                                       (it | k) != 0);
+                    ptx::umma_commit(&ctl.empty[s]);
+                }
+                ptx::umma_commit(&ctl.acc_ready);
+            }
+        } else {
+            ptx::mbar_wait(&ctl.acc_ready, 0);
+            ptx::tc_fence_after();
+            const int quad = warp & 3;
+            const int row = quad * 32 + lane;
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
+            for (int jc = 0; jc < ncols; ++jc) {
+                float *orow = p.dw + (((size_t)split * p.num_taps_total + gr.tap_flat[jc]) * p.cin + ci0 + row) * p.cout;
+                for (int c0 = 0; c0 < BN; c0 += 16) {
+                    float v[16];
+                    ptx::tmem_ld_16(taddr + (uint32_t)(jc * BN + c0), v);
+                    if (ci0 + row < p.cin) {
+                        float4 *dst = reinterpret_cast<float4 *>(orow + c0);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    }
+                }
+            }
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) ptx::tmem_dealloc(tmem_base, tmem_cols_for(ntot));
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -900,10 +1037,59 @@ extern "C" int hg_convt_wgrad(const void *x, const void *dy_s2d, float *dw, void
         cudaFuncSetAttribute(wgrad_reduce_kernel<25>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
         attr_set = true;
     }
-    dim3 grid(cin / kBM, cout / bn, np * pl.splits);
-    wgrad_gemm_kernel<<<grid, kThreads, smem, st>>>(p);
-    rc = check_launch("hg_convt_wgrad");
-    if (rc) return rc;
+    const char *grp_env = getenv("HG_WGRAD_GROUP");
+    const bool grouped = grp_env && grp_env[0] && grp_env[0] != '0' && bn == cout && cout <= 128 && c.taps > 1;
+    if (grouped) {
+        // pairs with the same shift share one CTA (<= 256 accumulator columns); the partial buffer, the split-K plan
+        // and the reduce kernel are those of the default path
+        WgradGroupParams gp{};
+        gp.tmX = p.tmX; gp.tmDY = p.tmDY;
+        gp.X = p.X; gp.Y = p.Y; gp.Z = p.Z; gp.Bn = p.Bn; gp.BN = bn; gp.cin = cin; gp.cout = cout; gp.dw = p.dw;
+        gp.num_taps_total = c.taps; gp.pos_tiles = pl.pos_tiles;
+        const int max_cols = 256 / bn < kWgMaxCols ? 256 / bn : kWgMaxCols;
+        int ng = 0;
+        for (int i = 0; i < np; ++i) {
+            const WgradParams::Pair &pr = p.pairs[i];
+            int g = -1;
+            for (int k = 0; k < ng; ++k)
+                if (gp.groups[k].sx == pr.sx && gp.groups[k].sy == pr.sy && gp.groups[k].sz == pr.sz && gp.groups[k].ncols < max_cols) {
+                    g = k;
+                    break;
+                }
+            if (g < 0) {
+                g = ng++;
+                gp.groups[g].sx = pr.sx; gp.groups[g].sy = pr.sy; gp.groups[g].sz = pr.sz; gp.groups[g].ncols = 0;
+            }
+            WgradGroupParams::Grp &gr = gp.groups[g];
+            gr.dy_c_off[gr.ncols] = pr.dy_c_off;
+            gr.tap_flat[gr.ncols] = pr.tap_flat;
+            gr.ncols++;
+        }
+        gp.num_groups = ng;
+        // same number of resident CTAs as the default plan, now spread over fewer (fatter) output tiles
+        int gsplits = (2 * sm_count()) / ((cin / kBM) * ng);
+        if (gsplits > pl.pos_tiles / 8) gsplits = pl.pos_tiles / 8;
+        if (gsplits < 1) gsplits = 1;
+        if (gsplits > pl.splits) gsplits = pl.splits;            // the partial buffer was sized for pl.splits
+        gp.splits = gsplits;
+        const int gstage = 2 * 64 * 128 + max_cols * (bn / 64) * 64 * 128;
+        gp.stages = pick_stages(gstage, (gp.pos_tiles + gsplits - 1) / gsplits, kWgradSmemBudget);
+        const size_t gsmem = (size_t)gp.stages * gstage + 1024;
+        static bool gattr = false;
+        if (!gattr) {
+            cudaFuncSetAttribute(wgrad_gemm_grouped_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgradSmemBudget);
+            gattr = true;
+        }
+        wgrad_gemm_grouped_kernel<<<dim3(cin / kBM, 1, ng * gsplits), kThreads, gsmem, st>>>(gp);
+        rc = check_launch("hg_convt_wgrad(grouped)");
+        if (rc) return rc;
+        pl.splits = gsplits;                                     // the reduce below sums the splits that were written
+    } else {
+        dim3 grid(cin / kBM, cout / bn, np * pl.splits);
+        wgrad_gemm_kernel<<<grid, kThreads, smem, st>>>(p);
+        rc = check_launch("hg_convt_wgrad");
+        if (rc) return rc;
+    }
     dim3 rgrid((cin + kBrickCi - 1) / kBrickCi, (cout + kBrickCo - 1) / kBrickCo);
     const size_t rsmem = (size_t)kBrickCi * brick_row_pitch(c.taps) * sizeof(float);
     const float *part = static_cast<const float *>(workspace);

@@ -116,6 +116,18 @@ def test_convt_k5_in_child_process():
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-1000:]
 
 
+@pytest.mark.xfail(strict=False, reason="grouped wgrad kernel (HG_WGRAD_GROUP=1: one X box feeds every parity class that uses its shift) "
+                                        "was written after the round's GPU budget was spent -- not yet run on a B200")
+def test_wgrad_grouped_in_child_process():
+    """The fwd / dgrad / wgrad cases below with the grouped wgrad kernel selected, in a child process."""
+    import subprocess
+    import sys
+    env = dict(os.environ, HG_WGRAD_GROUP="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-k", "test_convt_fwd_dgrad_wgrad", "-m", "gpu"],
+                       capture_output=True, text=True, timeout=300, env=env, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-1000:]
+
+
 @pytest.mark.parametrize("ndim,kernel,batch,cin,cout,size", CASES)
 def test_convt_fwd_dgrad_wgrad(ndim, kernel, batch, cin, cout, size):
     torch.backends.cudnn.allow_tf32 = False

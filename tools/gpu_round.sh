@@ -47,10 +47,14 @@ if has mma; then
 fi
 if has optin; then
   # code finished after round 1's GPU budget was spent: first measurements
-  timeout 900 python -m pytest tests -m gpu -q --runxfail -k "slab32 or k5_in_child or tcgen05_convs" > $OUT/${TAG}_pytest_optin.txt 2>&1
+  timeout 900 python -m pytest tests -m gpu -q --runxfail -k "slab32 or k5_in_child or tcgen05_convs or wgrad_grouped" > $OUT/${TAG}_pytest_optin.txt 2>&1
   echo "optin pytest exit $?"; tail -15 $OUT/${TAG}_pytest_optin.txt
   HG_BENCH_SLAB32=1 timeout 600 python tools/microbench.py rotate32 > $OUT/${TAG}_microbench_rotate32.txt 2>&1
   grep -E "32\^3" $OUT/${TAG}_microbench_rotate32.txt
+  HG_WGRAD_GROUP=1 timeout 300 python tools/microbench.py conv > $OUT/${TAG}_microbench_conv_grouped.txt 2>&1
+  grep -E "^block|^proj|totals" $OUT/${TAG}_microbench_conv_grouped.txt
+  HG_WGRAD_GROUP=1 timeout 300 python bench.py --steps 30 --warmup 6 --no-cpu-baseline --no-roofline > $OUT/${TAG}_bench_wgrad_group.json 2> $OUT/${TAG}_bench_wgrad_group.err
+  echo "bench wgrad_group exit $?"; cut -c1-220 $OUT/${TAG}_bench_wgrad_group.json
   HG_D_TCGEN05=1 timeout 300 python bench.py --steps 30 --warmup 6 --no-cpu-baseline --no-roofline > $OUT/${TAG}_bench_d_tcgen05.json 2> $OUT/${TAG}_bench_d_tcgen05.err
   echo "bench d_tcgen05 exit $?"; cut -c1-220 $OUT/${TAG}_bench_d_tcgen05.json; tail -3 $OUT/${TAG}_bench_d_tcgen05.err
 fi
