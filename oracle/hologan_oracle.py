@@ -209,33 +209,68 @@ def adain(x: Tensor, scale: Tensor, bias: Tensor) -> Tensor:
 # generator forward (functional over a reference-keyed state dict)
 # --------------------------------------------------------------------------------------
 
-def _style_block(h: Tensor, z: Tensor, p: Dict[str, Tensor], prefix: str, dims: int) -> Tensor:
+class _StoreBf16(torch.autograd.Function):
+    """Value stored as bf16 (round to nearest even), its gradient stored as bf16 too."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.to(torch.bfloat16).float()
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.to(torch.bfloat16).float()
+
+
+class _OperandBf16(torch.autograd.Function):
+    """bf16 copy of an fp32 master weight: the forward value is rounded, the gradient stays fp32."""
+
+    @staticmethod
+    def forward(ctx, w):
+        return w.to(torch.bfloat16).float()
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
+def _ident(t: Tensor) -> Tensor:
+    return t
+
+
+def _style_block(h: Tensor, z: Tensor, p: Dict[str, Tensor], prefix: str, dims: int, store=_ident,
+                 operand=_ident) -> Tensor:
     """BasicBlock.forward, hologan_generator.py:37-42."""
-    w, bia = p[prefix + ".convTranspose.weight"], p[prefix + ".convTranspose.bias"]
+    w, bia = operand(p[prefix + ".convTranspose.weight"]), p[prefix + ".convTranspose.bias"]
     if dims == 3:
         h = F.conv_transpose3d(h, w, bia, stride=2, padding=1, output_padding=1)      # :29-30
     else:
         h = F.conv_transpose2d(h, w, bia, stride=2, padding=1)                        # :26-27
     s, b = zmapping(z, p[prefix + ".zMapping.linear1.weight"], p[prefix + ".zMapping.linear1.bias"])
-    return F.relu(adain(h, s, b))
+    return store(F.relu(adain(store(h), s, b)))
 
 
 def generator_forward(p: Dict[str, Tensor], z: Tensor, view, img_size: int = 64,
-                      patched128: bool = True, stages: Optional[dict] = None) -> Tensor:
+                      patched128: bool = True, stages: Optional[dict] = None, bf16_storage: bool = False) -> Tensor:
     """Generator.forward, hologan_generator.py:116-143.  `p` uses the reference's
     state_dict keys.  img_size==128 needs `patched128` (the reference's 128
-    branch lacks stride=2; the patched variant uses ConvTranspose2d(k4,s2,p1))."""
+    branch lacks stride=2; the patched variant uses ConvTranspose2d(k4,s2,p1)).
+
+    `bf16_storage=True` is NOT the reference: it is the same fp32 CPU arithmetic with every activation (and its
+    gradient) that a bf16 pipeline keeps in memory rounded to bf16 where it is stored, and bf16 copies of the
+    convolution weights -- the error floor of ANY implementation with bf16 operands and fp32 accumulation, used by
+    the tests to tell kernel defects from the price of the storage format (tests/test_gpu_generator.py)."""
+    store, operand = (_StoreBf16.apply, _OperandBf16.apply) if bf16_storage else (_ident, _ident)
     bsz = z.shape[0]
     x = p["x"].repeat(bsz, 1, 1, 1, 1)                                                # :121
     s0, b0 = zmapping(z, p["zMapping.linear1.weight"], p["zMapping.linear1.bias"])    # :122
-    h0 = F.relu(adain(x, s0, b0))                                                     # :123-124
-    h1 = _style_block(h0, z, p, "block1", 3)                                          # :126
-    h2 = _style_block(h1, z, p, "block2", 3)                                          # :127
-    rot = rotate_resample(h2, view)                                                   # :129
+    h0 = store(F.relu(adain(x, s0, b0)))                                              # :123-124
+    h1 = _style_block(h0, z, p, "block1", 3, store, operand)                          # :126
+    h2 = _style_block(h1, z, p, "block2", 3, store, operand)                          # :127
+    rot = store(rotate_resample(h2, view))                                            # :129
     h2d = project_depth_to_channels(rot)                                              # :130-133
-    h3 = F.relu(F.conv_transpose2d(h2d, p["convTranspose2d1.weight"], p["convTranspose2d1.bias"]))  # :135-136
-    h4 = _style_block(h3, z, p, "block3", 2)                                          # :138
-    h5 = _style_block(h4, z, p, "block4", 2)                                          # :139
+    h3 = store(F.relu(F.conv_transpose2d(h2d, operand(p["convTranspose2d1.weight"]), p["convTranspose2d1.bias"])))  # :135-136
+    h4 = _style_block(h3, z, p, "block3", 2, store, operand)                          # :138
+    h5 = _style_block(h4, z, p, "block4", 2, store, operand)                          # :139
     if img_size == 64:
         h6 = F.conv2d(h5, p["final_layer.weight"], p["final_layer.bias"], padding=1)  # :70
     elif img_size == 128:

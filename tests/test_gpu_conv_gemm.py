@@ -80,6 +80,13 @@ CASES = [  # (ndim, kernel, batch, cin, cout, size)
     (3, 3, 4, 512, 128, 4),        # block1 (a4)
     (3, 3, 3, 512, 128, 4),        # odd batch: last 128-row box is half out of range
     (3, 3, 2, 128, 64, 8),         # block2 (a4)
+    # the bench configuration (BASELINE.json configs[1], batch 64): the split-K plans, tile counts and dual / single
+    # launch shapes that bench.py actually runs
+    (2, 4, 64, 1024, 256, 16),     # block3
+    (2, 4, 64, 256, 64, 32),       # block4
+    (3, 3, 64, 512, 128, 4),       # block1
+    (3, 3, 64, 128, 64, 8),        # block2
+    (2, 1, 64, 1024, 1024, 16),    # projection
 ]
 
 

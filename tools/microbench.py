@@ -151,6 +151,53 @@ def conv():
     print("totals: " + ", ".join(f"{k} {v*1e6:.0f} us" for k, v in tot.items()))
 
 
+def dconv():
+    """The discriminator's three Conv2d(k5, s2, p2) on the tcgen05 tap GEMMs (transposed-conv duality, ops.conv5x5_s2):
+    forward = hg_convt_dgrad, dx = hg_convt_fwd, dw = hg_convt_wgrad, next to cuDNN bf16 channels-last on the same shapes."""
+    import ctypes
+    import torch.nn.functional as F
+    from lightning_gan_zoo_b200 import _lib
+    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {"bf16_tflops": 1590.0}
+    peak = peaks["bf16_tflops"]
+    P = ops._ptr
+    for B, img in ((64, 64), (32, 128)):
+        print(f"# D convs at B={B}, {img}x{img}; bf16 peak {peak} TFLOP/s")
+        side = img // 4
+        for name, cin, cout in (("D blk0", 64, 128), ("D blk1", 128, 256), ("D blk2", 256, 512)):
+            size = side                                  # output extent
+            flops = 2.0 * B * size * size * cin * cout * 25
+            nb = 3
+            xs = [torch.randn(B, size, size, 4, cin, device=DEV).to(torch.bfloat16) for _ in range(nb)]
+            dys = [torch.randn(B, size, size, cout, device=DEV).to(torch.bfloat16) for _ in range(nb)]
+            w = torch.randn(cout, cin, 5, 5, device=DEV) * 0.02
+            wf, wd = ops.pack_convt_weight(w)
+            y = torch.empty_like(dys[0]); dx = torch.empty_like(xs[0]); dw = torch.empty_like(w)
+            nws = _lib.load().hg_convt_wgrad_workspace_bytes(B, cout, cin, 2, size, 5)
+            ws = torch.empty(max(nws, 16), dtype=torch.uint8, device=DEV)
+            f = lambda i: _lib.call("hg_convt_dgrad", P(xs[i]), P(wd), P(y), B, cout, cin, 2, size, 5, ops._stream())
+            g = lambda i: _lib.call("hg_convt_fwd", P(dys[i]), P(wf), P(None), P(dx), B, cout, cin, 2, size, 5, ctypes.c_float(1.0), ops._stream())
+            h = lambda i: _lib.call("hg_convt_wgrad", P(dys[i]), P(xs[i]), P(dw), P(ws), nws, B, cout, cin, 2, size, 5, 0, 0, 0, ops._stream())
+            row = f"{name} {cin:3d}->{cout:3d} out {size:2d}^2 {flops/1e9:6.1f} GF"
+            for tag, fn in (("fwd", f), ("dx", g), ("dw", h)):
+                if tag == "dw" and nws < 0:
+                    row += " | dw unsupported"
+                    continue
+                t = time_rot(fn, list(range(nb)), iters=12)
+                row += f" | {tag} {t*1e6:6.1f} us {flops/t/1e12:5.0f} TF/s ({flops/t/1e12/peak*100:4.1f}%)"
+            # cuDNN on the same shapes (channels-last bf16), forward and backward
+            xc = [torch.randn(B, cin, 2 * size, 2 * size, device=DEV).to(torch.bfloat16).contiguous(memory_format=torch.channels_last).requires_grad_(True) for _ in range(nb)]
+            wc = w.to(torch.bfloat16).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+            tf = time_rot(lambda i: F.conv2d(xc[i], wc, None, stride=2, padding=2), list(range(nb)), iters=12)
+            dyc = torch.randn(B, cout, size, size, device=DEV).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+            def fb(i):
+                xc[i].grad = None; wc.grad = None
+                F.conv2d(xc[i], wc, None, stride=2, padding=2).backward(dyc)
+            tfb = time_rot(fb, list(range(nb)), iters=12, graph=False)
+            row += f" | cuDNN fwd {tf*1e6:6.1f} us, fwd+bwd {tfb*1e6:6.1f} us"
+            print(row)
+            side //= 2
+
+
 def pipeline():
     """The HBM-bound kernels of the bf16 pipeline at their hot-path shapes (B = 64): channels-last AdaIN on
     s2d conv outputs, channels-last rotate (-> PROJ), final conv + tanh, weight packing, activation backward."""
@@ -261,5 +308,7 @@ if __name__ == "__main__":
         adain()
     if what in ("conv", "all"):
         conv()
+    if what in ("dconv", "all"):
+        dconv()
     if what in ("pipeline", "all"):
         pipeline()
