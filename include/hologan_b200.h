@@ -8,8 +8,10 @@
  * Conventions
  *   - every pointer is a DEVICE pointer unless the parameter name ends in `_host`;
  *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
- *   - functions only enqueue work: no allocation, no synchronisation, no global mutable state,
- *     safe to call from several host threads and inside CUDA-graph capture;
+ *   - functions only enqueue work: no allocation, no synchronisation, safe to call from several host
+ *     threads and inside CUDA-graph capture.  The only process-wide state is the table of tuning options
+ *     below (hg_set_option), which selects between equivalent kernels and is never read from the
+ *     environment at launch time;
  *   - return 0 on success, a negative hg_status_t otherwise; hg_last_error() returns a
  *     thread-local message for the last failure on the calling thread.
  */
@@ -23,7 +25,7 @@
 extern "C" {
 #endif
 
-#define HG_ABI_VERSION 1
+#define HG_ABI_VERSION 2
 #define HG_SN_MAX_LAYERS 4
 #define HG_LINEAR_GROUP_MAX 8
 
@@ -60,6 +62,18 @@ typedef enum {
 
 int hg_abi_version(void);
 const char *hg_last_error(void);
+
+/* Tuning options: switches between EQUIVALENT implementations of a pass (A/B measurements, tests of both kernels).
+ * Each option NAME is initialised once from the environment variable HG_<NAME> (when the library first needs an
+ * option) and changes afterwards only through hg_set_option; `name` may carry the HG_ prefix.
+ *   ADAIN_CL_NO_CLUSTER  (0)   1: channels-last AdaIN on the chunked two-kernel path only
+ *   ADAIN_CL_CLUSTER_BWD (0)   1: cluster single-pass kernel for the channels-last AdaIN backward
+ *   TAPGEMM_DUAL         (-1)  -1 auto; 0 / 1: force one / two tap-GEMM CTAs per SM
+ *   FINAL_CONV_MMA       (7)   bit mask of final-layer passes on the mma.sync kernels (1 fwd, 2 dx, 4 dw)
+ *   ROTATE_SLAB32        (1)   32^3 rotate forward on source-slab tiles (0: per-channel slab kernel)
+ *   ROTATE_GATHER_BWD    (1)   32^3 rotate backward as a table-free per-voxel gather (0: shared-memory scatter) */
+int hg_set_option(const char *name, int value);
+int hg_get_option(const char *name, int *value);
 
 /* ---- a6 + a7 (+ a8): rigid-body rotate + trilinear resample ------------------------------------
  * Replaces Generator.apply_transformation / interpolation / meshgrid
@@ -125,6 +139,9 @@ int hg_adain_act_bwd(const void *x, const void *dy, const float *scale, const fl
  *   scale / bias may both be NULL (= 1 / 0) and dscale / dbias may both be NULL (not computed); with
  *   biased_var = 1, eps = 1e-5, neg_slope = 0.2 that is the discriminator's InstanceNorm2d + LeakyReLU
  *   (core/models/hologan_discriminator.py:16-17,21-22) on channels-last activations.
+ *   classes = -4 (ndim 2): x is a plain channels-last (B, S, S, C) tensor and y (and dy) are stored in 2x2
+ *   space-to-depth order (B, S/2, S/2, 4, C), y[b, i, j, (py, px), c] = pixel (2i+py, 2j+px) -- the input layout of
+ *   hg_conv5s2_fwd, so the discriminator's blocks chain without a layout pass.
  *   workspace: hg_adain_cl_workspace_bytes() bytes of scratch for the per-chunk partial sums (0 for small
  *   instances, then it may be NULL); deterministic (fixed summation order). */
 long long hg_adain_cl_workspace_bytes(int batch, int channels, int ndim, int size, int classes);
@@ -229,6 +246,61 @@ int hg_spectral_norm_fwd(int layers, const float *const *w, float *const *u, flo
 int hg_spectral_norm_bwd(int layers, const void *const *dw, const float *const *w, const float *const *state,
                          float *const *dw_orig, const int *cout, const int *cin, const int *taps, int accumulate, int dw_dtype,
                          void *workspace, long long workspace_bytes, void *stream);
+
+/* w_out[i] may be NULL: only the power iteration and sigma (state[i][0], a device float) are produced -- the caller
+ * then folds 1 / sigma into its own weight pack (hg_conv5s2_pack_weight). */
+
+/* ---- a14 (f1): the discriminator's convolutions and heads on hand-written kernels -----------------------
+ * Conv2d(k5, s2, p2) of the three spectral-norm blocks (core/models/hologan_discriminator.py:12,20) on the tcgen05 tap
+ * GEMMs.  On a 2x2 space-to-depth input every kernel tap is a shift in {-1,0,1}^2 of one parity class, i.e. the op is
+ * the dgrad of the dual ConvTranspose2d(k5,s2,p2,op1) (kernel = 5 of hg_convt_*).  These layers have few output
+ * positions and a long K, so the K loop is split over taps across CTAs: fp32 partial tiles in `workspace`, summed in a
+ * fixed order by a second kernel (deterministic, no atomics).  No bias: InstanceNorm follows (a per-channel constant
+ * cancels).  bf16, channels-last:
+ *   x_s2d  (B, S, S, 4, Cin)  x_s2d[b, i, j, (py, px), c] = x[b, c, 2i+py, 2j+px];  y / dy (B, S, S, Cout), S = size_out
+ *   hg_conv5s2_pack_weight: torch Conv2d weight (Cout, Cin, 5, 5) fp32 contiguous, divided by *sigma (DEVICE float,
+ *   NULL = 1: the spectral norm of :15) -> w_k [25][Cout][Cin] (forward), w_t [25][Cin][Cout] (dx); either may be NULL
+ *   out_scale: DEVICE float or NULL -- the result of forward / dx is multiplied by it in the epilogue.  With 1 / sigma
+ *   there (state[1] of hg_spectral_norm_fwd) the packed weights can stay the UN-normalised weight_orig (packed once per
+ *   optimizer step, sigma = NULL) although sigma moves with every forward: conv(x, W / sigma) = conv(x, W) / sigma.
+ *   hg_conv5s2_dw: dw (Cout, Cin, 5, 5) fp32 w.r.t. the (normalised) weight; accumulate != 0 adds.
+ * Supported: Cin % 64 == 0, Cout % 128 == 0, B * S * S % 128 == 0 with S a power of two. */
+long long hg_conv5s2_workspace_bytes(int batch, int cin, int cout, int size_out);
+int hg_conv5s2_pack_weight(const float *w, const float *sigma, void *w_k, void *w_t, int cin, int cout, void *stream);
+int hg_conv5s2_fwd(const void *x_s2d, const void *w_k, const float *out_scale, void *y, void *workspace,
+                   long long workspace_bytes, int batch, int cin, int cout, int size_out, void *stream);
+int hg_conv5s2_dx(const void *dy, const void *w_t, const float *out_scale, void *dx_s2d, void *workspace,
+                  long long workspace_bytes, int batch, int cin, int cout, int size_out, void *stream);
+int hg_conv5s2_dw(const void *dy, const void *x_s2d, float *dw, void *workspace, long long workspace_bytes, int batch, int cin,
+                  int cout, int size_out, int accumulate, void *stream);
+
+/* First convolution of the discriminator: y = leaky_relu(Conv2d(3 -> 64, k5, s2, p2)(x) + bias, neg_slope)
+ * (core/models/hologan_discriminator.py:30,58).  x (B, 3, S, S) fp32 NCHW (the real batch, or the generator's output);
+ * y_s2d (B, S/4, S/4, 4, 64) bf16: the (S/2 x S/2) activation in the space-to-depth order hg_conv5s2_fwd reads.
+ * Warp-level tensor cores (mma.sync, bf16 operands, fp32 accumulation).  S % 32 == 0.
+ * backward: dy_s2d in y's layout; dx (B, 3, S, S) fp32 (NULL = not needed: real images), dw (64, 3, 5, 5) + dbias (64)
+ * fp32 (both NULL = not needed: generator step; accumulate != 0 adds to them).  workspace: hg_dconv0_bwd_workspace_bytes(). */
+int hg_dconv0_fwd(const float *x, const float *w, const float *bias, void *y_s2d, int batch, int cin, int cout, int size,
+                  float neg_slope, void *stream);
+long long hg_dconv0_bwd_workspace_bytes(int batch, int size);
+int hg_dconv0_bwd(const float *x, const float *w, const void *y_s2d, const void *dy_s2d, float *dx, float *dw, float *dbias,
+                  void *workspace, long long workspace_bytes, int batch, int cin, int cout, int size, float neg_slope,
+                  int accumulate, void *stream);
+
+/* The two heads (core/models/hologan_discriminator.py:41-51,64-68) on the last block's channels-last activation
+ * h (B, H*W, C) bf16 (the reference flattens (c, h, w): weights are addressed with feature f = c * HW + hw):
+ *   logits (B) = linear1(h);  t2 (B, 128) = leaky_relu(linear2(h), neg_slope);  z_pred (B, zdim) = tanh(linear3(t2))
+ * w1 (1, F), w2 (128, F), w3 (zdim, 128) fp32 torch layouts, F = C * HW; outputs fp32.  batch <= 64 per call, HW | 64.
+ * backward: dlogits (B) / dz_pred (B, zdim) fp32 (either may be NULL = zero); dh (B, HW, C) bf16 (may be NULL); the six
+ * parameter gradients are overwritten, all given or all NULL (generator step).  workspace: hg_dheads_workspace_bytes(). */
+long long hg_dheads_workspace_bytes(int batch, int channels, int hw, int zdim);
+int hg_dheads_fwd(const void *h, const float *w1, const float *b1, const float *w2, const float *b2, const float *w3,
+                  const float *b3, float *logits, float *t2, float *z_pred, void *workspace, long long workspace_bytes,
+                  int batch, int channels, int hw, int zdim, float neg_slope, void *stream);
+int hg_dheads_bwd(const void *h, const float *w1, const float *w2, const float *w3, const float *t2, const float *z_pred,
+                  const float *dlogits, const float *dz_pred, void *dh, float *dw1, float *db1, float *dw2, float *db2,
+                  float *dw3, float *db3, void *workspace, long long workspace_bytes, int batch, int channels, int hw, int zdim,
+                  float neg_slope, void *stream);
 
 /* ---- a13: the losses of HOLOGAN.training_step  (core/lightning_module.py:217-237) -------------------
  *   adv = wa * mean_i BCEWithLogits(a[i], ta) + wb * mean_j BCEWithLogits(b[j], tb)   (b may be NULL, nb = 0)

@@ -22,6 +22,8 @@ _c_int, _c_void_p, _c_float, _c_ll = ctypes.c_int, ctypes.c_void_p, ctypes.c_flo
 SIGNATURES = {
     "hg_abi_version": [],
     "hg_last_error": [],
+    "hg_set_option": [ctypes.c_char_p, _c_int],
+    "hg_get_option": [ctypes.c_char_p, _c_void_p],
     "hg_rotate_fwd": [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int,
                       _c_int, _c_int, _c_void_p],
     "hg_rotate_bwd_workspace_bytes": [_c_int, _c_int, _c_int],
@@ -56,6 +58,18 @@ SIGNATURES = {
     "hg_final_conv_tanh_bwd_workspace_bytes": [_c_int, _c_int, _c_int, _c_int],
     "hg_final_conv_tanh_bwd": [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
                                _c_ll, _c_int, _c_int, _c_int, _c_int, _c_void_p],
+    "hg_conv5s2_workspace_bytes": [_c_int, _c_int, _c_int, _c_int],
+    "hg_conv5s2_pack_weight": [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_void_p],
+    "hg_conv5s2_fwd": [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_ll, _c_int, _c_int, _c_int, _c_int, _c_void_p],
+    "hg_conv5s2_dx": [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_ll, _c_int, _c_int, _c_int, _c_int, _c_void_p],
+    "hg_conv5s2_dw": [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_ll, _c_int, _c_int, _c_int, _c_int, _c_int, _c_void_p],
+    "hg_dconv0_fwd": [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_float, _c_void_p],
+    "hg_dconv0_bwd_workspace_bytes": [_c_int, _c_int],
+    "hg_dconv0_bwd": [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_ll, _c_int,
+                      _c_int, _c_int, _c_int, _c_float, _c_int, _c_void_p],
+    "hg_dheads_workspace_bytes": [_c_int, _c_int, _c_int, _c_int],
+    "hg_dheads_fwd": [_c_void_p] * 11 + [_c_ll, _c_int, _c_int, _c_int, _c_int, _c_float, _c_void_p],
+    "hg_dheads_bwd": [_c_void_p] * 16 + [_c_ll, _c_int, _c_int, _c_int, _c_int, _c_float, _c_void_p],
     "hg_gan_loss_fwd": [_c_void_p, _c_int, _c_float, _c_float, _c_void_p, _c_int, _c_float, _c_float, _c_void_p, _c_void_p,
                         _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p],
     "hg_gan_loss_bwd": [_c_void_p, _c_void_p, _c_int, _c_float, _c_float, _c_void_p, _c_int, _c_float, _c_float, _c_void_p,
@@ -71,7 +85,9 @@ _RESTYPES = {"hg_last_error": ctypes.c_char_p, "hg_rotate_bwd_workspace_bytes": 
              "hg_convt_wgrad_workspace_bytes": ctypes.c_longlong, "hg_act_bwd_bias_workspace_bytes": ctypes.c_longlong,
              "hg_adain_cl_workspace_bytes": ctypes.c_longlong,
              "hg_final_conv_tanh_bwd_workspace_bytes": ctypes.c_longlong,
-             "hg_spectral_norm_state_floats": ctypes.c_longlong, "hg_spectral_norm_workspace_bytes": ctypes.c_longlong}
+             "hg_spectral_norm_state_floats": ctypes.c_longlong, "hg_spectral_norm_workspace_bytes": ctypes.c_longlong,
+             "hg_conv5s2_workspace_bytes": ctypes.c_longlong, "hg_dconv0_bwd_workspace_bytes": ctypes.c_longlong,
+             "hg_dheads_workspace_bytes": ctypes.c_longlong}
 
 _lib = None
 _lock = threading.Lock()
@@ -99,7 +115,7 @@ def load() -> ctypes.CDLL:
             fn = getattr(lib, name)       # AttributeError if the .so is stale
             fn.argtypes = argtypes
             fn.restype = _RESTYPES.get(name, _c_int)
-        if lib.hg_abi_version() != 1:
+        if lib.hg_abi_version() != 2:
             raise HologanB200Error("libhologan_b200.so ABI version mismatch; rebuild")
         _lib = lib
     return _lib
@@ -114,3 +130,20 @@ def call(name: str, *args) -> None:
     if rc != 0:
         msg = lib.hg_last_error()
         raise HologanB200Error(f"{name} failed ({rc}): {msg.decode() if msg else ''}")
+
+
+def set_option(name: str, value: int) -> int:
+    """Set a tuning option of the library (include/hologan_b200.h: hg_set_option); returns the previous value."""
+    lib = load()
+    old = ctypes.c_int(0)
+    if lib.hg_get_option(name.encode(), ctypes.byref(old)) != 0 or lib.hg_set_option(name.encode(), int(value)) != 0:
+        raise HologanB200Error(lib.hg_last_error().decode())
+    return old.value
+
+
+def get_option(name: str) -> int:
+    lib = load()
+    v = ctypes.c_int(0)
+    if lib.hg_get_option(name.encode(), ctypes.byref(v)) != 0:
+        raise HologanB200Error(lib.hg_last_error().decode())
+    return v.value

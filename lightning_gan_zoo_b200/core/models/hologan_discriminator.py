@@ -1,10 +1,11 @@
 """HoloGAN discriminator -- interface mirror of the reference's
 `core.models.hologan_discriminator` (core/models/hologan_discriminator.py:7-78).
 
-The discriminator is in the training-step metric but NOT in the custom-kernel list of the hot
-path: it runs on stock PyTorch modules (cuDNN) for now and keeps the
-reference's `state_dict` keys, including the `conv2d_spec_norm` alias of each spectrally
-normalised convolution.  `img_size=128` uses the patched head sizes.
+The discriminator is in the training-step metric.  Under bf16 autocast on CUDA with the
+reference's widths it runs entirely on the kernels of libhologan_b200.so (`_forward_b200`); the fp32 parity path
+and unsupported shapes use stock PyTorch modules.  The reference's `state_dict` keys are kept, including the
+`conv2d_spec_norm` alias of each spectrally normalised convolution.  `img_size=128` uses the patched head sizes
+(SURVEY.md R4).
 """
 from __future__ import annotations
 
@@ -86,32 +87,38 @@ class Discriminator(nn.Module):
             h = ops.instance_norm_act_channels_last(h.permute(0, 2, 3, 1), 0.2, blk.instance_norm.eps).permute(0, 3, 1, 2)
         return h
 
-    def _blocks_tcgen05(self, h):
-        """The same three blocks with the convolutions on the tcgen05 tap GEMMs (`ops.conv5x5_s2`: Conv2d(k5, s2, p2) as
-        the dgrad of the dual transposed convolution on a space-to-depth input) instead of cuDNN.  Opt-in
-        (HG_D_TCGEN05=1) until it has been measured on a B200; needs contiguous (not channels_last) weights, because the
-        weight pack reads the torch layout."""
+    def _forward_b200(self, x):
+        """The whole discriminator of the bf16 pipeline on hand-written kernels: first convolution +
+        LeakyReLU on warp-level tensor cores writing the space-to-depth operand of block 0 directly, the three
+        spectral-norm convolutions on the tcgen05 tap GEMMs (1 / sigma folded into the bf16 weight pack, K split over
+        taps), InstanceNorm + LeakyReLU storing the next block's space-to-depth operand, and both heads in one pass.
+        No cuDNN / cuBLAS kernel runs.  The convolution biases of the blocks are not applied: the InstanceNorm that
+        follows removes any per-channel constant (their gradient is identically zero)."""
+        h = ops.dconv0(x, self.conv2d.weight, self.conv2d.bias, 0.2)                  # (B, S/4, S/4, 4, 64)
         convs = [blk.conv2d for blk in self.blocks]
-        ws = ops.spectral_norm_weights([c.weight_orig for c in convs], [c.weight_u for c in convs],
-                                       [c.weight_v for c in convs], power_iteration=self.training,
-                                       out_dtype=torch.float32)
-        h = h.permute(0, 2, 3, 1)                                                     # logical NCHW on NHWC memory -> (B, H, W, C)
-        for blk, w in zip(self.blocks, ws):
-            y = ops.conv5x5_s2(ops.nhwc_to_s2d(h.contiguous()), w)                    # (B, H/2, W/2, Cout)
-            h = ops.instance_norm_act_channels_last(y, 0.2, blk.instance_norm.eps)
-        return h.permute(0, 3, 1, 2)
+        states = ops.spectral_norm_sigma([c.weight_orig for c in convs], [c.weight_u for c in convs],
+                                         [c.weight_v for c in convs], power_iteration=self.training)
+        for i, (blk, st) in enumerate(zip(self.blocks, states)):
+            y = ops.conv5s2_sn(h, blk.conv2d.weight_orig, st)                         # (B, S', S', Cout)
+            h = ops.instance_norm_act_channels_last(y, 0.2, blk.instance_norm.eps, s2d_out=i + 1 < len(self.blocks))
+        return ops.dheads(h, self.linear1.weight, self.linear1.bias, self.linear2.weight, self.linear2.bias,
+                          self.linear3.weight, self.linear3.bias, 0.2)
 
-    def _tcgen05_ok(self, x):
+    def _b200_ok(self, x):
         import os
-        if os.environ.get("HG_D_TCGEN05", "0") in ("", "0"):
+        if os.environ.get("HG_D_LIBRARY", "0") not in ("", "0"):                      # A/B switch: the cuDNN / cuBLAS pipeline
             return False
-        side = x.shape[-1] // 2                                                       # spatial extent entering the first block
+        if x.dim() != 4 or x.shape[-1] != x.shape[-2] or not ops.dconv0_supported(x.shape[1], self.conv2d.weight.shape[0], x.shape[-1]):
+            return False
+        side = x.shape[-1] // 2
         for blk in self.blocks:
             w = blk.conv2d.weight_orig
             side //= 2
-            if not (w.is_contiguous() and ops.conv5x5_s2_supported(w.shape[1], w.shape[0], side, x.shape[0])):
+            if not (w.is_contiguous() and ops.conv5s2_supported(w.shape[1], w.shape[0], side)):
                 return False
-        return True
+        c = self.blocks[-1].conv2d.weight_orig.shape[0]
+        return (ops.dheads_supported(x.shape[0], c, side * side) and self.linear2.weight.shape[0] == 128
+                and self.linear3.weight.shape[1] == 128 and self.linear1.weight.shape[1] == c * side * side)
 
     def _bf16_pipeline_ok(self, x):
         if not (x.is_cuda and torch.is_autocast_enabled() and torch.get_autocast_dtype("cuda") == torch.bfloat16):
@@ -123,12 +130,12 @@ class Discriminator(nn.Module):
 
     def forward(self, x):
         bf16 = x.is_cuda and torch.is_autocast_enabled() and torch.get_autocast_dtype("cuda") == torch.bfloat16
+        if bf16 and self._b200_ok(x):
+            return self._forward_b200(x)
         if bf16:
             x = x.contiguous(memory_format=torch.channels_last)      # NHWC pipeline (3 MB at B = 64)
         h = F.leaky_relu(self.conv2d(x), 0.2)
-        if bf16 and self._tcgen05_ok(x):
-            h = self._blocks_tcgen05(h).flatten(1)
-        elif bf16 and self._bf16_pipeline_ok(x):
+        if bf16 and self._bf16_pipeline_ok(x):
             h = self._blocks_bf16(h).flatten(1)
         else:
             h = self.blocks(h).flatten(1)                             # logical (c, h, w) order, as the reference (:60)

@@ -27,7 +27,6 @@
 // distributed shared memory (cluster.map_shared_rank, fixed rank order -> deterministic), and the normalised rows
 // are produced from the staged copy: ONE kernel, x is read from HBM exactly once (forward: 1 read + 1 write, backward: 2 reads + 1 write = the algorithmic traffic).
 #include <cooperative_groups.h>
-#include <stdlib.h>
 
 #include "hg_common.cuh"
 
@@ -77,6 +76,9 @@ __device__ __forceinline__ int upsampled_row(int r, int ndim, int logS, int logP
     return ((2 * iz + pz) * S2 + 2 * iy + py) * S2 + 2 * ix + px;
 }
 
+struct ClGeom;
+__device__ __forceinline__ int mapped_row(int r, const ClGeom &g);
+
 __device__ __forceinline__ float modulate_cl(float x, float mean, float rstd, float s, float b)
 {
     return __fadd_rn(__fmul_rn(s, __fmul_rn(__fsub_rn(x, mean), rstd)), b);
@@ -84,11 +86,24 @@ __device__ __forceinline__ float modulate_cl(float x, float mean, float rstd, fl
 
 struct ClGeom {
     int C, N, Nvar, ndim, logS, logP;
+    int s2d_out;        // plain (S x S) rows in, 2x2 space-to-depth row order out (classes == -4, see hg_adain_cl_fwd)
     int lanes;          // C / 8 threads per row
     int rows_per_pass;  // kClThreads / lanes
     int chunk_rows;     // rows per CTA (multiple of rows_per_pass)
     int chunks;
 };
+
+// Row of the output tensor (forward) / of dy (backward) that belongs to input row r.  Normally the depth-to-space shuffle
+// of a transposed convolution's s2d output; with s2d_out the opposite direction: pixel (iy, ix) of a plain S x S map goes
+// to row ((iy/2) * S/2 + ix/2) * 4 + (iy%2) * 2 + ix%2, the layout hg_conv5s2_fwd reads (discriminator blocks).
+__device__ __forceinline__ int mapped_row(int r, const ClGeom &g)
+{
+    if (g.s2d_out) {
+        const int ix = r & ((1 << g.logS) - 1), iy = r >> g.logS;
+        return ((((iy >> 1) << (g.logS - 1)) + (ix >> 1)) << 2) + ((iy & 1) << 1) + (ix & 1);
+    }
+    return upsampled_row(r, g.ndim, g.logS, g.logP);
+}
 
 // Sum the two 8-float partials of all row slots of the CTA in a fixed order; result valid for every thread.
 // Row slots that share a warp (lanes < 32) are folded with xor-shuffles first, the remaining <= 8 groups go
@@ -177,7 +192,7 @@ __device__ __forceinline__ void fwd_apply(const __nv_bfloat16 *__restrict__ xb, 
                     const float p = modulate_cl(f[j], mean[j], rstd[j], s[j], bb[j]);
                     f[j] = p > 0.f ? p : p * slope;
                 }
-                st_stream_16(yb + (size_t)upsampled_row(rr, g.ndim, g.logS, g.logP) * g.C, pack8(f));
+                st_stream_16(yb + (size_t)mapped_row(rr, g) * g.C, pack8(f));
             }
         }
     }
@@ -314,7 +329,7 @@ __device__ __forceinline__ void bwd_accumulate(const __nv_bfloat16 *__restrict__
             const int rr = r + u * g.rows_per_pass;
             if (rr < r1) {
                 xr[u] = __ldg(reinterpret_cast<const uint4 *>(xb + (size_t)rr * g.C));
-                gr[u] = __ldg(reinterpret_cast<const uint4 *>(gb + (size_t)upsampled_row(rr, g.ndim, g.logS, g.logP) * g.C));
+                gr[u] = __ldg(reinterpret_cast<const uint4 *>(gb + (size_t)mapped_row(rr, g) * g.C));
             }
         }
 #pragma unroll
@@ -346,7 +361,7 @@ __device__ __forceinline__ void bwd_apply(const __nv_bfloat16 *__restrict__ xb, 
             const int rr = r + u * g.rows_per_pass;
             if (rr < r1) {
                 xr[u] = __ldg(reinterpret_cast<const uint4 *>(xb + (size_t)rr * g.C));
-                gr[u] = __ldg(reinterpret_cast<const uint4 *>(gb + (size_t)upsampled_row(rr, g.ndim, g.logS, g.logP) * g.C));
+                gr[u] = __ldg(reinterpret_cast<const uint4 *>(gb + (size_t)mapped_row(rr, g) * g.C));
             }
         }
 #pragma unroll
@@ -563,7 +578,7 @@ __global__ void __launch_bounds__(kClThreads, 2) adain_cl_cluster_fwd_kernel(con
             const float p = fmaf(f[j], a[j], c[j]);
             f[j] = p > 0.f ? p : p * slope;
         }
-        st_stream_16(yb + (size_t)upsampled_row(r0 + u * g.rows_per_pass, g.ndim, g.logS, g.logP) * g.C, pack8(f));
+        st_stream_16(yb + (size_t)mapped_row(r0 + u * g.rows_per_pass, g) * g.C, pack8(f));
     }
     cluster.sync();                                                     // cpart stays alive until every peer has read it
 }
@@ -588,7 +603,7 @@ __global__ void __launch_bounds__(kClBwdClusterThreads, 1) adain_cl_cluster_bwd_
     for (int u = 0; u < U; ++u) {
         const int rr = r0 + u * g.rows_per_pass;
         cp_async_16(xt + u * NT, x + base + (size_t)rr * g.C);
-        cp_async_16(gt + u * NT, dy + base + (size_t)upsampled_row(rr, g.ndim, g.logS, g.logP) * g.C);
+        cp_async_16(gt + u * NT, dy + base + (size_t)mapped_row(rr, g) * g.C);
     }
     // phase 1 constants: a, c (the forward's pre-activation x * a + c -> activation mask) and the mean
     float a[8], c[8], mean[8];
@@ -659,6 +674,12 @@ using namespace hg;
 
 static int cl_geom(const char *who, int batch, int channels, int ndim, int size, int classes, int biased_var, ClGeom &g)
 {
+    g.s2d_out = 0;
+    if (classes == -4) {        // plain channels-last input, space-to-depth output order (2-D, even size)
+        HG_REQUIRE(ndim == 2 && size >= 2, HG_ERR_UNSUPPORTED, "%s: classes == -4 (s2d output) needs ndim 2 and size >= 2", who);
+        g.s2d_out = 1;
+        classes = 1;
+    }
     HG_REQUIRE(batch > 0 && channels > 0 && size > 0 && classes > 0, HG_ERR_INVALID_ARG, "%s: dims must be positive", who);
     HG_REQUIRE(batch <= 65535, HG_ERR_UNSUPPORTED, "%s: batch > 65535", who);
     HG_REQUIRE(ndim == 2 || ndim == 3, HG_ERR_INVALID_ARG, "%s: ndim must be 2 or 3", who);
@@ -698,8 +719,7 @@ static int cl_geom(const char *who, int batch, int channels, int ndim, int size,
 // HG_ADAIN_CL_NO_CLUSTER is set (A/B runs and tests of the chunked kernels) -> the chunked two-kernel path takes it.
 static bool cl_cluster_plan(const ClGeom &g, int threads, int max_u, bool backward, ClGeom &cg_out, int &cs_out, int &u_out)
 {
-    const char *off = getenv("HG_ADAIN_CL_NO_CLUSTER");
-    if (off && off[0] && off[0] != '0') return false;
+    if (option(kOptAdainClNoCluster)) return false;
     if (g.C > kClClusterMaxC || g.lanes > threads) return false;
     // Measured on B200 (profiles/r01g_microbench_pipeline.txt): a cluster launch has a ~6 us floor per wave, so the
     // forward only wins for the generator's 512 KB instances (24 us vs 32 us); the backward (two staged tensors ->
@@ -707,8 +727,7 @@ static bool cl_cluster_plan(const ClGeom &g, int threads, int max_u, bool backwa
     // opt-in (HG_ADAIN_CL_CLUSTER_BWD=1: tests, experiments).
     if ((long long)g.N * g.C * 2 < 256 * 1024) return false;
     if (backward) {
-        const char *on = getenv("HG_ADAIN_CL_CLUSTER_BWD");
-        if (!(on && on[0] && on[0] != '0')) return false;
+        if (!option(kOptAdainClClusterBwd)) return false;
     }
     const int rpp = threads / g.lanes;
     if (g.N % rpp) return false;

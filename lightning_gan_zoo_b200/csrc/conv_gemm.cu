@@ -15,7 +15,6 @@
 // three instances of one warp-specialised pipeline:  TMA producer warp -> 128B-swizzled smem ring ->
 // single-thread tcgen05.mma issue (fp32 accumulators in TMEM) -> 4 epilogue warps (tcgen05.ld).
 #include <cuda.h>
-#include <cstdlib>
 
 #include "hg_common.cuh"
 #include "sm100_ptx.cuh"
@@ -27,7 +26,7 @@ constexpr int kBK = 64;               // bf16 elements per 128-byte swizzle row
 constexpr int kThreads = 192;         // warp 0: TMA, warp 1: TMEM alloc + MMA, warps 2-5: epilogue
 constexpr int kMaxStages = 8;
 constexpr int kMaxTaps = 32;
-constexpr int kMaxGroups = 8;
+constexpr int kMaxGroups = 16;
 constexpr int kSmemBudget = 200 * 1024;
 constexpr int kDualSmemBudget = 100 * 1024;       // "dual" launches: two tap-GEMM CTAs per SM (<= 256 TMEM columns each)
 constexpr long long kDualMaxBytes = 2ll << 20;    // ... chosen when a CTA streams at most this many operand bytes
@@ -42,7 +41,7 @@ struct Tap {
 struct Group {
     int32_t tap_begin, tap_count;
     int32_t out_col_off;  // column offset of this group's output (parity class) in the output row
-    int32_t pad;
+    int32_t part;         // split-K: which fp32 partial buffer this group writes (TapGemmParams::partial)
 };
 
 enum EpilogueMode { kEpiBf16 = 0, kEpiF32Atomic = 1 };
@@ -61,6 +60,13 @@ struct TapGemmParams {
     void *out;
     const float *bias;    // per output column (without group offset) or null
     float slope;          // act(v) = v > 0 ? v : slope * v   (1 = identity)
+    // split-K over taps (small-M layers: the discriminator's convolutions): non-null -> the epilogue stores raw fp32
+    // accumulators to partial + group.part * partial_stride + m * ld_out + col (plain stores, no bias / activation);
+    // splitk_reduce_kernel sums the partials of every column block in a fixed order and writes the bf16 result
+    float *partial;
+    long long partial_stride;
+    const float *out_scale;     // device scalar (may be null): accumulators are multiplied by it before bias / activation
+                                // (1 / sigma of the spectral norm: conv(x, W / sigma) = conv(x, W) / sigma)
     int num_groups;
     Group groups[kMaxGroups];
     Tap taps[kMaxTaps];
@@ -83,24 +89,6 @@ struct WgradParams {
         int32_t dy_c_off;     // cls * Cout
         int32_t tap_flat;     // slice index in dw
     } pairs[kMaxTaps];
-};
-
-// Grouped wgrad (opt-in, HG_WGRAD_GROUP=1): pairs that read the SAME shifted X box are served by one CTA -- the box
-// is loaded once and multiplied against the dY column blocks of all (<= kWgMaxCols) parity classes that use this shift,
-// one BN-wide accumulator block each (N = ncols * BN <= 256 TMEM columns).
-constexpr int kWgMaxCols = 4;
-struct WgradGroupParams {
-    CUtensorMap tmX, tmDY;
-    int X, Y, Z, Bn;
-    int BN;               // Cout tile of one class (== Cout here: one N tile per class)
-    int stages, pos_tiles, splits, cin, cout, num_taps_total;
-    float *dw;            // split-K partials, fp32 [split][tap][Cin][Cout]
-    int num_groups;
-    struct Grp {
-        int16_t sx, sy, sz, ncols;
-        int32_t dy_c_off[kWgMaxCols];     // cls * Cout of every column block
-        int32_t tap_flat[kWgMaxCols];     // slice index in dw of every column block
-    } groups[kMaxTaps];
 };
 
 struct SharedCtl {
@@ -213,6 +201,8 @@ __global__ void __launch_bounds__(kThreads, 1) tap_gemm_kernel(const __grid_cons
         const long long m = (long long)blockIdx.x * kBM + row;
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
         __nv_bfloat16 *orow = static_cast<__nv_bfloat16 *>(p.out) + m * p.ld_out + grp.out_col_off + n0;
+        float *prow = p.partial ? p.partial + (size_t)grp.part * p.partial_stride + m * p.ld_out + grp.out_col_off + n0 : nullptr;
+        const float oscale = (p.out_scale && !prow) ? __ldg(p.out_scale) : 1.f;
         for (int c0 = 0; c0 < p.epi_cols; c0 += 32) {
             float v[32];
             if (c0 + 32 <= p.epi_cols) {
@@ -223,13 +213,23 @@ __global__ void __launch_bounds__(kThreads, 1) tap_gemm_kernel(const __grid_cons
 #pragma unroll
                 for (int j = 0; j < 16; ++j) { v[j] = t[j]; v[16 + j] = 0.f; }
             }
+            if (prow) {                                 // split-K partial: raw fp32 accumulators
+                if (m < p.m_total) {
+                    const int nvec = min(32, p.epi_cols - c0) / 4;
+                    float4 *dst = reinterpret_cast<float4 *>(prow + c0);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        if (j < nvec) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                }
+                continue;
+            }
             if (m < p.m_total) {
                 const int ncol = min(32, p.epi_cols - c0);
                 const int bcol = (n0 + c0) % p.bias_mod;      // bias_mod is a multiple of 16 and of ncol's run
                 uint32_t packed[16];
 #pragma unroll
                 for (int j = 0; j < 32; j += 2) {
-                    float a = v[j], b = v[j + 1];
+                    float a = v[j] * oscale, b = v[j + 1] * oscale;
                     if (p.bias && j < ncol) {
                         a += __ldg(p.bias + (bcol + j) % p.bias_mod);
                         b += __ldg(p.bias + (bcol + j + 1) % p.bias_mod);
@@ -252,6 +252,43 @@ __global__ void __launch_bounds__(kThreads, 1) tap_gemm_kernel(const __grid_cons
     ptx::tc_fence_before();
     __syncthreads();
     if (warp == 1) ptx::tmem_dealloc(tmem_base, tmem_cols_for(p.epi_cols));
+}
+
+// Sum of the split-K partials written by tap_gemm_kernel: out[m][col] = bf16(sum_{s < nsplit[col / block_cols]}
+// partial[s][m][col]), fixed order.  One thread per 8 consecutive columns.
+struct SplitReduceParams {
+    const float *partial;
+    const float *scale;                 // device scalar (may be null) applied to the sum
+    __nv_bfloat16 *out;
+    long long partial_stride, vecs;     // vecs = rows * ld / 8
+    int ld, block_cols;
+    int nsplit[kMaxGroups];
+};
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const SplitReduceParams p)
+{
+    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (i >= p.vecs) return;
+    const int col = (int)((i * 8) % p.ld);
+    const int n = p.nsplit[col / p.block_cols];
+    const float4 *src = reinterpret_cast<const float4 *>(p.partial + i * 8);
+    float4 a = src[0], b = src[1];
+    for (int s = 1; s < n; ++s) {
+        const float4 *q = reinterpret_cast<const float4 *>(p.partial + (size_t)s * p.partial_stride + i * 8);
+        const float4 c = q[0], d = q[1];
+        a.x += c.x; a.y += c.y; a.z += c.z; a.w += c.w;
+        b.x += d.x; b.y += d.y; b.z += d.z; b.w += d.w;
+    }
+    if (p.scale) {
+        const float sc = __ldg(p.scale);
+        a.x *= sc; a.y *= sc; a.z *= sc; a.w *= sc;
+        b.x *= sc; b.y *= sc; b.z *= sc; b.w *= sc;
+    }
+    __nv_bfloat162 h0 = __floats2bfloat162_rn(a.x, a.y), h1 = __floats2bfloat162_rn(a.z, a.w);
+    __nv_bfloat162 h2 = __floats2bfloat162_rn(b.x, b.y), h3 = __floats2bfloat162_rn(b.z, b.w);
+    uint4 o;
+    o.x = *reinterpret_cast<uint32_t *>(&h0); o.y = *reinterpret_cast<uint32_t *>(&h1);
+    o.z = *reinterpret_cast<uint32_t *>(&h2); o.w = *reinterpret_cast<uint32_t *>(&h3);
+    *reinterpret_cast<uint4 *>(p.out + i * 8) = o;
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -366,125 +403,6 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_gemm_kernel(const __grid_co
 }
 
 // -------------------------------------------------------------------------------------------------
-// Grouped wgrad kernel: wgrad_gemm_kernel with several dY column blocks per CTA (see WgradGroupParams).  Not yet run on a
-// B200: selected only by HG_WGRAD_GROUP=1, the default path above is untouched.
-// grid = (Cin/128, 1, groups * splits)
-// -------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads, 1) wgrad_gemm_grouped_kernel(const __grid_constant__ WgradGroupParams p)
-{
-    extern __shared__ uint8_t smem_raw[];
-    __shared__ SharedCtl ctl;
-    uint8_t *tiles = align_1024(smem_raw);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int BN = p.BN;
-    constexpr int kPos = 64;
-    const uint32_t box_bytes = kPos * 128;
-    const int grp_idx = blockIdx.z / p.splits, split = blockIdx.z % p.splits;
-    const WgradGroupParams::Grp gr = p.groups[grp_idx];
-    const int ncols = gr.ncols, ntot = ncols * BN;               // accumulator columns of this CTA
-    const uint32_t a_bytes = 2 * box_bytes, b_bytes = (uint32_t)(ntot / 64) * box_bytes, stage_bytes = a_bytes + b_bytes;
-    const int ci0 = blockIdx.x * kBM;
-    const int per = (p.pos_tiles + p.splits - 1) / p.splits;
-    const int t_begin = split * per, t_end = min(p.pos_tiles, t_begin + per);
-    const int total_iters = max(0, t_end - t_begin);
-
-    if (warp == 0 && ptx::elect_one()) {
-        ptx::prefetch_tensormap(&p.tmX);
-        ptx::prefetch_tensormap(&p.tmDY);
-        for (int s = 0; s < p.stages; ++s) {
-            ptx::mbar_init(&ctl.full[s], 1);
-            ptx::mbar_init(&ctl.empty[s], 1);
-        }
-        ptx::mbar_init(&ctl.acc_ready, 1);
-        ptx::fence_barrier_init();
-    }
-    if (warp == 1) {
-        ptx::tmem_alloc(&ctl.tmem_base, tmem_cols_for(ntot));
-        ptx::tmem_relinquish();
-    }
-    ptx::tc_fence_before();
-    __syncthreads();
-    ptx::tc_fence_after();
-    const uint32_t tmem_base = ctl.tmem_base;
-
-    if (total_iters == 0 && warp >= 2) {                       // empty K range: this split's partial tiles are all zero
-        const int row = (warp & 3) * 32 + lane;
-        if (ci0 + row < p.cin) {
-            for (int jc = 0; jc < ncols; ++jc) {
-                float *orow = p.dw + (((size_t)split * p.num_taps_total + gr.tap_flat[jc]) * p.cin + ci0 + row) * p.cout;
-                for (int c = 0; c < BN; c += 4) *reinterpret_cast<float4 *>(orow + c) = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-        }
-    }
-    if (total_iters > 0) {
-        if (warp == 0) {
-            if (ptx::elect_one()) {
-                for (int it = 0; it < total_iters; ++it) {
-                    long long pos = (long long)(t_begin + it) * kPos;
-                    const int x0 = (int)(pos % p.X); pos /= p.X;
-                    const int y0 = (int)(pos % p.Y); pos /= p.Y;
-                    const int z0 = (int)(pos % p.Z);
-                    const int b0 = (int)(pos / p.Z);
-                    const int s = it % p.stages;
-                    const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
-                    ptx::mbar_wait(&ctl.empty[s], ph ^ 1u);
-                    uint8_t *dst = tiles + (size_t)s * stage_bytes;
-                    ptx::mbar_arrive_expect_tx(&ctl.full[s], stage_bytes);
-                    for (int j = 0; j < 2; ++j)
-                        ptx::tma_load_5d(dst + j * box_bytes, &p.tmX, &ctl.full[s], ci0 + j * 64, x0 + gr.sx, y0 + gr.sy,
-                                         z0 + gr.sz, b0);
-                    int box = 0;
-                    for (int jc = 0; jc < ncols; ++jc)
-                        for (int j = 0; j < BN / 64; ++j, ++box)
-                            ptx::tma_load_5d(dst + a_bytes + box * box_bytes, &p.tmDY, &ctl.full[s], gr.dy_c_off[jc] + j * 64, x0, y0,
-                                             z0, b0);
-                }
-            }
-        } else if (warp == 1) {
-            if (ptx::elect_one()) {
-                const uint32_t idesc = ptx::idesc_bf16(kBM, ntot, true, true);
-                for (int it = 0; it < total_iters; ++it) {
-                    const int s = it % p.stages;
-                    const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
-                    ptx::mbar_wait(&ctl.full[s], ph);
-                    ptx::tc_fence_after();
-                    const uint32_t a_addr = ptx::smem_u32(tiles + (size_t)s * stage_bytes);
-                    const uint64_t a_desc = ptx::smem_desc_sw128(a_addr, box_bytes, 1024);
-                    const uint64_t b_desc = ptx::smem_desc_sw128(a_addr + a_bytes, box_bytes, 1024);
-#pragma unroll
-                    for (int k = 0; k < kPos / 16; ++k)
-                        ptx::umma_bf16(tmem_base, a_desc + (uint64_t)(k * 128), b_desc + (uint64_t)(k * 128), idesc,
-                                       (it | k) != 0);
-                    ptx::umma_commit(&ctl.empty[s]);
-                }
-                ptx::umma_commit(&ctl.acc_ready);
-            }
-        } else {
-            ptx::mbar_wait(&ctl.acc_ready, 0);
-            ptx::tc_fence_after();
-            const int quad = warp & 3;
-            const int row = quad * 32 + lane;
-            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
-            for (int jc = 0; jc < ncols; ++jc) {
-                float *orow = p.dw + (((size_t)split * p.num_taps_total + gr.tap_flat[jc]) * p.cin + ci0 + row) * p.cout;
-                for (int c0 = 0; c0 < BN; c0 += 16) {
-                    float v[16];
-                    ptx::tmem_ld_16(taddr + (uint32_t)(jc * BN + c0), v);
-                    if (ci0 + row < p.cin) {
-                        float4 *dst = reinterpret_cast<float4 *>(orow + c0);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                    }
-                }
-            }
-        }
-    }
-    ptx::tc_fence_before();
-    __syncthreads();
-    if (warp == 1) ptx::tmem_dealloc(tmem_base, tmem_cols_for(ntot));
-}
-
-// -------------------------------------------------------------------------------------------------
 // Weight packing: torch ConvTranspose layout (Cin, Cout, k^d) fp32  <->  GEMM operand layouts
 // -------------------------------------------------------------------------------------------------
 // Channel permutation of the projection operand (HG_PROJ): GEMM K index k' = y*C + c pairs with the
@@ -509,21 +427,28 @@ __host__ __device__ inline int brick_row_pitch(int taps) { return kBrickCo * bri
 // w_dgrad[t][ci][co] (rows = Cin, K = Cout), bf16, written as bf16x2 pairs.  T is a template parameter (1, 16,
 // 27 on the hot path) so the index arithmetic has no runtime divisions; global reads are float4 with four
 // independent loads in flight per thread.
+// `divisor` (device pointer, may be null): every weight is divided by *divisor first -- the spectral norm sigma of the
+// discriminator's convolutions (W / sigma, core/models/hologan_discriminator.py:15), so no normalised fp32 copy exists.
 template <int T>
 __global__ void __launch_bounds__(256) pack_weight_kernel(const float *__restrict__ w, __nv_bfloat16 *__restrict__ w_fwd,
                                                           __nv_bfloat16 *__restrict__ w_dgrad, int cin, int cout, int perm_c,
-                                                          int perm_s)
+                                                          int perm_s, const float *__restrict__ divisor)
 {
     extern __shared__ float brick[];                    // [kBrickCi][kBrickCo][tpitch] (+1 pad per ci row)
     constexpr int row_len = kBrickCo * T, tp = T | 1, pitch = kBrickCo * tp + 1, vec_per_row = row_len / 4;
     const int ci0 = blockIdx.x * kBrickCi, co0 = blockIdx.y * kBrickCo;
+    const float div = divisor ? __ldg(divisor) : 1.f;
 #pragma unroll 4
     for (int i = threadIdx.x; i < kBrickCi * vec_per_row; i += 256) {
         const int r = i / vec_per_row, c = (i - r * vec_per_row) * 4;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (ci0 + r < cin)      // cout % kBrickCo == 0 (checked on the host): the whole row is in range
             v = __ldg(reinterpret_cast<const float4 *>(w + ((size_t)torch_cin(ci0 + r, perm_c, perm_s) * cout + co0) * T + c));
-        const float e[4] = {v.x, v.y, v.z, v.w};
+        float e[4] = {v.x, v.y, v.z, v.w};
+        if (divisor) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) e[j] = __fdiv_rn(e[j], div);
+        }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int co = (c + j) / T, t = (c + j) - co * T;
@@ -556,12 +481,16 @@ __global__ void __launch_bounds__(256) pack_weight_kernel(const float *__restric
 // Sum the split-K partials [split][t][ci][co] and write the torch layout (Cin, Cout, T) fp32.  A thread reads
 // float4 (4 co) of one (t, ci) row for every split, two rows in flight; writes are float4 runs of the torch
 // rows.  accumulate != 0: dw += result (lets the caller target a live .grad buffer).  Fixed summation order.
-template <int T>
+// BCI = input channels per brick: 16 normally, 2 for small weights (a grid of Cin/16 x Cout/32 bricks would leave most
+// SMs idle and serialise `splits` dependent load rounds in a handful of CTAs: 16 CTAs x 11 splits took ~25 us for the
+// discriminator's first block, profiles/r02b_profile_d_tcgen05.txt).
+template <int T, int BCI>
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float *__restrict__ partial, float *__restrict__ dw, int cin,
                                                            int cout, int splits, int perm_c, int perm_s, int accumulate)
 {
     extern __shared__ float brick[];
     constexpr int row_len = kBrickCo * T, tp = T | 1, pitch = kBrickCo * tp + 1, vec_per_row = row_len / 4;
+    constexpr int kBrickCi = BCI;
     const int ci0 = blockIdx.x * kBrickCi, co0 = blockIdx.y * kBrickCo;
     const size_t split_stride = (size_t)T * cin * cout;
 #pragma unroll 2
@@ -760,12 +689,8 @@ static void for_each_class_tap(const ConvShape &c, Fn fn)
 // accumulator columns.  "dual": two co-resident CTAs per SM (kDualSmemBudget each, <= 256 columns each), so that a
 // CTA's prologue (tensor-map fetch, first TMA round trip) and epilogue (TMEM drain + stores) overlap its
 // neighbour's main loop -- the ~11 k cycles of fixed cost per CTA are half the life of a CTA on the narrow layers
-// (profiles/r01c_ncu_full_summary.txt).  HG_TAPGEMM_DUAL=0/1 overrides the choice (tuning only; read per call).
-static int dual_override()
-{
-    const char *e = getenv("HG_TAPGEMM_DUAL");
-    return e ? (e[0] == '1' ? 1 : 0) : -1;
-}
+// (profiles/r01c_ncu_full_summary.txt).  Option TAPGEMM_DUAL = 0 / 1 overrides the choice (tuning only).
+static int dual_override() { return option(kOptTapGemmDual); }
 static bool want_dual(int stage_bytes, int iters_per_cta, int epi_cols)
 {
     if (epi_cols > 256 || 2 * stage_bytes + 1024 > kDualSmemBudget) return false;
@@ -798,6 +723,38 @@ static int pick_bn_for_grid(int n, int m_tiles)
     int bn = pick_bn(n);
     while (bn > 64 && 4ll * m_tiles * (n / bn) < 3ll * sm_count()) bn /= 2;
     return bn;
+}
+
+template <int T, int BCI>
+static void launch_wgrad_reduce_t(const float *part, float *dw, int cin, int cout, int splits, int perm_c, int perm_s,
+                                  int accumulate, cudaStream_t st)
+{
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(wgrad_reduce_kernel<T, BCI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        attr_set = true;
+    }
+    dim3 grid((cin + BCI - 1) / BCI, (cout + kBrickCo - 1) / kBrickCo);
+    const size_t smem = (size_t)BCI * brick_row_pitch(T) * sizeof(float);
+    wgrad_reduce_kernel<T, BCI><<<grid, 256, smem, st>>>(part, dw, cin, cout, splits, perm_c, perm_s, accumulate);
+}
+
+static int launch_wgrad_reduce(const float *part, float *dw, int cin, int cout, int taps, int splits, int perm_c, int perm_s,
+                               int accumulate, cudaStream_t st)
+{
+    // enough bricks to cover the SMs: small weights use 2-channel bricks
+    const bool small = (long long)((cin + 15) / 16) * ((cout + kBrickCo - 1) / kBrickCo) < sm_count();
+#define HG_REDUCE(T)                                                                                         \
+    do {                                                                                                     \
+        if (small) launch_wgrad_reduce_t<T, 2>(part, dw, cin, cout, splits, perm_c, perm_s, accumulate, st);  \
+        else launch_wgrad_reduce_t<T, 16>(part, dw, cin, cout, splits, perm_c, perm_s, accumulate, st);       \
+    } while (0)
+    if (taps == 1) HG_REDUCE(1);
+    else if (taps == 16) HG_REDUCE(16);
+    else if (taps == 25) HG_REDUCE(25);
+    else HG_REDUCE(27);
+#undef HG_REDUCE
+    return check_launch("hg_convt_wgrad(reduce)");
 }
 
 }  // namespace hg
@@ -834,8 +791,17 @@ static int perm_ok(const char *who, int cin, int perm_c, int perm_s)
     return HG_OK;
 }
 
+static int pack_weight_impl(const float *w, void *w_fwd, void *w_dgrad, int cin, int cout, int taps, int perm_c, int perm_s,
+                            const float *divisor, void *stream);
+
 extern "C" int hg_convt_pack_weight(const float *w, void *w_fwd, void *w_dgrad, int cin, int cout, int taps, int perm_c,
                                     int perm_s, void *stream)
+{
+    return pack_weight_impl(w, w_fwd, w_dgrad, cin, cout, taps, perm_c, perm_s, nullptr, stream);
+}
+
+static int pack_weight_impl(const float *w, void *w_fwd, void *w_dgrad, int cin, int cout, int taps, int perm_c, int perm_s,
+                            const float *divisor, void *stream)
 {
     HG_REQUIRE(w && (w_fwd || w_dgrad), HG_ERR_INVALID_ARG, "hg_convt_pack_weight: null pointer");
     HG_REQUIRE(cin > 0 && cout > 0 && taps > 0 && taps <= 27, HG_ERR_INVALID_ARG, "hg_convt_pack_weight: bad dims");
@@ -855,15 +821,24 @@ extern "C" int hg_convt_pack_weight(const float *w, void *w_fwd, void *w_dgrad, 
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     __nv_bfloat16 *wf = static_cast<__nv_bfloat16 *>(w_fwd), *wd = static_cast<__nv_bfloat16 *>(w_dgrad);
-    if (taps == 1) pack_weight_kernel<1><<<grid, 256, smem, st>>>(w, wf, wd, cin, cout, perm_c, perm_s);
-    else if (taps == 16) pack_weight_kernel<16><<<grid, 256, smem, st>>>(w, wf, wd, cin, cout, perm_c, perm_s);
-    else if (taps == 25) pack_weight_kernel<25><<<grid, 256, smem, st>>>(w, wf, wd, cin, cout, perm_c, perm_s);
-    else pack_weight_kernel<27><<<grid, 256, smem, st>>>(w, wf, wd, cin, cout, perm_c, perm_s);
+    if (taps == 1) pack_weight_kernel<1><<<grid, 256, smem, st>>>(w, wf, wd, cin, cout, perm_c, perm_s, divisor);
+    else if (taps == 16) pack_weight_kernel<16><<<grid, 256, smem, st>>>(w, wf, wd, cin, cout, perm_c, perm_s, divisor);
+    else if (taps == 25) pack_weight_kernel<25><<<grid, 256, smem, st>>>(w, wf, wd, cin, cout, perm_c, perm_s, divisor);
+    else pack_weight_kernel<27><<<grid, 256, smem, st>>>(w, wf, wd, cin, cout, perm_c, perm_s, divisor);
     return check_launch("hg_convt_pack_weight");
 }
 
+static int convt_fwd_impl(const void *x, const void *w_fwd, const float *bias, const float *out_scale, void *y_s2d, int batch,
+                          int cin, int cout, int ndim, int size, int kernel, float neg_slope, void *stream);
+
 extern "C" int hg_convt_fwd(const void *x, const void *w_fwd, const float *bias, void *y_s2d, int batch, int cin, int cout,
                             int ndim, int size, int kernel, float neg_slope, void *stream)
+{
+    return convt_fwd_impl(x, w_fwd, bias, nullptr, y_s2d, batch, cin, cout, ndim, size, kernel, neg_slope, stream);
+}
+
+static int convt_fwd_impl(const void *x, const void *w_fwd, const float *bias, const float *out_scale, void *y_s2d, int batch,
+                          int cin, int cout, int ndim, int size, int kernel, float neg_slope, void *stream)
 {
     HG_REQUIRE(x && w_fwd && y_s2d, HG_ERR_INVALID_ARG, "hg_convt_fwd: null pointer");
     ConvShape c{batch, cin, cout, ndim, size, kernel};
@@ -882,6 +857,7 @@ extern "C" int hg_convt_fwd(const void *x, const void *w_fwd, const float *bias,
     p.BN = bn; p.k_chunks = cin / kBK; p.bias_mod = cout;
     const long long m_total = (long long)batch * c.X * c.Y * c.Z;
     p.m_total = (int)m_total; p.ld_out = (long long)c.P * cout; p.out = y_s2d; p.bias = bias; p.slope = neg_slope;
+    p.out_scale = out_scale;
     // Narrow layers (Cout <= 128 == one N tile): several parity classes share a CTA, one TMEM accumulator
     // each, so a CTA does classes_per_cta x the work per prologue/epilogue and writes one contiguous run of the
     // s2d output row.  Single launches may fill all 512 TMEM columns; dual launches (see want_dual) stop at 256,
@@ -1033,69 +1009,218 @@ extern "C" int hg_convt_wgrad(const void *x, const void *dy_s2d, float *dw, void
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(wgrad_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgradSmemBudget);
-        cudaFuncSetAttribute(wgrad_reduce_kernel<27>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-        cudaFuncSetAttribute(wgrad_reduce_kernel<25>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
         attr_set = true;
     }
-    const char *grp_env = getenv("HG_WGRAD_GROUP");
-    const bool grouped = grp_env && grp_env[0] && grp_env[0] != '0' && bn == cout && cout <= 128 && c.taps > 1;
-    if (grouped) {
-        // pairs with the same shift share one CTA (<= 256 accumulator columns); the partial buffer, the split-K plan
-        // and the reduce kernel are those of the default path
-        WgradGroupParams gp{};
-        gp.tmX = p.tmX; gp.tmDY = p.tmDY;
-        gp.X = p.X; gp.Y = p.Y; gp.Z = p.Z; gp.Bn = p.Bn; gp.BN = bn; gp.cin = cin; gp.cout = cout; gp.dw = p.dw;
-        gp.num_taps_total = c.taps; gp.pos_tiles = pl.pos_tiles;
-        const int max_cols = 256 / bn < kWgMaxCols ? 256 / bn : kWgMaxCols;
-        int ng = 0;
-        for (int i = 0; i < np; ++i) {
-            const WgradParams::Pair &pr = p.pairs[i];
-            int g = -1;
-            for (int k = 0; k < ng; ++k)
-                if (gp.groups[k].sx == pr.sx && gp.groups[k].sy == pr.sy && gp.groups[k].sz == pr.sz && gp.groups[k].ncols < max_cols) {
-                    g = k;
-                    break;
-                }
-            if (g < 0) {
-                g = ng++;
-                gp.groups[g].sx = pr.sx; gp.groups[g].sy = pr.sy; gp.groups[g].sz = pr.sz; gp.groups[g].ncols = 0;
-            }
-            WgradGroupParams::Grp &gr = gp.groups[g];
-            gr.dy_c_off[gr.ncols] = pr.dy_c_off;
-            gr.tap_flat[gr.ncols] = pr.tap_flat;
-            gr.ncols++;
-        }
-        gp.num_groups = ng;
-        // same number of resident CTAs as the default plan, now spread over fewer (fatter) output tiles
-        int gsplits = (2 * sm_count()) / ((cin / kBM) * ng);
-        if (gsplits > pl.pos_tiles / 8) gsplits = pl.pos_tiles / 8;
-        if (gsplits < 1) gsplits = 1;
-        if (gsplits > pl.splits) gsplits = pl.splits;            // the partial buffer was sized for pl.splits
-        gp.splits = gsplits;
-        const int gstage = 2 * 64 * 128 + max_cols * (bn / 64) * 64 * 128;
-        gp.stages = pick_stages(gstage, (gp.pos_tiles + gsplits - 1) / gsplits, kWgradSmemBudget);
-        const size_t gsmem = (size_t)gp.stages * gstage + 1024;
-        static bool gattr = false;
-        if (!gattr) {
-            cudaFuncSetAttribute(wgrad_gemm_grouped_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgradSmemBudget);
-            gattr = true;
-        }
-        wgrad_gemm_grouped_kernel<<<dim3(cin / kBM, 1, ng * gsplits), kThreads, gsmem, st>>>(gp);
-        rc = check_launch("hg_convt_wgrad(grouped)");
-        if (rc) return rc;
-        pl.splits = gsplits;                                     // the reduce below sums the splits that were written
-    } else {
-        dim3 grid(cin / kBM, cout / bn, np * pl.splits);
-        wgrad_gemm_kernel<<<grid, kThreads, smem, st>>>(p);
-        rc = check_launch("hg_convt_wgrad");
-        if (rc) return rc;
+    dim3 grid(cin / kBM, cout / bn, np * pl.splits);
+    wgrad_gemm_kernel<<<grid, kThreads, smem, st>>>(p);
+    rc = check_launch("hg_convt_wgrad");
+    if (rc) return rc;
+    return launch_wgrad_reduce(static_cast<const float *>(workspace), dw, cin, cout, c.taps, pl.splits, perm_c, perm_s, accumulate, st);
+}
+
+// -------------------------------------------------------------------------------------------------
+// The discriminator's Conv2d(k5, s2, p2) (reference core/models/hologan_discriminator.py:12) on the tap GEMMs.
+// On a space-to-depth copy of its input, x_s2d[b, i, j, (py, px), c] = x[b, c, 2i + py, 2j + px], every one of the
+// 25 kernel taps is a shift in {-1, 0, 1}^2 of one parity class -- the convolution is the dgrad of the dual
+// ConvTranspose2d(k5, s2, p2, op1), its dx that transposed convolution's forward, its dw the dual's wgrad.  These
+// layers have few output positions (B x 16^2 .. 4^2) and a long K (25 taps x Cin): the K loop is split over taps
+// across CTAs (fp32 partials + splitk_reduce_kernel) so that all SMs work on them.
+// -------------------------------------------------------------------------------------------------
+namespace hg {
+
+struct Conv5Plan {
+    int m_tiles, bn, n_tiles;
+    int nsplit[4];        // per parity class (dx) or [0] only (fwd)
+    int max_split;
+};
+
+static void conv5_fwd_plan(long long m_total, int cout, Conv5Plan &pl)
+{
+    pl.m_tiles = (int)((m_total + kBM - 1) / kBM);
+    int bn = pick_bn(cout);
+    if (bn == 256 && (long long)pl.m_tiles * (cout / 256) < 32) bn = 128;
+    pl.bn = bn;
+    pl.n_tiles = cout / bn;
+    const int tiles = pl.m_tiles * pl.n_tiles;
+    int ks = sm_count() / tiles;                        // never more CTAs than SMs: a second partial wave doubles the time
+    if (ks < 1) ks = 1;
+    if (ks > 12) ks = 12;
+    pl.nsplit[0] = pl.max_split = ks;
+}
+
+static void conv5_dx_plan(long long m_total, int cin, int cout, Conv5Plan &pl)
+{
+    pl.m_tiles = (int)((m_total + kBM - 1) / kBM);
+    int bn = pick_bn(cin);
+    if (bn > 128 && pl.m_tiles < 32) bn = 128;
+    pl.bn = bn;
+    pl.n_tiles = cin / bn;
+    const int taps_c[4] = {9, 6, 6, 4};                         // (py, px) = (0,0), (0,1), (1,0), (1,1): 3x3, 3x2, 2x3, 2x2
+    const int kc = cout / kBK;
+    const long long total = (long long)pl.m_tiles * pl.n_tiles * 25 * kc;
+    long long target = (total + sm_count() - 1) / sm_count();                       // iterations per CTA at one CTA per SM
+    if (target < 8) target = 8;
+    pl.max_split = 1;
+    for (int c = 0; c < 4; ++c) {
+        int sp = (int)((taps_c[c] * kc + target / 2) / target);
+        if (sp < 1) sp = 1;
+        if (sp > 4) sp = 4;
+        if (sp > taps_c[c]) sp = taps_c[c];
+        pl.nsplit[c] = sp;
     }
-    dim3 rgrid((cin + kBrickCi - 1) / kBrickCi, (cout + kBrickCo - 1) / kBrickCo);
-    const size_t rsmem = (size_t)kBrickCi * brick_row_pitch(c.taps) * sizeof(float);
-    const float *part = static_cast<const float *>(workspace);
-    if (c.taps == 1) wgrad_reduce_kernel<1><<<rgrid, 256, rsmem, st>>>(part, dw, cin, cout, pl.splits, perm_c, perm_s, accumulate);
-    else if (c.taps == 16) wgrad_reduce_kernel<16><<<rgrid, 256, rsmem, st>>>(part, dw, cin, cout, pl.splits, perm_c, perm_s, accumulate);
-    else if (c.taps == 25) wgrad_reduce_kernel<25><<<rgrid, 256, rsmem, st>>>(part, dw, cin, cout, pl.splits, perm_c, perm_s, accumulate);
-    else wgrad_reduce_kernel<27><<<rgrid, 256, rsmem, st>>>(part, dw, cin, cout, pl.splits, perm_c, perm_s, accumulate);
-    return check_launch("hg_convt_wgrad(reduce)");
+    // one wave: while the grid exceeds the SM count, undo the split of the class with the shortest runs
+    for (;;) {
+        int groups = 0, worst = -1;
+        for (int c = 0; c < 4; ++c) {
+            groups += pl.nsplit[c];
+            if (pl.nsplit[c] > 1 && (worst < 0 || taps_c[c] * pl.nsplit[worst] < taps_c[worst] * pl.nsplit[c])) worst = c;
+        }
+        if ((long long)pl.m_tiles * pl.n_tiles * groups <= sm_count() || worst < 0) break;
+        pl.nsplit[worst]--;
+    }
+    for (int c = 0; c < 4; ++c)
+        if (pl.nsplit[c] > pl.max_split) pl.max_split = pl.nsplit[c];
+}
+
+static int launch_splitk_reduce(const float *partial, void *out, long long rows, int ld, int block_cols, const int *nsplit,
+                                int nblocks, long long partial_stride, const float *scale, cudaStream_t st)
+{
+    SplitReduceParams rp{};
+    rp.partial = partial; rp.scale = scale; rp.out = static_cast<__nv_bfloat16 *>(out); rp.partial_stride = partial_stride;
+    rp.vecs = rows * ld / 8; rp.ld = ld; rp.block_cols = block_cols;
+    for (int i = 0; i < nblocks; ++i) rp.nsplit[i] = nsplit[i];
+    splitk_reduce_kernel<<<(unsigned)((rp.vecs + 255) / 256), 256, 0, st>>>(rp);
+    return check_launch("splitk_reduce");
+}
+
+}  // namespace hg
+
+static int conv5_shape(ConvShape &c, const char *who, int batch, int cin, int cout, int size_out)
+{
+    // the dual transposed convolution: Cin_T = Cout, Cout_T = Cin, input extent = size_out
+    c = ConvShape{batch, cout, cin, 2, size_out, 5};
+    return conv_shape(c, who);
+}
+
+extern "C" long long hg_conv5s2_workspace_bytes(int batch, int cin, int cout, int size_out)
+{
+    ConvShape c;
+    if (conv5_shape(c, "hg_conv5s2_workspace_bytes", batch, cin, cout, size_out)) return -1;
+    const long long m_total = (long long)batch * size_out * size_out;
+    Conv5Plan pf, pd;
+    conv5_fwd_plan(m_total, cout, pf);
+    conv5_dx_plan(m_total, cin, cout, pd);
+    long long fwd = pf.max_split > 1 ? (long long)pf.max_split * m_total * cout * 4 : 0;
+    long long dx = pd.max_split > 1 ? (long long)pd.max_split * m_total * 4 * cin * 4 : 0;
+    long long dw = hg_convt_wgrad_workspace_bytes(batch, cout, cin, 2, size_out, 5);
+    if (dw < 0) dw = 0;
+    long long m = fwd > dx ? fwd : dx;
+    return m > dw ? m : dw;
+}
+
+// y[b, i, j, co] = sum_{ci, ky, kx} x[b, ci, 2i + ky - 2, 2j + kx - 2] * w[co, ci, ky, kx]    (no bias)
+//   x_s2d (B, S, S, 4, Cin) bf16, w_k [25][Cout][Cin] bf16 (tap = ky * 5 + kx), y (B, S, S, Cout) bf16
+extern "C" int hg_conv5s2_fwd(const void *x_s2d, const void *w_k, const float *out_scale, void *y, void *workspace,
+                              long long workspace_bytes, int batch, int cin, int cout, int size_out, void *stream)
+{
+    HG_REQUIRE(x_s2d && w_k && y, HG_ERR_INVALID_ARG, "hg_conv5s2_fwd: null pointer");
+    ConvShape c;
+    int rc = conv5_shape(c, "hg_conv5s2_fwd", batch, cin, cout, size_out);
+    if (rc) return rc;
+    HG_REQUIRE(cin % kBK == 0 && cout % 16 == 0, HG_ERR_UNSUPPORTED, "hg_conv5s2_fwd: need Cin %% 64 == 0 and Cout %% 16 == 0 (got %d, %d)", cin, cout);
+    const long long m_total = (long long)batch * size_out * size_out;
+    Conv5Plan pl;
+    conv5_fwd_plan(m_total, cout, pl);
+    const int ks = pl.max_split;
+    HG_REQUIRE(ks == 1 || (workspace && workspace_bytes >= (long long)ks * m_total * cout * 4), HG_ERR_INVALID_ARG,
+               "hg_conv5s2_fwd: workspace smaller than hg_conv5s2_workspace_bytes()");
+    TapGemmParams p{};
+    int bx, by, bz, bb;
+    HG_REQUIRE(box_for(kBM, c.X, c.Y, c.Z, bx, by, bz, bb), HG_ERR_UNSUPPORTED, "hg_conv5s2_fwd: output size %d does not tile into 128-row boxes", size_out);
+    rc = make_map_5d(&p.tmA, x_s2d, 4ll * cin, c.X, c.Y, c.Z, batch, bx, by, bz, bb);
+    if (rc) return rc;
+    rc = make_map_2d(&p.tmB, w_k, cin, 25ll * cout, pl.bn);
+    if (rc) return rc;
+    p.X = c.X; p.Y = c.Y; p.Z = c.Z; p.Bn = batch;
+    p.BN = pl.bn; p.epi_cols = pl.bn; p.bias_mod = cout; p.k_chunks = cin / kBK;
+    p.m_total = (int)m_total; p.ld_out = cout; p.out = y; p.bias = nullptr; p.slope = 1.0f;
+    if (ks > 1) { p.partial = static_cast<float *>(workspace); p.partial_stride = m_total * cout; }
+    p.out_scale = out_scale;
+    int ntap = 0;
+    for_each_class_tap(c, [&](int cls, int flat, int sx, int sy, int sz) {
+        p.taps[ntap++] = Tap{(int16_t)-sx, (int16_t)-sy, (int16_t)-sz, 0, cls * cin, flat * cout};
+    });
+    p.num_groups = ks;
+    for (int s = 0; s < ks; ++s) {
+        const int t0 = s * ntap / ks, t1 = (s + 1) * ntap / ks;
+        p.groups[s] = Group{t0, t1 - t0, 0, s};
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    rc = launch_tap_gemm(p, pl.m_tiles, pl.n_tiles, st, "hg_conv5s2_fwd");
+    if (rc || ks == 1) return rc;
+    return launch_splitk_reduce(p.partial, y, m_total, cout, cout, pl.nsplit, 1, p.partial_stride, out_scale, st);
+}
+
+// dx_s2d[b, i, j, (py, px), ci] = d loss / d x[b, ci, 2i + py, 2j + px]
+//   dy (B, S, S, Cout) bf16, w_t [25][Cin][Cout] bf16, dx_s2d (B, S, S, 4, Cin) bf16
+extern "C" int hg_conv5s2_dx(const void *dy, const void *w_t, const float *out_scale, void *dx_s2d, void *workspace,
+                             long long workspace_bytes, int batch, int cin, int cout, int size_out, void *stream)
+{
+    HG_REQUIRE(dy && w_t && dx_s2d, HG_ERR_INVALID_ARG, "hg_conv5s2_dx: null pointer");
+    ConvShape c;
+    int rc = conv5_shape(c, "hg_conv5s2_dx", batch, cin, cout, size_out);
+    if (rc) return rc;
+    HG_REQUIRE(cout % kBK == 0 && cin % 16 == 0, HG_ERR_UNSUPPORTED, "hg_conv5s2_dx: need Cout %% 64 == 0 and Cin %% 16 == 0 (got %d, %d)", cout, cin);
+    const long long m_total = (long long)batch * size_out * size_out;
+    Conv5Plan pl;
+    conv5_dx_plan(m_total, cin, cout, pl);
+    if (pl.max_split == 1)      // enough CTAs without splitting: the transposed convolution's own launch plan
+        return convt_fwd_impl(dy, w_t, nullptr, out_scale, dx_s2d, batch, cout, cin, 2, size_out, 5, 1.0f, stream);
+    HG_REQUIRE(workspace && workspace_bytes >= (long long)pl.max_split * m_total * 4 * cin * 4, HG_ERR_INVALID_ARG,
+               "hg_conv5s2_dx: workspace smaller than hg_conv5s2_workspace_bytes()");
+    TapGemmParams p{};
+    int bx, by, bz, bb;
+    HG_REQUIRE(box_for(kBM, c.X, c.Y, c.Z, bx, by, bz, bb), HG_ERR_UNSUPPORTED, "hg_conv5s2_dx: output size %d does not tile into 128-row boxes", size_out);
+    rc = make_map_5d(&p.tmA, dy, cout, c.X, c.Y, c.Z, batch, bx, by, bz, bb);
+    if (rc) return rc;
+    rc = make_map_2d(&p.tmB, w_t, cout, 25ll * cin, pl.bn);
+    if (rc) return rc;
+    p.X = c.X; p.Y = c.Y; p.Z = c.Z; p.Bn = batch;
+    p.BN = pl.bn; p.epi_cols = pl.bn; p.bias_mod = cin; p.k_chunks = cout / kBK;
+    p.m_total = (int)m_total; p.ld_out = 4ll * cin; p.out = dx_s2d; p.bias = nullptr; p.slope = 1.0f;
+    p.partial = static_cast<float *>(workspace); p.partial_stride = m_total * 4 * cin;
+    // taps in class-major order (for_each_class_tap), a class's taps cut into nsplit[cls] contiguous runs
+    int ntap = 0, class_begin[5] = {0, 0, 0, 0, 0};
+    for_each_class_tap(c, [&](int cls, int flat, int sx, int sy, int sz) {
+        p.taps[ntap++] = Tap{(int16_t)sx, (int16_t)sy, (int16_t)sz, 0, 0, flat * cin};
+        class_begin[cls + 1] = ntap;
+    });
+    int ng = 0;
+    for (int cls = 0; cls < 4; ++cls) {
+        const int n = class_begin[cls + 1] - class_begin[cls], sp = pl.nsplit[cls];
+        for (int s = 0; s < sp; ++s) {
+            const int t0 = class_begin[cls] + s * n / sp, t1 = class_begin[cls] + (s + 1) * n / sp;
+            p.groups[ng++] = Group{t0, t1 - t0, cls * cin, s};
+        }
+    }
+    p.num_groups = ng;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    rc = launch_tap_gemm(p, pl.m_tiles, pl.n_tiles, st, "hg_conv5s2_dx");
+    if (rc) return rc;
+    return launch_splitk_reduce(p.partial, dx_s2d, m_total, 4 * cin, cin, pl.nsplit, 4, p.partial_stride, out_scale, st);
+}
+
+// dw[co, ci, ky, kx] (torch Conv2d layout, fp32) = sum over positions; accumulate != 0 adds into dw.
+extern "C" int hg_conv5s2_dw(const void *dy, const void *x_s2d, float *dw, void *workspace, long long workspace_bytes,
+                             int batch, int cin, int cout, int size_out, int accumulate, void *stream)
+{
+    return hg_convt_wgrad(dy, x_s2d, dw, workspace, workspace_bytes, batch, cout, cin, 2, size_out, 5, 0, 0, accumulate, stream);
+}
+
+// Conv2d weight (Cout, Cin, 5, 5) fp32 contiguous, divided by *sigma (device pointer, may be null) ->
+//   w_k [25][Cout][Cin] bf16 (hg_conv5s2_fwd) and w_t [25][Cin][Cout] bf16 (hg_conv5s2_dx); either may be null.
+extern "C" int hg_conv5s2_pack_weight(const float *w, const float *sigma, void *w_k, void *w_t, int cin, int cout, void *stream)
+{
+    // as the dual transposed convolution's weight: Cin_T = Cout, Cout_T = Cin -> w_dgrad [t][Cin_T][Cout_T] = w_k, w_fwd = w_t
+    return pack_weight_impl(w, w_t, w_k, cout, cin, 25, 0, 0, sigma, stream);
 }

@@ -1,0 +1,753 @@
+// The two ends of the HoloGAN discriminator (reference core/models/hologan_discriminator.py):
+//   conv0 : Conv2d(3 -> 64, k5, s2, p2) + bias + LeakyReLU(0.2)                         (:30, :58)
+//   heads : logits = linear1(h);  z = tanh(linear3(leaky_relu(linear2(h), 0.2)))        (:41-51, :64-68)
+// forward and backward, in the layouts of the bf16 pipeline: conv0 reads the fp32 NCHW image (real batch or the
+// generator's output) and writes its activation in the 2x2 space-to-depth order that the first spectral-norm block's
+// tap GEMM consumes (hg_conv5s2_fwd); the heads read the last block's channels-last activation (B, H, W, 512) -- the
+// reference flattens (c, h, w), so the kernels address the torch-layout weights with feature f = c * HW + hw.
+//
+// conv0 has K = 75 and three input channels: it is bandwidth-bound (3 MB in, 8 MB out at B = 64) but needs 0.3 GFMA,
+// which on the FP32 pipe costs more than the memory traffic, so it runs on the warp-level tensor cores
+// (mma.sync.m16n8k16, bf16 operands, fp32 accumulation) as an im2col GEMM whose A fragments are gathered straight
+// from a staged bf16 input patch.  The heads are a 64 x 129 x 8192 problem (0.07 GFMA): fp32 SIMT, split over the
+// feature axis across CTAs, partials summed in a fixed order.  Everything is deterministic; no atomics.
+#include "hg_common.cuh"
+#include "mma_sync.cuh"
+
+namespace hg {
+
+// -------------------------------------------------------------------------------------------------
+// conv0
+// -------------------------------------------------------------------------------------------------
+constexpr int kC0Threads = 256;
+constexpr int kC0Cout = 64, kC0Cin = 3;
+constexpr int kC0TH = 8, kC0TW = 16;                    // output tile: one row of 16 pixels per warp
+constexpr int kC0PH = 2 * kC0TH + 3, kC0PW = 2 * kC0TW + 3, kC0PPitch = 36;      // input patch 19 x 35 per channel
+constexpr int kC0KSteps = 6;                            // K index k = (ci * 5 + ky) * 6 + kx, kx < 6 (kx == 5: zero) -> 90 -> 96
+constexpr int kC0KReal = 90;
+constexpr int kC0OnesCol = 90;                          // dW kernel: im2col column 90 is all ones -> its "weight gradient" is dbias
+
+// element offset of im2col column k inside the patch (relative to the pixel's top-left tap); columns >= 90 map to 0
+__device__ __forceinline__ int c0_col_offset(int k)
+{
+    if (k >= kC0KReal) return 0;
+    const int kx = k % 6, r = k / 6, ky = r % 5, ci = r / 5;
+    return (ci * kC0PH + ky) * kC0PPitch + kx;
+}
+
+// stage the input patch of the tile as bf16 [3][19][36]; out-of-image elements are zero
+__device__ __forceinline__ void c0_stage_patch(__nv_bfloat16 *patch, const float *__restrict__ xb, int S, int oy0, int ox0)
+{
+    const int iy0 = 2 * oy0 - 2, ix0 = 2 * ox0 - 2;
+    for (int i = threadIdx.x; i < kC0Cin * kC0PH * kC0PPitch; i += kC0Threads) {
+        const int px = i % kC0PPitch, r = i / kC0PPitch, py = r % kC0PH, ci = r / kC0PH;
+        const int yy = iy0 + py, xx = ix0 + px;
+        float v = 0.f;
+        if (px < kC0PW && yy >= 0 && yy < S && xx >= 0 && xx < S) v = __ldg(xb + ((size_t)ci * S + yy) * S + xx);
+        patch[i] = __float2bfloat16_rn(v);
+    }
+}
+
+// row of the space-to-depth activation that holds pixel (oy, ox) of the (S2 x S2) map, S4 = S2 / 2
+__device__ __forceinline__ int c0_s2d_row(int oy, int ox, int S4)
+{
+    return (((oy >> 1) * S4 + (ox >> 1)) << 2) + ((oy & 1) << 1) + (ox & 1);
+}
+
+__global__ void __launch_bounds__(kC0Threads) dconv0_fwd_kernel(const float *__restrict__ x, const float *__restrict__ w,
+                                                                const float *__restrict__ bias, __nv_bfloat16 *__restrict__ y,
+                                                                int S, int total_tiles, float slope)
+{
+    __shared__ __align__(16) __nv_bfloat16 patch[kC0Cin * kC0PH * kC0PPitch];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, q = lane & 3;
+    const int S2 = S / 2, S4 = S / 4, tiles_x = S2 / kC0TW, tiles_img = tiles_x * (S2 / kC0TH);
+    // B fragments (weights) of all k-steps and n-tiles: B[k][co] = w[co][ci][ky][kx]
+    uint32_t bw[kC0KSteps][8][2];
+#pragma unroll
+    for (int ks = 0; ks < kC0KSteps; ++ks)
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int k = ks * 16 + 2 * q + 8 * h, co = nt * 8 + g;
+                float v[2];
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int kk = k + e, kx = kk % 6, r = kk / 6, ky = r % 5, ci = r / 5;
+                    v[e] = (kk < kC0KReal && kx < 5) ? __ldg(w + ((size_t)co * kC0Cin + ci) * 25 + ky * 5 + kx) : 0.f;
+                }
+                bw[ks][nt][h] = pack_bf16x2(v[0], v[1]);
+            }
+    int aoff[kC0KSteps][2];
+#pragma unroll
+    for (int ks = 0; ks < kC0KSteps; ++ks) {
+        aoff[ks][0] = c0_col_offset(ks * 16 + 2 * q);
+        aoff[ks][1] = c0_col_offset(ks * 16 + 2 * q + 8);
+    }
+    float bv[8][2];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+        bv[nt][0] = __ldg(bias + nt * 8 + 2 * q);
+        bv[nt][1] = __ldg(bias + nt * 8 + 2 * q + 1);
+    }
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int b = tile / tiles_img, t = tile - b * tiles_img;
+        const int oy0 = (t / tiles_x) * kC0TH, ox0 = (t % tiles_x) * kC0TW;
+        __syncthreads();
+        c0_stage_patch(patch, x + (size_t)b * kC0Cin * S * S, S, oy0, ox0);
+        __syncthreads();
+        float acc[8][4];
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[nt][j] = 0.f;
+        const unsigned char *prow = reinterpret_cast<const unsigned char *>(patch + (2 * warp) * kC0PPitch);
+#pragma unroll
+        for (int ks = 0; ks < kC0KSteps; ++ks) {
+            uint32_t a[4];
+            a[0] = lds32(prow + (aoff[ks][0] + 2 * g) * 2);
+            a[1] = lds32(prow + (aoff[ks][0] + 2 * (g + 8)) * 2);
+            a[2] = lds32(prow + (aoff[ks][1] + 2 * g) * 2);
+            a[3] = lds32(prow + (aoff[ks][1] + 2 * (g + 8)) * 2);
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) mma_bf16_16816(acc[nt], a, bw[ks][nt][0], bw[ks][nt][1]);
+        }
+        const int oy = oy0 + warp;
+        __nv_bfloat16 *yb = y + (size_t)b * S2 * S2 * kC0Cout;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int ox = ox0 + g + 8 * h;
+            __nv_bfloat16 *dst = yb + (size_t)c0_s2d_row(oy, ox, S4) * kC0Cout + 2 * q;
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+                float v0 = acc[nt][2 * h] + bv[nt][0], v1 = acc[nt][2 * h + 1] + bv[nt][1];
+                v0 = v0 > 0.f ? v0 : v0 * slope;
+                v1 = v1 > 0.f ? v1 : v1 * slope;
+                *reinterpret_cast<uint32_t *>(dst + nt * 8) = pack_bf16x2(v0, v1);
+            }
+        }
+    }
+}
+
+// gradient through the LeakyReLU: dpre = dy * (y > 0 ? 1 : slope), both in the s2d activation layout
+__device__ __forceinline__ float c0_dpre(__nv_bfloat16 dy, __nv_bfloat16 yv, float slope)
+{
+    const float d = __bfloat162float(dy);
+    return __bfloat162float(yv) > 0.f ? d : d * slope;
+}
+
+// ---- weight / bias gradient -----------------------------------------------------------------------
+// dW[co][k] = sum_pix dpre[pix][co] * im2col[pix][k]  as  M = co (64), N = k (96), K = pixels.  A CTA walks tiles, its 8
+// warps = 4 row groups x 2 channel halves hold a 32 x 96 accumulator each; the row groups are summed through shared memory
+// and every CTA writes one partial [64][96]; dconv0_bwd_w_reduce_kernel sums the CTA partials in order.
+constexpr int kC0DtPitch = kC0TH * kC0TW + 8;           // 136 bf16 per channel row of the transposed dpre tile
+
+__global__ void __launch_bounds__(kC0Threads) dconv0_bwd_w_kernel(const float *__restrict__ x, const __nv_bfloat16 *__restrict__ y,
+                                                                  const __nv_bfloat16 *__restrict__ dy, float *__restrict__ part,
+                                                                  int S, int total_tiles, float slope)
+{
+    __shared__ __align__(16) __nv_bfloat16 patch[kC0Cin * kC0PH * kC0PPitch];
+    __shared__ __align__(16) __nv_bfloat16 dt[kC0Cout * kC0DtPitch];             // dpre transposed: [co][pixel of the tile]
+    __shared__ float red[kC0Cout * 97];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, q = lane & 3;
+    const int rg = warp & 3, ch = warp >> 2;
+    const int S2 = S / 2, S4 = S / 4, tiles_x = S2 / kC0TW, tiles_img = tiles_x * (S2 / kC0TH);
+    float acc[2][12][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 12; ++nt)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[mt][nt][j] = 0.f;
+    int boff[12];                                       // patch offset of im2col column nt * 8 + g
+#pragma unroll
+    for (int nt = 0; nt < 12; ++nt) boff[nt] = c0_col_offset(nt * 8 + g);
+    const __nv_bfloat16 one = __float2bfloat16_rn(1.f), zero = __float2bfloat16_rn(0.f);
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int b = tile / tiles_img, t = tile - b * tiles_img;
+        const int oy0 = (t / tiles_x) * kC0TH, ox0 = (t % tiles_x) * kC0TW;
+        __syncthreads();
+        c0_stage_patch(patch, x + (size_t)b * kC0Cin * S * S, S, oy0, ox0);
+        {   // dpre of the tile, transposed: thread -> (pixel, 8 channels)
+            const size_t img = (size_t)b * S2 * S2 * kC0Cout;
+            for (int i = threadIdx.x; i < kC0TH * kC0TW * 8; i += kC0Threads) {
+                const int c8 = i & 7, pix = i >> 3, py = pix / kC0TW, px = pix % kC0TW;
+                const size_t off = img + (size_t)c0_s2d_row(oy0 + py, ox0 + px, S4) * kC0Cout + c8 * 8;
+                const uint4 yv = __ldg(reinterpret_cast<const uint4 *>(y + off));
+                const uint4 gv = __ldg(reinterpret_cast<const uint4 *>(dy + off));
+                const __nv_bfloat16 *yh = reinterpret_cast<const __nv_bfloat16 *>(&yv);
+                const __nv_bfloat16 *gh = reinterpret_cast<const __nv_bfloat16 *>(&gv);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) dt[(c8 * 8 + j) * kC0DtPitch + pix] = __float2bfloat16_rn(c0_dpre(gh[j], yh[j], slope));
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+            const int row = rg + 4 * rr;                // tile row = one 16-pixel K step
+            uint32_t a[2][4];
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+                const unsigned char *base = reinterpret_cast<const unsigned char *>(dt + (ch * 32 + mt * 16 + g) * kC0DtPitch + row * kC0TW + 2 * q);
+                a[mt][0] = lds32(base);
+                a[mt][1] = lds32(base + 8 * kC0DtPitch * 2);
+                a[mt][2] = lds32(base + 16);
+                a[mt][3] = lds32(base + 8 * kC0DtPitch * 2 + 16);
+            }
+            const __nv_bfloat16 *prow = patch + (2 * row) * kC0PPitch;
+#pragma unroll
+            for (int nt = 0; nt < 12; ++nt) {
+                // B[pix][kcol]: pixels 2q, 2q+1 (b0) and 2q+8, 2q+9 (b1) of im2col column kcol = nt * 8 + g
+                const int kcol = nt * 8 + g;
+                __nv_bfloat16 e[4];
+                if (kcol < kC0KReal) {
+                    const __nv_bfloat16 *src = prow + boff[nt];
+                    e[0] = src[2 * (2 * q)]; e[1] = src[2 * (2 * q + 1)]; e[2] = src[2 * (2 * q + 8)]; e[3] = src[2 * (2 * q + 9)];
+                } else {
+                    e[0] = e[1] = e[2] = e[3] = kcol == kC0OnesCol ? one : zero;
+                }
+                const uint32_t b0 = (uint32_t)__bfloat16_as_ushort(e[0]) | ((uint32_t)__bfloat16_as_ushort(e[1]) << 16);
+                const uint32_t b1 = (uint32_t)__bfloat16_as_ushort(e[2]) | ((uint32_t)__bfloat16_as_ushort(e[3]) << 16);
+                mma_bf16_16816(acc[0][nt], a[0], b0, b1);
+                mma_bf16_16816(acc[1][nt], a[1], b0, b1);
+            }
+        }
+    }
+    // sum the four row groups of each channel half in a fixed order, then one partial per CTA
+    for (int r = 0; r < 4; ++r) {
+        __syncthreads();
+        if (rg == r) {
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < 12; ++nt)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int co = ch * 32 + mt * 16 + g + 8 * (j >> 1), k = nt * 8 + 2 * q + (j & 1);
+                        float *d = red + co * 97 + k;
+                        *d = r == 0 ? acc[mt][nt][j] : *d + acc[mt][nt][j];
+                    }
+        }
+    }
+    __syncthreads();
+    float *dst = part + (size_t)blockIdx.x * kC0Cout * 96;
+    for (int i = threadIdx.x; i < kC0Cout * 96; i += kC0Threads) dst[i] = red[(i / 96) * 97 + i % 96];
+}
+
+// dw (64, 3, 5, 5) and dbias (64) from the CTA partials; accumulate != 0 adds to the existing values
+__global__ void __launch_bounds__(256) dconv0_bwd_w_reduce_kernel(const float *__restrict__ part, int nparts, float *__restrict__ dw,
+                                                                  float *__restrict__ dbias, int accumulate)
+{
+    const int i = blockIdx.x * 256 + threadIdx.x;       // (co, k) with k < 96
+    if (i >= kC0Cout * 96) return;
+    const int co = i / 96, k = i % 96;
+    float s = 0.f;
+    for (int p = 0; p < nparts; ++p) s += part[(size_t)p * kC0Cout * 96 + i];
+    if (k == kC0OnesCol) {
+        if (dbias) dbias[co] = accumulate ? dbias[co] + s : s;
+        return;
+    }
+    const int kx = k % 6, r = k / 6, ky = r % 5, ci = r / 5;
+    if (k >= kC0KReal || kx >= 5) return;
+    float *d = dw + ((size_t)co * kC0Cin + ci) * 25 + ky * 5 + kx;
+    *d = accumulate ? *d + s : s;
+}
+
+// ---- input gradient -----------------------------------------------------------------------------------
+// dX[b][ci][2i + py][2j + px] = sum_{co, taps of the parity class} dpre[b][i + 1 - ky/2][j + 1 - kx/2][co] * w[co][ci][ky][kx]
+// per class a GEMM  M = pixels (i, j), K = taps x 64, N = 3 -> 8.  A CTA owns an 8 x 16 block of (i, j): the dpre tile with
+// a one-pixel halo sits in shared memory (pixel pitch 144 B: conflict-free fragment loads), the weights as ready-made B
+// fragments; the 16 x 32 x 3 result goes through shared memory so that global rows are written contiguously.
+constexpr int kC0XPitch = kC0Cout * 2 + 16;             // bytes per staged dpre pixel
+constexpr int kC0HaloW = kC0TW + 2, kC0HaloH = kC0TH + 2;
+
+__global__ void __launch_bounds__(kC0Threads) dconv0_bwd_x_kernel(const __nv_bfloat16 *__restrict__ y, const __nv_bfloat16 *__restrict__ dy,
+                                                                  const float *__restrict__ w, float *__restrict__ dx, int S,
+                                                                  int total_tiles, float slope)
+{
+    extern __shared__ __align__(16) unsigned char c0x_smem[];
+    unsigned char *ds = c0x_smem;                                                              // [10 x 18 pixels][144 B]
+    uint2 *wfrag = reinterpret_cast<uint2 *>(ds + kC0HaloH * kC0HaloW * kC0XPitch);            // [25 taps][4 k-steps][32 lanes]
+    float *outs = reinterpret_cast<float *>(wfrag + 25 * 4 * 32);                              // [3][16][33]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, q = lane & 3;
+    const int S2 = S / 2, S4 = S / 4, tiles_x = S2 / kC0TW, tiles_img = tiles_x * (S2 / kC0TH);
+    for (int i = threadIdx.x; i < 25 * 4 * 32; i += kC0Threads) {
+        const int ln = i & 31, ks = (i >> 5) & 3, tap = i >> 7, gg = ln >> 2, qq = ln & 3;
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        if (gg < kC0Cin) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int co = ks * 16 + 2 * qq + (e & 1) + 8 * (e >> 1);
+                v[e] = __ldg(w + ((size_t)co * kC0Cin + gg) * 25 + tap);
+            }
+        }
+        wfrag[i] = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
+    }
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int b = tile / tiles_img, t = tile - b * tiles_img;
+        const int i0 = (t / tiles_x) * kC0TH, j0 = (t % tiles_x) * kC0TW;
+        __syncthreads();
+        {
+            const size_t img = (size_t)b * S2 * S2 * kC0Cout;
+            for (int i = threadIdx.x; i < kC0HaloH * kC0HaloW * 8; i += kC0Threads) {
+                const int c8 = i & 7, pix = i >> 3, hy = pix / kC0HaloW, hx = pix % kC0HaloW;
+                const int oy = i0 + hy - 1, ox = j0 + hx - 1;
+                uint4 o = make_uint4(0, 0, 0, 0);
+                if (oy >= 0 && oy < S2 && ox >= 0 && ox < S2) {
+                    const size_t off = img + (size_t)c0_s2d_row(oy, ox, S4) * kC0Cout + c8 * 8;
+                    const uint4 yv = __ldg(reinterpret_cast<const uint4 *>(y + off));
+                    const uint4 gv = __ldg(reinterpret_cast<const uint4 *>(dy + off));
+                    const __nv_bfloat16 *yh = reinterpret_cast<const __nv_bfloat16 *>(&yv);
+                    const __nv_bfloat16 *gh = reinterpret_cast<const __nv_bfloat16 *>(&gv);
+                    float f[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) f[j] = c0_dpre(gh[j], yh[j], slope);
+                    o = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+                }
+                *reinterpret_cast<uint4 *>(ds + (size_t)pix * kC0XPitch + c8 * 16) = o;
+            }
+        }
+        __syncthreads();
+        float acc[4][4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[c][j] = 0.f;
+#pragma unroll
+        for (int ky = 0; ky < 5; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 5; ++kx) {
+                const int cls = (ky & 1) * 2 + (kx & 1), dyy = 1 - (ky >> 1), dxx = 1 - (kx >> 1);
+                // tile-local halo coordinates of pixel (i = i0 + warp, j = j0 + g [+ 8]) shifted by (dyy, dxx)
+                const unsigned char *p0 = ds + (size_t)((warp + 1 + dyy) * kC0HaloW + (g + 1 + dxx)) * kC0XPitch + 4 * q;
+                const unsigned char *p1 = p0 + 8 * kC0XPitch;
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                    uint32_t a[4];
+                    a[0] = lds32(p0 + ks * 32); a[1] = lds32(p1 + ks * 32);
+                    a[2] = lds32(p0 + ks * 32 + 16); a[3] = lds32(p1 + ks * 32 + 16);
+                    const uint2 bf = wfrag[((ky * 5 + kx) * 4 + ks) * 32 + lane];
+                    mma_bf16_16816(acc[cls], a, bf.x, bf.y);
+                }
+            }
+        // C[pix g (+8)][ci = 2q, 2q+1] -> outs[ci][row 2*warp + py][col 2*(g [+8]) + px]
+        constexpr int OW = 2 * kC0TW + 1;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int py = c >> 1, px = c & 1;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int ci = 2 * q + (j & 1), col = 2 * (g + 8 * (j >> 1)) + px;
+                if (ci < kC0Cin) outs[(ci * 2 * kC0TH + 2 * warp + py) * OW + col] = acc[c][j];
+            }
+        }
+        __syncthreads();
+        float *dxb = dx + (size_t)b * kC0Cin * S * S;
+        for (int i = threadIdx.x; i < kC0Cin * 2 * kC0TH * 2 * kC0TW; i += kC0Threads) {
+            const int col = i % (2 * kC0TW), r = i / (2 * kC0TW), row = r % (2 * kC0TH), ci = r / (2 * kC0TH);
+            dxb[((size_t)ci * S + 2 * i0 + row) * S + 2 * j0 + col] = outs[(ci * 2 * kC0TH + row) * OW + col];
+        }
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// heads
+// -------------------------------------------------------------------------------------------------
+constexpr int kHdThreads = 256;
+constexpr int kHdSlab = 64;                             // features per CTA
+constexpr int kHdNPad = 160;                            // 129 output columns (128 of linear2 + the logit) padded to 5 x 32
+constexpr int kHdN = 129;
+constexpr int kHdLd = 132;                              // row pitch of the (B, 129) partial / gradient matrices
+constexpr int kHdMaxB = 64;
+
+// feature slab `slab`: channels [c0, c0 + cs) x all HW positions; local index k = c_local * HW + hw is the torch feature
+// c0 * HW + k (contiguous in the weight rows) and sits at h[b][hw * C + c0 + c_local] in the channels-last activation
+struct HeadGeom { int C, HW, cs, slabs, F; };
+
+// All staging loops issue their global loads in register batches (unrolled, independent) before touching shared memory:
+// a first version with one dependent load per trip was latency-bound (28 us for 58 KB per CTA).
+__device__ __forceinline__ void hd_stage_h(float *hs, const __nv_bfloat16 *__restrict__ h, const HeadGeom &g, int batch, int c0)
+{
+    // item i = b * 64 + hw * cs + cl (cl fastest: cs contiguous channels in memory); shared index k = cl * HW + hw
+    constexpr int kPer = kHdMaxB * kHdSlab / kHdThreads;       // 16
+    __nv_bfloat16 v[kPer];
+#pragma unroll
+    for (int j = 0; j < kPer; ++j) {
+        const int i = threadIdx.x + j * kHdThreads, b = i / kHdSlab, r = i % kHdSlab, hw = r / g.cs, cl = r - hw * g.cs;
+        v[j] = b < batch ? h[(size_t)b * g.F + (size_t)hw * g.C + c0 + cl] : __float2bfloat16_rn(0.f);
+    }
+#pragma unroll
+    for (int j = 0; j < kPer; ++j) {
+        const int i = threadIdx.x + j * kHdThreads, b = i / kHdSlab, r = i % kHdSlab, hw = r / g.cs, cl = r - hw * g.cs;
+        hs[b * kHdSlab + cl * g.HW + hw] = __bfloat162float(v[j]);
+    }
+}
+// ws[n][k] (pitch kHdSlab + 1): rows 0..127 = linear2, row 128 = linear1, rows 129.. zero
+__device__ __forceinline__ void hd_stage_w(float *ws, const float *__restrict__ w1, const float *__restrict__ w2, const HeadGeom &g,
+                                           int f0, int rows)
+{
+    constexpr int kVecRow = kHdSlab / 4, kVecs = kHdN * kVecRow, kPer = (kVecs + kHdThreads - 1) / kHdThreads;      // 16, 2064, 9
+    float4 v[kPer];
+#pragma unroll
+    for (int j = 0; j < kPer; ++j) {
+        const int i = threadIdx.x + j * kHdThreads, n = i / kVecRow, q = i % kVecRow;
+        if (i < kVecs) v[j] = __ldg(reinterpret_cast<const float4 *>((n < 128 ? w2 + (size_t)n * g.F : w1) + f0) + q);
+    }
+#pragma unroll
+    for (int j = 0; j < kPer; ++j) {
+        const int i = threadIdx.x + j * kHdThreads, n = i / kVecRow, q = i % kVecRow;
+        if (i < kVecs) {
+            float *d = ws + n * (kHdSlab + 1) + q * 4;
+            d[0] = v[j].x; d[1] = v[j].y; d[2] = v[j].z; d[3] = v[j].w;
+        }
+    }
+    for (int i = kHdN * (kHdSlab + 1) + threadIdx.x; i < rows * (kHdSlab + 1); i += kHdThreads) ws[i] = 0.f;
+}
+
+// partial[slab][b][n] = sum_{k in slab} h[b][k] * W[n][k]
+__global__ void __launch_bounds__(kHdThreads) dheads_fwd_partial_kernel(const __nv_bfloat16 *__restrict__ h, const float *__restrict__ w1,
+                                                                        const float *__restrict__ w2, float *__restrict__ part,
+                                                                        HeadGeom g, int batch)
+{
+    extern __shared__ __align__(16) float hd_smem[];
+    float *hs = hd_smem, *ws = hd_smem + kHdMaxB * kHdSlab;
+    const int slab = blockIdx.x, c0 = slab * g.cs, f0 = c0 * g.HW;
+    hd_stage_h(hs, h, g, batch, c0);
+    hd_stage_w(ws, w1, w2, g, f0, kHdNPad);
+    __syncthreads();
+    const int tn = threadIdx.x & 31, tb = threadIdx.x >> 5;
+    float acc[8][5];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 5; ++j) acc[i][j] = 0.f;
+#pragma unroll 4
+    for (int k = 0; k < kHdSlab; ++k) {
+        float hv[8], wv[5];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) hv[i] = hs[(tb * 8 + i) * kHdSlab + k];
+#pragma unroll
+        for (int j = 0; j < 5; ++j) wv[j] = ws[(tn + 32 * j) * (kHdSlab + 1) + k];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 5; ++j) acc[i][j] = fmaf(hv[i], wv[j], acc[i][j]);
+    }
+    float *dst = part + (size_t)slab * kHdMaxB * kHdLd;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+            const int n = tn + 32 * j;
+            if (n < kHdN) dst[(tb * 8 + i) * kHdLd + n] = acc[i][j];
+        }
+}
+
+// one CTA per sample, thread = column: sums the slab partials (8 independent loads in flight, fixed order), applies
+// bias / LeakyReLU, then linear3 + tanh with one warp per output row (coalesced weight rows, shuffle reduction)
+__global__ void __launch_bounds__(128) dheads_fwd_finish_kernel(const float *__restrict__ part, int slabs, const float *__restrict__ b1,
+                                                                const float *__restrict__ b2, const float *__restrict__ w3,
+                                                                const float *__restrict__ b3, float *__restrict__ logits,
+                                                                float *__restrict__ t2, float *__restrict__ zp, int zdim, float slope)
+{
+    __shared__ float ts[128];
+    const int b = blockIdx.x, n = threadIdx.x, lane = n & 31, warp = n >> 5;
+    const float *col = part + (size_t)b * kHdLd + n;
+    constexpr size_t kSlabStride = (size_t)kHdMaxB * kHdLd;
+    float acc[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) acc[u] = 0.f;
+    for (int sl = 0; sl < slabs; sl += 8) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            if (sl + u < slabs) acc[u] += col[(size_t)(sl + u) * kSlabStride];
+    }
+    float s = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7])) + b2[n];
+    s = s > 0.f ? s : s * slope;
+    ts[n] = s;
+    t2[(size_t)b * 128 + n] = s;
+    if (warp == 0) {                                    // the logit column: lanes stride over the slabs
+        float l = 0.f;
+        for (int sl = lane; sl < slabs; sl += 32) l += part[(size_t)sl * kSlabStride + (size_t)b * kHdLd + 128];
+        l = warp_sum(l);
+        if (lane == 0) logits[b] = l + b1[0];
+    }
+    __syncthreads();
+    const float t0 = ts[lane], t1 = ts[lane + 32], t2v = ts[lane + 64], t3 = ts[lane + 96];
+#pragma unroll 4
+    for (int j = warp; j < zdim; j += 4) {
+        const float *wr = w3 + (size_t)j * 128 + lane;
+        float a = __ldg(wr) * t0 + __ldg(wr + 32) * t1 + __ldg(wr + 64) * t2v + __ldg(wr + 96) * t3;
+        a = warp_sum(a);
+        if (lane == 0) zp[(size_t)b * zdim + j] = tanhf(a + b3[j]);
+    }
+}
+
+// backward, per sample: dt3 = dzp * (1 - zp^2);  dO[b][n] = (sum_j dt3[j] * W3[j][n]) * lrelu'(t2[n]);  dO[b][128] = dlogits[b]
+__global__ void __launch_bounds__(128) dheads_bwd_small_kernel(const float *__restrict__ dlogits, const float *__restrict__ dzp,
+                                                               const float *__restrict__ zp, const float *__restrict__ t2,
+                                                               const float *__restrict__ w3, float *__restrict__ dt3,
+                                                               float *__restrict__ dO, int zdim, float slope)
+{
+    extern __shared__ float d3[];
+    const int b = blockIdx.x, n = threadIdx.x;
+    for (int j = n; j < zdim; j += 128) {
+        const float z = zp[(size_t)b * zdim + j];
+        const float v = (dzp ? dzp[(size_t)b * zdim + j] : 0.f) * (1.f - z * z);
+        d3[j] = v;
+        dt3[(size_t)b * zdim + j] = v;
+    }
+    __syncthreads();
+    float s = 0.f;
+#pragma unroll 8
+    for (int j = 0; j < zdim; ++j) s = fmaf(d3[j], __ldg(w3 + (size_t)j * 128 + n), s);
+    dO[(size_t)b * kHdLd + n] = t2[(size_t)b * 128 + n] > 0.f ? s : s * slope;
+    if (n == 0) dO[(size_t)b * kHdLd + 128] = dlogits ? dlogits[b] : 0.f;
+}
+
+// small parameter gradients: dW3[j][n] = sum_b dt3[b][j] * t2[b][n], db3[j], db2[n], db1
+__global__ void __launch_bounds__(128) dheads_bwd_params_kernel(const float *__restrict__ dt3, const float *__restrict__ t2,
+                                                                const float *__restrict__ dO, float *__restrict__ dw3,
+                                                                float *__restrict__ db3, float *__restrict__ db2, float *__restrict__ db1,
+                                                                int batch, int zdim)
+{
+    const int j = blockIdx.x, n = threadIdx.x;
+    if (j < zdim) {
+        float s = 0.f, sb = 0.f;
+        for (int b = 0; b < batch; ++b) {
+            const float d = dt3[(size_t)b * zdim + j];
+            s = fmaf(d, t2[(size_t)b * 128 + n], s);
+            sb += d;
+        }
+        dw3[(size_t)j * 128 + n] = s;
+        if (n == 0) db3[j] = sb;
+    } else {                                            // one extra block: biases of linear2 / linear1
+        float s = 0.f, l = 0.f;
+        for (int b = 0; b < batch; ++b) {
+            s += dO[(size_t)b * kHdLd + n];
+            if (n == 0) l += dO[(size_t)b * kHdLd + 128];
+        }
+        db2[n] = s;
+        if (n == 0) db1[0] = l;
+    }
+}
+
+// big gradients per feature slab: dW[n][k] = sum_b dO[b][n] * h[b][k] (torch layout rows of W1 / W2, optional) and
+// dh[b][k] = sum_n dO[b][n] * W[n][k] (bf16, channels-last activation layout)
+__global__ void __launch_bounds__(kHdThreads) dheads_bwd_big_kernel(const __nv_bfloat16 *__restrict__ h, const float *__restrict__ w1,
+                                                                    const float *__restrict__ w2, const float *__restrict__ dO,
+                                                                    float *__restrict__ dw1, float *__restrict__ dw2,
+                                                                    __nv_bfloat16 *__restrict__ dh, HeadGeom g, int batch)
+{
+    extern __shared__ __align__(16) float hd_smem[];
+    float *hs = hd_smem, *ws = hs + kHdMaxB * kHdSlab, *os = ws + kHdNPad * (kHdSlab + 1);     // os[b][n], pitch kHdNPad
+    const int slab = blockIdx.x, c0 = slab * g.cs, f0 = c0 * g.HW;
+    hd_stage_h(hs, h, g, batch, c0);
+    hd_stage_w(ws, w1, w2, g, f0, kHdNPad);
+#pragma unroll 8
+    for (int i = threadIdx.x; i < kHdMaxB * kHdNPad; i += kHdThreads) {
+        const int n = i % kHdNPad, b = i / kHdNPad;
+        os[i] = (b < batch && n < kHdN) ? __ldg(dO + (size_t)b * kHdLd + n) : 0.f;
+    }
+    __syncthreads();
+    if (dw2) {
+        const int tn = threadIdx.x & 31, tk = threadIdx.x >> 5;
+        float acc[5][8];
+#pragma unroll
+        for (int j = 0; j < 5; ++j)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[j][i] = 0.f;
+        for (int b = 0; b < batch; ++b) {
+            float ov[5], hv[8];
+#pragma unroll
+            for (int j = 0; j < 5; ++j) ov[j] = os[b * kHdNPad + tn + 32 * j];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) hv[i] = hs[b * kHdSlab + tk * 8 + i];
+#pragma unroll
+            for (int j = 0; j < 5; ++j)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc[j][i] = fmaf(ov[j], hv[i], acc[j][i]);
+        }
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+            const int n = tn + 32 * j;
+            if (n < kHdN) {
+                float *dst = (n < 128 ? dw2 + (size_t)n * g.F : dw1) + f0 + tk * 8;
+                *reinterpret_cast<float4 *>(dst) = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
+                *reinterpret_cast<float4 *>(dst + 4) = make_float4(acc[j][4], acc[j][5], acc[j][6], acc[j][7]);
+            }
+        }
+    }
+    if (dh) {
+        const int k = threadIdx.x & 63, tb = threadIdx.x >> 6;
+        float acc[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+        for (int n = 0; n < kHdN; ++n) {
+            const float wv = ws[n * (kHdSlab + 1) + k];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) acc[i] = fmaf(os[(tb * 16 + i) * kHdNPad + n], wv, acc[i]);
+        }
+        const int cl = k / g.HW, hw = k - cl * g.HW;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const int b = tb * 16 + i;
+            if (b < batch) dh[(size_t)b * g.F + (size_t)hw * g.C + c0 + cl] = __float2bfloat16_rn(acc[i]);
+        }
+    }
+}
+
+static int head_geom(const char *who, int batch, int channels, int hw, HeadGeom &g)
+{
+    HG_REQUIRE(batch > 0 && batch <= kHdMaxB, HG_ERR_UNSUPPORTED, "%s: batch must be 1..%d per call (got %d)", who, kHdMaxB, batch);
+    HG_REQUIRE(channels > 0 && hw > 0 && (hw <= kHdSlab ? kHdSlab % hw == 0 : false), HG_ERR_UNSUPPORTED,
+               "%s: H*W must divide %d (got %d)", who, kHdSlab, hw);
+    g.C = channels; g.HW = hw; g.cs = kHdSlab / hw; g.F = channels * hw;
+    HG_REQUIRE(channels % g.cs == 0, HG_ERR_UNSUPPORTED, "%s: channels %% %d != 0", who, g.cs);
+    g.slabs = channels / g.cs;
+    return HG_OK;
+}
+
+static int c0_geom(const char *who, int batch, int cin, int cout, int size, int &tiles, int &grid)
+{
+    HG_REQUIRE(batch > 0 && size > 0, HG_ERR_INVALID_ARG, "%s: dims must be positive", who);
+    HG_REQUIRE(cin == kC0Cin && cout == kC0Cout, HG_ERR_UNSUPPORTED, "%s: only Conv2d(3 -> 64) is built (got %d -> %d)", who, cin, cout);
+    HG_REQUIRE(size % (2 * kC0TW) == 0, HG_ERR_UNSUPPORTED, "%s: image size must be a multiple of %d (got %d)", who, 2 * kC0TW, size);
+    const int S2 = size / 2;
+    tiles = batch * (S2 / kC0TH) * (S2 / kC0TW);
+    grid = tiles < 2 * sm_count() ? tiles : 2 * sm_count();
+    return HG_OK;
+}
+
+}  // namespace hg
+
+using namespace hg;
+
+extern "C" int hg_dconv0_fwd(const float *x, const float *w, const float *bias, void *y_s2d, int batch, int cin, int cout, int size,
+                             float neg_slope, void *stream)
+{
+    HG_REQUIRE(x && w && bias && y_s2d, HG_ERR_INVALID_ARG, "hg_dconv0_fwd: null pointer");
+    int tiles, grid;
+    int rc = c0_geom("hg_dconv0_fwd", batch, cin, cout, size, tiles, grid);
+    if (rc) return rc;
+    dconv0_fwd_kernel<<<grid, kC0Threads, 0, static_cast<cudaStream_t>(stream)>>>(x, w, bias, static_cast<__nv_bfloat16 *>(y_s2d), size,
+                                                                                 tiles, neg_slope);
+    return check_launch("hg_dconv0_fwd");
+}
+
+extern "C" long long hg_dconv0_bwd_workspace_bytes(int batch, int size)
+{
+    if (batch <= 0 || size <= 0 || size % (2 * kC0TW)) return -1;
+    return (long long)2 * sm_count() * kC0Cout * 96 * (long long)sizeof(float);
+}
+
+extern "C" int hg_dconv0_bwd(const float *x, const float *w, const void *y_s2d, const void *dy_s2d, float *dx, float *dw, float *dbias,
+                             void *workspace, long long workspace_bytes, int batch, int cin, int cout, int size, float neg_slope,
+                             int accumulate, void *stream)
+{
+    HG_REQUIRE(x && w && y_s2d && dy_s2d, HG_ERR_INVALID_ARG, "hg_dconv0_bwd: null pointer");
+    HG_REQUIRE((dw == nullptr) == (dbias == nullptr), HG_ERR_INVALID_ARG, "hg_dconv0_bwd: dw and dbias come as a pair");
+    int tiles, grid;
+    int rc = c0_geom("hg_dconv0_bwd", batch, cin, cout, size, tiles, grid);
+    if (rc) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const __nv_bfloat16 *yp = static_cast<const __nv_bfloat16 *>(y_s2d), *gp = static_cast<const __nv_bfloat16 *>(dy_s2d);
+    if (dw) {
+        int g = grid < sm_count() ? grid : sm_count();          // one CTA per SM: each writes one partial
+        HG_REQUIRE(workspace && workspace_bytes >= (long long)g * kC0Cout * 96 * (long long)sizeof(float), HG_ERR_INVALID_ARG,
+                   "hg_dconv0_bwd: workspace smaller than hg_dconv0_bwd_workspace_bytes()");
+        float *part = static_cast<float *>(workspace);
+        dconv0_bwd_w_kernel<<<g, kC0Threads, 0, st>>>(x, yp, gp, part, size, tiles, neg_slope);
+        rc = check_launch("hg_dconv0_bwd(dw)");
+        if (rc) return rc;
+        dconv0_bwd_w_reduce_kernel<<<(kC0Cout * 96 + 255) / 256, 256, 0, st>>>(part, g, dw, dbias, accumulate);
+        rc = check_launch("hg_dconv0_bwd(reduce)");
+        if (rc) return rc;
+    }
+    if (dx) {
+        constexpr size_t smem = (size_t)kC0HaloH * kC0HaloW * kC0XPitch + 25 * 4 * 32 * sizeof(uint2) +
+                                (size_t)kC0Cin * (2 * kC0TH) * (2 * kC0TW + 1) * sizeof(float);
+        static bool attr = false;
+        if (!attr) {
+            cudaFuncSetAttribute(dconv0_bwd_x_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            attr = true;
+        }
+        dconv0_bwd_x_kernel<<<grid, kC0Threads, smem, st>>>(yp, gp, w, dx, size, tiles, neg_slope);
+        rc = check_launch("hg_dconv0_bwd(dx)");
+    }
+    return rc;
+}
+
+static size_t hd_fwd_smem() { return (size_t)(kHdMaxB * kHdSlab + kHdNPad * (kHdSlab + 1)) * sizeof(float); }
+static size_t hd_bwd_smem() { return hd_fwd_smem() + (size_t)kHdMaxB * kHdNPad * sizeof(float); }
+
+extern "C" long long hg_dheads_workspace_bytes(int batch, int channels, int hw, int zdim)
+{
+    HeadGeom g;
+    if (head_geom("hg_dheads_workspace_bytes", batch, channels, hw, g) || zdim <= 0) return -1;
+    // forward: slab partials; backward: dt3 (B, zdim) + dO (B, 132)
+    const long long fwd = (long long)g.slabs * kHdMaxB * kHdLd * 4, bwd = (long long)batch * (zdim + kHdLd) * 4;
+    return fwd > bwd ? fwd : bwd;
+}
+
+extern "C" int hg_dheads_fwd(const void *h, const float *w1, const float *b1, const float *w2, const float *b2, const float *w3,
+                             const float *b3, float *logits, float *t2, float *z_pred, void *workspace, long long workspace_bytes,
+                             int batch, int channels, int hw, int zdim, float neg_slope, void *stream)
+{
+    HG_REQUIRE(h && w1 && b1 && w2 && b2 && w3 && b3 && logits && t2 && z_pred && workspace, HG_ERR_INVALID_ARG, "hg_dheads_fwd: null pointer");
+    HeadGeom g;
+    int rc = head_geom("hg_dheads_fwd", batch, channels, hw, g);
+    if (rc) return rc;
+    HG_REQUIRE(zdim > 0 && workspace_bytes >= hg_dheads_workspace_bytes(batch, channels, hw, zdim), HG_ERR_INVALID_ARG,
+               "hg_dheads_fwd: workspace smaller than hg_dheads_workspace_bytes()");
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(dheads_fwd_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hd_fwd_smem());
+        cudaFuncSetAttribute(dheads_bwd_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hd_bwd_smem());
+        attr = true;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    float *part = static_cast<float *>(workspace);
+    dheads_fwd_partial_kernel<<<g.slabs, kHdThreads, hd_fwd_smem(), st>>>(static_cast<const __nv_bfloat16 *>(h), w1, w2, part, g, batch);
+    rc = check_launch("hg_dheads_fwd(partial)");
+    if (rc) return rc;
+    dheads_fwd_finish_kernel<<<batch, 128, 0, st>>>(part, g.slabs, b1, b2, w3, b3, logits, t2, z_pred, zdim, neg_slope);
+    return check_launch("hg_dheads_fwd(finish)");
+}
+
+extern "C" int hg_dheads_bwd(const void *h, const float *w1, const float *w2, const float *w3, const float *t2, const float *z_pred,
+                             const float *dlogits, const float *dz_pred, void *dh, float *dw1, float *db1, float *dw2, float *db2,
+                             float *dw3, float *db3, void *workspace, long long workspace_bytes, int batch, int channels, int hw,
+                             int zdim, float neg_slope, void *stream)
+{
+    HG_REQUIRE(h && w1 && w2 && w3 && t2 && z_pred && workspace, HG_ERR_INVALID_ARG, "hg_dheads_bwd: null pointer");
+    const bool params = dw1 != nullptr;
+    HG_REQUIRE(params == (db1 != nullptr) && params == (dw2 != nullptr) && params == (db2 != nullptr) && params == (dw3 != nullptr) &&
+                   params == (db3 != nullptr), HG_ERR_INVALID_ARG, "hg_dheads_bwd: the six parameter gradients come together or not at all");
+    HeadGeom g;
+    int rc = head_geom("hg_dheads_bwd", batch, channels, hw, g);
+    if (rc) return rc;
+    HG_REQUIRE(zdim > 0 && workspace_bytes >= hg_dheads_workspace_bytes(batch, channels, hw, zdim), HG_ERR_INVALID_ARG,
+               "hg_dheads_bwd: workspace smaller than hg_dheads_workspace_bytes()");
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(dheads_bwd_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hd_bwd_smem());
+        attr = true;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    float *dt3 = static_cast<float *>(workspace), *dO = dt3 + (size_t)batch * zdim;
+    dheads_bwd_small_kernel<<<batch, 128, zdim * sizeof(float), st>>>(dlogits, dz_pred, z_pred, t2, w3, dt3, dO, zdim, neg_slope);
+    rc = check_launch("hg_dheads_bwd(small)");
+    if (rc) return rc;
+    if (params) {
+        dheads_bwd_params_kernel<<<zdim + 1, 128, 0, st>>>(dt3, t2, dO, dw3, db3, db2, db1, batch, zdim);
+        rc = check_launch("hg_dheads_bwd(params)");
+        if (rc) return rc;
+    }
+    if (params || dh) {
+        dheads_bwd_big_kernel<<<g.slabs, kHdThreads, hd_bwd_smem(), st>>>(static_cast<const __nv_bfloat16 *>(h), w1, w2, dO, dw1, dw2,
+                                                                          static_cast<__nv_bfloat16 *>(dh), g, batch);
+        rc = check_launch("hg_dheads_bwd(big)");
+    }
+    return rc;
+}

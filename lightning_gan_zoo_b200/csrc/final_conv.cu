@@ -370,15 +370,13 @@ int hg_final_conv_bwd_w_mma(const void *x, const float *out, const float *dout, 
                             cudaStream_t st);
 
 // Which passes run on the tensor-core kernels: bit 0 forward, bit 1 dx, bit 2 dw.  HG_FINAL_CONV_MMA overrides the
-// default (A/B measurements, tests of both implementations); read per call, no state kept.  Measured on B200 at B = 64
+// default (A/B measurements, tests of both implementations; hg_set_option).  Measured on B200 at B = 64
 // (profiles/r01j_*, r01k_*): training step 1.916 ms with all three (mask 7), 1.931 ms with the forward only (mask 1);
 // the forward kernel alone 43.5 us vs 56.7 us for the SIMT kernel.
-constexpr int kFcMmaDefault = 7;
 static int fc_mma_mask(int cin, int cout, int size)
 {
     if (!hg_final_conv_mma_supported(cin, cout, size)) return 0;
-    const char *e = getenv("HG_FINAL_CONV_MMA");
-    return (e && e[0]) ? atoi(e) : kFcMmaDefault;
+    return option(kOptFinalConvMma);
 }
 
 static int final_check(const char *who, int batch, int cin, int cout, int size)

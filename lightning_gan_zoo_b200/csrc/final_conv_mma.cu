@@ -21,6 +21,7 @@
 // pitches are chosen = 4 (mod 32) words, which makes the 8 x 4 (g, q) pattern of a warp hit 32 distinct banks.
 // Deterministic (fixed summation order), no atomics.  Selected by final_conv.cu (HG_FINAL_CONV_MMA).
 #include "hg_common.cuh"
+#include "mma_sync.cuh"
 
 namespace hg {
 
@@ -32,12 +33,6 @@ constexpr int kFmHaloPad = (kFmHaloPix + 15) / 16 * 16; // 352 = 22 m16 tiles
 constexpr int kFmXPitch = kFmC * 2 + 16;                // bytes per staged pixel (36 words)
 constexpr int kFmTPitch = 29;                           // floats per T row (odd: conflict-free gather)
 
-__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1)
-{
-    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
 
 __device__ __forceinline__ void split_bf16(float v, __nv_bfloat16 &hi, __nv_bfloat16 &lo)
 {
@@ -45,7 +40,6 @@ __device__ __forceinline__ void split_bf16(float v, __nv_bfloat16 &hi, __nv_bflo
     lo = __float2bfloat16_rn(v - __bfloat162float(hi));
 }
 
-__device__ __forceinline__ uint32_t lds32(const unsigned char *p) { return *reinterpret_cast<const uint32_t *>(p); }
 
 // Stage the (TH+2) x (TW+2) halo tile of x (NHWC bf16, C = 64) as [pixel][C] with kFmXPitch bytes per pixel; pixels
 // outside the image and the pad rows up to kFmHaloPad are zero.

@@ -29,6 +29,22 @@ inline int check_launch(const char *what)
     return HG_OK;
 }
 
+// ---- tuning options ------------------------------------------------------------------------------
+// Process-wide switches between EQUIVALENT kernels (A/B measurements, tests of both implementations of a pass).  Each is
+// read from the environment variable HG_<NAME> once, when the library first needs it, and can be changed afterwards only
+// through hg_set_option(); no kernel reads the environment at launch time.  They never change results beyond the
+// documented tolerances.  (defined in c_api.cu)
+enum Option {
+    kOptAdainClNoCluster = 0,   // 1: channels-last AdaIN on the chunked two-kernel path only
+    kOptAdainClClusterBwd,      // 1: cluster single-pass kernel for the channels-last AdaIN backward
+    kOptTapGemmDual,            // -1 auto, 0 / 1: force one / two tap-GEMM CTAs per SM
+    kOptFinalConvMma,           // bit mask: final layer passes on the mma.sync kernels (1 fwd, 2 dx, 4 dw)
+    kOptRotateSlab32,           // 1: 32^3 rotate forward on source-slab tiles
+    kOptRotateGatherBwd,        // 1: 32^3 rotate backward as a table-free per-voxel gather
+    kOptCount
+};
+int option(Option o);
+
 // ---- element access -----------------------------------------------------------------------------
 template <typename T> __device__ __forceinline__ float to_f32(T v);
 template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }

@@ -312,8 +312,7 @@ bool hg_rotate_slab32_enabled(int channels, int size, int dtype, int batch)
 {
     const int ci = dtype == HG_F32 ? 4 : 8;
     if (size != kSlabS || channels % ci != 0 || channels / ci > 65535 || batch > 65535) return false;
-    const char *e = getenv("HG_ROTATE_SLAB32");
-    return e && e[0] && e[0] != '0';
+    return option(kOptRotateSlab32) != 0;
 }
 
 int hg_rotate_slab32_fwd(const void *vol, const float *a_inv, void *out, int batch, int channels, int dtype, int border,
@@ -331,8 +330,7 @@ int hg_rotate_slab32_fwd(const void *vol, const float *a_inv, void *out, int bat
 bool hg_rotate_gather_bwd_enabled(int size, int batch)
 {
     if (size != 32 || batch > 65535) return false;
-    const char *e = getenv("HG_ROTATE_GATHER_BWD");
-    return e && e[0] && e[0] != '0';
+    return option(kOptRotateGatherBwd) != 0;
 }
 
 int hg_rotate_gather_bwd(const void *grad_out, const float *a_inv, void *grad_vol, int batch, int channels, int size, int logS,

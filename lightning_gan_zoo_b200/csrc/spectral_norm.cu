@@ -168,6 +168,7 @@ template <typename TO> __global__ void __launch_bounds__(256) sn_scale_kernel(co
     }
     const size_t n = (size_t)L.cout * L.K;
     TO *out = static_cast<TO *>(L.out);
+    if (out == nullptr) return;                          // sigma only: the caller folds 1 / sigma into its own weight pack
     if ((L.K & 3) == 0 && sn_aligned16(L.w, out)) {      // four elements per thread and trip: 16-byte loads, 8/16-byte stores
         for (size_t i = ((size_t)blockIdx.x * 256 + threadIdx.x) * 4; i < n; i += (size_t)gridDim.x * 1024) {
             const float4 a = __ldg(reinterpret_cast<const float4 *>(L.w + i));
@@ -298,7 +299,7 @@ extern "C" int hg_spectral_norm_fwd(int layers, const float *const *w, float *co
     int max_k = 0, max_cout = 0;
     size_t max_n = 0;
     for (int i = 0; i < layers; ++i) {
-        HG_REQUIRE(w[i] && u[i] && v[i] && w_out[i] && state[i], HG_ERR_INVALID_ARG, "hg_spectral_norm_fwd: null layer pointer");
+        HG_REQUIRE(w[i] && u[i] && v[i] && state[i], HG_ERR_INVALID_ARG, "hg_spectral_norm_fwd: null layer pointer");
         HG_REQUIRE(cout[i] > 0 && cin[i] > 0 && taps[i] > 0, HG_ERR_INVALID_ARG, "hg_spectral_norm_fwd: non-positive dims");
         SnLayer &L = p.l[i];
         L.w = w[i]; L.u = u[i]; L.v = v[i]; L.out = w_out[i]; L.state = state[i];

@@ -268,17 +268,58 @@ def convt_supported(cin: int, cout: int) -> bool:
     return cin % 128 == 0 and cout % 64 == 0
 
 
+# ---- packed bf16 operand copies of a parameter, refreshed only when the parameter changes -------------------------
+# The GEMM kernels read bf16 copies of the fp32 master weights in their own layouts.  For an nn.Parameter the copies are
+# cached on the parameter object and re-packed IN PLACE (same buffers: captured CUDA graphs keep pointing at them) when
+# its version counter / storage changes, i.e. after an optimizer step -- not on every forward.  Code that updates
+# parameters behind autograd's back (a replayed CUDA graph that contains the optimizer) calls refresh_packed_weights()
+# right after the update, inside the same graph.
+
+def _cached_pack(weight: Tensor, tag, alloc, fill):
+    if not isinstance(weight, torch.nn.Parameter):
+        bufs = alloc()
+        fill(bufs)
+        return bufs
+    cache = weight.__dict__.setdefault("_hg_pack", {})
+    ver = (weight._version, weight.data_ptr())
+    ent = cache.get(tag)
+    if ent is None or ent[1][0].device != weight.device:
+        bufs = alloc()
+        fill(bufs)
+        cache[tag] = [ver, bufs, fill]
+        return bufs
+    if ent[0] != ver:
+        fill(ent[1])
+        ent[0] = ver
+    return ent[1]
+
+
+def refresh_packed_weights(params) -> None:
+    """Re-pack (in place) every cached operand copy of the given parameters -- call right after an optimizer step."""
+    for p in params:
+        cache = getattr(p, "_hg_pack", None)
+        if cache:
+            for ent in cache.values():
+                ent[2](ent[1])
+                ent[0] = (p._version, p.data_ptr())
+
+
 def pack_convt_weight(weight: Tensor, perm: Tuple[int, int] = (0, 0)) -> Tuple[Tensor, Tensor]:
     """torch ConvTranspose weight (Cin, Cout, k..) fp32 -> (w_fwd [t][Cout][Cin], w_dgrad [t][Cin][Cout]) bf16.
     perm = (C, S): input channels re-ordered for the HG_PROJ operand (packed y*C + c <-> torch c*S + S-1-y)."""
     _require_cuda(weight)
-    w = weight.detach().float().contiguous()
-    cin, cout = w.shape[0], w.shape[1]
-    taps = w[0, 0].numel()
-    wf = torch.empty((taps, cout, cin), dtype=torch.bfloat16, device=w.device)
-    wd = torch.empty((taps, cin, cout), dtype=torch.bfloat16, device=w.device)
-    _lib.call("hg_convt_pack_weight", _ptr(w), _ptr(wf), _ptr(wd), cin, cout, taps, perm[0], perm[1], _stream())
-    return wf, wd
+    cin, cout = weight.shape[0], weight.shape[1]
+    taps = weight[0, 0].numel()
+
+    def alloc():
+        return (torch.empty((taps, cout, cin), dtype=torch.bfloat16, device=weight.device),
+                torch.empty((taps, cin, cout), dtype=torch.bfloat16, device=weight.device))
+
+    def fill(bufs):
+        w = weight.detach().float().contiguous()
+        _lib.call("hg_convt_pack_weight", _ptr(w), _ptr(bufs[0]), _ptr(bufs[1]), cin, cout, taps, perm[0], perm[1], _stream())
+
+    return _cached_pack(weight, ("convt", perm), alloc, fill)
 
 
 def convt_wgrad(x_cl: Tensor, dy_s2d: Tensor, wshape, ndim: int, kernel: int, perm: Tuple[int, int] = (0, 0),
@@ -392,65 +433,6 @@ def convt(x_cl: Tensor, weight: Tensor, bias: Optional[Tensor], ndim: int, kerne
     return _ConvT.apply(x_cl, weight, bias, ndim, kernel, neg_slope, perm)
 
 
-class _ConvS2K5(torch.autograd.Function):
-    """y = Conv2d(k5, s2, p2)(x) (no bias) on the tcgen05 tap GEMMs through the transposed-conv duality: the
-    discriminator's convolution (reference core/models/hologan_discriminator.py:12) is the dgrad of
-    ConvTranspose2d(k5, s2, p2, op1) with the same weight tensor (Conv2d (Cout, Cin, 5, 5) == ConvTranspose2d
-    (Cin_T = Cout, Cout_T = Cin, 5, 5)), so
-        forward  = hg_convt_dgrad   (x in space-to-depth layout plays dy_s2d),
-        dx       = hg_convt_fwd     (dy plays x; the result is dx in space-to-depth layout),
-        dw       = hg_convt_wgrad   (dy plays x, x_s2d plays dy_s2d; the result has the Conv2d weight layout).
-    x_s2d: (B, S, S, 4, Cin) bf16 with x_s2d[b, i, j, (py, px), c] = x[b, c, 2i + py, 2j + px]; y: (B, S, S, Cout) bf16."""
-
-    @staticmethod
-    def forward(ctx, x_s2d, weight):
-        _require_cuda(x_s2d, weight)
-        if x_s2d.dtype != torch.bfloat16 or not x_s2d.is_contiguous() or x_s2d.dim() != 5 or x_s2d.shape[3] != 4:
-            raise ValueError("x_s2d must be a contiguous bf16 tensor (B, S, S, 4, Cin)")
-        b, size, cin = x_s2d.shape[0], x_s2d.shape[1], x_s2d.shape[4]
-        cout = weight.shape[0]
-        if tuple(weight.shape[1:]) != (cin, 5, 5):
-            raise ValueError("weight must be (Cout, Cin, 5, 5)")
-        wf, wd = pack_convt_weight(weight)                  # as ConvTranspose2d weight: Cin_T = Cout, Cout_T = Cin
-        y = torch.empty((b, size, size, cout), dtype=torch.bfloat16, device=x_s2d.device)
-        _lib.call("hg_convt_dgrad", _ptr(x_s2d), _ptr(wd), _ptr(y), b, cout, cin, 2, size, 5, _stream())
-        ctx.save_for_backward(x_s2d, wf)
-        ctx.meta = (b, size, cin, cout, tuple(weight.shape))
-        return y
-
-    @staticmethod
-    def backward(ctx, dy):
-        x_s2d, wf = ctx.saved_tensors
-        b, size, cin, cout, wshape = ctx.meta
-        dy = dy.contiguous()
-        dx = dw = None
-        if ctx.needs_input_grad[0]:
-            dx = torch.empty_like(x_s2d)
-            _lib.call("hg_convt_fwd", _ptr(dy), _ptr(wf), _ptr(None), _ptr(dx), b, cout, cin, 2, size, 5, ctypes.c_float(1.0),
-                      _stream())
-        if ctx.needs_input_grad[1]:
-            dw = convt_wgrad(dy, x_s2d, wshape, 2, 5)
-        return dx, dw
-
-
-def conv5x5_s2(x_s2d: Tensor, weight: Tensor) -> Tensor:
-    """Conv2d(kernel 5, stride 2, padding 2, no bias) of a space-to-depth input on the tcgen05 kernels."""
-    return _ConvS2K5.apply(x_s2d, weight)
-
-
-def conv5x5_s2_supported(cin: int, cout: int, size_out: int, batch: int) -> bool:
-    """Shapes the dual transposed-conv kernels cover: forward needs Cin % 64 == 0 and Cout % 16 == 0, dx the converse
-    with 64 / 16 swapped, dw Cout % 128 == 0 and Cin % 64 == 0; rows tile into 128-position boxes."""
-    rows = size_out * size_out
-    return cin % 64 == 0 and cout % 128 == 0 and (rows % 128 == 0 or (128 % rows == 0 and (batch * rows) % 128 == 0))
-
-
-def nhwc_to_s2d(x: Tensor) -> Tensor:
-    """(B, H, W, C) channels-last -> (B, H/2, W/2, 4, C) space-to-depth (one copy)."""
-    b, h, w, c = x.shape
-    return x.reshape(b, h // 2, 2, w // 2, 2, c).permute(0, 1, 3, 2, 4, 5).reshape(b, h // 2, w // 2, 4, c).contiguous()
-
-
 # ---- layout glue (pure data movement) -------------------------------------------------------------
 
 def s2d_to_nc(y_s2d: Tensor, ndim: int) -> Tensor:
@@ -482,7 +464,10 @@ class _AdaInChannelsLast(torch.autograd.Function):
         b, size, c = x.shape[0], x.shape[1], x.shape[-1]
         sp, bp, sbs = _style_ptrs(scale, bias, c) if scale is not None else (_ptr(None), _ptr(None), 0)
         up = 2 if classes > 1 else 1
-        y = torch.empty((b,) + (up * size,) * ndim + (c,), dtype=torch.bfloat16, device=x.device)
+        if classes == -4:       # plain (B, S, S, C) in, 2x2 space-to-depth order out: the next stride-2 conv's operand
+            y = torch.empty((b, size // 2, size // 2, 4, c), dtype=torch.bfloat16, device=x.device)
+        else:
+            y = torch.empty((b,) + (up * size,) * ndim + (c,), dtype=torch.bfloat16, device=x.device)
         mean = torch.empty((b, c), dtype=torch.float32, device=x.device)
         rstd = torch.empty((b, c), dtype=torch.float32, device=x.device)
         nbytes = _lib.load().hg_adain_cl_workspace_bytes(b, c, ndim, size, classes)
@@ -525,10 +510,11 @@ def adain_act_channels_last(x: Tensor, scale: Tensor, bias: Optional[Tensor], nd
     return _AdaInChannelsLast.apply(x, scale, bias, ndim, classes, neg_slope, eps, False)
 
 
-def instance_norm_act_channels_last(x_nhwc: Tensor, neg_slope: float = 0.2, eps: float = 1e-5) -> Tensor:
+def instance_norm_act_channels_last(x_nhwc: Tensor, neg_slope: float = 0.2, eps: float = 1e-5, s2d_out: bool = False) -> Tensor:
     """InstanceNorm2d (no affine, biased variance) + LeakyReLU on a channels-last (B,H,W,C) bf16 tensor, H == W
-    -- the discriminator's norm + activation (reference core/models/hologan_discriminator.py:16-17,21-22)."""
-    return _AdaInChannelsLast.apply(x_nhwc, None, None, 2, 1, neg_slope, eps, True)
+    -- the discriminator's norm + activation (reference core/models/hologan_discriminator.py:16-17,21-22).
+    `s2d_out`: the result is stored as (B, H/2, W/2, 4, C) (2x2 space-to-depth order), the input layout of `conv5s2_sn`."""
+    return _AdaInChannelsLast.apply(x_nhwc, None, None, 2, -4 if s2d_out else 1, neg_slope, eps, True)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -789,3 +775,216 @@ def spectral_norm_weights(weights, us, vs, power_iteration: bool = True, out_dty
     when `power_iteration` -- torch.nn.utils.spectral_norm's training-mode forward as the reference uses it
     (core/models/hologan_discriminator.py:15).  Outputs have `out_dtype` and the weights' memory format."""
     return _SpectralNormWeights.apply(list(us), list(vs), power_iteration, out_dtype, eps, *weights)
+
+
+# ------------------------------------------------------------------------------------------------
+# a14 / f1: the discriminator on hand-written kernels (first conv, spectral-norm conv blocks, heads)
+# ------------------------------------------------------------------------------------------------
+
+class _DConv0(torch.autograd.Function):
+    """y_s2d = leaky_relu(Conv2d(3 -> 64, k5, s2, p2)(x) + bias): x (B,3,S,S) fp32 NCHW -> (B,S/4,S/4,4,64) bf16."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, neg_slope):
+        _require_cuda(x, weight, bias)
+        x = x.float().contiguous()
+        w = weight.detach().float().contiguous()
+        bb = bias.detach().float().contiguous()
+        b, cin, s = x.shape[0], x.shape[1], x.shape[2]
+        cout = w.shape[0]
+        if x.dim() != 4 or x.shape[3] != s or tuple(w.shape[1:]) != (cin, 5, 5):
+            raise ValueError("dconv0: x must be (B, Cin, S, S) and weight (Cout, Cin, 5, 5)")
+        y = torch.empty((b, s // 4, s // 4, 4, cout), dtype=torch.bfloat16, device=x.device)
+        _lib.call("hg_dconv0_fwd", _ptr(x), _ptr(w), _ptr(bb), _ptr(y), b, cin, cout, s, ctypes.c_float(neg_slope), _stream())
+        ctx.save_for_backward(x, w, y)
+        ctx.neg_slope = float(neg_slope)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, y = ctx.saved_tensors
+        b, cin, s = x.shape[0], x.shape[1], x.shape[2]
+        cout = w.shape[0]
+        dy = dy.contiguous()
+        want_dx, want_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
+        dx = torch.empty_like(x) if want_dx else None
+        dw = torch.empty_like(w) if want_dw else None
+        db = torch.empty(cout, dtype=torch.float32, device=x.device) if want_dw else None
+        nbytes = _lib.load().hg_dconv0_bwd_workspace_bytes(b, s)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+        _lib.call("hg_dconv0_bwd", _ptr(x), _ptr(w), _ptr(y), _ptr(dy), _ptr(dx), _ptr(dw), _ptr(db), _ptr(ws), nbytes, b, cin,
+                  cout, s, ctypes.c_float(ctx.neg_slope), 0, _stream())
+        return dx, dw, db, None
+
+
+def dconv0(x: Tensor, weight: Tensor, bias: Tensor, neg_slope: float = 0.2) -> Tensor:
+    """First discriminator convolution + LeakyReLU (reference core/models/hologan_discriminator.py:30,58) on the
+    warp-level tensor cores; the result is in the space-to-depth order `conv5s2_sn` reads."""
+    return _DConv0.apply(x, weight, bias, neg_slope)
+
+
+def dconv0_supported(cin: int, cout: int, size: int) -> bool:
+    return cin == 3 and cout == 64 and size % 32 == 0
+
+
+def spectral_norm_sigma(weights, us, vs, power_iteration: bool = True, eps: float = 1e-12):
+    """Power iteration + sigma for a group of weights WITHOUT materialising W / sigma: returns one state tensor per
+    layer ([0] sigma, [1] 1 / sigma, then the u and v used), consumed by `conv5s2_sn` (which folds 1 / sigma into its
+    bf16 weight pack) and by its backward.  `us` / `vs` are updated in place when `power_iteration` (training-mode
+    forward of torch.nn.utils.spectral_norm, reference core/models/hologan_discriminator.py:15).  No autograd."""
+    with torch.no_grad():
+        weights = [w.detach() for w in weights]
+        _require_cuda(*weights, *us, *vs)
+        n = len(weights)
+        channels_last, cout, cin, taps = _sn_geometry(weights)
+        if channels_last:
+            raise ValueError("spectral_norm_sigma: contiguous weights only")
+        lib = _lib.load()
+        ci_arr, co_arr, t_arr = _c_array(ctypes.c_int, cin), _c_array(ctypes.c_int, cout), _c_array(ctypes.c_int, taps)
+        nbytes = lib.hg_spectral_norm_workspace_bytes(n, co_arr, ci_arr, t_arr)
+        dev = weights[0].device
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        states = [torch.empty(lib.hg_spectral_norm_state_floats(co, ci, t), dtype=torch.float32, device=dev)
+                  for co, ci, t in zip(cout, cin, taps)]
+        vp = ctypes.c_void_p
+        _lib.call("hg_spectral_norm_fwd", n, _c_array(vp, [w.data_ptr() for w in weights]),
+                  _c_array(vp, [u.data_ptr() for u in us]), _c_array(vp, [v.data_ptr() for v in vs]),
+                  _c_array(vp, [0] * n), _c_array(vp, [s.data_ptr() for s in states]),
+                  co_arr, ci_arr, t_arr, 0, int(bool(power_iteration)), float(eps), HG_F32, _ptr(ws), nbytes, _stream())
+    return states
+
+
+class _Conv5s2SN(torch.autograd.Function):
+    """y = Conv2d(k5, s2, p2)(x, weight_orig / sigma) (no bias) on the tcgen05 tap GEMMs; x_s2d (B,S,S,4,Cin) bf16 ->
+    y (B,S,S,Cout) bf16.  `state` comes from `spectral_norm_sigma` (None: plain weight).  The backward produces the
+    gradient w.r.t. weight_orig (spectral-norm backward included)."""
+
+    @staticmethod
+    def forward(ctx, x_s2d, weight, state):
+        _require_cuda(x_s2d, weight)
+        if x_s2d.dtype != torch.bfloat16 or not x_s2d.is_contiguous() or x_s2d.dim() != 5 or x_s2d.shape[3] != 4:
+            raise ValueError("x_s2d must be a contiguous bf16 tensor (B, S, S, 4, Cin)")
+        b, size, cin = x_s2d.shape[0], x_s2d.shape[1], x_s2d.shape[4]
+        w = weight.detach()
+        cout = w.shape[0]
+        if w.dtype != torch.float32 or not w.is_contiguous() or tuple(w.shape[1:]) != (cin, 5, 5):
+            raise ValueError("weight must be a contiguous fp32 (Cout, Cin, 5, 5) tensor")
+        dev = x_s2d.device
+        # bf16 copies of the UN-normalised weight (cached: packed once per optimizer step); 1 / sigma, which moves with
+        # every forward's power iteration, is applied in the GEMM epilogue: conv(x, W / sigma) = conv(x, W) / sigma
+        wk, wt = _cached_pack(weight, "conv5s2",
+                              lambda: (torch.empty((25, cout, cin), dtype=torch.bfloat16, device=dev),
+                                       torch.empty((25, cin, cout), dtype=torch.bfloat16, device=dev)),
+                              lambda bufs: _lib.call("hg_conv5s2_pack_weight", _ptr(weight.detach()), _ptr(None), _ptr(bufs[0]),
+                                                     _ptr(bufs[1]), cin, cout, _stream()))
+        inv_sigma = ctypes.c_void_p(0 if state is None else state.data_ptr() + 4)
+        nbytes = _lib.load().hg_conv5s2_workspace_bytes(b, cin, cout, size)
+        if nbytes < 0:
+            raise _lib.HologanB200Error(f"hg_conv5s2: unsupported shape Cin={cin} Cout={cout} size={size}")
+        ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=dev)
+        y = torch.empty((b, size, size, cout), dtype=torch.bfloat16, device=dev)
+        _lib.call("hg_conv5s2_fwd", _ptr(x_s2d), _ptr(wk), inv_sigma, _ptr(y), _ptr(ws), nbytes, b, cin, cout, size, _stream())
+        ctx.save_for_backward(x_s2d, wt, w, state)
+        ctx.meta = (b, size, cin, cout, nbytes)
+        ctx.weight_param = weight if isinstance(weight, torch.nn.Parameter) else None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x_s2d, wt, w, state = ctx.saved_tensors
+        b, size, cin, cout, nbytes = ctx.meta
+        dy = dy.contiguous()
+        dev = dy.device
+        ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=dev)
+        dx = dw = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x_s2d)
+            inv_sigma = ctypes.c_void_p(0 if state is None else state.data_ptr() + 4)
+            _lib.call("hg_conv5s2_dx", _ptr(dy), _ptr(wt), inv_sigma, _ptr(dx), _ptr(ws), nbytes, b, cin, cout, size, _stream())
+        if ctx.needs_input_grad[1]:
+            dwn = torch.empty_like(w)                               # gradient w.r.t. the normalised weight
+            _lib.call("hg_conv5s2_dw", _ptr(dy), _ptr(x_s2d), _ptr(dwn), _ptr(ws), nbytes, b, cin, cout, size, 0, _stream())
+            if state is None:
+                dw = dwn
+            else:
+                target = _direct_grad_target(ctx.weight_param, w.shape)[0] if ctx.weight_param is not None else None
+                direct = target is not None and target.stride() == w.stride()
+                dw_orig = target if direct else torch.empty_like(w)
+                lib = _lib.load()
+                co_arr, ci_arr, t_arr = _c_array(ctypes.c_int, [cout]), _c_array(ctypes.c_int, [cin]), _c_array(ctypes.c_int, [25])
+                sn_bytes = lib.hg_spectral_norm_workspace_bytes(1, co_arr, ci_arr, t_arr)
+                sn_ws = torch.empty(sn_bytes, dtype=torch.uint8, device=dev)
+                vp = ctypes.c_void_p
+                _lib.call("hg_spectral_norm_bwd", 1, _c_array(vp, [dwn.data_ptr()]), _c_array(vp, [w.data_ptr()]),
+                          _c_array(vp, [state.data_ptr()]), _c_array(vp, [dw_orig.data_ptr()]), co_arr, ci_arr, t_arr,
+                          int(direct), HG_F32, _ptr(sn_ws), sn_bytes, _stream())
+                dw = None if direct else dw_orig
+        return dx, dw, None
+
+
+def conv5s2_sn(x_s2d: Tensor, weight_orig: Tensor, state: Optional[Tensor]) -> Tensor:
+    """Spectrally normalised Conv2d(kernel 5, stride 2, padding 2, no bias) of a space-to-depth input (reference
+    core/models/hologan_discriminator.py:12-15,20) on the tcgen05 kernels."""
+    return _Conv5s2SN.apply(x_s2d, weight_orig, state)
+
+
+def conv5s2_supported(cin: int, cout: int, size_out: int) -> bool:
+    return cin % 64 == 0 and cout % 128 == 0 and size_out >= 2 and (size_out & (size_out - 1)) == 0
+
+
+class _DHeads(torch.autograd.Function):
+    """(logits (B,1), z_pred (B,zdim)) fp32 from the last block's channels-last activation h (B,H,W,C) bf16."""
+
+    @staticmethod
+    def forward(ctx, h, w1, b1, w2, b2, w3, b3, neg_slope):
+        _require_cuda(h, w1, w2, w3)
+        if h.dtype != torch.bfloat16 or not h.is_contiguous() or h.dim() != 4:
+            raise ValueError("h must be a contiguous bf16 (B, H, W, C) tensor")
+        b, hw, c = h.shape[0], h.shape[1] * h.shape[2], h.shape[3]
+        zdim = w3.shape[0]
+        ps = [t.detach().float().contiguous() for t in (w1, b1, w2, b2, w3, b3)]
+        if tuple(ps[0].shape) != (1, c * hw) or tuple(ps[2].shape) != (128, c * hw) or ps[4].shape[1] != 128:
+            raise ValueError("dheads: linear1 (1, F), linear2 (128, F), linear3 (zdim, 128) with F = C * H * W")
+        dev = h.device
+        nbytes = _lib.load().hg_dheads_workspace_bytes(b, c, hw, zdim)
+        if nbytes < 0:
+            raise _lib.HologanB200Error(f"hg_dheads: unsupported shape B={b} C={c} HW={hw}")
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        logits = torch.empty((b, 1), dtype=torch.float32, device=dev)
+        t2 = torch.empty((b, 128), dtype=torch.float32, device=dev)
+        zp = torch.empty((b, zdim), dtype=torch.float32, device=dev)
+        _lib.call("hg_dheads_fwd", _ptr(h), *[_ptr(t) for t in ps], _ptr(logits), _ptr(t2), _ptr(zp), _ptr(ws), nbytes, b, c, hw,
+                  zdim, ctypes.c_float(neg_slope), _stream())
+        ctx.save_for_backward(h, ps[0], ps[2], ps[4], t2, zp)
+        ctx.meta = (b, c, hw, zdim, float(neg_slope), nbytes)
+        ctx.set_materialize_grads(False)
+        return logits, zp
+
+    @staticmethod
+    def backward(ctx, dlogits, dzp):
+        h, w1, w2, w3, t2, zp = ctx.saved_tensors
+        b, c, hw, zdim, neg_slope, nbytes = ctx.meta
+        dev = h.device
+        dlogits = None if dlogits is None else dlogits.float().contiguous()
+        dzp = None if dzp is None else dzp.float().contiguous()
+        want_params = any(ctx.needs_input_grad[1:7])
+        dh = torch.empty_like(h) if ctx.needs_input_grad[0] else None
+        grads = [None] * 6
+        if want_params:
+            grads = [torch.empty_like(w1), torch.empty(1, dtype=torch.float32, device=dev), torch.empty_like(w2),
+                     torch.empty(128, dtype=torch.float32, device=dev), torch.empty_like(w3),
+                     torch.empty(zdim, dtype=torch.float32, device=dev)]
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        _lib.call("hg_dheads_bwd", _ptr(h), _ptr(w1), _ptr(w2), _ptr(w3), _ptr(t2), _ptr(zp), _ptr(dlogits), _ptr(dzp), _ptr(dh),
+                  *[_ptr(g) for g in grads], _ptr(ws), nbytes, b, c, hw, zdim, ctypes.c_float(neg_slope), _stream())
+        return (dh,) + tuple(grads) + (None,)
+
+
+def dheads(h: Tensor, w1, b1, w2, b2, w3, b3, neg_slope: float = 0.2) -> Tuple[Tensor, Tensor]:
+    """logits = linear1(flat(h)), z_pred = tanh(linear3(leaky_relu(linear2(flat(h))))) with flat = the reference's
+    (c, h, w) flatten (core/models/hologan_discriminator.py:60-68); h is channels-last."""
+    return _DHeads.apply(h, w1, b1, w2, b2, w3, b3, neg_slope)
+
+
+def dheads_supported(batch: int, channels: int, hw: int) -> bool:
+    return 1 <= batch <= 64 and hw <= 64 and 64 % hw == 0 and channels % (64 // hw) == 0

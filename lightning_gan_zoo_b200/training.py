@@ -172,9 +172,9 @@ class HologanTrainer:
         if self.world > 1:               # identical replicas even if a rank's RNG had diverged
             for t in list(self.generator.state_dict().values()) + list(self.discriminator.state_dict().values()):
                 dist.broadcast(t, src=0)
-        if self.device.type == "cuda" and compute_dtype == torch.bfloat16 and os.environ.get("HG_D_TCGEN05", "0") in ("", "0"):
-            # bf16 pipeline: the discriminator's convolutions run NHWC (cuDNN's native tensor-core layout), so
-            # its weights live channels-last too -- no per-call layout conversions
+        if self.device.type == "cuda" and compute_dtype == torch.bfloat16 and os.environ.get("HG_D_LIBRARY", "0") not in ("", "0"):
+            # A/B switch HG_D_LIBRARY=1: the discriminator's convolutions on cuDNN run NHWC (its native tensor-core
+            # layout), so the weights live channels-last too; the default (hand-written kernels) keeps torch's layout
             self.discriminator.to(memory_format=torch.channels_last)
         sn_weights = [blk.conv2d.weight_orig for blk in self.discriminator.blocks] if self.device.type == "cuda" else ()
         self.d_grads = _FlatGrads(self.discriminator.parameters(), accumulate_into=sn_weights)
@@ -314,6 +314,8 @@ class HologanTrainer:
         grads.finish()
         grads.all_reduce_mean(self.world)
         opt.step()
+        if self.device.type == "cuda":          # bf16 operand copies of the stepped network: once per update, not per forward
+            ops.refresh_packed_weights((self.discriminator if idx == 0 else self.generator).parameters())
         return loss.detach()
 
     # ---- CUDA graphs: the whole step (forward, backward, gradient all-reduce, Adam) replayed as one launch ----
@@ -360,7 +362,12 @@ class HologanTrainer:
                     for k, v in stt.items():
                         if isinstance(v, torch.Tensor):
                             v.zero_() if f else v.copy_(saved[id(p)][k])
+        self._refresh_packs()                  # the packed operand copies follow the rolled-back parameters
         self._graphs = graphs
+
+    def _refresh_packs(self):
+        if self.device.type == "cuda":
+            ops.refresh_packed_weights(list(self.generator.parameters()) + list(self.discriminator.parameters()))
 
     def _replay(self, real, z, view, idx):
         st = self._static
@@ -412,6 +419,7 @@ class HologanTrainer:
         if extra:
             self.noise_rng.set_state(extra["noise_rng"])
             self.view_rng.set_state(extra["view_rng"])
+        self._refresh_packs()
         self._graphs = None
 
     def end_epoch(self):

@@ -359,20 +359,24 @@ def spectral_weight(w_orig: Tensor, u: Tensor, v: Tensor, training: bool
 
 
 def discriminator_forward(p: Dict[str, Tensor], x: Tensor, training: bool = True,
-                          update_buffers: bool = True) -> Tuple[Tensor, Tensor]:
+                          update_buffers: bool = True, bf16_storage: bool = False) -> Tuple[Tensor, Tensor]:
     """Discriminator.forward, hologan_discriminator.py:56-70 (+ BasicBlock :19-23).
     `p` holds the reference state_dict keys (weight_orig / weight_u / weight_v for the
     spectrally-normalised convs).  In training mode the u/v entries of `p` are replaced
     by the power-iteration result, like the reference's buffers."""
-    h = F.leaky_relu(F.conv2d(x, p["conv2d.weight"], p["conv2d.bias"], stride=2, padding=2), 0.2)
+    # bf16_storage: NOT the reference -- the same fp32 arithmetic with the tensors a bf16 pipeline keeps in memory
+    # (activations, their gradients, convolution operands) rounded to bf16 where they are stored: the error floor of
+    # any bf16-operand implementation (see generator_forward)
+    store, operand = (_StoreBf16.apply, _OperandBf16.apply) if bf16_storage else (_ident, _ident)
+    h = store(F.leaky_relu(F.conv2d(operand(x), operand(p["conv2d.weight"]), p["conv2d.bias"], stride=2, padding=2), 0.2))
     for i in range(3):
         k = f"blocks.{i}.conv2d."
         w, u, v = spectral_weight(p[k + "weight_orig"], p[k + "weight_u"], p[k + "weight_v"], training)
         if training and update_buffers:
             p[k + "weight_u"], p[k + "weight_v"] = u, v
-        h = F.conv2d(h, w, p[k + "bias"], stride=2, padding=2)
+        h = store(F.conv2d(h, operand(w), p[k + "bias"], stride=2, padding=2))
         h = F.instance_norm(h, eps=1e-5)                       # InstanceNorm2d defaults (:16)
-        h = F.leaky_relu(h, 0.2)
+        h = store(F.leaky_relu(h, 0.2))
     flat = h.reshape(x.shape[0], -1)
     logits = F.linear(flat, p["linear1.weight"], p["linear1.bias"])
     enc = F.leaky_relu(F.linear(flat, p["linear2.weight"], p["linear2.bias"]), 0.2)

@@ -70,3 +70,18 @@ def c_oracle():
 
 def np_ptr(a):
     return a.ctypes.data_as(ctypes.c_void_p)
+
+
+@pytest.fixture
+def hg_option():
+    """Set tuning options of libhologan_b200.so (hg_set_option) for one test; previous values are restored."""
+    from lightning_gan_zoo_b200 import _lib
+    saved = {}
+
+    def set_(name, value):
+        old = _lib.set_option(name, value)
+        saved.setdefault(name, old)
+
+    yield set_
+    for name, old in saved.items():
+        _lib.set_option(name, old)

@@ -31,7 +31,7 @@ def test_header_symbols_are_exported_and_bound():
 
 
 def test_abi_version():
-    assert _lib.load().hg_abi_version() == 1
+    assert _lib.load().hg_abi_version() == 2
 
 
 def test_argument_validation_without_gpu():

@@ -125,7 +125,7 @@ def test_adain_channels_last(b, ndim, size, c, classes, slope):
 
 @pytest.mark.parametrize("b,ndim,size,c,classes", [(3, 3, 8, 64, 8), (2, 2, 16, 256, 4), (2, 2, 32, 64, 4), (2, 2, 32, 128, 1),
                                                   (2, 2, 16, 512, 4), (3, 3, 4, 128, 8)])
-def test_adain_channels_last_cluster_vs_chunked(b, ndim, size, c, classes, monkeypatch):
+def test_adain_channels_last_cluster_vs_chunked(b, ndim, size, c, classes, hg_option):
     """The single-pass cluster kernels (DSMEM reduction, rows staged in shared memory) against the chunked two-kernel
     path on the same inputs: statistics to fp32 rounding, outputs / gradients to bf16 rounding."""
     gen = torch.Generator().manual_seed(size + c)
@@ -143,11 +143,11 @@ def test_adain_channels_last_cluster_vs_chunked(b, ndim, size, c, classes, monke
         (y.float() * dy.float()).sum().backward()
         return y.detach().float(), xg.grad.float(), sg.grad, bg.grad
 
-    monkeypatch.setenv("HG_ADAIN_CL_CLUSTER_BWD", "1")        # the cluster backward is opt-in (slower than the chunked one)
+    hg_option("ADAIN_CL_CLUSTER_BWD", 1)                     # the cluster backward is opt-in (slower than the chunked one)
     got = run()
-    monkeypatch.setenv("HG_ADAIN_CL_NO_CLUSTER", "1")
+    hg_option("ADAIN_CL_NO_CLUSTER", 1)
     ref = run()
-    monkeypatch.delenv("HG_ADAIN_CL_NO_CLUSTER")
+    hg_option("ADAIN_CL_NO_CLUSTER", 0)
     again = run()
     assert rel_err(got[0], ref[0]) < 2 ** -7 and rel_err(got[1], ref[1]) < 2 ** -6
     assert rel_err(got[2], ref[2]) < 1e-4 and rel_err(got[3], ref[3]) < 1e-4

@@ -105,37 +105,7 @@ def torch_convt(x, w, bias, ndim, kernel):
 K5_CASES = [(2, 5, 4, 128, 64, 16), (2, 5, 4, 256, 128, 8), (2, 5, 8, 512, 256, 4), (2, 5, 3, 128, 64, 16)]
 
 
-@pytest.mark.skipif(os.environ.get("HG_TEST_K5") != "1", reason="run through test_convt_k5_in_child_process")
-@pytest.mark.parametrize("ndim,kernel,batch,cin,cout,size", K5_CASES)
-def test_convt_k5_cases(ndim, kernel, batch, cin, cout, size):
-    test_convt_fwd_dgrad_wgrad(ndim, kernel, batch, cin, cout, size)
-
-
-@pytest.mark.xfail(strict=False, reason="kernel-5 tap tables were enabled (and checked on CPU against torch, tests/test_host_logic.py) "
-                                        "after the round's GPU budget was spent -- not yet run on a B200")
-def test_convt_k5_in_child_process():
-    """Child process: an unmeasured code path must not be able to poison this process's CUDA context."""
-    import subprocess
-    import sys
-    env = dict(os.environ, HG_TEST_K5="1")
-    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-k", "test_convt_k5_cases", "-m", "gpu"],
-                       capture_output=True, text=True, timeout=300, env=env, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-1000:]
-
-
-@pytest.mark.xfail(strict=False, reason="grouped wgrad kernel (HG_WGRAD_GROUP=1: one X box feeds every parity class that uses its shift) "
-                                        "was written after the round's GPU budget was spent -- not yet run on a B200")
-def test_wgrad_grouped_in_child_process():
-    """The fwd / dgrad / wgrad cases below with the grouped wgrad kernel selected, in a child process."""
-    import subprocess
-    import sys
-    env = dict(os.environ, HG_WGRAD_GROUP="1")
-    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-k", "test_convt_fwd_dgrad_wgrad", "-m", "gpu"],
-                       capture_output=True, text=True, timeout=300, env=env, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-1000:]
-
-
-@pytest.mark.parametrize("ndim,kernel,batch,cin,cout,size", CASES)
+@pytest.mark.parametrize("ndim,kernel,batch,cin,cout,size", CASES + K5_CASES)
 def test_convt_fwd_dgrad_wgrad(ndim, kernel, batch, cin, cout, size):
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False

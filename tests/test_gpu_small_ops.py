@@ -54,7 +54,7 @@ def test_final_conv_tanh(b, c, s, cout):
 
 @pytest.mark.parametrize("b,s", [(4, 64), (3, 32), (1, 128)])
 @pytest.mark.parametrize("mask", [7, 1, 6])
-def test_final_conv_tanh_mma_kernels(b, s, mask, monkeypatch):
+def test_final_conv_tanh_mma_kernels(b, s, mask, hg_option):
     """The tensor-core (mma.sync) kernels of the final layer at the hot-path shape Cin = 64, Cout = 3 -- forward (bit 0),
     dx (bit 1), dw (bit 2) selected through HG_FINAL_CONV_MMA -- against torch fp32 with the SIMT kernels' tolerances
     (weights and g enter the MMA as hi + lo bf16 pairs), and against the SIMT kernels themselves."""
@@ -76,10 +76,10 @@ def test_final_conv_tanh_mma_kernels(b, s, mask, monkeypatch):
         (out * dout.to(DEV)).sum().backward()
         return out.detach(), x_cl.grad.permute(0, 3, 1, 2).float(), wg.grad, bg.grad
 
-    monkeypatch.setenv("HG_FINAL_CONV_MMA", str(mask))
+    hg_option("FINAL_CONV_MMA", mask)
     out, dx, dw, db = run()
     out2 = run()[0]
-    monkeypatch.setenv("HG_FINAL_CONV_MMA", "0")
+    hg_option("FINAL_CONV_MMA", 0)
     out_s, dx_s, dw_s, db_s = run()
     errs = {"out": rel_err(out, ref), "dx": rel_err(dx, xr.grad), "dw": rel_err(dw, wr.grad), "db": rel_err(db, br.grad),
             "simt_out": rel_err(out_s, ref), "simt_dx": rel_err(dx_s, xr.grad), "simt_dw": rel_err(dw_s, wr.grad)}

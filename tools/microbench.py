@@ -74,15 +74,16 @@ def rotate(shapes=None, tune=0):
                 print(f"rotate ({b},{c},{s}^3) {str(dt)[6:]:8s} border={bn:4s} fwd {tf*1e6:8.1f} us {nbytes/tf/1e9:7.0f} GB/s "
                       f"({nbytes/tf/1e9/PEAK*100:4.1f}%)  bwd {tb*1e6:8.1f} us {nbytes/tb/1e9:7.0f} GB/s ({nbytes/tb/1e9/PEAK*100:4.1f}%)")
                 if s == 32 and os.environ.get("HG_BENCH_SLAB32", "0") != "0":
-                    # opt-in source-slab forward (rotate_slab.cu): A/B against the default kernel above
-                    os.environ["HG_ROTATE_SLAB32"] = "1"
+                    # A/B against the kernels that were the default before r02a (per-channel slab fwd, smem scatter bwd)
+                    from lightning_gan_zoo_b200 import _lib
+                    _lib.set_option("ROTATE_SLAB32", 0)
                     ts = time_rot(lambda v: ops.rotate_fwd_raw(v, a, border | tune), bufs)
-                    os.environ.pop("HG_ROTATE_SLAB32", None)
-                    os.environ["HG_ROTATE_GATHER_BWD"] = "1"
+                    _lib.set_option("ROTATE_SLAB32", 1)
+                    _lib.set_option("ROTATE_GATHER_BWD", 0)
                     tg = time_rot(lambda v: ops.rotate_bwd_raw(v, a, c, s, border | tune), bufs)
-                    os.environ.pop("HG_ROTATE_GATHER_BWD", None)
-                    print(f"rotate ({b},{c},{s}^3) {str(dt)[6:]:8s} border={bn:4s} fwd [slab32] {ts*1e6:8.1f} us "
-                          f"{nbytes/ts/1e9:7.0f} GB/s ({nbytes/ts/1e9/PEAK*100:4.1f}%)  bwd [gather] {tg*1e6:8.1f} us "
+                    _lib.set_option("ROTATE_GATHER_BWD", 1)
+                    print(f"rotate ({b},{c},{s}^3) {str(dt)[6:]:8s} border={bn:4s} fwd [old slab] {ts*1e6:8.1f} us "
+                          f"{nbytes/ts/1e9:7.0f} GB/s ({nbytes/ts/1e9/PEAK*100:4.1f}%)  bwd [old scatter] {tg*1e6:8.1f} us "
                           f"{nbytes/tg/1e9:7.0f} GB/s ({nbytes/tg/1e9/PEAK*100:4.1f}%)")
             del bufs
 
@@ -177,7 +178,15 @@ def dconv():
             f = lambda i: _lib.call("hg_convt_dgrad", P(xs[i]), P(wd), P(y), B, cout, cin, 2, size, 5, ops._stream())
             g = lambda i: _lib.call("hg_convt_fwd", P(dys[i]), P(wf), P(None), P(dx), B, cout, cin, 2, size, 5, ctypes.c_float(1.0), ops._stream())
             h = lambda i: _lib.call("hg_convt_wgrad", P(dys[i]), P(xs[i]), P(dw), P(ws), nws, B, cout, cin, 2, size, 5, 0, 0, 0, ops._stream())
+            # the split-K entry points the discriminator calls (hg_conv5s2_*), next to the unsplit transposed-conv duals
+            nw5 = _lib.load().hg_conv5s2_workspace_bytes(B, cin, cout, size)
+            ws5 = torch.empty(max(nw5, 16), dtype=torch.uint8, device=DEV)
+            f5 = lambda i: _lib.call("hg_conv5s2_fwd", P(xs[i]), P(wd), P(None), P(y), P(ws5), nw5, B, cin, cout, size, ops._stream())
+            g5 = lambda i: _lib.call("hg_conv5s2_dx", P(dys[i]), P(wf), P(None), P(dx), P(ws5), nw5, B, cin, cout, size, ops._stream())
             row = f"{name} {cin:3d}->{cout:3d} out {size:2d}^2 {flops/1e9:6.1f} GF"
+            for tag, fn in (("fwd[split]", f5), ("dx[split]", g5)):
+                t = time_rot(fn, list(range(nb)), iters=12)
+                row += f" | {tag} {t*1e6:6.1f} us ({flops/t/1e12/peak*100:4.1f}%)"
             for tag, fn in (("fwd", f), ("dx", g), ("dw", h)):
                 if tag == "dw" and nws < 0:
                     row += " | dw unsupported"
@@ -233,11 +242,12 @@ def pipeline():
         g = lambda x: _lib.call("hg_adain_cl_bwd", P(x), P(dy), P(sc), P(bi), P(mean), P(rstd), P(dx), P(ds), P(db), P(wsp), nws,
                                 B, c, ndim, size, classes, c, c, ctypes.c_float(0.0), biased, ops._stream())
         # default dispatch / cluster single-pass kernels forced for the backward too / chunked two-kernel path only
-        for tag, env in (("", {}), (" [cluster bwd]", {"HG_ADAIN_CL_CLUSTER_BWD": "1"}), (" [chunked]", {"HG_ADAIN_CL_NO_CLUSTER": "1"})):
-            os.environ.update(env)
+        for tag, env in (("", {}), (" [cluster bwd]", {"ADAIN_CL_CLUSTER_BWD": 1}), (" [chunked]", {"ADAIN_CL_NO_CLUSTER": 1})):
+            for k, v in env.items():
+                _lib.set_option(k, v)
             tf = time_rot(f, xs); f(xs[0]); tb = time_rot(g, xs)
             for k in env:
-                os.environ.pop(k, None)
+                _lib.set_option(k, 0)
             report(name + " fwd" + tag, tf, 2 * B * n * c * 2)
             report(name + " bwd" + tag, tb, 3 * B * n * c * 2)
     # spectral norm of the discriminator's three 5x5 convolutions (one grouped call each way); bytes: fwd reads W three
