@@ -71,7 +71,10 @@ const char *hg_last_error(void);
  *   TAPGEMM_DUAL         (-1)  -1 auto; 0 / 1: force one / two tap-GEMM CTAs per SM
  *   FINAL_CONV_MMA       (7)   bit mask of final-layer passes on the mma.sync kernels (1 fwd, 2 dx, 4 dw)
  *   ROTATE_SLAB32        (1)   32^3 rotate forward on source-slab tiles (0: per-channel slab kernel)
- *   ROTATE_GATHER_BWD    (1)   32^3 rotate backward as a table-free per-voxel gather (0: shared-memory scatter) */
+ *   ROTATE_GATHER_BWD    (1)   32^3 rotate backward as a table-free per-voxel gather (0: shared-memory scatter)
+ *   ADAIN_GEMM_STATS     (0)   host layer: the generator's AdaIN statistics come from the tap-GEMM epilogue
+ *                              (hg_convt_fwd_stats + hg_adain_cl_fwd_stats) instead of the single-pass cluster kernel;
+ *                              measured break-even on B200 (profiles/r02f_microbench_conv.txt), hence off */
 int hg_set_option(const char *name, int value);
 int hg_get_option(const char *name, int *value);
 
@@ -152,6 +155,12 @@ int hg_adain_cl_bwd(const void *x, const void *dy, const float *scale, const flo
                     const float *save_rstd, void *dx, float *dscale, float *dbias, void *workspace, long long workspace_bytes,
                     int batch, int channels, int ndim, int size, int classes, int sb_stride, int dsb_stride, float neg_slope,
                     int biased_var, void *stream);
+/* hg_adain_cl_fwd with the statistics partials of hg_convt_fwd_stats (same geometry: x = that call's y_s2d): a merge
+ * kernel (Chan's update over the 32-row groups x classes of each instance, fixed order) + one streaming pass.  The
+ * statistics are those of the fp32 GEMM results, i.e. before x was rounded to bf16.  S^ndim % 32 == 0. */
+int hg_adain_cl_fwd_stats(const void *x, const float *stats, const float *scale, const float *bias, void *y, float *save_mean,
+                          float *save_rstd, int batch, int channels, int ndim, int size, int classes, int sb_stride, float eps,
+                          float neg_slope, int biased_var, void *stream);
 
 /* ---- a4 / a9 / a10: transposed convolutions and the 1x1 projection as tcgen05 implicit GEMMs -------
  * Replace nn.ConvTranspose3d(k3,s2,p1,op1) / nn.ConvTranspose2d(k4,s2,p1) / nn.ConvTranspose2d(k1)
@@ -175,6 +184,15 @@ int hg_convt_pack_weight(const float *w, void *w_fwd, void *w_dgrad, int cin, in
 /* y_s2d = act(convT(x) + bias); bias (Cout) fp32 or NULL; act: v > 0 ? v : neg_slope * v (1 = none) */
 int hg_convt_fwd(const void *x, const void *w_fwd, const float *bias, void *y_s2d, int batch, int cin, int cout,
                  int ndim, int size, int kernel, float neg_slope, void *stream);
+/* hg_convt_fwd that also emits the AdaIN statistics of its output from the epilogue (north_star: "AdaIN fused into
+ * the GEMM epilogues"; SURVEY 8b epilogue flag adain-stats): for every group of 32 consecutive output positions g and
+ * every s2d column col = cls * Cout + co, stats[(g * P * Cout + col) * 2 + {0, 1}] = sum / sum of squares of the fp32
+ * results (after bias, before the activation).  `stats` holds hg_convt_stats_floats() floats.  hg_adain_cl_fwd_stats
+ * merges them per instance, so the convolution output is read once (by the normalise pass) instead of twice.
+ * Cout % 32 == 0. */
+long long hg_convt_stats_floats(int batch, int cout, int ndim, int size, int kernel);
+int hg_convt_fwd_stats(const void *x, const void *w_fwd, const float *bias, void *y_s2d, float *stats, int batch, int cin,
+                       int cout, int ndim, int size, int kernel, float neg_slope, void *stream);
 /* dx (B, .., Cin) = adjoint of the forward w.r.t. x */
 int hg_convt_dgrad(const void *dy_s2d, const void *w_dgrad, void *dx, int batch, int cin, int cout, int ndim, int size,
                    int kernel, void *stream);

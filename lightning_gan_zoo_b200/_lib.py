@@ -41,6 +41,11 @@ SIGNATURES = {
     "hg_convt_pack_weight": [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_void_p],
     "hg_convt_fwd": [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_float,
                      _c_void_p],
+    "hg_convt_stats_floats": [_c_int, _c_int, _c_int, _c_int, _c_int],
+    "hg_convt_fwd_stats": [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
+                           _c_float, _c_void_p],
+    "hg_adain_cl_fwd_stats": [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int,
+                              _c_int, _c_int, _c_int, _c_float, _c_float, _c_int, _c_void_p],
     "hg_convt_dgrad": [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_void_p],
     "hg_convt_wgrad_workspace_bytes": [_c_int, _c_int, _c_int, _c_int, _c_int, _c_int],
     "hg_convt_wgrad": [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_ll, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
@@ -86,7 +91,7 @@ _RESTYPES = {"hg_last_error": ctypes.c_char_p, "hg_rotate_bwd_workspace_bytes": 
              "hg_adain_cl_workspace_bytes": ctypes.c_longlong,
              "hg_final_conv_tanh_bwd_workspace_bytes": ctypes.c_longlong,
              "hg_spectral_norm_state_floats": ctypes.c_longlong, "hg_spectral_norm_workspace_bytes": ctypes.c_longlong,
-             "hg_conv5s2_workspace_bytes": ctypes.c_longlong, "hg_dconv0_bwd_workspace_bytes": ctypes.c_longlong,
+             "hg_convt_stats_floats": ctypes.c_longlong, "hg_conv5s2_workspace_bytes": ctypes.c_longlong, "hg_dconv0_bwd_workspace_bytes": ctypes.c_longlong,
              "hg_dheads_workspace_bytes": ctypes.c_longlong}
 
 _lib = None

@@ -145,6 +145,21 @@ class Generator(nn.Module):
         c0 = self.x.shape[1]
         return c0 % 512 == 0
 
+    @staticmethod
+    def _convt_adain(h, block, style, ndim, kernel):
+        """Transposed convolution (tcgen05 tap GEMM, s2d output) -> AdaIN + ReLU with the depth-to-space shuffle in its
+        store.  With the library option ADAIN_GEMM_STATS the GEMM epilogue also emits the AdaIN statistics partials and
+        the normalise pass is a single streaming kernel (measured break-even with the default single-pass cluster
+        kernel on B200, so off by default)."""
+        from ... import _lib
+        w = block.convTranspose.weight
+        classes = 2 ** ndim
+        if _lib.get_option("ADAIN_GEMM_STATS") and ops.convt_stats_supported(w.shape[1], ndim, h.shape[1]):
+            y, st = ops.convt(h, w, None, ndim, kernel, stats=True)
+            return ops.adain_act_channels_last(y, style, None, ndim=ndim, classes=classes, stats=st)
+        y = ops.convt(h, w, None, ndim, kernel)                                  # (B,[S,]S,S,P,Cout) s2d
+        return ops.adain_act_channels_last(y, style, None, ndim=ndim, classes=classes)
+
     def _trunk_tensor_core(self, z):
         """bf16 pipeline, view-independent half: styles, learned constant, the two ConvTranspose3d blocks.
         Returns (h2 NDHWC bf16, styles).  The ConvTranspose biases in front of an AdaIN are not applied: instance
@@ -157,8 +172,7 @@ class Generator(nn.Module):
         h0 = ops.adain_act(self.x, styles[0], None, neg_slope=0.0)               # (B,8P,4,4,4) fp32, NC*
         h = ops.nc_to_channels_last(h0.to(bf16))                                 # (B,4,4,4,8P)
         for block, style in ((self.block1, styles[1]), (self.block2, styles[2])):
-            y = ops.convt(h, block.convTranspose.weight, None, 3, 3)             # (B,S,S,S,8,Cout) s2d
-            h = ops.adain_act_channels_last(y, style, None, ndim=3, classes=8)   # (B,2S,2S,2S,Cout) NDHWC
+            h = self._convt_adain(h, block, style, 3, 3)                          # (B,2S,2S,2S,Cout) NDHWC
         return h, styles
 
     def _decode_tensor_core(self, h, a_inv, styles):
@@ -175,8 +189,7 @@ class Generator(nn.Module):
                       perm=(c, size))                                             # 1x1 conv + bias + ReLU
         h = h.reshape(n, size, size, -1)
         for block, style in ((self.block3, styles[3]), (self.block4, styles[4])):
-            y = ops.convt(h, block.convTranspose.weight, None, 2, 4)             # (B,S,S,4,Cout) s2d
-            h = ops.adain_act_channels_last(y, style, None, ndim=2, classes=4)   # (B,2S,2S,Cout) NHWC
+            h = self._convt_adain(h, block, style, 2, 4)                          # (B,2S,2S,Cout) NHWC
         if self.img_size == 64 and ops.final_conv_supported(h.shape[-1], self.final_layer.weight.shape[0]):
             return ops.final_conv_tanh(h, self.final_layer.weight, self.final_layer.bias)   # direct conv + tanh, fp32 out
         # patched-128 head (ConvTranspose2d k4 s2): cuDNN on the NHWC buffer viewed as channels_last NCHW

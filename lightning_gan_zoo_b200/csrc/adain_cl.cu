@@ -223,6 +223,78 @@ __global__ void __launch_bounds__(kClThreads) adain_cl_stats_kernel(const __nv_b
     }
 }
 
+// Statistics from the producing GEMM's epilogue (hg_convt_fwd_stats): stats[(g * ld + col) * 2 + {sum, sum of squares}] per
+// 32-row group g and s2d column col = cls * C + c of the fp32 conv results.  One thread per (b, c) merges the
+// groups x classes partials of its instance in a fixed order (Chan's parallel update on (mean, M2) -- each 32-element
+// partial is centred on its own mean first, so nothing cancels across the instance) and writes mean / rstd.
+// grid (C / 32, B), 256 threads = 32 channels x 8 slices of the partial list (8 loads in flight per thread, coalesced
+// over the channels); the slices meet in shared memory and are merged in a fixed order.
+__device__ __forceinline__ void chan_merge(float &mean, float &m2, float &n, float mw, float m2w, float nw)
+{
+    if (nw == 0.f) return;
+    const float nn = n + nw, delta = mw - mean;
+    mean += delta * (nw / nn);
+    m2 += m2w + delta * delta * (n * nw / nn);
+    n = nn;
+}
+__global__ void __launch_bounds__(256) adain_cl_stats_finalize_kernel(const float *__restrict__ stats, float *__restrict__ save_mean,
+                                                                      float *__restrict__ save_rstd, int C, int P, int groups,
+                                                                      int nvar, float eps)
+{
+    __shared__ float sm[8][3][33];
+    const int cx = threadIdx.x & 31, slice = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + cx, b = blockIdx.y;
+    const int ld = P * C, total = groups * P;           // partial q = g * P + p sits at float2 index (b * groups + g) * ld + p * C + c
+    const float2 *base = reinterpret_cast<const float2 *>(stats) + (size_t)b * groups * ld + c;
+    float mean = 0.f, m2 = 0.f, n = 0.f;
+    if (c < C) {
+        for (int q0 = slice; q0 < total; q0 += 64) {
+            float2 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int q = q0 + 8 * u;
+                if (q < total) v[u] = __ldg(base + (size_t)(q / P) * ld + (q % P) * C);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                if (q0 + 8 * u < total) {
+                    const float mw = v[u].x * (1.f / 32.f);
+                    chan_merge(mean, m2, n, mw, fmaxf(v[u].y - v[u].x * mw, 0.f), 32.f);
+                }
+            }
+        }
+    }
+    sm[slice][0][cx] = mean; sm[slice][1][cx] = m2; sm[slice][2][cx] = n;
+    __syncthreads();
+    if (slice == 0 && c < C) {
+        for (int k = 1; k < 8; ++k) chan_merge(mean, m2, n, sm[k][0][cx], sm[k][1][cx], sm[k][2][cx]);
+        save_mean[(size_t)b * C + c] = mean;
+        save_rstd[(size_t)b * C + c] = __frsqrt_rn(m2 / (float)nvar + eps);
+    }
+}
+
+// Streaming normalise / modulate / activate pass with the statistics already known (save_mean / save_rstd)
+__global__ void __launch_bounds__(kClThreads) adain_cl_apply_stats_kernel(const __nv_bfloat16 *__restrict__ x,
+                                                                          const float *__restrict__ scale,
+                                                                          const float *__restrict__ bias,
+                                                                          const float *__restrict__ save_mean,
+                                                                          const float *__restrict__ save_rstd,
+                                                                          __nv_bfloat16 *__restrict__ y, ClGeom g, int sbs, float slope)
+{
+    const int cs = threadIdx.x % g.lanes, rs = threadIdx.x / g.lanes;
+    const int b = blockIdx.y, chunk = blockIdx.x;
+    float mean[8], rstd[8], s[8], bb[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        mean[j] = save_mean[(size_t)b * g.C + cs * 8 + j];
+        rstd[j] = save_rstd[(size_t)b * g.C + cs * 8 + j];
+        s[j] = scale ? scale[(size_t)b * sbs + cs * 8 + j] : 1.f;
+        bb[j] = bias ? bias[(size_t)b * sbs + cs * 8 + j] : 0.f;
+    }
+    const int r0 = chunk * g.chunk_rows, r1 = min(g.N, r0 + g.chunk_rows);
+    fwd_apply(x + (size_t)b * g.N * g.C + cs * 8, y + (size_t)b * g.N * g.C + cs * 8, g, r0, r1, rs, mean, rstd, s, bb, slope);
+}
+
 // kFused: one CTA per sample computes the statistics itself (chunks == 1); else every CTA merges the chunk
 // partials in `part` (fixed order).
 template <bool kFused>
@@ -869,4 +941,38 @@ extern "C" int hg_adain_cl_bwd(const void *x, const void *dy, const float *scale
     adain_cl_bwd_apply_kernel<false><<<grid, kClThreads, 0, st>>>(xp, gp, part, scale, bias, save_mean, save_rstd, dp, dscale,
                                                                  dbias, g, sb_stride, dsb_stride, neg_slope);
     return check_launch("hg_adain_cl_bwd(apply)");
+}
+
+// AdaIN (+ activation) of a transposed convolution's s2d output whose statistics partials were produced by the GEMM
+// epilogue (hg_convt_fwd_stats): a tiny merge kernel + ONE streaming pass (1 read + 1 write of the activation).
+extern "C" int hg_adain_cl_fwd_stats(const void *x, const float *stats, const float *scale, const float *bias, void *y,
+                                     float *save_mean, float *save_rstd, int batch, int channels, int ndim, int size, int classes,
+                                     int sb_stride, float eps, float neg_slope, int biased_var, void *stream)
+{
+    HG_REQUIRE(x && stats && y && save_mean && save_rstd, HG_ERR_INVALID_ARG, "hg_adain_cl_fwd_stats: null pointer");
+    HG_REQUIRE((scale == nullptr) == (bias == nullptr), HG_ERR_INVALID_ARG, "hg_adain_cl_fwd_stats: scale and bias must both be given or both be null");
+    HG_REQUIRE(classes >= 1, HG_ERR_INVALID_ARG, "hg_adain_cl_fwd_stats: classes must be 1 or 2^ndim");
+    ClGeom g;
+    int rc = cl_geom("hg_adain_cl_fwd_stats", batch, channels, ndim, size, classes, biased_var, g);
+    if (rc) return rc;
+    long long pos = 1;
+    for (int i = 0; i < ndim; ++i) pos *= size;
+    HG_REQUIRE(pos % 32 == 0, HG_ERR_UNSUPPORTED, "hg_adain_cl_fwd_stats: positions per sample must be a multiple of 32 (got %lld)", pos);
+    HG_REQUIRE(!scale || sb_stride >= channels, HG_ERR_INVALID_ARG, "hg_adain_cl_fwd_stats: sb_stride < channels");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    adain_cl_stats_finalize_kernel<<<dim3((channels + 31) / 32, batch), 256, 0, st>>>(stats, save_mean, save_rstd, channels, classes,
+                                                                                    (int)(pos / 32), g.Nvar, eps);
+    rc = check_launch("hg_adain_cl_fwd_stats(finalize)");
+    if (rc) return rc;
+    // streaming pass: enough chunks for ~3 CTAs per SM, at least kClUnroll rows per thread
+    int chunks = (3 * sm_count() + batch - 1) / batch;
+    while (chunks > 1 && g.N / chunks < g.rows_per_pass * kClUnroll) --chunks;
+    int cr = (g.N + chunks - 1) / chunks;
+    cr = (cr + g.rows_per_pass - 1) / g.rows_per_pass * g.rows_per_pass;
+    g.chunk_rows = cr;
+    g.chunks = (g.N + cr - 1) / cr;
+    adain_cl_apply_stats_kernel<<<dim3(g.chunks, batch), kClThreads, 0, st>>>(static_cast<const __nv_bfloat16 *>(x), scale, bias, save_mean,
+                                                                             save_rstd, static_cast<__nv_bfloat16 *>(y), g, sb_stride,
+                                                                             neg_slope);
+    return check_launch("hg_adain_cl_fwd_stats(apply)");
 }

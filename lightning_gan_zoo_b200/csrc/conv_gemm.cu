@@ -65,6 +65,10 @@ struct TapGemmParams {
     // splitk_reduce_kernel sums the partials of every column block in a fixed order and writes the bf16 result
     float *partial;
     long long partial_stride;
+    float *stats;               // may be null.  AdaIN statistics fused into the epilogue (north_star "AdaIN fused into the GEMM
+                                // epilogues"): per 32-row group g = m / 32 and output column, the sum and the sum of squares of
+                                // the fp32 results (after bias, before the activation): stats[(g * ld_out + col) * 2 + {0, 1}].
+                                // hg_adain_cl_fwd_stats merges the groups of a sample (Chan) -- the conv output is not re-read.
     const float *out_scale;     // device scalar (may be null): accumulators are multiplied by it before bias / activation
                                 // (1 / sigma of the spectral norm: conv(x, W / sigma) = conv(x, W) / sigma)
     int num_groups;
@@ -223,17 +227,39 @@ __global__ void __launch_bounds__(kThreads, 1) tap_gemm_kernel(const __grid_cons
                 }
                 continue;
             }
+            const int ncol = min(32, p.epi_cols - c0);
+            const int bcol = (n0 + c0) % p.bias_mod;          // bias_mod is a multiple of 16 and of ncol's run
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                v[j] *= oscale;
+                if (p.bias && j < ncol) v[j] += __ldg(p.bias + (bcol + j) % p.bias_mod);
+            }
+            if (p.stats) {
+                // column sums over this warp's 32 rows through a padded shared-memory transpose (the operand ring is idle:
+                // acc_ready means every MMA that read it has retired); rows past the end of the tensor count as zero
+                float *scr = reinterpret_cast<float *>(tiles) + quad * (32 * 33);
+                const bool live = m < p.m_total;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) scr[lane * 33 + j] = live ? v[j] : 0.f;
+                __syncwarp();
+                float sum = 0.f, sq = 0.f;
+#pragma unroll
+                for (int r = 0; r < 32; ++r) {
+                    const float t = scr[r * 33 + lane];
+                    sum += t;
+                    sq = fmaf(t, t, sq);
+                }
+                __syncwarp();
+                if (lane < ncol) {
+                    const long long grow = (long long)blockIdx.x * 4 + quad;
+                    *reinterpret_cast<float2 *>(p.stats + (grow * p.ld_out + grp.out_col_off + n0 + c0 + lane) * 2) = make_float2(sum, sq);
+                }
+            }
             if (m < p.m_total) {
-                const int ncol = min(32, p.epi_cols - c0);
-                const int bcol = (n0 + c0) % p.bias_mod;      // bias_mod is a multiple of 16 and of ncol's run
                 uint32_t packed[16];
 #pragma unroll
                 for (int j = 0; j < 32; j += 2) {
-                    float a = v[j] * oscale, b = v[j + 1] * oscale;
-                    if (p.bias && j < ncol) {
-                        a += __ldg(p.bias + (bcol + j) % p.bias_mod);
-                        b += __ldg(p.bias + (bcol + j + 1) % p.bias_mod);
-                    }
+                    float a = v[j], b = v[j + 1];
                     a = a > 0.f ? a : a * p.slope;
                     b = b > 0.f ? b : b * p.slope;
                     __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
@@ -829,7 +855,7 @@ static int pack_weight_impl(const float *w, void *w_fwd, void *w_dgrad, int cin,
 }
 
 static int convt_fwd_impl(const void *x, const void *w_fwd, const float *bias, const float *out_scale, void *y_s2d, int batch,
-                          int cin, int cout, int ndim, int size, int kernel, float neg_slope, void *stream);
+                          int cin, int cout, int ndim, int size, int kernel, float neg_slope, void *stream, float *stats = nullptr);
 
 extern "C" int hg_convt_fwd(const void *x, const void *w_fwd, const float *bias, void *y_s2d, int batch, int cin, int cout,
                             int ndim, int size, int kernel, float neg_slope, void *stream)
@@ -837,8 +863,26 @@ extern "C" int hg_convt_fwd(const void *x, const void *w_fwd, const float *bias,
     return convt_fwd_impl(x, w_fwd, bias, nullptr, y_s2d, batch, cin, cout, ndim, size, kernel, neg_slope, stream);
 }
 
+// Number of floats hg_convt_fwd_stats writes: 2 per (32-row group, output column), groups padded to whole 128-row tiles.
+extern "C" long long hg_convt_stats_floats(int batch, int cout, int ndim, int size, int kernel)
+{
+    ConvShape c{batch, 64, cout, ndim, size, kernel};
+    if (conv_shape(c, "hg_convt_stats_floats")) return -1;
+    const long long m_total = (long long)batch * c.X * c.Y * c.Z;
+    return ((m_total + kBM - 1) / kBM) * 4 * (long long)c.P * cout * 2;
+}
+
+// hg_convt_fwd that also emits the AdaIN statistics partials of its output (TapGemmParams::stats)
+extern "C" int hg_convt_fwd_stats(const void *x, const void *w_fwd, const float *bias, void *y_s2d, float *stats, int batch, int cin,
+                                  int cout, int ndim, int size, int kernel, float neg_slope, void *stream)
+{
+    HG_REQUIRE(stats, HG_ERR_INVALID_ARG, "hg_convt_fwd_stats: null stats pointer");
+    HG_REQUIRE(cout % 32 == 0, HG_ERR_UNSUPPORTED, "hg_convt_fwd_stats: Cout must be a multiple of 32 (got %d)", cout);
+    return convt_fwd_impl(x, w_fwd, bias, nullptr, y_s2d, batch, cin, cout, ndim, size, kernel, neg_slope, stream, stats);
+}
+
 static int convt_fwd_impl(const void *x, const void *w_fwd, const float *bias, const float *out_scale, void *y_s2d, int batch,
-                          int cin, int cout, int ndim, int size, int kernel, float neg_slope, void *stream)
+                          int cin, int cout, int ndim, int size, int kernel, float neg_slope, void *stream, float *stats)
 {
     HG_REQUIRE(x && w_fwd && y_s2d, HG_ERR_INVALID_ARG, "hg_convt_fwd: null pointer");
     ConvShape c{batch, cin, cout, ndim, size, kernel};
@@ -857,7 +901,7 @@ static int convt_fwd_impl(const void *x, const void *w_fwd, const float *bias, c
     p.BN = bn; p.k_chunks = cin / kBK; p.bias_mod = cout;
     const long long m_total = (long long)batch * c.X * c.Y * c.Z;
     p.m_total = (int)m_total; p.ld_out = (long long)c.P * cout; p.out = y_s2d; p.bias = bias; p.slope = neg_slope;
-    p.out_scale = out_scale;
+    p.out_scale = out_scale; p.stats = stats;
     // Narrow layers (Cout <= 128 == one N tile): several parity classes share a CTA, one TMEM accumulator
     // each, so a CTA does classes_per_cta x the work per prologue/epilogue and writes one contiguous run of the
     // s2d output row.  Single launches may fill all 512 TMEM columns; dual launches (see want_dual) stop at 256,

@@ -443,39 +443,47 @@ __global__ void __launch_bounds__(kHdThreads) dheads_fwd_partial_kernel(const __
         }
 }
 
-// one CTA per sample, thread = column: sums the slab partials (8 independent loads in flight, fixed order), applies
-// bias / LeakyReLU, then linear3 + tanh with one warp per output row (coalesced weight rows, shuffle reduction)
-__global__ void __launch_bounds__(128) dheads_fwd_finish_kernel(const float *__restrict__ part, int slabs, const float *__restrict__ b1,
-                                                                const float *__restrict__ b2, const float *__restrict__ w3,
-                                                                const float *__restrict__ b3, float *__restrict__ logits,
-                                                                float *__restrict__ t2, float *__restrict__ zp, int zdim, float slope)
+// one CTA per sample: four thread groups split the slabs of every column (8 independent loads in flight each, the
+// groups meet in shared memory in a fixed order), bias / LeakyReLU, then linear3 + tanh with one warp per output row
+// (coalesced weight rows, shuffle reduction)
+constexpr int kHdFinThreads = 512;
+__global__ void __launch_bounds__(kHdFinThreads) dheads_fwd_finish_kernel(const float *__restrict__ part, int slabs,
+                                                                         const float *__restrict__ b1, const float *__restrict__ b2,
+                                                                         const float *__restrict__ w3, const float *__restrict__ b3,
+                                                                         float *__restrict__ logits, float *__restrict__ t2,
+                                                                         float *__restrict__ zp, int zdim, float slope)
 {
+    __shared__ float red[4][132];
     __shared__ float ts[128];
-    const int b = blockIdx.x, n = threadIdx.x, lane = n & 31, warp = n >> 5;
-    const float *col = part + (size_t)b * kHdLd + n;
+    const int b = blockIdx.x, n = threadIdx.x & 127, grp = threadIdx.x >> 7, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     constexpr size_t kSlabStride = (size_t)kHdMaxB * kHdLd;
+    const float *col = part + (size_t)b * kHdLd + n;
     float acc[8];
 #pragma unroll
     for (int u = 0; u < 8; ++u) acc[u] = 0.f;
-    for (int sl = 0; sl < slabs; sl += 8) {
+    for (int sl = grp; sl < slabs; sl += 32) {
 #pragma unroll
         for (int u = 0; u < 8; ++u)
-            if (sl + u < slabs) acc[u] += col[(size_t)(sl + u) * kSlabStride];
+            if (sl + 4 * u < slabs) acc[u] += col[(size_t)(sl + 4 * u) * kSlabStride];
     }
-    float s = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7])) + b2[n];
-    s = s > 0.f ? s : s * slope;
-    ts[n] = s;
-    t2[(size_t)b * 128 + n] = s;
-    if (warp == 0) {                                    // the logit column: lanes stride over the slabs
+    red[grp][n] = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
+    if (warp == 15) {                                   // the logit column: lanes stride over the slabs
         float l = 0.f;
         for (int sl = lane; sl < slabs; sl += 32) l += part[(size_t)sl * kSlabStride + (size_t)b * kHdLd + 128];
         l = warp_sum(l);
         if (lane == 0) logits[b] = l + b1[0];
     }
     __syncthreads();
+    if (grp == 0) {
+        float s = ((red[0][n] + red[1][n]) + (red[2][n] + red[3][n])) + b2[n];
+        s = s > 0.f ? s : s * slope;
+        ts[n] = s;
+        t2[(size_t)b * 128 + n] = s;
+    }
+    __syncthreads();
     const float t0 = ts[lane], t1 = ts[lane + 32], t2v = ts[lane + 64], t3 = ts[lane + 96];
 #pragma unroll 4
-    for (int j = warp; j < zdim; j += 4) {
+    for (int j = warp; j < zdim; j += kHdFinThreads / 32) {
         const float *wr = w3 + (size_t)j * 128 + lane;
         float a = __ldg(wr) * t0 + __ldg(wr + 32) * t1 + __ldg(wr + 64) * t2v + __ldg(wr + 96) * t3;
         a = warp_sum(a);
@@ -544,13 +552,26 @@ __global__ void __launch_bounds__(kHdThreads) dheads_bwd_big_kernel(const __nv_b
     const int slab = blockIdx.x, c0 = slab * g.cs, f0 = c0 * g.HW;
     hd_stage_h(hs, h, g, batch, c0);
     hd_stage_w(ws, w1, w2, g, f0, kHdNPad);
-#pragma unroll 8
-    for (int i = threadIdx.x; i < kHdMaxB * kHdNPad; i += kHdThreads) {
-        const int n = i % kHdNPad, b = i / kHdNPad;
-        os[i] = (b < batch && n < kHdN) ? __ldg(dO + (size_t)b * kHdLd + n) : 0.f;
+    {
+        constexpr int kPer = kHdMaxB * kHdNPad / kHdThreads;        // 40 elements per thread, loaded in two batches of 20
+        static_assert(kPer % 2 == 0, "batching");
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            float v[kPer / 2];
+#pragma unroll
+            for (int j = 0; j < kPer / 2; ++j) {
+                const int i = threadIdx.x + (half * (kPer / 2) + j) * kHdThreads, n = i % kHdNPad, b = i / kHdNPad;
+                v[j] = (b < batch && n < kHdN) ? __ldg(dO + (size_t)b * kHdLd + n) : 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < kPer / 2; ++j) os[threadIdx.x + (half * (kPer / 2) + j) * kHdThreads] = v[j];
+        }
     }
     __syncthreads();
-    if (dw2) {
+    // blockIdx.y selects the role when the launch has two (weight gradients and dh both wanted): halves the work per CTA
+    const bool do_dw = dw2 != nullptr && (gridDim.y == 1 || blockIdx.y == 0);
+    const bool do_dh = dh != nullptr && (gridDim.y == 1 || blockIdx.y == 1);
+    if (do_dw) {
         const int tn = threadIdx.x & 31, tk = threadIdx.x >> 5;
         float acc[5][8];
 #pragma unroll
@@ -578,7 +599,7 @@ __global__ void __launch_bounds__(kHdThreads) dheads_bwd_big_kernel(const __nv_b
             }
         }
     }
-    if (dh) {
+    if (do_dh) {
         const int k = threadIdx.x & 63, tb = threadIdx.x >> 6;
         float acc[16];
 #pragma unroll
@@ -711,7 +732,7 @@ extern "C" int hg_dheads_fwd(const void *h, const float *w1, const float *b1, co
     dheads_fwd_partial_kernel<<<g.slabs, kHdThreads, hd_fwd_smem(), st>>>(static_cast<const __nv_bfloat16 *>(h), w1, w2, part, g, batch);
     rc = check_launch("hg_dheads_fwd(partial)");
     if (rc) return rc;
-    dheads_fwd_finish_kernel<<<batch, 128, 0, st>>>(part, g.slabs, b1, b2, w3, b3, logits, t2, z_pred, zdim, neg_slope);
+    dheads_fwd_finish_kernel<<<batch, kHdFinThreads, 0, st>>>(part, g.slabs, b1, b2, w3, b3, logits, t2, z_pred, zdim, neg_slope);
     return check_launch("hg_dheads_fwd(finish)");
 }
 
@@ -745,7 +766,7 @@ extern "C" int hg_dheads_bwd(const void *h, const float *w1, const float *w2, co
         if (rc) return rc;
     }
     if (params || dh) {
-        dheads_bwd_big_kernel<<<g.slabs, kHdThreads, hd_bwd_smem(), st>>>(static_cast<const __nv_bfloat16 *>(h), w1, w2, dO, dw1, dw2,
+        dheads_bwd_big_kernel<<<dim3(g.slabs, (params && dh) ? 2 : 1), kHdThreads, hd_bwd_smem(), st>>>(static_cast<const __nv_bfloat16 *>(h), w1, w2, dO, dw1, dw2,
                                                                           static_cast<__nv_bfloat16 *>(dh), g, batch);
         rc = check_launch("hg_dheads_bwd(big)");
     }

@@ -41,6 +41,7 @@ enum Option {
     kOptFinalConvMma,           // bit mask: final layer passes on the mma.sync kernels (1 fwd, 2 dx, 4 dw)
     kOptRotateSlab32,           // 1: 32^3 rotate forward on source-slab tiles
     kOptRotateGatherBwd,        // 1: 32^3 rotate backward as a table-free per-voxel gather
+    kOptAdainGemmStats,         // 1: generator AdaIN statistics from the tap-GEMM epilogue (read by the Python layer)
     kOptCount
 };
 int option(Option o);

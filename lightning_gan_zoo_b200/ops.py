@@ -387,7 +387,7 @@ class _ConvT(torch.autograd.Function):
     """y_s2d = act(convT(x) + bias) with x (B,[S,]S,S,Cin) bf16 and y_s2d (B,[S,]S,S,P,Cout) bf16."""
 
     @staticmethod
-    def forward(ctx, x_cl, weight, bias, ndim, kernel, neg_slope, perm):
+    def forward(ctx, x_cl, weight, bias, ndim, kernel, neg_slope, perm, want_stats):
         _require_cuda(x_cl, weight)
         b, size, cin = _conv_dims(x_cl, ndim)
         cout = weight.shape[1]
@@ -397,15 +397,27 @@ class _ConvT(torch.autograd.Function):
         nclass = 1 if kernel == 1 else 2 ** ndim
         y = torch.empty((b,) + (size,) * ndim + (nclass, cout), dtype=torch.bfloat16, device=x_cl.device)
         bias_f = None if bias is None else bias.detach().float().contiguous()
-        _lib.call("hg_convt_fwd", _ptr(x_cl), _ptr(wf), _ptr(bias_f), _ptr(y), b, cin, cout, ndim, size, kernel,
-                  ctypes.c_float(neg_slope), _stream())
+        stats = None
+        if want_stats:          # AdaIN statistics partials from the GEMM epilogue (consumed by adain_act_channels_last)
+            n = _lib.load().hg_convt_stats_floats(b, cout, ndim, size, kernel)
+            if n < 0:
+                raise _lib.HologanB200Error("hg_convt_stats_floats: unsupported shape")
+            stats = torch.empty(n, dtype=torch.float32, device=x_cl.device)
+            _lib.call("hg_convt_fwd_stats", _ptr(x_cl), _ptr(wf), _ptr(bias_f), _ptr(y), _ptr(stats), b, cin, cout, ndim, size,
+                      kernel, ctypes.c_float(neg_slope), _stream())
+        else:
+            _lib.call("hg_convt_fwd", _ptr(x_cl), _ptr(wf), _ptr(bias_f), _ptr(y), b, cin, cout, ndim, size, kernel,
+                      ctypes.c_float(neg_slope), _stream())
         ctx.save_for_backward(x_cl, wd, y if neg_slope != 1.0 else None)
         ctx.meta = (b, cin, cout, ndim, size, kernel, neg_slope, tuple(weight.shape), bias is not None, perm)
         ctx.weight_param = weight if isinstance(weight, torch.nn.Parameter) else None
+        if want_stats:
+            ctx.mark_non_differentiable(stats)
+            return y, stats
         return y
 
     @staticmethod
-    def backward(ctx, dy):
+    def backward(ctx, dy, *_unused):
         x_cl, wd, y = ctx.saved_tensors
         b, cin, cout, ndim, size, kernel, neg_slope, wshape, has_bias, perm = ctx.meta
         dy = dy.contiguous()
@@ -425,12 +437,18 @@ class _ConvT(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             target, overwrite = _direct_grad_target(ctx.weight_param, wshape)
             dw = convt_wgrad(x_cl, dy, wshape, ndim, kernel, perm, accumulate_into=target, overwrite=overwrite)
-        return dx, dw, db, None, None, None, None
+        return dx, dw, db, None, None, None, None, None
 
 
 def convt(x_cl: Tensor, weight: Tensor, bias: Optional[Tensor], ndim: int, kernel: int, neg_slope: float = 1.0,
-          perm: Tuple[int, int] = (0, 0)) -> Tensor:
-    return _ConvT.apply(x_cl, weight, bias, ndim, kernel, neg_slope, perm)
+          perm: Tuple[int, int] = (0, 0), stats: bool = False):
+    """Transposed convolution / 1x1 projection on the tcgen05 tap GEMM.  `stats=True` returns (y_s2d, stats): the AdaIN
+    statistics partials of y computed in the GEMM epilogue -- pass them to `adain_act_channels_last(..., stats=stats)`."""
+    return _ConvT.apply(x_cl, weight, bias, ndim, kernel, neg_slope, perm, stats)
+
+
+def convt_stats_supported(cout: int, ndim: int, size: int) -> bool:
+    return cout % 32 == 0 and (size ** ndim) % 32 == 0
 
 
 # ---- layout glue (pure data movement) -------------------------------------------------------------
@@ -457,7 +475,7 @@ class _AdaInChannelsLast(torch.autograd.Function):
     y (B,[2S,]2S,2S,C) bf16 channels-last.  scale / bias None = 1 / 0 (no style gradients)."""
 
     @staticmethod
-    def forward(ctx, x, scale, bias, ndim, classes, neg_slope, eps, biased):
+    def forward(ctx, x, scale, bias, ndim, classes, neg_slope, eps, biased, stats=None):
         _require_cuda(x, scale, bias)
         if x.dtype != torch.bfloat16 or not x.is_contiguous():
             raise ValueError("x must be a contiguous bf16 tensor")
@@ -473,9 +491,13 @@ class _AdaInChannelsLast(torch.autograd.Function):
         nbytes = _lib.load().hg_adain_cl_workspace_bytes(b, c, ndim, size, classes)
         if nbytes < 0:
             raise _lib.HologanB200Error(f"hg_adain_cl_fwd: unsupported shape C={c} size={size} classes={classes}")
-        ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device) if nbytes else None
-        _lib.call("hg_adain_cl_fwd", _ptr(x), sp, bp, _ptr(y), _ptr(mean), _ptr(rstd), _ptr(ws), nbytes, b, c,
-                  ndim, size, classes, sbs, ctypes.c_float(eps), ctypes.c_float(neg_slope), int(biased), _stream())
+        if stats is not None:       # statistics partials from the producing GEMM's epilogue: merge + one streaming pass
+            _lib.call("hg_adain_cl_fwd_stats", _ptr(x), _ptr(stats), sp, bp, _ptr(y), _ptr(mean), _ptr(rstd), b, c, ndim, size,
+                      classes, sbs, ctypes.c_float(eps), ctypes.c_float(neg_slope), int(biased), _stream())
+        else:
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device) if nbytes else None
+            _lib.call("hg_adain_cl_fwd", _ptr(x), sp, bp, _ptr(y), _ptr(mean), _ptr(rstd), _ptr(ws), nbytes, b, c,
+                      ndim, size, classes, sbs, ctypes.c_float(eps), ctypes.c_float(neg_slope), int(biased), _stream())
         ctx.save_for_backward(x, scale, bias, mean, rstd)
         ctx.meta = (b, c, ndim, size, classes, float(neg_slope), int(biased))
         return y
@@ -498,16 +520,17 @@ class _AdaInChannelsLast(torch.autograd.Function):
                   dsp, dbp, _ptr(ws), nbytes, b, c, ndim,
                   size, classes, sbs, dstride, ctypes.c_float(neg_slope), biased, _stream())
         if dsb is None:
-            return dx, None, None, None, None, None, None, None
+            return dx, None, None, None, None, None, None, None, None
         if bias is None:
-            return dx, dsb, None, None, None, None, None, None
-        return dx, dsb[0], dsb[1], None, None, None, None, None
+            return dx, dsb, None, None, None, None, None, None, None
+        return dx, dsb[0], dsb[1], None, None, None, None, None, None
 
 
 def adain_act_channels_last(x: Tensor, scale: Tensor, bias: Optional[Tensor], ndim: int, classes: int,
-                            neg_slope: float = 0.0, eps: float = 1e-8) -> Tensor:
-    """`bias=None`: `scale` is the packed (B, 2C) style [scale | bias] (see adain_act)."""
-    return _AdaInChannelsLast.apply(x, scale, bias, ndim, classes, neg_slope, eps, False)
+                            neg_slope: float = 0.0, eps: float = 1e-8, stats: Optional[Tensor] = None) -> Tensor:
+    """`bias=None`: `scale` is the packed (B, 2C) style [scale | bias] (see adain_act).
+    `stats`: the statistics partials `convt(..., stats=True)` produced for x in its GEMM epilogue."""
+    return _AdaInChannelsLast.apply(x, scale, bias, ndim, classes, neg_slope, eps, False, stats)
 
 
 def instance_norm_act_channels_last(x_nhwc: Tensor, neg_slope: float = 0.2, eps: float = 1e-5, s2d_out: bool = False) -> Tensor:

@@ -148,6 +148,12 @@ def conv():
             t = time_rot(fn, list(range(nb)), iters=12)
             tot[tag] += t
             row += f" | {tag} {t*1e6:7.1f} us {flops/t/1e12:6.0f} TF/s ({flops/t/1e12/peak*100:4.1f}%)"
+        if k != 1:          # forward with the AdaIN statistics epilogue
+            nst = _lib.load().hg_convt_stats_floats(B, cout, ndim, size, k)
+            st = torch.empty(nst, device=DEV)
+            fs = lambda i: _lib.call("hg_convt_fwd_stats", P(xs[i]), P(wf), P(None), P(y), P(st), B, cin, cout, ndim, size, k, ctypes.c_float(1.0), ops._stream())
+            t = time_rot(fs, list(range(nb)), iters=12)
+            row += f" | fwd+stats {t*1e6:7.1f} us"
         print(row)
     print("totals: " + ", ".join(f"{k} {v*1e6:.0f} us" for k, v in tot.items()))
 
