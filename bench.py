@@ -50,6 +50,10 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--no-graphs", action="store_true", help="eager launches instead of CUDA-graph replay")
+    ap.add_argument("--mode", default="train", choices=["train", "sweep"],
+                    help="train: the training step (BASELINE configs[1] / [3]); sweep: azimuth-sweep inference (configs[4])")
+    ap.add_argument("--views", type=int, default=36, help="sweep mode: views per latent")
+    ap.add_argument("--sweep-batch", type=int, default=256, help="sweep mode: latents per GPU")
     return ap.parse_args()
 
 
@@ -179,7 +183,9 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": ips, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "img_size": args.img_size, "per_gpu_batch": args.batch},
+        "config": {"workload": f"HoloGAN {args.img_size}x{args.img_size} full training step ([D,G,G] schedule), reference algorithm on the "
+                               f"host CPU: batch {args.cpu_batch} per step, fp32 (bounded sample of the batch-{args.batch}-per-GPU bf16 workload)",
+                   "img_size": args.img_size, "per_gpu_batch": args.batch, "cpu_batch": args.cpu_batch},
         "cpu_baseline": {"value": ips, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": ips, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -269,10 +275,113 @@ def rotate_roofline(peaks, device):
 # main arm
 # --------------------------------------------------------------------------------------------------
 
+def run_sweep(args):
+    """BASELINE.json configs[4] (SURVEY 8d cfg 5): HoloGAN azimuth-sweep inference, `--sweep-batch` latents per GPU x
+    `--views` azimuths (linspace(220, 320, V) degrees at elevation 90, the pattern of core/figures/types.py:300-322),
+    no grad, bf16, patched 128 x 128 head by default (--img-size).  One "step" = one whole sweep per GPU.  Latents are
+    sharded over the ranks; there is no collective on the data path.  `value`: latents resident in HBM; `e2e`: latents
+    from pinned host memory, every image copied back D2H (on a copy stream, overlapped with the next views)."""
+    import torch.distributed as dist
+    from types import SimpleNamespace
+    from lightning_gan_zoo_b200 import _lib
+    from lightning_gan_zoo_b200.core.models.hologan_generator import Generator
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the B200 path has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    _lib.load()
+    B, V, S = args.sweep_batch, args.views, args.img_size if args.img_size != 64 or "--img-size" in sys.argv else 128
+    K, W = args.steps, max(args.warmup, 3)
+    torch.manual_seed(42)
+    net = Generator(64, 3, 128, SimpleNamespace(), S).to(device).eval()
+    views = np.zeros((V, 6))
+    views[:, 0] = np.deg2rad(np.linspace(220, 320, V))
+    views[:, 1] = np.deg2rad(90.0)
+    views[:, 2] = 1.0
+    gen = torch.Generator().manual_seed(7 + rank)
+    z_host = (torch.rand(B, 128, generator=gen) * 2 - 1).pin_memory()
+    z_dev = z_host.to(device)
+    out_host = torch.empty((B, V, 3, S, S), dtype=torch.float32).pin_memory()
+    copy_stream = torch.cuda.Stream(device=device)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def resident(_i):
+        with torch.autocast("cuda", dtype=torch.bfloat16), torch.no_grad():
+            net.render_views(z_dev, views)
+
+    def e2e(_i):
+        with torch.autocast("cuda", dtype=torch.bfloat16), torch.no_grad():
+            z = z_host.to(device, non_blocking=True)
+            out = net.render_views(z, views)
+            ev = torch.cuda.Event()
+            ev.record()
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(ev)
+                out_host.copy_(out, non_blocking=True)
+            out.record_stream(copy_stream)
+
+    def timed(fn, k):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(k):
+            fn(i)
+        torch.cuda.current_stream().wait_stream(copy_stream)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=device)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    for i in range(W):
+        resident(i)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = _lib.launch_count
+    ms_total = timed(resident, K)
+    launches = _lib.launch_count - l0
+    clocks = sampler.stop() if rank == 0 else None
+    e2e(0)
+    torch.cuda.synchronize()
+    ms_e2e = timed(e2e, K)
+    imgs = world * B * V * K
+    line = {
+        "metric": "hologan_sweep_images_per_s", "value": imgs / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K,
+        "warmup": W, "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"HoloGAN {S}x{S} azimuth sweep inference, {V} views per z, batch {B} latents per GPU, bf16"
+                               + (" (patched 128 head, SURVEY R4)" if S == 128 else ""),
+                   "img_size": S, "views": V, "per_gpu_latents": B, "parallelism": f"dp{world} (latents sharded, no collective)",
+                   "weights": "random init",
+                   "l2": "no flush: one sweep writes %.1f GB of images per GPU" % (B * V * 3 * S * S * 4 / 1e9)},
+        "e2e": {"value": imgs / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": B * 128 * 4,
+                "d2h_bytes_per_step": B * V * 3 * S * S * 4, "ms_per_step": ms_e2e / K},
+        "gpu_launches": launches, "clocks": clocks,
+    }
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        _exit_without_nccl_teardown(rank)
+
+
 def main():
     args = parse_args()
     if args.impl == "reference":
         run_reference(args)
+        return
+    if args.mode == "sweep":
+        run_sweep(args)
         return
     import torch.distributed as dist
     from lightning_gan_zoo_b200 import _lib, ops

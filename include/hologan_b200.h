@@ -245,6 +245,18 @@ int hg_final_conv_tanh_bwd(const void *x, const float *w, const float *out, cons
                            float *dbias, void *workspace, long long workspace_bytes, int batch, int cin, int cout, int size,
                            void *stream);
 
+/* The patched 128 x 128 head (the reference's img_size == 128 branch, core/models/hologan_generator.py:71-72,
+ * lacks stride = 2 and yields 65 x 65; the working variant is ConvTranspose2d(64 -> 3, k4, s2, p1)):
+ *   out (B, 3, S, S) fp32 NCHW = tanh(convT(x) + bias); x (B, S/2, S/2, 64) bf16 NHWC; w (64, 3, 4, 4) fp32 torch layout.
+ * Warp-level tensor cores (mma.sync) -- the kernels are shared with the discriminator's first convolution (disc_ends.cu).
+ * backward: g = dout * (1 - out^2); dx (B, S/2, S/2, 64) bf16 (NULL = not needed); dw (64, 3, 4, 4) + dbias (3) fp32 (both
+ * or neither).  S % 32 == 0.  Deterministic. */
+int hg_head128_fwd(const void *x, const float *w, const float *bias, float *out, int batch, int cin, int cout, int size,
+                   void *stream);
+long long hg_head128_bwd_workspace_bytes(int batch, int size);
+int hg_head128_bwd(const void *x, const float *w, const float *out, const float *dout, void *dx, float *dw, float *dbias,
+                   void *workspace, long long workspace_bytes, int batch, int cin, int cout, int size, void *stream);
+
 /* ---- a14: spectral normalisation of the discriminator's convolutions, grouped over the layers ----------
  * Replaces torch.nn.utils.spectral_norm (n_power_iterations = 1, eps = 1e-12, dim = 0) as used at
  * core/models/hologan_discriminator.py:15 -- per layer i, with W = w[i] viewed as (cout, K = cin * taps):

@@ -75,6 +75,10 @@ SIGNATURES = {
     "hg_dheads_workspace_bytes": [_c_int, _c_int, _c_int, _c_int],
     "hg_dheads_fwd": [_c_void_p] * 11 + [_c_ll, _c_int, _c_int, _c_int, _c_int, _c_float, _c_void_p],
     "hg_dheads_bwd": [_c_void_p] * 16 + [_c_ll, _c_int, _c_int, _c_int, _c_int, _c_float, _c_void_p],
+    "hg_head128_fwd": [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_void_p],
+    "hg_head128_bwd_workspace_bytes": [_c_int, _c_int],
+    "hg_head128_bwd": [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_ll, _c_int,
+                       _c_int, _c_int, _c_int, _c_void_p],
     "hg_gan_loss_fwd": [_c_void_p, _c_int, _c_float, _c_float, _c_void_p, _c_int, _c_float, _c_float, _c_void_p, _c_void_p,
                         _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p],
     "hg_gan_loss_bwd": [_c_void_p, _c_void_p, _c_int, _c_float, _c_float, _c_void_p, _c_int, _c_float, _c_float, _c_void_p,
@@ -92,6 +96,7 @@ _RESTYPES = {"hg_last_error": ctypes.c_char_p, "hg_rotate_bwd_workspace_bytes": 
              "hg_final_conv_tanh_bwd_workspace_bytes": ctypes.c_longlong,
              "hg_spectral_norm_state_floats": ctypes.c_longlong, "hg_spectral_norm_workspace_bytes": ctypes.c_longlong,
              "hg_convt_stats_floats": ctypes.c_longlong, "hg_conv5s2_workspace_bytes": ctypes.c_longlong, "hg_dconv0_bwd_workspace_bytes": ctypes.c_longlong,
+             "hg_head128_bwd_workspace_bytes": ctypes.c_longlong,
              "hg_dheads_workspace_bytes": ctypes.c_longlong}
 
 _lib = None

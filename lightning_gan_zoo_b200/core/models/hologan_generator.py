@@ -192,7 +192,9 @@ class Generator(nn.Module):
             h = self._convt_adain(h, block, style, 2, 4)                          # (B,2S,2S,Cout) NHWC
         if self.img_size == 64 and ops.final_conv_supported(h.shape[-1], self.final_layer.weight.shape[0]):
             return ops.final_conv_tanh(h, self.final_layer.weight, self.final_layer.bias)   # direct conv + tanh, fp32 out
-        # patched-128 head (ConvTranspose2d k4 s2): cuDNN on the NHWC buffer viewed as channels_last NCHW
+        if self.img_size == 128 and ops.head128_supported(h.shape[-1], self.final_layer.weight.shape[1], h.shape[1]):
+            return ops.head128_tanh(h, self.final_layer.weight, self.final_layer.bias)      # patched-128 head on mma.sync
+        # other widths: stock op on the NHWC buffer viewed as channels_last NCHW
         return torch.tanh(self.final_layer(h.permute(0, 3, 1, 2)))
 
     def _forward_tensor_core(self, z, view_in):

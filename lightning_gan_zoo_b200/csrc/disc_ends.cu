@@ -17,93 +17,127 @@
 namespace hg {
 
 // -------------------------------------------------------------------------------------------------
-// conv0
+// 3 <-> 64 channel stride-2 convolutions on mma.sync: the discriminator's first convolution (kernel 5, padding 2) and
+// the generator's patched 128 x 128 head ConvTranspose2d(64 -> 3, k4, s2, p1) + tanh (reference
+// core/models/hologan_generator.py:71-72 with the missing stride) share three kernels, templated on <KS, PAD, HEAD>:
+//   img2map : 3-channel image (2S x 2S) -> 64-channel map (S x S)      conv0 forward        | head dx
+//   map2img : 64-channel map (S x S)    -> 3-channel image (2S x 2S)   conv0 dx             | head forward (+ bias, tanh)
+//   dw      : sum over pixels of map (x) image patches                 conv0 dw (+ dbias)   | head dw
+// The weight element that couples map channel n (of 64), image channel c (of 3) and tap (ky, kx) sits at
+// w[((n * 3 + c) * KS + ky) * KS + kx] in BOTH torch layouts: Conv2d (64, 3, 5, 5) and ConvTranspose2d (64, 3, 4, 4).
+// Geometry: map pixel i and tap k touch image pixel 2i - PAD + k.
 // -------------------------------------------------------------------------------------------------
 constexpr int kC0Threads = 256;
 constexpr int kC0Cout = 64, kC0Cin = 3;
-constexpr int kC0TH = 8, kC0TW = 16;                    // output tile: one row of 16 pixels per warp
-constexpr int kC0PH = 2 * kC0TH + 3, kC0PW = 2 * kC0TW + 3, kC0PPitch = 36;      // input patch 19 x 35 per channel
-constexpr int kC0KSteps = 6;                            // K index k = (ci * 5 + ky) * 6 + kx, kx < 6 (kx == 5: zero) -> 90 -> 96
-constexpr int kC0KReal = 90;
-constexpr int kC0OnesCol = 90;                          // dW kernel: im2col column 90 is all ones -> its "weight gradient" is dbias
+constexpr int kC0TH = 8, kC0TW = 16;                    // map tile: one row of 16 pixels per warp
 
-// element offset of im2col column k inside the patch (relative to the pixel's top-left tap); columns >= 90 map to 0
-__device__ __forceinline__ int c0_col_offset(int k)
+template <int KS> struct C0Geom {
+    static constexpr int PH = 2 * kC0TH + KS - 2, PW = 2 * kC0TW + KS - 2;      // image patch of a tile
+    static constexpr int PPitch = (PW + 2) & ~1;                                // even: bf16 pairs stay 4-byte aligned
+    static constexpr int KX = (KS + 1) & ~1;                                    // taps per row padded to even (kx == KS: zero weight)
+    static constexpr int KReal = kC0Cin * KS * KX;                              // im2col columns k = (c * KS + ky) * KX + kx
+    static constexpr int KSteps = (KReal + 15) / 16;
+    static constexpr int KPad = KSteps * 16;
+};
+constexpr int kC0OnesCol = 90;                          // conv0 dw: the unused im2col column 90 is all ones -> its "dw" is dbias
+
+// element offset of im2col column k inside the patch (relative to the pixel's top-left tap); columns >= KReal map to 0
+template <int KS> __device__ __forceinline__ int c0_col_offset(int k)
 {
-    if (k >= kC0KReal) return 0;
-    const int kx = k % 6, r = k / 6, ky = r % 5, ci = r / 5;
-    return (ci * kC0PH + ky) * kC0PPitch + kx;
+    using G = C0Geom<KS>;
+    if (k >= G::KReal) return 0;
+    const int kx = k % G::KX, r = k / G::KX, ky = r % KS, ci = r / KS;
+    return (ci * G::PH + ky) * G::PPitch + kx;
 }
 
-// stage the input patch of the tile as bf16 [3][19][36]; out-of-image elements are zero
-__device__ __forceinline__ void c0_stage_patch(__nv_bfloat16 *patch, const float *__restrict__ xb, int S, int oy0, int ox0)
+// The 3-channel image the kernels read: conv0 -> x (fp32 NCHW); head -> g = dout * (1 - out^2) from two fp32 NCHW tensors
+struct C0Image {
+    const float *a;       // x, or dout
+    const float *b;       // null, or out (tanh output)
+    __device__ __forceinline__ float at(size_t i) const
+    {
+        const float v = __ldg(a + i);
+        if (!b) return v;
+        const float o = __ldg(b + i);
+        return v * (1.f - o * o);
+    }
+};
+
+// stage the image patch of the tile as bf16 [3][PH][PPitch]; out-of-image elements are zero
+template <int KS, int PAD>
+__device__ __forceinline__ void c0_stage_patch(__nv_bfloat16 *patch, const C0Image &img, size_t img_off, int S, int oy0, int ox0)
 {
-    const int iy0 = 2 * oy0 - 2, ix0 = 2 * ox0 - 2;
-    for (int i = threadIdx.x; i < kC0Cin * kC0PH * kC0PPitch; i += kC0Threads) {
-        const int px = i % kC0PPitch, r = i / kC0PPitch, py = r % kC0PH, ci = r / kC0PH;
+    using G = C0Geom<KS>;
+    const int iy0 = 2 * oy0 - PAD, ix0 = 2 * ox0 - PAD;
+    for (int i = threadIdx.x; i < kC0Cin * G::PH * G::PPitch; i += kC0Threads) {
+        const int px = i % G::PPitch, r = i / G::PPitch, py = r % G::PH, ci = r / G::PH;
         const int yy = iy0 + py, xx = ix0 + px;
         float v = 0.f;
-        if (px < kC0PW && yy >= 0 && yy < S && xx >= 0 && xx < S) v = __ldg(xb + ((size_t)ci * S + yy) * S + xx);
+        if (px < G::PW && yy >= 0 && yy < S && xx >= 0 && xx < S) v = img.at(img_off + ((size_t)ci * S + yy) * S + xx);
         patch[i] = __float2bfloat16_rn(v);
     }
 }
 
-// row of the space-to-depth activation that holds pixel (oy, ox) of the (S2 x S2) map, S4 = S2 / 2
-__device__ __forceinline__ int c0_s2d_row(int oy, int ox, int S4)
+// row of the 64-channel map that holds pixel (oy, ox): space-to-depth order (conv0, S4 = S2 / 2) or plain (head)
+template <bool HEAD> __device__ __forceinline__ int c0_map_row(int oy, int ox, int S2)
 {
-    return (((oy >> 1) * S4 + (ox >> 1)) << 2) + ((oy & 1) << 1) + (ox & 1);
+    if (HEAD) return oy * S2 + ox;
+    return (((oy >> 1) * (S2 >> 1) + (ox >> 1)) << 2) + ((oy & 1) << 1) + (ox & 1);
 }
 
-__global__ void __launch_bounds__(kC0Threads) dconv0_fwd_kernel(const float *__restrict__ x, const float *__restrict__ w,
-                                                                const float *__restrict__ bias, __nv_bfloat16 *__restrict__ y,
-                                                                int S, int total_tiles, float slope)
+// ---- image -> map --------------------------------------------------------------------------------------
+// im2col GEMM  M = 16 map pixels per warp, K = KPad, N = 64: A fragments gathered from the staged patch, B fragments
+// (weights) held in registers.  conv0: + bias, LeakyReLU; head dx: raw.
+template <int KS, int PAD, bool HEAD>
+__global__ void __launch_bounds__(kC0Threads) c0_img2map_kernel(C0Image img, const float *__restrict__ w, const float *__restrict__ bias,
+                                                                __nv_bfloat16 *__restrict__ y, int S, int total_tiles, float slope)
 {
-    __shared__ __align__(16) __nv_bfloat16 patch[kC0Cin * kC0PH * kC0PPitch];
+    using G = C0Geom<KS>;
+    __shared__ __align__(16) __nv_bfloat16 patch[kC0Cin * G::PH * G::PPitch];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, q = lane & 3;
-    const int S2 = S / 2, S4 = S / 4, tiles_x = S2 / kC0TW, tiles_img = tiles_x * (S2 / kC0TH);
-    // B fragments (weights) of all k-steps and n-tiles: B[k][co] = w[co][ci][ky][kx]
-    uint32_t bw[kC0KSteps][8][2];
+    const int S2 = S / 2, tiles_x = S2 / kC0TW, tiles_img = tiles_x * (S2 / kC0TH);
+    uint32_t bw[G::KSteps][8][2];                       // B[k][n] = w[n][c][ky][kx]
 #pragma unroll
-    for (int ks = 0; ks < kC0KSteps; ++ks)
+    for (int ks = 0; ks < G::KSteps; ++ks)
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-                const int k = ks * 16 + 2 * q + 8 * h, co = nt * 8 + g;
+                const int k = ks * 16 + 2 * q + 8 * h, n = nt * 8 + g;
                 float v[2];
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
-                    const int kk = k + e, kx = kk % 6, r = kk / 6, ky = r % 5, ci = r / 5;
-                    v[e] = (kk < kC0KReal && kx < 5) ? __ldg(w + ((size_t)co * kC0Cin + ci) * 25 + ky * 5 + kx) : 0.f;
+                    const int kk = k + e, kx = kk % G::KX, r = kk / G::KX, ky = r % KS, ci = r / KS;
+                    v[e] = (kk < G::KReal && kx < KS) ? __ldg(w + ((size_t)(n * kC0Cin + ci) * KS + ky) * KS + kx) : 0.f;
                 }
                 bw[ks][nt][h] = pack_bf16x2(v[0], v[1]);
             }
-    int aoff[kC0KSteps][2];
+    int aoff[G::KSteps][2];
 #pragma unroll
-    for (int ks = 0; ks < kC0KSteps; ++ks) {
-        aoff[ks][0] = c0_col_offset(ks * 16 + 2 * q);
-        aoff[ks][1] = c0_col_offset(ks * 16 + 2 * q + 8);
+    for (int ks = 0; ks < G::KSteps; ++ks) {
+        aoff[ks][0] = c0_col_offset<KS>(ks * 16 + 2 * q);
+        aoff[ks][1] = c0_col_offset<KS>(ks * 16 + 2 * q + 8);
     }
     float bv[8][2];
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
-        bv[nt][0] = __ldg(bias + nt * 8 + 2 * q);
-        bv[nt][1] = __ldg(bias + nt * 8 + 2 * q + 1);
+        bv[nt][0] = bias ? __ldg(bias + nt * 8 + 2 * q) : 0.f;
+        bv[nt][1] = bias ? __ldg(bias + nt * 8 + 2 * q + 1) : 0.f;
     }
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int b = tile / tiles_img, t = tile - b * tiles_img;
         const int oy0 = (t / tiles_x) * kC0TH, ox0 = (t % tiles_x) * kC0TW;
         __syncthreads();
-        c0_stage_patch(patch, x + (size_t)b * kC0Cin * S * S, S, oy0, ox0);
+        c0_stage_patch<KS, PAD>(patch, img, (size_t)b * kC0Cin * S * S, S, oy0, ox0);
         __syncthreads();
         float acc[8][4];
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
             for (int j = 0; j < 4; ++j) acc[nt][j] = 0.f;
-        const unsigned char *prow = reinterpret_cast<const unsigned char *>(patch + (2 * warp) * kC0PPitch);
+        const unsigned char *prow = reinterpret_cast<const unsigned char *>(patch + (2 * warp) * G::PPitch);
 #pragma unroll
-        for (int ks = 0; ks < kC0KSteps; ++ks) {
+        for (int ks = 0; ks < G::KSteps; ++ks) {
             uint32_t a[4];
             a[0] = lds32(prow + (aoff[ks][0] + 2 * g) * 2);
             a[1] = lds32(prow + (aoff[ks][0] + 2 * (g + 8)) * 2);
@@ -117,7 +151,7 @@ __global__ void __launch_bounds__(kC0Threads) dconv0_fwd_kernel(const float *__r
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const int ox = ox0 + g + 8 * h;
-            __nv_bfloat16 *dst = yb + (size_t)c0_s2d_row(oy, ox, S4) * kC0Cout + 2 * q;
+            __nv_bfloat16 *dst = yb + (size_t)c0_map_row<HEAD>(oy, ox, S2) * kC0Cout + 2 * q;
 #pragma unroll
             for (int nt = 0; nt < 8; ++nt) {
                 float v0 = acc[nt][2 * h] + bv[nt][0], v1 = acc[nt][2 * h + 1] + bv[nt][1];
@@ -129,56 +163,70 @@ __global__ void __launch_bounds__(kC0Threads) dconv0_fwd_kernel(const float *__r
     }
 }
 
-// gradient through the LeakyReLU: dpre = dy * (y > 0 ? 1 : slope), both in the s2d activation layout
-__device__ __forceinline__ float c0_dpre(__nv_bfloat16 dy, __nv_bfloat16 yv, float slope)
-{
-    const float d = __bfloat162float(dy);
-    return __bfloat162float(yv) > 0.f ? d : d * slope;
-}
+// The 64-channel map operand of the other two kernels: conv0 -> dpre = dy * (y > 0 ? 1 : slope) (gradient through the
+// LeakyReLU, both tensors in the s2d activation layout); head -> the activation x itself (gate == null).
+struct C0Map {
+    const __nv_bfloat16 *v;       // dy, or x
+    const __nv_bfloat16 *gate;    // y (LeakyReLU output), or null
+    float slope;
+    // 8 consecutive channels of one map row as fp32
+    __device__ __forceinline__ void load8(size_t off, float (&f)[8]) const
+    {
+        const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(v + off));
+        const __nv_bfloat16 *h = reinterpret_cast<const __nv_bfloat16 *>(&raw);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = __bfloat162float(h[j]);
+        if (gate) {
+            const uint4 yraw = __ldg(reinterpret_cast<const uint4 *>(gate + off));
+            const __nv_bfloat16 *yh = reinterpret_cast<const __nv_bfloat16 *>(&yraw);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (!(__bfloat162float(yh[j]) > 0.f)) f[j] *= slope;
+        }
+    }
+};
 
-// ---- weight / bias gradient -----------------------------------------------------------------------
-// dW[co][k] = sum_pix dpre[pix][co] * im2col[pix][k]  as  M = co (64), N = k (96), K = pixels.  A CTA walks tiles, its 8
-// warps = 4 row groups x 2 channel halves hold a 32 x 96 accumulator each; the row groups are summed through shared memory
-// and every CTA writes one partial [64][96]; dconv0_bwd_w_reduce_kernel sums the CTA partials in order.
-constexpr int kC0DtPitch = kC0TH * kC0TW + 8;           // 136 bf16 per channel row of the transposed dpre tile
+// ---- weight (/ bias) gradient -----------------------------------------------------------------------
+// dW[n][k] = sum_pix map[pix][n] * im2col[pix][k]  as  M = n (64), N = k (KPad), K = pixels.  A CTA walks tiles, its 8
+// warps = 4 row groups x 2 channel halves hold a 32 x KPad accumulator each; the row groups are summed through shared
+// memory and every CTA writes one partial [64][KPad]; c0_dw_reduce_kernel sums the CTA partials in order.
+constexpr int kC0DtPitch = kC0TH * kC0TW + 8;           // 136 bf16 per channel row of the transposed map tile
 
-__global__ void __launch_bounds__(kC0Threads) dconv0_bwd_w_kernel(const float *__restrict__ x, const __nv_bfloat16 *__restrict__ y,
-                                                                  const __nv_bfloat16 *__restrict__ dy, float *__restrict__ part,
-                                                                  int S, int total_tiles, float slope)
+template <int KS, int PAD, bool HEAD>
+__global__ void __launch_bounds__(kC0Threads) c0_dw_kernel(C0Image img, C0Map map, float *__restrict__ part, int S, int total_tiles)
 {
-    __shared__ __align__(16) __nv_bfloat16 patch[kC0Cin * kC0PH * kC0PPitch];
-    __shared__ __align__(16) __nv_bfloat16 dt[kC0Cout * kC0DtPitch];             // dpre transposed: [co][pixel of the tile]
-    __shared__ float red[kC0Cout * 97];
+    using G = C0Geom<KS>;
+    constexpr int NT = G::KPad / 8;
+    __shared__ __align__(16) __nv_bfloat16 patch[kC0Cin * G::PH * G::PPitch];
+    __shared__ __align__(16) __nv_bfloat16 dt[kC0Cout * kC0DtPitch];             // map tile transposed: [channel][pixel]
+    __shared__ float red[kC0Cout * (G::KPad + 1)];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, q = lane & 3;
     const int rg = warp & 3, ch = warp >> 2;
-    const int S2 = S / 2, S4 = S / 4, tiles_x = S2 / kC0TW, tiles_img = tiles_x * (S2 / kC0TH);
-    float acc[2][12][4];
+    const int S2 = S / 2, tiles_x = S2 / kC0TW, tiles_img = tiles_x * (S2 / kC0TH);
+    float acc[2][NT][4];
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-        for (int nt = 0; nt < 12; ++nt)
+        for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
             for (int j = 0; j < 4; ++j) acc[mt][nt][j] = 0.f;
-    int boff[12];                                       // patch offset of im2col column nt * 8 + g
+    int boff[NT];                                       // patch offset of im2col column nt * 8 + g
 #pragma unroll
-    for (int nt = 0; nt < 12; ++nt) boff[nt] = c0_col_offset(nt * 8 + g);
+    for (int nt = 0; nt < NT; ++nt) boff[nt] = c0_col_offset<KS>(nt * 8 + g);
     const __nv_bfloat16 one = __float2bfloat16_rn(1.f), zero = __float2bfloat16_rn(0.f);
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int b = tile / tiles_img, t = tile - b * tiles_img;
         const int oy0 = (t / tiles_x) * kC0TH, ox0 = (t % tiles_x) * kC0TW;
         __syncthreads();
-        c0_stage_patch(patch, x + (size_t)b * kC0Cin * S * S, S, oy0, ox0);
-        {   // dpre of the tile, transposed: thread -> (pixel, 8 channels)
-            const size_t img = (size_t)b * S2 * S2 * kC0Cout;
+        c0_stage_patch<KS, PAD>(patch, img, (size_t)b * kC0Cin * S * S, S, oy0, ox0);
+        {   // map tile, transposed: thread -> (pixel, 8 channels)
+            const size_t mimg = (size_t)b * S2 * S2 * kC0Cout;
             for (int i = threadIdx.x; i < kC0TH * kC0TW * 8; i += kC0Threads) {
                 const int c8 = i & 7, pix = i >> 3, py = pix / kC0TW, px = pix % kC0TW;
-                const size_t off = img + (size_t)c0_s2d_row(oy0 + py, ox0 + px, S4) * kC0Cout + c8 * 8;
-                const uint4 yv = __ldg(reinterpret_cast<const uint4 *>(y + off));
-                const uint4 gv = __ldg(reinterpret_cast<const uint4 *>(dy + off));
-                const __nv_bfloat16 *yh = reinterpret_cast<const __nv_bfloat16 *>(&yv);
-                const __nv_bfloat16 *gh = reinterpret_cast<const __nv_bfloat16 *>(&gv);
+                float f[8];
+                map.load8(mimg + (size_t)c0_map_row<HEAD>(oy0 + py, ox0 + px, S2) * kC0Cout + c8 * 8, f);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) dt[(c8 * 8 + j) * kC0DtPitch + pix] = __float2bfloat16_rn(c0_dpre(gh[j], yh[j], slope));
+                for (int j = 0; j < 8; ++j) dt[(c8 * 8 + j) * kC0DtPitch + pix] = __float2bfloat16_rn(f[j]);
             }
         }
         __syncthreads();
@@ -194,17 +242,17 @@ __global__ void __launch_bounds__(kC0Threads) dconv0_bwd_w_kernel(const float *_
                 a[mt][2] = lds32(base + 16);
                 a[mt][3] = lds32(base + 8 * kC0DtPitch * 2 + 16);
             }
-            const __nv_bfloat16 *prow = patch + (2 * row) * kC0PPitch;
+            const __nv_bfloat16 *prow = patch + (2 * row) * G::PPitch;
 #pragma unroll
-            for (int nt = 0; nt < 12; ++nt) {
+            for (int nt = 0; nt < NT; ++nt) {
                 // B[pix][kcol]: pixels 2q, 2q+1 (b0) and 2q+8, 2q+9 (b1) of im2col column kcol = nt * 8 + g
                 const int kcol = nt * 8 + g;
                 __nv_bfloat16 e[4];
-                if (kcol < kC0KReal) {
+                if (kcol < G::KReal) {
                     const __nv_bfloat16 *src = prow + boff[nt];
                     e[0] = src[2 * (2 * q)]; e[1] = src[2 * (2 * q + 1)]; e[2] = src[2 * (2 * q + 8)]; e[3] = src[2 * (2 * q + 9)];
                 } else {
-                    e[0] = e[1] = e[2] = e[3] = kcol == kC0OnesCol ? one : zero;
+                    e[0] = e[1] = e[2] = e[3] = (!HEAD && kcol == kC0OnesCol) ? one : zero;
                 }
                 const uint32_t b0 = (uint32_t)__bfloat16_as_ushort(e[0]) | ((uint32_t)__bfloat16_as_ushort(e[1]) << 16);
                 const uint32_t b1 = (uint32_t)__bfloat16_as_ushort(e[2]) | ((uint32_t)__bfloat16_as_ushort(e[3]) << 16);
@@ -220,65 +268,104 @@ __global__ void __launch_bounds__(kC0Threads) dconv0_bwd_w_kernel(const float *_
 #pragma unroll
             for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-                for (int nt = 0; nt < 12; ++nt)
+                for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         const int co = ch * 32 + mt * 16 + g + 8 * (j >> 1), k = nt * 8 + 2 * q + (j & 1);
-                        float *d = red + co * 97 + k;
+                        float *d = red + co * (G::KPad + 1) + k;
                         *d = r == 0 ? acc[mt][nt][j] : *d + acc[mt][nt][j];
                     }
         }
     }
     __syncthreads();
-    float *dst = part + (size_t)blockIdx.x * kC0Cout * 96;
-    for (int i = threadIdx.x; i < kC0Cout * 96; i += kC0Threads) dst[i] = red[(i / 96) * 97 + i % 96];
+    float *dst = part + (size_t)blockIdx.x * kC0Cout * G::KPad;
+    for (int i = threadIdx.x; i < kC0Cout * G::KPad; i += kC0Threads) dst[i] = red[(i / G::KPad) * (G::KPad + 1) + i % G::KPad];
 }
 
-// dw (64, 3, 5, 5) and dbias (64) from the CTA partials; accumulate != 0 adds to the existing values
-__global__ void __launch_bounds__(256) dconv0_bwd_w_reduce_kernel(const float *__restrict__ part, int nparts, float *__restrict__ dw,
-                                                                  float *__restrict__ dbias, int accumulate)
+// dw (64, 3, KS, KS) (and, conv0 only, dbias (64) from the ones column) from the CTA partials; accumulate != 0 adds
+template <int KS, bool HEAD>
+__global__ void __launch_bounds__(256) c0_dw_reduce_kernel(const float *__restrict__ part, int nparts, float *__restrict__ dw,
+                                                           float *__restrict__ dbias, int accumulate)
 {
-    const int i = blockIdx.x * 256 + threadIdx.x;       // (co, k) with k < 96
-    if (i >= kC0Cout * 96) return;
-    const int co = i / 96, k = i % 96;
+    using G = C0Geom<KS>;
+    const int i = blockIdx.x * 256 + threadIdx.x;       // (n, k) with k < KPad
+    if (i >= kC0Cout * G::KPad) return;
+    const int co = i / G::KPad, k = i % G::KPad;
     float s = 0.f;
-    for (int p = 0; p < nparts; ++p) s += part[(size_t)p * kC0Cout * 96 + i];
-    if (k == kC0OnesCol) {
+    for (int p = 0; p < nparts; ++p) s += part[(size_t)p * kC0Cout * G::KPad + i];
+    if (!HEAD && k == kC0OnesCol) {
         if (dbias) dbias[co] = accumulate ? dbias[co] + s : s;
         return;
     }
-    const int kx = k % 6, r = k / 6, ky = r % 5, ci = r / 5;
-    if (k >= kC0KReal || kx >= 5) return;
-    float *d = dw + ((size_t)co * kC0Cin + ci) * 25 + ky * 5 + kx;
+    const int kx = k % G::KX, r = k / G::KX, ky = r % KS, ci = r / KS;
+    if (k >= G::KReal || kx >= KS) return;
+    float *d = dw + ((size_t)(co * kC0Cin + ci) * KS + ky) * KS + kx;
     *d = accumulate ? *d + s : s;
 }
 
-// ---- input gradient -----------------------------------------------------------------------------------
-// dX[b][ci][2i + py][2j + px] = sum_{co, taps of the parity class} dpre[b][i + 1 - ky/2][j + 1 - kx/2][co] * w[co][ci][ky][kx]
-// per class a GEMM  M = pixels (i, j), K = taps x 64, N = 3 -> 8.  A CTA owns an 8 x 16 block of (i, j): the dpre tile with
-// a one-pixel halo sits in shared memory (pixel pitch 144 B: conflict-free fragment loads), the weights as ready-made B
-// fragments; the 16 x 32 x 3 result goes through shared memory so that global rows are written contiguously.
-constexpr int kC0XPitch = kC0Cout * 2 + 16;             // bytes per staged dpre pixel
-constexpr int kC0HaloW = kC0TW + 2, kC0HaloH = kC0TH + 2;
+// head only: dbias[c] = sum over the batch and all pixels of g = dout * (1 - out^2).  Two stages, fixed order:
+// grid (3, kC0BiasChunks) partial sums, then one warp per channel.
+constexpr int kC0BiasChunks = 32;
+__global__ void __launch_bounds__(256) c0_head_dbias_kernel(C0Image img, float *__restrict__ part, int batch, int S)
+{
+    __shared__ float sh[8];
+    const int c = blockIdx.x, chunk = blockIdx.y;
+    const size_t plane = (size_t)S * S, total = (size_t)batch * plane;
+    const size_t per = (total + kC0BiasChunks - 1) / kC0BiasChunks, i0 = chunk * per, i1 = i0 + per < total ? i0 + per : total;
+    float s = 0.f;
+#pragma unroll 4
+    for (size_t i = i0 + threadIdx.x; i < i1; i += 256) {
+        const size_t b = i / plane, r = i - b * plane;
+        s += img.at((b * kC0Cin + c) * plane + r);
+    }
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int k = 0; k < 8; ++k) t += sh[k];
+        part[c * kC0BiasChunks + chunk] = t;
+    }
+}
+__global__ void __launch_bounds__(96) c0_head_dbias_final_kernel(const float *__restrict__ part, float *__restrict__ dbias)
+{
+    const int c = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float s = warp_sum(part[c * kC0BiasChunks + lane]);
+    if (lane == 0) dbias[c] = s;
+}
 
-__global__ void __launch_bounds__(kC0Threads) dconv0_bwd_x_kernel(const __nv_bfloat16 *__restrict__ y, const __nv_bfloat16 *__restrict__ dy,
-                                                                  const float *__restrict__ w, float *__restrict__ dx, int S,
-                                                                  int total_tiles, float slope)
+// ---- map -> image ---------------------------------------------------------------------------------------
+// img[b][c][2i + p_y][2j + p_x] = sum_{n, taps of the parity class} map[b][i + d_y][j + d_x][n] * w[n][c][ky][kx], with
+// p = (k + PAD) & 1 and d = (p + PAD - k) / 2 per dimension: per class a GEMM  M = pixels (i, j), K = taps x 64, N = 3 -> 8.
+// A CTA owns an 8 x 16 block of (i, j): the map tile with a one-pixel halo sits in shared memory (pixel pitch 144 B:
+// conflict-free fragment loads), the weights as ready-made B fragments; the 16 x 32 x 3 result goes through shared memory
+// so that global rows are written contiguously.  conv0 dx: raw; head forward: tanh(. + bias).
+constexpr int kC0XPitch = kC0Cout * 2 + 16;             // bytes per staged map pixel
+constexpr int kC0HaloW = kC0TW + 2, kC0HaloH = kC0TH + 2;
+template <int KS> constexpr size_t c0_map2img_smem()
+{
+    return (size_t)kC0HaloH * kC0HaloW * kC0XPitch + (size_t)KS * KS * 4 * 32 * sizeof(uint2) +
+           (size_t)kC0Cin * (2 * kC0TH) * (2 * kC0TW + 1) * sizeof(float);
+}
+
+template <int KS, int PAD, bool HEAD>
+__global__ void __launch_bounds__(kC0Threads) c0_map2img_kernel(C0Map map, const float *__restrict__ w, const float *__restrict__ bias,
+                                                                float *__restrict__ out, int S, int total_tiles)
 {
     extern __shared__ __align__(16) unsigned char c0x_smem[];
     unsigned char *ds = c0x_smem;                                                              // [10 x 18 pixels][144 B]
-    uint2 *wfrag = reinterpret_cast<uint2 *>(ds + kC0HaloH * kC0HaloW * kC0XPitch);            // [25 taps][4 k-steps][32 lanes]
-    float *outs = reinterpret_cast<float *>(wfrag + 25 * 4 * 32);                              // [3][16][33]
+    uint2 *wfrag = reinterpret_cast<uint2 *>(ds + kC0HaloH * kC0HaloW * kC0XPitch);            // [taps][4 k-steps][32 lanes]
+    float *outs = reinterpret_cast<float *>(wfrag + KS * KS * 4 * 32);                         // [3][16][33]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, q = lane & 3;
-    const int S2 = S / 2, S4 = S / 4, tiles_x = S2 / kC0TW, tiles_img = tiles_x * (S2 / kC0TH);
-    for (int i = threadIdx.x; i < 25 * 4 * 32; i += kC0Threads) {
+    const int S2 = S / 2, tiles_x = S2 / kC0TW, tiles_img = tiles_x * (S2 / kC0TH);
+    for (int i = threadIdx.x; i < KS * KS * 4 * 32; i += kC0Threads) {
         const int ln = i & 31, ks = (i >> 5) & 3, tap = i >> 7, gg = ln >> 2, qq = ln & 3;
         float v[4] = {0.f, 0.f, 0.f, 0.f};
         if (gg < kC0Cin) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                const int co = ks * 16 + 2 * qq + (e & 1) + 8 * (e >> 1);
-                v[e] = __ldg(w + ((size_t)co * kC0Cin + gg) * 25 + tap);
+                const int n = ks * 16 + 2 * qq + (e & 1) + 8 * (e >> 1);
+                v[e] = __ldg(w + ((size_t)n * kC0Cin + gg) * (KS * KS) + tap);
             }
         }
         wfrag[i] = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
@@ -288,20 +375,14 @@ __global__ void __launch_bounds__(kC0Threads) dconv0_bwd_x_kernel(const __nv_bfl
         const int i0 = (t / tiles_x) * kC0TH, j0 = (t % tiles_x) * kC0TW;
         __syncthreads();
         {
-            const size_t img = (size_t)b * S2 * S2 * kC0Cout;
+            const size_t mimg = (size_t)b * S2 * S2 * kC0Cout;
             for (int i = threadIdx.x; i < kC0HaloH * kC0HaloW * 8; i += kC0Threads) {
                 const int c8 = i & 7, pix = i >> 3, hy = pix / kC0HaloW, hx = pix % kC0HaloW;
                 const int oy = i0 + hy - 1, ox = j0 + hx - 1;
                 uint4 o = make_uint4(0, 0, 0, 0);
                 if (oy >= 0 && oy < S2 && ox >= 0 && ox < S2) {
-                    const size_t off = img + (size_t)c0_s2d_row(oy, ox, S4) * kC0Cout + c8 * 8;
-                    const uint4 yv = __ldg(reinterpret_cast<const uint4 *>(y + off));
-                    const uint4 gv = __ldg(reinterpret_cast<const uint4 *>(dy + off));
-                    const __nv_bfloat16 *yh = reinterpret_cast<const __nv_bfloat16 *>(&yv);
-                    const __nv_bfloat16 *gh = reinterpret_cast<const __nv_bfloat16 *>(&gv);
                     float f[8];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) f[j] = c0_dpre(gh[j], yh[j], slope);
+                    map.load8(mimg + (size_t)c0_map_row<HEAD>(oy, ox, S2) * kC0Cout + c8 * 8, f);
                     o = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
                 }
                 *reinterpret_cast<uint4 *>(ds + (size_t)pix * kC0XPitch + c8 * 16) = o;
@@ -314,10 +395,12 @@ __global__ void __launch_bounds__(kC0Threads) dconv0_bwd_x_kernel(const __nv_bfl
 #pragma unroll
             for (int j = 0; j < 4; ++j) acc[c][j] = 0.f;
 #pragma unroll
-        for (int ky = 0; ky < 5; ++ky)
+        for (int ky = 0; ky < KS; ++ky)
 #pragma unroll
-            for (int kx = 0; kx < 5; ++kx) {
-                const int cls = (ky & 1) * 2 + (kx & 1), dyy = 1 - (ky >> 1), dxx = 1 - (kx >> 1);
+            for (int kx = 0; kx < KS; ++kx) {
+                constexpr int dummy = 0; (void)dummy;
+                const int py = (ky + PAD) & 1, px = (kx + PAD) & 1;
+                const int cls = py * 2 + px, dyy = (py + PAD - ky) / 2, dxx = (px + PAD - kx) / 2;
                 // tile-local halo coordinates of pixel (i = i0 + warp, j = j0 + g [+ 8]) shifted by (dyy, dxx)
                 const unsigned char *p0 = ds + (size_t)((warp + 1 + dyy) * kC0HaloW + (g + 1 + dxx)) * kC0XPitch + 4 * q;
                 const unsigned char *p1 = p0 + 8 * kC0XPitch;
@@ -326,11 +409,11 @@ __global__ void __launch_bounds__(kC0Threads) dconv0_bwd_x_kernel(const __nv_bfl
                     uint32_t a[4];
                     a[0] = lds32(p0 + ks * 32); a[1] = lds32(p1 + ks * 32);
                     a[2] = lds32(p0 + ks * 32 + 16); a[3] = lds32(p1 + ks * 32 + 16);
-                    const uint2 bf = wfrag[((ky * 5 + kx) * 4 + ks) * 32 + lane];
+                    const uint2 bf = wfrag[((ky * KS + kx) * 4 + ks) * 32 + lane];
                     mma_bf16_16816(acc[cls], a, bf.x, bf.y);
                 }
             }
-        // C[pix g (+8)][ci = 2q, 2q+1] -> outs[ci][row 2*warp + py][col 2*(g [+8]) + px]
+        // C[pix g (+8)][c = 2q, 2q+1] -> outs[c][row 2*warp + py][col 2*(g [+8]) + px]
         constexpr int OW = 2 * kC0TW + 1;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
@@ -342,10 +425,12 @@ __global__ void __launch_bounds__(kC0Threads) dconv0_bwd_x_kernel(const __nv_bfl
             }
         }
         __syncthreads();
-        float *dxb = dx + (size_t)b * kC0Cin * S * S;
+        float *ob = out + (size_t)b * kC0Cin * S * S;
         for (int i = threadIdx.x; i < kC0Cin * 2 * kC0TH * 2 * kC0TW; i += kC0Threads) {
             const int col = i % (2 * kC0TW), r = i / (2 * kC0TW), row = r % (2 * kC0TH), ci = r / (2 * kC0TH);
-            dxb[((size_t)ci * S + 2 * i0 + row) * S + 2 * j0 + col] = outs[(ci * 2 * kC0TH + row) * OW + col];
+            float v = outs[(ci * 2 * kC0TH + row) * OW + col];
+            if (HEAD) v = tanhf(v + __ldg(bias + ci));
+            ob[((size_t)ci * S + 2 * i0 + row) * S + 2 * j0 + col] = v;
         }
     }
 }
@@ -632,12 +717,42 @@ static int head_geom(const char *who, int batch, int channels, int hw, HeadGeom 
 static int c0_geom(const char *who, int batch, int cin, int cout, int size, int &tiles, int &grid)
 {
     HG_REQUIRE(batch > 0 && size > 0, HG_ERR_INVALID_ARG, "%s: dims must be positive", who);
-    HG_REQUIRE(cin == kC0Cin && cout == kC0Cout, HG_ERR_UNSUPPORTED, "%s: only Conv2d(3 -> 64) is built (got %d -> %d)", who, cin, cout);
+    HG_REQUIRE(cin == kC0Cin && cout == kC0Cout, HG_ERR_UNSUPPORTED, "%s: only 3 <-> 64 channels are built (got %d, %d)", who, cin, cout);
     HG_REQUIRE(size % (2 * kC0TW) == 0, HG_ERR_UNSUPPORTED, "%s: image size must be a multiple of %d (got %d)", who, 2 * kC0TW, size);
     const int S2 = size / 2;
     tiles = batch * (S2 / kC0TH) * (S2 / kC0TW);
     grid = tiles < 2 * sm_count() ? tiles : 2 * sm_count();
     return HG_OK;
+}
+
+template <int KS, int PAD, bool HEAD>
+static int c0_launch_dw(const char *who, const C0Image &img, const C0Map &map, float *dw, float *dbias, void *workspace,
+                        long long workspace_bytes, int size, int tiles, int grid, int accumulate, cudaStream_t st)
+{
+    using G = C0Geom<KS>;
+    const int g = grid < sm_count() ? grid : sm_count();          // one CTA per SM: each writes one partial
+    HG_REQUIRE(workspace && workspace_bytes >= (long long)g * kC0Cout * G::KPad * (long long)sizeof(float), HG_ERR_INVALID_ARG,
+               "%s: workspace too small", who);
+    float *part = static_cast<float *>(workspace);
+    c0_dw_kernel<KS, PAD, HEAD><<<g, kC0Threads, 0, st>>>(img, map, part, size, tiles);
+    int rc = check_launch(who);
+    if (rc) return rc;
+    c0_dw_reduce_kernel<KS, HEAD><<<(kC0Cout * G::KPad + 255) / 256, 256, 0, st>>>(part, g, dw, dbias, accumulate);
+    return check_launch(who);
+}
+
+template <int KS, int PAD, bool HEAD>
+static int c0_launch_map2img(const char *who, const C0Map &map, const float *w, const float *bias, float *out, int size, int tiles,
+                             int grid, cudaStream_t st)
+{
+    constexpr size_t smem = c0_map2img_smem<KS>();
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(c0_map2img_kernel<KS, PAD, HEAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr = true;
+    }
+    c0_map2img_kernel<KS, PAD, HEAD><<<grid, kC0Threads, smem, st>>>(map, w, bias, out, size, tiles);
+    return check_launch(who);
 }
 
 }  // namespace hg
@@ -651,15 +766,16 @@ extern "C" int hg_dconv0_fwd(const float *x, const float *w, const float *bias, 
     int tiles, grid;
     int rc = c0_geom("hg_dconv0_fwd", batch, cin, cout, size, tiles, grid);
     if (rc) return rc;
-    dconv0_fwd_kernel<<<grid, kC0Threads, 0, static_cast<cudaStream_t>(stream)>>>(x, w, bias, static_cast<__nv_bfloat16 *>(y_s2d), size,
-                                                                                 tiles, neg_slope);
+    c0_img2map_kernel<5, 2, false><<<grid, kC0Threads, 0, static_cast<cudaStream_t>(stream)>>>(C0Image{x, nullptr}, w, bias,
+                                                                                               static_cast<__nv_bfloat16 *>(y_s2d), size, tiles,
+                                                                                               neg_slope);
     return check_launch("hg_dconv0_fwd");
 }
 
 extern "C" long long hg_dconv0_bwd_workspace_bytes(int batch, int size)
 {
     if (batch <= 0 || size <= 0 || size % (2 * kC0TW)) return -1;
-    return (long long)2 * sm_count() * kC0Cout * 96 * (long long)sizeof(float);
+    return (long long)sm_count() * kC0Cout * C0Geom<5>::KPad * (long long)sizeof(float);
 }
 
 extern "C" int hg_dconv0_bwd(const float *x, const float *w, const void *y_s2d, const void *dy_s2d, float *dx, float *dw, float *dbias,
@@ -672,29 +788,61 @@ extern "C" int hg_dconv0_bwd(const float *x, const float *w, const void *y_s2d, 
     int rc = c0_geom("hg_dconv0_bwd", batch, cin, cout, size, tiles, grid);
     if (rc) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const __nv_bfloat16 *yp = static_cast<const __nv_bfloat16 *>(y_s2d), *gp = static_cast<const __nv_bfloat16 *>(dy_s2d);
+    const C0Map map{static_cast<const __nv_bfloat16 *>(dy_s2d), static_cast<const __nv_bfloat16 *>(y_s2d), neg_slope};
     if (dw) {
-        int g = grid < sm_count() ? grid : sm_count();          // one CTA per SM: each writes one partial
-        HG_REQUIRE(workspace && workspace_bytes >= (long long)g * kC0Cout * 96 * (long long)sizeof(float), HG_ERR_INVALID_ARG,
-                   "hg_dconv0_bwd: workspace smaller than hg_dconv0_bwd_workspace_bytes()");
-        float *part = static_cast<float *>(workspace);
-        dconv0_bwd_w_kernel<<<g, kC0Threads, 0, st>>>(x, yp, gp, part, size, tiles, neg_slope);
-        rc = check_launch("hg_dconv0_bwd(dw)");
-        if (rc) return rc;
-        dconv0_bwd_w_reduce_kernel<<<(kC0Cout * 96 + 255) / 256, 256, 0, st>>>(part, g, dw, dbias, accumulate);
-        rc = check_launch("hg_dconv0_bwd(reduce)");
+        rc = c0_launch_dw<5, 2, false>("hg_dconv0_bwd(dw)", C0Image{x, nullptr}, map, dw, dbias, workspace, workspace_bytes, size, tiles,
+                                       grid, accumulate, st);
         if (rc) return rc;
     }
+    if (dx) rc = c0_launch_map2img<5, 2, false>("hg_dconv0_bwd(dx)", map, w, nullptr, dx, size, tiles, grid, st);
+    return rc;
+}
+
+// The generator's patched 128 x 128 head: out = tanh(ConvTranspose2d(64 -> 3, k4, s2, p1)(x) + bias)
+//   x (B, S/2, S/2, 64) bf16 NHWC, w (64, 3, 4, 4) fp32 torch layout, out (B, 3, S, S) fp32 NCHW, S = size (the OUTPUT extent)
+extern "C" int hg_head128_fwd(const void *x, const float *w, const float *bias, float *out, int batch, int cin, int cout, int size,
+                              void *stream)
+{
+    HG_REQUIRE(x && w && bias && out, HG_ERR_INVALID_ARG, "hg_head128_fwd: null pointer");
+    int tiles, grid;
+    int rc = c0_geom("hg_head128_fwd", batch, cout, cin, size, tiles, grid);
+    if (rc) return rc;
+    const C0Map map{static_cast<const __nv_bfloat16 *>(x), nullptr, 1.f};
+    return c0_launch_map2img<4, 1, true>("hg_head128_fwd", map, w, bias, out, size, tiles, grid, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" long long hg_head128_bwd_workspace_bytes(int batch, int size)
+{
+    if (batch <= 0 || size <= 0 || size % (2 * kC0TW)) return -1;
+    return ((long long)sm_count() * kC0Cout * C0Geom<4>::KPad + kC0Cin * kC0BiasChunks) * (long long)sizeof(float);
+}
+
+// backward: g = dout * (1 - out^2); dx (B, S/2, S/2, 64) bf16 (may be null), dw (64, 3, 4, 4) + dbias (3) fp32 (both or neither)
+extern "C" int hg_head128_bwd(const void *x, const float *w, const float *out, const float *dout, void *dx, float *dw, float *dbias,
+                              void *workspace, long long workspace_bytes, int batch, int cin, int cout, int size, void *stream)
+{
+    HG_REQUIRE(x && w && out && dout, HG_ERR_INVALID_ARG, "hg_head128_bwd: null pointer");
+    HG_REQUIRE((dw == nullptr) == (dbias == nullptr), HG_ERR_INVALID_ARG, "hg_head128_bwd: dw and dbias come as a pair");
+    int tiles, grid;
+    int rc = c0_geom("hg_head128_bwd", batch, cout, cin, size, tiles, grid);
+    if (rc) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const C0Image g{dout, out};
     if (dx) {
-        constexpr size_t smem = (size_t)kC0HaloH * kC0HaloW * kC0XPitch + 25 * 4 * 32 * sizeof(uint2) +
-                                (size_t)kC0Cin * (2 * kC0TH) * (2 * kC0TW + 1) * sizeof(float);
-        static bool attr = false;
-        if (!attr) {
-            cudaFuncSetAttribute(dconv0_bwd_x_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            attr = true;
-        }
-        dconv0_bwd_x_kernel<<<grid, kC0Threads, smem, st>>>(yp, gp, w, dx, size, tiles, neg_slope);
-        rc = check_launch("hg_dconv0_bwd(dx)");
+        c0_img2map_kernel<4, 1, true><<<grid, kC0Threads, 0, st>>>(g, w, nullptr, static_cast<__nv_bfloat16 *>(dx), size, tiles, 1.f);
+        rc = check_launch("hg_head128_bwd(dx)");
+        if (rc) return rc;
+    }
+    if (dw) {
+        const C0Map map{static_cast<const __nv_bfloat16 *>(x), nullptr, 1.f};
+        HG_REQUIRE(workspace_bytes >= hg_head128_bwd_workspace_bytes(batch, size), HG_ERR_INVALID_ARG,
+                   "hg_head128_bwd: workspace smaller than hg_head128_bwd_workspace_bytes()");
+        rc = c0_launch_dw<4, 1, true>("hg_head128_bwd(dw)", g, map, dw, nullptr, workspace, workspace_bytes, size, tiles, grid, 0, st);
+        if (rc) return rc;
+        float *bpart = static_cast<float *>(workspace) + (size_t)sm_count() * kC0Cout * C0Geom<4>::KPad;
+        c0_head_dbias_kernel<<<dim3(kC0Cin, kC0BiasChunks), 256, 0, st>>>(g, bpart, batch, size);
+        c0_head_dbias_final_kernel<<<1, 96, 0, st>>>(bpart, dbias);
+        rc = check_launch("hg_head128_bwd(dbias)");
     }
     return rc;
 }

@@ -157,8 +157,10 @@ class _RotateResample(torch.autograd.Function):
 
 def rotate_resample(vol: Tensor, a_inv: Tensor, border: int = HG_BORDER_REFERENCE, in_layout: int = HG_NCDHW,
                     out_layout: int = HG_NCDHW) -> Tensor:
-    """Differentiable (w.r.t. `vol`) rigid-body rotate + trilinear resample."""
-    return _RotateResample.apply(vol, a_inv, border, in_layout, out_layout)
+    """Differentiable (w.r.t. `vol`) rigid-body rotate + trilinear resample: the registered custom op
+    `torch.ops.hologan.rotate_resample` (lightning_gan_zoo_b200/torch_ops.py)."""
+    from . import torch_ops  # noqa: F401  (registers the hologan:: operators on first use)
+    return torch.ops.hologan.rotate_resample(vol, a_inv, int(border), int(in_layout), int(out_layout))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -661,6 +663,50 @@ class _FinalConvTanh(torch.autograd.Function):
 def final_conv_tanh(x_cl: Tensor, weight: Tensor, bias: Tensor) -> Tensor:
     """tanh(conv2d(x, weight, bias, kernel 3, padding 1)) with x (B,S,S,C) bf16 NHWC -> (B,Cout,S,S) fp32 NCHW."""
     return _FinalConvTanh.apply(x_cl, weight, bias)
+
+
+class _Head128Tanh(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x_cl, weight, bias):
+        _require_cuda(x_cl, weight, bias)
+        if x_cl.dtype != torch.bfloat16 or not x_cl.is_contiguous() or x_cl.dim() != 4 or x_cl.shape[1] != x_cl.shape[2]:
+            raise ValueError("x must be a contiguous (B,S,S,C) bf16 tensor")
+        b, s2, cin = x_cl.shape[0], x_cl.shape[1], x_cl.shape[3]
+        w = weight.detach().float().contiguous()
+        bb = bias.detach().float().contiguous()
+        cout = w.shape[1]
+        if tuple(w.shape) != (cin, cout, 4, 4):
+            raise ValueError("weight must be the ConvTranspose2d parameter (Cin, Cout, 4, 4)")
+        out = torch.empty((b, cout, 2 * s2, 2 * s2), dtype=torch.float32, device=x_cl.device)
+        _lib.call("hg_head128_fwd", _ptr(x_cl), _ptr(w), _ptr(bb), _ptr(out), b, cin, cout, 2 * s2, _stream())
+        ctx.save_for_backward(x_cl, w, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x_cl, w, out = ctx.saved_tensors
+        b, s2, cin = x_cl.shape[0], x_cl.shape[1], x_cl.shape[3]
+        cout = w.shape[1]
+        dout = dout.float().contiguous()
+        nbytes = _lib.load().hg_head128_bwd_workspace_bytes(b, 2 * s2)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=x_cl.device)
+        dx = torch.empty_like(x_cl) if ctx.needs_input_grad[0] else None
+        want_w = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
+        dw = torch.empty_like(w) if want_w else None
+        db = torch.empty(cout, dtype=torch.float32, device=x_cl.device) if want_w else None
+        _lib.call("hg_head128_bwd", _ptr(x_cl), _ptr(w), _ptr(out), _ptr(dout), _ptr(dx), _ptr(dw), _ptr(db), _ptr(ws), nbytes, b,
+                  cin, cout, 2 * s2, _stream())
+        return dx, dw, db
+
+
+def head128_tanh(x_cl: Tensor, weight: Tensor, bias: Tensor) -> Tensor:
+    """tanh(conv_transpose2d(x, weight, bias, kernel 4, stride 2, padding 1)): the patched 128 x 128 head with
+    x (B,S,S,64) bf16 NHWC -> (B,3,2S,2S) fp32 NCHW, weight the torch ConvTranspose2d parameter (64, 3, 4, 4)."""
+    return _Head128Tanh.apply(x_cl, weight, bias)
+
+
+def head128_supported(cin: int, cout: int, size_in: int) -> bool:
+    return cin == 64 and cout == 3 and size_in % 16 == 0
 
 
 # ------------------------------------------------------------------------------------------------

@@ -97,6 +97,26 @@ def test_render_views_equals_per_view_forward(in_planes, bf16):
         net.render_views(z, np.zeros((4, 5)))
 
 
+@pytest.mark.parametrize("in_planes,bf16,tol", [(8, False, 1e-5), (64, True, 2e-2)])
+def test_render_views_vs_oracle(in_planes, bf16, tol):
+    """`Generator.render_views` (trunk once per latent, rotate + decoder per view) against the ORACLE's per-view forward
+    (the reference's pattern: core/figures/types.py:300-322 calls generator(z, view_in=view) once per view)."""
+    gen = torch.Generator().manual_seed(31)
+    p = orc.init_generator_params(in_planes, 3, 128, 64, generator=gen, bias_std=0.05)
+    z = torch.rand(3, 128, generator=gen) * 2 - 1
+    views = np.zeros((5, 6))
+    views[:, 0] = np.deg2rad(np.linspace(220, 320, 5))
+    views[:, 1] = np.deg2rad(90.0)
+    views[:, 2] = 1.0
+    net = Generator(in_planes, 3, 128, SimpleNamespace(), 64).to(DEV).eval()
+    net.load_state_dict(p)
+    with torch.autocast("cuda", dtype=torch.bfloat16, enabled=bf16), torch.no_grad():
+        sweep = net.render_views(z.to(DEV), views)
+    for v in range(5):
+        ref = orc.generator_forward(p, z, np.repeat(views[v:v + 1], 3, axis=0))
+        assert rel_err(sweep[:, v].float(), ref) < tol, v
+
+
 def _bf16_errors(net, p, z, view, dout):
     zg = z.to(DEV).requires_grad_(True)
     with torch.autocast("cuda", dtype=torch.bfloat16):
@@ -105,50 +125,68 @@ def _bf16_errors(net, p, z, view, dout):
     return out, zg.grad, dict(net.named_parameters())
 
 
-def test_generator_bf16_tensor_core_path_vs_oracle():
-    """Full-width generator (in_planes 64) under bf16 autocast: tcgen05 convs + AdaIN + rotate, forward
-    and backward, against the fp32 oracle.
+def _rms_err(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return ((a - b).pow(2).mean().sqrt() / b.pow(2).mean().sqrt().clamp_min(1e-30)).item()
 
-    Tolerances (max|a-b| / max|b|):
-      * activations (output image): north_star's 2e-2;
-      * gradients: bf16 rounding of the stored activations / gradients is amplified by every AdaIN backward
-        (it projects out the mean and x_hat components of the incoming gradient, which carry most of its
-        energy), so even stock PyTorch bf16 autocast (cuDNN convs) sits at 5-14 % for the deep layers on this
-        network (tools/bf16_error_report.py).  The bar here: 2e-2 where the stock bf16 path reaches it,
-        otherwise per tensor no worse than 2x, and on average over all tensors no worse than 1.15x, the
-        stock bf16 path's error on the same inputs (single-sample errors scatter by ~1.5x).
-    """
-    gen = torch.Generator().manual_seed(77)
+
+@pytest.mark.parametrize("bsz,seed", [(4, 77), (64, 64)])
+def test_generator_bf16_tensor_core_path_vs_oracle(bsz, seed):
+    """Full-width generator (in_planes 64) under bf16 autocast: tcgen05 convs + AdaIN + rotate, forward and backward,
+    against the fp32 oracle -- at a small batch and at the bench configuration's batch 64 (BASELINE configs[1]: the
+    split-K plans, tile counts and launch shapes bench.py runs).
+
+    Tolerance (max|a-b| / max|b|): north_star's 2e-2 for the output image and for every gradient tensor
+    whose bf16 STORAGE FLOOR allows it.  The floor is measured, not assumed: `orc.generator_forward(bf16_storage=True)`
+    is the fp32 CPU oracle with nothing changed except that every activation / gradient a bf16 pipeline keeps in memory
+    is rounded to bf16 where it is stored and the conv weights are bf16 copies -- no kernel of ours involved.  That alone
+    puts the gradients of everything below block4 at 4-20 % (max-normalised; 4-10 % rms: profiles/r02b_bf16_error_report.txt):
+    rounding flips the ReLU mask of ~0.05 % of the activations per layer and every AdaIN backward projects the mean and
+    x_hat components (most of the energy) out of the incoming gradient, so the relative error of what is left grows
+    layer by layer.  2e-2 is therefore unreachable for those tensors with ANY bf16-operand implementation, and the bar for
+    them is the floor itself: rms-relative error <= 1.25 x the floor's, max-normalised <= 2 x the floor's (a single
+    sample's max scatters by ~1.5x).  Measured: ours sits at 0.98-1.05 x the floor's rms on every tensor (and below the
+    stock cuDNN bf16 path)."""
+    gen = torch.Generator().manual_seed(seed)
     p = orc.init_generator_params(64, 3, 128, 64, generator=gen, bias_std=0.05)
-    bsz = 4
     z = torch.rand(bsz, 128, generator=gen) * 2 - 1
-    view = orc.sample_view(bsz, np.random.RandomState(77))
+    view = orc.sample_view(bsz, np.random.RandomState(seed))
     dout = torch.randn(bsz, 3, 64, 64, generator=gen)
-    pr = {k: v.clone().requires_grad_(True) for k, v in p.items()}
-    zr = z.clone().requires_grad_(True)
-    ref = orc.generator_forward(pr, zr, view)
-    (ref * dout).sum().backward()
+
+    def oracle(bf16_storage):
+        pr = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+        zr = z.clone().requires_grad_(True)
+        out = orc.generator_forward(pr, zr, view, bf16_storage=bf16_storage)
+        (out * dout).sum().backward()
+        return out.detach(), zr.grad, {k: v.grad for k, v in pr.items()}
+
+    ref, dz_ref, g_ref = oracle(False)
+    flo, dz_flo, g_flo = oracle(True)
 
     net = Generator(64, 3, 128, SimpleNamespace(), 64).to(DEV)
     net.load_state_dict(p)
     with torch.autocast("cuda", dtype=torch.bfloat16):
         assert net._use_tensor_core_path(z.to(DEV))
     out, dz, named = _bf16_errors(net, p, z, view, dout)
-    stock = Generator(64, 3, 128, SimpleNamespace(), 64).to(DEV)
-    stock.load_state_dict(p)
-    stock._use_tensor_core_path = lambda _z: False          # same module on torch/cuDNN bf16 convs
-    out_s, dz_s, named_s = _bf16_errors(stock, p, z, view, dout)
 
     assert rel_err(out.float(), ref) < 2e-2
-    ours, theirs = {"dz": rel_err(dz, zr.grad)}, {"dz": rel_err(dz_s, zr.grad)}
-    for k, v in pr.items():
+    ours = {"dz": (rel_err(dz, dz_ref), _rms_err(dz, dz_ref))}
+    floor = {"dz": (rel_err(dz_flo, dz_ref), _rms_err(dz_flo, dz_ref))}
+    for k, g in g_ref.items():
         if k.endswith("convTranspose.bias"):
             assert named[k].grad is None or named[k].grad.abs().max() == 0      # analytically zero
             continue
-        ours[k], theirs[k] = rel_err(named[k].grad, v.grad), rel_err(named_s[k].grad, v.grad)
-    bad = {k: (ours[k], theirs[k]) for k in ours if ours[k] > max(2e-2, 2.0 * theirs[k])}
-    assert not bad, bad
-    mean_ours, mean_theirs = sum(ours.values()) / len(ours), sum(theirs.values()) / len(theirs)
-    assert mean_ours <= 1.15 * mean_theirs, (mean_ours, mean_theirs)
-    assert rel_err(named["final_layer.weight"].grad, pr["final_layer.weight"].grad) < 2e-2
-    assert rel_err(named["block4.zMapping.linear1.weight"].grad, pr["block4.zMapping.linear1.weight"].grad) < 3e-2
+        ours[k] = (rel_err(named[k].grad, g), _rms_err(named[k].grad, g))
+        floor[k] = (rel_err(g_flo[k], g), _rms_err(g_flo[k], g))
+    report = {k: tuple(round(e, 4) for e in ours[k] + floor[k]) for k in ours}
+    # (1) north_star's 2e-2 wherever bf16 storage permits it
+    reachable = [k for k in ours if floor[k][0] <= 1e-2]
+    assert "final_layer.weight" in reachable and "final_layer.bias" in reachable, report
+    for k in reachable:
+        assert ours[k][0] < 2e-2, (k, report[k])
+    # (2) everywhere else: no worse than the storage format itself
+    bad = {k: report[k] for k in ours if ours[k][0] > max(2e-2, 2.0 * floor[k][0]) or ours[k][1] > max(1e-2, 1.25 * floor[k][1])}
+    assert not bad, (bad, report)
+    mean_ours = sum(v[1] for v in ours.values()) / len(ours)
+    mean_floor = sum(v[1] for v in floor.values()) / len(floor)
+    assert mean_ours <= 1.1 * mean_floor, (mean_ours, mean_floor, report)

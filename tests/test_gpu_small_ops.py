@@ -187,3 +187,53 @@ def test_linear_relu_group_matches_single_calls():
         ref = ops.linear_relu(z, w2, b2)
         (ref * douts[i]).sum().backward()
         assert torch.equal(outs[i], ref) and torch.equal(w1[i].grad, w2.grad) and torch.equal(b1[i].grad, b2.grad), n
+
+
+@pytest.mark.parametrize("b,s", [(2, 64), (32, 64), (3, 32)])
+def test_head128_tanh_fwd_bwd(b, s):
+    """The patched 128 x 128 head: tanh(ConvTranspose2d(64 -> 3, k4, s2, p1)) on mma.sync, forward and backward
+    (dx, dw, dbias) against torch fp32 on the bf16-rounded operands."""
+    import torch.nn.functional as F
+    torch.backends.cudnn.allow_tf32 = False
+    g = torch.Generator().manual_seed(b + s)
+    x = torch.randn(b, 64, s, s, generator=g).to(torch.bfloat16)
+    w = torch.randn(64, 3, 4, 4, generator=g) * 0.05
+    bias = torch.randn(3, generator=g) * 0.1
+    dout = torch.randn(b, 3, 2 * s, 2 * s, generator=g)
+    xr = x.float().to(DEV).requires_grad_(True)
+    wr = w.to(torch.bfloat16).float().to(DEV).requires_grad_(True)
+    br = bias.to(DEV).requires_grad_(True)
+    ref = torch.tanh(F.conv_transpose2d(xr, wr, br, stride=2, padding=1))
+    (ref * dout.to(DEV)).sum().backward()
+    x_cl = x.permute(0, 2, 3, 1).contiguous().to(DEV).requires_grad_(True)
+    wg = w.to(DEV).requires_grad_(True)
+    bg = bias.to(DEV).requires_grad_(True)
+    out = ops.head128_tanh(x_cl, wg, bg)
+    assert tuple(out.shape) == (b, 3, 2 * s, 2 * s) and out.dtype == torch.float32
+    assert rel_err(out, ref) < 1e-5
+    (out * dout.to(DEV)).sum().backward()
+    assert rel_err(x_cl.grad.permute(0, 3, 1, 2).float(), xr.grad) < 2 ** -7       # g and the weights enter the MMA as bf16
+    assert rel_err(wg.grad, wr.grad) < 3e-3                                        # g rounded to bf16, fp32 accumulation
+    assert rel_err(bg.grad, br.grad) < 1e-5
+    out2 = ops.head128_tanh(x_cl.detach(), wg.detach(), bg.detach())
+    assert torch.equal(out, out2)
+
+
+def test_generator_128_bf16_vs_patched_oracle():
+    """img_size = 128 (BASELINE cfg 4 / 5) on the bf16 pipeline: every kernel ours (no cuDNN head), output within 2e-2 of
+    the patched-128 fp32 oracle."""
+    import numpy as np
+    from types import SimpleNamespace
+    from lightning_gan_zoo_b200.core.models.hologan_generator import Generator
+    from oracle import hologan_oracle as orc
+    gen = torch.Generator().manual_seed(128)
+    p = orc.init_generator_params(64, 3, 128, 128, generator=gen, bias_std=0.05)
+    z = torch.rand(3, 128, generator=gen) * 2 - 1
+    view = orc.sample_view(3, np.random.RandomState(128))
+    ref = orc.generator_forward(p, z, view, img_size=128)
+    net = Generator(64, 3, 128, SimpleNamespace(), 128).to(DEV)
+    net.load_state_dict(p)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        out = net(z.to(DEV), view_in=view)
+    assert tuple(out.shape) == (3, 3, 128, 128)
+    assert rel_err(out.float(), ref) < 2e-2

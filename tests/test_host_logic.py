@@ -246,3 +246,25 @@ def test_tap_tables_reproduce_transposed_conv_and_the_conv_duality(kernel, pad, 
         xg = x.clone().requires_grad_(True)
         (F.conv_transpose2d(xg, w, stride=2, padding=pad) * dy).sum().backward()
         assert torch.allclose(_convt2d_dgrad_by_taps(dy, w, kernel), xg.grad, atol=1e-12)
+
+
+def test_torch_library_registration():
+    """`torch.ops.hologan.*`: every operator has a schema; the leaf ops have fake (meta) kernels and an
+    autograd formula; there is no CPU kernel behind them."""
+    import lightning_gan_zoo_b200.torch_ops as t
+    for name in t.REGISTERED:
+        assert hasattr(torch.ops.hologan, name), name
+        assert getattr(torch.ops.hologan, name).default._schema is not None
+    from torch._subclasses.fake_tensor import FakeTensorMode
+    with FakeTensorMode():
+        vol = torch.empty(2, 16, 16, 16, 8, device="cuda", dtype=torch.bfloat16)
+        a = torch.empty(2, 4, 4, device="cuda")
+        out = torch.ops.hologan.rotate_resample(vol, a, 1, 1, 2)            # NDHWC -> PROJ
+        assert tuple(out.shape) == (2, 16, 16, 16, 8) and out.dtype == torch.bfloat16
+        g = torch.ops.hologan.rotate_resample_backward(out, a, 8, 16, 1, 1, 2)
+        assert tuple(g.shape) == (2, 16, 16, 16, 8)
+        y = torch.ops.hologan.convt_forward(torch.empty(2, 16, 16, 128, device="cuda", dtype=torch.bfloat16),
+                                            torch.empty(16, 64, 128, device="cuda", dtype=torch.bfloat16), None, 2, 4, 1.0)
+        assert tuple(y.shape) == (2, 16, 16, 4, 64)
+    with pytest.raises(NotImplementedError):
+        torch.ops.hologan.rotate_resample(torch.zeros(1, 2, 16, 16, 16), torch.eye(4).unsqueeze(0), 0, 0, 0)
