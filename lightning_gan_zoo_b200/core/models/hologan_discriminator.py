@@ -53,8 +53,15 @@ class BasicBlock(nn.Module):
 
 
 class Discriminator(nn.Module):
-    def __init__(self, in_planes, out_planes, z_planes, img_size=64):
+    def __init__(self, in_planes, out_planes, z_planes, img_size=64, final_sigmoid=False):
+        """`img_size` / `final_sigmoid`: the reference's Hydra tree hands both to this constructor (conf/config.yaml:37-39
+        merges a `discriminator: {img_size, final_sigmoid}` block into every experiment), although its own
+        `Discriminator.__init__(in_planes, out_planes, z_planes)` accepts neither -- `instantiate(cfg.discriminator)` of
+        `+expt=hologan` raises TypeError there.  Here `img_size` sizes the heads (patched 128 variant) and
+        `final_sigmoid` must stay False (the loss is BCEWithLogits, conf/expt/hologan.yaml:12-13)."""
         super().__init__()
+        if final_sigmoid:
+            raise ValueError("the HoloGAN discriminator returns logits (BCEWithLogitsLoss); final_sigmoid must be False")
         self.conv2d = nn.Conv2d(in_planes, out_planes, kernel_size=5, stride=2, padding=2)
         truncated_normal_initializer(self.conv2d.weight)
         nn.init.zeros_(self.conv2d.bias)

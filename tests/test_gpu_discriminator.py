@@ -302,5 +302,5 @@ def test_discriminator_b200_path_launches_no_library_kernel():
     lib = [n for n in names if "hg::" not in n and
            any(t in n.lower() for t in ("cudnn", "cutlass", "nvjet", "gemm", "gemv", "convolve", "cublas", "implicit", "xmma"))]
     assert not lib, lib
-    assert any("tap_gemm_kernel" in n for n in names) and any("dconv0_fwd_kernel" in n for n in names) \
+    assert any("tap_gemm_kernel" in n for n in names) and any("c0_img2map_kernel" in n for n in names) \
         and any("dheads_fwd_partial_kernel" in n for n in names)

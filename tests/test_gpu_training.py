@@ -130,3 +130,38 @@ def test_step_host_matches_step(graphs):
         assert abs(r - g) < 5e-3 * max(1.0, abs(r)), (ref, got)
     worst = max(rel_err(pb, pa) for pa, pb in zip(a.generator.parameters(), b.generator.parameters()) if pa.dim() > 1)
     assert worst < 5e-2
+
+
+@pytest.mark.parametrize("optimizer_idx", [0, 1])
+def test_lightning_module_mirror_training_step_vs_oracle(optimizer_idx):
+    """`core.lightning_module.HOLOGAN` built from the `+expt=hologan` configuration through the `_target_` strings
+    (SURVEY 8-f4), full widths, bf16 autocast (every kernel ours): the step's loss against the oracle's restatement of
+    core/lightning_module.py:209-237 on the same parameters, latents and views."""
+    from lightning_gan_zoo_b200 import compat
+    from lightning_gan_zoo_b200.config import instantiate, load_hologan_config
+    compat.install()
+    torch.manual_seed(3)
+    cfg = load_hologan_config(overrides=["train.batch_size=8"])
+    lm = instantiate(cfg.model.lm, cfg, "logs").to(DEV)
+    bsz = 8
+    view = orc.sample_view(bsz, np.random.RandomState(5))
+    lm.generator.sample_view = lambda n: view
+    real = torch.rand(bsz, 3, 64, 64, device=DEV) * 2 - 1
+    gp = {k: v.detach().cpu().clone() for k, v in lm.generator.state_dict().items()}
+    dp = {k: v.detach().cpu().clone() for k, v in lm.discriminator.state_dict().items() if "conv2d_spec_norm" not in k}
+    torch.manual_seed(11)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        loss = lm.training_step((real, None), 0, optimizer_idx)
+    loss.backward()
+    torch.manual_seed(11)
+    z = lm.noise_distn.sample((bsz, 128))
+    fake = orc.generator_forward(gp, z, view)
+    ref, logs = orc.hologan_losses(optimizer_idx, dp, real.cpu(), fake, z)
+    assert abs(loss.item() - ref.item()) <= 2e-2 * abs(ref.item()), (loss.item(), ref.item())
+    key = "train/d_loss" if optimizer_idx == 0 else "train/g_loss"
+    logged = lm.logged if hasattr(lm, "logged") else {}
+    if logged:
+        assert abs(float(logged[key]) - float(logs[key])) <= 2e-2 * abs(float(logs[key])) + 1e-3
+        assert abs(float(logged["train/q_loss"]) - float(logs["train/q_loss"])) <= 2e-2 * float(logs["train/q_loss"]) + 1e-3
+    stepped = lm.discriminator if optimizer_idx == 0 else lm.generator
+    assert all(p.grad is not None for n, p in stepped.named_parameters() if not n.endswith("conv2d.bias") and "convTranspose.bias" not in n)
