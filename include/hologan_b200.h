@@ -332,6 +332,16 @@ int hg_dheads_bwd(const void *h, const float *w1, const float *w2, const float *
                   float *dw3, float *db3, void *workspace, long long workspace_bytes, int batch, int channels, int hw, int zdim,
                   float neg_slope, void *stream);
 
+/* ---- a13: the optimizer step.  torch.optim.Adam(lr, betas) of core/lightning_module.py:75-87 (no weight decay, no
+ * amsgrad) over ONE flat fp32 buffer holding every parameter of a network (param / grad / exp_avg / exp_avg_sq are
+ * parallel buffers of n floats, n % 4 == 0, 16-byte aligned).  grad is multiplied by grad_scale first (1 / world size
+ * of the data-parallel gradient SUM).  state: 4 device floats owned by the caller, state[0] = steps taken so far (the
+ * call increments it); lr: device float.  Both live on the device so that the step replays from a CUDA graph.
+ * Arithmetic as torch's fused kernel: m += (g - m)(1 - b1); v = b2 v + (1 - b2) g^2;
+ * p -= lr / (1 - b1^t) * m / (sqrt(v) / sqrt(1 - b2^t) + eps). */
+int hg_adam_step(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, long long n, float *state,
+                 const float *lr, float beta1, float beta2, float eps, float grad_scale, void *stream);
+
 /* ---- a13: the losses of HOLOGAN.training_step  (core/lightning_module.py:217-237) -------------------
  *   adv = wa * mean_i BCEWithLogits(a[i], ta) + wb * mean_j BCEWithLogits(b[j], tb)   (b may be NULL, nb = 0)
  *   q   = mean_k (zp[k] - z[k])^2

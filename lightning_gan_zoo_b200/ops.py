@@ -379,6 +379,14 @@ def _direct_grad_target(param, shape) -> Tuple[Optional[Tensor], bool]:
     return g, overwrite
 
 
+def _grad_ready(param) -> None:
+    """A parameter's gradient has just been written into its flat-buffer view: run the owner's hook, if any
+    (HologanTrainer starts the bucket's data-parallel all-reduce from it, overlapping the rest of the backward)."""
+    cb = None if param is None else getattr(param, "_hg_grad_ready", None)
+    if cb is not None:
+        cb()
+
+
 def _conv_dims(x_cl: Tensor, ndim: int):
     if x_cl.dtype != torch.bfloat16 or not x_cl.is_contiguous() or x_cl.dim() != ndim + 2:
         raise ValueError("activations must be contiguous channels-last bf16 tensors (B, [S,] S, S, C)")
@@ -439,6 +447,7 @@ class _ConvT(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             target, overwrite = _direct_grad_target(ctx.weight_param, wshape)
             dw = convt_wgrad(x_cl, dy, wshape, ndim, kernel, perm, accumulate_into=target, overwrite=overwrite)
+            _grad_ready(ctx.weight_param)
         return dx, dw, db, None, None, None, None, None
 
 
@@ -988,6 +997,8 @@ class _Conv5s2SN(torch.autograd.Function):
                           _c_array(vp, [state.data_ptr()]), _c_array(vp, [dw_orig.data_ptr()]), co_arr, ci_arr, t_arr,
                           int(direct), HG_F32, _ptr(sn_ws), sn_bytes, _stream())
                 dw = None if direct else dw_orig
+                if direct:
+                    _grad_ready(ctx.weight_param)
         return dx, dw, None
 
 

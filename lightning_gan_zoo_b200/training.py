@@ -70,25 +70,44 @@ class _FlatGrads:
     views, so autograd hands every parameter its freshly computed gradient (AccumulateGrad keeps the incoming tensor
     instead of launching `grad += new`); `finish()` moves them into the flat buffer with ONE multi-tensor copy and
     re-attaches the views.  The tcgen05 wgrad kernels store straight into their view (`_hg_direct_grad`).  A view
-    that no backward ever writes (a parameter without gradient) keeps its initial zeros."""
+    that no backward ever writes (a parameter without gradient) keeps its initial zeros.
 
-    def __init__(self, params, direct: bool = False, accumulate_into=()):
+    Data parallel: the buffer is laid out as `buckets` -- groups of parameters in the order their gradients become
+    final during the backward pass -- followed by the remaining parameters.  `fire(i)` starts the (asynchronous) sum
+    all-reduce of bucket i as soon as its gradients are in the buffer, so it overlaps the rest of the backward; the
+    tail goes last and `wait()` joins everything before the optimizer reads the buffer (DDP's bucketed overlap,
+    run_network.py:66-71, on a flat buffer)."""
+
+    def __init__(self, params, direct: bool = False, accumulate_into=(), buckets=()):
         """direct: every parameter's view is offered to the kernels as a store target (one backward per step).
         accumulate_into: parameters whose kernels ADD into the view (several backward calls per step, e.g. the
-        discriminator's spectral-norm weights: D runs on real and fake) -- those views are zeroed by `begin()`."""
-        self.params = [p for p in params]
+        discriminator's spectral-norm weights: D runs on real and fake) -- those views are zeroed by `begin()`.
+        buckets: sequence of parameter lists (see the class docstring)."""
+        params = [p for p in params]
+        ordered, seen, bounds = [], set(), []
+        for bucket in buckets:
+            start = sum(p.numel() for p in ordered)
+            for p in bucket:
+                if id(p) not in seen:
+                    ordered.append(p)
+                    seen.add(id(p))
+            bounds.append((start, sum(p.numel() for p in ordered)))
+        ordered += [p for p in params if id(p) not in seen]
+        self.params = ordered
         acc_ids = {id(p) for p in accumulate_into}
         self.zero_views = []
         n = sum(p.numel() for p in self.params)
+        self.numel = n
         dev, dt = self.params[0].device, self.params[0].dtype
-        self.flat = torch.zeros(n, device=dev, dtype=dt)
+        self.flat = torch.zeros((n + 3) // 4 * 4, device=dev, dtype=dt)      # padded: the fused Adam kernel works on float4
+        self.bucket_slices = bounds + [(bounds[-1][1] if bounds else 0, n)]
         self.views = []
         o = 0
         for p in self.params:
             chunk = self.flat[o:o + p.numel()]
             if p.dim() == 4 and not p.is_contiguous() and p.is_contiguous(memory_format=torch.channels_last):
-                n, c, h, w = p.shape                      # same strides as the parameter (fused Adam needs that)
-                view = chunk.view(n, h, w, c).permute(0, 3, 1, 2)
+                n_, c, h, w = p.shape                     # same strides as the parameter (fused Adam needs that)
+                view = chunk.view(n_, h, w, c).permute(0, 3, 1, 2)
             else:
                 view = chunk.view_as(p)
             p.grad = view
@@ -98,6 +117,7 @@ class _FlatGrads:
                 self.zero_views.append(view)
             self.views.append(view)
             o += p.numel()
+        self._handles, self._fired, self._counts = [], set(), {}
 
     def zero(self):
         self.flat.zero_()
@@ -108,6 +128,7 @@ class _FlatGrads:
         if self.zero_views:
             with torch.no_grad():
                 torch._foreach_zero_(self.zero_views)
+        self._handles, self._fired, self._counts = [], set(), {}
 
     def finish(self):
         src, dst = [], []
@@ -121,10 +142,90 @@ class _FlatGrads:
             with torch.no_grad():
                 torch._foreach_copy_(dst, src)
 
+    # ---- data-parallel exchange ---------------------------------------------------------------------
+    def fire(self, i: int, world: int, after_calls: int = 1):
+        """Start the sum all-reduce of bucket i (asynchronously) once this has been called `after_calls` times in the
+        current step -- the hook the kernels' backward call when a bucket's last gradient has been written."""
+        self._counts[i] = self._counts.get(i, 0) + 1
+        if world <= 1 or i in self._fired or self._counts[i] < after_calls:
+            return
+        self._fired.add(i)
+        s, e = self.bucket_slices[i]
+        if e > s:
+            self._handles.append(dist.all_reduce(self.flat[s:e], op=dist.ReduceOp.SUM, async_op=True))
+
+    def all_reduce_sum(self, world: int):
+        """All-reduce (sum) whatever `fire` has not started yet, then wait for every bucket."""
+        if world <= 1:
+            return
+        for i in range(len(self.bucket_slices)):
+            self.fire(i, world, after_calls=0)
+        for h in self._handles:
+            h.wait()
+        self._handles = []
+
     def all_reduce_mean(self, world: int):
         if world > 1:
-            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
+            self.all_reduce_sum(world)
             self.flat.div_(world)
+
+
+class FlatAdam(torch.optim.Optimizer):
+    """torch.optim.Adam(lr, betas, eps) (core/lightning_module.py:75-87) on one flat buffer: the parameters are
+    re-pointed to views of `flat_param` (in the order of `grads.params`), the moments are flat too, and `step()` is a
+    single fused kernel (hg_adam_step) that also applies the data-parallel 1 / world gradient scale.  The per-parameter
+    `state` exposes views of the flat moments plus a shared step counter, so `state_dict()` has torch Adam's layout
+    (checkpoints stay interchangeable); `load_state_dict` copies a torch Adam state back into the flat buffers."""
+
+    def __init__(self, grads: _FlatGrads, lr, betas=(0.9, 0.999), eps: float = 1e-8):
+        params = grads.params
+        super().__init__(params, dict(lr=lr, betas=tuple(betas), eps=eps))
+        dev = grads.flat.device
+        self.grads = grads
+        self.flat_param = torch.zeros_like(grads.flat)
+        self.exp_avg = torch.zeros_like(grads.flat)
+        self.exp_avg_sq = torch.zeros_like(grads.flat)
+        self.kstate = torch.zeros(4, device=dev)            # [0] steps taken, [1] lr / bc1, [2] 1 / sqrt(bc2)
+        lr_t = self.param_groups[0]["lr"]
+        if not isinstance(lr_t, torch.Tensor):
+            self.param_groups[0]["lr"] = torch.tensor(float(lr_t), device=dev)
+        o = 0
+        with torch.no_grad():
+            for p in params:
+                n = p.numel()
+                view = self.flat_param[o:o + n].view_as(p)
+                view.copy_(p)
+                p.data = view
+                self.state[p] = {"step": self.kstate[0], "exp_avg": self.exp_avg[o:o + n].view_as(p),
+                                 "exp_avg_sq": self.exp_avg_sq[o:o + n].view_as(p)}
+                o += n
+
+    @torch.no_grad()
+    def step(self, grad_scale: float = 1.0):
+        g = self.param_groups[0]
+        b1, b2 = g["betas"]
+        P = ops._ptr
+        _lib.call("hg_adam_step", P(self.flat_param), P(self.grads.flat), P(self.exp_avg), P(self.exp_avg_sq),
+                  self.flat_param.numel(), P(self.kstate), P(g["lr"]), float(b1), float(b2), float(g["eps"]), float(grad_scale),
+                  ops._stream())
+
+    def load_state_dict(self, state_dict):
+        """Accepts a torch.optim.Adam (or FlatAdam) state dict over the same parameters in the same order."""
+        packed = state_dict["state"]
+        ids = state_dict["param_groups"][0]["params"]
+        with torch.no_grad():
+            step = None
+            for idx, p in zip(ids, self.param_groups[0]["params"]):
+                st = packed.get(idx)
+                if st is None:
+                    continue
+                self.state[p]["exp_avg"].copy_(st["exp_avg"])
+                self.state[p]["exp_avg_sq"].copy_(st["exp_avg_sq"])
+                step = st["step"]
+            if step is not None:
+                self.kstate[0] = float(step)
+            lr = state_dict["param_groups"][0]["lr"]
+            self.param_groups[0]["lr"].fill_(float(lr))
 
 
 class PendingLoss:
@@ -176,17 +277,34 @@ class HologanTrainer:
             # A/B switch HG_D_LIBRARY=1: the discriminator's convolutions on cuDNN run NHWC (its native tensor-core
             # layout), so the weights live channels-last too; the default (hand-written kernels) keeps torch's layout
             self.discriminator.to(memory_format=torch.channels_last)
-        sn_weights = [blk.conv2d.weight_orig for blk in self.discriminator.blocks] if self.device.type == "cuda" else ()
-        self.d_grads = _FlatGrads(self.discriminator.parameters(), accumulate_into=sn_weights)
-        # the generator's tcgen05 wgrad kernels store straight into the flat buffer (ops._direct_grad_target)
-        self.g_grads = _FlatGrads(self.generator.parameters(), direct=self.device.type == "cuda")
         cuda = self.device.type == "cuda"
-        # fused multi-tensor Adam; capturable (device-side step counter, tensor lr) so that a whole
-        # optimizer step can live inside a CUDA graph
-        lr = torch.tensor(cfg.lr, device=self.device) if cuda else cfg.lr
-        kw = dict(betas=(cfg.beta1, cfg.beta2), fused=cuda, capturable=cuda)
-        self.opt_d = torch.optim.Adam(self.discriminator.parameters(), lr=lr, **kw)
-        self.opt_g = torch.optim.Adam(self.generator.parameters(), lr=lr.clone() if cuda else lr, **kw)
+        sn_weights = [blk.conv2d.weight_orig for blk in self.discriminator.blocks] if cuda else ()
+        # gradient buckets in the order the backward pass finishes them (data parallel: each is all-reduced as soon as
+        # it is final, overlapping the rest of the backward; world 1: only the buffer layout)
+        gen, disc = self.generator, self.discriminator
+        g_buckets = [[gen.block3.convTranspose.weight, gen.block4.convTranspose.weight], [gen.convTranspose2d1.weight]] if cuda else ()
+        d_buckets = [[disc.blocks[2].conv2d.weight_orig]] if cuda else ()
+        self.d_grads = _FlatGrads(self.discriminator.parameters(), accumulate_into=sn_weights, buckets=d_buckets)
+        # the generator's tcgen05 wgrad kernels store straight into the flat buffer (ops._direct_grad_target)
+        self.g_grads = _FlatGrads(self.generator.parameters(), direct=cuda, buckets=g_buckets)
+        self._flat_adam = cuda and os.environ.get("HG_D_LIBRARY", "0") in ("", "0") and os.environ.get("HG_TORCH_ADAM", "0") in ("", "0")
+        if self._flat_adam:
+            # one fused kernel per optimizer step over flat parameter / gradient / moment buffers (hg_adam_step)
+            self.opt_d = FlatAdam(self.d_grads, cfg.lr, betas=(cfg.beta1, cfg.beta2))
+            self.opt_g = FlatAdam(self.g_grads, cfg.lr, betas=(cfg.beta1, cfg.beta2))
+        else:
+            # torch's fused multi-tensor Adam; capturable (device-side step counter, tensor lr) so that a whole
+            # optimizer step can live inside a CUDA graph
+            lr = torch.tensor(cfg.lr, device=self.device) if cuda else cfg.lr
+            kw = dict(betas=(cfg.beta1, cfg.beta2), fused=cuda, capturable=cuda)
+            self.opt_d = torch.optim.Adam(self.d_grads.params, lr=lr, **kw)
+            self.opt_g = torch.optim.Adam(self.g_grads.params, lr=lr.clone() if cuda else lr, **kw)
+        if cuda and self.world > 1:
+            w = self.world
+            gen.block3.convTranspose.weight._hg_grad_ready = lambda: self.g_grads.fire(0, w)
+            gen.convTranspose2d1.weight._hg_grad_ready = lambda: self.g_grads.fire(1, w)
+            # the D step runs the discriminator on real and on fake: the bucket is final after the second backward
+            disc.blocks[2].conv2d.weight_orig._hg_grad_ready = lambda: self.d_grads.fire(0, w, after_calls=2)
         self._graphs = None
         lam = hologan_lr_lambda(cfg.num_epochs)
         self.sched_d = torch.optim.lr_scheduler.LambdaLR(self.opt_d, lam)
@@ -312,8 +430,12 @@ class HologanTrainer:
         loss = self.training_step(real, z, view, idx)
         loss.backward()
         grads.finish()
-        grads.all_reduce_mean(self.world)
-        opt.step()
+        if self._flat_adam:
+            grads.all_reduce_sum(self.world)            # buckets fired during the backward + the tail; 1 / world goes into Adam
+            opt.step(grad_scale=1.0 / self.world)
+        else:
+            grads.all_reduce_mean(self.world)
+            opt.step()
         if self.device.type == "cuda":          # bf16 operand copies of the stepped network: once per update, not per forward
             ops.refresh_packed_weights((self.discriminator if idx == 0 else self.generator).parameters())
         return loss.detach()
@@ -333,7 +455,7 @@ class HologanTrainer:
         opts = (self.opt_d, self.opt_g)
         model_t = list(self.generator.state_dict().values()) + list(self.discriminator.state_dict().values())
         model_saved = [t.clone() for t in model_t]
-        fresh = [len(o.state) == 0 for o in opts]       # torch creates Adam state lazily at the first step
+        fresh = [len(o.state) == 0 or (isinstance(o, FlatAdam) and float(o.kstate[0]) == 0) for o in opts]   # torch creates Adam state lazily
         opt_saved = [None if f else {id(p): {k: v.clone() for k, v in stt.items() if isinstance(v, torch.Tensor)}
                                      for p, stt in o.state.items()} for o, f in zip(opts, fresh)]
         side = torch.cuda.Stream(device=self.device)

@@ -114,7 +114,7 @@ def test_flat_grads_views_and_zero():
     lin = torch.nn.Linear(4, 3)
     fg = _FlatGrads(lin.parameters())
     lin(torch.ones(2, 4)).sum().backward()
-    assert fg.flat.numel() == 15 and fg.flat.abs().sum() > 0
+    assert fg.numel == 15 and fg.flat.numel() == 16 and fg.flat.abs().sum() > 0      # padded to a float4 multiple
     assert lin.weight.grad.data_ptr() == fg.flat.data_ptr()
     fg.zero()
     assert lin.weight.grad.abs().sum() == 0 and lin.bias.grad.abs().sum() == 0
@@ -149,3 +149,37 @@ def test_bench_multi_rank_exit_handshake(tmp_path):
                        capture_output=True, text=True, timeout=180)
     assert r.returncode == 0, r.stderr[-2000:]
     assert "LINE" in r.stdout
+
+
+def _bucket_worker(rank: int, port: int, out_dir: str):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=WORLD)
+    try:
+        torch.manual_seed(0)
+        net = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Linear(5, 4), torch.nn.Linear(4, 3))
+        early = [net[2].weight, net[2].bias]                           # final first in the backward pass
+        fg = _FlatGrads(net.parameters(), buckets=[early, [net[1].weight]])
+        assert fg.params[0] is net[2].weight and fg.params[2] is net[1].weight and len(fg.bucket_slices) == 3
+        x = torch.full((2, 6), float(rank + 1))
+        fg.begin()
+        net(x).sum().backward()
+        fg.finish()
+        before = fg.flat.clone()
+        fg.fire(0, WORLD)                                              # bucket 0 starts while "the backward goes on"
+        fg.fire(1, WORLD, after_calls=2)                               # not yet: needs two calls
+        assert 1 not in fg._fired
+        fg.fire(1, WORLD, after_calls=2)
+        assert 1 in fg._fired
+        fg.all_reduce_sum(WORLD)                                       # tail bucket + wait
+        torch.save({"before": before, "after": fg.flat.clone()}, os.path.join(out_dir, f"b{rank}.pt"))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_bucketed_async_all_reduce_equals_flat_sum(tmp_path):
+    """Gradient buckets fired one by one (the overlap schedule of HologanTrainer) sum to the same buffer as one flat
+    all-reduce: every element exactly once, on every rank."""
+    mp.spawn(_bucket_worker, args=(_free_port(), str(tmp_path)), nprocs=WORLD, join=True)
+    r0, r1 = torch.load(tmp_path / "b0.pt"), torch.load(tmp_path / "b1.pt")
+    assert torch.equal(r0["after"], r1["after"])
+    assert torch.allclose(r0["after"], r0["before"] + r1["before"])

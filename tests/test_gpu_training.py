@@ -165,3 +165,37 @@ def test_lightning_module_mirror_training_step_vs_oracle(optimizer_idx):
         assert abs(float(logged["train/q_loss"]) - float(logs["train/q_loss"])) <= 2e-2 * float(logs["train/q_loss"]) + 1e-3
     stepped = lm.discriminator if optimizer_idx == 0 else lm.generator
     assert all(p.grad is not None for n, p in stepped.named_parameters() if not n.endswith("conv2d.bias") and "convTranspose.bias" not in n)
+
+
+def test_flat_adam_matches_torch_adam():
+    """hg_adam_step on flat buffers (FlatAdam) against torch.optim.Adam on the same parameters / gradients, three
+    steps, with a gradient scale (the data-parallel 1 / world) and an lr change in between; state_dict round trip."""
+    from lightning_gan_zoo_b200.training import FlatAdam, _FlatGrads
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(37, 19), torch.nn.Linear(19, 5)).to(DEV)
+    ref = torch.nn.Sequential(torch.nn.Linear(37, 19), torch.nn.Linear(19, 5)).to(DEV)
+    ref.load_state_dict(net.state_dict())
+    fg = _FlatGrads(net.parameters())
+    opt = FlatAdam(fg, 1e-3, betas=(0.9, 0.999))
+    ropt = torch.optim.Adam(ref.parameters(), lr=1e-3, betas=(0.9, 0.999))
+    sched = torch.optim.lr_scheduler.LambdaLR(opt, lambda e: 0.5 ** e)
+    rsched = torch.optim.lr_scheduler.LambdaLR(ropt, lambda e: 0.5 ** e)
+    for it in range(3):
+        x = torch.randn(8, 37, device=DEV)
+        fg.begin()
+        (net(x).square().sum() * 4.0).backward()
+        fg.finish()
+        ropt.zero_grad()
+        ref(x).square().sum().backward()
+        opt.step(grad_scale=0.25)
+        ropt.step()
+        sched.step(); rsched.step()
+        for a, b in zip(net.parameters(), ref.parameters()):
+            assert rel_err(a, b) < 1e-6, it
+    sd = opt.state_dict()
+    assert set(sd["state"][0]) == {"step", "exp_avg", "exp_avg_sq"} and float(sd["state"][0]["step"]) == 3
+    net2 = torch.nn.Sequential(torch.nn.Linear(37, 19), torch.nn.Linear(19, 5)).to(DEV)
+    opt2 = FlatAdam(_FlatGrads(net2.parameters()), 1e-3)
+    opt2.load_state_dict(ropt.state_dict())                    # a torch Adam state loads into the flat buffers
+    assert rel_err(opt2.exp_avg_sq[:37 * 19], ropt.state[next(ref.parameters())]["exp_avg_sq"].flatten()) < 1e-6
+    assert float(opt2.kstate[0]) == 3
