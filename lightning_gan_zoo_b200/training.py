@@ -84,24 +84,25 @@ class _FlatGrads:
         discriminator's spectral-norm weights: D runs on real and fake) -- those views are zeroed by `begin()`.
         buckets: sequence of parameter lists (see the class docstring)."""
         params = [p for p in params]
+        pad = lambda n: (n + 3) // 4 * 4                  # every parameter starts 16-byte aligned (float4 / TMA-free kernels)
         ordered, seen, bounds = [], set(), []
         for bucket in buckets:
-            start = sum(p.numel() for p in ordered)
+            start = sum(pad(p.numel()) for p in ordered)
             for p in bucket:
                 if id(p) not in seen:
                     ordered.append(p)
                     seen.add(id(p))
-            bounds.append((start, sum(p.numel() for p in ordered)))
+            bounds.append((start, sum(pad(p.numel()) for p in ordered)))
         ordered += [p for p in params if id(p) not in seen]
         self.params = ordered
         acc_ids = {id(p) for p in accumulate_into}
         self.zero_views = []
-        n = sum(p.numel() for p in self.params)
-        self.numel = n
+        self.numel = sum(p.numel() for p in self.params)
+        total = sum(pad(p.numel()) for p in self.params)
         dev, dt = self.params[0].device, self.params[0].dtype
-        self.flat = torch.zeros((n + 3) // 4 * 4, device=dev, dtype=dt)      # padded: the fused Adam kernel works on float4
-        self.bucket_slices = bounds + [(bounds[-1][1] if bounds else 0, n)]
-        self.views = []
+        self.flat = torch.zeros(total, device=dev, dtype=dt)     # padding elements stay zero
+        self.bucket_slices = bounds + [(bounds[-1][1] if bounds else 0, total)]
+        self.views, self.offsets = [], []
         o = 0
         for p in self.params:
             chunk = self.flat[o:o + p.numel()]
@@ -116,7 +117,8 @@ class _FlatGrads:
             if id(p) in acc_ids:
                 self.zero_views.append(view)
             self.views.append(view)
-            o += p.numel()
+            self.offsets.append(o)
+            o += pad(p.numel())
         self._handles, self._fired, self._counts = [], set(), {}
 
     def zero(self):
@@ -189,16 +191,14 @@ class FlatAdam(torch.optim.Optimizer):
         lr_t = self.param_groups[0]["lr"]
         if not isinstance(lr_t, torch.Tensor):
             self.param_groups[0]["lr"] = torch.tensor(float(lr_t), device=dev)
-        o = 0
         with torch.no_grad():
-            for p in params:
+            for p, o in zip(params, grads.offsets):       # same (16-byte aligned) layout as the gradient buffer
                 n = p.numel()
                 view = self.flat_param[o:o + n].view_as(p)
                 view.copy_(p)
                 p.data = view
                 self.state[p] = {"step": self.kstate[0], "exp_avg": self.exp_avg[o:o + n].view_as(p),
                                  "exp_avg_sq": self.exp_avg_sq[o:o + n].view_as(p)}
-                o += n
 
     @torch.no_grad()
     def step(self, grad_scale: float = 1.0):

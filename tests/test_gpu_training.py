@@ -197,5 +197,5 @@ def test_flat_adam_matches_torch_adam():
     net2 = torch.nn.Sequential(torch.nn.Linear(37, 19), torch.nn.Linear(19, 5)).to(DEV)
     opt2 = FlatAdam(_FlatGrads(net2.parameters()), 1e-3)
     opt2.load_state_dict(ropt.state_dict())                    # a torch Adam state loads into the flat buffers
-    assert rel_err(opt2.exp_avg_sq[:37 * 19], ropt.state[next(ref.parameters())]["exp_avg_sq"].flatten()) < 1e-6
+    assert rel_err(opt2.exp_avg_sq[:19 * 37], ropt.state[next(ref.parameters())]["exp_avg_sq"].flatten()) < 1e-6
     assert float(opt2.kstate[0]) == 3
