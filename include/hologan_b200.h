@@ -74,7 +74,12 @@ const char *hg_last_error(void);
  *   ROTATE_GATHER_BWD    (1)   32^3 rotate backward as a table-free per-voxel gather (0: shared-memory scatter)
  *   ADAIN_GEMM_STATS     (0)   host layer: the generator's AdaIN statistics come from the tap-GEMM epilogue
  *                              (hg_convt_fwd_stats + hg_adain_cl_fwd_stats) instead of the single-pass cluster kernel;
- *                              measured break-even on B200 (profiles/r02f_microbench_conv.txt), hence off */
+ *                              measured break-even on B200 (profiles/r02f_microbench_conv.txt), hence off
+ *   TAPGEMM_PERSISTENT   (0)   1: tap GEMMs with more tiles than SMs run one persistent CTA per SM that walks the tiles with two
+ *                              TMEM accumulator stages (epilogue of tile i overlaps the main loop of tile i + 1).  Measured on
+ *                              B200 (profiles/r02m_*): wins on the wide tiles (block3 dgrad 129 -> 106 us) but loses on the
+ *                              narrow layers, where two co-resident one-tile CTAs issue MMAs from two threads; step 1.87 vs
+ *                              1.81 ms, hence off */
 int hg_set_option(const char *name, int value);
 int hg_get_option(const char *name, int *value);
 

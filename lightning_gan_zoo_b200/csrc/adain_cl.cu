@@ -79,11 +79,6 @@ __device__ __forceinline__ int upsampled_row(int r, int ndim, int logS, int logP
 struct ClGeom;
 __device__ __forceinline__ int mapped_row(int r, const ClGeom &g);
 
-__device__ __forceinline__ float modulate_cl(float x, float mean, float rstd, float s, float b)
-{
-    return __fadd_rn(__fmul_rn(s, __fmul_rn(__fsub_rn(x, mean), rstd)), b);
-}
-
 struct ClGeom {
     int C, N, Nvar, ndim, logS, logP;
     int s2d_out;        // plain (S x S) rows in, 2x2 space-to-depth row order out (classes == -4, see hg_adain_cl_fwd)
@@ -170,9 +165,11 @@ __device__ __forceinline__ void fwd_accumulate(const __nv_bfloat16 *__restrict__
     }
 }
 
+// y = act(x * a + c) with a = scale * rstd, c = bias - mean * a: ONE fma per element (the statistics pass and the
+// backward recompute the same a, c from the saved mean / rstd -> same bits, same activation mask).  The kernels are
+// issue-bound (ncu: 0.5 instructions per scheduler cycle at 16 warps per SM), so every instruction per element counts.
 __device__ __forceinline__ void fwd_apply(const __nv_bfloat16 *__restrict__ xb, __nv_bfloat16 *__restrict__ yb, const ClGeom &g,
-                                          int r0, int r1, int rs, const float (&mean)[8], const float (&rstd)[8],
-                                          const float (&s)[8], const float (&bb)[8], float slope)
+                                          int r0, int r1, int rs, const float (&a)[8], const float (&c)[8], float slope)
 {
     for (int r = r0 + rs; r < r1; r += kClUnroll * g.rows_per_pass) {
         uint4 raw[kClUnroll];
@@ -189,7 +186,7 @@ __device__ __forceinline__ void fwd_apply(const __nv_bfloat16 *__restrict__ xb, 
                 unpack8(raw[u], f);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    const float p = modulate_cl(f[j], mean[j], rstd[j], s[j], bb[j]);
+                    const float p = fmaf(f[j], a[j], c[j]);
                     f[j] = p > 0.f ? p : p * slope;
                 }
                 st_stream_16(yb + (size_t)mapped_row(rr, g) * g.C, pack8(f));
@@ -198,8 +195,19 @@ __device__ __forceinline__ void fwd_apply(const __nv_bfloat16 *__restrict__ xb, 
     }
 }
 
+// a = scale * rstd, c = bias - mean * a (exactly as the cluster kernels compute them)
+__device__ __forceinline__ void affine_coeffs(const float *scale, const float *bias, int b, int sbs, int c0, const float (&mean)[8],
+                                              const float (&rstd)[8], float (&a)[8], float (&c)[8])
+{
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        a[j] = __fmul_rn(scale ? scale[(size_t)b * sbs + c0 + j] : 1.f, rstd[j]);
+        c[j] = __fsub_rn(bias ? bias[(size_t)b * sbs + c0 + j] : 0.f, __fmul_rn(mean[j], a[j]));
+    }
+}
+
 // grid (chunks, B).  part[(b * chunks + chunk) * 2C + {0, C} + c]
-__global__ void __launch_bounds__(kClThreads) adain_cl_stats_kernel(const __nv_bfloat16 *__restrict__ x, float *__restrict__ part,
+__global__ void __launch_bounds__(kClThreads, 3) adain_cl_stats_kernel(const __nv_bfloat16 *__restrict__ x, float *__restrict__ part,
                                                                     ClGeom g)
 {
     __shared__ float red[kClThreads * 16];
@@ -274,7 +282,7 @@ __global__ void __launch_bounds__(256) adain_cl_stats_finalize_kernel(const floa
 }
 
 // Streaming normalise / modulate / activate pass with the statistics already known (save_mean / save_rstd)
-__global__ void __launch_bounds__(kClThreads) adain_cl_apply_stats_kernel(const __nv_bfloat16 *__restrict__ x,
+__global__ void __launch_bounds__(kClThreads, 3) adain_cl_apply_stats_kernel(const __nv_bfloat16 *__restrict__ x,
                                                                           const float *__restrict__ scale,
                                                                           const float *__restrict__ bias,
                                                                           const float *__restrict__ save_mean,
@@ -283,22 +291,21 @@ __global__ void __launch_bounds__(kClThreads) adain_cl_apply_stats_kernel(const 
 {
     const int cs = threadIdx.x % g.lanes, rs = threadIdx.x / g.lanes;
     const int b = blockIdx.y, chunk = blockIdx.x;
-    float mean[8], rstd[8], s[8], bb[8];
+    float mean[8], rstd[8], a[8], c[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         mean[j] = save_mean[(size_t)b * g.C + cs * 8 + j];
         rstd[j] = save_rstd[(size_t)b * g.C + cs * 8 + j];
-        s[j] = scale ? scale[(size_t)b * sbs + cs * 8 + j] : 1.f;
-        bb[j] = bias ? bias[(size_t)b * sbs + cs * 8 + j] : 0.f;
     }
+    affine_coeffs(scale, bias, b, sbs, cs * 8, mean, rstd, a, c);
     const int r0 = chunk * g.chunk_rows, r1 = min(g.N, r0 + g.chunk_rows);
-    fwd_apply(x + (size_t)b * g.N * g.C + cs * 8, y + (size_t)b * g.N * g.C + cs * 8, g, r0, r1, rs, mean, rstd, s, bb, slope);
+    fwd_apply(x + (size_t)b * g.N * g.C + cs * 8, y + (size_t)b * g.N * g.C + cs * 8, g, r0, r1, rs, a, c, slope);
 }
 
 // kFused: one CTA per sample computes the statistics itself (chunks == 1); else every CTA merges the chunk
 // partials in `part` (fixed order).
 template <bool kFused>
-__global__ void __launch_bounds__(kClThreads) adain_cl_apply_kernel(const __nv_bfloat16 *__restrict__ x,
+__global__ void __launch_bounds__(kClThreads, 3) adain_cl_apply_kernel(const __nv_bfloat16 *__restrict__ x,
                                                                     const float *__restrict__ part,
                                                                     const float *__restrict__ scale,
                                                                     const float *__restrict__ bias,
@@ -310,7 +317,7 @@ __global__ void __launch_bounds__(kClThreads) adain_cl_apply_kernel(const __nv_b
     const int cs = threadIdx.x % g.lanes, rs = threadIdx.x / g.lanes;
     const int b = blockIdx.y, chunk = blockIdx.x;
     const __nv_bfloat16 *xb = x + (size_t)b * g.N * g.C + cs * 8;
-    float mean[8], rstd[8], s[8], bb[8];
+    float mean[8], rstd[8];
     if (kFused) {
         float piv[8], s1[8], s2[8];
         unpack8(__ldg(reinterpret_cast<const uint4 *>(xb)), piv);
@@ -364,18 +371,15 @@ __global__ void __launch_bounds__(kClThreads) adain_cl_apply_kernel(const __nv_b
             }
         }
     }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        s[j] = scale ? scale[(size_t)b * sbs + cs * 8 + j] : 1.f;
-        bb[j] = bias ? bias[(size_t)b * sbs + cs * 8 + j] : 0.f;
-    }
+    float a[8], c[8];
+    affine_coeffs(scale, bias, b, sbs, cs * 8, mean, rstd, a, c);
     const int r0 = kFused ? 0 : chunk * g.chunk_rows, r1 = kFused ? g.N : min(g.N, r0 + g.chunk_rows);
-    fwd_apply(xb, y + (size_t)b * g.N * g.C + cs * 8, g, r0, r1, rs, mean, rstd, s, bb, slope);
+    fwd_apply(xb, y + (size_t)b * g.N * g.C + cs * 8, g, r0, r1, rs, a, c, slope);
 }
 
 // ---- backward pieces ----------------------------------------------------------------------------------
 struct ClStyle {
-    float mean[8], rstd[8], s[8], bb[8];
+    float mean[8], rstd[8], a[8], c[8];                 // a = scale * rstd, c = bias - mean * a (the forward's coefficients)
 };
 
 __device__ __forceinline__ void load_style(ClStyle &st, const float *scale, const float *bias, const float *save_mean,
@@ -385,11 +389,11 @@ __device__ __forceinline__ void load_style(ClStyle &st, const float *scale, cons
     for (int j = 0; j < 8; ++j) {
         st.mean[j] = save_mean[(size_t)b * C + c0 + j];
         st.rstd[j] = save_rstd[(size_t)b * C + c0 + j];
-        st.s[j] = scale ? scale[(size_t)b * sbs + c0 + j] : 1.f;
-        st.bb[j] = bias ? bias[(size_t)b * sbs + c0 + j] : 0.f;
     }
+    affine_coeffs(scale, bias, b, sbs, c0, st.mean, st.rstd, st.a, st.c);
 }
 
+// sg += sum(g), sgx += sum(g * (x - mean)) with g = dy through the activation (mask from the forward's x * a + c)
 __device__ __forceinline__ void bwd_accumulate(const __nv_bfloat16 *__restrict__ xb, const __nv_bfloat16 *__restrict__ gb,
                                                const ClGeom &g, int r0, int r1, int rs, const ClStyle &st, float slope,
                                                float (&sg)[8], float (&sgx)[8])
@@ -412,19 +416,19 @@ __device__ __forceinline__ void bwd_accumulate(const __nv_bfloat16 *__restrict__
                 unpack8(gr[u], gf);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    const float pre = modulate_cl(xf[j], st.mean[j], st.rstd[j], st.s[j], st.bb[j]);   // the forward's bits
-                    const float gg = pre > 0.f ? gf[j] : gf[j] * slope;
+                    const float gg = fmaf(xf[j], st.a[j], st.c[j]) > 0.f ? gf[j] : gf[j] * slope;
                     sg[j] += gg;
-                    sgx[j] = fmaf(gg, (xf[j] - st.mean[j]) * st.rstd[j], sgx[j]);
+                    sgx[j] = fmaf(gg, xf[j] - st.mean[j], sgx[j]);
                 }
             }
         }
     }
 }
 
+// dx = rstd * (g s - s sum(g) / N - xhat s sum(g xhat) / Nvar) = g * a - (x * c2 + c1)
 __device__ __forceinline__ void bwd_apply(const __nv_bfloat16 *__restrict__ xb, const __nv_bfloat16 *__restrict__ gb,
                                           __nv_bfloat16 *__restrict__ db, const ClGeom &g, int r0, int r1, int rs,
-                                          const ClStyle &st, float slope, const float (&k1)[8], const float (&k2)[8])
+                                          const ClStyle &st, float slope, const float (&c1)[8], const float (&c2)[8])
 {
     for (int r = r0 + rs; r < r1; r += kClUnrollBwd * g.rows_per_pass) {
         uint4 xr[kClUnrollBwd], gr[kClUnrollBwd];
@@ -445,10 +449,8 @@ __device__ __forceinline__ void bwd_apply(const __nv_bfloat16 *__restrict__ xb, 
                 unpack8(gr[u], gf);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    const float xh = (xf[j] - st.mean[j]) * st.rstd[j];
-                    const float pre = modulate_cl(xf[j], st.mean[j], st.rstd[j], st.s[j], st.bb[j]);
-                    const float gg = pre > 0.f ? gf[j] : gf[j] * slope;
-                    xf[j] = st.rstd[j] * (gg * st.s[j] - k1[j] - xh * k2[j]);
+                    const float gg = fmaf(xf[j], st.a[j], st.c[j]) > 0.f ? gf[j] : gf[j] * slope;
+                    xf[j] = fmaf(gg, st.a[j], -fmaf(xf[j], c2[j], c1[j]));
                 }
                 st_stream_16(db + (size_t)rr * g.C, pack8(xf));
             }
@@ -456,7 +458,7 @@ __device__ __forceinline__ void bwd_apply(const __nv_bfloat16 *__restrict__ xb, 
     }
 }
 
-__global__ void __launch_bounds__(kClThreads) adain_cl_bwd_sums_kernel(const __nv_bfloat16 *__restrict__ x,
+__global__ void __launch_bounds__(kClThreads, 3) adain_cl_bwd_sums_kernel(const __nv_bfloat16 *__restrict__ x,
                                                                        const __nv_bfloat16 *__restrict__ dy,
                                                                        const float *__restrict__ scale,
                                                                        const float *__restrict__ bias,
@@ -487,7 +489,7 @@ __global__ void __launch_bounds__(kClThreads) adain_cl_bwd_sums_kernel(const __n
 }
 
 template <bool kFused>
-__global__ void __launch_bounds__(kClThreads) adain_cl_bwd_apply_kernel(const __nv_bfloat16 *__restrict__ x,
+__global__ void __launch_bounds__(kClThreads, 3) adain_cl_bwd_apply_kernel(const __nv_bfloat16 *__restrict__ x,
                                                                         const __nv_bfloat16 *__restrict__ dy,
                                                                         const float *__restrict__ part,
                                                                         const float *__restrict__ scale,
@@ -520,21 +522,20 @@ __global__ void __launch_bounds__(kClThreads) adain_cl_bwd_apply_kernel(const __
             sgx[0] += q0.x; sgx[1] += q0.y; sgx[2] += q0.z; sgx[3] += q0.w; sgx[4] += q1.x; sgx[5] += q1.y; sgx[6] += q1.z; sgx[7] += q1.w;
         }
     }
-    if ((kFused || chunk == 0) && rs == 0 && dscale && dbias) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            dbias[(size_t)b * dsbs + cs * 8 + j] = sg[j];
-            dscale[(size_t)b * dsbs + cs * 8 + j] = sgx[j];
-        }
-    }
-    float k1[8], k2[8];
+    const bool publish = (kFused || chunk == 0) && rs == 0 && dscale && dbias;
+    float c1[8], c2[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        k1[j] = st.s[j] * sg[j] / (float)g.N;
-        k2[j] = st.s[j] * sgx[j] / (float)g.Nvar;
+        const float sgxh = sgx[j] * st.rstd[j];                         // sum(g * xhat)
+        if (publish) {
+            dbias[(size_t)b * dsbs + cs * 8 + j] = sg[j];
+            dscale[(size_t)b * dsbs + cs * 8 + j] = sgxh;
+        }
+        c2[j] = st.a[j] * st.rstd[j] * (sgxh / (float)g.Nvar);          // s rstd^2 sum(g xhat) / Nvar
+        c1[j] = st.a[j] * (sg[j] / (float)g.N) - st.mean[j] * c2[j];
     }
     const int r0 = kFused ? 0 : chunk * g.chunk_rows, r1 = kFused ? g.N : min(g.N, r0 + g.chunk_rows);
-    bwd_apply(x + base, dy + base, dx + base, g, r0, r1, rs, st, slope, k1, k2);
+    bwd_apply(x + base, dy + base, dx + base, g, r0, r1, rs, st, slope, c1, c2);
 }
 
 
@@ -769,10 +770,10 @@ static int cl_geom(const char *who, int batch, int channels, int ndim, int size,
     g.lanes = lanes; g.rows_per_pass = kClThreads / lanes;
     // small instance (<= 64 KB): one CTA per sample does both phases; else ~16 chunks per sample
     const long long bytes = rows * channels * 2;
-    // else cut every sample into chunks so that ~2 fat CTAs per SM stream >= kClUnroll rows per thread each
+    // else cut every sample into chunks so that the grid is one wave of 3 CTAs per SM, >= kClUnroll rows per thread each
     int chunks = 1;
     if (bytes > 64 * 1024) {
-        chunks = (2 * sm_count() + batch - 1) / batch;
+        chunks = (3 * sm_count()) / batch;             // one wave at three resident CTAs per SM
         if (chunks < 2) chunks = 2;
         if (chunks > kClMaxChunks) chunks = kClMaxChunks;
         while (chunks > 1 && rows / chunks < (long long)g.rows_per_pass * kClUnroll) --chunks;

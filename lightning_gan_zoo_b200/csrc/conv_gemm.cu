@@ -71,7 +71,15 @@ struct TapGemmParams {
                                 // hg_adain_cl_fwd_stats merges the groups of a sample (Chan) -- the conv output is not re-read.
     const float *out_scale;     // device scalar (may be null): accumulators are multiplied by it before bias / activation
                                 // (1 / sigma of the spectral norm: conv(x, W / sigma) = conv(x, W) / sigma)
+    // tile scheduler: a CTA walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ... of the (group, n tile, m tile) space
+    // (m fastest, groups in the order of `order`: longest K loops first).  A one-tile-per-CTA launch is the special case
+    // gridDim.x == total tiles.  nacc accumulator stages of acc_stride TMEM columns each: with two, the epilogue of
+    // tile i overlaps the main loop of tile i + 1.
+    int m_tiles, n_tiles;
+    int nacc, acc_stride;
+    int stats_scratch;          // 1: the epilogue's statistics scratch sits behind the operand ring (persistent launches)
     int num_groups;
+    uint8_t order[kMaxGroups];
     Group groups[kMaxGroups];
     Tap taps[kMaxTaps];
 };
@@ -98,7 +106,9 @@ struct WgradParams {
 struct SharedCtl {
     uint64_t full[kMaxStages];
     uint64_t empty[kMaxStages];
-    uint64_t acc_ready;
+    uint64_t acc_ready;         // wgrad kernel (one tile per CTA)
+    uint64_t acc_full[2];       // tap kernel: MMA warp -> epilogue warps, per accumulator stage
+    uint64_t acc_empty[2];      // epilogue warps -> MMA warp
     uint32_t tmem_base;
 };
 
@@ -123,9 +133,8 @@ __global__ void __launch_bounds__(kThreads, 1) tap_gemm_kernel(const __grid_cons
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int BN = p.BN;
     const uint32_t a_bytes = kBM * 128, b_bytes = (uint32_t)BN * 128, stage_bytes = a_bytes + b_bytes;
-    const Group grp = p.groups[blockIdx.z];
-    const int n0 = blockIdx.y * BN;
-    const int total_iters = grp.tap_count * p.k_chunks;
+    const int tiles_mn = p.m_tiles * p.n_tiles, total_tiles = tiles_mn * p.num_groups;
+    const uint32_t tmem_cols = tmem_cols_for(p.nacc * p.acc_stride);
 
     if (warp == 0 && ptx::elect_one()) {
         ptx::prefetch_tensormap(&p.tmA);
@@ -134,11 +143,14 @@ __global__ void __launch_bounds__(kThreads, 1) tap_gemm_kernel(const __grid_cons
             ptx::mbar_init(&ctl.full[s], 1);
             ptx::mbar_init(&ctl.empty[s], 1);
         }
-        ptx::mbar_init(&ctl.acc_ready, 1);
+        for (int a = 0; a < 2; ++a) {
+            ptx::mbar_init(&ctl.acc_full[a], 1);
+            ptx::mbar_init(&ctl.acc_empty[a], 4);       // one arrival per epilogue warp
+        }
         ptx::fence_barrier_init();
     }
     if (warp == 1) {
-        ptx::tmem_alloc(&ctl.tmem_base, tmem_cols_for(p.epi_cols));
+        ptx::tmem_alloc(&ctl.tmem_base, tmem_cols);
         ptx::tmem_relinquish();
     }
     ptx::tc_fence_before();
@@ -148,24 +160,29 @@ __global__ void __launch_bounds__(kThreads, 1) tap_gemm_kernel(const __grid_cons
 
     if (warp == 0) {
         if (ptx::elect_one()) {
-            // ===== TMA producer =====
-            long long pos = (long long)blockIdx.x * kBM;
-            const int x0 = (int)(pos % p.X); pos /= p.X;
-            const int y0 = (int)(pos % p.Y); pos /= p.Y;
-            const int z0 = (int)(pos % p.Z);
-            const int b0 = (int)(pos / p.Z);
+            // ===== TMA producer: runs ahead of the MMA warp across tile boundaries =====
             int it = 0;
-            for (int t = 0; t < grp.tap_count; ++t) {
-                const Tap tap = p.taps[grp.tap_begin + t];
-                for (int kc = 0; kc < p.k_chunks; ++kc, ++it) {
-                    const int s = it % p.stages;
-                    const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
-                    ptx::mbar_wait(&ctl.empty[s], ph ^ 1u);
-                    uint8_t *a_dst = tiles + (size_t)s * stage_bytes;
-                    ptx::mbar_arrive_expect_tx(&ctl.full[s], stage_bytes);
-                    ptx::tma_load_5d(a_dst, &p.tmA, &ctl.full[s], tap.a_c_off + kc * kBK, x0 + tap.sx, y0 + tap.sy,
-                                     z0 + tap.sz, b0);
-                    ptx::tma_load_2d(a_dst + a_bytes, &p.tmB, &ctl.full[s], kc * kBK, tap.b_row_off + n0);
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                const int gi = t / tiles_mn, r = t - gi * tiles_mn, n_idx = r / p.m_tiles, m_idx = r - n_idx * p.m_tiles;
+                const Group grp = p.groups[p.order[gi]];
+                const int n0 = n_idx * BN;
+                long long pos = (long long)m_idx * kBM;
+                const int x0 = (int)(pos % p.X); pos /= p.X;
+                const int y0 = (int)(pos % p.Y); pos /= p.Y;
+                const int z0 = (int)(pos % p.Z);
+                const int b0 = (int)(pos / p.Z);
+                for (int tp = 0; tp < grp.tap_count; ++tp) {
+                    const Tap tap = p.taps[grp.tap_begin + tp];
+                    for (int kc = 0; kc < p.k_chunks; ++kc, ++it) {
+                        const int s = it % p.stages;
+                        const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+                        ptx::mbar_wait(&ctl.empty[s], ph ^ 1u);
+                        uint8_t *a_dst = tiles + (size_t)s * stage_bytes;
+                        ptx::mbar_arrive_expect_tx(&ctl.full[s], stage_bytes);
+                        ptx::tma_load_5d(a_dst, &p.tmA, &ctl.full[s], tap.a_c_off + kc * kBK, x0 + tap.sx, y0 + tap.sy,
+                                         z0 + tap.sz, b0);
+                        ptx::tma_load_2d(a_dst + a_bytes, &p.tmB, &ctl.full[s], kc * kBK, tap.b_row_off + n0);
+                    }
                 }
             }
         }
@@ -173,111 +190,132 @@ __global__ void __launch_bounds__(kThreads, 1) tap_gemm_kernel(const __grid_cons
         if (ptx::elect_one()) {
             // ===== MMA issuer =====
             const uint32_t idesc = ptx::idesc_bf16(kBM, BN, false, false);
-            uint32_t started = 0;                       // accumulators that already hold a partial sum
-            int it = 0;
-            for (int t = 0; t < grp.tap_count; ++t) {
-                const int acc = p.taps[grp.tap_begin + t].acc;
-                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-                for (int kc = 0; kc < p.k_chunks; ++kc, ++it) {
-                    const int s = it % p.stages;
-                    const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
-                    ptx::mbar_wait(&ctl.full[s], ph);
-                    ptx::tc_fence_after();
-                    const uint32_t a_addr = ptx::smem_u32(tiles + (size_t)s * stage_bytes);
-                    const uint64_t a_desc = ptx::smem_desc_sw128(a_addr, 16, 1024);
-                    const uint64_t b_desc = ptx::smem_desc_sw128(a_addr + a_bytes, 16, 1024);
+            int it = 0, i = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++i) {
+                const int gi = t / tiles_mn;
+                const Group grp = p.groups[p.order[gi]];
+                const int acc_stage = i % p.nacc;
+                const uint32_t aph = (uint32_t)(i / p.nacc) & 1u;
+                ptx::mbar_wait(&ctl.acc_empty[acc_stage], aph ^ 1u);       // the epilogue has drained this stage
+                ptx::tc_fence_after();
+                uint32_t started = 0;                       // accumulators that already hold a partial sum
+                for (int tp = 0; tp < grp.tap_count; ++tp) {
+                    const int acc = p.taps[grp.tap_begin + tp].acc;
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(acc_stage * p.acc_stride + acc * BN);
+                    for (int kc = 0; kc < p.k_chunks; ++kc, ++it) {
+                        const int s = it % p.stages;
+                        const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+                        ptx::mbar_wait(&ctl.full[s], ph);
+                        ptx::tc_fence_after();
+                        const uint32_t a_addr = ptx::smem_u32(tiles + (size_t)s * stage_bytes);
+                        const uint64_t a_desc = ptx::smem_desc_sw128(a_addr, 16, 1024);
+                        const uint64_t b_desc = ptx::smem_desc_sw128(a_addr + a_bytes, 16, 1024);
 #pragma unroll
-                    for (int k = 0; k < kBK / 16; ++k)  // +32 bytes (>>4 = 2) per 16-element K step inside the swizzle row
-                        ptx::umma_bf16(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc,
-                                       ((started >> acc) & 1u) != 0 || k != 0);
-                    started |= 1u << acc;
-                    ptx::umma_commit(&ctl.empty[s]);    // frees the smem slot when these MMAs retire
+                        for (int k = 0; k < kBK / 16; ++k)  // +32 bytes (>>4 = 2) per 16-element K step inside the swizzle row
+                            ptx::umma_bf16(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc,
+                                           ((started >> acc) & 1u) != 0 || k != 0);
+                        started |= 1u << acc;
+                        ptx::umma_commit(&ctl.empty[s]);    // frees the smem slot when these MMAs retire
+                    }
                 }
+                ptx::umma_commit(&ctl.acc_full[acc_stage]);
             }
-            ptx::umma_commit(&ctl.acc_ready);
         }
     } else {
         // ===== epilogue: TMEM -> registers -> bias / activation -> bf16 -> global =====
-        ptx::mbar_wait(&ctl.acc_ready, 0);
-        ptx::tc_fence_after();
         const int quad = warp & 3;                      // a warp may only touch TMEM lanes 32*(warp%4) .. +31
         const int row = quad * 32 + lane;
-        const long long m = (long long)blockIdx.x * kBM + row;
-        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
-        __nv_bfloat16 *orow = static_cast<__nv_bfloat16 *>(p.out) + m * p.ld_out + grp.out_col_off + n0;
-        float *prow = p.partial ? p.partial + (size_t)grp.part * p.partial_stride + m * p.ld_out + grp.out_col_off + n0 : nullptr;
-        const float oscale = (p.out_scale && !prow) ? __ldg(p.out_scale) : 1.f;
-        for (int c0 = 0; c0 < p.epi_cols; c0 += 32) {
-            float v[32];
-            if (c0 + 32 <= p.epi_cols) {
-                ptx::tmem_ld_32(taddr + (uint32_t)c0, v);
-            } else {                                    // 16-column tail (epi_cols is a multiple of 16)
-                float t[16];
-                ptx::tmem_ld_16(taddr + (uint32_t)c0, t);
+        // statistics scratch: behind the ring when tiles overlap (persistent), else the idle ring itself
+        float *scr = reinterpret_cast<float *>(p.stats_scratch ? tiles + (size_t)p.stages * stage_bytes : tiles) + quad * (32 * 33);
+        int i = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++i) {
+            const int gi = t / tiles_mn, r = t - gi * tiles_mn, n_idx = r / p.m_tiles, m_idx = r - n_idx * p.m_tiles;
+            const Group grp = p.groups[p.order[gi]];
+            const int n0 = n_idx * BN;
+            const int acc_stage = i % p.nacc;
+            const uint32_t aph = (uint32_t)(i / p.nacc) & 1u;
+            ptx::mbar_wait(&ctl.acc_full[acc_stage], aph);
+            ptx::tc_fence_after();
+            const long long m = (long long)m_idx * kBM + row;
+            const uint32_t taddr = tmem_base + (uint32_t)(acc_stage * p.acc_stride) + ((uint32_t)(quad * 32) << 16);
+            __nv_bfloat16 *orow = static_cast<__nv_bfloat16 *>(p.out) + m * p.ld_out + grp.out_col_off + n0;
+            float *prow = p.partial ? p.partial + (size_t)grp.part * p.partial_stride + m * p.ld_out + grp.out_col_off + n0 : nullptr;
+            const float oscale = (p.out_scale && !prow) ? __ldg(p.out_scale) : 1.f;
+            for (int c0 = 0; c0 < p.epi_cols; c0 += 32) {
+                float v[32];
+                if (c0 + 32 <= p.epi_cols) {
+                    ptx::tmem_ld_32(taddr + (uint32_t)c0, v);
+                } else {                                    // 16-column tail (epi_cols is a multiple of 16)
+                    float tt[16];
+                    ptx::tmem_ld_16(taddr + (uint32_t)c0, tt);
 #pragma unroll
-                for (int j = 0; j < 16; ++j) { v[j] = t[j]; v[16 + j] = 0.f; }
-            }
-            if (prow) {                                 // split-K partial: raw fp32 accumulators
+                    for (int j = 0; j < 16; ++j) { v[j] = tt[j]; v[16 + j] = 0.f; }
+                }
+                if (prow) {                                 // split-K partial: raw fp32 accumulators
+                    if (m < p.m_total) {
+                        const int nvec = min(32, p.epi_cols - c0) / 4;
+                        float4 *dst = reinterpret_cast<float4 *>(prow + c0);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            if (j < nvec) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    }
+                    continue;
+                }
+                const int ncol = min(32, p.epi_cols - c0);
+                const int bcol = (n0 + c0) % p.bias_mod;          // bias_mod is a multiple of 16 and of ncol's run
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    v[j] *= oscale;
+                    if (p.bias && j < ncol) v[j] += __ldg(p.bias + (bcol + j) % p.bias_mod);
+                }
+                if (p.stats) {
+                    // column sums over this warp's 32 rows through a padded shared-memory transpose; rows past the end
+                    // of the tensor count as zero
+                    const bool live = m < p.m_total;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) scr[lane * 33 + j] = live ? v[j] : 0.f;
+                    __syncwarp();
+                    float sum = 0.f, sq = 0.f;
+#pragma unroll
+                    for (int rr = 0; rr < 32; ++rr) {
+                        const float tv = scr[rr * 33 + lane];
+                        sum += tv;
+                        sq = fmaf(tv, tv, sq);
+                    }
+                    __syncwarp();
+                    if (lane < ncol) {
+                        const long long grow = (long long)m_idx * 4 + quad;
+                        *reinterpret_cast<float2 *>(p.stats + (grow * p.ld_out + grp.out_col_off + n0 + c0 + lane) * 2) = make_float2(sum, sq);
+                    }
+                }
                 if (m < p.m_total) {
-                    const int nvec = min(32, p.epi_cols - c0) / 4;
-                    float4 *dst = reinterpret_cast<float4 *>(prow + c0);
+                    uint32_t packed[16];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        if (j < nvec) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                }
-                continue;
-            }
-            const int ncol = min(32, p.epi_cols - c0);
-            const int bcol = (n0 + c0) % p.bias_mod;          // bias_mod is a multiple of 16 and of ncol's run
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                v[j] *= oscale;
-                if (p.bias && j < ncol) v[j] += __ldg(p.bias + (bcol + j) % p.bias_mod);
-            }
-            if (p.stats) {
-                // column sums over this warp's 32 rows through a padded shared-memory transpose (the operand ring is idle:
-                // acc_ready means every MMA that read it has retired); rows past the end of the tensor count as zero
-                float *scr = reinterpret_cast<float *>(tiles) + quad * (32 * 33);
-                const bool live = m < p.m_total;
-#pragma unroll
-                for (int j = 0; j < 32; ++j) scr[lane * 33 + j] = live ? v[j] : 0.f;
-                __syncwarp();
-                float sum = 0.f, sq = 0.f;
-#pragma unroll
-                for (int r = 0; r < 32; ++r) {
-                    const float t = scr[r * 33 + lane];
-                    sum += t;
-                    sq = fmaf(t, t, sq);
-                }
-                __syncwarp();
-                if (lane < ncol) {
-                    const long long grow = (long long)blockIdx.x * 4 + quad;
-                    *reinterpret_cast<float2 *>(p.stats + (grow * p.ld_out + grp.out_col_off + n0 + c0 + lane) * 2) = make_float2(sum, sq);
+                    for (int j = 0; j < 32; j += 2) {
+                        float a = v[j], b = v[j + 1];
+                        a = a > 0.f ? a : a * p.slope;
+                        b = b > 0.f ? b : b * p.slope;
+                        __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+                        packed[j >> 1] = *reinterpret_cast<uint32_t *>(&h);
+                    }
+                    uint4 *dst = reinterpret_cast<uint4 *>(orow + c0);
+                    dst[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+                    dst[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+                    if (ncol > 16) {
+                        dst[2] = make_uint4(packed[8], packed[9], packed[10], packed[11]);
+                        dst[3] = make_uint4(packed[12], packed[13], packed[14], packed[15]);
+                    }
                 }
             }
-            if (m < p.m_total) {
-                uint32_t packed[16];
-#pragma unroll
-                for (int j = 0; j < 32; j += 2) {
-                    float a = v[j], b = v[j + 1];
-                    a = a > 0.f ? a : a * p.slope;
-                    b = b > 0.f ? b : b * p.slope;
-                    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-                    packed[j >> 1] = *reinterpret_cast<uint32_t *>(&h);
-                }
-                uint4 *dst = reinterpret_cast<uint4 *>(orow + c0);
-                dst[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-                dst[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
-                if (ncol > 16) {
-                    dst[2] = make_uint4(packed[8], packed[9], packed[10], packed[11]);
-                    dst[3] = make_uint4(packed[12], packed[13], packed[14], packed[15]);
-                }
-            }
+            // this warp is done with the accumulator stage: hand it back to the MMA warp
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&ctl.acc_empty[acc_stage]);
         }
     }
     ptx::tc_fence_before();
     __syncthreads();
-    if (warp == 1) ptx::tmem_dealloc(tmem_base, tmem_cols_for(p.epi_cols));
+    if (warp == 1) ptx::tmem_dealloc(tmem_base, tmem_cols);
 }
 
 // Sum of the split-K partials written by tap_gemm_kernel: out[m][col] = bf16(sum_{s < nsplit[col / block_cols]}
@@ -730,15 +768,42 @@ static int launch_tap_gemm(TapGemmParams &p, int m_tiles, int n_tiles, cudaStrea
     const int stage_bytes = kBM * 128 + p.BN * 128;
     int max_iters = 0;
     for (int g = 0; g < p.num_groups; ++g) max_iters = p.groups[g].tap_count * p.k_chunks > max_iters ? p.groups[g].tap_count * p.k_chunks : max_iters;
-    const bool dual = want_dual(stage_bytes, max_iters, p.epi_cols);
-    p.stages = pick_stages(stage_bytes, max_iters, dual ? kDualSmemBudget : kSmemBudget);
-    const size_t smem = (size_t)p.stages * stage_bytes + 1024;
+    p.m_tiles = m_tiles; p.n_tiles = n_tiles;
+    // longest K loops first (tiles of one group are equally long)
+    for (int g = 0; g < p.num_groups; ++g) p.order[g] = (uint8_t)g;
+    for (int a = 1; a < p.num_groups; ++a)
+        for (int b = a; b > 0 && p.groups[p.order[b]].tap_count > p.groups[p.order[b - 1]].tap_count; --b) {
+            const uint8_t tmp = p.order[b]; p.order[b] = p.order[b - 1]; p.order[b - 1] = tmp;
+        }
+    const long long total = (long long)m_tiles * n_tiles * p.num_groups;
+    const int scratch = p.stats ? 4 * 32 * 33 * (int)sizeof(float) : 0;
+    const bool persistent = option(kOptTapGemmPersistent) != 0 && total > sm_count();
+    unsigned grid;
+    size_t smem;
+    if (persistent) {
+        // one CTA per SM walks the tile list; two accumulator stages when they fit (<= 256 columns each): the epilogue of
+        // a tile overlaps the main loop of the next, and prologue / TMEM allocation / tensor-map fetch happen once
+        p.nacc = p.epi_cols <= 256 ? 2 : 1;
+        p.acc_stride = p.epi_cols <= 256 ? (int)(p.epi_cols <= 32 ? 32 : p.epi_cols <= 64 ? 64 : p.epi_cols <= 128 ? 128 : 256) : 512;
+        p.stats_scratch = p.stats ? 1 : 0;
+        p.stages = pick_stages(stage_bytes, 1 << 20, kSmemBudget - scratch);
+        smem = (size_t)p.stages * stage_bytes + 1024 + scratch;
+        grid = (unsigned)sm_count();
+    } else {
+        const bool dual = want_dual(stage_bytes, max_iters, p.epi_cols);
+        p.nacc = 1;
+        p.acc_stride = p.epi_cols;
+        p.stats_scratch = 0;
+        p.stages = pick_stages(stage_bytes, max_iters, dual ? kDualSmemBudget : kSmemBudget);
+        if (p.stats && (size_t)p.stages * stage_bytes < (size_t)scratch) p.stages = (scratch + stage_bytes - 1) / stage_bytes;
+        smem = (size_t)p.stages * stage_bytes + 1024;
+        grid = (unsigned)total;
+    }
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(tap_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+        cudaFuncSetAttribute(tap_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget + 2048);
         attr_set = true;
     }
-    dim3 grid(m_tiles, n_tiles, p.num_groups);
     tap_gemm_kernel<<<grid, kThreads, smem, st>>>(p);
     return check_launch(who);
 }

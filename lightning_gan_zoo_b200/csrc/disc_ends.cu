@@ -87,31 +87,35 @@ template <bool HEAD> __device__ __forceinline__ int c0_map_row(int oy, int ox, i
 
 // ---- image -> map --------------------------------------------------------------------------------------
 // im2col GEMM  M = 16 map pixels per warp, K = KPad, N = 64: A fragments gathered from the staged patch, B fragments
-// (weights) held in registers.  conv0: + bias, LeakyReLU; head dx: raw.
+// (weights) fragment-ready in shared memory.  conv0: + bias, LeakyReLU; head dx: raw.
 template <int KS, int PAD, bool HEAD>
-__global__ void __launch_bounds__(kC0Threads) c0_img2map_kernel(C0Image img, const float *__restrict__ w, const float *__restrict__ bias,
+__global__ void __launch_bounds__(kC0Threads, 3) c0_img2map_kernel(C0Image img, const float *__restrict__ w, const float *__restrict__ bias,
                                                                 __nv_bfloat16 *__restrict__ y, int S, int total_tiles, float slope)
 {
     using G = C0Geom<KS>;
     __shared__ __align__(16) __nv_bfloat16 patch[kC0Cin * G::PH * G::PPitch];
+    // B fragments (weights) of all k-steps and n-tiles, fragment-ready: one conflict-free 8-byte load per MMA.  They live
+    // in shared memory, not registers (a register-resident version needed 255 registers = one CTA per SM, and the kernel
+    // is latency-bound: patch loads, shared-memory gathers)
+    __shared__ __align__(8) uint2 bws[G::KSteps * 8 * 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, q = lane & 3;
     const int S2 = S / 2, tiles_x = S2 / kC0TW, tiles_img = tiles_x * (S2 / kC0TH);
-    uint32_t bw[G::KSteps][8][2];                       // B[k][n] = w[n][c][ky][kx]
+    for (int i = threadIdx.x; i < G::KSteps * 8 * 32; i += kC0Threads) {      // B[k][n] = w[n][c][ky][kx]
+        const int ln = i & 31, nt = (i >> 5) & 7, ks = i >> 8, gg = ln >> 2, qq = ln & 3;
+        uint32_t frag[2];
 #pragma unroll
-    for (int ks = 0; ks < G::KSteps; ++ks)
+        for (int h = 0; h < 2; ++h) {
+            const int k = ks * 16 + 2 * qq + 8 * h, n = nt * 8 + gg;
+            float v[2];
 #pragma unroll
-        for (int nt = 0; nt < 8; ++nt)
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int k = ks * 16 + 2 * q + 8 * h, n = nt * 8 + g;
-                float v[2];
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const int kk = k + e, kx = kk % G::KX, r = kk / G::KX, ky = r % KS, ci = r / KS;
-                    v[e] = (kk < G::KReal && kx < KS) ? __ldg(w + ((size_t)(n * kC0Cin + ci) * KS + ky) * KS + kx) : 0.f;
-                }
-                bw[ks][nt][h] = pack_bf16x2(v[0], v[1]);
+            for (int e = 0; e < 2; ++e) {
+                const int kk = k + e, kx = kk % G::KX, r = kk / G::KX, ky = r % KS, ci = r / KS;
+                v[e] = (kk < G::KReal && kx < KS) ? __ldg(w + ((size_t)(n * kC0Cin + ci) * KS + ky) * KS + kx) : 0.f;
             }
+            frag[h] = pack_bf16x2(v[0], v[1]);
+        }
+        bws[i] = make_uint2(frag[0], frag[1]);
+    }
     int aoff[G::KSteps][2];
 #pragma unroll
     for (int ks = 0; ks < G::KSteps; ++ks) {
@@ -144,7 +148,10 @@ __global__ void __launch_bounds__(kC0Threads) c0_img2map_kernel(C0Image img, con
             a[2] = lds32(prow + (aoff[ks][1] + 2 * g) * 2);
             a[3] = lds32(prow + (aoff[ks][1] + 2 * (g + 8)) * 2);
 #pragma unroll
-            for (int nt = 0; nt < 8; ++nt) mma_bf16_16816(acc[nt], a, bw[ks][nt][0], bw[ks][nt][1]);
+            for (int nt = 0; nt < 8; ++nt) {
+                const uint2 bf = bws[(ks * 8 + nt) * 32 + lane];
+                mma_bf16_16816(acc[nt], a, bf.x, bf.y);
+            }
         }
         const int oy = oy0 + warp;
         __nv_bfloat16 *yb = y + (size_t)b * S2 * S2 * kC0Cout;
@@ -721,7 +728,8 @@ static int c0_geom(const char *who, int batch, int cin, int cout, int size, int 
     HG_REQUIRE(size % (2 * kC0TW) == 0, HG_ERR_UNSUPPORTED, "%s: image size must be a multiple of %d (got %d)", who, 2 * kC0TW, size);
     const int S2 = size / 2;
     tiles = batch * (S2 / kC0TH) * (S2 / kC0TW);
-    grid = tiles < 2 * sm_count() ? tiles : 2 * sm_count();
+    const int per_cta = (tiles + 3 * sm_count() - 1) / (3 * sm_count());     // balanced: every CTA walks the same number of tiles
+    grid = (tiles + per_cta - 1) / per_cta;
     return HG_OK;
 }
 

@@ -42,6 +42,7 @@ enum Option {
     kOptRotateSlab32,           // 1: 32^3 rotate forward on source-slab tiles
     kOptRotateGatherBwd,        // 1: 32^3 rotate backward as a table-free per-voxel gather
     kOptAdainGemmStats,         // 1: generator AdaIN statistics from the tap-GEMM epilogue (read by the Python layer)
+    kOptTapGemmPersistent,      // 1: tap GEMMs with more tiles than SMs run one persistent CTA per SM (0: one tile per CTA)
     kOptCount
 };
 int option(Option o);

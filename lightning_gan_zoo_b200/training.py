@@ -282,8 +282,9 @@ class HologanTrainer:
         # gradient buckets in the order the backward pass finishes them (data parallel: each is all-reduced as soon as
         # it is final, overlapping the rest of the backward; world 1: only the buffer layout)
         gen, disc = self.generator, self.discriminator
-        g_buckets = [[gen.block3.convTranspose.weight, gen.block4.convTranspose.weight], [gen.convTranspose2d1.weight]] if cuda else ()
-        d_buckets = [[disc.blocks[2].conv2d.weight_orig]] if cuda else ()
+        g_buckets = [[gen.block3.convTranspose.weight, gen.block4.convTranspose.weight], [gen.convTranspose2d1.weight],
+                     [gen.block2.convTranspose.weight], [gen.block1.convTranspose.weight]] if cuda else ()
+        d_buckets = [[disc.blocks[2].conv2d.weight_orig], [disc.blocks[1].conv2d.weight_orig]] if cuda else ()
         self.d_grads = _FlatGrads(self.discriminator.parameters(), accumulate_into=sn_weights, buckets=d_buckets)
         # the generator's tcgen05 wgrad kernels store straight into the flat buffer (ops._direct_grad_target)
         self.g_grads = _FlatGrads(self.generator.parameters(), direct=cuda, buckets=g_buckets)
@@ -299,12 +300,15 @@ class HologanTrainer:
             kw = dict(betas=(cfg.beta1, cfg.beta2), fused=cuda, capturable=cuda)
             self.opt_d = torch.optim.Adam(self.d_grads.params, lr=lr, **kw)
             self.opt_g = torch.optim.Adam(self.g_grads.params, lr=lr.clone() if cuda else lr, **kw)
-        if cuda and self.world > 1:
+        if cuda and self.world > 1 and os.environ.get("HG_NO_GRAD_OVERLAP", "0") in ("", "0"):   # A/B switch: one all-reduce after the backward
             w = self.world
             gen.block3.convTranspose.weight._hg_grad_ready = lambda: self.g_grads.fire(0, w)
             gen.convTranspose2d1.weight._hg_grad_ready = lambda: self.g_grads.fire(1, w)
-            # the D step runs the discriminator on real and on fake: the bucket is final after the second backward
+            gen.block2.convTranspose.weight._hg_grad_ready = lambda: self.g_grads.fire(2, w)
+            gen.block1.convTranspose.weight._hg_grad_ready = lambda: self.g_grads.fire(3, w)
+            # the D step runs the discriminator on real and on fake: a bucket is final after the second backward
             disc.blocks[2].conv2d.weight_orig._hg_grad_ready = lambda: self.d_grads.fire(0, w, after_calls=2)
+            disc.blocks[1].conv2d.weight_orig._hg_grad_ready = lambda: self.d_grads.fire(1, w, after_calls=2)
         self._graphs = None
         lam = hologan_lr_lambda(cfg.num_epochs)
         self.sched_d = torch.optim.lr_scheduler.LambdaLR(self.opt_d, lam)

@@ -79,10 +79,12 @@ for st in $STAGES; do
   case $st in ncu:*)
     targets=$(echo ${st#ncu:} | tr ',' ' ')
     for t in $targets; do
-      HG_NCU_REPS=1 timeout 900 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:hg:: -c 40 -f \
+      HG_NCU_REPS=1 timeout 900 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:hg:: -c ${NCU_COUNT:-40} -f \
           -o $OUT/${TAG}_full_$t python tools/ncu_targets.py $t > $OUT/${TAG}_full_$t.log 2>&1
       echo "ncu full $t exit $?"
       ncu -i $OUT/${TAG}_full_$t.ncu-rep --page raw --csv > $OUT/${TAG}_full_${t}_raw.csv 2>/dev/null
+      # gpurun merges at most 64 MiB back: keep the report only when it is small, the raw CSV always
+      [ $(stat -c %s $OUT/${TAG}_full_$t.ncu-rep) -gt 12000000 ] && rm -f $OUT/${TAG}_full_$t.ncu-rep
     done;;
   esac
 done

@@ -295,6 +295,45 @@ def pipeline():
     nbytes = B * 64 * 64 * 64 * 2 + B * 3 * 64 * 64 * 4
     report("final_conv_tanh (64,64^2,64->3) fwd", tf, nbytes)
     report("final_conv_tanh fwd+bwd (dx + dw)", tfb, 3 * nbytes)
+    # discriminator ends + patched 128 head (disc_ends.cu): bytes = image fp32 + 64-channel map bf16
+    for S, Bq in ((64, B), (128, 32)):
+        x = [torch.rand(Bq, 3, S, S, device=DEV) * 2 - 1 for _ in range(6)]
+        w0 = torch.randn(64, 3, 5, 5, device=DEV) * 0.05; b0 = torch.zeros(64, device=DEV)
+        y = torch.empty(Bq, S // 4, S // 4, 4, 64, device=DEV, dtype=bf)
+        dy = torch.randn(Bq, S // 4, S // 4, 4, 64, device=DEV).to(bf)
+        dxi = torch.empty(Bq, 3, S, S, device=DEV); dw0 = torch.empty_like(w0); db0 = torch.empty(64, device=DEV)
+        nb0 = _lib.load().hg_dconv0_bwd_workspace_bytes(Bq, S); ws0 = torch.empty(nb0, dtype=torch.uint8, device=DEV)
+        nbytes = Bq * 3 * S * S * 4 + Bq * (S // 2) ** 2 * 64 * 2
+        t = time_rot(lambda xi: _lib.call("hg_dconv0_fwd", P(xi), P(w0), P(b0), P(y), Bq, 3, 64, S, ctypes.c_float(0.2), ops._stream()), x)
+        report(f"dconv0 fwd (B{Bq}, {S}^2)", t, nbytes)
+        t = time_rot(lambda xi: _lib.call("hg_dconv0_bwd", P(xi), P(w0), P(y), P(dy), P(None), P(dw0), P(db0), P(ws0), nb0, Bq, 3, 64, S,
+                                          ctypes.c_float(0.2), 0, ops._stream()), x)
+        report(f"dconv0 bwd dw (B{Bq}, {S}^2)", t, nbytes + Bq * (S // 2) ** 2 * 64 * 2)
+        t = time_rot(lambda xi: _lib.call("hg_dconv0_bwd", P(xi), P(w0), P(y), P(dy), P(dxi), P(None), P(None), P(ws0), nb0, Bq, 3, 64, S,
+                                          ctypes.c_float(0.2), 0, ops._stream()), x)
+        report(f"dconv0 bwd dx (B{Bq}, {S}^2)", t, nbytes + Bq * (S // 2) ** 2 * 64 * 2)
+    hs = [torch.randn(B, 4, 4, 512, device=DEV).to(bf).requires_grad_(True) for _ in range(6)]
+    hp = [torch.randn(1, 8192, device=DEV) * 0.02, torch.zeros(1, device=DEV), torch.randn(128, 8192, device=DEV) * 0.02,
+          torch.zeros(128, device=DEV), torch.randn(128, 128, device=DEV) * 0.1, torch.zeros(128, device=DEV)]
+    hp = [t_.requires_grad_(True) for t_ in hp]
+    with torch.no_grad():
+        t = time_rot(lambda h_: ops.dheads(h_, *hp, 0.2), hs)
+    report("dheads fwd (B64, 8192 features)", t, B * 8192 * 2 + 129 * 8192 * 4)
+    def hfb(h_):
+        lg, zp = ops.dheads(h_, *hp, 0.2)
+        (lg.sum() + zp.sum()).backward()
+    t = time_rot(hfb, hs, graph=False)
+    report("dheads fwd+bwd (eager, incl. autograd)", t, 3 * (B * 8192 * 2 + 129 * 8192 * 4))
+    x128 = [torch.randn(32, 64, 64, 64, device=DEV).to(bf).requires_grad_(True) for _ in range(6)]
+    w128 = (torch.randn(64, 3, 4, 4, device=DEV) * 0.05).requires_grad_(True); b128 = torch.zeros(3, device=DEV, requires_grad=True)
+    with torch.no_grad():
+        t = time_rot(lambda xi: ops.head128_tanh(xi, w128, b128), x128)
+    report("head128 fwd (B32, 64^2 x64 -> 3 x 128^2)", t, 32 * 64 * 64 * 64 * 2 + 32 * 3 * 128 * 128 * 4)
+    d128 = torch.randn(32, 3, 128, 128, device=DEV)
+    def h128fb(xi):
+        ops.head128_tanh(xi, w128, b128).backward(d128)
+    t = time_rot(h128fb, x128, graph=False)
+    report("head128 fwd+bwd (eager, incl. autograd)", t, 3 * (32 * 64 * 64 * 64 * 2 + 32 * 3 * 128 * 128 * 4))
     # weight packing (all five conv layers of G) and activation backward of the projection
     ws = [torch.randn(512, 128, 3, 3, 3, device=DEV), torch.randn(128, 64, 3, 3, 3, device=DEV), torch.randn(1024, 1024, 1, 1, device=DEV),
           torch.randn(1024, 256, 4, 4, device=DEV), torch.randn(256, 64, 4, 4, device=DEV)]

@@ -66,11 +66,22 @@ if on("pack"):
         for _ in range(REPS):
             ops.pack_convt_weight(wt)
 if on("conv"):
-    for name, ndim, k, cin, cout, size in [("block3", 2, 4, 1024, 256, 16), ("block4", 2, 4, 256, 64, 32), ("block2", 3, 3, 128, 64, 8)]:
+    for name, ndim, k, cin, cout, size in [("block3", 2, 4, 1024, 256, 16), ("block4", 2, 4, 256, 64, 32), ("block2", 3, 3, 128, 64, 8),
+                                           ("proj", 2, 1, 1024, 1024, 16), ("block1", 3, 3, 512, 128, 4)]:
         x = torch.randn(B, *([size] * ndim), cin, device=DEV).to(bf).requires_grad_(True)
         w = (torch.randn(cin, cout, *([k] * ndim), device=DEV) * 0.02).requires_grad_(True)
         for _ in range(REPS):
             y = ops.convt(x, w, None, ndim, k)
             y.backward(torch.randn_like(y))
+if on("disc"):
+    from lightning_gan_zoo_b200.core.models.hologan_discriminator import Discriminator
+    d = Discriminator(3, 64, 128).to(DEV)
+    x = (torch.rand(B, 3, 64, 64, device=DEV) * 2 - 1).requires_grad_(True)
+    z = torch.rand(B, 128, device=DEV) * 2 - 1
+    for _ in range(REPS):
+        with torch.autocast("cuda", dtype=bf):
+            lg, zp = d(x)
+        loss, _ = ops.hologan_g_loss(lg, zp, z)
+        loss.backward()
 torch.cuda.synchronize()
 print("done")
