@@ -79,7 +79,12 @@ const char *hg_last_error(void);
  *                              TMEM accumulator stages (epilogue of tile i overlaps the main loop of tile i + 1).  Measured on
  *                              B200 (profiles/r02m_*): wins on the wide tiles (block3 dgrad 129 -> 106 us) but loses on the
  *                              narrow layers, where two co-resident one-tile CTAs issue MMAs from two threads; step 1.87 vs
- *                              1.81 ms, hence off */
+ *                              1.81 ms, hence off
+ *   TAPGEMM_MSUB         (0)   1: wide tap GEMMs (256-column tiles: block3, the projection, block4 dgrad) process two 128-row
+ *                              sub-tiles per CTA that share every weight tile of the K loop (a third less L2 traffic per
+ *                              FLOP).  Measured on B200 (profiles/r02q_*): block3 dgrad 138 -> 123 us, but the projection
+ *                              50 -> 63 us and block4 dgrad 49 -> 64 us (three 64 KB stages instead of four 48 KB ones,
+ *                              no second CTA per SM); step 1.91 vs 1.86 ms, hence off */
 int hg_set_option(const char *name, int value);
 int hg_get_option(const char *name, int *value);
 

@@ -76,7 +76,11 @@ struct TapGemmParams {
     // gridDim.x == total tiles.  nacc accumulator stages of acc_stride TMEM columns each: with two, the epilogue of
     // tile i overlaps the main loop of tile i + 1.
     int m_tiles, n_tiles;
-    int nacc, acc_stride;
+    int m_sub;                  // 128-row sub-tiles per CTA tile (1 or 2).  With 2, both share every B (weight) tile of the K
+                                // loop: 64 KB per 256 x 256 x 64 MMA block instead of 2 x 48 KB -- the wide GEMMs are bound by
+                                // the bytes they must keep in flight from L2, not by the tensor pipe (profiles/r02o_*)
+    int nacc, acc_stride;       // acc_stride covers all sub-tiles of one stage (m_sub * sub_stride)
+    int sub_stride;
     int stats_scratch;          // 1: the epilogue's statistics scratch sits behind the operand ring (persistent launches)
     int num_groups;
     uint8_t order[kMaxGroups];
@@ -132,7 +136,8 @@ __global__ void __launch_bounds__(kThreads, 1) tap_gemm_kernel(const __grid_cons
     uint8_t *tiles = align_1024(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int BN = p.BN;
-    const uint32_t a_bytes = kBM * 128, b_bytes = (uint32_t)BN * 128, stage_bytes = a_bytes + b_bytes;
+    const uint32_t a_bytes = kBM * 128, b_bytes = (uint32_t)BN * 128, stage_bytes = (uint32_t)p.m_sub * a_bytes + b_bytes;
+    const uint32_t b_off = (uint32_t)p.m_sub * a_bytes;            // stage layout: [A sub 0][A sub 1]?[B]
     const int tiles_mn = p.m_tiles * p.n_tiles, total_tiles = tiles_mn * p.num_groups;
     const uint32_t tmem_cols = tmem_cols_for(p.nacc * p.acc_stride);
 
@@ -166,11 +171,14 @@ __global__ void __launch_bounds__(kThreads, 1) tap_gemm_kernel(const __grid_cons
                 const int gi = t / tiles_mn, r = t - gi * tiles_mn, n_idx = r / p.m_tiles, m_idx = r - n_idx * p.m_tiles;
                 const Group grp = p.groups[p.order[gi]];
                 const int n0 = n_idx * BN;
-                long long pos = (long long)m_idx * kBM;
-                const int x0 = (int)(pos % p.X); pos /= p.X;
-                const int y0 = (int)(pos % p.Y); pos /= p.Y;
-                const int z0 = (int)(pos % p.Z);
-                const int b0 = (int)(pos / p.Z);
+                int x0[2], y0[2], z0[2], b0[2];
+                for (int sub = 0; sub < p.m_sub; ++sub) {   // a sub-tile past the end of the tensor lands out of range: zero fill
+                    long long pos = ((long long)m_idx * p.m_sub + sub) * kBM;
+                    x0[sub] = (int)(pos % p.X); pos /= p.X;
+                    y0[sub] = (int)(pos % p.Y); pos /= p.Y;
+                    z0[sub] = (int)(pos % p.Z);
+                    b0[sub] = (int)(pos / p.Z);
+                }
                 for (int tp = 0; tp < grp.tap_count; ++tp) {
                     const Tap tap = p.taps[grp.tap_begin + tp];
                     for (int kc = 0; kc < p.k_chunks; ++kc, ++it) {
@@ -179,9 +187,10 @@ __global__ void __launch_bounds__(kThreads, 1) tap_gemm_kernel(const __grid_cons
                         ptx::mbar_wait(&ctl.empty[s], ph ^ 1u);
                         uint8_t *a_dst = tiles + (size_t)s * stage_bytes;
                         ptx::mbar_arrive_expect_tx(&ctl.full[s], stage_bytes);
-                        ptx::tma_load_5d(a_dst, &p.tmA, &ctl.full[s], tap.a_c_off + kc * kBK, x0 + tap.sx, y0 + tap.sy,
-                                         z0 + tap.sz, b0);
-                        ptx::tma_load_2d(a_dst + a_bytes, &p.tmB, &ctl.full[s], kc * kBK, tap.b_row_off + n0);
+                        for (int sub = 0; sub < p.m_sub; ++sub)
+                            ptx::tma_load_5d(a_dst + sub * a_bytes, &p.tmA, &ctl.full[s], tap.a_c_off + kc * kBK, x0[sub] + tap.sx,
+                                             y0[sub] + tap.sy, z0[sub] + tap.sz, b0[sub]);
+                        ptx::tma_load_2d(a_dst + b_off, &p.tmB, &ctl.full[s], kc * kBK, tap.b_row_off + n0);
                     }
                 }
             }
@@ -208,12 +217,14 @@ __global__ void __launch_bounds__(kThreads, 1) tap_gemm_kernel(const __grid_cons
                         ptx::mbar_wait(&ctl.full[s], ph);
                         ptx::tc_fence_after();
                         const uint32_t a_addr = ptx::smem_u32(tiles + (size_t)s * stage_bytes);
-                        const uint64_t a_desc = ptx::smem_desc_sw128(a_addr, 16, 1024);
-                        const uint64_t b_desc = ptx::smem_desc_sw128(a_addr + a_bytes, 16, 1024);
+                        const uint64_t b_desc = ptx::smem_desc_sw128(a_addr + b_off, 16, 1024);
+                        for (int sub = 0; sub < p.m_sub; ++sub) {       // the sub-tiles share this stage's B tile
+                            const uint64_t a_desc = ptx::smem_desc_sw128(a_addr + sub * a_bytes, 16, 1024);
 #pragma unroll
-                        for (int k = 0; k < kBK / 16; ++k)  // +32 bytes (>>4 = 2) per 16-element K step inside the swizzle row
-                            ptx::umma_bf16(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc,
-                                           ((started >> acc) & 1u) != 0 || k != 0);
+                            for (int k = 0; k < kBK / 16; ++k)  // +32 bytes (>>4 = 2) per 16-element K step inside the swizzle row
+                                ptx::umma_bf16(d_tmem + (uint32_t)(sub * p.sub_stride), a_desc + (uint64_t)(k * 2),
+                                               b_desc + (uint64_t)(k * 2), idesc, ((started >> acc) & 1u) != 0 || k != 0);
+                        }
                         started |= 1u << acc;
                         ptx::umma_commit(&ctl.empty[s]);    // frees the smem slot when these MMAs retire
                     }
@@ -236,8 +247,10 @@ __global__ void __launch_bounds__(kThreads, 1) tap_gemm_kernel(const __grid_cons
             const uint32_t aph = (uint32_t)(i / p.nacc) & 1u;
             ptx::mbar_wait(&ctl.acc_full[acc_stage], aph);
             ptx::tc_fence_after();
-            const long long m = (long long)m_idx * kBM + row;
-            const uint32_t taddr = tmem_base + (uint32_t)(acc_stage * p.acc_stride) + ((uint32_t)(quad * 32) << 16);
+          for (int sub = 0; sub < p.m_sub; ++sub) {
+            const long long m128 = (long long)m_idx * p.m_sub + sub;        // index of this 128-row sub-tile
+            const long long m = m128 * kBM + row;
+            const uint32_t taddr = tmem_base + (uint32_t)(acc_stage * p.acc_stride + sub * p.sub_stride) + ((uint32_t)(quad * 32) << 16);
             __nv_bfloat16 *orow = static_cast<__nv_bfloat16 *>(p.out) + m * p.ld_out + grp.out_col_off + n0;
             float *prow = p.partial ? p.partial + (size_t)grp.part * p.partial_stride + m * p.ld_out + grp.out_col_off + n0 : nullptr;
             const float oscale = (p.out_scale && !prow) ? __ldg(p.out_scale) : 1.f;
@@ -284,7 +297,7 @@ __global__ void __launch_bounds__(kThreads, 1) tap_gemm_kernel(const __grid_cons
                     }
                     __syncwarp();
                     if (lane < ncol) {
-                        const long long grow = (long long)m_idx * 4 + quad;
+                        const long long grow = m128 * 4 + quad;
                         *reinterpret_cast<float2 *>(p.stats + (grow * p.ld_out + grp.out_col_off + n0 + c0 + lane) * 2) = make_float2(sum, sq);
                     }
                 }
@@ -307,6 +320,7 @@ __global__ void __launch_bounds__(kThreads, 1) tap_gemm_kernel(const __grid_cons
                     }
                 }
             }
+          }
             // this warp is done with the accumulator stage: hand it back to the MMA warp
             ptx::tc_fence_before();
             __syncwarp();
@@ -493,12 +507,14 @@ __host__ __device__ inline int brick_row_pitch(int taps) { return kBrickCo * bri
 // independent loads in flight per thread.
 // `divisor` (device pointer, may be null): every weight is divided by *divisor first -- the spectral norm sigma of the
 // discriminator's convolutions (W / sigma, core/models/hologan_discriminator.py:15), so no normalised fp32 copy exists.
-template <int T>
+// BCI = input channels per brick: 16 normally, 4 for small weights (more bricks than SMs; see wgrad_reduce_kernel).
+template <int T, int BCI>
 __global__ void __launch_bounds__(256) pack_weight_kernel(const float *__restrict__ w, __nv_bfloat16 *__restrict__ w_fwd,
                                                           __nv_bfloat16 *__restrict__ w_dgrad, int cin, int cout, int perm_c,
                                                           int perm_s, const float *__restrict__ divisor)
 {
     extern __shared__ float brick[];                    // [kBrickCi][kBrickCo][tpitch] (+1 pad per ci row)
+    constexpr int kBrickCi = BCI;
     constexpr int row_len = kBrickCo * T, tp = T | 1, pitch = kBrickCo * tp + 1, vec_per_row = row_len / 4;
     const int ci0 = blockIdx.x * kBrickCi, co0 = blockIdx.y * kBrickCo;
     const float div = divisor ? __ldg(divisor) : 1.f;
@@ -765,9 +781,18 @@ static bool want_dual(int stage_bytes, int iters_per_cta, int epi_cols)
 
 static int launch_tap_gemm(TapGemmParams &p, int m_tiles, int n_tiles, cudaStream_t st, const char *who)
 {
-    const int stage_bytes = kBM * 128 + p.BN * 128;
     int max_iters = 0;
     for (int g = 0; g < p.num_groups; ++g) max_iters = p.groups[g].tap_count * p.k_chunks > max_iters ? p.groups[g].tap_count * p.k_chunks : max_iters;
+    // two 128-row sub-tiles per CTA tile for the wide GEMMs (one 256-column accumulator each = all 512 TMEM columns), when
+    // that still leaves at least ~1.5 tiles per SM
+    p.m_sub = 1;
+    if (option(kOptTapGemmMsub) != 0 && p.BN == 256 && p.epi_cols == 256 && !p.partial &&
+        (long long)(m_tiles / 2) * n_tiles * p.num_groups >= (3ll * sm_count()) / 2) {
+        p.m_sub = 2;
+        m_tiles = (m_tiles + 1) / 2;
+    }
+    p.sub_stride = p.m_sub == 2 ? 256 : 0;
+    const int stage_bytes = p.m_sub * kBM * 128 + p.BN * 128;
     p.m_tiles = m_tiles; p.n_tiles = n_tiles;
     // longest K loops first (tiles of one group are equally long)
     for (int g = 0; g < p.num_groups; ++g) p.order[g] = (uint8_t)g;
@@ -783,16 +808,17 @@ static int launch_tap_gemm(TapGemmParams &p, int m_tiles, int n_tiles, cudaStrea
     if (persistent) {
         // one CTA per SM walks the tile list; two accumulator stages when they fit (<= 256 columns each): the epilogue of
         // a tile overlaps the main loop of the next, and prologue / TMEM allocation / tensor-map fetch happen once
-        p.nacc = p.epi_cols <= 256 ? 2 : 1;
-        p.acc_stride = p.epi_cols <= 256 ? (int)(p.epi_cols <= 32 ? 32 : p.epi_cols <= 64 ? 64 : p.epi_cols <= 128 ? 128 : 256) : 512;
+        p.nacc = (p.epi_cols <= 256 && p.m_sub == 1) ? 2 : 1;
+        p.acc_stride = p.m_sub == 2 ? 512
+                                    : p.epi_cols <= 256 ? (int)(p.epi_cols <= 32 ? 32 : p.epi_cols <= 64 ? 64 : p.epi_cols <= 128 ? 128 : 256) : 512;
         p.stats_scratch = p.stats ? 1 : 0;
         p.stages = pick_stages(stage_bytes, 1 << 20, kSmemBudget - scratch);
         smem = (size_t)p.stages * stage_bytes + 1024 + scratch;
         grid = (unsigned)sm_count();
     } else {
-        const bool dual = want_dual(stage_bytes, max_iters, p.epi_cols);
+        const bool dual = p.m_sub == 1 && want_dual(stage_bytes, max_iters, p.epi_cols);
         p.nacc = 1;
-        p.acc_stride = p.epi_cols;
+        p.acc_stride = p.m_sub == 2 ? 512 : p.epi_cols;
         p.stats_scratch = 0;
         p.stages = pick_stages(stage_bytes, max_iters, dual ? kDualSmemBudget : kSmemBudget);
         if (p.stats && (size_t)p.stages * stage_bytes < (size_t)scratch) p.stages = (scratch + stage_bytes - 1) / stage_bytes;
@@ -885,6 +911,20 @@ static int perm_ok(const char *who, int cin, int perm_c, int perm_s)
 static int pack_weight_impl(const float *w, void *w_fwd, void *w_dgrad, int cin, int cout, int taps, int perm_c, int perm_s,
                             const float *divisor, void *stream);
 
+template <int T, int BCI>
+static void launch_pack_t(const float *w, __nv_bfloat16 *wf, __nv_bfloat16 *wd, int cin, int cout, int perm_c, int perm_s,
+                          const float *divisor, cudaStream_t st)
+{
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(pack_weight_kernel<T, BCI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        attr_set = true;
+    }
+    dim3 grid((cin + BCI - 1) / BCI, cout / kBrickCo);
+    const size_t smem = (size_t)BCI * brick_row_pitch(T) * sizeof(float);
+    pack_weight_kernel<T, BCI><<<grid, 256, smem, st>>>(w, wf, wd, cin, cout, perm_c, perm_s, divisor);
+}
+
 extern "C" int hg_convt_pack_weight(const float *w, void *w_fwd, void *w_dgrad, int cin, int cout, int taps, int perm_c,
                                     int perm_s, void *stream)
 {
@@ -902,20 +942,19 @@ static int pack_weight_impl(const float *w, void *w_fwd, void *w_dgrad, int cin,
                "hg_convt_pack_weight: Cin must be even and Cout a multiple of %d (got %d, %d)", kBrickCo, cin, cout);
     HG_REQUIRE(taps == 1 || taps == 16 || taps == 25 || taps == 27, HG_ERR_UNSUPPORTED,
                "hg_convt_pack_weight: taps must be 1 (k1), 16 (2-D k4), 25 (2-D k5) or 27 (3-D k3), got %d", taps);
-    dim3 grid((cin + kBrickCi - 1) / kBrickCi, cout / kBrickCo);
-    const size_t smem = (size_t)kBrickCi * brick_row_pitch(taps) * sizeof(float);
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(pack_weight_kernel<27>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-        cudaFuncSetAttribute(pack_weight_kernel<25>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-        attr_set = true;
-    }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     __nv_bfloat16 *wf = static_cast<__nv_bfloat16 *>(w_fwd), *wd = static_cast<__nv_bfloat16 *>(w_dgrad);
-    if (taps == 1) pack_weight_kernel<1><<<grid, 256, smem, st>>>(w, wf, wd, cin, cout, perm_c, perm_s, divisor);
-    else if (taps == 16) pack_weight_kernel<16><<<grid, 256, smem, st>>>(w, wf, wd, cin, cout, perm_c, perm_s, divisor);
-    else if (taps == 25) pack_weight_kernel<25><<<grid, 256, smem, st>>>(w, wf, wd, cin, cout, perm_c, perm_s, divisor);
-    else pack_weight_kernel<27><<<grid, 256, smem, st>>>(w, wf, wd, cin, cout, perm_c, perm_s, divisor);
+    const bool small = (long long)((cin + 15) / 16) * (cout / kBrickCo) < 2ll * sm_count();
+#define HG_PACK(T)                                                                                           \
+    do {                                                                                                     \
+        if (small) launch_pack_t<T, 4>(w, wf, wd, cin, cout, perm_c, perm_s, divisor, st);                    \
+        else launch_pack_t<T, 16>(w, wf, wd, cin, cout, perm_c, perm_s, divisor, st);                         \
+    } while (0)
+    if (taps == 1) HG_PACK(1);
+    else if (taps == 16) HG_PACK(16);
+    else if (taps == 25) HG_PACK(25);
+    else HG_PACK(27);
+#undef HG_PACK
     return check_launch("hg_convt_pack_weight");
 }
 

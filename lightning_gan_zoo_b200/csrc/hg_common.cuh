@@ -43,6 +43,7 @@ enum Option {
     kOptRotateGatherBwd,        // 1: 32^3 rotate backward as a table-free per-voxel gather
     kOptAdainGemmStats,         // 1: generator AdaIN statistics from the tap-GEMM epilogue (read by the Python layer)
     kOptTapGemmPersistent,      // 1: tap GEMMs with more tiles than SMs run one persistent CTA per SM (0: one tile per CTA)
+    kOptTapGemmMsub,            // 1: wide tap GEMMs (256-column tiles) process two 128-row sub-tiles per CTA that share every B tile
     kOptCount
 };
 int option(Option o);
