@@ -246,6 +246,45 @@ def conv_roofline(peaks, device):
             "us_per_launch": ms * 1e3, "algorithmic_flops": flops}
 
 
+def conv_roofline_flop_weighted(peaks, device):
+    """All 15 dense contractions of one generator forward + backward at B = 64 (5 layers x forward / dgrad / wgrad on
+    hg::tap_gemm_kernel / hg::wgrad_gemm_kernel), each timed alone with CUDA events: total algorithmic FLOPs / total time.
+    The single best instance (`roofline`) must not be mistaken for the step: this is the FLOP-weighted figure."""
+    import ctypes
+    from lightning_gan_zoo_b200 import _lib, ops
+    B, P = 64, ops._ptr
+    layers = [("block1", 3, 3, 512, 128, 4), ("block2", 3, 3, 128, 64, 8), ("proj1x1", 2, 1, 1024, 1024, 16),
+              ("block3", 2, 4, 1024, 256, 16), ("block4", 2, 4, 256, 64, 32)]
+    tot_flops, tot_s, per = 0.0, 0.0, {}
+    for name, ndim, k, cin, cout, size in layers:
+        sp = (size,) * ndim
+        ncls = 1 if k == 1 else 2 ** ndim
+        flops = 2.0 * B * size ** ndim * cin * cout * k ** ndim
+        xs = [torch.randn(B, *sp, cin, device=device).to(torch.bfloat16) for _ in range(3)]
+        dys = [torch.randn(B, *sp, ncls, cout, device=device).to(torch.bfloat16) for _ in range(3)]
+        w = torch.randn(cin, cout, *((k,) * ndim), device=device) * 0.02
+        wf, wd = ops.pack_convt_weight(w)
+        y, dx, dw = torch.empty_like(dys[0]), torch.empty_like(xs[0]), torch.empty_like(w)
+        nws = _lib.load().hg_convt_wgrad_workspace_bytes(B, cin, cout, ndim, size, k)
+        ws = torch.empty(nws, dtype=torch.uint8, device=device)
+        st = ops._stream
+        passes = {
+            "fwd": lambda i: _lib.call("hg_convt_fwd", P(xs[i]), P(wf), P(None), P(y), B, cin, cout, ndim, size, k, ctypes.c_float(1.0), st()),
+            "dgrad": lambda i: _lib.call("hg_convt_dgrad", P(dys[i]), P(wd), P(dx), B, cin, cout, ndim, size, k, st()),
+            "wgrad": lambda i: _lib.call("hg_convt_wgrad", P(xs[i]), P(dys[i]), P(dw), P(ws), nws, B, cin, cout, ndim, size, k, 0, 0, 0, st()),
+        }
+        for tag, fn in passes.items():
+            sec = _event_time_ms(fn, 3, 20) * 1e-3
+            tot_flops += flops
+            tot_s += sec
+            per[f"{name}.{tag}"] = round(flops / sec / 1e12, 1)
+    achieved = tot_flops / tot_s / 1e12
+    return {"bound": "tensor", "kernel": "all 15 generator contractions (5 layers x fwd / dgrad / wgrad), FLOP-weighted, B=64, bf16",
+            "achieved": achieved, "peak": peaks["bf16_tflops"], "peak_source": peaks["source"] + " (burst)", "unit": "TFLOP/s",
+            "frac": achieved / peaks["bf16_tflops"], "traffic": None, "us_total": tot_s * 1e6, "algorithmic_flops": tot_flops,
+            "tflops_per_kernel": per}
+
+
 def rotate_roofline(peaks, device):
     """cfg 3 microbench ("voxel-rotate HBM GB/s" of the metric): (64, 64, 16^3) fp32 rotate-resample, forward and
     backward.  Algorithmic bytes per launch = read one volume + write one volume = 2*B*C*S^3*4 = 128 MiB
@@ -268,6 +307,27 @@ def rotate_roofline(peaks, device):
                     "peak_source": peaks["source"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
                     "traffic": _ncu_traffic(key), "us_per_launch": ms * 1e3, "algorithmic_bytes": bytes_alg}
     out["l2_policy"] = "8 rotating 64 MiB inputs (512 MiB) > 126 MB L2"
+    del vols
+    # cfg 3 at 32^3 (slab forward, table-free gather backward) and the bf16-pipeline kernel the training step runs
+    extra = []
+    s32 = 32
+    a32 = ops.view_to_affine(view, s32, s32).to(device)
+    v32 = [torch.randn(b, c, s32, s32, s32, device=device) for _ in range(3)]          # 3 x 512 MiB
+    extra.append(("fwd_32", "hg::rotate_fwd_slab32_kernel<float> (64,64,32^3) fp32", 2 * b * c * s32 ** 3 * 4,
+                  _event_time_ms(lambda i: ops.rotate_fwd_raw(v32[i], a32, ops.HG_BORDER_REFERENCE), 3, 10)))
+    extra.append(("bwd_32", "hg::rotate_bwd_gather_kernel<float> (64,64,32^3) fp32", 2 * b * c * s32 ** 3 * 4,
+                  _event_time_ms(lambda i: ops.rotate_bwd_raw(v32[i], a32, c, s32, ops.HG_BORDER_REFERENCE), 3, 10)))
+    del v32
+    vcl = [torch.randn(b, s, s, s, c, device=device).to(torch.bfloat16) for _ in range(nbuf)]
+    extra.append(("fwd_cl", "hg::rotate_cl_fwd_kernel NDHWC->PROJ (64,16^3,64) bf16 (the training step's)", 2 * b * c * s ** 3 * 2,
+                  _event_time_ms(lambda i: ops.rotate_fwd_raw(vcl[i], a, ops.HG_BORDER_ZERO, ops.HG_NDHWC, ops.HG_PROJ), nbuf, 40)))
+    extra.append(("bwd_cl", "hg::rotate_adjoint_table_kernel + hg::rotate_cl_bwd_ell_kernel (64,16^3,64) bf16", 2 * b * c * s ** 3 * 2,
+                  _event_time_ms(lambda i: ops.rotate_bwd_raw(vcl[i], a, c, s, ops.HG_BORDER_ZERO, ops.HG_NDHWC, ops.HG_PROJ), nbuf, 40)))
+    for tag, kern, nbytes, ms in extra:
+        achieved = nbytes / (ms * 1e-3) / 1e9
+        out[tag] = {"bound": "hbm", "kernel": kern, "achieved": achieved, "peak": peaks["hbm_gbs"], "peak_source": peaks["source"],
+                    "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": None, "us_per_launch": ms * 1e3,
+                    "algorithmic_bytes": nbytes}
     return out
 
 
@@ -489,6 +549,7 @@ def main():
         peaks = measured_peaks()
         if not args.no_roofline:
             line["roofline"] = conv_roofline(peaks, device)
+            line["roofline_flop_weighted"] = conv_roofline_flop_weighted(peaks, device)
             line["roofline_rotate"] = rotate_roofline(peaks, device)
         if world == 1 and not args.no_cpu_baseline:
             ips, ms, threads = cpu_training_steps(args.cpu_batch, S, steps=6, warmup=3)
