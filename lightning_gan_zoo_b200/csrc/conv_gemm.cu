@@ -129,15 +129,17 @@ __device__ __forceinline__ uint8_t *align_1024(uint8_t *p)
 // -------------------------------------------------------------------------------------------------
 // K-major kernel: forward and dgrad (and plain GEMMs).  grid = (m_tiles, n_tiles, groups)
 // -------------------------------------------------------------------------------------------------
+template <int MSUB>
 __global__ void __launch_bounds__(kThreads, 1) tap_gemm_kernel(const __grid_constant__ TapGemmParams p)
 {
     extern __shared__ uint8_t smem_raw[];
     __shared__ SharedCtl ctl;
+    __shared__ __align__(16) float bias_stage[4][512 + 16];        // one copy of the tile's bias columns per epilogue warp
     uint8_t *tiles = align_1024(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int BN = p.BN;
-    const uint32_t a_bytes = kBM * 128, b_bytes = (uint32_t)BN * 128, stage_bytes = (uint32_t)p.m_sub * a_bytes + b_bytes;
-    const uint32_t b_off = (uint32_t)p.m_sub * a_bytes;            // stage layout: [A sub 0][A sub 1]?[B]
+    const uint32_t a_bytes = kBM * 128, b_bytes = (uint32_t)BN * 128, stage_bytes = (uint32_t)MSUB * a_bytes + b_bytes;
+    const uint32_t b_off = (uint32_t)MSUB * a_bytes;               // stage layout: [A sub 0][A sub 1]?[B]
     const int tiles_mn = p.m_tiles * p.n_tiles, total_tiles = tiles_mn * p.num_groups;
     const uint32_t tmem_cols = tmem_cols_for(p.nacc * p.acc_stride);
 
@@ -162,18 +164,25 @@ __global__ void __launch_bounds__(kThreads, 1) tap_gemm_kernel(const __grid_cons
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = ctl.tmem_base;
+    // The producer and the MMA issuer are ONE thread each and the K loops are short: ring slot / phase are advanced
+    // incrementally (no division), barrier and tile addresses stay in the shared window, descriptors are derived from one
+    // base by adds (same-box A/B, profiles/r02v_tap_gemm_ab.txt: a few % on the narrow layers; the large term was the
+    // epilogue's per-element bias branches, see below).
+    const uint32_t tiles_a = ptx::smem_u32(tiles), full_a = ptx::smem_u32(&ctl.full[0]), empty_a = ptx::smem_u32(&ctl.empty[0]);
+    const uint32_t nstages = (uint32_t)p.stages;
 
     if (warp == 0) {
         if (ptx::elect_one()) {
             // ===== TMA producer: runs ahead of the MMA warp across tile boundaries =====
-            int it = 0;
+            uint32_t s = 0, ph = 1;                     // waits on empty[s] with the inverted phase: passes on a fresh barrier
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
                 const int gi = t / tiles_mn, r = t - gi * tiles_mn, n_idx = r / p.m_tiles, m_idx = r - n_idx * p.m_tiles;
                 const Group grp = p.groups[p.order[gi]];
                 const int n0 = n_idx * BN;
-                int x0[2], y0[2], z0[2], b0[2];
-                for (int sub = 0; sub < p.m_sub; ++sub) {   // a sub-tile past the end of the tensor lands out of range: zero fill
-                    long long pos = ((long long)m_idx * p.m_sub + sub) * kBM;
+                int x0[MSUB], y0[MSUB], z0[MSUB], b0[MSUB];
+#pragma unroll
+                for (int sub = 0; sub < MSUB; ++sub) {      // a sub-tile past the end of the tensor lands out of range: zero fill
+                    long long pos = ((long long)m_idx * MSUB + sub) * kBM;
                     x0[sub] = (int)(pos % p.X); pos /= p.X;
                     y0[sub] = (int)(pos % p.Y); pos /= p.Y;
                     z0[sub] = (int)(pos % p.Z);
@@ -181,16 +190,19 @@ __global__ void __launch_bounds__(kThreads, 1) tap_gemm_kernel(const __grid_cons
                 }
                 for (int tp = 0; tp < grp.tap_count; ++tp) {
                     const Tap tap = p.taps[grp.tap_begin + tp];
-                    for (int kc = 0; kc < p.k_chunks; ++kc, ++it) {
-                        const int s = it % p.stages;
-                        const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
-                        ptx::mbar_wait(&ctl.empty[s], ph ^ 1u);
-                        uint8_t *a_dst = tiles + (size_t)s * stage_bytes;
-                        ptx::mbar_arrive_expect_tx(&ctl.full[s], stage_bytes);
-                        for (int sub = 0; sub < p.m_sub; ++sub)
-                            ptx::tma_load_5d(a_dst + sub * a_bytes, &p.tmA, &ctl.full[s], tap.a_c_off + kc * kBK, x0[sub] + tap.sx,
-                                             y0[sub] + tap.sy, z0[sub] + tap.sz, b0[sub]);
-                        ptx::tma_load_2d(a_dst + b_off, &p.tmB, &ctl.full[s], kc * kBK, tap.b_row_off + n0);
+                    const int brow = tap.b_row_off + n0;
+                    int cx[MSUB], cy[MSUB], cz[MSUB];
+#pragma unroll
+                    for (int sub = 0; sub < MSUB; ++sub) { cx[sub] = x0[sub] + tap.sx; cy[sub] = y0[sub] + tap.sy; cz[sub] = z0[sub] + tap.sz; }
+                    for (int kc = 0, kcol = 0; kc < p.k_chunks; ++kc, kcol += kBK) {
+                        const uint32_t fb = full_a + 8u * s, dst = tiles_a + s * stage_bytes;
+                        ptx::mbar_wait_a(empty_a + 8u * s, ph);
+                        ptx::mbar_arrive_expect_tx_a(fb, stage_bytes);
+#pragma unroll
+                        for (int sub = 0; sub < MSUB; ++sub)
+                            ptx::tma_load_5d_a(dst + sub * a_bytes, &p.tmA, fb, tap.a_c_off + kcol, cx[sub], cy[sub], cz[sub], b0[sub]);
+                        ptx::tma_load_2d_a(dst + b_off, &p.tmB, fb, kcol, brow);
+                        if (++s == nstages) { s = 0; ph ^= 1u; }
                     }
                 }
             }
@@ -199,7 +211,12 @@ __global__ void __launch_bounds__(kThreads, 1) tap_gemm_kernel(const __grid_cons
         if (ptx::elect_one()) {
             // ===== MMA issuer =====
             const uint32_t idesc = ptx::idesc_bf16(kBM, BN, false, false);
-            int it = 0, i = 0;
+            // descriptor of a K-major 128B-swizzled tile at shared address 0; the address field (bits 0-13, 16-byte units)
+            // is added per stage -- shared addresses stay below 256 KB, so the add never carries out of the field
+            const uint64_t desc0 = ptx::smem_desc_sw128(0, 16, 1024);
+            const uint32_t stage_units = stage_bytes >> 4, b_units = b_off >> 4, a_units = a_bytes >> 4, tiles_units = tiles_a >> 4;
+            uint32_t s = 0, ph = 0;
+            int i = 0;
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++i) {
                 const int gi = t / tiles_mn;
                 const Group grp = p.groups[p.order[gi]];
@@ -211,22 +228,26 @@ __global__ void __launch_bounds__(kThreads, 1) tap_gemm_kernel(const __grid_cons
                 for (int tp = 0; tp < grp.tap_count; ++tp) {
                     const int acc = p.taps[grp.tap_begin + tp].acc;
                     const uint32_t d_tmem = tmem_base + (uint32_t)(acc_stage * p.acc_stride + acc * BN);
-                    for (int kc = 0; kc < p.k_chunks; ++kc, ++it) {
-                        const int s = it % p.stages;
-                        const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
-                        ptx::mbar_wait(&ctl.full[s], ph);
+                    uint32_t accumulate = (started >> acc) & 1u;
+                    started |= 1u << acc;
+                    for (int kc = 0; kc < p.k_chunks; ++kc) {
+                        ptx::mbar_wait_a(full_a + 8u * s, ph);
                         ptx::tc_fence_after();
-                        const uint32_t a_addr = ptx::smem_u32(tiles + (size_t)s * stage_bytes);
-                        const uint64_t b_desc = ptx::smem_desc_sw128(a_addr + b_off, 16, 1024);
-                        for (int sub = 0; sub < p.m_sub; ++sub) {       // the sub-tiles share this stage's B tile
-                            const uint64_t a_desc = ptx::smem_desc_sw128(a_addr + sub * a_bytes, 16, 1024);
+                        const uint64_t a_desc = desc0 + (uint64_t)(tiles_units + s * stage_units);
+                        const uint64_t b_desc = a_desc + b_units;
 #pragma unroll
-                            for (int k = 0; k < kBK / 16; ++k)  // +32 bytes (>>4 = 2) per 16-element K step inside the swizzle row
-                                ptx::umma_bf16(d_tmem + (uint32_t)(sub * p.sub_stride), a_desc + (uint64_t)(k * 2),
-                                               b_desc + (uint64_t)(k * 2), idesc, ((started >> acc) & 1u) != 0 || k != 0);
+                        for (int sub = 0; sub < MSUB; ++sub) {          // the sub-tiles share this stage's B tile
+                            const uint64_t as = a_desc + (uint64_t)(sub * a_units);
+                            const uint32_t d = d_tmem + (uint32_t)(sub * p.sub_stride);
+                            // +32 bytes (2 units) per 16-element K step inside the swizzle row
+                            ptx::umma_bf16(d, as, b_desc, idesc, accumulate != 0);
+                            ptx::umma_bf16(d, as + 2, b_desc + 2, idesc, true);
+                            ptx::umma_bf16(d, as + 4, b_desc + 4, idesc, true);
+                            ptx::umma_bf16(d, as + 6, b_desc + 6, idesc, true);
                         }
-                        started |= 1u << acc;
-                        ptx::umma_commit(&ctl.empty[s]);    // frees the smem slot when these MMAs retire
+                        accumulate = 1u;
+                        ptx::umma_commit_a(empty_a + 8u * s);   // frees the smem slot when these MMAs retire
+                        if (++s == nstages) { s = 0; ph ^= 1u; }
                     }
                 }
                 ptx::umma_commit(&ctl.acc_full[acc_stage]);
@@ -237,6 +258,7 @@ __global__ void __launch_bounds__(kThreads, 1) tap_gemm_kernel(const __grid_cons
         const int quad = warp & 3;                      // a warp may only touch TMEM lanes 32*(warp%4) .. +31
         const int row = quad * 32 + lane;
         // statistics scratch: behind the ring when tiles overlap (persistent), else the idle ring itself
+        float *bias_s = bias_stage[quad];               // per-warp copy: no cross-warp synchronisation
         float *scr = reinterpret_cast<float *>(p.stats_scratch ? tiles + (size_t)p.stages * stage_bytes : tiles) + quad * (32 * 33);
         int i = 0;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++i) {
@@ -245,10 +267,15 @@ __global__ void __launch_bounds__(kThreads, 1) tap_gemm_kernel(const __grid_cons
             const int n0 = n_idx * BN;
             const int acc_stage = i % p.nacc;
             const uint32_t aph = (uint32_t)(i / p.nacc) & 1u;
+            if (p.bias) {                               // this tile's bias columns, staged while the main loop runs
+                __syncwarp();
+                for (int c = lane; c < p.epi_cols; c += 32) bias_s[c] = __ldg(p.bias + (n0 + c) % p.bias_mod);
+                __syncwarp();
+            }
             ptx::mbar_wait(&ctl.acc_full[acc_stage], aph);
             ptx::tc_fence_after();
-          for (int sub = 0; sub < p.m_sub; ++sub) {
-            const long long m128 = (long long)m_idx * p.m_sub + sub;        // index of this 128-row sub-tile
+          for (int sub = 0; sub < MSUB; ++sub) {
+            const long long m128 = (long long)m_idx * MSUB + sub;           // index of this 128-row sub-tile
             const long long m = m128 * kBM + row;
             const uint32_t taddr = tmem_base + (uint32_t)(acc_stage * p.acc_stride + sub * p.sub_stride) + ((uint32_t)(quad * 32) << 16);
             __nv_bfloat16 *orow = static_cast<__nv_bfloat16 *>(p.out) + m * p.ld_out + grp.out_col_off + n0;
@@ -275,11 +302,21 @@ __global__ void __launch_bounds__(kThreads, 1) tap_gemm_kernel(const __grid_cons
                     continue;
                 }
                 const int ncol = min(32, p.epi_cols - c0);
-                const int bcol = (n0 + c0) % p.bias_mod;          // bias_mod is a multiple of 16 and of ncol's run
+                // ONE uniform branch per chunk: per-element tests (`if (bias && j < ncol)`) compile to 32 divergence
+                // regions and cost ~1.5 k cycles per chunk -- a quarter of a tile's life on the narrow layers
+                if (p.bias) {
+                    const float4 *b4 = reinterpret_cast<const float4 *>(bias_s + c0);      // broadcast reads
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    v[j] *= oscale;
-                    if (p.bias && j < ncol) v[j] += __ldg(p.bias + (bcol + j) % p.bias_mod);
+                    for (int j = 0; j < 8; ++j) {       // columns past a 16-wide tail pick up stale shared memory: never stored
+                        const float4 b = b4[j];
+                        v[4 * j] = fmaf(v[4 * j], oscale, b.x);
+                        v[4 * j + 1] = fmaf(v[4 * j + 1], oscale, b.y);
+                        v[4 * j + 2] = fmaf(v[4 * j + 2], oscale, b.z);
+                        v[4 * j + 3] = fmaf(v[4 * j + 3], oscale, b.w);
+                    }
+                } else if (p.out_scale) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] *= oscale;
                 }
                 if (p.stats) {
                     // column sums over this warp's 32 rows through a padded shared-memory transpose; rows past the end
@@ -827,10 +864,12 @@ static int launch_tap_gemm(TapGemmParams &p, int m_tiles, int n_tiles, cudaStrea
     }
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(tap_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget + 2048);
+        cudaFuncSetAttribute(tap_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget + 2048);
+        cudaFuncSetAttribute(tap_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget + 2048);
         attr_set = true;
     }
-    tap_gemm_kernel<<<grid, kThreads, smem, st>>>(p);
+    if (p.m_sub == 2) tap_gemm_kernel<2><<<grid, kThreads, smem, st>>>(p);
+    else tap_gemm_kernel<1><<<grid, kThreads, smem, st>>>(p);
     return check_launch(who);
 }
 
