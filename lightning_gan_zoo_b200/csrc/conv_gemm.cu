@@ -182,11 +182,11 @@ __global__ void __launch_bounds__(kThreads, 1) tap_gemm_kernel(const __grid_cons
                 int x0[MSUB], y0[MSUB], z0[MSUB], b0[MSUB];
 #pragma unroll
                 for (int sub = 0; sub < MSUB; ++sub) {      // a sub-tile past the end of the tensor lands out of range: zero fill
-                    long long pos = ((long long)m_idx * MSUB + sub) * kBM;
-                    x0[sub] = (int)(pos % p.X); pos /= p.X;
-                    y0[sub] = (int)(pos % p.Y); pos /= p.Y;
-                    z0[sub] = (int)(pos % p.Z);
-                    b0[sub] = (int)(pos / p.Z);
+                    uint32_t pos = ((uint32_t)m_idx * MSUB + sub) * kBM;        // 32-bit: m_total fits an int (64-bit divisions
+                    x0[sub] = (int)(pos % (uint32_t)p.X); pos /= (uint32_t)p.X;  // cost ~100 instructions each in this one thread)
+                    y0[sub] = (int)(pos % (uint32_t)p.Y); pos /= (uint32_t)p.Y;
+                    z0[sub] = (int)(pos % (uint32_t)p.Z);
+                    b0[sub] = (int)(pos / (uint32_t)p.Z);
                 }
                 for (int tp = 0; tp < grp.tap_count; ++tp) {
                     const Tap tap = p.taps[grp.tap_begin + tp];
@@ -453,44 +453,56 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_gemm_kernel(const __grid_co
         }
     }
     if (total_iters > 0) {
+        // one producer thread and one MMA thread: keep their per-iteration instruction streams short (no divisions --
+        // the position of the next 64-position tile is a mixed-radix increment -- shared-window addresses, descriptor adds)
+        const uint32_t tiles_a = ptx::smem_u32(tiles), full_a = ptx::smem_u32(&ctl.full[0]), empty_a = ptx::smem_u32(&ctl.empty[0]);
+        const uint32_t nstages = (uint32_t)p.stages;
         if (warp == 0) {
             if (ptx::elect_one()) {
+                const uint32_t X = (uint32_t)p.X, Y = (uint32_t)p.Y, Z = (uint32_t)p.Z;
+                uint32_t q = (uint32_t)t_begin * kPos;          // < B * X * Y * Z, which fits an int (m_total)
+                uint32_t x0 = q % X; q /= X;
+                uint32_t y0 = q % Y; q /= Y;
+                uint32_t z0 = q % Z;
+                uint32_t b0 = q / Z;
+                const uint32_t dx = kPos % X, c1 = kPos / X, dy = c1 % Y, c2 = c1 / Y, dz = c2 % Z, db = c2 / Z;
+                const int cA0 = ci0, cA1 = ci0 + 64, cB0 = pr.dy_c_off + co0, nb = BN / 64;
+                uint32_t s = 0, ph = 1;
                 for (int it = 0; it < total_iters; ++it) {
-                    long long pos = (long long)(t_begin + it) * kPos;
-                    const int x0 = (int)(pos % p.X); pos /= p.X;
-                    const int y0 = (int)(pos % p.Y); pos /= p.Y;
-                    const int z0 = (int)(pos % p.Z);
-                    const int b0 = (int)(pos / p.Z);
-                    const int s = it % p.stages;
-                    const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
-                    ptx::mbar_wait(&ctl.empty[s], ph ^ 1u);
-                    uint8_t *dst = tiles + (size_t)s * stage_bytes;
-                    ptx::mbar_arrive_expect_tx(&ctl.full[s], stage_bytes);
-                    for (int j = 0; j < 2; ++j)
-                        ptx::tma_load_5d(dst + j * box_bytes, &p.tmX, &ctl.full[s], ci0 + j * 64, x0 + pr.sx, y0 + pr.sy,
-                                         z0 + pr.sz, b0);
-                    for (int j = 0; j < BN / 64; ++j)
-                        ptx::tma_load_5d(dst + a_bytes + j * box_bytes, &p.tmDY, &ctl.full[s], pr.dy_c_off + co0 + j * 64, x0,
-                                         y0, z0, b0);
+                    const uint32_t fb = full_a + 8u * s, dst = tiles_a + s * stage_bytes;
+                    ptx::mbar_wait_a(empty_a + 8u * s, ph);
+                    ptx::mbar_arrive_expect_tx_a(fb, stage_bytes);
+                    const int xs = (int)x0 + pr.sx, ys = (int)y0 + pr.sy, zs = (int)z0 + pr.sz;
+                    ptx::tma_load_5d_a(dst, &p.tmX, fb, cA0, xs, ys, zs, (int)b0);
+                    ptx::tma_load_5d_a(dst + box_bytes, &p.tmX, fb, cA1, xs, ys, zs, (int)b0);
+                    for (int j = 0; j < nb; ++j)
+                        ptx::tma_load_5d_a(dst + a_bytes + j * box_bytes, &p.tmDY, fb, cB0 + j * 64, (int)x0, (int)y0, (int)z0, (int)b0);
+                    if (++s == nstages) { s = 0; ph ^= 1u; }
+                    x0 += dx; uint32_t carry = x0 >= X ? 1u : 0u; x0 -= carry ? X : 0u;
+                    y0 += dy + carry; carry = y0 >= Y ? 1u : 0u; y0 -= carry ? Y : 0u;
+                    z0 += dz + carry; carry = z0 >= Z ? 1u : 0u; z0 -= carry ? Z : 0u;
+                    b0 += db + carry;
                 }
             }
         } else if (warp == 1) {
             if (ptx::elect_one()) {
                 const uint32_t idesc = ptx::idesc_bf16(kBM, BN, true, true);
+                // MN-major: LBO = distance between 64-channel groups (one box), SBO = 8 positions
+                const uint64_t desc0 = ptx::smem_desc_sw128(0, box_bytes, 1024);
+                const uint32_t stage_units = stage_bytes >> 4, a_units = a_bytes >> 4, tiles_units = tiles_a >> 4;
+                uint32_t s = 0, ph = 0;
                 for (int it = 0; it < total_iters; ++it) {
-                    const int s = it % p.stages;
-                    const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
-                    ptx::mbar_wait(&ctl.full[s], ph);
+                    ptx::mbar_wait_a(full_a + 8u * s, ph);
                     ptx::tc_fence_after();
-                    const uint32_t a_addr = ptx::smem_u32(tiles + (size_t)s * stage_bytes);
-                    // MN-major: LBO = distance between 64-channel groups (one box), SBO = 8 positions
-                    const uint64_t a_desc = ptx::smem_desc_sw128(a_addr, box_bytes, 1024);
-                    const uint64_t b_desc = ptx::smem_desc_sw128(a_addr + a_bytes, box_bytes, 1024);
-#pragma unroll
-                    for (int k = 0; k < kPos / 16; ++k)   // 16 positions = 16 rows x 128 B = 2048 B (>>4 = 128)
-                        ptx::umma_bf16(tmem_base, a_desc + (uint64_t)(k * 128), b_desc + (uint64_t)(k * 128), idesc,
-                                       (it | k) != 0);
-                    ptx::umma_commit(&ctl.empty[s]);
+                    const uint64_t a_desc = desc0 + (uint64_t)(tiles_units + s * stage_units);
+                    const uint64_t b_desc = a_desc + a_units;
+                    // 16 positions = 16 rows x 128 B = 2048 B (>>4 = 128)
+                    ptx::umma_bf16(tmem_base, a_desc, b_desc, idesc, it != 0);
+                    ptx::umma_bf16(tmem_base, a_desc + 128, b_desc + 128, idesc, true);
+                    ptx::umma_bf16(tmem_base, a_desc + 256, b_desc + 256, idesc, true);
+                    ptx::umma_bf16(tmem_base, a_desc + 384, b_desc + 384, idesc, true);
+                    ptx::umma_commit_a(empty_a + 8u * s);
+                    if (++s == nstages) { s = 0; ph ^= 1u; }
                 }
                 ptx::umma_commit(&ctl.acc_ready);
             }
