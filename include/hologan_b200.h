@@ -84,7 +84,14 @@ const char *hg_last_error(void);
  *                              sub-tiles per CTA that share every weight tile of the K loop (a third less L2 traffic per
  *                              FLOP).  Measured on B200 (profiles/r02q_*): block3 dgrad 138 -> 123 us, but the projection
  *                              50 -> 63 us and block4 dgrad 49 -> 64 us (three 64 KB stages instead of four 48 KB ones,
- *                              no second CTA per SM); step 1.91 vs 1.86 ms, hence off */
+ *                              no second CTA per SM); step 1.91 vs 1.86 ms, hence off
+ *   TAPGEMM_SHARE_A      (2)   forward of the narrow layers (several parity classes per CTA): every shifted activation box is
+ *                              loaded ONCE per K chunk for all classes of the CTA that use it, their weight boxes (at most this
+ *                              many, <= 256 rows) are stacked behind each other and one MMA per run of adjacent classes adds
+ *                              into their accumulators -- 9 activation boxes instead of 16 (k4, 2-D), 8 instead of 27 (k3, 3-D).
+ *                              0: one activation box and one weight box per (class, tap).  B200, B=64 (profiles/r02x_*): block4
+ *                              54.9 -> 48.1 us with 2 boxes (50.8 with 4: 48 KB stages leave two per co-resident CTA), block2
+ *                              31.7 -> 28.6; the forward of these layers sits at the L2 -> SM throughput cap (~12-14 TB/s) */
 int hg_set_option(const char *name, int value);
 int hg_get_option(const char *name, int *value);
 

@@ -17,6 +17,8 @@
 #include <cuda.h>
 
 #include "hg_common.cuh"
+#include <algorithm>
+
 #include "sm100_ptx.cuh"
 
 namespace hg {
@@ -37,6 +39,23 @@ struct Tap {
     int16_t acc;          // which accumulator (TMEM column block of BN columns) this tap adds into
     int32_t a_c_off;      // channel offset added to the A box (selects the parity class in s2d tensors)
     int32_t b_row_off;    // first row of this tap's slice in the packed weight matrix
+};
+// Shift-major work item (forward of the narrow layers, several parity classes per CTA): all (class, tap) pairs of the
+// CTA's classes that read the SAME shifted A box.  The box is loaded once per K chunk, the weight boxes of the pairs are
+// stacked behind each other in the stage, and one MMA per run of TMEM-adjacent classes (N = run * Cout <= 256) adds into
+// their accumulators -- 9 A boxes instead of 16 (k4 2-D) or 8 instead of 27 (k3 3-D), and N up to 256 instead of Cout.
+constexpr int kItemBoxes = 4;
+struct Item {
+    int16_t sx, sy, sz;
+    uint8_t nb, nseg;                 // weight boxes (<= kItemBoxes, nb * BN <= 256 rows) and MMA segments
+    int32_t a_c_off;
+    int32_t b_row[kItemBoxes];        // first row of every box in the packed weight matrix
+    struct Seg {
+        uint16_t col;                 // first accumulator column
+        uint16_t b_units;             // offset of the segment's first weight row inside the stage's B region, 16-byte units
+        uint32_t idesc;               // instruction descriptor with N = run * BN
+        uint32_t first;               // 1: no earlier MMA of this tile wrote these columns (the first K step overwrites)
+    } seg[kItemBoxes];
 };
 struct Group {
     int32_t tap_begin, tap_count;
@@ -86,6 +105,8 @@ struct TapGemmParams {
     uint8_t order[kMaxGroups];
     Group groups[kMaxGroups];
     Tap taps[kMaxTaps];
+    int item_rows;              // > 0: the groups index `items` (tap_begin / tap_count count items); rows of the stage's B region
+    Item items[kMaxTaps];
 };
 
 struct WgradParams {
@@ -129,7 +150,7 @@ __device__ __forceinline__ uint8_t *align_1024(uint8_t *p)
 // -------------------------------------------------------------------------------------------------
 // K-major kernel: forward and dgrad (and plain GEMMs).  grid = (m_tiles, n_tiles, groups)
 // -------------------------------------------------------------------------------------------------
-template <int MSUB>
+template <int MSUB, bool ITEMS>
 __global__ void __launch_bounds__(kThreads, 1) tap_gemm_kernel(const __grid_constant__ TapGemmParams p)
 {
     extern __shared__ uint8_t smem_raw[];
@@ -138,7 +159,8 @@ __global__ void __launch_bounds__(kThreads, 1) tap_gemm_kernel(const __grid_cons
     uint8_t *tiles = align_1024(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int BN = p.BN;
-    const uint32_t a_bytes = kBM * 128, b_bytes = (uint32_t)BN * 128, stage_bytes = (uint32_t)MSUB * a_bytes + b_bytes;
+    const uint32_t a_bytes = kBM * 128, b_bytes = (uint32_t)BN * 128;
+    const uint32_t stage_bytes = ITEMS ? a_bytes + (uint32_t)p.item_rows * 128 : (uint32_t)MSUB * a_bytes + b_bytes;
     const uint32_t b_off = (uint32_t)MSUB * a_bytes;               // stage layout: [A sub 0][A sub 1]?[B]
     const int tiles_mn = p.m_tiles * p.n_tiles, total_tiles = tiles_mn * p.num_groups;
     const uint32_t tmem_cols = tmem_cols_for(p.nacc * p.acc_stride);
@@ -188,6 +210,25 @@ __global__ void __launch_bounds__(kThreads, 1) tap_gemm_kernel(const __grid_cons
                     z0[sub] = (int)(pos % (uint32_t)p.Z);
                     b0[sub] = (int)(pos / (uint32_t)p.Z);
                 }
+                if constexpr (ITEMS) {
+                    for (int ii = 0; ii < grp.tap_count; ++ii) {
+                        const Item &it = p.items[grp.tap_begin + ii];
+                        const int cx = x0[0] + it.sx, cy = y0[0] + it.sy, cz = z0[0] + it.sz, nb = it.nb;
+                        const uint32_t tx = a_bytes + (uint32_t)nb * b_bytes;
+                        const int r0 = it.b_row[0] + n0, r1 = it.b_row[1] + n0, r2 = it.b_row[2] + n0, r3 = it.b_row[3] + n0;
+                        for (int kc = 0, kcol = 0; kc < p.k_chunks; ++kc, kcol += kBK) {
+                            const uint32_t fb = full_a + 8u * s, dst = tiles_a + s * stage_bytes;
+                            ptx::mbar_wait_a(empty_a + 8u * s, ph);
+                            ptx::mbar_arrive_expect_tx_a(fb, tx);
+                            ptx::tma_load_5d_a(dst, &p.tmA, fb, it.a_c_off + kcol, cx, cy, cz, b0[0]);
+                            ptx::tma_load_2d_a(dst + a_bytes, &p.tmB, fb, kcol, r0);
+                            if (nb > 1) ptx::tma_load_2d_a(dst + a_bytes + b_bytes, &p.tmB, fb, kcol, r1);
+                            if (nb > 2) ptx::tma_load_2d_a(dst + a_bytes + 2 * b_bytes, &p.tmB, fb, kcol, r2);
+                            if (nb > 3) ptx::tma_load_2d_a(dst + a_bytes + 3 * b_bytes, &p.tmB, fb, kcol, r3);
+                            if (++s == nstages) { s = 0; ph ^= 1u; }
+                        }
+                    }
+                } else
                 for (int tp = 0; tp < grp.tap_count; ++tp) {
                     const Tap tap = p.taps[grp.tap_begin + tp];
                     const int brow = tap.b_row_off + n0;
@@ -224,6 +265,33 @@ __global__ void __launch_bounds__(kThreads, 1) tap_gemm_kernel(const __grid_cons
                 const uint32_t aph = (uint32_t)(i / p.nacc) & 1u;
                 ptx::mbar_wait(&ctl.acc_empty[acc_stage], aph ^ 1u);       // the epilogue has drained this stage
                 ptx::tc_fence_after();
+                if constexpr (ITEMS) {
+                    const uint32_t acc0 = tmem_base + (uint32_t)(acc_stage * p.acc_stride);
+                    for (int ii = 0; ii < grp.tap_count; ++ii) {
+                        const Item &it = p.items[grp.tap_begin + ii];
+                        const int nseg = it.nseg;
+                        for (int kc = 0; kc < p.k_chunks; ++kc) {
+                            ptx::mbar_wait_a(full_a + 8u * s, ph);
+                            ptx::tc_fence_after();
+                            const uint64_t a_desc = desc0 + (uint64_t)(tiles_units + s * stage_units);
+                            const uint64_t b_base = a_desc + a_units;
+#pragma unroll
+                            for (int sg = 0; sg < kItemBoxes; ++sg) {
+                                if (sg < nseg) {
+                                    const Item::Seg seg = it.seg[sg];
+                                    const uint32_t d = acc0 + seg.col;
+                                    const uint64_t b_desc = b_base + seg.b_units;
+                                    ptx::umma_bf16(d, a_desc, b_desc, seg.idesc, (seg.first == 0u) || kc != 0);
+                                    ptx::umma_bf16(d, a_desc + 2, b_desc + 2, seg.idesc, true);
+                                    ptx::umma_bf16(d, a_desc + 4, b_desc + 4, seg.idesc, true);
+                                    ptx::umma_bf16(d, a_desc + 6, b_desc + 6, seg.idesc, true);
+                                }
+                            }
+                            ptx::umma_commit_a(empty_a + 8u * s);
+                            if (++s == nstages) { s = 0; ph ^= 1u; }
+                        }
+                    }
+                } else {
                 uint32_t started = 0;                       // accumulators that already hold a partial sum
                 for (int tp = 0; tp < grp.tap_count; ++tp) {
                     const int acc = p.taps[grp.tap_begin + tp].acc;
@@ -249,6 +317,7 @@ __global__ void __launch_bounds__(kThreads, 1) tap_gemm_kernel(const __grid_cons
                         ptx::umma_commit_a(empty_a + 8u * s);   // frees the smem slot when these MMAs retire
                         if (++s == nstages) { s = 0; ph ^= 1u; }
                     }
+                }
                 }
                 ptx::umma_commit(&ctl.acc_full[acc_stage]);
             }
@@ -828,6 +897,69 @@ static bool want_dual(int stage_bytes, int iters_per_cta, int epi_cols)
     return (long long)stage_bytes * iters_per_cta <= kDualMaxBytes;
 }
 
+// Regroup the (class, tap) list of every group into shift-major items (struct Item).  Taps of one group: `acc` is the class
+// index inside the group, accumulator columns acc * BN.  The zero-shift bucket goes first: every class has a tap with
+// shift 0 (both the k3 and the k4 stride-2 tables), so its MMAs initialise all accumulators and everything after
+// accumulates.  Kept general anyway: a segment never mixes fresh and started accumulators.
+static void build_shift_items(TapGemmParams &p, int cpc)
+{
+    const int max_boxes = std::min(std::min(kItemBoxes, option(kOptTapGemmShareA)), 256 / p.BN);
+    if (max_boxes < 2) return;
+    int nitems = 0, item_rows = 0;
+    Item items[kMaxTaps];
+    Group groups[kMaxGroups];
+    for (int g = 0; g < p.num_groups; ++g) {
+        const Group &grp = p.groups[g];
+        groups[g] = grp;
+        groups[g].tap_begin = nitems;
+        bool used[kMaxTaps] = {};
+        uint32_t started = 0;
+        for (int pass = 0; pass < 2; ++pass)                    // pass 0: the zero shift; pass 1: the rest in tap order
+            for (int t0 = 0; t0 < grp.tap_count; ++t0) {
+                const Tap &lead = p.taps[grp.tap_begin + t0];
+                if (used[t0] || (pass == 0 && (lead.sx | lead.sy | lead.sz) != 0)) continue;
+                // bucket: all taps of the group with lead's shift, by class
+                int idx[kMaxTaps], n = 0;
+                for (int t = t0; t < grp.tap_count; ++t) {
+                    const Tap &tp = p.taps[grp.tap_begin + t];
+                    if (!used[t] && tp.sx == lead.sx && tp.sy == lead.sy && tp.sz == lead.sz && tp.a_c_off == lead.a_c_off) {
+                        used[t] = true;
+                        idx[n++] = t;
+                    }
+                }
+                std::sort(idx, idx + n, [&](int a, int b) { return p.taps[grp.tap_begin + a].acc < p.taps[grp.tap_begin + b].acc; });
+                for (int b0 = 0; b0 < n; b0 += max_boxes) {
+                    Item it{};
+                    it.sx = lead.sx; it.sy = lead.sy; it.sz = lead.sz; it.a_c_off = lead.a_c_off;
+                    it.nb = (uint8_t)std::min(max_boxes, n - b0);
+                    for (int j = 0; j < kItemBoxes; ++j) it.b_row[j] = p.taps[grp.tap_begin + idx[b0 + std::min<int>(j, it.nb - 1)]].b_row_off;
+                    int j = 0;
+                    while (j < it.nb) {                          // maximal runs of adjacent classes with one started state
+                        const int acc0 = p.taps[grp.tap_begin + idx[b0 + j]].acc;
+                        const uint32_t st0 = (started >> acc0) & 1u;
+                        int run = 1;
+                        while (j + run < it.nb && p.taps[grp.tap_begin + idx[b0 + j + run]].acc == acc0 + run &&
+                               ((started >> (acc0 + run)) & 1u) == st0)
+                            ++run;
+                        Item::Seg &sg = it.seg[it.nseg++];
+                        sg.col = (uint16_t)(acc0 * p.BN);
+                        sg.b_units = (uint16_t)((j * p.BN * 128) >> 4);
+                        sg.idesc = ptx::idesc_bf16(kBM, run * p.BN, false, false);
+                        sg.first = st0 ? 0u : 1u;
+                        for (int r = 0; r < run; ++r) started |= 1u << (acc0 + r);
+                        j += run;
+                    }
+                    item_rows = std::max(item_rows, it.nb * p.BN);
+                    items[nitems++] = it;
+                }
+            }
+        groups[g].tap_count = nitems - groups[g].tap_begin;
+    }
+    for (int g = 0; g < p.num_groups; ++g) p.groups[g] = groups[g];
+    for (int i = 0; i < nitems; ++i) p.items[i] = items[i];
+    p.item_rows = item_rows;
+}
+
 static int launch_tap_gemm(TapGemmParams &p, int m_tiles, int n_tiles, cudaStream_t st, const char *who)
 {
     int max_iters = 0;
@@ -835,13 +967,13 @@ static int launch_tap_gemm(TapGemmParams &p, int m_tiles, int n_tiles, cudaStrea
     // two 128-row sub-tiles per CTA tile for the wide GEMMs (one 256-column accumulator each = all 512 TMEM columns), when
     // that still leaves at least ~1.5 tiles per SM
     p.m_sub = 1;
-    if (option(kOptTapGemmMsub) != 0 && p.BN == 256 && p.epi_cols == 256 && !p.partial &&
+    if (option(kOptTapGemmMsub) != 0 && p.item_rows == 0 && p.BN == 256 && p.epi_cols == 256 && !p.partial &&
         (long long)(m_tiles / 2) * n_tiles * p.num_groups >= (3ll * sm_count()) / 2) {
         p.m_sub = 2;
         m_tiles = (m_tiles + 1) / 2;
     }
     p.sub_stride = p.m_sub == 2 ? 256 : 0;
-    const int stage_bytes = p.m_sub * kBM * 128 + p.BN * 128;
+    const int stage_bytes = p.item_rows > 0 ? kBM * 128 + p.item_rows * 128 : p.m_sub * kBM * 128 + p.BN * 128;
     p.m_tiles = m_tiles; p.n_tiles = n_tiles;
     // longest K loops first (tiles of one group are equally long)
     for (int g = 0; g < p.num_groups; ++g) p.order[g] = (uint8_t)g;
@@ -876,12 +1008,14 @@ static int launch_tap_gemm(TapGemmParams &p, int m_tiles, int n_tiles, cudaStrea
     }
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(tap_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget + 2048);
-        cudaFuncSetAttribute(tap_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget + 2048);
+        cudaFuncSetAttribute(tap_gemm_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget + 2048);
+        cudaFuncSetAttribute(tap_gemm_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget + 2048);
+        cudaFuncSetAttribute(tap_gemm_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget + 2048);
         attr_set = true;
     }
-    if (p.m_sub == 2) tap_gemm_kernel<2><<<grid, kThreads, smem, st>>>(p);
-    else tap_gemm_kernel<1><<<grid, kThreads, smem, st>>>(p);
+    if (p.item_rows > 0) tap_gemm_kernel<1, true><<<grid, kThreads, smem, st>>>(p);
+    else if (p.m_sub == 2) tap_gemm_kernel<2, false><<<grid, kThreads, smem, st>>>(p);
+    else tap_gemm_kernel<1, false><<<grid, kThreads, smem, st>>>(p);
     return check_launch(who);
 }
 
@@ -1106,6 +1240,7 @@ static int convt_fwd_impl(const void *x, const void *w_fwd, const float *bias, c
         p.groups[g].tap_count++;
         ntap++;
     });
+    if (cpc > 1 && option(kOptTapGemmShareA) != 0) build_shift_items(p, cpc);
     return launch_tap_gemm(p, m_tiles, cout / bn, static_cast<cudaStream_t>(stream), "hg_convt_fwd");
 }
 

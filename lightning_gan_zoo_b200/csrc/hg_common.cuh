@@ -44,6 +44,7 @@ enum Option {
     kOptAdainGemmStats,         // 1: generator AdaIN statistics from the tap-GEMM epilogue (read by the Python layer)
     kOptTapGemmPersistent,      // 1: tap GEMMs with more tiles than SMs run one persistent CTA per SM (0: one tile per CTA)
     kOptTapGemmMsub,            // 1: wide tap GEMMs (256-column tiles) process two 128-row sub-tiles per CTA that share every B tile
+    kOptTapGemmShareA,          // > 0: forward of the narrow layers loads every shifted A box once for all parity classes of a CTA (value = weight boxes per item)
     kOptCount
 };
 int option(Option o);

@@ -142,6 +142,28 @@ def test_convt_fwd_dgrad_wgrad(ndim, kernel, batch, cin, cout, size):
         assert rel_err(dw, wr.grad) < 1e-4        # fp32 accumulation of exact bf16 products
 
 
+@pytest.mark.parametrize("ndim,kernel,batch,cin,cout,size", [
+    (2, 4, 64, 256, 64, 32), (3, 3, 64, 128, 64, 8), (3, 3, 64, 512, 128, 4), (3, 3, 3, 512, 128, 4), (2, 4, 4, 128, 32, 16),
+    (3, 3, 2, 64, 32, 8), (2, 5, 4, 128, 64, 16), (2, 4, 2, 64, 96, 16)])
+@pytest.mark.parametrize("boxes", [0, 2, 4])
+def test_convt_fwd_shift_major_items(hg_option, boxes, ndim, kernel, batch, cin, cout, size):
+    """Option TAPGEMM_SHARE_A: the forward of the narrow layers with every shifted activation box loaded once for all
+    parity classes of a CTA (stacked weight boxes, one MMA per run of adjacent classes) against torch, for 0 (per-tap
+    boxes), 2 and 4 weight boxes per item."""
+    hg_option("TAPGEMM_SHARE_A", boxes)
+    g = torch.Generator(device="cpu").manual_seed(cin + 3 * cout + boxes)
+    sp = (size,) * ndim
+    x = bf(torch.randn(batch, cin, *sp, generator=g)).to(DEV)
+    w = bf(torch.randn(cin, cout, *((kernel,) * ndim), generator=g) * 0.05).to(DEV)
+    bias = torch.randn(cout, generator=g).to(DEV)
+    wf, _ = pack(w.float(), kernel ** ndim)
+    y_s2d = torch.empty((batch,) + sp + (2 ** ndim, cout), dtype=torch.bfloat16, device=DEV)
+    _lib.call("hg_convt_fwd", P(to_channels_last(x)), P(wf), P(bias), P(y_s2d), batch, cin, cout, ndim, size, kernel,
+              ctypes.c_float(0.2), ops._stream())
+    ref = F.leaky_relu(torch_convt(x.float(), w.float(), bias, ndim, kernel), 0.2)
+    assert rel_err(nc_from_s2d(y_s2d, ndim).float(), ref) < 2 ** -7
+
+
 def test_fwd_relu_epilogue_and_errors():
     x = bf(torch.randn(2, 16, 16, 64)).to(DEV)
     w = torch.randn(64, 32, 1, 1, device=DEV) * 0.1
