@@ -42,20 +42,21 @@ __device__ __forceinline__ void split_bf16(float v, __nv_bfloat16 &hi, __nv_bflo
 
 
 // Stage the (TH+2) x (TW+2) halo tile of x (NHWC bf16, C = 64) as [pixel][C] with kFmXPitch bytes per pixel; pixels
-// outside the image and the pad rows up to kFmHaloPad are zero.
-__device__ __forceinline__ void fm_stage_x_halo(unsigned char *xs, const __nv_bfloat16 *__restrict__ xb, int S, int x0, int y0)
+// outside the image and the pad rows up to kFmHaloPad are zero.  Asynchronous copies (one commit group): all 11 copies of
+// a thread are in flight together; the caller waits (cp_async_wait_group) and synchronises the CTA before reading.
+__device__ __forceinline__ void fm_stage_x_halo_async(unsigned char *xs, const __nv_bfloat16 *__restrict__ xb, int S, int x0, int y0)
 {
     constexpr int L = kFmC / 8;
-    for (int i = threadIdx.x; i < kFmHaloPad * L; i += kFmThreads) {
+#pragma unroll
+    for (int i0 = 0; i0 < kFmHaloPad * L; i0 += kFmThreads) {
+        const int i = i0 + threadIdx.x;
         const int v = i % L, pix = i / L;
-        uint4 val = make_uint4(0, 0, 0, 0);
-        if (pix < kFmHaloPix) {
-            const int gx = pix % (kFmTW + 2), gy = pix / (kFmTW + 2);
-            const int yy = y0 + gy - 1, xx = x0 + gx - 1;
-            if (yy >= 0 && yy < S && xx >= 0 && xx < S) val = __ldg(reinterpret_cast<const uint4 *>(xb + ((size_t)yy * S + xx) * kFmC) + v);
-        }
-        *reinterpret_cast<uint4 *>(xs + (size_t)pix * kFmXPitch + v * 16) = val;
+        const int gx = pix % (kFmTW + 2), gy = pix / (kFmTW + 2);
+        const int yy = y0 + gy - 1, xx = x0 + gx - 1;
+        const bool ok = pix < kFmHaloPix && yy >= 0 && yy < S && xx >= 0 && xx < S;
+        cp_async_16_zfill(xs + (size_t)pix * kFmXPitch + v * 16, ok ? xb + ((size_t)yy * S + xx) * kFmC + v * 8 : xb, ok);
     }
+    cp_async_commit();
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -80,21 +81,29 @@ __global__ void __launch_bounds__(kFmThreads, 2) final_conv_tanh_fwd_mma_kernel(
     const int b = blockIdx.y, tile_x = blockIdx.x % tiles_x, tile_y = blockIdx.x / tiles_x;
     const int x0 = tile_x * kFmTW, y0 = tile_y * kFmTH;
 
-    // weights: torch (co, ci, tap) fp32 -> rows n = tap * 3 + co of bf16 hi / mid / lo, rows 27..31 zero
-    for (int i = threadIdx.x; i < kFmN * kFmC; i += kFmThreads) {
-        const int ci = i % kFmC, n = i / kFmC;
-        __nv_bfloat16 hi = __float2bfloat16_rn(0.f), mid = hi, lo = hi;
-        if (n < 9 * kFmCout) {
+    fm_stage_x_halo_async(xs, x + (size_t)b * S * S * kFmC, S, x0, y0);      // in flight while the weights are prepared
+    // weights: torch (co, ci, tap) fp32 -> rows n = tap * 3 + co of bf16 hi / mid / lo, rows 27..31 zero.  All 8 loads of a
+    // thread are issued before the first is used.
+    {
+        float wv[kFmN * kFmC / kFmThreads];
+#pragma unroll
+        for (int k = 0; k < kFmN * kFmC / kFmThreads; ++k) {
+            const int i = threadIdx.x + k * kFmThreads, ci = i % kFmC, n = i / kFmC;
             const int tap = n / kFmCout, co = n - tap * kFmCout;
-            const float v = __ldg(w + ((size_t)co * kFmC + ci) * 9 + tap);
-            split_bf16(v, hi, mid);
-            lo = __float2bfloat16_rn((v - __bfloat162float(hi)) - __bfloat162float(mid));
+            wv[k] = n < 9 * kFmCout ? __ldg(w + ((size_t)co * kFmC + ci) * 9 + tap) : 0.f;
         }
-        *reinterpret_cast<__nv_bfloat16 *>(wh + (size_t)n * kFmXPitch + ci * 2) = hi;
-        *reinterpret_cast<__nv_bfloat16 *>(wm + (size_t)n * kFmXPitch + ci * 2) = mid;
-        *reinterpret_cast<__nv_bfloat16 *>(wl + (size_t)n * kFmXPitch + ci * 2) = lo;
+#pragma unroll
+        for (int k = 0; k < kFmN * kFmC / kFmThreads; ++k) {
+            const int i = threadIdx.x + k * kFmThreads, ci = i % kFmC, n = i / kFmC;
+            __nv_bfloat16 hi, mid;
+            split_bf16(wv[k], hi, mid);
+            const __nv_bfloat16 lo = __float2bfloat16_rn((wv[k] - __bfloat162float(hi)) - __bfloat162float(mid));
+            *reinterpret_cast<__nv_bfloat16 *>(wh + (size_t)n * kFmXPitch + ci * 2) = hi;
+            *reinterpret_cast<__nv_bfloat16 *>(wm + (size_t)n * kFmXPitch + ci * 2) = mid;
+            *reinterpret_cast<__nv_bfloat16 *>(wl + (size_t)n * kFmXPitch + ci * 2) = lo;
+        }
     }
-    fm_stage_x_halo(xs, x + (size_t)b * S * S * kFmC, S, x0, y0);
+    cp_async_wait_group<0>();
     __syncthreads();
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, q = lane & 3;
@@ -159,21 +168,43 @@ __global__ void __launch_bounds__(kFmThreads, 2) final_conv_tanh_fwd_mma_kernel(
 // -------------------------------------------------------------------------------------------------
 // g = dout * (1 - out^2) of a tile with a one-pixel halo (zero outside the image): gs[co][(TH+2)][(TW+2)] fp32
 // -------------------------------------------------------------------------------------------------
+constexpr int kFmGsN = kFmCout * (kFmTH + 2) * (kFmTW + 2);               // 1020 values
+constexpr int kFmGsPer = (kFmGsN + kFmThreads - 1) / kFmThreads;         // 4 per thread
+struct FmGRegs { float v[kFmGsPer]; };
+// loads of a tile's g into registers: all 8 (out, dout) loads of a thread are issued together; fm_store_g writes them to
+// shared memory later (the dw kernel fetches the next tile's g while it computes on the current one)
+__device__ __forceinline__ void fm_load_g(FmGRegs &r, const float *__restrict__ out, const float *__restrict__ dout, int b, int S, int x0,
+                                          int y0)
+{
+    constexpr int gw = kFmTW + 2, gh = kFmTH + 2;
+    float o[kFmGsPer], d[kFmGsPer];
+#pragma unroll
+    for (int k = 0; k < kFmGsPer; ++k) {
+        const int i = threadIdx.x + k * kFmThreads;
+        const int gx = i % gw, gy = (i / gw) % gh, co = i / (gw * gh);
+        const int yy = y0 + gy - 1, xx = x0 + gx - 1;
+        const bool ok = i < kFmGsN && yy >= 0 && yy < S && xx >= 0 && xx < S;
+        const size_t idx = ok ? (((size_t)b * kFmCout + co) * S + yy) * S + xx : 0;
+        o[k] = ok ? __ldg(out + idx) : 0.f;
+        d[k] = ok ? __ldg(dout + idx) : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < kFmGsPer; ++k) r.v[k] = d[k] * (1.f - o[k] * o[k]);
+}
+__device__ __forceinline__ void fm_store_g(float *gs, const FmGRegs &r)
+{
+#pragma unroll
+    for (int k = 0; k < kFmGsPer; ++k) {
+        const int i = threadIdx.x + k * kFmThreads;
+        if (i < kFmGsN) gs[i] = r.v[k];
+    }
+}
 __device__ __forceinline__ void fm_stage_g(float *gs, const float *__restrict__ out, const float *__restrict__ dout, int b, int S,
                                            int x0, int y0)
 {
-    constexpr int gw = kFmTW + 2, gh = kFmTH + 2;
-    for (int i = threadIdx.x; i < kFmCout * gh * gw; i += kFmThreads) {
-        const int gx = i % gw, gy = (i / gw) % gh, co = i / (gw * gh);
-        const int yy = y0 + gy - 1, xx = x0 + gx - 1;
-        float v = 0.f;
-        if (yy >= 0 && yy < S && xx >= 0 && xx < S) {
-            const size_t k = (((size_t)b * kFmCout + co) * S + yy) * S + xx;
-            const float o = __ldg(out + k);
-            v = __ldg(dout + k) * (1.f - o * o);
-        }
-        gs[i] = v;
-    }
+    FmGRegs r;
+    fm_load_g(r, out, dout, b, S, x0, y0);
+    fm_store_g(gs, r);
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -200,18 +231,28 @@ __global__ void __launch_bounds__(kFmThreads, 2) final_conv_tanh_bwd_x_mma_kerne
     const int x0 = tile_x * kFmTW, y0 = tile_y * kFmTH;
     constexpr int gw = kFmTW + 2, gh = kFmTH + 2;
 
+    // g and the weights: every global load of the thread is issued before the first result is used
+    FmGRegs greg;
+    fm_load_g(greg, out, dout, b, S, x0, y0);
     // B operand: rows n = ci, K index k = tap * 3 + co (27 -> 32, zero padded), hi / lo
-    for (int i = threadIdx.x; i < kFmC * kFmN; i += kFmThreads) {
-        const int k = i % kFmN, ci = i / kFmN;
-        __nv_bfloat16 hi = __float2bfloat16_rn(0.f), lo = hi;
-        if (k < 9 * kFmCout) {
+    {
+        float wv[kFmC * kFmN / kFmThreads];
+#pragma unroll
+        for (int j = 0; j < kFmC * kFmN / kFmThreads; ++j) {
+            const int i = threadIdx.x + j * kFmThreads, k = i % kFmN, ci = i / kFmN;
             const int tap = k / kFmCout, co = k - tap * kFmCout;
-            split_bf16(__ldg(w + ((size_t)co * kFmC + ci) * 9 + tap), hi, lo);
+            wv[j] = k < 9 * kFmCout ? __ldg(w + ((size_t)co * kFmC + ci) * 9 + tap) : 0.f;
         }
-        *reinterpret_cast<__nv_bfloat16 *>(wh + (size_t)ci * kFmGPitch + k * 2) = hi;
-        *reinterpret_cast<__nv_bfloat16 *>(wl + (size_t)ci * kFmGPitch + k * 2) = lo;
+#pragma unroll
+        for (int j = 0; j < kFmC * kFmN / kFmThreads; ++j) {
+            const int i = threadIdx.x + j * kFmThreads, k = i % kFmN, ci = i / kFmN;
+            __nv_bfloat16 hi, lo;
+            split_bf16(wv[j], hi, lo);
+            *reinterpret_cast<__nv_bfloat16 *>(wh + (size_t)ci * kFmGPitch + k * 2) = hi;
+            *reinterpret_cast<__nv_bfloat16 *>(wl + (size_t)ci * kFmGPitch + k * 2) = lo;
+        }
     }
-    fm_stage_g(gs, out, dout, b, S, x0, y0);
+    fm_store_g(gs, greg);
     __syncthreads();
     // A operand: im2col of g.  dx[y][x] takes tap (ty, tx) from g[y - ty + 1][x - tx + 1] = halo (ly + 2 - ty, lx + 2 - tx)
     for (int i = threadIdx.x; i < kFmPix * kFmN; i += kFmThreads) {
@@ -274,8 +315,8 @@ __global__ void __launch_bounds__(kFmThreads, 2) final_conv_tanh_bwd_x_mma_kerne
 //   part[(cta * Cout + co) * (9 * C + 1) + tap * C + ci],  bias sum at index 9 * C
 // -------------------------------------------------------------------------------------------------
 constexpr int kFmGtPitch = kFmPix * 2 + 16;             // bytes per row of Gt [n][pixel]   (132 words)
-// shared memory: gs [3][10][34] fp32 | Gth, Gtl [32][528 B] | xs [256][144 B] | red [8 warps][32][64] fp32
-constexpr size_t kFmDwSmem = kFmGsBytes + 2 * (size_t)kFmN * kFmGtPitch + (size_t)kFmPix * kFmXPitch;
+// shared memory: gs [3][10][34] fp32 | Gth, Gtl [32][528 B] | xs0, xs1 [256][144 B] | red [8 warps][32][64] fp32 (alias)
+constexpr size_t kFmDwSmem = kFmGsBytes + 2 * (size_t)kFmN * kFmGtPitch + 2 * (size_t)kFmPix * kFmXPitch;
 constexpr size_t kFmDwRedBytes = (size_t)(kFmThreads / 32) * kFmN * kFmC * 4;      // 64 KB, aliases the staging buffers
 
 __global__ void __launch_bounds__(kFmThreads, 1) final_conv_tanh_bwd_w_mma_kernel(const __nv_bfloat16 *__restrict__ x,
@@ -289,7 +330,8 @@ __global__ void __launch_bounds__(kFmThreads, 1) final_conv_tanh_bwd_w_mma_kerne
     float *gs = reinterpret_cast<float *>(fm_smem);
     unsigned char *Gth = fm_smem + kFmGsBytes;
     unsigned char *Gtl = Gth + (size_t)kFmN * kFmGtPitch;
-    unsigned char *xs = Gtl + (size_t)kFmN * kFmGtPitch;
+    unsigned char *xs0 = Gtl + (size_t)kFmN * kFmGtPitch;
+    unsigned char *xs1 = xs0 + (size_t)kFmPix * kFmXPitch;
     constexpr int gw = kFmTW + 2, gh = kFmTH + 2;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, q = lane & 3;
     const int n_tiles = B * tiles_x * tiles_y;
@@ -303,19 +345,33 @@ __global__ void __launch_bounds__(kFmThreads, 1) final_conv_tanh_bwd_w_mma_kerne
             for (int j = 0; j < 4; ++j) acc[mt][nt][j] = 0.f;
     float gsum[kFmCout] = {0.f, 0.f, 0.f};
 
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    // Software pipeline over the CTA's tiles: the x tile of trip i + 1 streams into the other staging buffer (cp.async) and
+    // its g values wait in registers while trip i runs its im2col and MMAs.
+    auto fetch = [&](int tile, unsigned char *xbuf, FmGRegs &gr) {
         const int tile_x = tile % tiles_x, tile_y = (tile / tiles_x) % tiles_y, b = tile / (tiles_x * tiles_y);
         const int x0 = tile_x * kFmTW, y0 = tile_y * kFmTH;
-        __syncthreads();                                // the previous trip's MMAs are done with the staging buffers
-        fm_stage_g(gs, out, dout, b, S, x0, y0);
         // x tile (no halo): the K index of this GEMM is the tile pixel p = ly * TW + lx
         const __nv_bfloat16 *xb = x + (size_t)b * S * S * kFmC;
-        for (int i = threadIdx.x; i < kFmPix * (kFmC / 8); i += kFmThreads) {
+#pragma unroll
+        for (int i0 = 0; i0 < kFmPix * (kFmC / 8); i0 += kFmThreads) {
+            const int i = i0 + threadIdx.x;
             const int v = i % (kFmC / 8), p = i / (kFmC / 8), lx = p % kFmTW, ly = p / kFmTW;
-            *reinterpret_cast<uint4 *>(xs + (size_t)p * kFmXPitch + v * 16) =
-                __ldg(reinterpret_cast<const uint4 *>(xb + ((size_t)(y0 + ly) * S + x0 + lx) * kFmC) + v);
+            cp_async_16_zfill(xbuf + (size_t)p * kFmXPitch + v * 16, xb + ((size_t)(y0 + ly) * S + x0 + lx) * kFmC + v * 8, true);
         }
+        fm_load_g(gr, out, dout, b, S, x0, y0);
+    };
+    FmGRegs greg;
+    int buf = 0;
+    if ((int)blockIdx.x < n_tiles) fetch(blockIdx.x, xs0, greg);
+    cp_async_commit();
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        unsigned char *xs = buf ? xs1 : xs0;
+        __syncthreads();                                // the previous trip's MMAs are done with gs, Gt and the other x buffer
+        fm_store_g(gs, greg);
         __syncthreads();
+        const int next = tile + gridDim.x;
+        if (next < n_tiles) fetch(next, buf ? xs0 : xs1, greg);
+        cp_async_commit();                              // (possibly empty) group of the next tile
         // Gt[n = tap * 3 + co][p]: input pixel p = (ly, lx) meets g at (ly - ty + 1, lx - tx + 1) = halo (ly + 2 - ty, lx + 2 - tx)
         for (int i = threadIdx.x; i < kFmN * kFmPix; i += kFmThreads) {
             const int p = i % kFmPix, n = i / kFmPix;
@@ -334,6 +390,7 @@ __global__ void __launch_bounds__(kFmThreads, 1) final_conv_tanh_bwd_w_mma_kerne
 #pragma unroll
             for (int co = 0; co < kFmCout; ++co) gsum[co] += gs[(co * gh + ly + 1) * gw + lx + 1];
         }
+        cp_async_wait_group<1>();                       // this trip's x tile has landed (the next one may still be in flight)
         __syncthreads();
         // K = 256 pixels = 16 k-chunks; warp w takes chunks w, w + 8
         for (int kc = warp; kc < kFmPix / 16; kc += kFmThreads / 32) {
@@ -362,7 +419,9 @@ __global__ void __launch_bounds__(kFmThreads, 1) final_conv_tanh_bwd_w_mma_kerne
                 }
             }
         }
+        buf ^= 1;
     }
+    cp_async_wait_group<0>();
     // ---- fixed-order reduction over the 8 warps, then the per-CTA partial -------------------------------------
 #pragma unroll
     for (int co = 0; co < kFmCout; ++co) gsum[co] = warp_sum(gsum[co]);

@@ -74,6 +74,20 @@ __device__ __forceinline__ uint4 ld_stream_16(const void *p)
                  : "l"(p));
     return r;
 }
+// 16-byte asynchronous global -> shared copy (LDGSTS, bypasses L1 and the register file).  `valid == false` reads nothing
+// and fills the 16 bytes with zeros (src-size 0): halo pixels outside the image.  A staging loop written with these keeps
+// every copy of a thread in flight at once; the same loop with `smem = __ldg(global)` pays one memory round trip per
+// iteration whenever the compiler cannot hoist the loads over the stores.
+__device__ __forceinline__ void cp_async_16_zfill(void *smem_dst, const void *gsrc, bool valid)
+{
+    const unsigned n = valid ? 16u : 0u;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc), "r"(n)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 __device__ __forceinline__ void st_stream_16(void *p, uint4 v)
 {
     asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z),
