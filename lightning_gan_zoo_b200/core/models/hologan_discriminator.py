@@ -101,15 +101,54 @@ class Discriminator(nn.Module):
         taps), InstanceNorm + LeakyReLU storing the next block's space-to-depth operand, and both heads in one pass.
         No cuDNN / cuBLAS kernel runs.  The convolution biases of the blocks are not applied: the InstanceNorm that
         follows removes any per-channel constant (their gradient is identically zero)."""
+        self._b200_used = True
         h = ops.dconv0(x, self.conv2d.weight, self.conv2d.bias, 0.2)                  # (B, S/4, S/4, 4, 64)
-        convs = [blk.conv2d for blk in self.blocks]
-        states = ops.spectral_norm_sigma([c.weight_orig for c in convs], [c.weight_u for c in convs],
-                                         [c.weight_v for c in convs], power_iteration=self.training)
+        states = self._take_spectral_norm_states()
         for i, (blk, st) in enumerate(zip(self.blocks, states)):
             y = ops.conv5s2_sn(h, blk.conv2d.weight_orig, st)                         # (B, S', S', Cout)
             h = ops.instance_norm_act_channels_last(y, 0.2, blk.instance_norm.eps, s2d_out=i + 1 < len(self.blocks))
         return ops.dheads(h, self.linear1.weight, self.linear1.bias, self.linear2.weight, self.linear2.bias,
                           self.linear3.weight, self.linear3.bias, 0.2)
+
+    def _spectral_norm_states(self):
+        convs = [blk.conv2d for blk in self.blocks]
+        return ops.spectral_norm_sigma([c.weight_orig for c in convs], [c.weight_u for c in convs],
+                                       [c.weight_v for c in convs], power_iteration=self.training)
+
+    def prefetch_spectral_norm(self, forwards: int = 1):
+        """Run the power iteration + sigma of the next `forwards` forward passes NOW, on a side stream: the grouped
+        spectral-norm kernels are tiny (3 .. 48 CTAs, ~40 us per forward) and depend only on the weights, so they overlap
+        whatever the caller launches next on the current stream (the generator's forward in both the D and the G step)
+        instead of sitting in front of the first block.  Each later `forward` consumes one prefetched state, in order --
+        u / v advance exactly as if every forward had run its own iteration (reference
+        core/models/hologan_discriminator.py:15: one power iteration per training-mode forward).  Works inside CUDA-graph
+        capture (the side stream forks from and joins the capturing stream)."""
+        w = self.blocks[0].conv2d.weight_orig
+        if not w.is_cuda or not getattr(self, "_b200_used", False):     # only once a forward has taken the path that consumes them
+            return
+        cur = torch.cuda.current_stream(w.device)
+        if getattr(self, "_sn_stream", None) is None or self._sn_stream.device != w.device:
+            self._sn_stream = torch.cuda.Stream(device=w.device)
+            self._sn_ready = []
+        self._sn_stream.wait_stream(cur)                # the weights may have just been written by the optimizer
+        with torch.cuda.stream(self._sn_stream):
+            for _ in range(forwards):
+                states = self._spectral_norm_states()
+                ev = torch.cuda.Event()
+                ev.record(self._sn_stream)
+                for t in states:
+                    t.record_stream(cur)
+                self._sn_ready.append((states, ev, self.training))
+
+    def _take_spectral_norm_states(self):
+        ready = getattr(self, "_sn_ready", None)
+        if ready:
+            states, ev, training = ready.pop(0)
+            if training == self.training:
+                torch.cuda.current_stream(states[0].device).wait_event(ev)
+                return states
+            ready.clear()                               # mode changed since the prefetch: recompute in line
+        return self._spectral_norm_states()
 
     def _b200_ok(self, x):
         import os

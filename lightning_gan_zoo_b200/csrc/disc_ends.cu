@@ -69,12 +69,24 @@ __device__ __forceinline__ void c0_stage_patch(__nv_bfloat16 *patch, const C0Ima
 {
     using G = C0Geom<KS>;
     const int iy0 = 2 * oy0 - PAD, ix0 = 2 * ox0 - PAD;
-    for (int i = threadIdx.x; i < kC0Cin * G::PH * G::PPitch; i += kC0Threads) {
-        const int px = i % G::PPitch, r = i / G::PPitch, py = r % G::PH, ci = r / G::PH;
-        const int yy = iy0 + py, xx = ix0 + px;
-        float v = 0.f;
-        if (px < G::PW && yy >= 0 && yy < S && xx >= 0 && xx < S) v = img.at(img_off + ((size_t)ci * S + yy) * S + xx);
-        patch[i] = __float2bfloat16_rn(v);
+    // batches of 4 elements per thread: the loads of a batch are issued together (one memory round trip per batch, not
+    // per element -- the loop body is a conditional load followed by a shared-memory store, which the compiler keeps in order)
+    constexpr int N = kC0Cin * G::PH * G::PPitch, U = 4;
+    for (int i0 = threadIdx.x; i0 < N; i0 += U * kC0Threads) {
+        float v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int i = i0 + u * kC0Threads;
+            const int px = i % G::PPitch, r = i / G::PPitch, py = r % G::PH, ci = r / G::PH;
+            const int yy = iy0 + py, xx = ix0 + px;
+            const bool ok = i < N && px < G::PW && yy >= 0 && yy < S && xx >= 0 && xx < S;
+            v[u] = ok ? img.at(img_off + ((size_t)ci * S + yy) * S + xx) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int i = i0 + u * kC0Threads;
+            if (i < N) patch[i] = __float2bfloat16_rn(v[u]);
+        }
     }
 }
 
@@ -228,12 +240,20 @@ __global__ void __launch_bounds__(kC0Threads) c0_dw_kernel(C0Image img, C0Map ma
         c0_stage_patch<KS, PAD>(patch, img, (size_t)b * kC0Cin * S * S, S, oy0, ox0);
         {   // map tile, transposed: thread -> (pixel, 8 channels)
             const size_t mimg = (size_t)b * S2 * S2 * kC0Cout;
-            for (int i = threadIdx.x; i < kC0TH * kC0TW * 8; i += kC0Threads) {
-                const int c8 = i & 7, pix = i >> 3, py = pix / kC0TW, px = pix % kC0TW;
-                float f[8];
-                map.load8(mimg + (size_t)c0_map_row<HEAD>(oy0 + py, ox0 + px, S2) * kC0Cout + c8 * 8, f);
+            constexpr int NV = kC0TH * kC0TW * 8 / kC0Threads;      // 4 vectors per thread: loaded together, then scattered
+            float f[NV][8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) dt[(c8 * 8 + j) * kC0DtPitch + pix] = __float2bfloat16_rn(f[j]);
+            for (int u = 0; u < NV; ++u) {
+                const int i = threadIdx.x + u * kC0Threads;
+                const int c8 = i & 7, pix = i >> 3, py = pix / kC0TW, px = pix % kC0TW;
+                map.load8(mimg + (size_t)c0_map_row<HEAD>(oy0 + py, ox0 + px, S2) * kC0Cout + c8 * 8, f[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < NV; ++u) {
+                const int i = threadIdx.x + u * kC0Threads;
+                const int c8 = i & 7, pix = i >> 3;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) dt[(c8 * 8 + j) * kC0DtPitch + pix] = __float2bfloat16_rn(f[u][j]);
             }
         }
         __syncthreads();
@@ -383,16 +403,27 @@ __global__ void __launch_bounds__(kC0Threads) c0_map2img_kernel(C0Map map, const
         __syncthreads();
         {
             const size_t mimg = (size_t)b * S2 * S2 * kC0Cout;
-            for (int i = threadIdx.x; i < kC0HaloH * kC0HaloW * 8; i += kC0Threads) {
-                const int c8 = i & 7, pix = i >> 3, hy = pix / kC0HaloW, hx = pix % kC0HaloW;
-                const int oy = i0 + hy - 1, ox = j0 + hx - 1;
-                uint4 o = make_uint4(0, 0, 0, 0);
-                if (oy >= 0 && oy < S2 && ox >= 0 && ox < S2) {
-                    float f[8];
-                    map.load8(mimg + (size_t)c0_map_row<HEAD>(oy, ox, S2) * kC0Cout + c8 * 8, f);
-                    o = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+            constexpr int NH = kC0HaloH * kC0HaloW * 8, U = 3;      // 1440 vectors: two batches of 3 per thread, loads together
+            for (int i0v = threadIdx.x; i0v < NH; i0v += U * kC0Threads) {
+                float f[U][8];
+                bool ok[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int i = i0v + u * kC0Threads;
+                    const int c8 = i & 7, pix = i >> 3, hy = pix / kC0HaloW, hx = pix % kC0HaloW;
+                    const int oy = i0 + hy - 1, ox = j0 + hx - 1;
+                    ok[u] = i < NH && oy >= 0 && oy < S2 && ox >= 0 && ox < S2;
+                    map.load8(ok[u] ? mimg + (size_t)c0_map_row<HEAD>(oy, ox, S2) * kC0Cout + c8 * 8 : mimg, f[u]);
                 }
-                *reinterpret_cast<uint4 *>(ds + (size_t)pix * kC0XPitch + c8 * 16) = o;
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int i = i0v + u * kC0Threads;
+                    const int c8 = i & 7, pix = i >> 3;
+                    const uint4 o = ok[u] ? make_uint4(pack_bf16x2(f[u][0], f[u][1]), pack_bf16x2(f[u][2], f[u][3]),
+                                                       pack_bf16x2(f[u][4], f[u][5]), pack_bf16x2(f[u][6], f[u][7]))
+                                          : make_uint4(0, 0, 0, 0);
+                    if (i < NH) *reinterpret_cast<uint4 *>(ds + (size_t)pix * kC0XPitch + c8 * 16) = o;
+                }
             }
         }
         __syncthreads();

@@ -288,6 +288,8 @@ class HologanTrainer:
         self.d_grads = _FlatGrads(self.discriminator.parameters(), accumulate_into=sn_weights, buckets=d_buckets)
         # the generator's tcgen05 wgrad kernels store straight into the flat buffer (ops._direct_grad_target)
         self.g_grads = _FlatGrads(self.generator.parameters(), direct=cuda, buckets=g_buckets)
+        # A/B switch: HG_NO_SN_PREFETCH=1 keeps the discriminator's spectral-norm iteration in line (in front of its first block)
+        self._sn_prefetch = cuda and os.environ.get("HG_NO_SN_PREFETCH", "0") in ("", "0") and os.environ.get("HG_D_LIBRARY", "0") in ("", "0")
         self._flat_adam = cuda and os.environ.get("HG_D_LIBRARY", "0") in ("", "0") and os.environ.get("HG_TORCH_ADAM", "0") in ("", "0")
         if self._flat_adam:
             # one fused kernel per optimizer step over flat parameter / gradient / moment buffers (hg_adam_step)
@@ -346,6 +348,10 @@ class HologanTrainer:
         (the reference samples them inside); `real` is (B,3,H,W) in [-1,1] on the device."""
         bce = F.binary_cross_entropy_with_logits
         cuda = self.device.type == "cuda"
+        if cuda and self._sn_prefetch and self.compute_dtype == torch.bfloat16:
+            # the discriminator's spectral-norm power iterations (two forwards in the D step, one in a G step) overlap the
+            # generator's forward on a side stream
+            self.discriminator.prefetch_spectral_norm(2 if optimizer_idx == 0 else 1)
         if optimizer_idx == 0:
             with torch.no_grad(), self._autocast():     # the D step detaches fake (:221): no G graph is needed
                 fake = self.generator(z, view_in=view)

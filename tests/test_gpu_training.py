@@ -102,6 +102,32 @@ def test_cuda_graph_step_matches_eager():
 
 
 @pytest.mark.parametrize("graphs", [False, True])
+def test_spectral_norm_prefetch_is_transparent(graphs):
+    """The discriminator's power iterations run ahead on a side stream (Discriminator.prefetch_spectral_norm); u / v and
+    the losses must be exactly what the in-line iteration gives -- same kernels on the same data, only earlier."""
+    cfg = HologanConfig(batch_size=8)
+    a = HologanTrainer(cfg, device=DEV, seed=5)
+    b = HologanTrainer(cfg, device=DEV, seed=5)
+    assert a._sn_prefetch
+    b._sn_prefetch = False
+    if graphs:
+        a.enable_cuda_graphs(8)
+        b.enable_cuda_graphs(8)
+    gen = torch.Generator().manual_seed(1)
+    for i in range(6):
+        real = (torch.rand(8, 3, 64, 64, generator=gen) * 2 - 1).to(DEV)
+        z = (torch.rand(8, 128, generator=gen) * 2 - 1).to(DEV)
+        view = orc.sample_view(8, np.random.RandomState(i))
+        la, lb = a.step(real, i, z=z, view=view), b.step(real, i, z=z, view=view)
+        assert la.item() == lb.item(), (i, la.item(), lb.item())
+    torch.cuda.synchronize()
+    for blk_a, blk_b in zip(a.discriminator.blocks, b.discriminator.blocks):
+        assert torch.equal(blk_a.conv2d.weight_u, blk_b.conv2d.weight_u)
+        assert torch.equal(blk_a.conv2d.weight_orig, blk_b.conv2d.weight_orig)
+    assert not a.discriminator._sn_ready
+
+
+@pytest.mark.parametrize("graphs", [False, True])
 def test_step_host_matches_step(graphs):
     """The pipelined host-input entry (pinned staging, copy stream, asynchronous loss read-back) runs the same
     step as `step` on device-resident inputs: same losses, read one step late, and same weights afterwards."""
