@@ -75,16 +75,15 @@ const char *hg_last_error(void);
  *   ADAIN_GEMM_STATS     (0)   host layer: the generator's AdaIN statistics come from the tap-GEMM epilogue
  *                              (hg_convt_fwd_stats + hg_adain_cl_fwd_stats) instead of the single-pass cluster kernel;
  *                              measured break-even on B200 (profiles/r02f_microbench_conv.txt), hence off
- *   TAPGEMM_PERSISTENT   (0)   1: tap GEMMs with more tiles than SMs run one persistent CTA per SM that walks the tiles with two
- *                              TMEM accumulator stages (epilogue of tile i overlaps the main loop of tile i + 1).  Measured on
- *                              B200 (profiles/r02m_*): wins on the wide tiles (block3 dgrad 129 -> 106 us) but loses on the
- *                              narrow layers, where two co-resident one-tile CTAs issue MMAs from two threads; step 1.87 vs
- *                              1.81 ms, hence off
- *   TAPGEMM_MSUB         (0)   1: wide tap GEMMs (256-column tiles: block3, the projection, block4 dgrad) process two 128-row
- *                              sub-tiles per CTA that share every weight tile of the K loop (a third less L2 traffic per
- *                              FLOP).  Measured on B200 (profiles/r02q_*): block3 dgrad 138 -> 123 us, but the projection
- *                              50 -> 63 us and block4 dgrad 49 -> 64 us (three 64 KB stages instead of four 48 KB ones,
- *                              no second CTA per SM); step 1.91 vs 1.86 ms, hence off
+ *   TAPGEMM_PERSISTENT   (-1)  tap GEMMs with more tiles than SMs as one persistent CTA per SM that walks the tiles with two
+ *                              TMEM accumulator stages (epilogue of tile i overlaps the main loop of tile i + 1).  -1 auto: the
+ *                              wide tiles only (256-column MMAs: projection, block3, block4 dgrad); 0 never; 1 always.
+ *                              B200 (profiles/r02z_tap_gemm_options.txt): auto is +1.0 % step throughput over 0; forcing it on
+ *                              the narrow layers loses (two co-resident one-tile CTAs issue MMAs from two threads)
+ *   TAPGEMM_MSUB         (0)   1: wide tap GEMMs (256-column tiles) process two 128-row sub-tiles per CTA that share every
+ *                              weight tile of the K loop (a third less L2 traffic per FLOP).  B200 (same file): block3 dgrad
+ *                              107 -> 99 us, everything else unchanged or slower (256 tiles on 148 SMs quantise worse than
+ *                              512); +0.4 % alone, -0.4 % on top of the persistent default, hence off
  *   TAPGEMM_SHARE_A      (2)   forward of the narrow layers (several parity classes per CTA): every shifted activation box is
  *                              loaded ONCE per K chunk for all classes of the CTA that use it, their weight boxes (at most this
  *                              many, <= 256 rows) are stacked behind each other and one MMA per run of adjacent classes adds

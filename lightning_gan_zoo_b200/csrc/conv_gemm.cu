@@ -983,7 +983,11 @@ static int launch_tap_gemm(TapGemmParams &p, int m_tiles, int n_tiles, cudaStrea
         }
     const long long total = (long long)m_tiles * n_tiles * p.num_groups;
     const int scratch = p.stats ? 4 * 32 * 33 * (int)sizeof(float) : 0;
-    const bool persistent = option(kOptTapGemmPersistent) != 0 && total > sm_count();
+    // persistent (one CTA per SM walks the tiles, two accumulator stages): auto = the wide tiles (BN == 256: the projection,
+    // block3, block4 dgrad), whose one-tile launches get two shallow stages per co-resident CTA or no epilogue overlap at
+    // all; the narrow layers keep two co-resident one-tile CTAs (profiles/r02z_tap_gemm_options.txt)
+    const int popt = option(kOptTapGemmPersistent);
+    const bool persistent = (popt > 0 || (popt < 0 && p.BN == 256 && p.item_rows == 0 && !p.stats)) && total > sm_count();
     unsigned grid;
     size_t smem;
     if (persistent) {
