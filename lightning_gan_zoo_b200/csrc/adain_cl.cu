@@ -539,6 +539,149 @@ __global__ void __launch_bounds__(kClThreads, 3) adain_cl_bwd_apply_kernel(const
 }
 
 
+// ---- ring path (the two backward passes of the chunked kernels) ------------------------------------------
+// The register-staged loops above alternate between a load phase and a compute phase: ncu shows both backward kernels
+// waiting on long-scoreboard stalls at ~30 % of the issue slots and ~2.3 TB/s (profiles/r02x_ncu_full_summary.txt).
+// Here every thread streams its rows through a PRIVATE ring of shared-memory slots filled by cp.async: kRingS - 1 stages
+// of kRingUN rows x 2 tensors x 16 bytes stay in flight per thread for the whole loop, with no register cost and no
+// cross-thread synchronisation (a thread only reads the slots it filled itself; cp.async.wait_group orders them).
+constexpr int kRingUN = 2, kRingS = 4;
+constexpr size_t kRingBytes = (size_t)kRingS * kRingUN * 2 * kClThreads * 16;        // 64 KB per CTA, three CTAs per SM
+
+template <typename Body>
+__device__ __forceinline__ void ring_stream2(uint4 *ring, const __nv_bfloat16 *__restrict__ xb, const __nv_bfloat16 *__restrict__ gb,
+                                             const ClGeom &g, int r0, int r1, int rs, Body body)
+{
+    uint4 *col = ring + threadIdx.x;                    // [stage][u][tensor][thread]
+    const int step = g.rows_per_pass;
+    int ri = r0 + rs;
+    auto issue = [&](int stage) {
+#pragma unroll
+        for (int u = 0; u < kRingUN; ++u) {
+            const int rr = ri + u * step;
+            const bool ok = rr < r1;
+            cp_async_16_zfill(col + ((stage * kRingUN + u) * 2 + 0) * kClThreads, ok ? xb + (size_t)rr * g.C : xb, ok);
+            cp_async_16_zfill(col + ((stage * kRingUN + u) * 2 + 1) * kClThreads, ok ? gb + (size_t)mapped_row(rr, g) * g.C : gb, ok);
+        }
+        ri += kRingUN * step;
+        cp_async_commit();
+    };
+#pragma unroll
+    for (int sgi = 0; sgi < kRingS - 1; ++sgi) issue(sgi);
+    int stage = 0;
+    for (int r = r0 + rs; r < r1; r += kRingUN * step) {
+        int nxt = stage + kRingS - 1;
+        if (nxt >= kRingS) nxt -= kRingS;
+        issue(nxt);                                     // past the end: zero-size copies, the group still counts
+        cp_async_wait_group<kRingS - 1>();
+#pragma unroll
+        for (int u = 0; u < kRingUN; ++u) {
+            const int rr = r + u * step;
+            if (rr < r1) body(rr, col[((stage * kRingUN + u) * 2 + 0) * kClThreads], col[((stage * kRingUN + u) * 2 + 1) * kClThreads]);
+        }
+        if (++stage == kRingS) stage = 0;
+    }
+    cp_async_wait_group<0>();
+}
+
+__global__ void __launch_bounds__(kClThreads, 3) adain_cl_bwd_sums_ring_kernel(const __nv_bfloat16 *__restrict__ x,
+                                                                            const __nv_bfloat16 *__restrict__ dy,
+                                                                            const float *__restrict__ scale,
+                                                                            const float *__restrict__ bias,
+                                                                            const float *__restrict__ save_mean,
+                                                                            const float *__restrict__ save_rstd,
+                                                                            float *__restrict__ part, ClGeom g, int sbs, float slope)
+{
+    extern __shared__ __align__(16) unsigned char cl_dyn[];
+    uint4 *ring = reinterpret_cast<uint4 *>(cl_dyn);
+    float *red = reinterpret_cast<float *>(cl_dyn);     // reused after the stream (cta_rowslot_sum synchronises first)
+    const int cs = threadIdx.x % g.lanes, rs = threadIdx.x / g.lanes;
+    const int b = blockIdx.y, chunk = blockIdx.x;
+    const size_t base = (size_t)b * g.N * g.C + cs * 8;
+    ClStyle st;
+    load_style(st, scale, bias, save_mean, save_rstd, b, g.C, sbs, cs * 8);
+    float sg[8], sgx[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sg[j] = sgx[j] = 0.f;
+    const int r0 = chunk * g.chunk_rows, r1 = min(g.N, r0 + g.chunk_rows);
+    ring_stream2(ring, x + base, dy + base, g, r0, r1, rs, [&](int, const uint4 &xr, const uint4 &gr) {
+        float xf[8], gf[8];
+        unpack8(xr, xf);
+        unpack8(gr, gf);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float gg = fmaf(xf[j], st.a[j], st.c[j]) > 0.f ? gf[j] : gf[j] * slope;
+            sg[j] += gg;
+            sgx[j] = fmaf(gg, xf[j] - st.mean[j], sgx[j]);
+        }
+    });
+    cta_rowslot_sum(sg, sgx, red, g.lanes, g.rows_per_pass, cs, rs);
+    if (rs == 0) {
+        float *dst = part + ((size_t)b * g.chunks + chunk) * 2 * g.C + cs * 8;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            dst[j] = sg[j];
+            dst[g.C + j] = sgx[j];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kClThreads, 3) adain_cl_bwd_apply_ring_kernel(const __nv_bfloat16 *__restrict__ x,
+                                                                             const __nv_bfloat16 *__restrict__ dy,
+                                                                             const float *__restrict__ part,
+                                                                             const float *__restrict__ scale,
+                                                                             const float *__restrict__ bias,
+                                                                             const float *__restrict__ save_mean,
+                                                                             const float *__restrict__ save_rstd,
+                                                                             __nv_bfloat16 *__restrict__ dx, float *__restrict__ dscale,
+                                                                             float *__restrict__ dbias, ClGeom g, int sbs, int dsbs,
+                                                                             float slope)
+{
+    extern __shared__ __align__(16) unsigned char cl_dyn[];
+    uint4 *ring = reinterpret_cast<uint4 *>(cl_dyn);
+    const int cs = threadIdx.x % g.lanes, rs = threadIdx.x / g.lanes;
+    const int b = blockIdx.y, chunk = blockIdx.x;
+    const size_t base = (size_t)b * g.N * g.C + cs * 8;
+    ClStyle st;
+    load_style(st, scale, bias, save_mean, save_rstd, b, g.C, sbs, cs * 8);
+    float sg[8], sgx[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sg[j] = sgx[j] = 0.f;
+    const float *src = part + (size_t)b * g.chunks * 2 * g.C + cs * 8;      // chunk partials of the sums kernel, fixed order
+    for (int k = 0; k < g.chunks; ++k) {
+        const float4 *a4 = reinterpret_cast<const float4 *>(src + (size_t)k * 2 * g.C);
+        const float4 *q4 = reinterpret_cast<const float4 *>(src + (size_t)k * 2 * g.C + g.C);
+        const float4 a0 = a4[0], a1 = a4[1], q0 = q4[0], q1 = q4[1];
+        sg[0] += a0.x; sg[1] += a0.y; sg[2] += a0.z; sg[3] += a0.w; sg[4] += a1.x; sg[5] += a1.y; sg[6] += a1.z; sg[7] += a1.w;
+        sgx[0] += q0.x; sgx[1] += q0.y; sgx[2] += q0.z; sgx[3] += q0.w; sgx[4] += q1.x; sgx[5] += q1.y; sgx[6] += q1.z; sgx[7] += q1.w;
+    }
+    const bool publish = chunk == 0 && rs == 0 && dscale && dbias;
+    float c1[8], c2[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float sgxh = sgx[j] * st.rstd[j];                         // sum(g * xhat)
+        if (publish) {
+            dbias[(size_t)b * dsbs + cs * 8 + j] = sg[j];
+            dscale[(size_t)b * dsbs + cs * 8 + j] = sgxh;
+        }
+        c2[j] = st.a[j] * st.rstd[j] * (sgxh / (float)g.Nvar);
+        c1[j] = st.a[j] * (sg[j] / (float)g.N) - st.mean[j] * c2[j];
+    }
+    const int r0 = chunk * g.chunk_rows, r1 = min(g.N, r0 + g.chunk_rows);
+    __nv_bfloat16 *db = dx + base;
+    ring_stream2(ring, x + base, dy + base, g, r0, r1, rs, [&](int rr, const uint4 &xr, const uint4 &gr) {
+        float xf[8], gf[8];
+        unpack8(xr, xf);
+        unpack8(gr, gf);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float gg = fmaf(xf[j], st.a[j], st.c[j]) > 0.f ? gf[j] : gf[j] * slope;
+            xf[j] = fmaf(gg, st.a[j], -fmaf(xf[j], c2[j], c1[j]));
+        }
+        st_stream_16(db + (size_t)rr * g.C, pack8(xf));
+    });
+}
+
 // ---- cluster path -------------------------------------------------------------------------------------
 // grid (CS, B), cluster (CS, 1, 1): CTA `blockIdx.x` of the cluster owns rows [blockIdx.x * U * rpp, +U * rpp) of
 // sample blockIdx.y; thread (rs, cs) holds rows r0 + rs + u * rpp, u < U, of channel octet cs in registers.
@@ -936,6 +1079,21 @@ extern "C" int hg_adain_cl_bwd(const void *x, const void *dy, const float *scale
     HG_REQUIRE(workspace && workspace_bytes >= (long long)batch * (g.chunks + 1) * 2 * channels * (long long)sizeof(float),
                HG_ERR_INVALID_ARG, "hg_adain_cl_bwd: workspace smaller than hg_adain_cl_workspace_bytes()");
     float *part = static_cast<float *>(workspace);
+    if (option(kOptAdainClRing) != 0) {                 // cp.async ring (see ring_stream2)
+        static bool ring_attr = false;                  // not a stream operation (graph-capture safe)
+        if (!ring_attr) {
+            cudaFuncSetAttribute(adain_cl_bwd_sums_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRingBytes);
+            cudaFuncSetAttribute(adain_cl_bwd_apply_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRingBytes);
+            ring_attr = true;
+        }
+        adain_cl_bwd_sums_ring_kernel<<<grid, kClThreads, kRingBytes, st>>>(xp, gp, scale, bias, save_mean, save_rstd, part, g, sb_stride,
+                                                                           neg_slope);
+        rc = check_launch("hg_adain_cl_bwd(sums, ring)");
+        if (rc) return rc;
+        adain_cl_bwd_apply_ring_kernel<<<grid, kClThreads, kRingBytes, st>>>(xp, gp, part, scale, bias, save_mean, save_rstd, dp, dscale,
+                                                                            dbias, g, sb_stride, dsb_stride, neg_slope);
+        return check_launch("hg_adain_cl_bwd(apply, ring)");
+    }
     adain_cl_bwd_sums_kernel<<<grid, kClThreads, 0, st>>>(xp, gp, scale, bias, save_mean, save_rstd, part, g, sb_stride, neg_slope);
     rc = check_launch("hg_adain_cl_bwd(sums)");
     if (rc) return rc;

@@ -45,6 +45,7 @@ enum Option {
     kOptTapGemmPersistent,      // 1: tap GEMMs with more tiles than SMs run one persistent CTA per SM (0: one tile per CTA)
     kOptTapGemmMsub,            // 1: wide tap GEMMs (256-column tiles) process two 128-row sub-tiles per CTA that share every B tile
     kOptTapGemmShareA,          // > 0: forward of the narrow layers loads every shifted A box once for all parity classes of a CTA (value = weight boxes per item)
+    kOptAdainClRing,            // 1: chunked channels-last AdaIN backward streams through per-thread cp.async rings
     kOptCount
 };
 int option(Option o);

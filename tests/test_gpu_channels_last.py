@@ -155,6 +155,32 @@ def test_adain_channels_last_cluster_vs_chunked(b, ndim, size, c, classes, hg_op
         assert torch.equal(u, v)                      # deterministic (fixed reduction order through the cluster)
 
 
+@pytest.mark.parametrize("b,ndim,size,c,classes", [(64, 2, 16, 256, 4), (64, 2, 32, 64, 4), (64, 3, 8, 64, 8), (3, 3, 8, 64, 8),
+                                                  (5, 2, 32, 128, 1), (2, 2, 16, 512, 4)])
+def test_adain_channels_last_backward_ring_is_bitwise(b, ndim, size, c, classes, hg_option):
+    """Option ADAIN_CL_RING: the chunked backward streaming its rows through per-thread cp.async rings instead of
+    register-staged loads -- same arithmetic in the same order, so every output must match bit for bit."""
+    gen = torch.Generator().manual_seed(b + size + c)
+    sp = (size,) * ndim
+    shape = (b, *sp, classes, c) if classes > 1 else (b, *sp, c)
+    x = (torch.randn(*shape, generator=gen) * 1.5 + 0.3).to(BF).to(DEV)
+    s = (torch.rand(b, c, generator=gen) + 0.2).to(DEV)
+    bb = torch.randn(b, c, generator=gen).to(DEV)
+    up = 2 if classes > 1 else 1
+    dy = torch.randn(b, *((up * size,) * ndim), c, generator=gen).to(BF).to(DEV)
+    hg_option("ADAIN_CL_NO_CLUSTER", 1)                      # both runs on the chunked path
+
+    def run(ring):
+        hg_option("ADAIN_CL_RING", ring)
+        xg = x.clone().requires_grad_(True); sg = s.clone().requires_grad_(True); bg = bb.clone().requires_grad_(True)
+        y = ops.adain_act_channels_last(xg, sg, bg, ndim, classes, 0.2)
+        y.backward(dy)
+        return xg.grad, sg.grad, bg.grad
+
+    for u, v in zip(run(1), run(0)):
+        assert torch.equal(u, v)
+
+
 def test_unsupported():
     from lightning_gan_zoo_b200._lib import HologanB200Error
     x = torch.zeros(1, 16, 16, 4, 24, dtype=BF, device=DEV)
