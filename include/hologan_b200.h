@@ -360,6 +360,13 @@ int hg_dheads_bwd(const void *h, const float *w1, const float *w2, const float *
  * p -= lr / (1 - b1^t) * m / (sqrt(v) / sqrt(1 - b2^t) + eps). */
 int hg_adam_step(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, long long n, float *state,
                  const float *lr, float beta1, float beta2, float eps, float grad_scale, void *stream);
+/* The same step in two parts, for an optimizer that runs bucket by bucket behind the gradient exchange (the data-parallel
+ * harness applies a bucket on a side stream as soon as its all-reduce has finished, while the backward pass continues --
+ * run_network.py:66-71's DDP overlap, extended to the update): hg_adam_tick advances state[0] and the bias corrections
+ * ONCE per step; hg_adam_apply updates any 16-byte aligned sub-range (n % 4 == 0) of the four flat buffers with them. */
+int hg_adam_tick(float *state, const float *lr, float beta1, float beta2, void *stream);
+int hg_adam_apply(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, long long n, const float *state,
+                  float beta1, float beta2, float eps, float grad_scale, void *stream);
 
 /* ---- a13: the losses of HOLOGAN.training_step  (core/lightning_module.py:217-237) -------------------
  *   adv = wa * mean_i BCEWithLogits(a[i], ta) + wb * mean_j BCEWithLogits(b[j], tb)   (b may be NULL, nb = 0)

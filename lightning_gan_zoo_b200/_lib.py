@@ -81,6 +81,8 @@ SIGNATURES = {
                        _c_int, _c_int, _c_int, _c_void_p],
     "hg_adam_step": [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_ll, _c_void_p, _c_void_p, _c_float, _c_float, _c_float,
                      _c_float, _c_void_p],
+    "hg_adam_tick": [_c_void_p, _c_void_p, _c_float, _c_float, _c_void_p],
+    "hg_adam_apply": [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_ll, _c_void_p, _c_float, _c_float, _c_float, _c_float, _c_void_p],
     "hg_gan_loss_fwd": [_c_void_p, _c_int, _c_float, _c_float, _c_void_p, _c_int, _c_float, _c_float, _c_void_p, _c_void_p,
                         _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p],
     "hg_gan_loss_bwd": [_c_void_p, _c_void_p, _c_int, _c_float, _c_float, _c_void_p, _c_int, _c_float, _c_float, _c_void_p,

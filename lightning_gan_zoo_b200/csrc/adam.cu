@@ -47,21 +47,39 @@ __global__ void __launch_bounds__(256) adam_kernel(float *__restrict__ p, const 
 
 using namespace hg;
 
-// n must be a multiple of 4 and the four buffers 16-byte aligned (the trainer pads its flat buffers).
 // state: 4 device floats owned by the caller ([0] = number of steps taken so far; zero it to reset).
-extern "C" int hg_adam_step(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, long long n, float *state,
-                            const float *lr, float beta1, float beta2, float eps, float grad_scale, void *stream)
+// hg_adam_tick advances the step counter and the bias-correction factors ONCE per optimizer step; hg_adam_apply then updates
+// any 16-byte aligned sub-range of the flat buffers (the trainer applies a gradient bucket as soon as its all-reduce has
+// finished, on a side stream, while the rest of the backward still runs).  hg_adam_step = tick + apply on one range.
+extern "C" int hg_adam_tick(float *state, const float *lr, float beta1, float beta2, void *stream)
 {
-    HG_REQUIRE(param && grad && exp_avg && exp_avg_sq && state && lr, HG_ERR_INVALID_ARG, "hg_adam_step: null pointer");
-    HG_REQUIRE(n > 0 && n % 4 == 0, HG_ERR_INVALID_ARG, "hg_adam_step: n must be a positive multiple of 4 (got %lld)", n);
+    HG_REQUIRE(state && lr, HG_ERR_INVALID_ARG, "hg_adam_tick: null pointer");
+    adam_tick_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(state, lr, beta1, beta2);
+    return check_launch("hg_adam_tick");
+}
+
+// n must be a multiple of 4 and the four buffers 16-byte aligned (the trainer pads its flat buffers).
+extern "C" int hg_adam_apply(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, long long n, const float *state,
+                             float beta1, float beta2, float eps, float grad_scale, void *stream)
+{
+    HG_REQUIRE(param && grad && exp_avg && exp_avg_sq && state, HG_ERR_INVALID_ARG, "hg_adam_apply: null pointer");
+    HG_REQUIRE(n > 0 && n % 4 == 0, HG_ERR_INVALID_ARG, "hg_adam_apply: n must be a positive multiple of 4 (got %lld)", n);
     HG_REQUIRE(((reinterpret_cast<uintptr_t>(param) | reinterpret_cast<uintptr_t>(grad) | reinterpret_cast<uintptr_t>(exp_avg) |
-                 reinterpret_cast<uintptr_t>(exp_avg_sq)) & 15) == 0, HG_ERR_INVALID_ARG, "hg_adam_step: buffers must be 16-byte aligned");
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    adam_tick_kernel<<<1, 1, 0, st>>>(state, lr, beta1, beta2);
+                 reinterpret_cast<uintptr_t>(exp_avg_sq)) & 15) == 0, HG_ERR_INVALID_ARG, "hg_adam_apply: buffers must be 16-byte aligned");
     const long long n4 = n / 4;
     long long blocks = (n4 + 255) / 256;
     const long long cap = (long long)sm_count() * 8;
     if (blocks > cap) blocks = cap;
-    adam_kernel<<<(unsigned)blocks, 256, 0, st>>>(param, grad, exp_avg, exp_avg_sq, n4, state, beta1, beta2, eps, grad_scale);
-    return check_launch("hg_adam_step");
+    adam_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(param, grad, exp_avg, exp_avg_sq, n4, state, beta1, beta2, eps,
+                                                                               grad_scale);
+    return check_launch("hg_adam_apply");
+}
+
+extern "C" int hg_adam_step(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, long long n, float *state,
+                            const float *lr, float beta1, float beta2, float eps, float grad_scale, void *stream)
+{
+    HG_REQUIRE(param && grad && exp_avg && exp_avg_sq && state && lr, HG_ERR_INVALID_ARG, "hg_adam_step: null pointer");
+    int rc = hg_adam_tick(state, lr, beta1, beta2, stream);
+    if (rc) return rc;
+    return hg_adam_apply(param, grad, exp_avg, exp_avg_sq, n, state, beta1, beta2, eps, grad_scale, stream);
 }

@@ -120,6 +120,8 @@ class _FlatGrads:
             self.offsets.append(o)
             o += pad(p.numel())
         self._handles, self._fired, self._counts = [], set(), {}
+        self.bucket_update = None           # see fire()
+        self._side, self._side_used = None, False
 
     def zero(self):
         self.flat.zero_()
@@ -146,15 +148,42 @@ class _FlatGrads:
 
     # ---- data-parallel exchange ---------------------------------------------------------------------
     def fire(self, i: int, world: int, after_calls: int = 1):
-        """Start the sum all-reduce of bucket i (asynchronously) once this has been called `after_calls` times in the
-        current step -- the hook the kernels' backward call when a bucket's last gradient has been written."""
+        """Bucket i's gradients are in the buffer (the hook the kernels' backward call; effective once it has been called
+        `after_calls` times in the current step).  Without `bucket_update`: start the bucket's asynchronous sum all-reduce.
+        With `bucket_update` (a callable (start, end), set by the trainer to FlatAdam.apply_range): all-reduce AND the
+        optimizer update of the bucket run on a side stream, stream-ordered behind the gradients, overlapping the rest of
+        the backward -- also on one GPU, where only the update is left."""
         self._counts[i] = self._counts.get(i, 0) + 1
-        if world <= 1 or i in self._fired or self._counts[i] < after_calls:
+        if i in self._fired or self._counts[i] < after_calls:
+            return
+        s, e = self.bucket_slices[i]
+        if self.bucket_update is not None:
+            self._fired.add(i)
+            if e > s:
+                cur = torch.cuda.current_stream(self.flat.device)
+                if self._side is None:
+                    self._side = torch.cuda.Stream(device=self.flat.device)
+                self._side.wait_stream(cur)
+                with torch.cuda.stream(self._side):
+                    if world > 1:
+                        dist.all_reduce(self.flat[s:e], op=dist.ReduceOp.SUM)      # stream-ordered on the side stream
+                    self.bucket_update(s, e)
+                self._side_used = True
+            return
+        if world <= 1:
             return
         self._fired.add(i)
-        s, e = self.bucket_slices[i]
         if e > s:
             self._handles.append(dist.all_reduce(self.flat[s:e], op=dist.ReduceOp.SUM, async_op=True))
+
+    def flush(self, world: int):
+        """`bucket_update` mode: exchange + update every bucket `fire` has not handled yet (the tail), then join the side
+        stream: afterwards all parameters of the network are updated on the current stream."""
+        for i in range(len(self.bucket_slices)):
+            self.fire(i, world, after_calls=0)
+        if self._side_used:
+            torch.cuda.current_stream(self.flat.device).wait_stream(self._side)
+            self._side_used = False
 
     def all_reduce_sum(self, world: int):
         """All-reduce (sum) whatever `fire` has not started yet, then wait for every bucket."""
@@ -208,6 +237,24 @@ class FlatAdam(torch.optim.Optimizer):
         _lib.call("hg_adam_step", P(self.flat_param), P(self.grads.flat), P(self.exp_avg), P(self.exp_avg_sq),
                   self.flat_param.numel(), P(self.kstate), P(g["lr"]), float(b1), float(b2), float(g["eps"]), float(grad_scale),
                   ops._stream())
+
+    # the same step bucket by bucket: tick() once (before the backward), apply_range() per gradient bucket
+    @torch.no_grad()
+    def tick(self):
+        g = self.param_groups[0]
+        b1, b2 = g["betas"]
+        _lib.call("hg_adam_tick", ops._ptr(self.kstate), ops._ptr(g["lr"]), float(b1), float(b2), ops._stream())
+
+    @torch.no_grad()
+    def apply_range(self, start: int, end: int, grad_scale: float = 1.0):
+        if end <= start:
+            return
+        g = self.param_groups[0]
+        b1, b2 = g["betas"]
+        P = ops._ptr
+        _lib.call("hg_adam_apply", P(self.flat_param[start:end]), P(self.grads.flat[start:end]), P(self.exp_avg[start:end]),
+                  P(self.exp_avg_sq[start:end]), end - start, P(self.kstate), float(b1), float(b2), float(g["eps"]),
+                  float(grad_scale), ops._stream())
 
     def load_state_dict(self, state_dict):
         """Accepts a torch.optim.Adam (or FlatAdam) state dict over the same parameters in the same order."""
@@ -302,7 +349,19 @@ class HologanTrainer:
             kw = dict(betas=(cfg.beta1, cfg.beta2), fused=cuda, capturable=cuda)
             self.opt_d = torch.optim.Adam(self.d_grads.params, lr=lr, **kw)
             self.opt_g = torch.optim.Adam(self.g_grads.params, lr=lr.clone() if cuda else lr, **kw)
-        if cuda and self.world > 1 and os.environ.get("HG_NO_GRAD_OVERLAP", "0") in ("", "0"):   # A/B switch: one all-reduce after the backward
+        # Bucket hooks: the all-reduce (world > 1) and, with the flat Adam, the optimizer update of a gradient bucket run on a
+        # side stream as soon as the bucket is final, overlapping the rest of the backward.  A/B switches:
+        # HG_NO_GRAD_OVERLAP=1 (one exchange + one update after the backward), HG_ADAM_OVERLAP=0 / 1 (update behind the
+        # buckets off / on; default: on for world > 1 only -- on one GPU the HBM-bound update running beside the backward
+        # kernels measured 1.1 % slower than one update at the end, profiles/r02H_adam_overlap.txt).
+        overlap = cuda and os.environ.get("HG_NO_GRAD_OVERLAP", "0") in ("", "0")
+        ao = os.environ.get("HG_ADAM_OVERLAP", "")
+        self._adam_overlap = overlap and self._flat_adam and (ao == "1" or (ao == "" and self.world > 1))
+        if self._adam_overlap:
+            inv = 1.0 / self.world
+            self.d_grads.bucket_update = lambda s, e: self.opt_d.apply_range(s, e, inv)
+            self.g_grads.bucket_update = lambda s, e: self.opt_g.apply_range(s, e, inv)
+        if overlap and (self.world > 1 or self._adam_overlap):
             w = self.world
             gen.block3.convTranspose.weight._hg_grad_ready = lambda: self.g_grads.fire(0, w)
             gen.convTranspose2d1.weight._hg_grad_ready = lambda: self.g_grads.fire(1, w)
@@ -437,10 +496,19 @@ class HologanTrainer:
         for p in self.discriminator.parameters():
             p.requires_grad_(idx == 0)
         grads.begin()
-        loss = self.training_step(real, z, view, idx)
-        loss.backward()
-        grads.finish()
-        if self._flat_adam:
+        if self._adam_overlap:
+            opt.tick()                                  # step counter / bias corrections once, before any bucket update
+            loss = self.training_step(real, z, view, idx)
+            loss.backward()                             # hooks: buckets exchanged + updated on the side stream
+            grads.finish()
+            grads.flush(self.world)                     # the tail, then join
+        else:
+            loss = self.training_step(real, z, view, idx)
+            loss.backward()
+            grads.finish()
+        if self._adam_overlap:
+            pass
+        elif self._flat_adam:
             grads.all_reduce_sum(self.world)            # buckets fired during the backward + the tail; 1 / world goes into Adam
             opt.step(grad_scale=1.0 / self.world)
         else:

@@ -102,6 +102,35 @@ def test_cuda_graph_step_matches_eager():
 
 
 @pytest.mark.parametrize("graphs", [False, True])
+def test_bucketwise_adam_overlap_is_transparent(graphs, monkeypatch):
+    """Gradient buckets are updated by hg_adam_apply on a side stream as soon as they are final (FlatAdam.tick +
+    apply_range from the backward hooks); losses and parameters must equal the single hg_adam_step after the backward
+    bit for bit."""
+    cfg = HologanConfig(batch_size=8)
+    monkeypatch.setenv("HG_ADAM_OVERLAP", "1")          # default on for world > 1 only
+    a = HologanTrainer(cfg, device=DEV, seed=7)
+    monkeypatch.setenv("HG_ADAM_OVERLAP", "0")
+    b = HologanTrainer(cfg, device=DEV, seed=7)
+    monkeypatch.delenv("HG_ADAM_OVERLAP")
+    assert a._adam_overlap and not b._adam_overlap
+    if graphs:
+        a.enable_cuda_graphs(8)
+        b.enable_cuda_graphs(8)
+    gen = torch.Generator().manual_seed(2)
+    for i in range(6):
+        real = (torch.rand(8, 3, 64, 64, generator=gen) * 2 - 1).to(DEV)
+        z = (torch.rand(8, 128, generator=gen) * 2 - 1).to(DEV)
+        view = orc.sample_view(8, np.random.RandomState(i))
+        la, lb = a.step(real, i, z=z, view=view), b.step(real, i, z=z, view=view)
+        assert la.item() == lb.item(), (i, la.item(), lb.item())
+    torch.cuda.synchronize()
+    for pa, pb in zip(list(a.generator.parameters()) + list(a.discriminator.parameters()),
+                      list(b.generator.parameters()) + list(b.discriminator.parameters())):
+        assert torch.equal(pa, pb)
+    assert float(a.opt_g.kstate[0]) == float(b.opt_g.kstate[0]) == 4 and float(a.opt_d.kstate[0]) == 2
+
+
+@pytest.mark.parametrize("graphs", [False, True])
 def test_spectral_norm_prefetch_is_transparent(graphs):
     """The discriminator's power iterations run ahead on a side stream (Discriminator.prefetch_spectral_norm); u / v and
     the losses must be exactly what the in-line iteration gives -- same kernels on the same data, only earlier."""
