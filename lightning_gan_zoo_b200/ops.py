@@ -8,6 +8,7 @@ memory, streams and autograd bookkeeping here; all arithmetic on the path runs i
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import Optional, Tuple
 
 import numpy as np
@@ -379,6 +380,44 @@ def _direct_grad_target(param, shape) -> Tuple[Optional[Tensor], bool]:
     return g, overwrite
 
 
+# Side streams for work that runs BESIDE the backward's critical path.  "wgrad": the weight-gradient GEMMs (only the
+# optimizer needs their result).  "comm": the data-parallel bucket exchange and the bucket-wise optimizer update
+# (training._FlatGrads), which waits for the wgrad stream before it touches a bucket -- two streams, so that a wgrad never
+# queues behind a collective.
+_SIDE_STREAMS = {}
+_SIDE_PENDING = set()
+WGRAD_SIDE_STREAM = os.environ.get("HG_WGRAD_SIDE", "1") not in ("", "0")     # A/B switch (profiles/r02I_wgrad_side.txt)
+
+
+def _dev_key(device) -> int:
+    dev = torch.device(device)
+    return dev.index if dev.index is not None else torch.cuda.current_device()
+
+
+def side_stream(device, which: str = "wgrad") -> "torch.cuda.Stream":
+    key = (_dev_key(device), which)
+    st = _SIDE_STREAMS.get(key)
+    if st is None:
+        st = _SIDE_STREAMS[key] = torch.cuda.Stream(device=key[0])
+    return st
+
+
+def side_stream_mark(device, which: str = "wgrad") -> None:
+    _SIDE_PENDING.add((_dev_key(device), which))
+
+
+def join_side_stream(device, which: str = "wgrad", into=None) -> None:
+    """Make `into` (default: the current stream) wait for everything enqueued on the side stream so far (no-op if the side
+    stream has not been used since the last join into the current stream)."""
+    if torch.device(device).type != "cuda" or not _SIDE_PENDING:
+        return
+    key = (_dev_key(device), which)
+    if key in _SIDE_PENDING:
+        (into if into is not None else torch.cuda.current_stream(key[0])).wait_stream(_SIDE_STREAMS[key])
+        if into is None:
+            _SIDE_PENDING.discard(key)
+
+
 def _grad_ready(param) -> None:
     """A parameter's gradient has just been written into its flat-buffer view: run the owner's hook, if any
     (HologanTrainer starts the bucket's data-parallel all-reduce from it, overlapping the rest of the backward)."""
@@ -441,12 +480,25 @@ class _ConvT(torch.autograd.Function):
                 dy, _ = act_bwd_bias(y, dy, neg_slope, False)
         if want_db and db is None:
             db = dy.reshape(-1, nclass, cout).float().sum(dim=(0, 1))
+        target, overwrite = _direct_grad_target(ctx.weight_param, wshape) if ctx.needs_input_grad[1] else (None, False)
+        on_side = WGRAD_SIDE_STREAM and target is not None and ctx.needs_input_grad[0]
+        if on_side:
+            # The weight gradient goes straight into the owner's flat buffer and only the optimizer reads it: fork it onto
+            # the side stream BEFORE the dgrad is enqueued, so the two GEMMs (and whatever the backward launches next) run
+            # concurrently.  The owner joins the side stream before its optimizer step (training._FlatGrads.finish).
+            cur, side = torch.cuda.current_stream(dy.device), side_stream(dy.device)
+            side.wait_stream(cur)                       # dy is final on the current stream
+            with torch.cuda.stream(side):
+                convt_wgrad(x_cl, dy, wshape, ndim, kernel, perm, accumulate_into=target, overwrite=overwrite)
+            x_cl.record_stream(side)
+            dy.record_stream(side)
+            side_stream_mark(dy.device)
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x_cl)
             _lib.call("hg_convt_dgrad", _ptr(dy), _ptr(wd), _ptr(dx), b, cin, cout, ndim, size, kernel, _stream())
         if ctx.needs_input_grad[1]:
-            target, overwrite = _direct_grad_target(ctx.weight_param, wshape)
-            dw = convt_wgrad(x_cl, dy, wshape, ndim, kernel, perm, accumulate_into=target, overwrite=overwrite)
+            if not on_side:
+                dw = convt_wgrad(x_cl, dy, wshape, ndim, kernel, perm, accumulate_into=target, overwrite=overwrite)
             _grad_ready(ctx.weight_param)
         return dx, dw, db, None, None, None, None, None
 

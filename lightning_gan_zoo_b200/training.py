@@ -135,6 +135,8 @@ class _FlatGrads:
         self._handles, self._fired, self._counts = [], set(), {}
 
     def finish(self):
+        if self.flat.is_cuda:
+            ops.join_side_stream(self.flat.device)      # weight-gradient GEMMs that ran beside the backward
         src, dst = [], []
         for p, view in zip(self.params, self.views):
             g = p.grad
@@ -162,8 +164,9 @@ class _FlatGrads:
             if e > s:
                 cur = torch.cuda.current_stream(self.flat.device)
                 if self._side is None:
-                    self._side = torch.cuda.Stream(device=self.flat.device)
+                    self._side = ops.side_stream(self.flat.device, "comm")
                 self._side.wait_stream(cur)
+                ops.join_side_stream(self.flat.device, "wgrad", into=self._side)    # a side-stream wgrad may have produced this bucket
                 with torch.cuda.stream(self._side):
                     if world > 1:
                         dist.all_reduce(self.flat[s:e], op=dist.ReduceOp.SUM)      # stream-ordered on the side stream
@@ -174,6 +177,7 @@ class _FlatGrads:
             return
         self._fired.add(i)
         if e > s:
+            ops.join_side_stream(self.flat.device)      # a side-stream wgrad may have produced this bucket
             self._handles.append(dist.all_reduce(self.flat[s:e], op=dist.ReduceOp.SUM, async_op=True))
 
     def flush(self, world: int):

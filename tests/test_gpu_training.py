@@ -131,6 +131,32 @@ def test_bucketwise_adam_overlap_is_transparent(graphs, monkeypatch):
 
 
 @pytest.mark.parametrize("graphs", [False, True])
+def test_side_stream_wgrad_is_transparent(graphs, monkeypatch):
+    """ops.WGRAD_SIDE_STREAM: the generator's weight-gradient GEMMs run on a side stream beside the backward's dgrad /
+    AdaIN chain (only the optimizer reads their result).  Same kernels on the same data: bit-identical training."""
+    from lightning_gan_zoo_b200 import ops as hops
+    cfg = HologanConfig(batch_size=8)
+    gen = torch.Generator().manual_seed(3)
+    batches = [((torch.rand(8, 3, 64, 64, generator=gen) * 2 - 1).to(DEV), (torch.rand(8, 128, generator=gen) * 2 - 1).to(DEV),
+                orc.sample_view(8, np.random.RandomState(i))) for i in range(6)]
+
+    def run(side):
+        monkeypatch.setattr(hops, "WGRAD_SIDE_STREAM", side)
+        t = HologanTrainer(cfg, device=DEV, seed=9)
+        if graphs:
+            t.enable_cuda_graphs(8)
+        losses = [t.step(real, i, z=z, view=view).item() for i, (real, z, view) in enumerate(batches)]
+        torch.cuda.synchronize()
+        return losses, [p.detach().clone() for p in t.generator.parameters()]
+
+    la, pa = run(True)
+    lb, pb = run(False)
+    assert la == lb
+    for u, v in zip(pa, pb):
+        assert torch.equal(u, v)
+
+
+@pytest.mark.parametrize("graphs", [False, True])
 def test_spectral_norm_prefetch_is_transparent(graphs):
     """The discriminator's power iterations run ahead on a side stream (Discriminator.prefetch_spectral_norm); u / v and
     the losses must be exactly what the in-line iteration gives -- same kernels on the same data, only earlier."""
