@@ -1025,32 +1025,50 @@ class _Conv5s2SN(torch.autograd.Function):
         b, size, cin, cout, nbytes = ctx.meta
         dy = dy.contiguous()
         dev = dy.device
-        ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=dev)
         dx = dw = None
+        target = None
+        if ctx.needs_input_grad[1] and state is not None and ctx.weight_param is not None:
+            target = _direct_grad_target(ctx.weight_param, w.shape)[0]
+        direct = target is not None and target.stride() == w.stride()
+
+        def weight_grad():
+            ws2 = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=dev)
+            dwn = torch.empty_like(w)                                   # gradient w.r.t. the normalised weight
+            _lib.call("hg_conv5s2_dw", _ptr(dy), _ptr(x_s2d), _ptr(dwn), _ptr(ws2), nbytes, b, cin, cout, size, 0, _stream())
+            if state is None:
+                return dwn
+            dw_orig = target if direct else torch.empty_like(w)
+            lib = _lib.load()
+            co_arr, ci_arr, t_arr = _c_array(ctypes.c_int, [cout]), _c_array(ctypes.c_int, [cin]), _c_array(ctypes.c_int, [25])
+            sn_bytes = lib.hg_spectral_norm_workspace_bytes(1, co_arr, ci_arr, t_arr)
+            sn_ws = torch.empty(sn_bytes, dtype=torch.uint8, device=dev)
+            vp = ctypes.c_void_p
+            _lib.call("hg_spectral_norm_bwd", 1, _c_array(vp, [dwn.data_ptr()]), _c_array(vp, [w.data_ptr()]),
+                      _c_array(vp, [state.data_ptr()]), _c_array(vp, [dw_orig.data_ptr()]), co_arr, ci_arr, t_arr,
+                      int(direct), HG_F32, _ptr(sn_ws), sn_bytes, _stream())
+            return None if direct else dw_orig
+
+        # the weight gradient (conv dw + spectral-norm backward) adds straight into the owner's flat buffer: it runs on the
+        # wgrad side stream beside the dx chain (see _ConvT.backward); the two passes of a D step stay ordered on that stream
+        on_side = WGRAD_SIDE_STREAM and direct and ctx.needs_input_grad[0]
+        if on_side:
+            cur, side = torch.cuda.current_stream(dev), side_stream(dev)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                weight_grad()
+            for t in (dy, x_s2d, state):
+                t.record_stream(side)
+            side_stream_mark(dev)
         if ctx.needs_input_grad[0]:
+            ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=dev)
             dx = torch.empty_like(x_s2d)
             inv_sigma = ctypes.c_void_p(0 if state is None else state.data_ptr() + 4)
             _lib.call("hg_conv5s2_dx", _ptr(dy), _ptr(wt), inv_sigma, _ptr(dx), _ptr(ws), nbytes, b, cin, cout, size, _stream())
         if ctx.needs_input_grad[1]:
-            dwn = torch.empty_like(w)                               # gradient w.r.t. the normalised weight
-            _lib.call("hg_conv5s2_dw", _ptr(dy), _ptr(x_s2d), _ptr(dwn), _ptr(ws), nbytes, b, cin, cout, size, 0, _stream())
-            if state is None:
-                dw = dwn
-            else:
-                target = _direct_grad_target(ctx.weight_param, w.shape)[0] if ctx.weight_param is not None else None
-                direct = target is not None and target.stride() == w.stride()
-                dw_orig = target if direct else torch.empty_like(w)
-                lib = _lib.load()
-                co_arr, ci_arr, t_arr = _c_array(ctypes.c_int, [cout]), _c_array(ctypes.c_int, [cin]), _c_array(ctypes.c_int, [25])
-                sn_bytes = lib.hg_spectral_norm_workspace_bytes(1, co_arr, ci_arr, t_arr)
-                sn_ws = torch.empty(sn_bytes, dtype=torch.uint8, device=dev)
-                vp = ctypes.c_void_p
-                _lib.call("hg_spectral_norm_bwd", 1, _c_array(vp, [dwn.data_ptr()]), _c_array(vp, [w.data_ptr()]),
-                          _c_array(vp, [state.data_ptr()]), _c_array(vp, [dw_orig.data_ptr()]), co_arr, ci_arr, t_arr,
-                          int(direct), HG_F32, _ptr(sn_ws), sn_bytes, _stream())
-                dw = None if direct else dw_orig
-                if direct:
-                    _grad_ready(ctx.weight_param)
+            if not on_side:
+                dw = weight_grad()
+            if direct:
+                _grad_ready(ctx.weight_param)
         return dx, dw, None
 
 
