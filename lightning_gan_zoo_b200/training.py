@@ -359,6 +359,15 @@ class HologanTrainer:
         # buckets off / on; default: on for world > 1 only -- on one GPU the HBM-bound update running beside the backward
         # kernels measured 1.1 % slower than one update at the end, profiles/r02H_adam_overlap.txt).
         overlap = cuda and os.environ.get("HG_NO_GRAD_OVERLAP", "0") in ("", "0")
+        # D(real) on a side stream in the D step (needs the wgrad side stream: both passes' weight gradients are ordered there);
+        # HG_D_REAL_SIDE=0 switches it off
+        self._d_real_side = (cuda and ops.WGRAD_SIDE_STREAM and self._sn_prefetch and compute_dtype == torch.bfloat16
+                             and os.environ.get("HG_D_REAL_SIDE", "1") not in ("", "0"))
+        if self._d_real_side:
+            # leaf gradients now arrive from two streams on purpose (autograd synchronises them)
+            quiet = getattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch", None)
+            if quiet is not None:
+                quiet(False)
         ao = os.environ.get("HG_ADAM_OVERLAP", "")
         self._adam_overlap = overlap and self._flat_adam and (ao == "1" or (ao == "" and self.world > 1))
         if self._adam_overlap:
@@ -416,11 +425,28 @@ class HologanTrainer:
             # generator's forward on a side stream
             self.discriminator.prefetch_spectral_norm(2 if optimizer_idx == 0 else 1)
         if optimizer_idx == 0:
-            with torch.no_grad(), self._autocast():     # the D step detaches fake (:221): no G graph is needed
-                fake = self.generator(z, view_in=view)
-            with self._autocast():
-                d_real, _ = self.discriminator(real)
-                d_fake, z_pred = self.discriminator(fake)
+            if cuda and self._d_real_side:
+                # D(real) does not depend on the generator: its forward runs on a side stream beside the generator's
+                # (no-grad) forward, and autograd then runs its backward on that stream beside D(fake)'s.  The discriminator's
+                # kernels at B = 64 fill a fraction of the GPU (<= 148 CTAs, 5-30 us each), so the two chains overlap
+                # almost for free.  The spectral-norm states are consumed in the same order (real first).
+                cur, side = torch.cuda.current_stream(self.device), ops.side_stream(self.device, "dreal")
+                side.wait_stream(cur)
+                with torch.cuda.stream(side), self._autocast():
+                    d_real, _ = self.discriminator(real)
+                real.record_stream(side)
+                with torch.no_grad(), self._autocast():
+                    fake = self.generator(z, view_in=view)
+                with self._autocast():
+                    d_fake, z_pred = self.discriminator(fake)
+                cur.wait_stream(side)
+                d_real.record_stream(cur)
+            else:
+                with torch.no_grad(), self._autocast():     # the D step detaches fake (:221): no G graph is needed
+                    fake = self.generator(z, view_in=view)
+                with self._autocast():
+                    d_real, _ = self.discriminator(real)
+                    d_fake, z_pred = self.discriminator(fake)
             if cuda:                                    # both losses + their gradients: one launch each way
                 loss, parts = ops.hologan_d_loss(d_real, d_fake, z_pred, z)
                 self.logs["train/d_loss"], self.logs["train/q_loss"] = parts[0], parts[1]
@@ -504,11 +530,15 @@ class HologanTrainer:
             opt.tick()                                  # step counter / bias corrections once, before any bucket update
             loss = self.training_step(real, z, view, idx)
             loss.backward()                             # hooks: buckets exchanged + updated on the side stream
+            if idx == 0 and self._d_real_side:
+                torch.cuda.current_stream(self.device).wait_stream(ops.side_stream(self.device, "dreal"))
             grads.finish()
             grads.flush(self.world)                     # the tail, then join
         else:
             loss = self.training_step(real, z, view, idx)
             loss.backward()
+            if idx == 0 and self._d_real_side:
+                torch.cuda.current_stream(self.device).wait_stream(ops.side_stream(self.device, "dreal"))
             grads.finish()
         if self._adam_overlap:
             pass

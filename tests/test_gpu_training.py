@@ -157,6 +157,33 @@ def test_side_stream_wgrad_is_transparent(graphs, monkeypatch):
 
 
 @pytest.mark.parametrize("graphs", [False, True])
+def test_d_real_side_stream_is_transparent(graphs):
+    """D step: D(real) forward / backward on a side stream beside the generator's forward and D(fake)'s backward.  Losses,
+    parameters and the spectral-norm vectors must be those of the serial order, bit for bit."""
+    cfg = HologanConfig(batch_size=8)
+    a = HologanTrainer(cfg, device=DEV, seed=11)
+    b = HologanTrainer(cfg, device=DEV, seed=11)
+    assert a._d_real_side
+    b._d_real_side = False
+    if graphs:
+        a.enable_cuda_graphs(8)
+        b.enable_cuda_graphs(8)
+    gen = torch.Generator().manual_seed(4)
+    for i in range(7):
+        real = (torch.rand(8, 3, 64, 64, generator=gen) * 2 - 1).to(DEV)
+        z = (torch.rand(8, 128, generator=gen) * 2 - 1).to(DEV)
+        view = orc.sample_view(8, np.random.RandomState(i))
+        la, lb = a.step(real, i, z=z, view=view), b.step(real, i, z=z, view=view)
+        assert la.item() == lb.item(), (i, la.item(), lb.item())
+    torch.cuda.synchronize()
+    for pa, pb in zip(list(a.generator.parameters()) + list(a.discriminator.parameters()),
+                      list(b.generator.parameters()) + list(b.discriminator.parameters())):
+        assert torch.equal(pa, pb)
+    for blk_a, blk_b in zip(a.discriminator.blocks, b.discriminator.blocks):
+        assert torch.equal(blk_a.conv2d.weight_u, blk_b.conv2d.weight_u)
+
+
+@pytest.mark.parametrize("graphs", [False, True])
 def test_spectral_norm_prefetch_is_transparent(graphs):
     """The discriminator's power iterations run ahead on a side stream (Discriminator.prefetch_spectral_norm); u / v and
     the losses must be exactly what the in-line iteration gives -- same kernels on the same data, only earlier."""
