@@ -255,8 +255,9 @@ int hg_linear_relu_group_bwd(int layers, const float *z, const float *const *out
 /* ---- a11: final_layer + tanh  (core/models/hologan_generator.py:69-75,141-142, img_size 64) ---------
  *   out (B,Cout,S,S) fp32 NCHW = tanh(conv2d(x, w, bias, k3, p1)); x (B,S,S,Cin) bf16 NHWC,
  *   w torch (Cout,Cin,3,3) fp32.  Cout <= 4, Cin = 8 * 2^k <= 256.  Direct convolution (bandwidth-bound).
- *   backward: dx (B,S,S,Cin) bf16 (may be NULL), dw, dbias from dout (B,Cout,S,S) fp32; deterministic
- *   two-stage reduction through `workspace`. */
+ *   backward: dx (B,S,S,Cin) bf16 (may be NULL), dw, dbias (both NULL: input gradient only -- the two halves are
+ *   independent and may be issued as two calls on two streams, each with its own workspace) from dout (B,Cout,S,S) fp32;
+ *   deterministic two-stage reduction through `workspace`. */
 int hg_final_conv_tanh_fwd(const void *x, const float *w, const float *bias, float *out, int batch, int cin, int cout,
                            int size, void *stream);
 long long hg_final_conv_tanh_bwd_workspace_bytes(int batch, int cin, int cout, int size);

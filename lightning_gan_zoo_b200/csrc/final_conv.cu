@@ -442,7 +442,9 @@ extern "C" int hg_final_conv_tanh_bwd(const void *x, const float *w, const float
                                       float *dbias, void *workspace, long long workspace_bytes, int batch, int cin, int cout,
                                       int size, void *stream)
 {
-    HG_REQUIRE(x && w && out && dout && dw && dbias && workspace, HG_ERR_INVALID_ARG, "hg_final_conv_tanh_bwd: null pointer");
+    HG_REQUIRE(x && w && out && dout && workspace, HG_ERR_INVALID_ARG, "hg_final_conv_tanh_bwd: null pointer");
+    HG_REQUIRE((dw == nullptr) == (dbias == nullptr), HG_ERR_INVALID_ARG, "hg_final_conv_tanh_bwd: dw and dbias must both be given or both be null");
+    HG_REQUIRE(dx || dw, HG_ERR_INVALID_ARG, "hg_final_conv_tanh_bwd: nothing to compute");
     int rc = final_check("hg_final_conv_tanh_bwd", batch, cin, cout, size);
     if (rc) return rc;
     HG_REQUIRE(workspace_bytes >= hg_final_conv_tanh_bwd_workspace_bytes(batch, cin, cout, size), HG_ERR_INVALID_ARG,
@@ -473,6 +475,7 @@ extern "C" int hg_final_conv_tanh_bwd(const void *x, const float *w, const float
         rc = check_launch("hg_final_conv_tanh_bwd(x)");
         if (rc) return rc;
     }
+    if (!dw) return HG_OK;                              // input gradient only (the caller runs the weight part elsewhere)
     const int groups = g.L >= 32 ? kFcThreads / g.L : kFcThreads / 32;
     size_t wsmem = tile_floats > (size_t)groups * cin ? tile_floats : (size_t)groups * cin;
     wsmem *= sizeof(float);

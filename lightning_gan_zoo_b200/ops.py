@@ -703,6 +703,7 @@ class _FinalConvTanh(torch.autograd.Function):
         out = torch.empty((b, cout, s, s), dtype=torch.float32, device=x_cl.device)
         _lib.call("hg_final_conv_tanh_fwd", _ptr(x_cl), _ptr(w), _ptr(bb), _ptr(out), b, cin, cout, s, _stream())
         ctx.save_for_backward(x_cl, w, out)
+        ctx.params = (weight if isinstance(weight, torch.nn.Parameter) else None, bias if isinstance(bias, torch.nn.Parameter) else None)
         return out
 
     @staticmethod
@@ -711,11 +712,29 @@ class _FinalConvTanh(torch.autograd.Function):
         b, s, cin = x_cl.shape[0], x_cl.shape[1], x_cl.shape[3]
         cout = w.shape[0]
         dout = dout.float().contiguous()
+        dev = x_cl.device
         nbytes = _lib.load().hg_final_conv_tanh_bwd_workspace_bytes(b, cin, cout, s)
-        ws = torch.empty(nbytes, dtype=torch.uint8, device=x_cl.device)
         dx = torch.empty_like(x_cl) if ctx.needs_input_grad[0] else None
+        # weight / bias gradient straight into the owner's flat buffer on the wgrad side stream (see _ConvT.backward)
+        tw, ow = _direct_grad_target(ctx.params[0], w.shape)
+        tb, ob = _direct_grad_target(ctx.params[1], (cout,))
+        if WGRAD_SIDE_STREAM and dx is not None and tw is not None and tb is not None and ow and ob:
+            cur, side = torch.cuda.current_stream(dev), side_stream(dev)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                ws2 = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+                _lib.call("hg_final_conv_tanh_bwd", _ptr(x_cl), _ptr(w), _ptr(out), _ptr(dout), _ptr(None), _ptr(tw), _ptr(tb),
+                          _ptr(ws2), nbytes, b, cin, cout, s, _stream())
+            for t in (x_cl, out, dout):
+                t.record_stream(side)
+            side_stream_mark(dev)
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            _lib.call("hg_final_conv_tanh_bwd", _ptr(x_cl), _ptr(w), _ptr(out), _ptr(dout), _ptr(dx), _ptr(None), _ptr(None),
+                      _ptr(ws), nbytes, b, cin, cout, s, _stream())
+            return dx, None, None
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         dw = torch.empty_like(w)
-        db = torch.empty(cout, dtype=torch.float32, device=x_cl.device)
+        db = torch.empty(cout, dtype=torch.float32, device=dev)
         _lib.call("hg_final_conv_tanh_bwd", _ptr(x_cl), _ptr(w), _ptr(out), _ptr(dout), _ptr(dx), _ptr(dw), _ptr(db),
                   _ptr(ws), nbytes, b, cin, cout, s, _stream())
         return dx, dw, db
