@@ -1381,6 +1381,14 @@ static void conv5_fwd_plan(long long m_total, int cout, Conv5Plan &pl)
     pl.n_tiles = cout / bn;
     const int tiles = pl.m_tiles * pl.n_tiles;
     int ks = sm_count() / tiles;                        // never more CTAs than SMs: a second partial wave doubles the time
+    // Re-measured after the epilogue / producer fixes (profiles/r02M_dconv_split.txt): the fp32 partials + reduce pass only
+    // pay when there are very few row tiles (B = 64: block 2, 8 tiles: 16.6 vs 20.9 us); with >= 16 the unsplit kernel wins
+    // (block 1: 14.2 vs 20.5 us; at 128 x 128: 17.9 vs 30.4 and 21.8 vs 29.1 us)
+    if (pl.m_tiles > 8) ks = 1;
+    if (ks <= 1) {                                      // unsplit: narrow the N tile until the grid fills the SMs instead
+        pl.bn = pick_bn_for_grid(cout, pl.m_tiles);
+        pl.n_tiles = cout / pl.bn;
+    }
     if (ks < 1) ks = 1;
     if (ks > 12) ks = 12;
     pl.nsplit[0] = pl.max_split = ks;
