@@ -71,6 +71,8 @@ const char *hg_last_error(void);
  *   ADAIN_CL_RING        (1)   chunked channels-last AdaIN backward: rows stream through per-thread cp.async rings in shared
  *                              memory (3 stages of 2 rows x 2 tensors in flight per thread) instead of register-staged loads;
  *                              bit-identical results; B200: 45.5 -> 40.4 us (block2), 49.8 -> 44.4 (block3), +1.2 % step
+ *   ADAIN_CL_SMALL_REGS  (1)   one-CTA-per-sample channels-last norm kernels with 9-16 rows per thread keep their rows in
+ *                              registers: one load pass for statistics + normalise / gradient (D block 0 backward 16.2 -> 10.8 us)
  *   TAPGEMM_DUAL         (-1)  -1 auto; 0 / 1: force one / two tap-GEMM CTAs per SM
  *   FINAL_CONV_MMA       (7)   bit mask of final-layer passes on the mma.sync kernels (1 fwd, 2 dx, 4 dw)
  *   ROTATE_SLAB32        (1)   32^3 rotate forward on source-slab tiles (0: per-channel slab kernel)

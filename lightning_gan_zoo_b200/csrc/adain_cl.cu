@@ -539,6 +539,156 @@ __global__ void __launch_bounds__(kClThreads, 3) adain_cl_bwd_apply_kernel(const
 }
 
 
+// ---- small instances, register resident -------------------------------------------------------------------
+// One CTA per sample and at most kSmallRows rows per thread (the discriminator's three InstanceNorm + LeakyReLU sites:
+// 256 x 128, 64 x 256, 16 x 512 at B = 64).  The fused kernels above walk their rows twice in batches of 4-8 loads, i.e.
+// 4-8 dependent memory round trips on a grid that cannot hide them (64 CTAs); here every row of the thread is loaded ONCE,
+// all loads in flight together, and both the statistics and the normalise / gradient pass run from registers.  Same
+// arithmetic in the same order as the fused kernels (bit-identical; tests/test_gpu_channels_last.py).
+constexpr int kSmallRows = 16;
+
+__global__ void __launch_bounds__(kClThreads, 1) adain_cl_small_fwd_kernel(const __nv_bfloat16 *__restrict__ x,
+                                                                         const float *__restrict__ scale,
+                                                                         const float *__restrict__ bias,
+                                                                         __nv_bfloat16 *__restrict__ y, float *__restrict__ save_mean,
+                                                                         float *__restrict__ save_rstd, ClGeom g, int sbs, float eps,
+                                                                         float slope)
+{
+    __shared__ float red[kClThreads * 16];
+    const int cs = threadIdx.x % g.lanes, rs = threadIdx.x / g.lanes;
+    const int b = blockIdx.x;
+    const __nv_bfloat16 *xb = x + (size_t)b * g.N * g.C + cs * 8;
+    uint4 raw[kSmallRows];
+#pragma unroll
+    for (int u = 0; u < kSmallRows; ++u) {
+        const int rr = rs + u * g.rows_per_pass;
+        if (rr < g.N) raw[u] = __ldg(reinterpret_cast<const uint4 *>(xb + (size_t)rr * g.C));
+    }
+    float piv[8], s1[8], s2[8];
+    unpack8(__ldg(reinterpret_cast<const uint4 *>(xb)), piv);           // pivot K = the sample's first row
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
+#pragma unroll
+    for (int u = 0; u < kSmallRows; ++u) {
+        if (rs + u * g.rows_per_pass < g.N) {
+            float f[8];
+            unpack8(raw[u], f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float d = f[j] - piv[j];
+                s1[j] += d;
+                s2[j] = fmaf(d, d, s2[j]);
+            }
+        }
+    }
+    cta_rowslot_sum(s1, s2, red, g.lanes, g.rows_per_pass, cs, rs);
+    float mean[8], rstd[8];
+    const float inv_n = 1.f / (float)g.N;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float d = s1[j] * inv_n;
+        mean[j] = piv[j] + d;
+        const float var = fmaxf(s2[j] - s1[j] * d, 0.f) / (float)g.Nvar;
+        rstd[j] = __frsqrt_rn(var + eps);
+    }
+    if (rs == 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            save_mean[(size_t)b * g.C + cs * 8 + j] = mean[j];
+            save_rstd[(size_t)b * g.C + cs * 8 + j] = rstd[j];
+        }
+    }
+    float a[8], c[8];
+    affine_coeffs(scale, bias, b, sbs, cs * 8, mean, rstd, a, c);
+    __nv_bfloat16 *yb = y + (size_t)b * g.N * g.C + cs * 8;
+#pragma unroll
+    for (int u = 0; u < kSmallRows; ++u) {
+        const int rr = rs + u * g.rows_per_pass;
+        if (rr < g.N) {
+            float f[8];
+            unpack8(raw[u], f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float p = fmaf(f[j], a[j], c[j]);
+                f[j] = p > 0.f ? p : p * slope;
+            }
+            st_stream_16(yb + (size_t)mapped_row(rr, g) * g.C, pack8(f));
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kClThreads, 1) adain_cl_small_bwd_kernel(const __nv_bfloat16 *__restrict__ x,
+                                                                         const __nv_bfloat16 *__restrict__ dy,
+                                                                         const float *__restrict__ scale,
+                                                                         const float *__restrict__ bias,
+                                                                         const float *__restrict__ save_mean,
+                                                                         const float *__restrict__ save_rstd,
+                                                                         __nv_bfloat16 *__restrict__ dx, float *__restrict__ dscale,
+                                                                         float *__restrict__ dbias, ClGeom g, int sbs, int dsbs,
+                                                                         float slope)
+{
+    __shared__ float red[kClThreads * 16];
+    const int cs = threadIdx.x % g.lanes, rs = threadIdx.x / g.lanes;
+    const int b = blockIdx.x;
+    const size_t base = (size_t)b * g.N * g.C + cs * 8;
+    uint4 xr[kSmallRows], gr[kSmallRows];
+#pragma unroll
+    for (int u = 0; u < kSmallRows; ++u) {
+        const int rr = rs + u * g.rows_per_pass;
+        if (rr < g.N) {
+            xr[u] = __ldg(reinterpret_cast<const uint4 *>(x + base + (size_t)rr * g.C));
+            gr[u] = __ldg(reinterpret_cast<const uint4 *>(dy + base + (size_t)mapped_row(rr, g) * g.C));
+        }
+    }
+    ClStyle st;
+    load_style(st, scale, bias, save_mean, save_rstd, b, g.C, sbs, cs * 8);
+    float sg[8], sgx[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sg[j] = sgx[j] = 0.f;
+#pragma unroll
+    for (int u = 0; u < kSmallRows; ++u) {
+        if (rs + u * g.rows_per_pass < g.N) {
+            float xf[8], gf[8];
+            unpack8(xr[u], xf);
+            unpack8(gr[u], gf);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float gg = fmaf(xf[j], st.a[j], st.c[j]) > 0.f ? gf[j] : gf[j] * slope;
+                sg[j] += gg;
+                sgx[j] = fmaf(gg, xf[j] - st.mean[j], sgx[j]);
+            }
+        }
+    }
+    cta_rowslot_sum(sg, sgx, red, g.lanes, g.rows_per_pass, cs, rs);
+    const bool publish = rs == 0 && dscale && dbias;
+    float c1[8], c2[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float sgxh = sgx[j] * st.rstd[j];                         // sum(g * xhat)
+        if (publish) {
+            dbias[(size_t)b * dsbs + cs * 8 + j] = sg[j];
+            dscale[(size_t)b * dsbs + cs * 8 + j] = sgxh;
+        }
+        c2[j] = st.a[j] * st.rstd[j] * (sgxh / (float)g.Nvar);
+        c1[j] = st.a[j] * (sg[j] / (float)g.N) - st.mean[j] * c2[j];
+    }
+#pragma unroll
+    for (int u = 0; u < kSmallRows; ++u) {
+        const int rr = rs + u * g.rows_per_pass;
+        if (rr < g.N) {
+            float xf[8], gf[8];
+            unpack8(xr[u], xf);
+            unpack8(gr[u], gf);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float gg = fmaf(xf[j], st.a[j], st.c[j]) > 0.f ? gf[j] : gf[j] * slope;
+                xf[j] = fmaf(gg, st.a[j], -fmaf(xf[j], c2[j], c1[j]));
+            }
+            st_stream_16(dx + base + (size_t)rr * g.C, pack8(xf));
+        }
+    }
+}
+
 // ---- ring path (the two backward passes of the chunked kernels) ------------------------------------------
 // The register-staged loops above alternate between a load phase and a compute phase: ncu shows both backward kernels
 // waiting on long-scoreboard stalls at ~30 % of the issue slots and ~2.3 TB/s (profiles/r02x_ncu_full_summary.txt).
@@ -986,6 +1136,13 @@ static int cl_cluster_launch(const char *what, K kernel, int cs, int batch, int 
     return check_launch(what);
 }
 
+// register-resident one-CTA-per-sample kernels: only where a thread owns 9 .. 16 rows (D block 0: backward 16.2 -> 10.8 us);
+// with <= 8 rows the fused kernels already need one batch of loads per pass (profiles/r02Q_adain_small.txt)
+static bool cl_small_regs(const ClGeom &g)
+{
+    return option(kOptAdainClSmallRegs) != 0 && g.N <= kSmallRows * g.rows_per_pass && g.N > 8 * g.rows_per_pass;
+}
+
 extern "C" long long hg_adain_cl_workspace_bytes(int batch, int channels, int ndim, int size, int classes)
 {
     ClGeom g;
@@ -1023,6 +1180,10 @@ extern "C" int hg_adain_cl_fwd(const void *x, const float *scale, const float *b
         }
     }
     dim3 grid(g.chunks, batch);
+    if (g.chunks == 1 && cl_small_regs(g)) {
+        adain_cl_small_fwd_kernel<<<batch, kClThreads, 0, st>>>(xp, scale, bias, yp, save_mean, save_rstd, g, sb_stride, eps, neg_slope);
+        return check_launch("hg_adain_cl_fwd(small)");
+    }
     if (g.chunks == 1) {
         adain_cl_apply_kernel<true><<<grid, kClThreads, 0, st>>>(xp, nullptr, scale, bias, yp, save_mean, save_rstd, g, sb_stride,
                                                                 eps, neg_slope);
@@ -1071,6 +1232,11 @@ extern "C" int hg_adain_cl_bwd(const void *x, const void *dy, const float *scale
         }
     }
     dim3 grid(g.chunks, batch);
+    if (g.chunks == 1 && cl_small_regs(g)) {
+        adain_cl_small_bwd_kernel<<<batch, kClThreads, 0, st>>>(xp, gp, scale, bias, save_mean, save_rstd, dp, dscale, dbias, g, sb_stride,
+                                                               dsb_stride, neg_slope);
+        return check_launch("hg_adain_cl_bwd(small)");
+    }
     if (g.chunks == 1) {
         adain_cl_bwd_apply_kernel<true><<<grid, kClThreads, 0, st>>>(xp, gp, nullptr, scale, bias, save_mean, save_rstd, dp, dscale,
                                                                     dbias, g, sb_stride, dsb_stride, neg_slope);

@@ -31,6 +31,7 @@ static const OptionDef kOptionDefs[kOptCount] = {
     {"FINAL_CONV_MMA", 7},      {"ROTATE_SLAB32", 1},        {"ROTATE_GATHER_BWD", 1},
     {"ADAIN_GEMM_STATS", 0},    {"TAPGEMM_PERSISTENT", -1},  {"TAPGEMM_MSUB", 0},
     {"TAPGEMM_SHARE_A", 2},     {"ADAIN_CL_RING", 1},
+    {"ADAIN_CL_SMALL_REGS", 1},
 };
 static std::atomic<int> g_options[kOptCount];
 static std::once_flag g_options_once;

@@ -46,6 +46,7 @@ enum Option {
     kOptTapGemmMsub,            // 1: wide tap GEMMs (256-column tiles) process two 128-row sub-tiles per CTA that share every B tile
     kOptTapGemmShareA,          // > 0: forward of the narrow layers loads every shifted A box once for all parity classes of a CTA (value = weight boxes per item)
     kOptAdainClRing,            // 1: chunked channels-last AdaIN backward streams through per-thread cp.async rings
+    kOptAdainClSmallRegs,       // 1: one-CTA-per-sample channels-last norm kernels keep their rows in registers (one load pass)
     kOptCount
 };
 int option(Option o);
