@@ -210,6 +210,26 @@ def test_instance_norm_lrelu_channels_last(b, c, s):
     assert rel_err(x_cl.grad.permute(0, 3, 1, 2).float(), xr.grad) < 2e-2
 
 
+@pytest.mark.parametrize("b,c,s,s2d", [(64, 128, 16, True), (5, 128, 16, False), (64, 64, 16, False)])
+def test_small_instance_register_kernels_are_bitwise(b, c, s, s2d, hg_option):
+    """Option ADAIN_CL_SMALL_REGS: one-CTA-per-sample norm kernels with 9-16 rows per thread keep their rows in registers
+    (one load pass) -- same arithmetic in the same order as the two-pass fused kernels: bit-identical outputs / gradients."""
+    gen = torch.Generator().manual_seed(b + c)
+    x = (torch.randn(b, s, s, c, generator=gen) * 1.5 + 0.3).to(BF).to(DEV)
+    dshape = (b, s // 2, s // 2, 4, c) if s2d else (b, s, s, c)
+    dy = torch.randn(*dshape, generator=gen).to(BF).to(DEV)
+
+    def run(flag):
+        hg_option("ADAIN_CL_SMALL_REGS", flag)
+        xg = x.clone().requires_grad_(True)
+        y = ops.instance_norm_act_channels_last(xg, 0.2, 1e-5, s2d_out=s2d)
+        y.backward(dy)
+        return y.detach(), xg.grad
+
+    for u, v in zip(run(1), run(0)):
+        assert torch.equal(u, v)
+
+
 STATS_CASES = [  # (ndim, kernel, batch, cin, cout, size): the generator's four AdaIN sites
     (3, 3, 4, 512, 128, 4), (3, 3, 3, 128, 64, 8), (2, 4, 4, 1024, 256, 16), (2, 4, 5, 256, 64, 32),
     (3, 3, 64, 512, 128, 4), (2, 4, 64, 256, 64, 32),           # bench batch: dual / single launch shapes, class groups
