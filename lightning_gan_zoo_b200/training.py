@@ -570,7 +570,12 @@ class HologanTrainer:
         fresh = [len(o.state) == 0 or (isinstance(o, FlatAdam) and float(o.kstate[0]) == 0) for o in opts]   # torch creates Adam state lazily
         opt_saved = [None if f else {id(p): {k: v.clone() for k, v in stt.items() if isinstance(v, torch.Tensor)}
                                      for p, stt in o.state.items()} for o, f in zip(opts, fresh)]
-        side = torch.cuda.Stream(device=self.device)
+        # The capture stream -- the step's critical chain -- gets a HIGHER priority than the side streams (wgrad, sn, dreal,
+        # comm: default priority): the CTAs of a critical-chain kernel are scheduled first, the side work fills the SMs that
+        # its tail waves and launch gaps leave idle.  Stream priorities are recorded in the captured kernel nodes.
+        # HG_CAPTURE_PRIORITY=0 keeps the default priority (A/B).
+        prio = -1 if os.environ.get("HG_CAPTURE_PRIORITY", "1") not in ("", "0") else 0
+        side = torch.cuda.Stream(device=self.device, priority=prio)
         side.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(side):
             for idx in (0, 1, 1):
@@ -585,7 +590,7 @@ class HologanTrainer:
                 # watchdog thread's event queries must not invalidate the capture: thread-local error mode
                 torch.cuda.synchronize(self.device)
                 dist.barrier()
-            with torch.cuda.graph(g, capture_error_mode="thread_local" if self.world > 1 else "global"):
+            with torch.cuda.graph(g, stream=side, capture_error_mode="thread_local" if self.world > 1 else "global"):
                 loss = self._eager_step(st["real"], st["z"], st["a"], idx)
             graphs[idx] = (g, loss, _lib.launch_count - n0)
         with torch.no_grad():
