@@ -148,7 +148,8 @@ __device__ __forceinline__ uint8_t *align_1024(uint8_t *p)
 }
 
 // -------------------------------------------------------------------------------------------------
-// K-major kernel: forward and dgrad (and plain GEMMs).  grid = (m_tiles, n_tiles, groups)
+// K-major kernel: forward and dgrad (and plain GEMMs).  1-D grid over the (group, n tile, m tile) list: one tile per CTA,
+// or one persistent CTA per SM walking the list (TapGemmParams: tile scheduler)
 // -------------------------------------------------------------------------------------------------
 template <int MSUB, bool ITEMS>
 __global__ void __launch_bounds__(kThreads, 1) tap_gemm_kernel(const __grid_constant__ TapGemmParams p)
